@@ -1,0 +1,47 @@
+# Build of the B200-native RNA-SeQC hot path.
+#   make            -> product: CUDA library + host helper library + CLI     (needs nvcc; cross-compiles sm_100a)
+#   make oracle     -> test infrastructure: CPU oracle library + oracle-backed CLI harness
+#   make ref        -> test infrastructure: the unmodified reference binary into oracle/_ref/ (needs /root/reference)
+NVCC     ?= /usr/local/cuda/bin/nvcc
+CXX      ?= g++
+CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Iinclude -Irnaseqc_b200/csrc/host
+NVFLAGS  := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Iinclude
+LIBDIR   := rnaseqc_b200/lib
+BINDIR   := rnaseqc_b200/bin
+OBJDIR   := build
+ODIR     := oracle/_build
+
+HOST_SRCS := annotation.cpp alnreader.cpp report.cpp pipeline.cpp
+HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
+
+all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
+oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle
+ref:
+	$(MAKE) -f oracle/Makefile.ref
+
+$(OBJDIR)/host/%.o: rnaseqc_b200/csrc/host/%.cpp $(wildcard rnaseqc_b200/csrc/host/*.h) include/rsq_b200.h
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIBDIR)/librsq_b200.so: rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_capi.cu $(wildcard rnaseqc_b200/csrc/*.cuh) include/rsq_b200.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_capi.cu -lcudart 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
+
+$(LIBDIR)/librsq_host.so: $(HOST_OBJS) $(OBJDIR)/host/host_capi.o
+	@mkdir -p $(LIBDIR)
+	$(CXX) -shared -o $@ $^ -lz -ldl
+
+$(BINDIR)/rnaseqc: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(LIBDIR)/librsq_b200.so
+	@mkdir -p $(BINDIR)
+	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(LIBDIR) -lrsq_b200 -lz -Wl,-rpath,'$$ORIGIN/../lib'
+
+$(ODIR)/librsq_oracle.so: oracle/rsq_oracle.cpp include/rsq_b200.h
+	@mkdir -p $(ODIR)
+	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Iinclude -shared -o $@ $<
+
+$(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
+	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -Wl,-rpath,'$$ORIGIN'
+
+clean:
+	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) $(ODIR)
+.PHONY: all oracle ref clean

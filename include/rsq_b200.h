@@ -1,0 +1,249 @@
+/*
+ * rsq_b200.h — C-ABI of the B200-native RNA-SeQC per-read hot path.
+ *
+ * The reference (getzlab/rnaseqc 2.4.3) exposes NO plugin/FFI interface for this path: it is inline in
+ * main() (src/RNASeQC.cpp:242-382) plus free functions that mutate globals (src/Expression.h:19-37,
+ * src/Metrics.h:208-209).  The boundary is therefore cut at the natural seam — after BAM decode / GTF+BED
+ * parsing and before report generation.  Every entry point below names the reference
+ * interface it replaces.  Plain pointers and sizes only; no C++/torch types cross this boundary; no
+ * exceptions cross it (int status, rsq_last_error() for text).
+ *
+ * Two shared libraries export this identical ABI:
+ *   rnaseqc_b200/lib/librsq_b200.so   — the product: hand-written sm_100a CUDA kernels (no CPU fallback;
+ *                                       rsq_create fails with RSQ_ERR_NO_DEVICE when no GPU is present)
+ *   oracle/_build/librsq_oracle.so    — TEST INFRASTRUCTURE: CPU restatement of the reference algorithm
+ */
+#ifndef RSQ_B200_H
+#define RSQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSQ_ABI_VERSION 1u
+
+/* ---- status codes -------------------------------------------------------------------------------------- */
+enum {
+    RSQ_OK = 0,
+    RSQ_ERR_INVALID = 1,    /* bad argument / struct size / sequence of calls          */
+    RSQ_ERR_NO_DEVICE = 2,  /* CUDA device missing (the product never falls back to CPU) */
+    RSQ_ERR_CUDA = 3,       /* CUDA runtime error (text in rsq_last_error)              */
+    RSQ_ERR_NOMEM = 4,
+    RSQ_ERR_CAPACITY = 5    /* name-hash set or pair table full (raise max_records)      */
+};
+
+/* ---- SAM flag bits used on the path (SeqLib/SeqLib/BamRecord.h:245-302) --------------------------------- */
+enum {
+    RSQ_F_PAIRED = 0x1, RSQ_F_PROPER = 0x2, RSQ_F_UNMAP = 0x4, RSQ_F_MUNMAP = 0x8, RSQ_F_REVERSE = 0x10,
+    RSQ_F_MREVERSE = 0x20, RSQ_F_READ1 = 0x40, RSQ_F_READ2 = 0x80, RSQ_F_SECONDARY = 0x100,
+    RSQ_F_QCFAIL = 0x200, RSQ_F_DUP = 0x400, RSQ_F_SUPPLEMENTARY = 0x800
+};
+
+/* ---- rsq_read.aux bits (sufficient statistics the decoder extracts) -------------- */
+enum {
+    RSQ_AUX_HAS_NM = 0x01,          /* int-typed NM aux present: GetIntTag, SeqLib/SeqLib/BamRecord.h:740-750  */
+    RSQ_AUX_CHIMERIC_TAG = 0x02,    /* readStringTag(chimeric_tag): src/RNASeQC.cpp:780-800                     */
+    RSQ_AUX_MATE_OTHER_CONTIG = 0x04, /* ChrID() != MateChrID(): src/RNASeQC.cpp:287                           */
+    RSQ_AUX_TID_OUT_OF_RANGE = 0x08,  /* ChrID()<0 || >= nChrs: src/RNASeQC.cpp:333                              */
+    RSQ_AUX_CONTIG_DROPPED = 0x10   /* features[chr] already cleared by dropFeatures (src/RNASeQC.cpp:346-349,
+                                       src/Expression.cpp:96-103): a BAM that RETURNS to a contig finds nothing */
+};
+
+/* One decoded alignment record: 48 bytes, 16-byte aligned.  Replaces the SeqLib::BamRecord accessors the
+ * loop touches (src/RNASeQC.cpp:254-376, src/Expression.cpp:26-67,119-125,308-479,482-540). */
+typedef struct rsq_read {
+    int32_t  pos;         /* core.pos, 0-based                                                     */
+    int32_t  mpos;        /* core.mpos                                                             */
+    int32_t  endpos;      /* BamRecord::PositionEnd(), SeqLib/src/BamRecord.cpp:51-53               */
+    int32_t  isize;       /* core.isize                                                            */
+    int32_t  l_qseq;      /* BamRecord::Length()                                                   */
+    int32_t  nm;          /* value of NM when RSQ_AUX_HAS_NM, else 0                                */
+    uint16_t flag;        /* core.flag                                                             */
+    uint8_t  mapq;        /* core.qual                                                             */
+    uint8_t  aux;         /* RSQ_AUX_* bits                                                        */
+    int16_t  contig;      /* annotation contig index of the read's reference name, -1 if the name
+                             carries no GTF feature (chromosomeMap, src/Fasta.cpp:17-25)            */
+    uint8_t  filter_mask; /* bit k set: --tag k present (GetTag, SeqLib/src/BamRecord.cpp:474-497)  */
+    uint8_t  reserved0;
+    uint64_t name_hash;   /* 64-bit hash of Qname(): identity for fragmentTracker (src/Metrics.cpp:22)
+                             and the fragment-size mate map (src/Expression.cpp:511-531)            */
+    uint32_t block_off;   /* index of this read's first aligned block in the blocks array of the SAME
+                             submit call                                                           */
+    uint16_t n_blocks;    /* number of M/=/X blocks (extractBlocks, src/Expression.cpp:26-67)       */
+    uint16_t reserved1;
+} rsq_read;
+
+/* One aligned block (extractBlocks, src/Expression.cpp:39-48): 1-based start and M/=/X length; the
+ * reference's quirky closed end is start+len (src/Expression.cpp:45). */
+typedef struct rsq_block {
+    int32_t start;
+    int32_t len;
+} rsq_block;
+
+/* ---- run constants: the locals of main() the loop captures (src/RNASeQC.cpp:78-100) --------------------- */
+typedef struct rsq_config {
+    uint32_t struct_size;             /* = sizeof(rsq_config)                                       */
+    int32_t  device;                  /* CUDA device ordinal                                        */
+    uint32_t mapq_threshold;          /* MAPPING_QUALITY_THRESHOLD, default 255 (:90)               */
+    uint32_t base_mismatch_threshold; /* BASE_MISMATCH_THRESHOLD, default 6 (:89)                   */
+    int32_t  chimeric_distance;       /* CHIMERIC_DISTANCE, default 2000000 (:87)                   */
+    uint32_t strand_mode;             /* 0 = unstranded, 1 = FR (Strand::Forward), 2 = RF (:78-85)  */
+    uint32_t unpaired;                /* -u (:61)                                                   */
+    uint32_t exclude_chimeric;        /* --exclude-chimeric (:60)                                   */
+    uint32_t n_filter_tags;           /* number of --tag filters, <= 8 (:58)                        */
+    uint32_t fragment_samples;        /* FRAGMENT_SIZE_SAMPLES when --bed given, else 0 (:88,176)   */
+    uint64_t max_records;             /* upper bound on records this ctx will see (sizes the
+                                         fragment-tracker hash set); 0 = 1<<24                     */
+    uint32_t collect_coverage;        /* 1: accumulate per-base exon coverage (always on in the
+                                         reference; 0 only for ablation benchmarks)               */
+    uint32_t reserved[7];
+} rsq_config;
+
+/* ---- exon flags / gene-segment flags ------------------------------------------------------------------- */
+enum { RSQ_STRAND_FWD = 0, RSQ_STRAND_REV = 1, RSQ_STRAND_UNKNOWN = 2 }; /* src/Fasta.h:40 */
+enum { RSQ_EXON_STRAND_MASK = 0x3, RSQ_EXON_RIBOSOMAL = 0x4 };
+enum { /* OR over the Gene features covering one elementary segment, per gene strand */
+    RSQ_SEG_GENE_FWD = 0x01, RSQ_SEG_GENE_REV = 0x02, RSQ_SEG_GENE_UNK = 0x04,
+    RSQ_SEG_RIBO_FWD = 0x08, RSQ_SEG_RIBO_REV = 0x10, RSQ_SEG_RIBO_UNK = 0x20
+};
+enum { RSQ_GENE_GLOBIN = 0x1 }; /* geneNames[id] in blacklistedGlobins, src/Expression.cpp:24,396-399 */
+
+/* Flattened annotation: replaces map<chrom, list<Feature>> features (src/RNASeQC.cpp:104,150-156) and the
+ * string-keyed globals of src/GTF.cpp:22-27.  All arrays are caller-owned and copied by the call. */
+typedef struct rsq_annotation {
+    uint32_t struct_size;
+    uint32_t n_contigs;
+    uint32_t n_genes;           /* gene universe: every distinct gene_id on a Gene or Exon line          */
+    uint32_t n_exons;
+    uint32_t n_segs;
+    uint32_t reserved;
+    const uint32_t* exon_off;   /* [n_contigs+1] exons of contig c are [exon_off[c], exon_off[c+1])       */
+    const int32_t*  exon_start; /* [n_exons] 1-based closed, stable-sorted by start within a contig       */
+    const int32_t*  exon_end;   /* [n_exons]                                                              */
+    const uint32_t* exon_gene;  /* [n_exons] gene index                                                   */
+    const uint32_t* exon_slot;  /* [n_exons] output slot (index into exonList, src/GTF.cpp:106)           */
+    const uint8_t*  exon_flags; /* [n_exons] RSQ_EXON_*                                                   */
+    const uint64_t* exon_cov_off; /* [n_exons] first base of this exon in the coverage array              */
+    const uint32_t* seg_off;    /* [n_contigs+1]                                                          */
+    const int32_t*  seg_start;  /* [n_segs] elementary gene segments: segment k of a contig covers
+                                   [seg_start[k], seg_start[k+1]) ; strictly increasing within a contig   */
+    const uint8_t*  seg_flags;  /* [n_segs] RSQ_SEG_*                                                     */
+    const uint8_t*  gene_flags; /* [n_genes] RSQ_GENE_*                                                   */
+    uint64_t cov_len;           /* total exon bases (sum of exonLengths, src/GTF.cpp:108)                 */
+} rsq_annotation;
+
+/* BED intervals for the fragment-size sampler (src/BED.cpp:18-43, src/RNASeQC.cpp:172-187); intervals of a
+ * contig sorted by start.  name_id: identical BED lines share an id (feature_id = whole line). */
+typedef struct rsq_bed {
+    uint32_t struct_size;
+    uint32_t n_contigs;         /* same contig index space as rsq_annotation                               */
+    uint32_t n_intervals;
+    uint32_t reserved;
+    const uint32_t* off;        /* [n_contigs+1]                                                           */
+    const int32_t*  start;      /* [n_intervals] = BED start + 1                                          */
+    const int32_t*  end;        /* [n_intervals] = BED end + 1                                            */
+    const uint32_t* name_id;    /* [n_intervals]                                                          */
+    const uint8_t*  contig_present; /* [n_contigs] bedFeatures->find(chr) != end (src/RNASeQC.cpp:372)     */
+} rsq_bed;
+
+/* ---- counters: fixed indices replacing the string-keyed Metrics map (src/Metrics.h:31-41) --------------- */
+enum {
+    RSQ_C_ALTERNATIVE_ALIGNMENTS = 0, RSQ_C_SUPPLEMENTARY_ALIGNMENTS, RSQ_C_FAILED_VENDOR_QC,
+    RSQ_C_LOW_MAPPING_QUALITY, RSQ_C_CHIMERIC_AUTO, RSQ_C_CHIMERIC_TAG, RSQ_C_UMVQ, RSQ_C_UNPAIRED_READS,
+    RSQ_C_MAPPED_READS, RSQ_C_MAPPED_DUPLICATE_READS, RSQ_C_MAPPED_UNIQUE_READS, RSQ_C_TOTAL_MAPPED_PAIRS,
+    RSQ_C_END1_MAPPED_READS, RSQ_C_END1_MISMATCHES, RSQ_C_END1_BASES, RSQ_C_DUPLICATE_PAIRS,
+    RSQ_C_UNIQUE_FRAGMENTS, RSQ_C_END2_MAPPED_READS, RSQ_C_END2_MISMATCHES, RSQ_C_END2_BASES,
+    RSQ_C_MISMATCHED_BASES, RSQ_C_TOTAL_BASES, RSQ_C_HIGH_QUALITY_READS, RSQ_C_LOW_QUALITY_READS,
+    RSQ_C_READS_USED, RSQ_C_ALIGNMENT_BLOCKS, RSQ_C_NON_GLOBIN_READS, RSQ_C_NON_GLOBIN_DUPLICATE_READS,
+    RSQ_C_INTRONIC_READS, RSQ_C_INTRAGENIC_READS, RSQ_C_HQ_INTRONIC_READS, RSQ_C_HQ_INTRAGENIC_READS,
+    RSQ_C_INTERGENIC_READS, RSQ_C_HQ_INTERGENIC_READS, RSQ_C_EXONIC_READS, RSQ_C_HQ_EXONIC_READS,
+    RSQ_C_AMBIGUOUS_READS, RSQ_C_HQ_AMBIGUOUS_READS, RSQ_C_RRNA_READS, RSQ_C_END1_SENSE,
+    RSQ_C_END1_ANTISENSE, RSQ_C_END2_SENSE, RSQ_C_END2_ANTISENSE,
+    RSQ_C_TOTAL_ALIGNMENTS,        /* alignmentCount, src/RNASeQC.cpp:245 (the int truncation of :397 is the writer's) */
+    RSQ_C_FILTERED_BY_TAG0,        /* .. +7: "Filtered by tag: X", src/RNASeQC.cpp:325 */
+    RSQ_C_SPLIT_READS = RSQ_C_FILTERED_BY_TAG0 + 8, /* legacy only; always 0 here */
+    RSQ_C_FRAGMENT_CANDIDATES,     /* diagnostics: reads that entered the fragment-size mate map */
+    RSQ_N_COUNTERS = 64
+};
+
+/* ---- results ------------------------------------------------------------------------------------------ */
+typedef struct rsq_results {
+    uint32_t struct_size;
+    uint32_t reserved;
+    uint64_t counters[RSQ_N_COUNTERS];
+    /* caller-provided arrays (NULL = skip); replace the global count tables of src/Metrics.cpp:20 */
+    uint64_t* gene_reads;      /* [n_genes]  geneCounts                                                  */
+    uint64_t* gene_unique;     /* [n_genes]  uniqueGeneCounts                                            */
+    uint64_t* gene_fragments;  /* [n_genes]  geneFragmentCounts                                          */
+    uint64_t* exon_whole;      /* [n_exons by slot] integer part of exonCounts                           */
+    uint64_t* exon_frac;       /* [n_exons by slot] fractional part in units of 2^-64 (exact Q64.64 sum
+                                  of isz/length, src/Expression.cpp:345, src/Metrics.cpp:59-66)          */
+    uint32_t* coverage;        /* [cov_len] per-base exon coverage (BaseCoverage::coverage after all
+                                  commits, src/Metrics.cpp:106-124)                                     */
+    uint64_t* fragment_hist;   /* [fragment_hist_len] fragmentSizes[|isize|] (src/Expression.cpp:530);
+                                  the last bin collects |isize| >= fragment_hist_len-1                   */
+    uint64_t  fragment_hist_len;
+    uint64_t  fragment_samples_taken;
+} rsq_results;
+
+typedef struct rsq_ctx rsq_ctx;
+
+/* Library identity: "cuda-sm_100a" for the product, "oracle-cpu" for the test oracle. */
+const char* rsq_backend(void);
+uint32_t    rsq_abi_version(void);
+
+/* Page-locked host memory for submit buffers (plain malloc in the oracle). */
+void* rsq_host_alloc(size_t bytes);
+void  rsq_host_free(void* p);
+
+/* Replaces the loop-constant locals of main() (src/RNASeQC.cpp:78-100,204-211). */
+int rsq_create(const rsq_config* cfg, rsq_ctx** out);
+void rsq_destroy(rsq_ctx* ctx);
+const char* rsq_last_error(const rsq_ctx* ctx); /* ctx may be NULL: error of the failed rsq_create */
+
+/* Replaces map<chrom,list<Feature>> features + GTF globals (src/RNASeQC.cpp:104-156, src/GTF.cpp:22-27). */
+int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* ann);
+/* Replaces bedFeatures (src/RNASeQC.cpp:169-187). */
+int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* bed);
+
+/* Replaces one or more iterations of the loop body src/RNASeQC.cpp:242-382 (and everything it calls:
+ * extractBlocks' output is the blocks array; trimFeatures/intersectBlock/exonAlignmentMetrics/
+ * fragmentSizeMetrics, src/Expression.cpp:80-117,308-540; Metrics/Collector/BaseCoverage add/commit,
+ * src/Metrics.cpp:28-129).  Records must arrive in stream (BAM) order across calls.  Host buffers
+ * (pinned or pageable); asynchronous: the buffers are owned by the caller until rsq_sync returns. */
+int rsq_submit(rsq_ctx* ctx, const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks);
+/* Same, for batches that already live in device memory of cfg.device (device pointers). */
+int rsq_submit_device(rsq_ctx* ctx, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks,
+                      size_t n_blocks);
+int rsq_sync(rsq_ctx* ctx);
+
+/* Clears all accumulators (annotation and BED stay): a new sample / a new timed step. */
+int rsq_reset(rsq_ctx* ctx);
+
+/* End of stream: resolves the fragment-size first-N cut, integrates the coverage difference array, and
+ * copies results to the caller's arrays (replaces the reads of the globals at src/RNASeQC.cpp:397-521). */
+int rsq_finalize(rsq_ctx* ctx, rsq_results* out);
+
+/* Device-resident count vector for the end-of-run all-reduce over NVLink (counters ‖ gene_reads ‖
+ * gene_unique ‖ gene_fragments ‖ exon_whole ‖ exon_frac_hi32 ‖ exon_frac_lo32), all uint64, additive across
+ * partitions.  Returns a DEVICE pointer and the number of uint64 words; valid until rsq_destroy.
+ * rsq_finalize must not have been called between rsq_export_counts and rsq_import_counts. */
+int rsq_export_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words);
+/* After the caller reduced the exported buffer in place (NCCL sum), fold it back into the ctx state. */
+int rsq_import_counts(rsq_ctx* ctx);
+
+/* Algorithmic HBM bytes of everything submitted since the last reset, by the definition of
+ * 40 + 8*nb per record, + (8 + 8*nb_a) for HQ assigned reads, + 8*nb_a coverage. */
+int rsq_algorithmic_bytes(rsq_ctx* ctx, uint64_t* bytes);
+/* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+int rsq_launch_count(rsq_ctx* ctx, uint64_t* launches);
+/* Device time of all hot-path kernels since the last reset, from CUDA events on the ctx stream (ms). */
+int rsq_kernel_time_ms(rsq_ctx* ctx, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSQ_B200_H */

@@ -1,0 +1,93 @@
+// alnreader.h — SAM/BAM decode into the device record format (rsq_read + rsq_block).
+//
+// Own implementation (BGZF via zlib + BAM record parse; SAM text parse): the reference decodes through
+// SeqLib::BamReader -> htslib sam_read1 (src/BamReader.cpp:12-27).  Only the fields the hot loop touches
+// are extracted.  CRAM is not supported.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "annotation.h"
+#include "rsq_b200.h"
+
+namespace rsqh {
+
+struct AlnHeader {
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+};
+
+struct AuxField {
+    char tag[2];
+    char type;      // BAM type letter: A c C s S i I f d Z H B
+    int64_t ival;   // value for integer types; the character for 'A'
+};
+
+struct RawAln {
+    int32_t tid = -1, pos = -1, mtid = -1, mpos = -1, isize = 0, l_qseq = 0;
+    uint16_t flag = 0;
+    uint8_t mapq = 0;
+    std::string qname;
+    std::vector<uint32_t> cigar;   // BAM encoding: len << 4 | op, op index into "MIDNSHP=XB"
+    std::vector<AuxField> aux;
+};
+
+class AlnReader {
+public:
+    virtual ~AlnReader() {}
+    virtual const AlnHeader& header() const = 0;
+    virtual bool next(RawAln& out) = 0;   // false at EOF; throws HostError(-1) on corrupt input
+    static std::unique_ptr<AlnReader> open(const std::string& path);  // throws HostError(10) if unreadable
+};
+
+// 64-bit read-name identity (FNV-1a with a splitmix64 finaliser).
+uint64_t hash_qname(const char* s, size_t n);
+
+struct DecodeOptions {
+    std::string chimeric_tag = "ch";          // --chimeric-tag (src/RNASeQC.cpp:98)
+    std::vector<std::string> filter_tags;     // --tag (src/RNASeQC.cpp:97)
+    bool exclude_chimeric = false;
+    int chimeric_distance = 2000000;
+    int verbosity = 0;
+};
+
+// Converts records and carries the order-dependent scalar state of the reference loop that cannot be a
+// commutative device reduction: readLength (src/RNASeQC.cpp:277-278), current_chrom / dropFeatures
+// (:346-353), the unsorted warning (:354-356), alignmentCount (:245) and the contig visit order that fixes
+// the row order of coverage.tsv.
+class Decoder {
+public:
+    Decoder(const AlnHeader& hdr, ContigMap& contigs, size_t n_annotation_contigs, const DecodeOptions& opt);
+    // Appends one record (and its blocks) to the batch vectors.  Throws HostError(7) on an unknown CIGAR op
+    // (src/Expression.cpp:61-63).
+    void convert(const RawAln& aln, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
+
+    int read_length() const { return read_length_; }
+    uint64_t alignment_count() const { return alignment_count_; }
+    // contigs in the order their feature lists were dropped during the stream (dropFeatures calls)
+    const std::vector<uint32_t>& dropped_order() const { return dropped_order_; }
+    bool any_overlap_with(const std::vector<uint8_t>& contig_has_features) const;
+    const std::vector<int>& tid_to_contig() const { return tid_to_contig_; }
+    // current_chrom at this point of the stream, and the position of the last read that reached trimFeatures on
+    // it (INT32_MIN when none did): fixes which genes of the final contig were evicted before the end-of-run sweep
+    int64_t current_contig() const { return current_chrom_; }
+    int32_t trim_position() const { return last_metrics_chrom_ == current_chrom_ ? last_position_ : INT32_MIN; }
+
+private:
+    DecodeOptions opt_;
+    std::vector<int> tid_to_contig_;        // BAM tid -> ContigMap id (always valid: names are added)
+    size_t n_annotation_contigs_;
+    int read_length_ = 0;
+    uint64_t alignment_count_ = 0;
+    int64_t current_chrom_ = -1;             // ContigMap id; -1 plays the role of the initial 0
+    int32_t last_position_ = 0;
+    int64_t last_metrics_chrom_ = -2;
+    std::vector<uint8_t> dropped_;           // per ContigMap id
+    std::vector<uint32_t> dropped_order_;
+    bool warned_unsorted_ = false;
+};
+
+}  // namespace rsqh

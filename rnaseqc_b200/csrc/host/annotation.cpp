@@ -1,0 +1,393 @@
+// annotation.cpp — GTF/BED -> flattened annotation (see annotation.h).
+#include "annotation.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <set>
+#include <unordered_set>
+
+namespace rsqh {
+
+namespace {
+
+// The 12 globin gene names the reference excludes (src/Expression.cpp:24).
+const char* const kGlobins[] = {"HBA1", "HBA2", "HBB",  "HBD", "HBG1",  "HBG2",
+                                "HBE1", "HBM",  "HBQ1", "HBZ", "HBBP1", "HBZP1"};
+
+// std::stoull semantics as used at src/GTF.cpp:54,57: skip leading whitespace, optional sign, digits;
+// no digits -> invalid_argument (-> gtfException, exit 11).
+bool parse_u64(const std::string& s, unsigned long long& v) {
+    const char* p = s.c_str();
+    char* endp = nullptr;
+    errno = 0;
+    v = std::strtoull(p, &endp, 10);
+    return endp != p;
+}
+
+// parseAttributes (src/GTF.cpp:146-161): split on every ';' (quotes are NOT honoured), key = text before
+// the first '"' minus its last character, left-trimmed of blanks/tabs; value = text up to the next '"'.
+// A piece with no quote at all leaves the value equal to the whole piece (std::getline does not clear its
+// target once eofbit is set).  Later duplicates overwrite earlier ones (std::map assignment).
+void parse_attributes(const std::string& text, std::map<std::string, std::string>& attrs) {
+    size_t pos = 0;
+    const size_t n = text.size();
+    while (pos < n) {  // getline(tokenizer, buffer, ';') stops yielding once the input is exhausted
+        size_t semi = text.find(';', pos);
+        std::string piece = text.substr(pos, semi == std::string::npos ? std::string::npos : semi - pos);
+        pos = (semi == std::string::npos) ? n : semi + 1;
+        std::string key, value;
+        size_t q1 = piece.find('"');
+        std::string head = piece.substr(0, q1 == std::string::npos ? std::string::npos : q1);
+        key = head.empty() ? std::string() : head.substr(0, head.size() - 1);
+        while (!key.empty() && (key[0] == ' ' || key[0] == '\t')) key = key.substr(1);
+        if (q1 == std::string::npos) {
+            value = piece.empty() ? std::string() : piece;  // stale `current` == the piece just read
+        } else {
+            size_t q2 = piece.find('"', q1 + 1);
+            value = piece.substr(q1 + 1, q2 == std::string::npos ? std::string::npos : q2 - q1 - 1);
+        }
+        attrs[key] = value;
+    }
+}
+
+bool split_tab(const std::string& line, size_t& cursor, std::string& field) {
+    // getline(tokenizer, buffer, '\t'): fails only when no characters remain at all
+    if (cursor > line.size()) return false;
+    if (cursor == line.size()) {
+        // stream exhausted: a previous read consumed the last char; getline extracts nothing -> fail
+        return false;
+    }
+    size_t tab = line.find('\t', cursor);
+    if (tab == std::string::npos) {
+        field = line.substr(cursor);
+        cursor = line.size() + 1;
+    } else {
+        field = line.substr(cursor, tab - cursor);
+        cursor = tab + 1;
+        if (cursor == line.size()) cursor = line.size();  // trailing tab: next getline yields nothing
+    }
+    return true;
+}
+
+}  // namespace
+
+uint32_t Annotation::gene_universe(const std::string& id) {
+    auto it = gene_index.find(id);
+    if (it != gene_index.end()) return it->second;
+    uint32_t g = (uint32_t)gene_ids.size();
+    gene_ids.push_back(id);
+    gene_index.emplace(id, g);
+    gene_coding_len.push_back(0);
+    exons_for_gene.emplace_back();
+    return g;
+}
+
+void load_gtf(const std::string& path, Annotation& A) {
+    std::ifstream in(path);
+    if (!in.is_open()) throw HostError(10, "Unable to open GTF file: " + path);
+
+    // State of the single re-used Feature object (src/RNASeQC.cpp:109): these three survive from line to line
+    // because operator>> only assigns them when the attribute exists (src/GTF.cpp:81,89,90,95,110).
+    std::string cur_feature_id, cur_gene_id, cur_transcript_type;
+    std::unordered_set<std::string> seen_gene_ids, seen_exon_ids;
+    std::map<std::string, unsigned> unnamed_exon_counter;            // exon_names (src/GTF.cpp:27)
+    std::unordered_map<std::string, std::string> gene_names;          // geneNames (src/GTF.cpp:22), keyed by feature_id
+    std::vector<GeneFeature> kept_genes;
+    std::vector<ExonFeature> kept_exons;
+    size_t kept_counter = 0;
+
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line[0] == '#') continue;
+        size_t cur = 0;
+        std::string f_chr, f_track, f_type, f_start, f_end, f_score, f_strand, f_frame, f_attr;
+        if (!split_tab(line, cur, f_chr)) throw HostError(11, "Failed to parse the GTF: Unable to parse chromosome. Invalid GTF line: " + line);
+        uint32_t contig = A.contigs.get(f_chr);
+        if (!split_tab(line, cur, f_track)) throw HostError(11, "Failed to parse the GTF: Unable to parse track. Invalid GTF line: " + line);
+        if (!split_tab(line, cur, f_type)) throw HostError(11, "Failed to parse the GTF: Unable to parse feature type. Invalid GTF line: " + line);
+        enum { T_GENE, T_TRANSCRIPT, T_EXON, T_OTHER } type =
+            f_type == "exon" ? T_EXON : f_type == "gene" ? T_GENE : f_type == "transcript" ? T_TRANSCRIPT : T_OTHER;
+        if (!split_tab(line, cur, f_start)) throw HostError(11, "Failed to parse the GTF: Unable to parse start. Invalid GTF line: " + line);
+        unsigned long long ustart = 0, uend = 0;
+        if (!parse_u64(f_start, ustart)) throw HostError(11, "Failed to parse the GTF: GTF is in an invalid format: stoull");
+        if (!split_tab(line, cur, f_end)) throw HostError(11, "Failed to parse the GTF: Unable to parse end. Invalid GTF line: " + line);
+        if (!parse_u64(f_end, uend)) throw HostError(11, "Failed to parse the GTF: GTF is in an invalid format: stoull");
+        if (!split_tab(line, cur, f_score)) throw HostError(11, "Failed to parse the GTF: Unable to parse score. Invalid GTF line: " + line);
+        if (!split_tab(line, cur, f_strand)) throw HostError(11, "Failed to parse the GTF: Unable to parse strand. Invalid GTF line: " + line);
+        uint8_t strand = f_strand.empty() ? RSQ_STRAND_UNKNOWN
+                         : f_strand[0] == '+' ? RSQ_STRAND_FWD
+                         : f_strand[0] == '-' ? RSQ_STRAND_REV
+                                              : RSQ_STRAND_UNKNOWN;
+        if (!split_tab(line, cur, f_frame)) throw HostError(11, "Failed to parse the GTF: Unable to parse frame. Invalid GTF line: " + line);
+        // attributes = the rest of the line, tabs included (getline with '\n')
+        if (cur >= line.size()) throw HostError(11, "Failed to parse the GTF: Unable to parse attributes. Invalid GTF line: " + line);
+        f_attr = line.substr(cur);
+        std::map<std::string, std::string> attrs;
+        parse_attributes(f_attr, attrs);
+        const int64_t start = (int64_t)ustart, end = (int64_t)uend;
+        if (end < start) std::cerr << "Bad feature range:" << start << " - " << end << std::endl;
+
+        auto has = [&](const char* k) { return attrs.find(k) != attrs.end(); };
+        if (type == T_GENE && has("gene_id")) {
+            cur_feature_id = attrs["gene_id"];
+            if (seen_gene_ids.count(cur_feature_id))
+                throw HostError(11, "Failed to parse the GTF: Detected non-unique Gene ID: " + cur_feature_id);
+            seen_gene_ids.insert(cur_feature_id);
+            A.gene_list.push_back(A.gene_universe(cur_feature_id));
+        }
+        if (type == T_TRANSCRIPT && has("transcript_id")) cur_feature_id = attrs["transcript_id"];
+        if (has("gene_id")) cur_gene_id = attrs["gene_id"];
+        uint32_t exon_slot = 0;
+        if (type == T_EXON) {
+            if (has("exon_id")) {
+                cur_feature_id = attrs["exon_id"];
+            } else if (has("gene_id")) {
+                const std::string& gid = attrs["gene_id"];
+                cur_feature_id = gid + "_" + std::to_string(++unnamed_exon_counter[gid]);
+                std::cerr << "Unnamed exon: Gene: " << gid << " Position: [" << start << ", " << end
+                          << "] Inferred Exon Name: " << cur_feature_id << std::endl;
+            } else {
+                throw HostError(11, "Failed to parse the GTF: Exon missing exon_id and gene_id fields: " + line);
+            }
+            if (seen_exon_ids.count(cur_feature_id))
+                throw HostError(11, "Failed to parse the GTF: Detected non-unique Exon ID: " + cur_feature_id);
+            seen_exon_ids.insert(cur_feature_id);
+            exon_slot = (uint32_t)A.exon_ids.size();
+            A.exon_ids.push_back(cur_feature_id);
+            A.exon_len.push_back(1 + (end - start));
+            uint32_t g = A.gene_universe(cur_gene_id);
+            A.gene_coding_len[g] += 1 + (end - start);
+        }
+        if (has("transcript_type")) cur_transcript_type = attrs["transcript_type"];
+        if (has("gene_name")) gene_names[cur_feature_id] = attrs["gene_name"];
+        else if (has("gene_id")) gene_names[cur_feature_id] = attrs["gene_id"];
+        const bool ribosomal = cur_transcript_type.find("rRNA") != std::string::npos;  // regex "rRNA", src/GTF.cpp:21,113
+
+        // main(): keep genes and exons only (src/RNASeQC.cpp:137-139)
+        if (type == T_GENE) {
+            GeneFeature gf{contig, start, end, strand, ribosomal, A.gene_universe(cur_feature_id), (uint32_t)kept_counter++};
+            kept_genes.push_back(gf);
+        } else if (type == T_EXON) {
+            ExonFeature ef{contig, start, end, strand, ribosomal, A.gene_universe(cur_gene_id), exon_slot, (uint32_t)kept_counter++};
+            kept_exons.push_back(ef);
+        }
+    }
+
+    if (A.gene_list.empty() || A.exon_ids.empty()) {
+        std::cerr << "There were either no genes or no exons in the GTF" << std::endl;
+        std::cerr << A.gene_list.size() << " genes parsed" << std::endl;
+        std::cerr << A.exon_ids.size() << " exons parsed" << std::endl;
+        throw HostError(11, "There were either no genes or no exons in the GTF");
+    }
+
+    // geneNames lookups happen after parsing completes, so the final map state is what counts.
+    A.gene_desc.assign(A.gene_ids.size(), std::string());
+    A.gene_flags.assign(A.gene_ids.size(), 0);
+    for (size_t g = 0; g < A.gene_ids.size(); ++g) {
+        auto it = gene_names.find(A.gene_ids[g]);
+        if (it != gene_names.end()) A.gene_desc[g] = it->second;
+        for (const char* glob : kGlobins)
+            if (A.gene_desc[g] == glob) A.gene_flags[g] |= RSQ_GENE_GLOBIN;
+    }
+    A.exon_desc.assign(A.exon_ids.size(), std::string());
+    for (size_t e = 0; e < A.exon_ids.size(); ++e) {
+        auto it = gene_names.find(A.exon_ids[e]);
+        if (it != gene_names.end()) A.exon_desc[e] = it->second;
+    }
+
+    // Per contig, list.sort(compIntervalStart) — a stable sort by start over genes and exons interleaved
+    // (src/RNASeQC.cpp:150-152).  Genes and exons are separated here; relative order inside each kind is
+    // what the stable sort would give, which is all that exonsForGene and the eviction order depend on.
+    const size_t nc = A.contigs.names.size();
+    A.genes_by_contig.assign(nc, {});
+    A.exons_by_contig.assign(nc, {});
+    for (auto& g : kept_genes) A.genes_by_contig[g.contig].push_back(g);
+    for (auto& e : kept_exons) A.exons_by_contig[e.contig].push_back(e);
+    for (size_t c = 0; c < nc; ++c) {
+        std::stable_sort(A.genes_by_contig[c].begin(), A.genes_by_contig[c].end(),
+                         [](const GeneFeature& a, const GeneFeature& b) { return a.start < b.start; });
+        std::stable_sort(A.exons_by_contig[c].begin(), A.exons_by_contig[c].end(),
+                         [](const ExonFeature& a, const ExonFeature& b) { return a.start < b.start; });
+        // exonsForGene, filled in chromosome-id order then list order (src/RNASeQC.cpp:150-155)
+        for (auto& e : A.exons_by_contig[c]) A.exons_for_gene[e.gene].push_back(e.slot);
+    }
+
+    // Coverage layout: one contiguous run per gene in stitched (exonsForGene) order, so a gene's transcript
+    // coverage (src/Metrics.cpp:307-308) is a single contiguous slice of the device array.
+    A.exon_cov_off.assign(A.exon_ids.size(), 0);
+    uint64_t off = 0;
+    for (size_t g = 0; g < A.gene_ids.size(); ++g)
+        for (uint32_t slot : A.exons_for_gene[g]) {
+            A.exon_cov_off[slot] = off;
+            off += (uint64_t)std::max<int64_t>(A.exon_len[slot], 0);
+        }
+    A.cov_len = off;
+
+    // ---- flatten ------------------------------------------------------------------------------------------
+    A.f_exon_off.assign(nc + 1, 0);
+    A.f_seg_off.assign(nc + 1, 0);
+    for (size_t c = 0; c < nc; ++c) {
+        A.f_exon_off[c] = (uint32_t)A.f_exon_start.size();
+        for (auto& e : A.exons_by_contig[c]) {
+            if (e.start > INT32_MAX - 2 || e.end > INT32_MAX - 2)
+                throw HostError(11, "Failed to parse the GTF: coordinate beyond 2^31");
+            A.f_exon_start.push_back((int32_t)e.start);
+            A.f_exon_end.push_back((int32_t)e.end);
+            A.f_exon_gene.push_back(e.gene);
+            A.f_exon_slot.push_back(e.slot);
+            A.f_exon_flags.push_back((uint8_t)(e.strand | (e.ribosomal ? RSQ_EXON_RIBOSOMAL : 0)));
+            A.f_exon_cov_off.push_back(A.exon_cov_off[e.slot]);
+        }
+        // Elementary gene segments: sweep over [start, end+1) of every Gene feature with one counter per
+        // (strand, ribosomal) class; a segment's flags say which classes cover it.
+        A.f_seg_off[c] = (uint32_t)A.f_seg_start.size();
+        struct Ev { int64_t pos; int cls; int delta; };
+        std::vector<Ev> evs;
+        for (auto& g : A.genes_by_contig[c]) {
+            if (g.end < g.start) continue;
+            if (g.end > INT32_MAX - 2) throw HostError(11, "Failed to parse the GTF: coordinate beyond 2^31");
+            evs.push_back({g.start, g.strand, +1});
+            evs.push_back({g.end + 1, g.strand, -1});
+            if (g.ribosomal) {
+                evs.push_back({g.start, 3 + g.strand, +1});
+                evs.push_back({g.end + 1, 3 + g.strand, -1});
+            }
+        }
+        std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.pos < b.pos; });
+        int counts[6] = {0, 0, 0, 0, 0, 0};
+        A.f_seg_start.push_back(INT32_MIN);  // sentinel segment: nothing before the first gene
+        A.f_seg_flags.push_back(0);
+        size_t i = 0;
+        while (i < evs.size()) {
+            int64_t p = evs[i].pos;
+            while (i < evs.size() && evs[i].pos == p) { counts[evs[i].cls] += evs[i].delta; ++i; }
+            uint8_t fl = 0;
+            for (int k = 0; k < 6; ++k) if (counts[k] > 0) fl |= (uint8_t)(1u << k);
+            if (fl == A.f_seg_flags.back()) continue;  // merge equal neighbours
+            A.f_seg_start.push_back((int32_t)p);
+            A.f_seg_flags.push_back(fl);
+        }
+    }
+    A.f_exon_off[nc] = (uint32_t)A.f_exon_start.size();
+    A.f_seg_off[nc] = (uint32_t)A.f_seg_start.size();
+}
+
+void Annotation::pad_contigs(size_t n_contigs) {
+    while (genes_by_contig.size() < n_contigs) {
+        genes_by_contig.emplace_back();
+        exons_by_contig.emplace_back();
+        f_exon_off.push_back(f_exon_off.back());
+        f_seg_start.push_back(INT32_MIN);
+        f_seg_flags.push_back(0);
+        f_seg_off.push_back((uint32_t)f_seg_start.size());
+    }
+}
+
+rsq_annotation Annotation::view() const {
+    rsq_annotation v{};
+    v.struct_size = sizeof(rsq_annotation);
+    v.n_contigs = (uint32_t)genes_by_contig.size();
+    v.n_genes = (uint32_t)gene_ids.size();
+    v.n_exons = (uint32_t)f_exon_start.size();
+    v.n_segs = (uint32_t)f_seg_start.size();
+    v.exon_off = f_exon_off.data();
+    v.exon_start = f_exon_start.data();
+    v.exon_end = f_exon_end.data();
+    v.exon_gene = f_exon_gene.data();
+    v.exon_slot = f_exon_slot.data();
+    v.exon_flags = f_exon_flags.data();
+    v.exon_cov_off = f_exon_cov_off.data();
+    v.seg_off = f_seg_off.data();
+    v.seg_start = f_seg_start.data();
+    v.seg_flags = f_seg_flags.data();
+    v.gene_flags = gene_flags.data();
+    v.cov_len = cov_len;
+    return v;
+}
+
+void load_bed(const std::string& path, ContigMap& contigs, BedModel& bed) {
+    std::ifstream in(path);
+    if (!in.is_open()) throw HostError(10, "Unable to open BED file: " + path);
+    std::unordered_map<std::string, uint32_t> name_index;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line[0] == '#') continue;
+        // `tokenizer >> buffer` x3: whitespace-separated chromosome, start, end (src/BED.cpp:27-33)
+        size_t p = 0;
+        auto next_tok = [&](std::string& tok) {
+            while (p < line.size() && isspace((unsigned char)line[p])) ++p;
+            if (p >= line.size()) return false;
+            size_t q = p;
+            while (q < line.size() && !isspace((unsigned char)line[q])) ++q;
+            tok = line.substr(p, q - p);
+            p = q;
+            return true;
+        };
+        std::string t_chr, t_start, t_end;
+        if (!next_tok(t_chr)) continue;  // blank line (the reference would re-use stale tokens; not reproduced)
+        unsigned long long s = 0, e = 0;
+        if (!next_tok(t_start) || !parse_u64(t_start, s) || !next_tok(t_end) || !parse_u64(t_end, e))
+            throw HostError(11, "Failed to parse the BED: Encountered an unknown error while parsing the BED: stoull");
+        uint32_t c = contigs.get(t_chr);
+        if (bed.starts.size() <= c) {
+            bed.starts.resize(c + 1);
+            bed.ends.resize(c + 1);
+            bed.name_ids.resize(c + 1);
+            bed.present.resize(c + 1, 0);
+        }
+        auto it = name_index.find(line);
+        uint32_t nid;
+        if (it == name_index.end()) {
+            nid = (uint32_t)bed.names.size();
+            bed.names.push_back(line);
+            name_index.emplace(line, nid);
+        } else nid = it->second;
+        if (!bed.starts[c].empty() && (int64_t)(s + 1) < bed.starts[c].back()) bed.was_sorted = false;
+        bed.starts[c].push_back((int64_t)s + 1);
+        bed.ends[c].push_back((int64_t)e + 1);
+        bed.name_ids[c].push_back(nid);
+        bed.present[c] = 1;
+    }
+}
+
+void flatten_bed(BedModel& bed, size_t n_contigs) {
+    bed.starts.resize(n_contigs);
+    bed.ends.resize(n_contigs);
+    bed.name_ids.resize(n_contigs);
+    bed.present.resize(n_contigs, 0);
+    bed.f_off.assign(n_contigs + 1, 0);
+    bed.f_start.clear(); bed.f_end.clear(); bed.f_name.clear();
+    if (!bed.was_sorted)
+        std::cerr << "Warning: BED intervals are not sorted by start; they are sorted here (the reference walks "
+                     "them in file order, src/Expression.cpp:69-78,111)" << std::endl;
+    for (size_t c = 0; c < n_contigs; ++c) {
+        bed.f_off[c] = (uint32_t)bed.f_start.size();
+        std::vector<size_t> order(bed.starts[c].size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return bed.starts[c][a] < bed.starts[c][b]; });
+        for (size_t i : order) {
+            bed.f_start.push_back((int32_t)bed.starts[c][i]);
+            bed.f_end.push_back((int32_t)bed.ends[c][i]);
+            bed.f_name.push_back(bed.name_ids[c][i]);
+        }
+    }
+    bed.f_off[n_contigs] = (uint32_t)bed.f_start.size();
+}
+
+rsq_bed BedModel::view() const {
+    rsq_bed v{};
+    v.struct_size = sizeof(rsq_bed);
+    v.n_contigs = (uint32_t)(f_off.size() - 1);
+    v.n_intervals = (uint32_t)f_start.size();
+    v.off = f_off.data();
+    v.start = f_start.data();
+    v.end = f_end.data();
+    v.name_id = f_name.data();
+    v.contig_present = present.data();
+    return v;
+}
+
+}  // namespace rsqh

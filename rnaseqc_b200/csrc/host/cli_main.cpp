@@ -1,0 +1,17 @@
+// cli_main.cpp — `rnaseqc gtf bam outdir {OPTIONS}`: drop-in CLI over the C-ABI (src/RNASeQC.cpp:36).
+// Linked against rnaseqc_b200/lib/librsq_b200.so this is the product binary (CUDA hot path, no CPU
+// fallback).  The SAME source linked against oracle/_build/librsq_oracle.so gives the test harness
+// oracle/_build/rnaseqc_oracle used to validate host parsing/reporting without a GPU.
+#include <iostream>
+
+#include "pipeline.h"
+
+int main(int argc, char** argv) {
+    rsqh::CliOptions opt;
+    int rc = rsqh::parse_cli(argc, argv, opt);
+    if (rc >= 0) return rc;
+    rsqh::Backend be{rsq_backend, rsq_create,  rsq_destroy,  rsq_last_error, rsq_set_annotation, rsq_set_bed,
+                     rsq_submit,  rsq_sync,    rsq_finalize, rsq_host_alloc, rsq_host_free};
+    if (opt.verbosity) std::cout << "hot-path backend: " << be.backend() << std::endl;
+    return rsqh::run_sample(be, opt);
+}

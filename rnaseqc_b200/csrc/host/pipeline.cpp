@@ -1,0 +1,300 @@
+// pipeline.cpp — host driver (see pipeline.h).
+#include "pipeline.h"
+
+#include <chrono>
+#include <cstring>
+#include <filesystem>
+#include <iostream>
+
+namespace rsqh {
+
+namespace {
+
+const char* kVersion = "RNASeQC 2.4.3";  // the CLI this build is a drop-in for (src/RNASeQC.cpp:25)
+
+void usage(std::ostream& o) {
+    o << "  rnaseqc gtf bam output {OPTIONS}\n\n"
+         "    " << kVersion << " — B200-native hot path (rnaseqc-b200)\n\n"
+         "  OPTIONS:\n"
+         "      -h, --help                        Display this message and quit\n"
+         "      --version                         Display the version and quit\n"
+         "      gtf                               The input GTF file containing features to check the bam against\n"
+         "      bam                               The input SAM/BAM file containing reads to process\n"
+         "      output                            Output directory\n"
+         "      -s[sample], --sample=[sample]     The name of the current sample. Default: The bam's filename\n"
+         "      --bed=[BEDFILE]                   BED file with non-overlapping exons used for fragment size calculations\n"
+         "      --fasta=[fasta]                   (not supported by this build)\n"
+         "      --chimeric-distance=[DISTANCE]    Maximum accepted distance between read mates. Default: 2000000 [bp]\n"
+         "      --fragment-samples=[SAMPLES]      Number of fragment size samples. Requires --bed. Default: 1000000\n"
+         "      -q[QUALITY], --mapping-quality=[QUALITY]  Lower bound on read quality for exon coverage counting. Default: 255\n"
+         "      --base-mismatch=[MISMATCHES]      Maximum number of allowed mismatches. Default: 6\n"
+         "      --offset=[OFFSET]                 Offset into the gene for the 3' and 5' windows in bias calculation\n"
+         "      --window-size=[SIZE]              Size of the 3' and 5' windows in bias calculation. Default: 100 [bp]\n"
+         "      --gene-length=[LENGTH]            Minimum size of a gene for bias calculation\n"
+         "      --legacy                          (not supported by this build)\n"
+         "      --stranded=[stranded]             Strand-specific metrics: 'RF', 'rf', 'FR', or 'fr'\n"
+         "      -v, --verbose                     Give some feedback; twice for progress updates\n"
+         "      -t[TAG...], --tag=[TAG...]        Filter out reads with the specified tag\n"
+         "      --chimeric-tag=[TAG]              Reads marked with the specified tag are labeled Chimeric. Default 'ch'\n"
+         "      --exclude-chimeric                Exclude chimeric reads from the read counts\n"
+         "      -u, --unpaired                    Allow unpaired reads to be quantified\n"
+         "      --rpkm                            Output gene RPKM values instead of TPMs\n"
+         "      --coverage                        Write per-transcript coverage statistics to a table\n"
+         "      --coverage-mask=[SIZE]            Bases masked at both transcript ends for coverage. Default: 500bp\n"
+         "      -d[threshold], --detection-threshold=[threshold]  Counts on a gene to consider it detected. Default: 5\n"
+         "      --batch-records=[N]               Records per device batch (this build). Default: 1048576\n"
+         "      --exact-complexity                Literal 1e9-iteration library-complexity scan (this build)\n";
+}
+
+struct ArgError { int code; std::string msg; };
+
+}  // namespace
+
+int parse_cli(int argc, char** argv, CliOptions& opt) {
+    memset(&opt.cfg, 0, sizeof(opt.cfg));
+    opt.cfg.struct_size = sizeof(rsq_config);
+    opt.cfg.device = 0;
+    opt.cfg.chimeric_distance = 2000000;
+    opt.cfg.base_mismatch_threshold = 6;
+    opt.cfg.mapq_threshold = 255;
+    opt.cfg.collect_coverage = 1;
+    unsigned fragment_samples = 1000000u;
+    bool mapq_given = false;
+    std::vector<std::string> positional;
+    try {
+        for (int i = 1; i < argc; ++i) {
+            std::string a = argv[i];
+            auto value = [&](const std::string& longname, char shortname) -> std::string {
+                // --name=value | --name value | -nvalue | -n value
+                if (a.compare(0, 2, "--") == 0) {
+                    size_t eq = a.find('=');
+                    if (eq != std::string::npos) return a.substr(eq + 1);
+                } else if (shortname && a.size() > 2) {
+                    return a.substr(2);
+                }
+                if (i + 1 >= argc) throw ArgError{5, "Flag '" + longname + "' requires an argument but received none"};
+                return argv[++i];
+            };
+            auto is = [&](const char* longname, char shortname = 0) {
+                std::string l = std::string("--") + longname;
+                if (a == l || a.compare(0, l.size() + 1, l + "=") == 0) return true;
+                return shortname && a.size() >= 2 && a[0] == '-' && a[1] == shortname && a[1] != '-';
+            };
+            if (is("help", 'h')) { usage(std::cout); return 4; }
+            else if (a == "--version") { std::cout << kVersion << std::endl; return 0; }
+            else if (is("sample", 's')) { opt.run.sample_name = value("sample", 's'); opt.run.sample_given = true; }
+            else if (is("bed")) opt.bed = value("bed", 0);
+            else if (is("fasta")) opt.fasta = value("fasta", 0);
+            else if (is("chimeric-distance")) opt.cfg.chimeric_distance = std::stoi(value("chimeric-distance", 0));
+            else if (is("fragment-samples")) fragment_samples = (unsigned)std::stoul(value("fragment-samples", 0));
+            else if (is("mapping-quality", 'q')) { opt.cfg.mapq_threshold = (unsigned)std::stoul(value("mapping-quality", 'q')); mapq_given = true; }
+            else if (is("base-mismatch")) opt.cfg.base_mismatch_threshold = (unsigned)std::stoul(value("base-mismatch", 0));
+            else if (is("offset")) opt.run.bias_offset = std::stoi(value("offset", 0));
+            else if (is("window-size")) opt.run.bias_window = std::stoi(value("window-size", 0));
+            else if (is("gene-length")) opt.run.bias_gene_length = std::stoul(value("gene-length", 0));
+            else if (a == "--legacy") opt.legacy = true;
+            else if (is("stranded")) {
+                std::string s = value("stranded", 0);
+                if (s == "RF" || s == "rf") opt.cfg.strand_mode = 2;
+                else if (s == "FR" || s == "fr") opt.cfg.strand_mode = 1;
+                else throw ArgError{6, "--stranded argument must be in {'RF', 'rf', 'FR', 'fr'}"};
+            }
+            else if (a == "--verbose") ++opt.verbosity;
+            else if (a.size() >= 2 && a[0] == '-' && a[1] == 'v' && a.find_first_not_of('v', 1) == std::string::npos) opt.verbosity += (int)a.size() - 1;
+            else if (is("tag", 't')) opt.decode.filter_tags.push_back(value("tag", 't'));
+            else if (is("chimeric-tag")) opt.decode.chimeric_tag = value("chimeric-tag", 0);
+            else if (a == "--exclude-chimeric") opt.cfg.exclude_chimeric = 1;
+            else if (a == "--unpaired" || a == "-u") opt.cfg.unpaired = 1;
+            else if (a == "--rpkm") opt.run.use_rpkm = true;
+            else if (a == "--coverage") opt.run.write_coverage = true;
+            else if (is("coverage-mask")) opt.run.coverage_mask = (unsigned)std::stoul(value("coverage-mask", 0));
+            else if (is("detection-threshold", 'd')) opt.run.detection_threshold = (unsigned)std::stoul(value("detection-threshold", 'd'));
+            else if (is("batch-records")) opt.batch_records = std::stoul(value("batch-records", 0));
+            else if (is("device")) opt.cfg.device = std::stoi(value("device", 0));
+            else if (a == "--exact-complexity") opt.run.exact_complexity_scan = true;
+            else if (a.size() > 1 && a[0] == '-') throw ArgError{5, "Flag could not be matched: " + a};
+            else positional.push_back(a);
+        }
+        if (positional.size() > 3) throw ArgError{5, "Passed in argument, but no positional arguments were ready to receive it: " + positional[3]};
+        if (positional.size() < 1) throw ArgError{6, "No GTF file provided"};
+        if (positional.size() < 2) throw ArgError{6, "No BAM file provided"};
+        if (positional.size() < 3) throw ArgError{6, "No output directory provided"};
+    } catch (ArgError& e) {
+        usage(std::cerr);
+        std::cerr << (e.code == 5 ? "Argument parsing error: " : "Argument validation error: ") << e.msg << std::endl;
+        return e.code;
+    } catch (std::exception& e) {  // stoi/stoul failures are ParseErrors in args.hxx
+        usage(std::cerr);
+        std::cerr << "Argument parsing error: " << e.what() << std::endl;
+        return 5;
+    }
+    opt.gtf = positional[0];
+    opt.bam = positional[1];
+    opt.output_dir = positional[2];
+    opt.run.output_dir = opt.output_dir;
+    if (!opt.run.sample_given) opt.run.sample_name = std::filesystem::path(opt.bam).filename().string();  // :99
+    if (opt.legacy) {
+        std::cerr << "--legacy counting rules are not implemented in this build (SURVEY.md §8f)" << std::endl;
+        return 6;
+    }
+    if (!opt.fasta.empty()) {
+        std::cerr << "--fasta (GC content / CRAM reference) is not implemented in this build (SURVEY.md §8f)" << std::endl;
+        return 6;
+    }
+    (void)mapq_given;
+    if (opt.decode.filter_tags.size() > 8) {
+        std::cerr << "At most 8 --tag filters are supported" << std::endl;
+        return 6;
+    }
+    opt.cfg.n_filter_tags = (uint32_t)opt.decode.filter_tags.size();
+    opt.cfg.fragment_samples = opt.bed.empty() ? 0u : fragment_samples;
+    opt.decode.exclude_chimeric = opt.cfg.exclude_chimeric;
+    opt.decode.chimeric_distance = opt.cfg.chimeric_distance;
+    opt.decode.verbosity = opt.verbosity;
+    opt.run.filter_tags = opt.decode.filter_tags;
+    return -1;
+}
+
+void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool want_coverage, HostResults& R) {
+    const size_t ng = A.gene_ids.size(), ne = A.exon_ids.size();
+    R.gene_reads.assign(ng, 0); R.gene_unique.assign(ng, 0); R.gene_fragments.assign(ng, 0);
+    R.exon_whole.assign(ne, 0); R.exon_frac.assign(ne, 0);
+    if (want_coverage) R.coverage.assign(A.cov_len + 1, 0); else R.coverage.clear();
+    R.fragment_hist.assign(1u << 20, 0);
+    rsq_results out;
+    memset(&out, 0, sizeof(out));
+    out.struct_size = sizeof(out);
+    out.gene_reads = R.gene_reads.data(); out.gene_unique = R.gene_unique.data(); out.gene_fragments = R.gene_fragments.data();
+    out.exon_whole = R.exon_whole.data(); out.exon_frac = R.exon_frac.data();
+    out.coverage = want_coverage ? R.coverage.data() : nullptr;
+    out.fragment_hist = R.fragment_hist.data(); out.fragment_hist_len = R.fragment_hist.size();
+    int rc = be.finalize(ctx, &out);
+    if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_finalize failed: ") + be.last_error(ctx));
+    memcpy(R.counters, out.counters, sizeof(R.counters));
+    R.fragment_samples_taken = out.fragment_samples_taken;
+    // trim the histogram to its used range
+    size_t last = 0;
+    for (size_t i = 0; i < R.fragment_hist.size(); ++i) if (R.fragment_hist[i]) last = i + 1;
+    R.fragment_hist.resize(last);
+}
+
+int run_sample(const Backend& be, CliOptions& opt) {
+    using clk = std::chrono::steady_clock;
+    rsq_ctx* ctx = nullptr;
+    void* pinned[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t pinned_cap[2][2] = {{0, 0}, {0, 0}};
+    int exit_code = 0;
+    try {
+        Annotation A;
+        auto t0 = clk::now();
+        if (opt.verbosity) std::cout << "Reading GTF Features..." << std::endl;
+        load_gtf(opt.gtf, A);
+        if (opt.verbosity)
+            std::cout << "Finished processing GTF in " << std::chrono::duration<double>(clk::now() - t0).count() << " seconds" << std::endl;
+        BedModel bed;
+        if (!opt.bed.empty()) {
+            if (opt.verbosity) std::cout << "Parsing BED intervals for fragment size computations..." << std::endl;
+            load_bed(opt.bed, A.contigs, bed);
+        }
+        const size_t n_contigs = A.contigs.names.size();
+        A.pad_contigs(n_contigs);
+        if (!opt.bed.empty()) flatten_bed(bed, n_contigs);
+        if (n_contigs > 32767) throw HostError(11, "more than 32767 annotated contigs");
+        try {
+            if (!std::filesystem::exists(opt.output_dir)) std::filesystem::create_directories(opt.output_dir);
+        } catch (std::filesystem::filesystem_error& e) {
+            throw HostError(8, std::string("Filesystem error:  ") + e.what());
+        }
+
+        std::unique_ptr<AlnReader> reader = AlnReader::open(opt.bam);
+        Decoder decoder(reader->header(), A.contigs, n_contigs, opt.decode);
+        {
+            std::vector<uint8_t> has_features(A.contigs.names.size(), 0);
+            for (size_t c = 0; c < A.genes_by_contig.size(); ++c)
+                has_features[c] = !A.genes_by_contig[c].empty() || !A.exons_by_contig[c].empty();
+            if (!decoder.any_overlap_with(has_features)) {
+                std::cerr << "BAM file shares no contigs with GTF" << std::endl;   // src/RNASeQC.cpp:234-238
+                return 11;
+            }
+        }
+
+        int rc = be.create(&opt.cfg, &ctx);
+        if (rc != RSQ_OK) throw HostError(rc == RSQ_ERR_NO_DEVICE ? 10 : -1, std::string("rsq_create failed: ") + be.last_error(nullptr));
+        rsq_annotation av = A.view();
+        rc = be.set_annotation(ctx, &av);
+        if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_annotation failed: ") + be.last_error(ctx));
+        if (!opt.bed.empty()) {
+            rsq_bed bv = bed.view();
+            rc = be.set_bed(ctx, &bv);
+            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_bed failed: ") + be.last_error(ctx));
+        }
+
+        if (opt.verbosity) std::cout << "Parsing bam..." << std::endl;
+        auto t1 = clk::now();
+        std::vector<rsq_read> reads;
+        std::vector<rsq_block> blocks;
+        reads.reserve(opt.batch_records);
+        RawAln aln;
+        int slot = 0;
+        bool more = true;
+        while (more) {
+            reads.clear();
+            blocks.clear();
+            while (reads.size() < opt.batch_records) {
+                if (!reader->next(aln)) { more = false; break; }
+                decoder.convert(aln, reads, blocks);
+            }
+            if (reads.empty()) break;
+            // stage into page-locked buffers; a slot is reused only after the device drained it
+            const size_t need[2] = {reads.size() * sizeof(rsq_read), std::max<size_t>(blocks.size(), 1) * sizeof(rsq_block)};
+            if (pinned_cap[slot][0]) { rc = be.sync(ctx); if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(ctx)); }
+            for (int k = 0; k < 2; ++k)
+                if (pinned_cap[slot][k] < need[k]) {
+                    if (pinned[slot][k]) be.host_free(pinned[slot][k]);
+                    pinned_cap[slot][k] = need[k] + need[k] / 4;
+                    pinned[slot][k] = be.host_alloc(pinned_cap[slot][k]);
+                    if (!pinned[slot][k]) throw HostError(10, "Memory allocation failure. Out of memory");
+                }
+            memcpy(pinned[slot][0], reads.data(), reads.size() * sizeof(rsq_read));
+            memcpy(pinned[slot][1], blocks.data(), blocks.size() * sizeof(rsq_block));
+            rc = be.submit(ctx, (const rsq_read*)pinned[slot][0], reads.size(), (const rsq_block*)pinned[slot][1], blocks.size());
+            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_submit failed: ") + be.last_error(ctx));
+            slot ^= 1;
+            if (opt.verbosity > 1)
+                std::cout << "Time elapsed: " << std::chrono::duration<double>(clk::now() - t1).count()
+                          << "; Alignments processed: " << decoder.alignment_count() << std::endl;
+        }
+        rc = be.sync(ctx);
+        if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(ctx));
+        if (opt.verbosity) {
+            const double dt = std::chrono::duration<double>(clk::now() - t1).count();
+            std::cout << "Time Elapsed: " << dt << "; Alignments processed: " << decoder.alignment_count() << std::endl;
+            if (opt.verbosity > 1) std::cout << "Average Reads/Sec: " << (double)decoder.alignment_count() / dt << std::endl;
+            std::cout << "Estimating library complexity..." << std::endl;
+        }
+        HostResults R;
+        fetch_results(be, ctx, A, true, R);
+        StreamState st;
+        st.read_length = decoder.read_length();
+        st.alignment_count = decoder.alignment_count();
+        st.dropped_order = decoder.dropped_order();
+        st.final_contig = decoder.current_contig();
+        st.final_position = decoder.trim_position();
+        if (opt.verbosity) std::cout << "Generating report" << std::endl;
+        write_reports(A, R, opt.run, st);
+    } catch (HostError& e) {
+        std::cerr << e.what() << std::endl;
+        exit_code = e.exit_code;
+    } catch (std::bad_alloc& e) {
+        std::cerr << "Memory allocation failure. Out of memory" << std::endl << e.what() << std::endl;
+        exit_code = 10;
+    } catch (std::exception& e) {
+        std::cerr << "Unknown error" << std::endl << e.what() << std::endl;
+        exit_code = -1;
+    }
+    for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) if (pinned[s][k]) be.host_free(pinned[s][k]);
+    if (ctx) be.destroy(ctx);
+    return exit_code;
+}
+
+}  // namespace rsqh

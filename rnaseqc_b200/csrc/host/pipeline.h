@@ -1,0 +1,53 @@
+// pipeline.h — the host driver shared by the CLI and the Python binding: GTF/BED -> annotation,
+// SAM/BAM -> record batches -> rsq_submit (whatever library implements include/rsq_b200.h is linked or
+// passed in as a function table) -> rsq_finalize -> report files.  Mirrors the phases of main()
+// (src/RNASeQC.cpp:36-676); the hot loop itself lives behind the C-ABI.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "alnreader.h"
+#include "annotation.h"
+#include "report.h"
+#include "rsq_b200.h"
+
+namespace rsqh {
+
+// Function table of one backend library (resolved with dlsym by the Python binding, or bound statically
+// by the CLI).  Keeps pipeline.cpp independent of WHICH library implements the ABI.
+struct Backend {
+    decltype(&rsq_backend) backend;
+    decltype(&rsq_create) create;
+    decltype(&rsq_destroy) destroy;
+    decltype(&rsq_last_error) last_error;
+    decltype(&rsq_set_annotation) set_annotation;
+    decltype(&rsq_set_bed) set_bed;
+    decltype(&rsq_submit) submit;
+    decltype(&rsq_sync) sync;
+    decltype(&rsq_finalize) finalize;
+    decltype(&rsq_host_alloc) host_alloc;
+    decltype(&rsq_host_free) host_free;
+};
+
+struct CliOptions {
+    std::string gtf, bam, output_dir, bed;
+    RunOptions run;
+    DecodeOptions decode;
+    rsq_config cfg;
+    bool legacy = false;
+    std::string fasta;
+    size_t batch_records = 1u << 20;
+    int verbosity = 0;
+};
+
+// Fills `opt` from argv with the reference's flag set (src/RNASeQC.cpp:39-65).  Returns an exit code < 0 to
+// continue, or >= 0 to exit immediately (help/version/validation error: 0, 4, 5, 6).
+int parse_cli(int argc, char** argv, CliOptions& opt);
+
+// Runs one sample end to end; returns the process exit code (the reference's table, src/RNASeQC.cpp:678-764).
+int run_sample(const Backend& be, CliOptions& opt);
+
+// Pulls results out of a finalised ctx into HostResults sized for annotation A.
+void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool want_coverage, HostResults& R);
+
+}  // namespace rsqh

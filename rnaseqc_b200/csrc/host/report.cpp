@@ -1,0 +1,543 @@
+// report.cpp — end-of-run statistics and output files (see report.h).
+//
+// Everything here runs once per sample on a few MB of counts (plus the per-base coverage array for the
+// per-gene statistics) and deliberately keeps the reference's sequential fp64 evaluation order so that
+// the printed text matches.  It is written from the behaviour of src/RNASeQC.cpp:397-676 and
+// src/Metrics.cpp:132-337,342-412; file:line comments give the statement being reproduced.
+#include "report.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+namespace rsqh {
+
+double exon_count_to_double(uint64_t whole, uint64_t frac) {
+    // whole + frac * 2^-64, rounded once
+    long double v = (long double)whole + std::ldexp((long double)frac, -64);
+    return (double)v;
+}
+
+namespace {
+
+const double kMadFactor = 1.4826;  // src/RNASeQC.cpp:26
+
+// computeMedian (src/Metrics.h:147-160): NOTE the inverted parity — an ODD size averages two elements,
+// an EVEN size returns element (size-1)/2.
+template <typename Get>
+double median_quirk(unsigned long size, Get get) {
+    if (size == 0) throw HostError(2, "Invalid range\nCannot compute median of an empty list");
+    if (size == 1) return (double)get(0);
+    const unsigned long mid = (size - 1) / 2;
+    if (size % 2) return ((double)get(mid) + (double)get(mid + 1)) / 2.0;
+    return (double)get(mid);
+}
+
+struct Stats { double avg, med, std, mad; };
+
+// getStatistics (src/Metrics.h:166-186); sorts `data` in place like the reference does.
+Stats get_statistics(std::vector<double>& data) {
+    if (data.empty()) return Stats{NAN, NAN, NAN, NAN};
+    double avg = 0.0, sd = 0.0;
+    std::vector<double> deviations;
+    std::sort(data.begin(), data.end());
+    const double size = (double)data.size();
+    const double median = median_quirk((unsigned long)size, [&](unsigned long i) { return data[i]; });
+    for (double x : data) {
+        avg += x / size;
+        deviations.push_back(std::fabs(x - median));
+    }
+    std::sort(deviations.begin(), deviations.end());
+    const double med_dev = median_quirk(deviations.size(), [&](unsigned long i) { return deviations[i]; }) * kMadFactor;
+    for (double x : data) sd += std::pow(x - avg, 2.0) / size;
+    sd = std::pow(sd, 0.5);
+    return Stats{avg, median, sd, med_dev};
+}
+
+// BiasCounter::computeBias (src/Metrics.cpp:160-235).  `cov` is mutated exactly as the reference mutates the
+// caller's vector (low-coverage flanks are erased when the peak-window value is >= 100).
+void compute_bias(std::vector<unsigned long>& cov, uint8_t strand, const RunOptions& opt, uint64_t& five_end,
+                  uint64_t& three_end) {
+    if (cov.size() < opt.bias_gene_length) return;                                   // :163
+    unsigned long peak = 0;
+    size_t peak_pos = 0;
+    for (size_t i = 0; i < cov.size(); ++i)
+        if (cov[i] > peak) { peak_pos = i; peak = cov[i]; }                          // :166-170 (first maximum)
+    // :171-176 — half a window right (clamped at end()), then back one window (clamped at begin()); only the
+    // NUMBER of entries collected is used afterwards (the sorted list itself is ignored).
+    size_t p1 = peak_pos;
+    for (int i = 0; i < opt.bias_window / 2 && p1 != cov.size(); ++i) ++p1;
+    size_t n = 0, it = p1;
+    for (int i = 0; i < opt.bias_window && it != 0; ++i) { ++n; --it; }
+    // :178 — computeMedian(n, iterator into the UNSORTED coverage vector)
+    auto at = [&](unsigned long i) -> double {
+        size_t idx = it + i;
+        return idx < cov.size() ? (double)cov[idx] : 0.0;
+    };
+    if (n == 0) return;  // cannot happen for size >= 1 (the reference would throw range_error)
+    const double peak_median = median_quirk(n, at);
+    if (!(peak_median >= 100)) return;                                                // :181
+    std::vector<unsigned long> pct(cov);                                              // :182-188
+    std::sort(pct.begin(), pct.end());
+    pct.erase(pct.begin(), std::find_if(pct.begin(), pct.end(), [](unsigned long v) { return v != 0ul; }));
+    const unsigned long lower = pct[(size_t)(pct.size() * 0.05)];                     // :189
+    {
+        size_t k = 0;
+        while (k < cov.size() && cov[k] <= lower) ++k;                                // :193-199
+        cov.erase(cov.begin(), cov.begin() + k);
+    }
+    while (!cov.empty() && cov.back() <= lower) cov.pop_back();                       // :202-205
+    if (cov.size() < opt.bias_gene_length) return;                                    // :208
+    std::vector<double> lcov, rcov;
+    const unsigned offset = (unsigned)opt.bias_offset, window = (unsigned)opt.bias_window;
+    for (unsigned i = offset; i < offset + window && i < cov.size(); ++i) lcov.push_back((double)cov[i]);   // :214
+    for (int i = (int)(cov.size() - (size_t)(opt.bias_window + opt.bias_offset));
+         i >= 0 && (size_t)i < cov.size() - (size_t)opt.bias_offset; ++i)
+        rcov.push_back((double)cov[i]);                                               // :216
+    std::sort(lcov.begin(), lcov.end());
+    std::sort(rcov.begin(), rcov.end());
+    const double ml = median_quirk(lcov.size(), [&](unsigned long i) { return lcov[i]; });
+    const double mr = median_quirk(rcov.size(), [&](unsigned long i) { return rcov[i]; });
+    // :220-228 — the maps hold unsigned long: `+=` with a double truncates
+    if (strand == RSQ_STRAND_FWD) {
+        three_end = (uint64_t)((double)three_end + mr);
+        five_end = (uint64_t)((double)five_end + ml);
+    } else {
+        three_end = (uint64_t)((double)three_end + ml);
+        five_end = (uint64_t)((double)five_end + mr);
+    }
+}
+
+std::string fmt_default(double v) {
+    std::ostringstream s;
+    s << v;
+    return s.str();
+}
+
+}  // namespace
+
+void compute_coverage_summary(const Annotation& A, const HostResults& R, const RunOptions& opt,
+                              const StreamState& st, CoverageSummary& out) {
+    const size_t ng = A.gene_ids.size();
+    out.five_end.assign(ng, 0);
+    out.three_end.assign(ng, 0);
+    const unsigned M = opt.coverage_mask;
+
+    // ---- eviction order -------------------------------------------------------------------
+    // trimFeatures evicts from the FRONT of the start-sorted list (src/Expression.cpp:80-93) and dropFeatures
+    // walks the rest in list order (:96-103), so within a contig the order is always list order.  Contigs come
+    // in the order their lists were dropped (chr switches, src/RNASeQC.cpp:346-349); the genes of the final
+    // contig that were already trimmed come before the end-of-run sweep over all contigs in id order (:385-386).
+    std::vector<const GeneFeature*> order;
+    std::vector<uint8_t> done(A.genes_by_contig.size(), 0);
+    for (uint32_t c : st.dropped_order) {
+        if (c >= A.genes_by_contig.size() || done[c]) continue;
+        // the final contig may ALSO appear here if the stream left and came back; its list is then empty
+        for (const GeneFeature& g : A.genes_by_contig[c]) order.push_back(&g);
+        done[c] = 1;
+    }
+    std::vector<uint8_t> gene_emitted;
+    if (st.final_contig >= 0 && (size_t)st.final_contig < A.genes_by_contig.size() && !done[st.final_contig]) {
+        // features popped so far on the final contig: the longest prefix of the combined (gene+exon) start-sorted
+        // list whose every element has end < pos of the last read that reached trimFeatures.
+        const auto& genes = A.genes_by_contig[st.final_contig];
+        const auto& exons = A.exons_by_contig[st.final_contig];
+        gene_emitted.assign(genes.size(), 0);
+        size_t gi = 0, ei = 0;
+        const int64_t P = st.final_position;
+        while (gi < genes.size() || ei < exons.size()) {
+            // merge by (start, GTF line order) == the stable sort of the interleaved list
+            bool take_gene = ei >= exons.size() ||
+                             (gi < genes.size() && (genes[gi].start < exons[ei].start ||
+                                                    (genes[gi].start == exons[ei].start && genes[gi].line_order < exons[ei].line_order)));
+            int64_t end = take_gene ? genes[gi].end : exons[ei].end;
+            if (!(end < P)) break;
+            if (take_gene) { order.push_back(&genes[gi]); gene_emitted[gi] = 1; ++gi; }
+            else ++ei;
+        }
+    }
+    for (size_t c = 0; c < A.genes_by_contig.size(); ++c) {
+        if (done[c]) continue;
+        const auto& genes = A.genes_by_contig[c];
+        for (size_t i = 0; i < genes.size(); ++i) {
+            if ((int64_t)c == st.final_contig && !gene_emitted.empty() && gene_emitted[i]) continue;
+            order.push_back(&genes[i]);
+        }
+    }
+
+    // ---- computeCoverage per evicted gene (src/Metrics.cpp:265-337) ------------------------------------------
+    std::vector<unsigned long> gene_cov;
+    std::vector<uint32_t> zero_cov;
+    if (R.coverage.size() < A.cov_len) zero_cov.assign(A.cov_len + 1, 0);
+    const uint32_t* cov_base = R.coverage.size() < A.cov_len ? zero_cov.data() : R.coverage.data();
+    for (const GeneFeature* gf : order) {
+        const uint32_t g = gf->gene;
+        const auto& slots = A.exons_for_gene[g];
+        uint64_t T = 0;
+        for (uint32_t s : slots) T += (uint64_t)std::max<int64_t>(A.exon_len[s], 0);
+        // unmasked transcript positions are [M, T-M): the first M and the last M bases are masked (:267-279)
+        const uint64_t lo = M, hi = T > M ? T - M : 0;
+        gene_cov.clear();
+        gene_cov.reserve(T);
+        uint64_t o = 0;
+        for (uint32_t s : slots) {
+            const uint64_t L = (uint64_t)std::max<int64_t>(A.exon_len[s], 0);
+            const uint32_t* cov = cov_base + A.exon_cov_off[s];
+            double exon_mean = 0.0, exon_std = 0.0, exon_size = 0.0;
+            for (uint64_t j = 0; j < L; ++j) if (o + j >= lo && o + j < hi) exon_size += 1.0;                 // :286
+            if (exon_size > 0) {
+                for (uint64_t j = 0; j < L; ++j)
+                    if (o + j >= lo && o + j < hi) exon_mean += (double)cov[j] / exon_size;                  // :290-291
+                for (uint64_t j = 0; j < L; ++j)
+                    if (o + j >= lo && o + j < hi) exon_std += std::pow((double)cov[j] - exon_mean, 2.0) / exon_size;  // :293-294
+                exon_std = std::pow(exon_std, 0.5);
+                exon_std /= exon_mean;                                                                       // :296 (now a CV)
+                if (!(std::isnan(exon_std) || std::isinf(exon_std))) out.exon_cvs.emplace_back(A.exon_ids[s], exon_std);
+            }
+            for (uint64_t j = 0; j < L; ++j) gene_cov.push_back(cov[j]);                                     // :307-308
+            o += L;
+        }
+        compute_bias(gene_cov, gf->strand, opt, out.five_end[g], out.three_end[g]);                          // :311
+        double avg = 0.0, sd = 0.0;
+        if (M) {                                                                                             // :314-322
+            if (M > gene_cov.size()) gene_cov.clear();
+            else gene_cov.erase(gene_cov.end() - M, gene_cov.end());
+            if (!gene_cov.empty()) {
+                if (M > gene_cov.size()) gene_cov.clear();
+                else gene_cov.erase(gene_cov.begin(), gene_cov.begin() + M);
+            }
+        }
+        const double size = (double)gene_cov.size();
+        std::string row = A.gene_ids[g] + "\t";
+        if (size > 0) {
+            for (unsigned long v : gene_cov) avg += (double)v / size;
+            for (unsigned long v : gene_cov) sd += std::pow((double)v - avg, 2.0) / size;
+            sd = std::pow(sd, 0.5);
+            row += fmt_default(avg) + "\t" + fmt_default(sd) + "\t" + fmt_default(sd / avg);
+            out.gene_means.push_back(avg);
+            out.gene_stds.push_back(sd);
+            out.gene_cvs.push_back(sd / avg);
+        } else {
+            row += "0\t0\tnan";                                                                              // :335
+        }
+        out.rows.push_back(row);
+    }
+}
+
+namespace {
+
+// Lander-Waterman scan (src/RNASeQC.cpp:398-415).  The literal loop runs up to 1e9 exp() calls; the estimate
+// x*(1-exp(-n/x)) is increasing in x with slope < 1, so the first minimum of the truncated error can be
+// bracketed by bisection and then found by replaying the reference loop over a window around it.
+unsigned library_complexity(double duplicates, double unique, bool exact) {
+    if (!(duplicates > 0)) return 0u;
+    const double num_reads = duplicates + unique;
+    auto estimate = [&](double x) { return x * (1.0 - std::exp(-1.0 * num_reads / x)); };
+    auto scan = [&](double from, double to, unsigned& min_reads, unsigned& min_error) {
+        for (double x = from; x < to; ++x) {
+            unsigned error = (unsigned)std::fabs(estimate(x) - unique);
+            if (error < min_error) { min_error = error; min_reads = (unsigned)x; }
+        }
+    };
+    unsigned min_reads = 0u, min_error = UINT_MAX;
+    if (exact || unique < 1.0) {
+        scan(unique, 1e9, min_reads, min_error);
+        return min_reads;
+    }
+    // steps k = 0 .. K-1 with x = unique + k < 1e9
+    const double K = std::ceil(1e9 - unique);
+    if (K <= 0) return 0u;
+    const double W = 1 << 20;
+    if (K <= 4 * W) { scan(unique, 1e9, min_reads, min_error); return min_reads; }
+    // target error value: the smallest truncated error reachable = 0 if the estimate crosses unique-1 before 1e9,
+    // else the truncated error at the last step.
+    const double x_last = unique + (K - 1);
+    double target;  // first x with estimate(x) > unique - target is the answer (monotone part, estimate <= unique)
+    if (estimate(x_last) > unique - 1.0) target = 1.0;
+    else target = std::floor(unique - estimate(x_last)) + 1.0;
+    double lo = 0, hi = K - 1;  // invariant: predicate false at lo-1 (or lo==0), true at hi
+    while (lo < hi) {
+        double mid = std::floor((lo + hi) / 2);
+        if (estimate(unique + mid) > unique - target) hi = mid; else lo = mid + 1;
+    }
+    // replay the literal loop on [lo-W, lo+W); seed min_error with the error just before the window so that
+    // "first strictly smaller" behaves as in the full scan.
+    double from = std::max(0.0, lo - W), to = std::min(K, lo + W);
+    if (from > 0) {
+        // errors before the window are >= the error at from-1 (monotone decreasing up to rounding noise)
+        min_error = (unsigned)std::fabs(estimate(unique + from - 1) - unique);
+        min_reads = (unsigned)(unique + from - 1);
+        // walk back to the first x with that same truncated error is unnecessary: a strictly smaller error
+        // exists inside the window by construction, so this seed is overwritten.
+    }
+    scan(unique + from, unique + to, min_reads, min_error);
+    return min_reads;
+}
+
+struct CounterName { int idx; const char* name; };
+// dump order of operator<<(ofstream&, Metrics&) (src/Metrics.cpp:344-380)
+const CounterName kDumpOrder[] = {
+    {RSQ_C_END1_ANTISENSE, "End 1 Antisense"}, {RSQ_C_END2_ANTISENSE, "End 2 Antisense"},
+    {RSQ_C_END1_BASES, "End 1 Bases"}, {RSQ_C_END2_BASES, "End 2 Bases"},
+    {RSQ_C_END1_MAPPED_READS, "End 1 Mapped Reads"}, {RSQ_C_END2_MAPPED_READS, "End 2 Mapped Reads"},
+    {RSQ_C_END1_MISMATCHES, "End 1 Mismatches"}, {RSQ_C_END2_MISMATCHES, "End 2 Mismatches"},
+    {RSQ_C_END1_SENSE, "End 1 Sense"}, {RSQ_C_END2_SENSE, "End 2 Sense"},
+    {RSQ_C_EXONIC_READS, "Exonic Reads"}, {RSQ_C_FAILED_VENDOR_QC, "Failed Vendor QC"},
+    {RSQ_C_HIGH_QUALITY_READS, "High Quality Reads"}, {RSQ_C_INTERGENIC_READS, "Intergenic Reads"},
+    {RSQ_C_INTRAGENIC_READS, "Intragenic Reads"}, {RSQ_C_AMBIGUOUS_READS, "Ambiguous Reads"},
+    {RSQ_C_INTRONIC_READS, "Intronic Reads"}, {RSQ_C_LOW_MAPPING_QUALITY, "Low Mapping Quality"},
+    {RSQ_C_LOW_QUALITY_READS, "Low Quality Reads"}, {RSQ_C_MAPPED_DUPLICATE_READS, "Mapped Duplicate Reads"},
+    {RSQ_C_MAPPED_READS, "Mapped Reads"}, {RSQ_C_MAPPED_UNIQUE_READS, "Mapped Unique Reads"},
+    {RSQ_C_MISMATCHED_BASES, "Mismatched Bases"}, {RSQ_C_NON_GLOBIN_READS, "Non-Globin Reads"},
+    {RSQ_C_NON_GLOBIN_DUPLICATE_READS, "Non-Globin Duplicate Reads"},
+    {RSQ_C_READS_USED, "Reads used for Intron/Exon counts"}, {RSQ_C_RRNA_READS, "rRNA Reads"},
+    {RSQ_C_SPLIT_READS, "Split Reads"}, {RSQ_C_TOTAL_BASES, "Total Bases"},
+    {RSQ_C_TOTAL_MAPPED_PAIRS, "Total Mapped Pairs"},
+    {RSQ_C_UMVQ, "Unique Mapping, Vendor QC Passed Reads"}, {RSQ_C_UNPAIRED_READS, "Unpaired Reads"},
+};
+
+}  // namespace
+
+void write_reports(const Annotation& A, const HostResults& R, const RunOptions& opt, const StreamState& st) {
+    namespace fs = std::filesystem;
+    try {
+        if (!fs::exists(opt.output_dir)) fs::create_directories(opt.output_dir);   // src/RNASeQC.cpp:190-193
+    } catch (fs::filesystem_error& e) {
+        throw HostError(8, std::string("Filesystem error:  ") + e.what());
+    }
+    const std::string base = opt.output_dir + "/" + opt.sample_name;
+    uint64_t C[RSQ_N_COUNTERS];
+    for (int i = 0; i < RSQ_N_COUNTERS; ++i) C[i] = R.counters[i];
+    // counter.increment("Total Alignments", alignmentCount): the int parameter truncates (src/RNASeQC.cpp:397,
+    // src/Metrics.cpp:33-36)
+    const uint64_t total_alignments = (uint64_t)(int64_t)(int)st.alignment_count;
+    auto frac = [&](int a, int b) { return (double)C[a] / C[b]; };                   // Metrics::frac, src/Metrics.cpp:43-46
+
+    // ---- coverage statistics (the reference computes them as genes leave the window) -------------------------
+    CoverageSummary cov;
+    compute_coverage_summary(A, R, opt, st, cov);
+    {
+        std::ofstream w(opt.write_coverage ? base + ".coverage.tsv" : std::string("/dev/null"));
+        if (!w.is_open() && opt.write_coverage) throw HostError(-1, "Unable to open BaseCoverage output file");
+        w << "gene_id\tcoverage_mean\tcoverage_std\tcoverage_CV" << std::endl;     // src/Metrics.h:113
+        for (const std::string& r : cov.rows) w << r << std::endl;
+    }
+
+    const unsigned min_reads = library_complexity((double)C[RSQ_C_DUPLICATE_PAIRS], (double)C[RSQ_C_UNIQUE_FRAGMENTS],
+                                                  opt.exact_complexity_scan);
+
+    // ---- gene tables (src/RNASeQC.cpp:419-475) -----------------------------------------------------------------
+    unsigned genes_detected = 0;
+    unsigned bias_genes = 0;
+    std::vector<double> ratios;
+    {
+        std::ofstream gene_report(base + ".gene_reads.gct");
+        std::ofstream gene_rpkm(base + ".gene_" + (opt.use_rpkm ? "rpkm" : "tpm") + ".gct");
+        std::ofstream fragment_report(base + ".gene_fragments.gct");
+        gene_report << "#1.2" << std::endl;
+        gene_rpkm << "#1.2" << std::endl;
+        fragment_report << "#1.2" << std::endl;
+        gene_report << A.gene_list.size() << "\t1" << std::endl;
+        gene_rpkm << A.gene_list.size() << "\t1" << std::endl;
+        fragment_report << A.gene_list.size() << "\t1" << std::endl;
+        gene_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << std::endl;
+        gene_rpkm << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : (opt.use_rpkm ? "RPKM" : "TPM")) << std::endl;
+        gene_rpkm << std::fixed;
+        fragment_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Fragments") << std::endl;
+        const double scale_rpkm = (double)C[RSQ_C_EXONIC_READS] / 1000000.0;
+        double scale_tpm = 0.0;
+        std::vector<double> tpms(A.gene_list.size(), 0.0);
+        for (size_t i = 0; i < A.gene_list.size(); ++i) {
+            const uint32_t g = A.gene_list[i];
+            const double count = (double)R.gene_reads[g];
+            gene_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_reads[g] << std::endl;
+            fragment_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_fragments[g] << std::endl;
+            if (opt.use_rpkm) {
+                double rpkm = (1000.0 * count / scale_rpkm) / (double)A.gene_coding_len[g];
+                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << rpkm << std::endl;
+            } else {
+                double tpm = (1000.0 * count) / (double)A.gene_coding_len[g];
+                tpms[i] = tpm;
+                scale_tpm += tpm;
+            }
+            if ((double)R.gene_unique[g] >= opt.detection_threshold) ++genes_detected;   // :461
+            // BiasCounter::getBias (src/Metrics.cpp:239-249)
+            const double cov5 = (double)cov.five_end[g], cov3 = (double)cov.three_end[g];
+            if (cov5 + cov3 > 0.0) { ++bias_genes; ratios.push_back(cov3 / (cov5 + cov3)); }
+        }
+        if (!opt.use_rpkm) {
+            scale_tpm /= 1000000.0;
+            for (size_t i = 0; i < A.gene_list.size(); ++i) {
+                const uint32_t g = A.gene_list[i];
+                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << tpms[i] / scale_tpm << std::endl;
+            }
+        }
+    }
+
+    // ---- 3'/5' ratio statistics (src/RNASeQC.cpp:478-508) ------------------------------------------------------
+    double ratio_avg = 0.0, ratio_mad = 0.0, ratio_median = 0.0, ratio_std = 0.0, ratio75 = 0.0, ratio25 = 0.0;
+    if (ratios.size() > 1) {
+        Stats s = get_statistics(ratios);  // sorts ratios in place, as the reference's template does
+        ratio_avg = s.avg; ratio_median = s.med; ratio_std = s.std; ratio_mad = s.mad;
+        auto at = [&](double idx) {  // ratios[static_cast<int>(idx)]; the reference reads past the end for n in {2,3,4}
+            size_t k = (size_t)(int)idx;
+            return k < ratios.size() ? ratios[k] : 0.0;
+        };
+        double index = .25 * ratios.size();
+        if (index > std::floor(index)) { index = std::ceil(index); ratio25 = at(index); }
+        else { index = std::ceil(index); ratio25 = (at(index) + at(index + 1)) / 2.0; }
+        index = .75 * ratios.size();
+        if (index > std::floor(index)) { index = std::ceil(index); ratio75 = at(index); }
+        else { index = std::ceil(index); ratio75 = (at(index) + at(index + 1)) / 2.0; }
+    }
+
+    // ---- exon table (src/RNASeQC.cpp:510-521) -------------------------------------------------------------------
+    {
+        std::ofstream exon_report(base + ".exon_reads.gct");
+        size_t nonzero = 0;
+        for (size_t e = 0; e < A.exon_ids.size(); ++e) if (R.exon_whole[e] || R.exon_frac[e]) ++nonzero;
+        exon_report << "#1.2" << std::endl;
+        exon_report << nonzero << "\t1" << std::endl;                                  // exonCounts.size(), :513
+        exon_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << std::endl;
+        exon_report << std::fixed;
+        for (size_t e = 0; e < A.exon_ids.size(); ++e) {
+            const double v = R.exon_seq.empty() ? exon_count_to_double(R.exon_whole[e], R.exon_frac[e]) : R.exon_seq[e];
+            exon_report << A.exon_ids[e] << "\t" << A.exon_desc[e] << "\t" << v << std::endl;
+        }
+    }
+
+    // ---- metrics.tsv (src/RNASeQC.cpp:523-564, src/Metrics.cpp:381-410) -----------------------------------------
+    std::ofstream output(base + ".metrics.tsv");
+    output << "Sample\t" << opt.sample_name << std::endl;
+    output << "Mapping Rate\t" << frac(RSQ_C_MAPPED_READS, RSQ_C_UMVQ) << std::endl;
+    output << "Unique Rate of Mapped\t" << frac(RSQ_C_MAPPED_UNIQUE_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Duplicate Rate of Mapped\t" << frac(RSQ_C_MAPPED_DUPLICATE_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Duplicate Rate of Mapped, excluding Globins\t" << frac(RSQ_C_NON_GLOBIN_DUPLICATE_READS, RSQ_C_NON_GLOBIN_READS) << std::endl;
+    output << "Base Mismatch\t" << frac(RSQ_C_MISMATCHED_BASES, RSQ_C_TOTAL_BASES) << std::endl;
+    output << "End 1 Mapping Rate\t" << 2.0 * frac(RSQ_C_END1_MAPPED_READS, RSQ_C_UMVQ) << std::endl;
+    output << "End 2 Mapping Rate\t" << 2.0 * frac(RSQ_C_END2_MAPPED_READS, RSQ_C_UMVQ) << std::endl;
+    output << "End 1 Mismatch Rate\t" << frac(RSQ_C_END1_MISMATCHES, RSQ_C_END1_BASES) << std::endl;
+    output << "End 2 Mismatch Rate\t" << frac(RSQ_C_END2_MISMATCHES, RSQ_C_END2_BASES) << std::endl;
+    output << "Expression Profiling Efficiency\t" << frac(RSQ_C_EXONIC_READS, RSQ_C_UMVQ) << std::endl;
+    output << "High Quality Rate\t" << frac(RSQ_C_HIGH_QUALITY_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Exonic Rate\t" << frac(RSQ_C_EXONIC_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Intronic Rate\t" << frac(RSQ_C_INTRONIC_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Intergenic Rate\t" << frac(RSQ_C_INTERGENIC_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Intragenic Rate\t" << frac(RSQ_C_INTRAGENIC_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "Ambiguous Alignment Rate\t" << frac(RSQ_C_AMBIGUOUS_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "High Quality Exonic Rate\t" << frac(RSQ_C_HQ_EXONIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
+    output << "High Quality Intronic Rate\t" << frac(RSQ_C_HQ_INTRONIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
+    output << "High Quality Intergenic Rate\t" << frac(RSQ_C_HQ_INTERGENIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
+    output << "High Quality Intragenic Rate\t" << frac(RSQ_C_HQ_INTRAGENIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
+    output << "High Quality Ambiguous Alignment Rate\t" << frac(RSQ_C_HQ_AMBIGUOUS_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
+    output << "Discard Rate\t" << (double)(C[RSQ_C_MAPPED_READS] - C[RSQ_C_READS_USED]) / C[RSQ_C_MAPPED_READS] << std::endl;
+    output << "rRNA Rate\t" << frac(RSQ_C_RRNA_READS, RSQ_C_MAPPED_READS) << std::endl;
+    output << "End 1 Sense Rate\t" << (double)C[RSQ_C_END1_SENSE] / (C[RSQ_C_END1_SENSE] + C[RSQ_C_END1_ANTISENSE]) << std::endl;
+    output << "End 2 Sense Rate\t" << (double)C[RSQ_C_END2_SENSE] / (C[RSQ_C_END2_SENSE] + C[RSQ_C_END2_ANTISENSE]) << std::endl;
+    output << "Avg. Splits per Read\t" << frac(RSQ_C_ALIGNMENT_BLOCKS, RSQ_C_MAPPED_READS) - 1.0 << std::endl;
+    // operator<<(ofstream&, Metrics&)
+    output << "Total Alignments\t" << total_alignments << std::endl;
+    output << "Alternative Alignments\t" << C[RSQ_C_ALTERNATIVE_ALIGNMENTS] << std::endl;
+    output << "Supplementary Alignments\t" << C[RSQ_C_SUPPLEMENTARY_ALIGNMENTS] << std::endl;
+    output << "Total Reads\t" << total_alignments - C[RSQ_C_ALTERNATIVE_ALIGNMENTS] - C[RSQ_C_SUPPLEMENTARY_ALIGNMENTS] << std::endl;
+    output << "Chimeric Fragments\t";
+    if (C[RSQ_C_CHIMERIC_TAG]) {
+        output << C[RSQ_C_CHIMERIC_TAG] << std::endl;
+        output << "Chimeric Alignment Rate\t" << frac(RSQ_C_CHIMERIC_TAG, RSQ_C_TOTAL_MAPPED_PAIRS) << std::endl;
+    } else {
+        output << C[RSQ_C_CHIMERIC_AUTO] << std::endl;
+        output << "Chimeric Alignment Rate\t" << frac(RSQ_C_CHIMERIC_AUTO, RSQ_C_TOTAL_MAPPED_PAIRS) << std::endl;
+    }
+    for (const CounterName& k : kDumpOrder)
+        if (k.idx != RSQ_C_SPLIT_READS || C[RSQ_C_SPLIT_READS]) output << k.name << "\t" << C[k.idx] << std::endl;
+    {
+        // "Filtered by tag: X" rows exist only for tags that fired, in std::map (lexicographic) order
+        std::map<std::string, uint64_t> fired;
+        for (size_t k = 0; k < opt.filter_tags.size() && k < 8; ++k)
+            if (C[RSQ_C_FILTERED_BY_TAG0 + k]) fired["Filtered by tag: " + opt.filter_tags[k]] += C[RSQ_C_FILTERED_BY_TAG0 + k];
+        for (auto& kv : fired) output << kv.first << "\t" << kv.second << std::endl;
+    }
+    output << "Read Length\t" << st.read_length << std::endl;
+    output << "Genes Detected\t" << genes_detected << std::endl;
+    output << "Estimated Library Complexity\t" << min_reads << std::endl;
+    output << "Genes used in 3' bias\t" << bias_genes << std::endl;
+    output << "Mean 3' bias\t" << ratio_avg << std::endl;
+    output << "Median 3' bias\t" << ratio_median << std::endl;
+    output << "3' bias Std\t" << ratio_std << std::endl;
+    output << "3' bias MAD_Std\t" << ratio_mad << std::endl;
+    output << "3' Bias, 25th Percentile\t" << ratio25 << std::endl;
+    output << "3' Bias, 75th Percentile\t" << ratio75 << std::endl;
+
+    // ---- fragment sizes (src/RNASeQC.cpp:570-607) ----------------------------------------------------------------
+    {
+        std::vector<std::pair<long long, unsigned long>> frag;  // fragmentSizes map contents, ascending
+        for (size_t i = 0; i < R.fragment_hist.size(); ++i)
+            if (R.fragment_hist[i]) frag.emplace_back((long long)i, (unsigned long)R.fragment_hist[i]);
+        if (!frag.empty()) {
+            double fragment_avg = 0.0, fragment_std = 0.0, fragment_mad = 0.0;
+            unsigned long total = 0;
+            for (auto& f : frag) total += f.second;
+            const double size = (double)total;
+            // median over the expanded sorted list
+            auto expanded_at = [&](unsigned long i) {
+                unsigned long acc = 0;
+                for (auto& f : frag) { acc += f.second; if (i < acc) return (double)f.first; }
+                return (double)frag.back().first;
+            };
+            const double fragment_med = median_quirk((unsigned long)size, expanded_at);
+            std::ofstream fragment_list(base + ".fragmentSizes.txt");
+            fragment_list << "Fragment Size\tCount" << std::endl;
+            std::vector<double> deviations;
+            for (auto& f : frag) {
+                fragment_list << f.first << "\t" << f.second << std::endl;
+                fragment_avg += (double)(f.first * (long long)f.second) / size;
+                double deviation = std::fabs((double)f.first - fragment_med);
+                for (unsigned long i = 0; i < f.second; ++i) deviations.push_back(deviation);
+            }
+            fragment_list.close();
+            std::sort(deviations.begin(), deviations.end());
+            fragment_mad = median_quirk(deviations.size(), [&](unsigned long i) { return deviations[i]; }) * kMadFactor;
+            for (auto& f : frag)
+                for (unsigned long i = 0; i < f.second; ++i) fragment_std += std::pow((double)f.first - fragment_avg, 2.0) / size;
+            fragment_std = std::pow(fragment_std, 0.5);
+            output << "Average Fragment Length\t" << fragment_avg << std::endl;
+            output << "Fragment Length Median\t" << fragment_med << std::endl;
+            output << "Fragment Length Std\t" << fragment_std << std::endl;
+            output << "Fragment Length MAD_Std\t" << fragment_mad << std::endl;
+        }
+    }
+
+    // ---- coverage medians and exon_cv.tsv (src/RNASeQC.cpp:609-659) --------------------------------------------
+    {
+        std::vector<double> means = cov.gene_means, stds = cov.gene_stds, cvs;
+        const unsigned long n_transcripts = means.size();
+        std::sort(means.begin(), means.end());
+        std::sort(stds.begin(), stds.end());
+        for (double v : cov.gene_cvs) if (!(std::isnan(v) || std::isinf(v))) cvs.push_back(v);
+        std::sort(cvs.begin(), cvs.end());
+        const unsigned long n_cvs = cvs.size();
+        output << "Median of Avg Transcript Coverage\t" << median_quirk(n_transcripts, [&](unsigned long i) { return means[i]; }) << std::endl;
+        output << "Median of Transcript Coverage Std\t" << median_quirk(n_transcripts, [&](unsigned long i) { return stds[i]; }) << std::endl;
+        output << "Median of Transcript Coverage CV\t" << (n_cvs ? median_quirk(n_cvs, [&](unsigned long i) { return cvs[i]; }) : 0.0) << std::endl;
+        std::map<std::string, double> exon_cov;  // exonCoverage: later entries overwrite
+        for (auto& kv : cov.exon_cvs) exon_cov[kv.first] = kv.second;
+        std::ofstream cv_report(base + ".exon_cv.tsv");
+        cv_report << "Exon ID\tExon CV" << std::endl;
+        std::vector<double> total_exon_cv;
+        for (auto& kv : exon_cov) {
+            cv_report << kv.first << "\t" << kv.second << std::endl;
+            total_exon_cv.push_back(kv.second);
+        }
+        Stats cs = get_statistics(total_exon_cv);
+        output << "Median Exon CV\t" << cs.med << std::endl;
+        output << "Exon CV MAD\t" << cs.mad << std::endl;
+    }
+    output.close();
+}
+
+}  // namespace rsqh
