@@ -3,7 +3,7 @@
 #   make oracle     -> test infrastructure: CPU oracle library + oracle-backed CLI harness
 #   make ref        -> test infrastructure: the unmodified reference binary into oracle/_ref/ (needs /root/reference)
 NVCC     ?= /usr/local/cuda/bin/nvcc
-CXX      ?= g++
+CXX      := /usr/bin/g++
 CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Iinclude -Irnaseqc_b200/csrc/host
 NVFLAGS  := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Iinclude
 LIBDIR   := rnaseqc_b200/lib

@@ -99,7 +99,10 @@ typedef struct rsq_config {
                                          fragment-tracker hash set); 0 = 1<<24                     */
     uint32_t collect_coverage;        /* 1: accumulate per-base exon coverage (always on in the
                                          reference; 0 only for ablation benchmarks)               */
-    uint32_t reserved[7];
+    uint32_t reserved0;
+    uint64_t user_stream;             /* cudaStream_t to run the kernels on (0 = the ctx creates its
+                                         own); lets the caller time the path with its own events   */
+    uint32_t reserved[4];
 } rsq_config;
 
 /* ---- exon flags / gene-segment flags ------------------------------------------------------------------- */

@@ -1,0 +1,400 @@
+"""ctypes binding of the C-ABI in include/rsq_b200.h plus the host helper library (librsq_host.so).
+
+`Backend(path)` loads ONE library implementing the ABI.  The product is `librsq_b200.so` (CUDA, sm_100a); tests
+may also load the CPU oracle `oracle/_build/librsq_oracle.so` through the same class to compare results — the
+product code never does (PRODUCT_LIB below is the only path `default_backend()` will load, and it raises if the
+library is missing or no GPU is present).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT_LIB = os.path.join(ROOT, "rnaseqc_b200", "lib", "librsq_b200.so")
+HOST_LIB = os.path.join(ROOT, "rnaseqc_b200", "lib", "librsq_host.so")
+
+RSQ_N_COUNTERS = 64
+RSQ_OK, RSQ_ERR_INVALID, RSQ_ERR_NO_DEVICE, RSQ_ERR_CUDA, RSQ_ERR_NOMEM, RSQ_ERR_CAPACITY = range(6)
+
+COUNTER_NAMES = [
+    "Alternative Alignments", "Supplementary Alignments", "Failed Vendor QC", "Low Mapping Quality",
+    "Chimeric Fragments_auto", "Chimeric Fragments_tag", "Unique Mapping, Vendor QC Passed Reads", "Unpaired Reads",
+    "Mapped Reads", "Mapped Duplicate Reads", "Mapped Unique Reads", "Total Mapped Pairs", "End 1 Mapped Reads",
+    "End 1 Mismatches", "End 1 Bases", "Duplicate Pairs", "Unique Fragments", "End 2 Mapped Reads", "End 2 Mismatches",
+    "End 2 Bases", "Mismatched Bases", "Total Bases", "High Quality Reads", "Low Quality Reads",
+    "Reads used for Intron/Exon counts", "Alignment Blocks", "Non-Globin Reads", "Non-Globin Duplicate Reads",
+    "Intronic Reads", "Intragenic Reads", "HQ Intronic Reads", "HQ Intragenic Reads", "Intergenic Reads",
+    "HQ Intergenic Reads", "Exonic Reads", "HQ Exonic Reads", "Ambiguous Reads", "HQ Ambiguous Reads", "rRNA Reads",
+    "End 1 Sense", "End 1 Antisense", "End 2 Sense", "End 2 Antisense", "Total Alignments",
+] + [f"Filtered by tag {k}" for k in range(8)] + ["Split Reads", "Fragment Candidates"]
+COUNTER_INDEX = {n: i for i, n in enumerate(COUNTER_NAMES)}
+
+READ_DTYPE = np.dtype([
+    ("pos", "<i4"), ("mpos", "<i4"), ("endpos", "<i4"), ("isize", "<i4"), ("l_qseq", "<i4"), ("nm", "<i4"),
+    ("flag", "<u2"), ("mapq", "u1"), ("aux", "u1"), ("contig", "<i2"), ("filter_mask", "u1"), ("reserved0", "u1"),
+    ("name_hash", "<u8"), ("block_off", "<u4"), ("n_blocks", "<u2"), ("reserved1", "<u2")])
+BLOCK_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4")])
+
+
+class RsqConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("mapq_threshold", C.c_uint32),
+                ("base_mismatch_threshold", C.c_uint32), ("chimeric_distance", C.c_int32), ("strand_mode", C.c_uint32),
+                ("unpaired", C.c_uint32), ("exclude_chimeric", C.c_uint32), ("n_filter_tags", C.c_uint32),
+                ("fragment_samples", C.c_uint32), ("max_records", C.c_uint64), ("collect_coverage", C.c_uint32),
+                ("reserved0", C.c_uint32), ("user_stream", C.c_uint64), ("reserved", C.c_uint32 * 4)]
+
+
+class RsqAnnotation(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_contigs", C.c_uint32), ("n_genes", C.c_uint32), ("n_exons", C.c_uint32),
+                ("n_segs", C.c_uint32), ("reserved", C.c_uint32),
+                ("exon_off", C.POINTER(C.c_uint32)), ("exon_start", C.POINTER(C.c_int32)), ("exon_end", C.POINTER(C.c_int32)),
+                ("exon_gene", C.POINTER(C.c_uint32)), ("exon_slot", C.POINTER(C.c_uint32)), ("exon_flags", C.POINTER(C.c_uint8)),
+                ("exon_cov_off", C.POINTER(C.c_uint64)), ("seg_off", C.POINTER(C.c_uint32)), ("seg_start", C.POINTER(C.c_int32)),
+                ("seg_flags", C.POINTER(C.c_uint8)), ("gene_flags", C.POINTER(C.c_uint8)), ("cov_len", C.c_uint64)]
+
+
+class RsqBed(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_contigs", C.c_uint32), ("n_intervals", C.c_uint32), ("reserved", C.c_uint32),
+                ("off", C.POINTER(C.c_uint32)), ("start", C.POINTER(C.c_int32)), ("end", C.POINTER(C.c_int32)),
+                ("name_id", C.POINTER(C.c_uint32)), ("contig_present", C.POINTER(C.c_uint8))]
+
+
+class RsqResults(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("counters", C.c_uint64 * RSQ_N_COUNTERS),
+                ("gene_reads", C.POINTER(C.c_uint64)), ("gene_unique", C.POINTER(C.c_uint64)),
+                ("gene_fragments", C.POINTER(C.c_uint64)), ("exon_whole", C.POINTER(C.c_uint64)),
+                ("exon_frac", C.POINTER(C.c_uint64)), ("coverage", C.POINTER(C.c_uint32)),
+                ("fragment_hist", C.POINTER(C.c_uint64)), ("fragment_hist_len", C.c_uint64),
+                ("fragment_samples_taken", C.c_uint64)]
+
+
+class RunOptionsC(C.Structure):
+    _fields_ = [("sample_name", C.c_char_p), ("sample_given", C.c_int), ("output_dir", C.c_char_p), ("use_rpkm", C.c_int),
+                ("write_coverage", C.c_int), ("coverage_mask", C.c_uint), ("bias_offset", C.c_int), ("bias_window", C.c_int),
+                ("bias_gene_length", C.c_ulong), ("detection_threshold", C.c_uint), ("filter_tags", C.POINTER(C.c_char_p)),
+                ("n_filter_tags", C.c_int), ("exact_complexity_scan", C.c_int)]
+
+
+class StreamStateC(C.Structure):
+    _fields_ = [("read_length", C.c_int), ("alignment_count", C.c_ulonglong), ("final_contig", C.c_longlong),
+                ("final_position", C.c_int), ("n_dropped", C.c_uint), ("dropped", C.c_uint * 1024)]
+
+
+ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
+               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_submit", "rsq_submit_device", "rsq_sync",
+               "rsq_reset", "rsq_finalize", "rsq_export_counts", "rsq_import_counts", "rsq_algorithmic_bytes",
+               "rsq_launch_count", "rsq_kernel_time_ms"]
+
+
+def make_config(device: int = 0, mapq: int = 255, mismatches: int = 6, chimeric_distance: int = 2000000,
+                strand_mode: int = 0, unpaired: bool = False, exclude_chimeric: bool = False, n_filter_tags: int = 0,
+                fragment_samples: int = 0, max_records: int = 0, collect_coverage: bool = True, user_stream: int = 0) -> RsqConfig:
+    cfg = RsqConfig()
+    cfg.struct_size = C.sizeof(RsqConfig)
+    cfg.device = device
+    cfg.mapq_threshold = mapq
+    cfg.base_mismatch_threshold = mismatches
+    cfg.chimeric_distance = chimeric_distance
+    cfg.strand_mode = strand_mode
+    cfg.unpaired = int(unpaired)
+    cfg.exclude_chimeric = int(exclude_chimeric)
+    cfg.n_filter_tags = n_filter_tags
+    cfg.fragment_samples = fragment_samples
+    cfg.max_records = max_records
+    cfg.collect_coverage = int(collect_coverage)
+    cfg.user_stream = user_stream
+    return cfg
+
+
+class RsqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rsq error {code}: {msg}")
+        self.code = code
+
+
+class Results:
+    """Host copy of everything rsq_finalize returns."""
+
+    def __init__(self, n_genes: int, n_exons: int, cov_len: int, hist_len: int = 1 << 16, want_coverage: bool = True):
+        self.counters = np.zeros(RSQ_N_COUNTERS, np.uint64)
+        self.gene_reads = np.zeros(n_genes, np.uint64)
+        self.gene_unique = np.zeros(n_genes, np.uint64)
+        self.gene_fragments = np.zeros(n_genes, np.uint64)
+        self.exon_whole = np.zeros(n_exons, np.uint64)
+        self.exon_frac = np.zeros(n_exons, np.uint64)
+        self.coverage = np.zeros(cov_len + 1, np.uint32) if want_coverage else None
+        self.fragment_hist = np.zeros(hist_len, np.uint64)
+        self.fragment_samples_taken = 0
+
+    def struct(self) -> RsqResults:
+        r = RsqResults()
+        r.struct_size = C.sizeof(RsqResults)
+        p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+        r.gene_reads, r.gene_unique, r.gene_fragments = p64(self.gene_reads), p64(self.gene_unique), p64(self.gene_fragments)
+        r.exon_whole, r.exon_frac = p64(self.exon_whole), p64(self.exon_frac)
+        if self.coverage is not None:
+            r.coverage = self.coverage.ctypes.data_as(C.POINTER(C.c_uint32))
+        r.fragment_hist = p64(self.fragment_hist)
+        r.fragment_hist_len = len(self.fragment_hist)
+        return r
+
+    def counter(self, name: str) -> int:
+        return int(self.counters[COUNTER_INDEX[name]])
+
+    def exon_counts(self) -> np.ndarray:
+        """exact Q64.64 -> float64 (what exon_reads.gct prints)"""
+        return self.exon_whole.astype(np.float64) + self.exon_frac.astype(np.float64) * 2.0 ** -64
+
+
+class Backend:
+    """One loaded library that implements include/rsq_b200.h."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} is not built (run `make` / __graft_entry__.build())")
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.rsq_backend.restype = C.c_char_p
+        L.rsq_abi_version.restype = C.c_uint32
+        L.rsq_host_alloc.restype = C.c_void_p
+        L.rsq_host_alloc.argtypes = [C.c_size_t]
+        L.rsq_host_free.argtypes = [C.c_void_p]
+        L.rsq_create.argtypes = [C.POINTER(RsqConfig), C.POINTER(C.c_void_p)]
+        L.rsq_destroy.argtypes = [C.c_void_p]
+        L.rsq_last_error.restype = C.c_char_p
+        L.rsq_last_error.argtypes = [C.c_void_p]
+        L.rsq_set_annotation.argtypes = [C.c_void_p, C.POINTER(RsqAnnotation)]
+        L.rsq_set_bed.argtypes = [C.c_void_p, C.POINTER(RsqBed)]
+        L.rsq_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.rsq_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.rsq_sync.argtypes = [C.c_void_p]
+        L.rsq_reset.argtypes = [C.c_void_p]
+        L.rsq_finalize.argtypes = [C.c_void_p, C.POINTER(RsqResults)]
+        L.rsq_export_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.rsq_import_counts.argtypes = [C.c_void_p]
+        L.rsq_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.rsq_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.rsq_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+
+    @property
+    def name(self) -> str:
+        return self.lib.rsq_backend().decode()
+
+    def create(self, cfg: RsqConfig) -> "Context":
+        h = C.c_void_p()
+        rc = self.lib.rsq_create(C.byref(cfg), C.byref(h))
+        if rc != RSQ_OK:
+            raise RsqError(rc, self.lib.rsq_last_error(None).decode())
+        return Context(self, h, cfg)
+
+
+class Context:
+    def __init__(self, be: Backend, handle: C.c_void_p, cfg: RsqConfig):
+        self.be, self.h, self.cfg = be, handle, cfg
+        self.n_genes = self.n_exons = self.cov_len = 0
+
+    def _check(self, rc: int) -> None:
+        if rc != RSQ_OK:
+            raise RsqError(rc, self.be.lib.rsq_last_error(self.h).decode())
+
+    def close(self) -> None:
+        if self.h:
+            self.be.lib.rsq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_annotation(self, ann: "Annotation") -> None:
+        v = ann.view
+        self.n_genes, self.n_exons, self.cov_len = v.n_genes, v.n_exons, v.cov_len
+        self._check(self.be.lib.rsq_set_annotation(self.h, C.byref(v)))
+        if ann.bed_view is not None and self.cfg.fragment_samples:
+            self._check(self.be.lib.rsq_set_bed(self.h, ann.bed_view))
+
+    def submit(self, reads: np.ndarray, blocks: np.ndarray) -> None:
+        """host arrays (structured READ_DTYPE/BLOCK_DTYPE, or raw uint8/int32 views of the same bytes)"""
+        assert reads.flags["C_CONTIGUOUS"] and blocks.flags["C_CONTIGUOUS"]
+        n_reads = reads.nbytes // 48
+        n_blocks = blocks.nbytes // 8
+        self._check(self.be.lib.rsq_submit(self.h, reads.ctypes.data, n_reads, blocks.ctypes.data, n_blocks))
+
+    def submit_ptr(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
+        self._check(self.be.lib.rsq_submit(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
+
+    def submit_device(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
+        self._check(self.be.lib.rsq_submit_device(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
+
+    def sync(self) -> None:
+        self._check(self.be.lib.rsq_sync(self.h))
+
+    def reset(self) -> None:
+        self._check(self.be.lib.rsq_reset(self.h))
+
+    def finalize(self, want_coverage: bool = True, hist_len: int = 1 << 16) -> Results:
+        res = Results(self.n_genes, self.n_exons, self.cov_len, hist_len, want_coverage)
+        st = res.struct()
+        self._check(self.be.lib.rsq_finalize(self.h, C.byref(st)))
+        res.counters[:] = np.frombuffer(st.counters, dtype=np.uint64)
+        res.fragment_samples_taken = int(st.fragment_samples_taken)
+        return res
+
+    def export_counts(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.be.lib.rsq_export_counts(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def import_counts(self) -> None:
+        self._check(self.be.lib.rsq_import_counts(self.h))
+
+    def algorithmic_bytes(self) -> int:
+        v = C.c_uint64()
+        self._check(self.be.lib.rsq_algorithmic_bytes(self.h, C.byref(v)))
+        return int(v.value)
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._check(self.be.lib.rsq_launch_count(self.h, C.byref(v)))
+        return int(v.value)
+
+    def kernel_time_ms(self) -> float:
+        v = C.c_double()
+        self._check(self.be.lib.rsq_kernel_time_ms(self.h, C.byref(v)))
+        return float(v.value)
+
+
+def default_backend() -> Backend:
+    """The product library.  Raises if it is not built; Context creation raises RsqError(NO_DEVICE) without a GPU."""
+    return Backend(PRODUCT_LIB)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# host helper library: GTF/BED parsing, SAM/BAM decode, report writing (C++; librsq_host.so)
+# ------------------------------------------------------------------------------------------------------------------
+_host = None
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB):
+            raise FileNotFoundError(f"{HOST_LIB} is not built (run `make`)")
+        H = C.CDLL(HOST_LIB)
+        H.rsqh_load_annotation.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+        H.rsqh_free_annotation.argtypes = [C.c_void_p]
+        H.rsqh_annotation_view.restype = C.POINTER(RsqAnnotation)
+        H.rsqh_annotation_view.argtypes = [C.c_void_p]
+        H.rsqh_bed_view.restype = C.POINTER(RsqBed)
+        H.rsqh_bed_view.argtypes = [C.c_void_p]
+        for f in ("rsqh_n_gene_list", "rsqh_n_contigs"):
+            getattr(H, f).restype = C.c_uint
+            getattr(H, f).argtypes = [C.c_void_p]
+        H.rsqh_gene_list_index.restype = C.c_uint
+        H.rsqh_gene_list_index.argtypes = [C.c_void_p, C.c_uint]
+        for f in ("rsqh_gene_id", "rsqh_exon_id", "rsqh_contig_name"):
+            getattr(H, f).restype = C.c_char_p
+            getattr(H, f).argtypes = [C.c_void_p, C.c_uint]
+        H.rsqh_contig_index.restype = C.c_int
+        H.rsqh_contig_index.argtypes = [C.c_void_p, C.c_char_p]
+        H.rsqh_decode_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                       C.POINTER(StreamStateC), C.c_char_p, C.c_size_t]
+        H.rsqh_free.argtypes = [C.c_void_p]
+        H.rsqh_hash_qname.restype = C.c_uint64
+        H.rsqh_hash_qname.argtypes = [C.c_char_p, C.c_size_t]
+        H.rsqh_write_reports.argtypes = [C.c_void_p, C.POINTER(RsqResults), C.c_void_p, C.POINTER(RunOptionsC),
+                                         C.POINTER(StreamStateC), C.c_char_p, C.c_size_t]
+        _host = H
+    return _host
+
+
+class Annotation:
+    """Flattened annotation parsed from GTF (+BED) text by the C++ host library."""
+
+    def __init__(self, gtf: str, bed: Optional[str] = None):
+        H = host_lib()
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = H.rsqh_load_annotation(gtf.encode(), bed.encode() if bed else None, C.byref(self._h), err, 1024)
+        if rc != 0:
+            raise RuntimeError(f"annotation load failed (exit code {rc}): {err.value.decode()}")
+        self.view = H.rsqh_annotation_view(self._h).contents
+        bv = H.rsqh_bed_view(self._h)
+        self.bed_view = bv if bv else None
+
+    def __del__(self):
+        try:
+            if self._h:
+                host_lib().rsqh_free_annotation(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def n_genes(self) -> int:
+        return self.view.n_genes
+
+    @property
+    def n_exons(self) -> int:
+        return self.view.n_exons
+
+    @property
+    def cov_len(self) -> int:
+        return self.view.cov_len
+
+    def contig_index(self, name: str) -> int:
+        return host_lib().rsqh_contig_index(self._h, name.encode())
+
+    def gene_ids(self) -> List[str]:
+        H = host_lib()
+        return [H.rsqh_gene_id(self._h, g).decode() for g in range(self.n_genes)]
+
+    def array(self, field: str, n: int, dtype) -> np.ndarray:
+        ptr = getattr(self.view, field)
+        return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+    def decode(self, path: str, chimeric_tag: str = "ch", filter_tags: Sequence[str] = (), exclude_chimeric: bool = False,
+               chimeric_distance: int = 2000000) -> Tuple[np.ndarray, np.ndarray, StreamStateC]:
+        """SAM/BAM -> (reads, blocks, stream state) through the C++ decoder."""
+        H = host_lib()
+        tags = (C.c_char_p * max(len(filter_tags), 1))(*[t.encode() for t in filter_tags])
+        pr, pb = C.c_void_p(), C.c_void_p()
+        nr, nbk = C.c_size_t(), C.c_size_t()
+        st = StreamStateC()
+        err = C.create_string_buffer(1024)
+        rc = H.rsqh_decode_file(self._h, path.encode(), chimeric_tag.encode(), tags, len(filter_tags), int(exclude_chimeric),
+                                chimeric_distance, C.byref(pr), C.byref(nr), C.byref(pb), C.byref(nbk), C.byref(st), err, 1024)
+        if rc != 0:
+            raise RuntimeError(f"decode failed (exit code {rc}): {err.value.decode()}")
+        reads = np.frombuffer(C.string_at(pr.value, nr.value * 48), dtype=READ_DTYPE).copy() if nr.value else np.zeros(0, READ_DTYPE)
+        blocks = np.frombuffer(C.string_at(pb.value, nbk.value * 8), dtype=BLOCK_DTYPE).copy() if nbk.value else np.zeros(0, BLOCK_DTYPE)
+        H.rsqh_free(pr)
+        H.rsqh_free(pb)
+        return reads, blocks, st
+
+    def write_reports(self, res: Results, out_dir: str, sample: str, state: StreamStateC, sample_given: bool = False,
+                      write_coverage: bool = False, use_rpkm: bool = False, filter_tags: Sequence[str] = (),
+                      exon_seq: Optional[np.ndarray] = None, coverage_mask: int = 500, detection_threshold: int = 5) -> None:
+        H = host_lib()
+        o = RunOptionsC()
+        o.sample_name = sample.encode(); o.sample_given = int(sample_given); o.output_dir = out_dir.encode()
+        o.use_rpkm = int(use_rpkm); o.write_coverage = int(write_coverage); o.coverage_mask = coverage_mask
+        o.bias_offset = 0; o.bias_window = 100; o.bias_gene_length = 200; o.detection_threshold = detection_threshold
+        tags = (C.c_char_p * max(len(filter_tags), 1))(*[t.encode() for t in filter_tags])
+        o.filter_tags = tags; o.n_filter_tags = len(filter_tags); o.exact_complexity_scan = 0
+        st = res.struct()
+        C.memmove(st.counters, res.counters.ctypes.data, 8 * RSQ_N_COUNTERS)
+        st.fragment_samples_taken = res.fragment_samples_taken
+        err = C.create_string_buffer(1024)
+        rc = H.rsqh_write_reports(self._h, C.byref(st), exon_seq.ctypes.data if exon_seq is not None else None, C.byref(o),
+                                  C.byref(state), err, 1024)
+        if rc != 0:
+            raise RuntimeError(f"write_reports failed (exit code {rc}): {err.value.decode()}")

@@ -317,7 +317,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
     // src/Metrics.cpp:33-36)
     const uint64_t total_alignments = (uint64_t)(int64_t)(int)st.alignment_count;
     auto frac = [&](int a, int b) { return (double)C[a] / C[b]; };                   // Metrics::frac, src/Metrics.cpp:43-46
-
     // ---- coverage statistics (the reference computes them as genes leave the window) -------------------------
     CoverageSummary cov;
     compute_coverage_summary(A, R, opt, st, cov);
@@ -327,10 +326,8 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         w << "gene_id\tcoverage_mean\tcoverage_std\tcoverage_CV" << std::endl;     // src/Metrics.h:113
         for (const std::string& r : cov.rows) w << r << std::endl;
     }
-
     const unsigned min_reads = library_complexity((double)C[RSQ_C_DUPLICATE_PAIRS], (double)C[RSQ_C_UNIQUE_FRAGMENTS],
                                                   opt.exact_complexity_scan);
-
     // ---- gene tables (src/RNASeQC.cpp:419-475) -----------------------------------------------------------------
     unsigned genes_detected = 0;
     unsigned bias_genes = 0;
@@ -378,7 +375,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             }
         }
     }
-
     // ---- 3'/5' ratio statistics (src/RNASeQC.cpp:478-508) ------------------------------------------------------
     double ratio_avg = 0.0, ratio_mad = 0.0, ratio_median = 0.0, ratio_std = 0.0, ratio75 = 0.0, ratio25 = 0.0;
     if (ratios.size() > 1) {
@@ -395,7 +391,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         if (index > std::floor(index)) { index = std::ceil(index); ratio75 = at(index); }
         else { index = std::ceil(index); ratio75 = (at(index) + at(index + 1)) / 2.0; }
     }
-
     // ---- exon table (src/RNASeQC.cpp:510-521) -------------------------------------------------------------------
     {
         std::ofstream exon_report(base + ".exon_reads.gct");
@@ -410,7 +405,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             exon_report << A.exon_ids[e] << "\t" << A.exon_desc[e] << "\t" << v << std::endl;
         }
     }
-
     // ---- metrics.tsv (src/RNASeQC.cpp:523-564, src/Metrics.cpp:381-410) -----------------------------------------
     std::ofstream output(base + ".metrics.tsv");
     output << "Sample\t" << opt.sample_name << std::endl;
@@ -472,7 +466,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
     output << "3' bias MAD_Std\t" << ratio_mad << std::endl;
     output << "3' Bias, 25th Percentile\t" << ratio25 << std::endl;
     output << "3' Bias, 75th Percentile\t" << ratio75 << std::endl;
-
     // ---- fragment sizes (src/RNASeQC.cpp:570-607) ----------------------------------------------------------------
     {
         std::vector<std::pair<long long, unsigned long>> frag;  // fragmentSizes map contents, ascending
@@ -511,7 +504,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             output << "Fragment Length MAD_Std\t" << fragment_mad << std::endl;
         }
     }
-
     // ---- coverage medians and exon_cv.tsv (src/RNASeQC.cpp:609-659) --------------------------------------------
     {
         std::vector<double> means = cov.gene_means, stds = cov.gene_stds, cvs;

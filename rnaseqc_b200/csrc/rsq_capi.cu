@@ -1,0 +1,522 @@
+// rsq_capi.cu — C-ABI (include/rsq_b200.h) over the sm_100a kernels: device memory, streams, staging.
+// One rsq_ctx drives one GPU.  There is no CPU fallback: without a CUDA device rsq_create fails with
+// RSQ_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rsq_b200.h"
+#include "rsq_device.h"
+
+namespace {
+
+using namespace rsqd;
+
+std::string g_create_error;
+
+struct Ctx {
+    rsq_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = true;
+    // annotation
+    bool have_ann = false, have_bed = false;
+    uint32_t n_contigs = 0, n_genes = 0, n_exons = 0, n_segs = 0;
+    uint64_t cov_len = 0;
+    AnnView ann{};
+    BedView bed{};
+    std::vector<void*> ann_allocs, bed_allocs;
+    // accumulators
+    Accum acc{};
+    unsigned int* d_cov = nullptr;            // integrated coverage (finalize)
+    unsigned int* d_scan = nullptr;           // scan scratch
+    size_t scan_elems = 0;
+    unsigned long long frag_cap = 0, pair_cap = 0;
+    unsigned long long* d_export = nullptr;
+    size_t export_words = 0;
+    unsigned long long* d_hist = nullptr;
+    size_t hist_len = 0;
+    unsigned int* d_pair_scratch = nullptr;
+    size_t pair_scratch_elems = 0;
+    size_t sample_cap = 0;                    // capacity of sample_flag / sample_isize / cand (records per sub-batch)
+    // staging for host submits (two slots)
+    rsq_read* d_reads[2] = {nullptr, nullptr};
+    rsq_block* d_blocks[2] = {nullptr, nullptr};
+    size_t cap_reads[2] = {0, 0}, cap_blocks[2] = {0, 0};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
+    unsigned slot = 0;
+    // bookkeeping
+    unsigned long long records_submitted = 0;
+    unsigned long long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;
+    size_t timers_used = 0;
+    double kernel_ms = 0.0;
+};
+
+constexpr size_t kSubBatch = 1u << 24;   // records per hot-kernel launch (bounds the BED candidate buffers)
+
+#define CU_TRY(expr)                                                                                      \
+    do {                                                                                                  \
+        cudaError_t e__ = (expr);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            c->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                 \
+            return RSQ_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+unsigned long long next_pow2(unsigned long long v) {
+    unsigned long long p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <typename T>
+int upload(Ctx* c, std::vector<void*>& owner, const T* host, size_t n, const T** out) {
+    T* d = nullptr;
+    CU_TRY(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    owner.push_back(d);
+    if (n) CU_TRY(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *out = d;
+    return RSQ_OK;
+}
+
+void free_list(std::vector<void*>& v) {
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+
+int zero_accumulators(Ctx* c) {
+    Accum& a = c->acc;
+    CU_TRY(cudaMemsetAsync(a.counters, 0, 8 * RSQ_N_COUNTERS, c->stream));
+    CU_TRY(cudaMemsetAsync(a.gene_reads, 0, 8ull * c->n_genes, c->stream));
+    CU_TRY(cudaMemsetAsync(a.gene_unique, 0, 8ull * c->n_genes, c->stream));
+    CU_TRY(cudaMemsetAsync(a.gene_fragments, 0, 8ull * c->n_genes, c->stream));
+    CU_TRY(cudaMemsetAsync(a.exon_whole, 0, 8ull * c->n_exons, c->stream));
+    CU_TRY(cudaMemsetAsync(a.exon_frac, 0, 8ull * c->n_exons, c->stream));
+    CU_TRY(cudaMemsetAsync(a.cov_diff, 0, 4ull * (c->cov_len + 1), c->stream));
+    CU_TRY(cudaMemsetAsync(a.frag_set, 0, 8ull * c->frag_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(a.algo_bytes, 0, 8, c->stream));
+    CU_TRY(cudaMemsetAsync(a.error_flag, 0, 4, c->stream));
+    if (c->have_bed && c->cfg.fragment_samples) {
+        CU_TRY(cudaMemsetAsync(a.pair_keys, 0, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.pair_first, 0xff, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.sample_count, 0, 8, c->stream));
+    }
+    c->records_submitted = 0;
+    c->kernel_ms = 0.0;
+    c->timers_used = 0;
+    return RSQ_OK;
+}
+
+int ensure_bed_buffers(Ctx* c, size_t n_reads) {
+    if (!(c->have_bed && c->cfg.fragment_samples)) return RSQ_OK;
+    const size_t need = std::min(n_reads, kSubBatch);
+    if (need > c->sample_cap) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->acc.sample_flag); cudaFree(c->acc.sample_isize); cudaFree(c->acc.cand); cudaFree(c->d_pair_scratch);
+        c->sample_cap = need;
+        CU_TRY(cudaMalloc(&c->acc.sample_flag, need));
+        CU_TRY(cudaMalloc(&c->acc.sample_isize, 4 * need));
+        CU_TRY(cudaMalloc(&c->acc.cand, sizeof(PairCandidate) * need));
+        c->acc.cand_capacity = (unsigned int)need;
+        c->pair_scratch_elems = pair_scan_scratch_elems(need);
+        CU_TRY(cudaMalloc(&c->d_pair_scratch, 4 * c->pair_scratch_elems));
+    }
+    return RSQ_OK;
+}
+
+// grows the fragment-tracker set so that (records so far + n) <= capacity / 2
+int ensure_frag_capacity(Ctx* c, size_t n) {
+    const unsigned long long need = 2ull * (c->records_submitted + n);
+    if (need <= c->frag_cap) return RSQ_OK;
+    const unsigned long long new_cap = next_pow2(need);
+    unsigned long long* nt = nullptr;
+    CU_TRY(cudaMalloc(&nt, 8ull * new_cap));
+    CU_TRY(cudaMemsetAsync(nt, 0, 8ull * new_cap, c->stream));
+    c->launches += launch_rehash(c->acc.frag_set, c->frag_cap, nt, new_cap - 1, c->acc.error_flag, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->acc.frag_set);
+    c->acc.frag_set = nt;
+    c->acc.frag_mask = new_cap - 1;
+    c->frag_cap = new_cap;
+    return RSQ_OK;
+}
+
+int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks, size_t n_blocks) {
+    int rc = ensure_frag_capacity(c, n_reads);
+    if (rc != RSQ_OK) return rc;
+    rc = ensure_bed_buffers(c, n_reads);
+    if (rc != RSQ_OK) return rc;
+    Params prm{};
+    prm.mapq_threshold = c->cfg.mapq_threshold;
+    prm.base_mismatch_threshold = c->cfg.base_mismatch_threshold;
+    prm.chimeric_distance = c->cfg.chimeric_distance;
+    prm.strand_mode = c->cfg.strand_mode;
+    prm.unpaired = c->cfg.unpaired;
+    prm.exclude_chimeric = c->cfg.exclude_chimeric;
+    prm.n_filter_tags = c->cfg.n_filter_tags;
+    prm.collect_coverage = c->cfg.collect_coverage;
+    prm.bed_enabled = (c->have_bed && c->cfg.fragment_samples) ? 1u : 0u;
+    prm.fragment_samples = c->cfg.fragment_samples;
+    // timing events around the kernels of this batch
+    if (c->timers_used == c->timers.size()) {
+        if (c->timers.size() >= 1024) {   // fold what is finished so far
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            for (size_t k = 0; k < c->timers_used; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, c->timers[k].first, c->timers[k].second);
+                c->kernel_ms += ms;
+            }
+            c->timers_used = 0;
+        } else {
+            cudaEvent_t a, b;
+            CU_TRY(cudaEventCreate(&a));
+            CU_TRY(cudaEventCreate(&b));
+            c->timers.emplace_back(a, b);
+        }
+    }
+    auto& tm = c->timers[c->timers_used++];
+    CU_TRY(cudaEventRecord(tm.first, c->stream));
+    for (size_t base = 0; base < n_reads; base += kSubBatch) {
+        const size_t n = std::min(kSubBatch, n_reads - base);
+        prm.record_base = c->records_submitted + base;
+        if (prm.bed_enabled) {
+            CU_TRY(cudaMemsetAsync(c->acc.cand_count, 0, 4, c->stream));
+            CU_TRY(cudaMemsetAsync(c->acc.sample_flag, 0, n, c->stream));
+        }
+        c->launches += launch_hot_path(d_reads + base, d_blocks, n, n_blocks, c->ann, c->bed, c->acc, prm, c->stream);
+        if (prm.bed_enabled) c->launches += launch_pair_stages(n, c->acc, prm, c->d_pair_scratch, c->stream);
+    }
+    CU_TRY(cudaEventRecord(tm.second, c->stream));
+    CU_TRY(cudaGetLastError());
+    c->records_submitted += n_reads;
+    return RSQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rsq_backend(void) { return "cuda-sm_100a"; }
+uint32_t rsq_abi_version(void) { return RSQ_ABI_VERSION; }
+
+void* rsq_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void rsq_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int rsq_create(const rsq_config* cfg, rsq_ctx** out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(rsq_config)) { g_create_error = "bad rsq_config"; return RSQ_ERR_INVALID; }
+    if (cfg->n_filter_tags > 8) { g_create_error = "at most 8 filter tags"; return RSQ_ERR_INVALID; }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev <= 0 || cfg->device < 0 || cfg->device >= n_dev) {
+        g_create_error = std::string("no usable CUDA device (this build has no CPU fallback): ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return RSQ_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return RSQ_ERR_CUDA; }
+    Ctx* c = new Ctx();
+    c->cfg = *cfg;
+    c->own_stream = cfg->user_stream == 0;
+    if (!c->own_stream) c->stream = reinterpret_cast<cudaStream_t>(cfg->user_stream);
+    if ((c->own_stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaStreamCreate failed";
+        delete c;
+        return RSQ_ERR_CUDA;
+    }
+    for (int k = 0; k < 2; ++k) {
+        cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming);
+    }
+    *out = reinterpret_cast<rsq_ctx*>(c);
+    return RSQ_OK;
+}
+
+void rsq_destroy(rsq_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    free_list(c->ann_allocs);
+    free_list(c->bed_allocs);
+    Accum& a = c->acc;
+    void* ptrs[] = {a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_frac, a.cov_diff, a.frag_set,
+                    a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
+                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->d_hist, c->d_pair_scratch,
+                    c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1]};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& t : c->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(c->ev_copied[k]); cudaEventDestroy(c->ev_done[k]); }
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+const char* rsq_last_error(const rsq_ctx* ctx) {
+    return ctx ? reinterpret_cast<const Ctx*>(ctx)->err.c_str() : g_create_error.c_str();
+}
+
+int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !a || a->struct_size != sizeof(rsq_annotation)) return RSQ_ERR_INVALID;
+    if (c->have_ann) { c->err = "annotation already set"; return RSQ_ERR_INVALID; }
+    if (a->n_genes >= (1u << 24)) { c->err = "more than 2^24 genes"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    c->n_contigs = a->n_contigs; c->n_genes = a->n_genes; c->n_exons = a->n_exons; c->n_segs = a->n_segs; c->cov_len = a->cov_len;
+    // repack host-side into the device layout: (start,end) pairs and 16-byte metadata
+    std::vector<int2> se(a->n_exons);
+    std::vector<ExonMeta> meta(a->n_exons);
+    for (uint32_t i = 0; i < a->n_exons; ++i) {
+        se[i] = make_int2(a->exon_start[i], a->exon_end[i]);
+        meta[i].gene_flags = a->exon_gene[i] | ((uint32_t)a->exon_flags[i] << 24);
+        meta[i].slot = a->exon_slot[i];
+        meta[i].cov_off = a->exon_cov_off[i];
+    }
+    AnnView& v = c->ann;
+    v.n_contigs = a->n_contigs; v.n_genes = a->n_genes; v.n_exons = a->n_exons; v.n_segs = a->n_segs;
+    int rc;
+    if ((rc = upload(c, c->ann_allocs, a->exon_off, (size_t)a->n_contigs + 1, &v.exon_off))) return rc;
+    if ((rc = upload(c, c->ann_allocs, se.data(), se.size(), &v.exon_se))) return rc;
+    if ((rc = upload(c, c->ann_allocs, meta.data(), meta.size(), &v.exon_meta))) return rc;
+    if ((rc = upload(c, c->ann_allocs, a->seg_off, (size_t)a->n_contigs + 1, &v.seg_off))) return rc;
+    if ((rc = upload(c, c->ann_allocs, a->seg_start, (size_t)a->n_segs, &v.seg_start))) return rc;
+    if ((rc = upload(c, c->ann_allocs, a->seg_flags, (size_t)a->n_segs, &v.seg_flags))) return rc;
+    if ((rc = upload(c, c->ann_allocs, a->gene_flags, (size_t)a->n_genes, &v.gene_flags))) return rc;
+    int32_t* pmax = nullptr;
+    CU_TRY(cudaMalloc(&pmax, std::max<size_t>(a->n_exons, 1) * 4));
+    c->ann_allocs.push_back(pmax);
+    c->launches += launch_prefix_max(v.exon_se, v.exon_off, a->n_contigs, pmax, c->stream);
+    v.exon_pmax = pmax;
+    // accumulators
+    Accum& acc = c->acc;
+    CU_TRY(cudaMalloc(&acc.counters, 8 * RSQ_N_COUNTERS));
+    CU_TRY(cudaMalloc(&acc.gene_reads, 8ull * std::max(a->n_genes, 1u)));
+    CU_TRY(cudaMalloc(&acc.gene_unique, 8ull * std::max(a->n_genes, 1u)));
+    CU_TRY(cudaMalloc(&acc.gene_fragments, 8ull * std::max(a->n_genes, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_whole, 8ull * std::max(a->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_frac, 8ull * std::max(a->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.cov_diff, 4ull * (a->cov_len + 1)));
+    CU_TRY(cudaMalloc(&c->d_cov, 4ull * (a->cov_len + 1)));
+    c->scan_elems = coverage_scan_scratch_elems(a->cov_len + 1);
+    CU_TRY(cudaMalloc(&c->d_scan, 4ull * c->scan_elems));
+    c->frag_cap = next_pow2(2ull * (c->cfg.max_records ? c->cfg.max_records : (1ull << 24)));
+    CU_TRY(cudaMalloc(&acc.frag_set, 8ull * c->frag_cap));
+    acc.frag_mask = c->frag_cap - 1;
+    CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
+    CU_TRY(cudaMalloc(&acc.error_flag, 4));
+    c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * a->n_exons;
+    CU_TRY(cudaMalloc(&c->d_export, 8ull * c->export_words));
+    c->have_ann = true;
+    rc = zero_accumulators(c);
+    if (rc != RSQ_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+    return RSQ_OK;
+}
+
+int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* b) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !b || b->struct_size != sizeof(rsq_bed)) return RSQ_ERR_INVALID;
+    if (!c->have_ann) { c->err = "set the annotation first"; return RSQ_ERR_INVALID; }
+    if (c->have_bed) { c->err = "BED already set"; return RSQ_ERR_INVALID; }
+    if (b->n_contigs != c->n_contigs) { c->err = "BED and annotation contig spaces differ"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    std::vector<int2> se(b->n_intervals);
+    for (uint32_t i = 0; i < b->n_intervals; ++i) se[i] = make_int2(b->start[i], b->end[i]);
+    BedView& v = c->bed;
+    v.n_intervals = b->n_intervals;
+    int rc;
+    if ((rc = upload(c, c->bed_allocs, b->off, (size_t)b->n_contigs + 1, &v.off))) return rc;
+    if ((rc = upload(c, c->bed_allocs, se.data(), se.size(), &v.se))) return rc;
+    if ((rc = upload(c, c->bed_allocs, b->name_id, (size_t)b->n_intervals, &v.name_id))) return rc;
+    if ((rc = upload(c, c->bed_allocs, b->contig_present, (size_t)b->n_contigs, &v.present))) return rc;
+    int32_t* pmax = nullptr;
+    CU_TRY(cudaMalloc(&pmax, std::max<size_t>(b->n_intervals, 1) * 4));
+    c->bed_allocs.push_back(pmax);
+    c->launches += launch_prefix_max(v.se, v.off, b->n_contigs, pmax, c->stream);
+    v.pmax = pmax;
+    c->have_bed = true;
+    if (c->cfg.fragment_samples) {
+        Accum& acc = c->acc;
+        c->pair_cap = next_pow2(c->cfg.max_records ? c->cfg.max_records : (1ull << 24));
+        CU_TRY(cudaMalloc(&acc.pair_keys, 8ull * c->pair_cap));
+        CU_TRY(cudaMalloc(&acc.pair_first, 8ull * c->pair_cap));
+        CU_TRY(cudaMalloc(&acc.pair_payload, 8ull * c->pair_cap));
+        acc.pair_mask = c->pair_cap - 1;
+        CU_TRY(cudaMalloc(&acc.cand_count, 4));
+        CU_TRY(cudaMalloc(&acc.sample_vals, 4ull * c->cfg.fragment_samples));
+        CU_TRY(cudaMalloc(&acc.sample_count, 8));
+        CU_TRY(cudaMemsetAsync(acc.pair_keys, 0, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(acc.pair_first, 0xff, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(acc.sample_count, 0, 8, c->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return RSQ_OK;
+}
+
+int rsq_submit_device(rsq_ctx* ctx, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks, size_t n_blocks) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann) return RSQ_ERR_INVALID;
+    if (!n_reads) return RSQ_OK;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    return run_batch(c, d_reads, n_reads, d_blocks, n_blocks);
+}
+
+int rsq_submit(rsq_ctx* ctx, const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann || (n_reads && !reads)) return RSQ_ERR_INVALID;
+    if (!n_reads) return RSQ_OK;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const unsigned s = c->slot;
+    c->slot ^= 1u;
+    // the slot's previous kernels must have drained before its buffers are overwritten (or re-allocated)
+    if (c->slot_used[s]) {
+        if (n_reads > c->cap_reads[s] || n_blocks > c->cap_blocks[s]) CU_TRY(cudaEventSynchronize(c->ev_done[s]));
+        else CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[s], 0));
+    }
+    if (n_reads > c->cap_reads[s]) {
+        cudaFree(c->d_reads[s]);
+        c->cap_reads[s] = n_reads + n_reads / 8;
+        CU_TRY(cudaMalloc(&c->d_reads[s], c->cap_reads[s] * sizeof(rsq_read)));
+    }
+    if (std::max<size_t>(n_blocks, 1) > c->cap_blocks[s]) {
+        cudaFree(c->d_blocks[s]);
+        c->cap_blocks[s] = std::max<size_t>(n_blocks, 1) + n_blocks / 8;
+        CU_TRY(cudaMalloc(&c->d_blocks[s], c->cap_blocks[s] * sizeof(rsq_block)));
+    }
+    CU_TRY(cudaMemcpyAsync(c->d_reads[s], reads, n_reads * sizeof(rsq_read), cudaMemcpyHostToDevice, c->copy_stream));
+    if (n_blocks) CU_TRY(cudaMemcpyAsync(c->d_blocks[s], blocks, n_blocks * sizeof(rsq_block), cudaMemcpyHostToDevice, c->copy_stream));
+    CU_TRY(cudaEventRecord(c->ev_copied[s], c->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
+    int rc = run_batch(c, c->d_reads[s], n_reads, c->d_blocks[s], n_blocks);
+    if (rc != RSQ_OK) return rc;
+    CU_TRY(cudaEventRecord(c->ev_done[s], c->stream));
+    c->slot_used[s] = true;
+    return RSQ_OK;
+}
+
+int rsq_sync(rsq_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return RSQ_OK;
+}
+
+int rsq_reset(rsq_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    return zero_accumulators(c);
+}
+
+int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !out || out->struct_size != sizeof(rsq_results) || !c->have_ann) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    cudaStream_t st = c->stream;
+    const Accum& a = c->acc;
+    unsigned int err_flag = 0;
+    CU_TRY(cudaMemcpyAsync(&err_flag, a.error_flag, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->counters, a.counters, 8 * RSQ_N_COUNTERS, cudaMemcpyDeviceToHost, st));
+    if (out->gene_reads) CU_TRY(cudaMemcpyAsync(out->gene_reads, a.gene_reads, 8ull * c->n_genes, cudaMemcpyDeviceToHost, st));
+    if (out->gene_unique) CU_TRY(cudaMemcpyAsync(out->gene_unique, a.gene_unique, 8ull * c->n_genes, cudaMemcpyDeviceToHost, st));
+    if (out->gene_fragments) CU_TRY(cudaMemcpyAsync(out->gene_fragments, a.gene_fragments, 8ull * c->n_genes, cudaMemcpyDeviceToHost, st));
+    if (out->exon_whole) CU_TRY(cudaMemcpyAsync(out->exon_whole, a.exon_whole, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
+    if (out->exon_frac) CU_TRY(cudaMemcpyAsync(out->exon_frac, a.exon_frac, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
+    if (c->cov_len && c->cfg.collect_coverage) {   // integrate the difference array on the device; copy out only on request
+        c->launches += launch_coverage_scan(a.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
+        if (out->coverage) CU_TRY(cudaMemcpyAsync(out->coverage, c->d_cov, 4ull * c->cov_len, cudaMemcpyDeviceToHost, st));
+    } else if (out->coverage && c->cov_len) {
+        memset(out->coverage, 0, 4ull * c->cov_len);
+    }
+    out->fragment_samples_taken = 0;
+    if (out->fragment_hist && out->fragment_hist_len) {
+        memset(out->fragment_hist, 0, 8 * out->fragment_hist_len);
+        if (c->have_bed && c->cfg.fragment_samples) {
+            unsigned long long found = 0;
+            CU_TRY(cudaMemcpyAsync(&found, a.sample_count, 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            const unsigned long long take = std::min<unsigned long long>(found, c->cfg.fragment_samples);
+            if (c->hist_len < out->fragment_hist_len) {
+                cudaFree(c->d_hist);
+                c->hist_len = out->fragment_hist_len;
+                CU_TRY(cudaMalloc(&c->d_hist, 8ull * c->hist_len));
+            }
+            CU_TRY(cudaMemsetAsync(c->d_hist, 0, 8ull * out->fragment_hist_len, st));
+            c->launches += launch_sample_histogram(a.sample_vals, take, c->d_hist, out->fragment_hist_len, st);
+            CU_TRY(cudaMemcpyAsync(out->fragment_hist, c->d_hist, 8ull * out->fragment_hist_len, cudaMemcpyDeviceToHost, st));
+            out->fragment_samples_taken = take;
+        }
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    if (err_flag) {
+        c->err = std::string("device table overflow:") + ((err_flag & 1) ? " fragment-tracker set" : "") +
+                 ((err_flag & 2) ? " mate table" : "") + ((err_flag & 4) ? " candidate list" : "") + " (raise rsq_config.max_records)";
+        return RSQ_ERR_CAPACITY;
+    }
+    return RSQ_OK;
+}
+
+int rsq_export_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !d_words || !n_words || !c->have_ann) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    c->launches += launch_pack_counts(c->acc, c->n_genes, c->n_exons, c->d_export, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *d_words = reinterpret_cast<uint64_t*>(c->d_export);
+    *n_words = c->export_words;
+    return RSQ_OK;
+}
+
+int rsq_import_counts(rsq_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    c->launches += launch_unpack_counts(c->acc, c->n_genes, c->n_exons, c->d_export, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return RSQ_OK;
+}
+
+int rsq_algorithmic_bytes(rsq_ctx* ctx, uint64_t* bytes) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !bytes || !c->have_ann) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaMemcpy(bytes, c->acc.algo_bytes, 8, cudaMemcpyDeviceToHost));
+    return RSQ_OK;
+}
+
+int rsq_launch_count(rsq_ctx* ctx, uint64_t* n) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !n) return RSQ_ERR_INVALID;
+    *n = c->launches;
+    return RSQ_OK;
+}
+
+int rsq_kernel_time_ms(rsq_ctx* ctx, double* ms) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !ms) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    double total = c->kernel_ms;
+    for (size_t k = 0; k < c->timers_used; ++k) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->timers[k].first, c->timers[k].second) == cudaSuccess) total += t;
+    }
+    *ms = total;
+    return RSQ_OK;
+}
+
+}  // extern "C"

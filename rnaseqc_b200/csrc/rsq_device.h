@@ -1,0 +1,103 @@
+// rsq_device.h — device-side views shared by the kernels (rsq_kernels.cu) and the C-ABI layer (rsq_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rsq_b200.h"
+
+namespace rsqd {
+
+// Exon metadata packed for one 128-bit load.
+struct __align__(16) ExonMeta {
+    uint32_t gene_flags;   // gene index in the low 24 bits, RSQ_EXON_* flags in the high 8
+    uint32_t slot;         // output slot (exonList order)
+    uint64_t cov_off;      // first base of this exon in the coverage array
+};
+
+// Annotation resident in HBM (replicated per GPU; <= ~10 MB at GENCODE scale, i.e. L2-resident).
+struct AnnView {
+    uint32_t n_contigs, n_genes, n_exons, n_segs;
+    const uint32_t* exon_off;     // [n_contigs+1]
+    const int2*     exon_se;      // [n_exons] (start, end), start-sorted per contig
+    const int32_t*  exon_pmax;    // [n_exons] running max of end within the contig (monotone)
+    const ExonMeta* exon_meta;    // [n_exons]
+    const uint32_t* seg_off;      // [n_contigs+1]
+    const int32_t*  seg_start;    // [n_segs]
+    const uint8_t*  seg_flags;    // [n_segs]
+    const uint8_t*  gene_flags;   // [n_genes]
+};
+
+struct BedView {
+    uint32_t n_intervals;
+    const uint32_t* off;          // [n_contigs+1]
+    const int2*     se;           // [n_intervals]
+    const int32_t*  pmax;         // [n_intervals]
+    const uint32_t* name_id;      // [n_intervals]
+    const uint8_t*  present;      // [n_contigs]
+};
+
+// One read that entered the fragment-size mate map (src/Expression.cpp:508-516), emitted by the hot kernel.
+struct __align__(16) PairCandidate {
+    unsigned long long name_hash;
+    uint32_t local_idx;    // record index inside the batch
+    uint32_t name_id;      // BED interval identity
+    int32_t  endpos;
+    uint32_t abs_isize;
+    uint32_t cond_ok;      // !MateReverse && Reverse && pos != mpos (src/Expression.cpp:528, minus the endpos test)
+    uint32_t slot;         // table slot, filled by the hot kernel
+};
+
+// Mutable accumulators in HBM.
+struct Accum {
+    unsigned long long* counters;        // [RSQ_N_COUNTERS]
+    unsigned long long* gene_reads;      // [n_genes]
+    unsigned long long* gene_unique;
+    unsigned long long* gene_fragments;
+    unsigned long long* exon_whole;      // [n_exons] by slot
+    unsigned long long* exon_frac;       // [n_exons] by slot, units of 2^-64
+    unsigned int*       cov_diff;        // [cov_len+1] coverage difference array (wrapping u32)
+    unsigned long long* frag_set;        // fragment-tracker hash set (open addressing), 0 = empty
+    unsigned long long  frag_mask;       // capacity-1
+    unsigned long long* algo_bytes;      // [1]
+    unsigned int*       error_flag;      // [1] bit0: fragment set full, bit1: pair table full, bit2: candidate list full
+    // fragment-size sampler (BED mode)
+    unsigned long long* pair_keys;       // mate map keys (name hash, 0 = empty)
+    unsigned long long* pair_first;      // global record index of the FIRST candidate with this name (atomicMin)
+    unsigned long long* pair_payload;    // (name_id << 32) | (uint32)endpos of that first candidate
+    unsigned long long  pair_mask;
+    PairCandidate*      cand;            // per-batch candidate list
+    unsigned int*       cand_count;      // [1]
+    unsigned int        cand_capacity;
+    unsigned char*      sample_flag;     // [batch capacity] 1 = this record completes a sample
+    unsigned int*       sample_isize;    // [batch capacity]
+    unsigned int*       sample_vals;     // [fragment_samples] |isize| of the k-th sample in stream order
+    unsigned long long* sample_count;    // [1] samples found so far (may exceed fragment_samples)
+};
+
+struct Params {
+    uint32_t mapq_threshold, base_mismatch_threshold;
+    int32_t  chimeric_distance;
+    uint32_t strand_mode, unpaired, exclude_chimeric, n_filter_tags, collect_coverage;
+    uint32_t bed_enabled;
+    uint32_t fragment_samples;
+    unsigned long long record_base;      // global index of reads[0] in the stream (ordering of fragment samples)
+};
+
+// launchers (rsq_kernels.cu); every launcher returns the number of kernels it launched
+int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann,
+                    const BedView& bed, const Accum& acc, const Params& prm, cudaStream_t stream);
+int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
+int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned long long n, unsigned int* block_sums,
+                         cudaStream_t stream);
+size_t coverage_scan_scratch_elems(unsigned long long n);
+int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap, unsigned long long* new_tab,
+                  unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream);
+int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* out, cudaStream_t stream);
+int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* in, cudaStream_t stream);
+// BED mode, after launch_hot_path of the same batch: owners publish, seconds test, samples are ranked in stream order
+int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsigned int* scan_scratch, cudaStream_t stream);
+size_t pair_scan_scratch_elems(size_t n_reads);
+int launch_sample_histogram(const unsigned int* vals, unsigned long long n, unsigned long long* hist, unsigned long long hist_len,
+                            cudaStream_t stream);
+
+}  // namespace rsqd

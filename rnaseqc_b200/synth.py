@@ -211,8 +211,20 @@ def _splitmix64(x: torch.Tensor) -> torch.Tensor:
     return x ^ srl(x, 31)
 
 
+def gene_weights(ann: SynthAnnotation, seed: int = 20260925) -> np.ndarray:
+    """Sampling weight of every gene: log-normal expression (sigma 2) x usable transcript length."""
+    ex_len = ann.exon_end - ann.exon_start + 1
+    ex_cum = np.concatenate([[0], np.cumsum(ex_len)])
+    t_len = ex_cum[ann.gene_exon_off[1:]] - ex_cum[ann.gene_exon_off[:-1]]
+    expr = np.exp(np.random.default_rng(seed + 1).normal(0.0, 2.0, size=ann.n_genes))
+    return expr * np.maximum(t_len - 150, 0)
+
+
 def simulate_reads(ann: SynthAnnotation, n_records: int, seed: int = 20260925, device: str = "cpu",
-                   genomic_frac: float = 0.15, sort: bool = True) -> SynthReads:
+                   genomic_frac: float = 0.15, sort: bool = True, dup_frac: float = 0.05,
+                   region: Optional[dict] = None, name_base: int = 0, weight_seed: int = 20260925) -> SynthReads:
+    """region (multi-GPU, rnaseqc_b200.shard.rank_region): {"gene_lo", "gene_hi", "lin_lo", "lin_hi"} restricts the
+    draw to one coordinate slice of the genome; name_base offsets the pair ids so read names stay unique."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -224,9 +236,14 @@ def simulate_reads(ann: SynthAnnotation, n_records: int, seed: int = 20260925, d
     ex_len_np = (ann.exon_end - ann.exon_start + 1)
     ex_cum_np = np.concatenate([[0], np.cumsum(ex_len_np)])            # global stitched coordinate of every exon
     t_len_np = ex_cum_np[ann.gene_exon_off[1:]] - ex_cum_np[ann.gene_exon_off[:-1]]
-    rng = np.random.default_rng(seed + 1)
-    expr = np.exp(rng.normal(0.0, 2.0, size=ann.n_genes))
-    w = expr * np.maximum(t_len_np - 150, 0)                            # genes shorter than a read get no fragments
+    w = gene_weights(ann, weight_seed)                                  # genes shorter than a read get no fragments
+    if region is not None:
+        mask = np.zeros(ann.n_genes, bool)
+        mask[region["gene_lo"]:region["gene_hi"]] = True
+        w = np.where(mask, w, 0.0)
+    if w.sum() <= 0:
+        w = np.ones(ann.n_genes)
+        genomic_frac = 1.0
     w = w / w.sum()
     ex_start = torch.from_numpy(ann.exon_start).to(dev)
     ex_cum = torch.from_numpy(ex_cum_np).to(dev)
@@ -269,11 +286,17 @@ def simulate_reads(ann: SynthAnnotation, n_records: int, seed: int = 20260925, d
     rs, rl, rnb = project(fstart + flen - 150, 150)
     # ---- genomic fragments ----------------------------------------------------------------------------------------
     clen = torch.tensor(ann.contig_lens, dtype=torch.float64, device=dev)
-    ccum = torch.cumsum(clen / clen.sum(), 0)
-    gc = torch.searchsorted(ccum, rand(n_pairs).double()).clamp_(max=len(ann.contig_lens) - 1)
+    coff = torch.cumsum(clen, 0) - clen                                  # linear genome coordinate of every contig start
+    lin_lo = float(region["lin_lo"]) if region is not None else 0.0
+    lin_hi = float(region["lin_hi"]) if region is not None else float(clen.sum().item())
+    lin = lin_lo + rand(n_pairs).double() * max(lin_hi - lin_lo - 1.0, 1.0)
+    gc = (torch.searchsorted(coff, lin, right=True) - 1).clamp_(min=0, max=len(ann.contig_lens) - 1)
     gflen = (250.0 + 60.0 * randn(n_pairs)).round().long().clamp_(min=150)
-    room = (clen[gc] - gflen.double() - 2000).clamp_(min=1.0)
-    gpos = (1000 + rand(n_pairs).double() * room).long()
+    gpos = (lin - coff[gc]).long()
+    gpos = torch.minimum(gpos, (clen[gc] - gflen.double() - 1000).long()).clamp_(min=1000)
+    if region is not None:   # keep the fragment inside the slice (slices are cut where no gene lies)
+        gpos = torch.minimum(gpos, (lin_hi - coff[gc] - gflen.double() - 10).long()).clamp_(min=1)
+        gpos = torch.maximum(gpos, (lin_lo - coff[gc]).long().clamp_(min=1))
     gi = is_genomic
     ls[gi] = 0; ll[gi] = 0; rs[gi] = 0; rl[gi] = 0
     ls[gi, 0] = gpos[gi]; ll[gi, 0] = 150
@@ -285,10 +308,10 @@ def simulate_reads(ann: SynthAnnotation, n_records: int, seed: int = 20260925, d
 
     # ---- pair-level attributes ------------------------------------------------------------------------------------
     read1_left = rand(n_pairs) < 0.5
-    dup = rand(n_pairs) < 0.05
+    dup = rand(n_pairs) < dup_frac
     mate_unmapped = rand(n_pairs) < 0.01
     mate_elsewhere = (rand(n_pairs) < 0.003) & ~mate_unmapped
-    pair_id = torch.arange(n_pairs, device=dev, dtype=torch.int64)
+    pair_id = torch.arange(n_pairs, device=dev, dtype=torch.int64) + name_base
 
     def side(starts, lens, nb, is_left):
         n = n_pairs
@@ -372,15 +395,26 @@ def simulate_reads(ann: SynthAnnotation, n_records: int, seed: int = 20260925, d
     nb = torch.where(ins | dele, 2, nb)
     l_qseq = torch.full((n,), 150, dtype=torch.int64, device=dev)
 
-    if sort:
-        key = contig * (1 << 32) + pos
-        order = torch.argsort(key, stable=True)
-        contig, pos, mpos, endp, isize, flag, mapq, nm, aux, name_id, nb, lead_soft, ins_len, mate_contig, l_qseq = [
-            t[order] for t in (contig, pos, mpos, endp, isize, flag, mapq, nm, aux, name_id, nb, lead_soft, ins_len, mate_contig, l_qseq)]
-        bs, bl = bs[order], bl[order]
     i32 = lambda t: t.to(torch.int32)
-    return SynthReads(n, i32(contig), i32(pos), i32(mpos), i32(endp), i32(isize), i32(l_qseq), i32(nm), i32(flag), i32(mapq),
-                      i32(aux), name_id, i32(nb), i32(bs), i32(bl), i32(lead_soft), i32(ins_len), i32(mate_contig))
+    out = SynthReads(n, i32(contig), i32(pos), i32(mpos), i32(endp), i32(isize), i32(l_qseq), i32(nm), i32(flag), i32(mapq),
+                     i32(aux), name_id, i32(nb), i32(bs), i32(bl), i32(lead_soft), i32(ins_len), i32(mate_contig))
+    return sort_reads(out) if sort else out
+
+
+_FIELDS = ["contig", "pos", "mpos", "endpos", "isize", "l_qseq", "nm", "flag", "mapq", "aux", "name_id", "n_blocks",
+           "blk_start", "blk_len", "lead_soft", "ins_len", "mate_contig"]
+
+
+def sort_reads(r: SynthReads) -> SynthReads:
+    """stable sort by (contig, pos): coordinate order, as a BAM would be"""
+    key = r.contig.long() * (1 << 32) + r.pos.long()
+    order = torch.argsort(key, stable=True)
+    del key
+    return SynthReads(r.n, **{f: getattr(r, f)[order] for f in _FIELDS})
+
+
+def concat(parts: List[SynthReads]) -> SynthReads:
+    return SynthReads(sum(p.n for p in parts), **{f: torch.cat([getattr(p, f) for p in parts]) for f in _FIELDS})
 
 
 def pack(reads: SynthReads, contig_index: Optional[List[int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -470,3 +504,26 @@ def write_sam(ann: SynthAnnotation, reads: SynthReads, path: str, chimeric_tag: 
                 tags.append(f"{chimeric_tag}:A:1")
             f.write(f"r{name[i]}\t{flag[i]}\t{ann.contig_names[contig[i]]}\t{pos[i] + 1}\t{mapq[i]}\t{cigar}\t{rnext}\t{mpos[i] + 1}\t{isize[i]}\t{seq}\t{qual}"
                     + ("\t" + "\t".join(tags) if tags else "") + "\n")
+
+
+def write_bam(ann: SynthAnnotation, reads: SynthReads, path: str, level: int = 1) -> None:
+    """BAM of the records through the C++ writer in librsq_host.so (fast enough for multi-million-record samples)."""
+    import ctypes as C
+    from . import api
+    H = api.host_lib()
+    c = lambda t: np.ascontiguousarray(t.cpu().numpy().astype(np.int32))
+    names = (C.c_char_p * len(ann.contig_names))(*[n.encode() for n in ann.contig_names])
+    lens = np.asarray(ann.contig_lens, np.int64)
+    arrs = dict(tid=c(reads.contig), pos=c(reads.pos), mtid=c(reads.mate_contig), mpos=c(reads.mpos), isize=c(reads.isize),
+                flag=c(reads.flag), mapq=c(reads.mapq), nm=c(reads.nm), aux=c(reads.aux), nb=c(reads.n_blocks),
+                bs=c(reads.blk_start), bl=c(reads.blk_len), ls=c(reads.lead_soft), il=c(reads.ins_len))
+    name_id = np.ascontiguousarray(reads.name_id.cpu().numpy().astype(np.int64))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    H.rsqh_write_bam.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_size_t] + [C.c_void_p] * 13 + \
+        [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    rc = H.rsqh_write_bam(path.encode(), len(ann.contig_names), names, p(lens), reads.n, p(arrs["tid"]), p(arrs["pos"]),
+                          p(arrs["mtid"]), p(arrs["mpos"]), p(arrs["isize"]), p(arrs["flag"]), p(arrs["mapq"]), p(arrs["nm"]),
+                          p(arrs["aux"]), p(name_id), p(arrs["nb"]), p(arrs["bs"]), p(arrs["bl"]), reads.blk_start.shape[1],
+                          p(arrs["ls"]), p(arrs["il"]), 150, level)
+    if rc != 0:
+        raise RuntimeError(f"rsqh_write_bam failed: {rc}")

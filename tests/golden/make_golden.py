@@ -1,0 +1,200 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures from the UNMODIFIED reference binary (oracle/_ref/rnaseqc, built by
+`make ref` from /root/reference).  Run in the build container only; the GPU box uses the committed files.
+
+    python tests/golden/make_golden.py
+
+Cases
+  synth_small : seeded synthetic annotation (90 genes / 3 contigs incl. a tiny chrM) + 30 k 150 bp PE records from
+                rnaseqc_b200.synth; reference run with --coverage --bed.
+  kat         : hand-written known-answer GTF + SAM, one read (pair) per quirk listed in SURVEY.md §8c; reference run
+                under several flag sets (default, --stranded rf/fr, -u, --exclude-chimeric, -t XS, --rpkm -s).
+"""
+import gzip
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.path.join(ROOT, "oracle", "_ref", "rnaseqc")
+
+KAT_FLAGSETS = {
+    "default": ["--coverage"],
+    "stranded_rf": ["--stranded", "rf"],
+    "stranded_fr": ["--stranded", "fr"],
+    "unpaired": ["-u"],
+    "exclude_chimeric": ["--exclude-chimeric"],
+    "tag_filter": ["-t", "XS", "-t", "XT"],
+    "rpkm_sample": ["--rpkm", "-s", "mysample", "-q", "3", "--base-mismatch", "2", "--chimeric-distance", "1000"],
+}
+SYNTH_FLAGSETS = {"coverage_bed": ["--coverage", "--bed", "a.bed"]}
+
+
+def run_ref(gtf, sam, out, flags, cwd):
+    shutil.rmtree(out, ignore_errors=True)
+    p = subprocess.run([REF, gtf, sam, out] + flags, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if p.returncode != 0:
+        raise SystemExit(f"reference failed ({p.returncode}): {p.stderr}")
+
+
+def make_synth_small():
+    from rnaseqc_b200 import synth
+    d = os.path.join(HERE, "synth_small")
+    os.makedirs(d, exist_ok=True)
+    ann = synth.make_annotation(seed=31, n_genes=90, contig_names=["chr1", "chr2", "chrM"], contig_lens=[12_000_000, 8_000_000, 16569])
+    synth.write_gtf(ann, os.path.join(d, "a.gtf"))
+    synth.write_bed(ann, os.path.join(d, "a.bed"), min_len=400)
+    reads = synth.simulate_reads(ann, 30000, seed=32)
+    sam = os.path.join(d, "a.sam")
+    synth.write_sam(ann, reads, sam)
+    for name, flags in SYNTH_FLAGSETS.items():
+        run_ref("a.gtf", "a.sam", os.path.join("expected", name), flags, d)
+    with open(sam, "rb") as fi, gzip.open(sam + ".gz", "wb", compresslevel=9) as fo:
+        shutil.copyfileobj(fi, fo)
+    os.remove(sam)
+
+
+GTF_ATTR = 'gene_id "{g}"; transcript_id "{g}"; gene_type "{t}"; gene_name "{n}"; transcript_type "{t}";'
+
+
+def kat_gtf():
+    L = ["##kat annotation"]
+
+    def gene(chrom, gid, name, strand, exons, ttype="protein_coding", exon_ids=True, omit_ttype=False):
+        s, e = min(x[0] for x in exons), max(x[1] for x in exons)
+        attr = GTF_ATTR.format(g=gid, t=ttype, n=name)
+        if omit_ttype:
+            attr = f'gene_id "{gid}"; transcript_id "{gid}"; gene_name "{name}";'
+        L.append(f"{chrom}\tkat\tgene\t{s}\t{e}\t.\t{strand}\t.\t{attr}")
+        L.append(f"{chrom}\tkat\ttranscript\t{s}\t{e}\t.\t{strand}\t.\t{attr}")
+        for k, (a, b) in enumerate(exons):
+            ex = f' exon_id "{gid}_{k + 1}";' if exon_ids else ""
+            L.append(f"{chrom}\tkat\texon\t{a}\t{b}\t.\t{strand}\t.\t{attr}{ex}")
+
+    gene("chrA", "GA", "GeneA", "+", [(1000, 1199), (2000, 2199), (3000, 3499)])
+    gene("chrA", "GB", "GeneB", "-", [(2100, 2600)])
+    gene("chrA", "GC", "GeneC", "+", [(10000, 10999), (12000, 14000)])
+    gene("chrA", "GD", "HBB", "-", [(20000, 20500)])
+    gene("chrA", "GE", "Ribo", "+", [(30000, 30300)], ttype="rRNA")
+    gene("chrA", "GF", "CarryOver", "+", [(31000, 31400)], omit_ttype=True)   # inherits transcript_type "rRNA" (GTF.cpp:110)
+    gene("chrA", "GH", "Unnamed", "-", [(40000, 40200), (40500, 40800)], exon_ids=False)
+    gene("chrA", "GI", "Dot", ".", [(50000, 50400)])
+    gene("chrA", "GJ", "Short", "+", [(60000, 60150)])
+    gene("chrA", "GK", "FarAway", "+", [(3000000, 3000500)])
+    gene("chrB", "GL", "OnB", "+", [(500, 900), (1500, 2500)])
+    gene("chrC", "GM", "NoReads", "-", [(100, 2000)])
+    return "\n".join(L) + "\n"
+
+
+def kat_sam():
+    H = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:chrA\tLN:5000000", "@SQ\tSN:chrB\tLN:100000", "@SQ\tSN:chrZ\tLN:100000"]
+    R = []
+    n = [0]
+
+    def rd(chrom, pos, cigar, flag=99, mapq=255, nm=0, lq=150, rnext="=", pnext=None, tlen=300, tags=(), name=None):
+        n[0] += 1
+        name = name or f"k{n[0]}"
+        pnext = pos + 150 if pnext is None else pnext
+        seq = "*" if lq == 0 else "A" * lq
+        qual = "*" if lq == 0 else "F" * lq
+        t = list(tags)
+        if nm is not None:
+            t.insert(0, f"NM:i:{nm}")
+        R.append((chrom, pos, "\t".join([name, str(flag), chrom, str(pos), str(mapq), cigar, rnext, str(pnext), str(tlen), seq, qual] + t)))
+
+    # --- chrA, GeneA/GeneB --------------------------------------------------------------------------------------
+    rd("chrA", 850, "150M")                       # ends at 999: overhang-by-one vs exon@1000 -> Ambiguous
+    rd("chrA", 1010, "150M")                      # fully inside exon 1
+    rd("chrA", 1100, "150M")                      # partial overlap -> Ambiguous
+    rd("chrA", 1100, "100M800N50M")               # spliced exon1 -> exon2, fractions 100/150 + 50/150
+    rd("chrA", 1100, "100M800N50M", flag=147, name="k4")   # its mate: same qname -> one fragment
+    rd("chrA", 1150, "50M1800N100M")              # exon1 -> exon3, skipping exon2
+    rd("chrA", 1300, "150M")                      # intron of GeneA
+    rd("chrA", 2120, "50M", lq=50)                # inside GeneA exon2 AND GeneB exon: both genes counted
+    rd("chrA", 2120, "50M", lq=50, flag=147)      # same, reverse strand second mate
+    rd("chrA", 2300, "100M", lq=100)              # GeneB exon only (GeneA intron)
+    rd("chrA", 2150, "100M", lq=100)              # spans GeneA exon2 end: partial for A, full for B
+    rd("chrA", 3010, "70M2I78M")                  # insertion: two abutting blocks in one exon
+    rd("chrA", 3010, "70M2D80M", lq=150)          # deletion
+    rd("chrA", 3020, "10S140M")                   # soft clip
+    rd("chrA", 3030, "50=1X99=")                  # = and X ops
+    rd("chrA", 3040, "5H145M", lq=145)            # hard clip
+    rd("chrA", 3050, "20S30I", lq=50)             # no aligned block at all
+    rd("chrA", 3060, "150M", nm=None)             # NM absent
+    rd("chrA", 3070, "150M", nm=7)                # too many mismatches -> low quality
+    rd("chrA", 3080, "150M", mapq=3)              # low MAPQ
+    rd("chrA", 3090, "150M", flag=99 | 0x100, mapq=0)     # secondary + low MAPQ (both counted)
+    rd("chrA", 3100, "150M", flag=99 | 0x800)             # supplementary without ch -> Chimeric auto
+    rd("chrA", 3110, "150M", flag=99 | 0x800, tags=["ch:A:1"])   # supplementary with ch
+    rd("chrA", 3120, "150M", flag=99 | 0x200)             # QC fail
+    rd("chrA", 3130, "150M", flag=99 | 0x400)             # duplicate
+    rd("chrA", 3130, "150M", flag=147 | 0x400, name="k25")
+    rd("chrA", 3140, "150M", flag=0)                      # unpaired
+    rd("chrA", 3150, "150M", flag=73, pnext=3150, tlen=0)  # mate unmapped (0x8)
+    rd("chrA", 3160, "150M", flag=97, rnext="chrB", pnext=700, tlen=0)   # mate on another contig
+    rd("chrA", 3170, "150M", flag=97, pnext=4000000, tlen=0)             # mate too far
+    rd("chrA", 3180, "150M", tags=["ch:Z:chimera"])        # STAR chimeric tag, first mate
+    rd("chrA", 3190, "150M", flag=147, tags=["ch:A:1"])    # chimeric tag on second mate
+    rd("chrA", 3200, "150M", tags=["XS:i:1"])              # user filter tag (int)
+    rd("chrA", 3210, "150M", tags=["XT:Z:foo"])            # user filter tag (string)
+    rd("chrA", 3220, "150M", tags=["XS:A:+"])              # type A is not seen by GetTag
+    rd("chrA", 3230, "150M", tags=["XS:f:1.5"])            # float is
+    rd("chrA", 3240, "150M", flag=83)                      # reverse first mate
+    rd("chrA", 3250, "150M", flag=163)                     # forward second mate
+    rd("chrA", 3300, "100M", lq=100)                       # shorter read
+    rd("chrA", 3300, "60M6600N40M", lq=100)                # long span with short length: Read Length quirk; 2nd block in GeneC
+    # --- GeneC: deep coverage for the bias / mask paths --------------------------------------------------------------
+    for k in range(1400):
+        p = 10000 + (k * 7) % 840
+        rd("chrA", p, "150M", flag=99 if k % 2 == 0 else 147, name=f"c{k // 2}")
+    for k in range(1100):
+        p = 12000 + (k * 13) % 1840
+        rd("chrA", p, "150M", flag=83 if k % 2 == 0 else 163, name=f"d{k // 2}")
+    rd("chrA", 10900, "100M1000N50M")             # junction of GeneC
+    # --- other genes ----------------------------------------------------------------------------------------------------------
+    rd("chrA", 20100, "150M")                     # globin
+    rd("chrA", 20100, "150M", flag=147 | 0x400)   # globin duplicate
+    rd("chrA", 30050, "150M")                     # rRNA
+    rd("chrA", 31100, "150M")                     # rRNA by carry-over
+    rd("chrA", 40010, "150M", flag=83)            # unnamed exons
+    rd("chrA", 40100, "100M300N50M", flag=163)
+    rd("chrA", 50100, "150M")                     # gene with strand '.'
+    rd("chrA", 60000, "150M")                     # gene shorter than 200 bp (bias skip), exactly exon-sized
+    rd("chrA", 70000, "150M")                     # intergenic
+    rd("chrA", 3000100, "150M")                   # far away gene (chimeric distance tests)
+    # --- chrB, then chrZ (not in the GTF), then back to chrA (its features were dropped) ------------------------------------
+    rd("chrB", 600, "150M")
+    rd("chrB", 800, "100M600N50M")
+    rd("chrB", 1600, "150M", flag=147)
+    rd("chrZ", 100, "150M")
+    # unmapped, no contig
+    R.sort(key=lambda x: ({"chrA": 0, "chrB": 1, "chrZ": 2}[x[0]], x[1]))
+    lines = H + [x[2] for x in R]
+    lines.append("\t".join(["back1", "99", "chrA", "1010", "255", "150M", "=", "1160", "300", "A" * 150, "F" * 150, "NM:i:0"]))
+    lines.append("\t".join(["u1", "77", "*", "0", "0", "*", "*", "0", "0", "A" * 150, "F" * 150]))
+    lines.append("\t".join(["u1", "141", "*", "0", "0", "*", "*", "0", "0", "A" * 150, "F" * 150]))
+    return "\n".join(lines) + "\n"
+
+
+def make_kat():
+    d = os.path.join(HERE, "kat")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "kat.gtf"), "w").write(kat_gtf())
+    sam = os.path.join(d, "kat.sam")
+    open(sam, "w").write(kat_sam())
+    for name, flags in KAT_FLAGSETS.items():
+        run_ref("kat.gtf", "kat.sam", os.path.join("expected", name), flags, d)
+    with open(sam, "rb") as fi, gzip.open(sam + ".gz", "wb", compresslevel=9) as fo:
+        shutil.copyfileobj(fi, fo)
+    os.remove(sam)
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF):
+        raise SystemExit("build the reference first: make ref")
+    make_synth_small()
+    make_kat()
+    print("golden fixtures written under", HERE)

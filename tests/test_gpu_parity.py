@@ -1,0 +1,156 @@
+"""GPU tests (`-m gpu`): the CUDA hot path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs (bit-exact: counters, gene tables, exact Q64.64 exon sums, per-base coverage, fragment-size histogram) and
+against the golden outputs of the unmodified reference binary."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from util import assert_results_equal, compare_outputs, run_cli, unpack_case
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_golden import KAT_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(api, lib, ann, reads, blocks, cfg, chunks=1):
+    ctx = api.Backend(lib).create(cfg)
+    ctx.set_annotation(ann)
+    n = len(reads)
+    bounds = [n * k // chunks for k in range(chunks + 1)]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if a == b:
+            continue
+        r = reads[a:b].copy()
+        b0 = int(r["block_off"][0])
+        b1 = int(r["block_off"][-1]) + int(r["n_blocks"][-1])
+        r["block_off"] -= b0
+        ctx.submit(r, blocks[b0:b1].copy())
+    ctx.sync()
+    res = ctx.finalize()
+    nbytes = ctx.algorithmic_bytes()
+    ctx.close()
+    return res, nbytes
+
+
+@pytest.fixture(scope="module")
+def synth_case(libs, tmp_path_factory):
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    d = str(tmp_path_factory.mktemp("synth"))
+    sa = synth.make_annotation(seed=101, n_genes=400, contig_names=["chr1", "chr2", "chr3", "chrM"],
+                               contig_lens=[40_000_000, 30_000_000, 20_000_000, 16569])
+    synth.write_gtf(sa, os.path.join(d, "a.gtf"))
+    synth.write_bed(sa, os.path.join(d, "a.bed"), min_len=400)
+    ann = api.Annotation(os.path.join(d, "a.gtf"), os.path.join(d, "a.bed"))
+    sr = synth.simulate_reads(sa, 400000, seed=102)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    return ann, reads, blocks
+
+
+CONFIGS = {
+    "default": dict(),
+    "bed": dict(fragment_samples=1000000),
+    "bed_few_samples": dict(fragment_samples=777),
+    "stranded_fr": dict(strand_mode=1),
+    "stranded_rf": dict(strand_mode=2),
+    "unpaired": dict(unpaired=True),
+    "exclude_chimeric": dict(exclude_chimeric=True),
+    "loose": dict(mapq=3, mismatches=2, chimeric_distance=1000),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_cuda_matches_oracle_on_synthetic_records(libs, synth_case, name):
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    cfg = lambda: api.make_config(max_records=len(reads), **CONFIGS[name])
+    want, want_bytes = _run(api, libs["oracle"], ann, reads, blocks, cfg())
+    got, got_bytes = _run(api, libs["product"], ann, reads, blocks, cfg())
+    assert_results_equal(got, want, name)
+    assert got_bytes == want_bytes
+    assert want.counter("Exonic Reads") > 100000 and want.gene_reads.sum() > 100000
+    if "bed" in name:
+        assert want.fragment_samples_taken > 0
+
+
+def test_batching_does_not_change_results(libs, synth_case):
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    one, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(fragment_samples=5000, max_records=len(reads)))
+    many, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(fragment_samples=5000, max_records=1000), chunks=7)
+    assert_results_equal(many, one, "7 submits vs 1")
+
+
+def test_filter_tags_and_aux_bits(libs, synth_case):
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    r = reads.copy()
+    rng = np.random.default_rng(5)
+    r["filter_mask"] = (rng.random(len(r)) < 0.05) * rng.integers(1, 4, len(r))
+    r["aux"] |= ((rng.random(len(r)) < 0.01) * 0x08).astype(np.uint8)     # tid out of range
+    r["aux"] |= ((rng.random(len(r)) < 0.02) * 0x10).astype(np.uint8)     # contig already dropped
+    r["contig"][rng.random(len(r)) < 0.01] = -1
+    cfg = lambda: api.make_config(n_filter_tags=2, max_records=len(r))
+    want, _ = _run(api, libs["oracle"], ann, r, blocks, cfg())
+    got, _ = _run(api, libs["product"], ann, r, blocks, cfg())
+    assert_results_equal(got, want, "filter tags")
+    assert want.counters[api.COUNTER_INDEX["Filtered by tag 0"]] > 0
+
+
+def test_empty_and_tiny_batches(libs, synth_case):
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    ctx = api.Backend(libs["product"]).create(api.make_config())
+    ctx.set_annotation(ann)
+    ctx.submit(reads[:0].copy(), blocks[:0].copy())
+    res = ctx.finalize()
+    assert res.counters.sum() == 0 and res.gene_reads.sum() == 0
+    want, _ = _run(api, libs["oracle"], ann, reads[:33], blocks, api.make_config())
+    got, _ = _run(api, libs["product"], ann, reads[:33], blocks, api.make_config())
+    assert_results_equal(got, want, "33 reads")
+    # reset gives a clean slate
+    ctx.submit(reads[:1000].copy(), blocks)
+    ctx.reset()
+    ctx.submit(reads[:33].copy(), blocks)
+    assert_results_equal(ctx.finalize(), want, "after reset")
+
+
+@pytest.mark.parametrize("flagset", sorted(KAT_FLAGSETS))
+def test_kat_product_cli_matches_reference(libs, tmp_path, flagset):
+    d = unpack_case("kat", tmp_path)
+    out = os.path.join(d, "out_" + flagset)
+    run_cli(libs["cli"], os.path.join(d, "kat.gtf"), os.path.join(d, "kat.sam"), out, *KAT_FLAGSETS[flagset])
+    names = set(compare_outputs(os.path.join(d, "expected", flagset), out))
+    assert any(n.endswith("gene_reads.gct") for n in names) and any(n.endswith("metrics.tsv") for n in names), names
+
+
+@pytest.mark.parametrize("flagset", sorted(SYNTH_FLAGSETS))
+def test_synth_small_product_cli_matches_reference(libs, tmp_path, flagset):
+    d = unpack_case("synth_small", tmp_path)
+    out = os.path.join(d, "out_" + flagset)
+    flags = [f if f != "a.bed" else os.path.join(d, "a.bed") for f in SYNTH_FLAGSETS[flagset]]
+    run_cli(libs["cli"], os.path.join(d, "a.gtf"), os.path.join(d, "a.sam"), out, *flags)
+    identical = set(compare_outputs(os.path.join(d, "expected", flagset), out))
+    assert {"a.sam.gene_reads.gct", "a.sam.gene_fragments.gct", "a.sam.metrics.tsv", "a.sam.fragmentSizes.txt"} <= identical, identical
+
+
+def test_device_resident_submit_and_export_roundtrip(libs, synth_case):
+    import torch
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    want, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=len(reads)))
+    ctx = api.Backend(libs["product"]).create(api.make_config(max_records=len(reads)))
+    ctx.set_annotation(ann)
+    dr = torch.from_numpy(reads.view(np.uint8).reshape(-1, 48)).cuda()
+    db = torch.from_numpy(blocks.view(np.int32).reshape(-1, 2)).cuda()
+    ctx.submit_device(dr.data_ptr(), len(reads), db.data_ptr(), len(blocks))
+    ptr, n = ctx.export_counts()
+    assert n == api.RSQ_N_COUNTERS + 3 * ann.n_genes + 3 * ann.n_exons
+    ctx.import_counts()           # identity round trip through the all-reduce layout
+    got = ctx.finalize()
+    assert_results_equal(got, want, "device submit + export/import")
+    assert ctx.launch_count() > 0 and ctx.kernel_time_ms() > 0
