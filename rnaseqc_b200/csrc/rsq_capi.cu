@@ -147,8 +147,32 @@ int ensure_frag_capacity(Ctx* c, size_t n) {
     return RSQ_OK;
 }
 
+// grows the mate map (BED mode) so that the records seen so far + n fit at load <= 3/4 even if every record
+// carried a distinct candidate name
+int ensure_pair_capacity(Ctx* c, size_t n) {
+    if (!(c->have_bed && c->cfg.fragment_samples)) return RSQ_OK;
+    const unsigned long long need = c->records_submitted + n;
+    if (need <= c->pair_cap / 4 * 3) return RSQ_OK;
+    const unsigned long long new_cap = next_pow2(need / 3 * 4 + 4);
+    unsigned long long *nk = nullptr, *nf = nullptr, *np = nullptr;
+    CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
+    CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
+    CU_TRY(cudaMalloc(&np, 8ull * new_cap));
+    CU_TRY(cudaMemsetAsync(nk, 0, 8ull * new_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(nf, 0xff, 8ull * new_cap, c->stream));
+    c->launches += launch_pair_rehash(c->acc, c->pair_cap, nk, nf, np, new_cap - 1, c->acc.error_flag, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->acc.pair_keys); cudaFree(c->acc.pair_first); cudaFree(c->acc.pair_payload);
+    c->acc.pair_keys = nk; c->acc.pair_first = nf; c->acc.pair_payload = np;
+    c->acc.pair_mask = new_cap - 1;
+    c->pair_cap = new_cap;
+    return RSQ_OK;
+}
+
 int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks, size_t n_blocks) {
     int rc = ensure_frag_capacity(c, n_reads);
+    if (rc != RSQ_OK) return rc;
+    rc = ensure_pair_capacity(c, n_reads);
     if (rc != RSQ_OK) return rc;
     rc = ensure_bed_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
@@ -296,6 +320,23 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     c->ann_allocs.push_back(pmax);
     c->launches += launch_prefix_max(v.exon_se, v.exon_off, a->n_contigs, pmax, c->stream);
     v.exon_pmax = pmax;
+    // direct-address bucket index over each contig's annotated span
+    {
+        std::vector<uint32_t> boff(a->n_contigs + 1, 0);
+        for (uint32_t k = 0; k < a->n_contigs; ++k) {
+            int64_t mx = 0;
+            for (uint32_t i = a->exon_off[k]; i < a->exon_off[k + 1]; ++i) mx = std::max<int64_t>(mx, a->exon_end[i]);
+            for (uint32_t i = a->seg_off[k]; i < a->seg_off[k + 1]; ++i) mx = std::max<int64_t>(mx, a->seg_start[i]);
+            boff[k + 1] = boff[k] + (uint32_t)(mx >> kBucketShift) + 2u;
+        }
+        if ((rc = upload(c, c->ann_allocs, boff.data(), boff.size(), &v.bucket_off))) return rc;
+        int4* buckets = nullptr;
+        CU_TRY(cudaMalloc(&buckets, std::max<size_t>(boff.back(), 1) * sizeof(int4)));
+        c->ann_allocs.push_back(buckets);
+        v.buckets = buckets;
+        CU_TRY(cudaStreamSynchronize(c->stream));   // boff is a local
+        c->launches += launch_build_buckets(v, buckets, boff.back(), c->stream);
+    }
     // accumulators
     Accum& acc = c->acc;
     CU_TRY(cudaMalloc(&acc.counters, 8 * RSQ_N_COUNTERS));
@@ -346,7 +387,7 @@ int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* b) {
     c->have_bed = true;
     if (c->cfg.fragment_samples) {
         Accum& acc = c->acc;
-        c->pair_cap = next_pow2(c->cfg.max_records ? c->cfg.max_records : (1ull << 24));
+        c->pair_cap = next_pow2((c->cfg.max_records ? c->cfg.max_records : (1ull << 24)) / 3 * 4 + 4);
         CU_TRY(cudaMalloc(&acc.pair_keys, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_first, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_payload, 8ull * c->pair_cap));

@@ -25,7 +25,13 @@ struct AnnView {
     const int32_t*  seg_start;    // [n_segs]
     const uint8_t*  seg_flags;    // [n_segs]
     const uint8_t*  gene_flags;   // [n_genes]
+    // direct-address bucket index: bucket b of contig c covers coordinates [b << kBucketShift, (b+1) << kBucketShift)
+    const uint32_t* bucket_off;   // [n_contigs+1] first bucket of each contig
+    const int4*     buckets;      // per bucket: x = first exon with running-max end >= bucket start,
+                                  //             y = first exon with start >= bucket start,
+                                  //             z = last gene segment with start <= bucket start, w = unused
 };
+constexpr int kBucketShift = 10;
 
 struct BedView {
     uint32_t n_intervals;
@@ -87,6 +93,9 @@ struct Params {
 int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann,
                     const BedView& bed, const Accum& acc, const Params& prm, cudaStream_t stream);
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
+int launch_build_buckets(const AnnView& ann, int4* buckets, uint32_t n_buckets, cudaStream_t stream);
+int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,
+                       unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream);
 int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned long long n, unsigned int* block_sums,
                          cudaStream_t stream);
 size_t coverage_scan_scratch_elems(unsigned long long n);

@@ -86,11 +86,23 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
 
 struct Window { int lo, hi; };
 
-__device__ __forceinline__ Window exon_window(const AnnView& ann, int c_lo, int c_hi, int bs, int be) {
-    Window w;
-    w.hi = upper_bound_start(ann.exon_se, c_lo, c_hi, be);      // every i < hi has start <= block.end   (Expression.cpp:111)
-    w.lo = lower_bound_pmax(ann.exon_pmax, c_lo, w.hi, bs);     // nothing before lo can reach block.start (GTF.cpp:171-179)
+// Exon window of a block through the direct-address bucket index: two table reads (independent, issued together)
+// and two short forward scans replace two ~17-step dependent binary searches.
+__device__ __forceinline__ Window exon_window(const AnnView& ann, int c_lo, int c_hi, int bk_lo, int bk_n, int bs, int be) {
+    const int b0 = min(max(bs, 0) >> kBucketShift, bk_n - 1), b1 = min(max(be, 0) >> kBucketShift, bk_n - 1);
+    int lo = __ldg(&ann.buckets[bk_lo + b0].x);
+    int hi = __ldg(&ann.buckets[bk_lo + b1].y);
+    while (hi < c_hi && __ldg(&ann.exon_se[hi].x) <= be) ++hi;        // every i < hi has start <= block.end   (Expression.cpp:111)
+    while (lo < hi && __ldg(&ann.exon_pmax[lo]) < bs) ++lo;           // nothing before lo can reach block.start (GTF.cpp:171-179)
+    Window w; w.lo = lo; w.hi = hi;
     return w;
+}
+// last gene segment whose start <= bs
+__device__ __forceinline__ int seg_lookup(const AnnView& ann, int s_hi, int bk_lo, int bk_n, int bs) {
+    const int b0 = min(max(bs, 0) >> kBucketShift, bk_n - 1);
+    int k = __ldg(&ann.buckets[bk_lo + b0].z);
+    while (k + 1 < s_hi && __ldg(&ann.seg_start[k + 1]) <= bs) ++k;
+    return k;
 }
 
 // does block (bs, be) lie fully inside an exon of `gene` (strand-admissible)?  src/Expression.cpp:341-344
@@ -117,8 +129,28 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     if (threadIdx.x == 0) s_bytes = 0ull;
     __syncthreads();
 
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
+    const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+    const size_t n_tiles = (n_reads + 31) >> 5;
+    // Persistent warps: warp w of the grid takes 32-record tiles w, w + W, w + 2W, ... (records are coordinate
+    // sorted, so a tile touches a handful of neighbouring index entries).  No CTA barrier inside the loop.
+    size_t tile = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    if (tile < n_tiles && tile * 32 + lane < n_reads) {
+        const int4* rp = reinterpret_cast<const int4*>(reads + tile * 32 + lane);
+        q0 = __ldg(rp); q1 = __ldg(rp + 1); q2 = __ldg(rp + 2);
+    }
+  for (; tile < n_tiles; tile += warps_total) {
+    const size_t i = tile * 32 + lane;
+    // software pipeline: the next tile's records are requested before this tile is processed
+    int4 p0 = make_int4(0, 0, 0, 0), p1 = p0, p2 = p0;
+    {
+        const size_t nx = (tile + warps_total) * 32 + lane;
+        if (nx < n_reads) {
+            const int4* rp = reinterpret_cast<const int4*>(reads + nx);
+            p0 = __ldg(rp); p1 = __ldg(rp + 1); p2 = __ldg(rp + 2);
+        }
+    }
 
     unsigned long long cm = 0ull;       // bit k set: counter k += 1
     int v_mm1 = 0, v_b1 = 0, v_mm2 = 0, v_b2 = 0, v_mm = 0, v_tb = 0, v_nb = 0;
@@ -128,9 +160,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
 
 #define CNT(k) (cm |= 1ull << (k))
     if (i < n_reads) {
-        // ---- record: three 128-bit loads -------------------------------------------------------------------
-        const int4* rp = reinterpret_cast<const int4*>(reads + i);
-        const int4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2);
+        // ---- record: three 128-bit loads (issued one tile ahead) ------------------------------------------------
         const int pos = q0.x, mpos = q0.y, endpos = q0.z, isize = q0.w;
         const int l_qseq = q1.x, nm_raw = q1.y;
         const uint32_t w6 = (uint32_t)q1.z, w7 = (uint32_t)q1.w;
@@ -219,10 +249,11 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                 if ((prm.strand_mode == 1) != ((f & RSQ_F_READ1) != 0)) target = !target;
                 rstrand = target ? RSQ_STRAND_REV : RSQ_STRAND_FWD;
             }
-            int c_lo = 0, c_hi = 0, s_lo = 0, s_hi = 0;
+            int c_lo = 0, c_hi = 0, s_hi = 0, bk_lo = 0, bk_n = 1;
             if (!cleared) {
                 c_lo = (int)__ldg(&ann.exon_off[contig]); c_hi = (int)__ldg(&ann.exon_off[contig + 1]);
-                s_lo = (int)__ldg(&ann.seg_off[contig]);  s_hi = (int)__ldg(&ann.seg_off[contig + 1]);
+                s_hi = (int)__ldg(&ann.seg_off[contig + 1]);
+                bk_lo = (int)__ldg(&ann.bucket_off[contig]); bk_n = (int)__ldg(&ann.bucket_off[contig + 1]) - bk_lo;
             }
             bool intragenic = false, plus = false, minus = false, ribosomal = false, exonic = false, do_exon = false;
             uint32_t length = 0;                                                       // extractBlocks' return, :359
@@ -236,7 +267,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                 if (b == 0) { bs0 = bs; be0 = be; } else if (b == 1) { bs1 = bs; be1 = be; }
                 if (cleared) continue;
                 // Gene features: elementary segments overlapping [bs, be]  (:352-358)
-                for (int k = seg_find(ann.seg_start, s_lo, s_hi, bs); k < s_hi && __ldg(&ann.seg_start[k]) <= be; ++k) {
+                for (int k = seg_lookup(ann, s_hi, bk_lo, bk_n, bs); k < s_hi && __ldg(&ann.seg_start[k]) <= be; ++k) {
                     uint32_t fl = __ldg(&ann.seg_flags[k]);
                     if (rstrand != RSQ_STRAND_UNKNOWN) fl &= (RSQ_SEG_GENE_FWD | RSQ_SEG_RIBO_FWD) << rstrand;   // :331
                     if (fl & (RSQ_SEG_GENE_FWD | RSQ_SEG_GENE_REV | RSQ_SEG_GENE_UNK)) intragenic = true;
@@ -245,7 +276,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                     if (fl & (RSQ_SEG_RIBO_FWD | RSQ_SEG_RIBO_REV | RSQ_SEG_RIBO_UNK)) ribosomal = true;
                 }
                 // Exon features (:335-351)
-                const Window w = exon_window(ann, c_lo, c_hi, bs, be);
+                const Window w = exon_window(ann, c_lo, c_hi, bk_lo, bk_n, bs, be);
                 if (b == 0) w0 = w; else if (b == 1) w1 = w;
                 for (int e = w.lo; e < w.hi; ++e) {
                     const int2 x = __ldg(&ann.exon_se[e]);
@@ -278,7 +309,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                         else {
                             const int2 blk = __ldg(reinterpret_cast<const int2*>(bp + b));
                             bs = blk.x; be = blk.x + blk.y;
-                            w = exon_window(ann, c_lo, c_hi, bs, be);
+                            w = exon_window(ann, c_lo, c_hi, bk_lo, bk_n, bs, be);
                         }
                         in_all = block_has_gene(ann, w, bs, be, g, rstrand);
                     }
@@ -306,7 +337,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                         else {
                             const int2 blk = __ldg(reinterpret_cast<const int2*>(bp + b));
                             bs = blk.x; be = blk.x + blk.y;
-                            w = exon_window(ann, c_lo, c_hi, bs, be);
+                            w = exon_window(ann, c_lo, c_hi, bk_lo, bk_n, bs, be);
                         }
                         const uint32_t len = (uint32_t)(be - bs);
                         if (len == 0) continue;                                        // Collector::add keeps coverage > 0, Metrics.cpp:51
@@ -461,6 +492,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             if (s_bytes_w) atomicAdd(&s_bytes, (unsigned long long)s_bytes_w);
         }
     }
+    q0 = p0; q1 = p1; q2 = p2;
+  }  // tile loop
     __syncthreads();
     // one global atomic per counter per CTA
     for (int k = threadIdx.x; k < RSQ_N_COUNTERS; k += blockDim.x)
@@ -478,6 +511,41 @@ __global__ void prefix_max_kernel(const int2* __restrict__ se, const uint32_t* _
         m = max(m, se[i].y);
         pmax[i] = m;
     }
+}
+
+// direct-address bucket index (one thread per bucket, binary searches once per run)
+__global__ void build_buckets_kernel(const AnnView ann, int4* __restrict__ buckets, uint32_t n_buckets) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_buckets) return;
+    int a = 0, b = (int)ann.n_contigs;           // contig of this bucket: last c with bucket_off[c] <= g
+    while (a < b) { const int mid = (a + b) >> 1; if (ann.bucket_off[mid] > g) b = mid; else a = mid + 1; }
+    const int c = a - 1;
+    const long long x0 = (long long)(g - ann.bucket_off[c]) << kBucketShift;
+    const int key = (int)min(x0, (long long)INT32_MAX);
+    const int c_lo = (int)ann.exon_off[c], c_hi = (int)ann.exon_off[c + 1];
+    int4 e;
+    e.x = lower_bound_pmax(ann.exon_pmax, c_lo, c_hi, key);
+    e.y = upper_bound_start(ann.exon_se, c_lo, c_hi, key - 1);
+    e.z = seg_find(ann.seg_start, (int)ann.seg_off[c], (int)ann.seg_off[c + 1], key);
+    e.w = 0;
+    buckets[g] = e;
+}
+
+// mate-map growth: re-insert (key, first index, payload) triples into a larger table
+__global__ void pair_rehash_kernel(const Accum old_acc, unsigned long long old_cap, unsigned long long* __restrict__ nk,
+                                   unsigned long long* __restrict__ nf, unsigned long long* __restrict__ np, unsigned long long new_mask,
+                                   unsigned int* err) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= old_cap) return;
+    const unsigned long long key = old_acc.pair_keys[i];
+    if (!key) return;
+    unsigned long long slot = mix64(key) & new_mask;
+    for (int probe = 0; probe < 4096; ++probe) {
+        const unsigned long long cur = atomicCAS(&nk[slot], 0ull, key);
+        if (cur == 0ull) { nf[slot] = old_acc.pair_first[i]; np[slot] = old_acc.pair_payload[i]; return; }
+        slot = (slot + 1) & new_mask;
+    }
+    atomicOr(err, 2u);
 }
 
 // ---- coverage: integrate the difference array (three-phase scan) ----------------------------------------------------------
@@ -685,7 +753,19 @@ __global__ void sample_hist_kernel(const unsigned int* __restrict__ vals, unsign
 int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann, const BedView& bed,
                     const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
-    const unsigned grid = (unsigned)((n_reads + kHotThreads - 1) / kHotThreads);
+    // persistent grid: every SM holds exactly as many CTAs as its register file admits
+    static int per_sm[2] = {0, 0}, sms = 0;
+    const int which = prm.bed_enabled ? 1 : 0;
+    if (!per_sm[which]) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (which) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], hot_path_kernel<true>, kHotThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], hot_path_kernel<false>, kHotThreads, 0);
+        if (per_sm[which] < 1) per_sm[which] = 1;
+    }
+    const size_t tiles = (n_reads + 31) / 32;
+    const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
     if (prm.bed_enabled) hot_path_kernel<true><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm);
     else hot_path_kernel<false><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm);
     return 1;
@@ -694,6 +774,18 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream) {
     if (!n_contigs) return 0;
     prefix_max_kernel<<<(n_contigs + 63) / 64, 64, 0, stream>>>(se, off, n_contigs, pmax);
+    return 1;
+}
+
+int launch_build_buckets(const AnnView& ann, int4* buckets, uint32_t n_buckets, cudaStream_t stream) {
+    if (!n_buckets) return 0;
+    build_buckets_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(ann, buckets, n_buckets);
+    return 1;
+}
+
+int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,
+                       unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream) {
+    pair_rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_acc, old_cap, nk, nf, np, new_mask, error_flag);
     return 1;
 }
 
