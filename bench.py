@@ -157,7 +157,8 @@ def run_ours(args):
     be = api.default_backend()
     stream = torch.cuda.Stream()          # the library runs on this stream, so torch's CUDA events bracket its kernels
     torch.cuda.set_stream(stream)
-    ctx = be.create(api.make_config(device=local_rank, max_records=n_reads, user_stream=stream.cuda_stream))
+    ctx = be.create(api.make_config(device=local_rank, max_records=n_reads, user_stream=stream.cuda_stream,
+                                    collect_coverage=os.environ.get("RSQ_BENCH_COVERAGE", "1") != "0"))   # env: ablation runs only
     ctx.set_annotation(ann)
 
     def barrier():

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_LIB = os.path.join(ROOT, "rnaseqc_b200", "lib", "librsq_b200.so")
+PRODUCT_LIB = os.environ.get("RSQ_B200_LIB") or os.path.join(ROOT, "rnaseqc_b200", "lib", "librsq_b200.so")  # env override: A/B builds of the CUDA library
 HOST_LIB = os.path.join(ROOT, "rnaseqc_b200", "lib", "librsq_host.so")
 
 RSQ_N_COUNTERS = 64

@@ -33,6 +33,7 @@ struct Ctx {
     // accumulators
     Accum acc{};
     unsigned int* d_cov = nullptr;            // integrated coverage (finalize)
+    unsigned long long* d_exon_out = nullptr; // canonical (whole | frac) exon sums for the read-back
     unsigned int* d_scan = nullptr;           // scan scratch
     size_t scan_elems = 0;
     unsigned long long frag_cap = 0, pair_cap = 0;
@@ -97,7 +98,8 @@ int zero_accumulators(Ctx* c) {
     CU_TRY(cudaMemsetAsync(a.gene_unique, 0, 8ull * c->n_genes, c->stream));
     CU_TRY(cudaMemsetAsync(a.gene_fragments, 0, 8ull * c->n_genes, c->stream));
     CU_TRY(cudaMemsetAsync(a.exon_whole, 0, 8ull * c->n_exons, c->stream));
-    CU_TRY(cudaMemsetAsync(a.exon_frac, 0, 8ull * c->n_exons, c->stream));
+    CU_TRY(cudaMemsetAsync(a.exon_fhi, 0, 8ull * c->n_exons, c->stream));
+    CU_TRY(cudaMemsetAsync(a.exon_flo, 0, 8ull * c->n_exons, c->stream));
     CU_TRY(cudaMemsetAsync(a.cov_diff, 0, 4ull * (c->cov_len + 1), c->stream));
     CU_TRY(cudaMemsetAsync(a.frag_set, 0, 8ull * c->frag_cap, c->stream));
     CU_TRY(cudaMemsetAsync(a.algo_bytes, 0, 8, c->stream));
@@ -273,7 +275,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     free_list(c->ann_allocs);
     free_list(c->bed_allocs);
     Accum& a = c->acc;
-    void* ptrs[] = {a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_frac, a.cov_diff, a.frag_set,
+    void* ptrs[] = {a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1]};
@@ -297,8 +299,9 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     CU_TRY(cudaSetDevice(c->cfg.device));
     c->n_contigs = a->n_contigs; c->n_genes = a->n_genes; c->n_exons = a->n_exons; c->n_segs = a->n_segs; c->cov_len = a->cov_len;
     // repack host-side into the device layout: (start,end) pairs and 16-byte metadata
-    std::vector<int2> se(a->n_exons);
-    std::vector<ExonMeta> meta(a->n_exons);
+    std::vector<int2> se((size_t)a->n_exons + 4, make_int2(INT32_MAX, INT32_MAX));   // padded for the rounded-up bulk copies
+    std::vector<ExonMeta> meta((size_t)a->n_exons + 4);
+    memset(meta.data(), 0, meta.size() * sizeof(ExonMeta));
     for (uint32_t i = 0; i < a->n_exons; ++i) {
         se[i] = make_int2(a->exon_start[i], a->exon_end[i]);
         meta[i].gene_flags = a->exon_gene[i] | ((uint32_t)a->exon_flags[i] << 24);
@@ -312,8 +315,9 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     if ((rc = upload(c, c->ann_allocs, se.data(), se.size(), &v.exon_se))) return rc;
     if ((rc = upload(c, c->ann_allocs, meta.data(), meta.size(), &v.exon_meta))) return rc;
     if ((rc = upload(c, c->ann_allocs, a->seg_off, (size_t)a->n_contigs + 1, &v.seg_off))) return rc;
-    if ((rc = upload(c, c->ann_allocs, a->seg_start, (size_t)a->n_segs, &v.seg_start))) return rc;
-    if ((rc = upload(c, c->ann_allocs, a->seg_flags, (size_t)a->n_segs, &v.seg_flags))) return rc;
+    std::vector<int2> sf((size_t)a->n_segs + 4, make_int2(INT32_MAX, 0));   // padded: bulk copies round up to 16 bytes
+    for (uint32_t i = 0; i < a->n_segs; ++i) sf[i] = make_int2(a->seg_start[i], (int)a->seg_flags[i]);
+    if ((rc = upload(c, c->ann_allocs, sf.data(), sf.size(), &v.seg_sf))) return rc;
     if ((rc = upload(c, c->ann_allocs, a->gene_flags, (size_t)a->n_genes, &v.gene_flags))) return rc;
     int32_t* pmax = nullptr;
     CU_TRY(cudaMalloc(&pmax, std::max<size_t>(a->n_exons, 1) * 4));
@@ -344,7 +348,9 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     CU_TRY(cudaMalloc(&acc.gene_unique, 8ull * std::max(a->n_genes, 1u)));
     CU_TRY(cudaMalloc(&acc.gene_fragments, 8ull * std::max(a->n_genes, 1u)));
     CU_TRY(cudaMalloc(&acc.exon_whole, 8ull * std::max(a->n_exons, 1u)));
-    CU_TRY(cudaMalloc(&acc.exon_frac, 8ull * std::max(a->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_fhi, 8ull * std::max(a->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_flo, 8ull * std::max(a->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&c->d_exon_out, 16ull * std::max(a->n_exons, 1u)));
     CU_TRY(cudaMalloc(&acc.cov_diff, 4ull * (a->cov_len + 1)));
     CU_TRY(cudaMalloc(&c->d_cov, 4ull * (a->cov_len + 1)));
     c->scan_elems = coverage_scan_scratch_elems(a->cov_len + 1);
@@ -473,8 +479,11 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
     if (out->gene_reads) CU_TRY(cudaMemcpyAsync(out->gene_reads, a.gene_reads, 8ull * c->n_genes, cudaMemcpyDeviceToHost, st));
     if (out->gene_unique) CU_TRY(cudaMemcpyAsync(out->gene_unique, a.gene_unique, 8ull * c->n_genes, cudaMemcpyDeviceToHost, st));
     if (out->gene_fragments) CU_TRY(cudaMemcpyAsync(out->gene_fragments, a.gene_fragments, 8ull * c->n_genes, cudaMemcpyDeviceToHost, st));
-    if (out->exon_whole) CU_TRY(cudaMemcpyAsync(out->exon_whole, a.exon_whole, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
-    if (out->exon_frac) CU_TRY(cudaMemcpyAsync(out->exon_frac, a.exon_frac, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
+    if (out->exon_whole || out->exon_frac) {
+        c->launches += launch_combine_exon(a, c->n_exons, c->d_exon_out, c->d_exon_out + c->n_exons, st);
+        if (out->exon_whole) CU_TRY(cudaMemcpyAsync(out->exon_whole, c->d_exon_out, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
+        if (out->exon_frac) CU_TRY(cudaMemcpyAsync(out->exon_frac, c->d_exon_out + c->n_exons, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
+    }
     if (c->cov_len && c->cfg.collect_coverage) {   // integrate the difference array on the device; copy out only on request
         c->launches += launch_coverage_scan(a.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
         if (out->coverage) CU_TRY(cudaMemcpyAsync(out->coverage, c->d_cov, 4ull * c->cov_len, cudaMemcpyDeviceToHost, st));

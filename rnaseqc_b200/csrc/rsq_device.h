@@ -22,8 +22,7 @@ struct AnnView {
     const int32_t*  exon_pmax;    // [n_exons] running max of end within the contig (monotone)
     const ExonMeta* exon_meta;    // [n_exons]
     const uint32_t* seg_off;      // [n_contigs+1]
-    const int32_t*  seg_start;    // [n_segs]
-    const uint8_t*  seg_flags;    // [n_segs]
+    const int2*     seg_sf;       // [n_segs] (start, RSQ_SEG_* flags): elementary gene segments, start-sorted per contig
     const uint8_t*  gene_flags;   // [n_genes]
     // direct-address bucket index: bucket b of contig c covers coordinates [b << kBucketShift, (b+1) << kBucketShift)
     const uint32_t* bucket_off;   // [n_contigs+1] first bucket of each contig
@@ -59,8 +58,10 @@ struct Accum {
     unsigned long long* gene_reads;      // [n_genes]
     unsigned long long* gene_unique;
     unsigned long long* gene_fragments;
-    unsigned long long* exon_whole;      // [n_exons] by slot
-    unsigned long long* exon_frac;       // [n_exons] by slot, units of 2^-64
+    // exon counts, exact Q64.64 kept as three carry-free sums (by slot): value = whole + (fhi * 2^32 + flo) * 2^-64
+    unsigned long long* exon_whole;      // [n_exons]
+    unsigned long long* exon_fhi;        // [n_exons] sum of (frac >> 32)
+    unsigned long long* exon_flo;        // [n_exons] sum of (frac & 0xffffffff)
     unsigned int*       cov_diff;        // [cov_len+1] coverage difference array (wrapping u32)
     unsigned long long* frag_set;        // fragment-tracker hash set (open addressing), 0 = empty
     unsigned long long  frag_mask;       // capacity-1
@@ -103,6 +104,7 @@ int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap,
                   unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream);
 int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* out, cudaStream_t stream);
 int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* in, cudaStream_t stream);
+int launch_combine_exon(const Accum& acc, uint32_t n_exons, unsigned long long* whole_out, unsigned long long* frac_out, cudaStream_t stream);
 // BED mode, after launch_hot_path of the same batch: owners publish, seconds test, samples are ranked in stream order
 int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsigned int* scan_scratch, cudaStream_t stream);
 size_t pair_scan_scratch_elems(size_t n_reads);
