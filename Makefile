@@ -23,9 +23,10 @@ $(OBJDIR)/host/%.o: rnaseqc_b200/csrc/host/%.cpp $(wildcard rnaseqc_b200/csrc/ho
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIBDIR)/librsq_b200.so: rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_capi.cu $(wildcard rnaseqc_b200/csrc/*.cuh) include/rsq_b200.h
+CU_SRCS := rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_covstats.cu rnaseqc_b200/csrc/rsq_capi.cu
+$(LIBDIR)/librsq_b200.so: $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_capi.cu -lcudart 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_SRCS) -lcudart 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 
 $(LIBDIR)/librsq_host.so: $(HOST_OBJS) $(OBJDIR)/host/host_capi.o
 	@mkdir -p $(LIBDIR)

@@ -230,6 +230,42 @@ int rsq_reset(rsq_ctx* ctx);
  * copies results to the caller's arrays (replaces the reads of the globals at src/RNASeQC.cpp:397-521). */
 int rsq_finalize(rsq_ctx* ctx, rsq_results* out);
 
+/* ---- per-gene coverage statistics on the device ------------------------------------------------------------------
+ * Replaces BaseCoverage::compute / computeCoverage (src/Metrics.cpp:132-151,265-337) and BiasCounter::computeBias
+ * (src/Metrics.cpp:160-235) for every kept "gene" line: per-exon masked mean/std/CV, stitched-transcript 3'/5' bias
+ * windows (with the reference's peak-window / 5th-percentile flank trimming) and masked transcript mean/std/CV, computed
+ * from the integrated per-base coverage that never leaves the GPU.  The caller (host report writer) keeps the text
+ * formatting, the eviction order of coverage.tsv and the medians over genes. */
+typedef struct rsq_transcripts {
+    uint32_t struct_size;
+    uint32_t n_genes;              /* Gene features to evaluate                                              */
+    uint32_t n_exon_refs;          /* exons over all listed genes, stitched (exonsForGene) order             */
+    uint32_t coverage_mask;        /* COVERAGE_MASK, src/RNASeQC.cpp:91                                       */
+    int32_t  bias_offset;          /* BIAS_OFFSET :94 (>= 0)                                                  */
+    int32_t  bias_window;          /* BIAS_WINDOW :95 (1..1024)                                               */
+    uint32_t bias_gene_length;     /* BIAS_LENGTH :96                                                         */
+    uint32_t reserved;
+    const uint64_t* gene_cov_off;  /* [n_genes] first base of the gene's stitched transcript in the coverage array */
+    const uint32_t* gene_exon_off; /* [n_genes+1] into exon_len / exon_slot                                   */
+    const uint8_t*  gene_strand;   /* [n_genes] RSQ_STRAND_*                                                  */
+    const uint32_t* exon_len;      /* [n_exon_refs]                                                           */
+    const uint32_t* exon_slot;     /* [n_exon_refs]                                                           */
+} rsq_transcripts;
+
+typedef struct rsq_coverage_stats {
+    uint32_t struct_size;
+    uint32_t reserved;
+    double*   gene_mean;           /* [n_genes] -1 when nothing is left after masking (row "0 0 nan", not counted) */
+    double*   gene_std;            /* [n_genes]                                                                */
+    double*   gene_cv;             /* [n_genes]                                                                */
+    uint64_t* five_end;            /* [n_genes] BiasCounter::fiveEnd (truncated median, src/Metrics.h:76)      */
+    uint64_t* three_end;           /* [n_genes]                                                                */
+    double*   exon_cv;             /* [n_exons by slot] NaN = no exonCoverage entry (src/Metrics.cpp:298-304)  */
+} rsq_coverage_stats;
+
+/* Runs after all records are submitted (integrates the coverage difference array itself). */
+int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* req, rsq_coverage_stats* out);
+
 /* Device-resident count vector for the end-of-run all-reduce over NVLink (counters ‖ gene_reads ‖
  * gene_unique ‖ gene_fragments ‖ exon_whole ‖ exon_frac_hi32 ‖ exon_frac_lo32), all uint64, additive across
  * partitions.  Returns a DEVICE pointer and the number of uint64 words; valid until rsq_destroy.

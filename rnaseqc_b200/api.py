@@ -72,6 +72,19 @@ class RsqResults(C.Structure):
                 ("fragment_samples_taken", C.c_uint64)]
 
 
+class RsqTranscripts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_genes", C.c_uint32), ("n_exon_refs", C.c_uint32), ("coverage_mask", C.c_uint32),
+                ("bias_offset", C.c_int32), ("bias_window", C.c_int32), ("bias_gene_length", C.c_uint32), ("reserved", C.c_uint32),
+                ("gene_cov_off", C.POINTER(C.c_uint64)), ("gene_exon_off", C.POINTER(C.c_uint32)), ("gene_strand", C.POINTER(C.c_uint8)),
+                ("exon_len", C.POINTER(C.c_uint32)), ("exon_slot", C.POINTER(C.c_uint32))]
+
+
+class RsqCoverageStats(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("gene_mean", C.POINTER(C.c_double)),
+                ("gene_std", C.POINTER(C.c_double)), ("gene_cv", C.POINTER(C.c_double)), ("five_end", C.POINTER(C.c_uint64)),
+                ("three_end", C.POINTER(C.c_uint64)), ("exon_cv", C.POINTER(C.c_double))]
+
+
 class RunOptionsC(C.Structure):
     _fields_ = [("sample_name", C.c_char_p), ("sample_given", C.c_int), ("output_dir", C.c_char_p), ("use_rpkm", C.c_int),
                 ("write_coverage", C.c_int), ("coverage_mask", C.c_uint), ("bias_offset", C.c_int), ("bias_window", C.c_int),
@@ -86,7 +99,7 @@ class StreamStateC(C.Structure):
 
 ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
                "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_submit", "rsq_submit_device", "rsq_sync",
-               "rsq_reset", "rsq_finalize", "rsq_export_counts", "rsq_import_counts", "rsq_algorithmic_bytes",
+               "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_export_counts", "rsq_import_counts", "rsq_algorithmic_bytes",
                "rsq_launch_count", "rsq_kernel_time_ms"]
 
 
@@ -175,6 +188,7 @@ class Backend:
         L.rsq_sync.argtypes = [C.c_void_p]
         L.rsq_reset.argtypes = [C.c_void_p]
         L.rsq_finalize.argtypes = [C.c_void_p, C.POINTER(RsqResults)]
+        L.rsq_coverage_statistics.argtypes = [C.c_void_p, C.POINTER(RsqTranscripts), C.POINTER(RsqCoverageStats)]
         L.rsq_export_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.rsq_import_counts.argtypes = [C.c_void_p]
         L.rsq_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -247,6 +261,23 @@ class Context:
         res.fragment_samples_taken = int(st.fragment_samples_taken)
         return res
 
+    def coverage_statistics(self, ann: "Annotation", mask: int = 500, bias_offset: int = 0, bias_window: int = 100,
+                            bias_gene_length: int = 200) -> dict:
+        """per-gene-line coverage statistics (rsq_coverage_statistics); arrays indexed by gene line (contig, start order)"""
+        q = RsqTranscripts()
+        host_lib().rsqh_transcripts(ann._h, mask, bias_offset, bias_window, bias_gene_length, C.byref(q))
+        n = q.n_genes
+        out = {"gene_mean": np.zeros(n), "gene_std": np.zeros(n), "gene_cv": np.zeros(n), "five_end": np.zeros(n, np.uint64),
+               "three_end": np.zeros(n, np.uint64), "exon_cv": np.zeros(self.n_exons)}
+        st = RsqCoverageStats()
+        st.struct_size = C.sizeof(RsqCoverageStats)
+        pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        st.gene_mean, st.gene_std, st.gene_cv, st.exon_cv = pd(out["gene_mean"]), pd(out["gene_std"]), pd(out["gene_cv"]), pd(out["exon_cv"])
+        st.five_end = out["five_end"].ctypes.data_as(C.POINTER(C.c_uint64))
+        st.three_end = out["three_end"].ctypes.data_as(C.POINTER(C.c_uint64))
+        self._check(self.be.lib.rsq_coverage_statistics(self.h, C.byref(q), C.byref(st)))
+        return out
+
     def export_counts(self) -> Tuple[int, int]:
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self.be.lib.rsq_export_counts(self.h, C.byref(p), C.byref(n)))
@@ -294,6 +325,7 @@ def host_lib():
         H.rsqh_annotation_view.argtypes = [C.c_void_p]
         H.rsqh_bed_view.restype = C.POINTER(RsqBed)
         H.rsqh_bed_view.argtypes = [C.c_void_p]
+        H.rsqh_transcripts.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_ulong, C.POINTER(RsqTranscripts)]
         for f in ("rsqh_n_gene_list", "rsqh_n_contigs"):
             getattr(H, f).restype = C.c_uint
             getattr(H, f).argtypes = [C.c_void_p]

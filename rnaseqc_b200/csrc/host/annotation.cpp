@@ -273,6 +273,7 @@ void load_gtf(const std::string& path, Annotation& A) {
     }
     A.f_exon_off[nc] = (uint32_t)A.f_exon_start.size();
     A.f_seg_off[nc] = (uint32_t)A.f_seg_start.size();
+    A.build_transcripts();
 }
 
 void Annotation::pad_contigs(size_t n_contigs) {
@@ -284,6 +285,32 @@ void Annotation::pad_contigs(size_t n_contigs) {
         f_seg_flags.push_back(0);
         f_seg_off.push_back((uint32_t)f_seg_start.size());
     }
+}
+
+void Annotation::build_transcripts() {
+    t_gene_cov_off.clear(); t_gene_exon_off.assign(1, 0); t_exon_len.clear(); t_exon_slot.clear(); t_gene_strand.clear();
+    uint32_t flat = 0;
+    for (auto& genes : genes_by_contig)
+        for (GeneFeature& g : genes) {
+            g.flat = flat++;
+            const auto& slots = exons_for_gene[g.gene];
+            t_gene_cov_off.push_back(slots.empty() ? 0 : exon_cov_off[slots[0]]);   // a gene's exons are contiguous in the coverage array
+            for (uint32_t s : slots) { t_exon_len.push_back((uint32_t)std::max<int64_t>(exon_len[s], 0)); t_exon_slot.push_back(s); }
+            t_gene_exon_off.push_back((uint32_t)t_exon_len.size());
+            t_gene_strand.push_back(g.strand);
+        }
+}
+
+rsq_transcripts Annotation::transcripts(unsigned coverage_mask, int bias_offset, int bias_window, unsigned long bias_gene_length) const {
+    rsq_transcripts q{};
+    q.struct_size = sizeof(rsq_transcripts);
+    q.n_genes = (uint32_t)t_gene_strand.size();
+    q.n_exon_refs = (uint32_t)t_exon_len.size();
+    q.coverage_mask = coverage_mask;
+    q.bias_offset = bias_offset; q.bias_window = bias_window; q.bias_gene_length = (uint32_t)bias_gene_length;
+    q.gene_cov_off = t_gene_cov_off.data(); q.gene_exon_off = t_gene_exon_off.data(); q.gene_strand = t_gene_strand.data();
+    q.exon_len = t_exon_len.data(); q.exon_slot = t_exon_slot.data();
+    return q;
 }
 
 rsq_annotation Annotation::view() const {

@@ -46,6 +46,7 @@ struct GeneFeature {      // one kept line of type "gene" (src/RNASeQC.cpp:137-1
     bool ribosomal;
     uint32_t gene;        // gene-universe index of feature_id
     uint32_t line_order;  // position among kept lines (ties of the stable sort)
+    uint32_t flat = 0;    // index of this gene line in the rsq_transcripts request (contig order, then start order)
 };
 
 struct ExonFeature {      // one kept line of type "exon"
@@ -89,6 +90,12 @@ struct Annotation {
     // Extends the contig index space (BED-only contigs) with empty slices.
     void pad_contigs(size_t n_contigs);
     rsq_annotation view() const;
+    // request for rsq_coverage_statistics: one entry per kept gene line (see GeneFeature::flat)
+    std::vector<uint64_t> t_gene_cov_off;
+    std::vector<uint32_t> t_gene_exon_off, t_exon_len, t_exon_slot;
+    std::vector<uint8_t> t_gene_strand;
+    void build_transcripts();
+    rsq_transcripts transcripts(unsigned coverage_mask, int bias_offset, int bias_window, unsigned long bias_gene_length) const;
 
     uint32_t gene_universe(const std::string& id);
 };

@@ -73,6 +73,9 @@ int rsqh_load_annotation(const char* gtf, const char* bed, void** out, char* err
 void rsqh_free_annotation(void* h) { delete static_cast<Handle*>(h); }
 const rsq_annotation* rsqh_annotation_view(void* h) { return &static_cast<Handle*>(h)->ann_view; }
 const rsq_bed* rsqh_bed_view(void* h) { Handle* H = static_cast<Handle*>(h); return H->have_bed ? &H->bed_view : nullptr; }
+void rsqh_transcripts(void* h, unsigned mask, int bias_offset, int bias_window, unsigned long bias_gene_length, rsq_transcripts* out) {
+    *out = static_cast<Handle*>(h)->ann.transcripts(mask, bias_offset, bias_window, bias_gene_length);
+}
 unsigned rsqh_n_gene_list(void* h) { return (unsigned)static_cast<Handle*>(h)->ann.gene_list.size(); }
 unsigned rsqh_gene_list_index(void* h, unsigned i) { return static_cast<Handle*>(h)->ann.gene_list[i]; }
 const char* rsqh_gene_id(void* h, unsigned g) { return static_cast<Handle*>(h)->ann.gene_ids[g].c_str(); }

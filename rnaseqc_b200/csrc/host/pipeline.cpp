@@ -178,6 +178,21 @@ void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool wa
     R.fragment_hist.resize(last);
 }
 
+void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation& A, const RunOptions& opt, HostResults& R) {
+    rsq_transcripts q = A.transcripts(opt.coverage_mask, opt.bias_offset, opt.bias_window, opt.bias_gene_length);
+    R.cs_mean.assign(q.n_genes, 0); R.cs_std.assign(q.n_genes, 0); R.cs_cv.assign(q.n_genes, 0);
+    R.cs_five.assign(q.n_genes, 0); R.cs_three.assign(q.n_genes, 0);
+    R.cs_exon_cv.assign(A.exon_ids.size(), 0);
+    rsq_coverage_stats out;
+    memset(&out, 0, sizeof(out));
+    out.struct_size = sizeof(out);
+    out.gene_mean = R.cs_mean.data(); out.gene_std = R.cs_std.data(); out.gene_cv = R.cs_cv.data();
+    out.five_end = R.cs_five.data(); out.three_end = R.cs_three.data(); out.exon_cv = R.cs_exon_cv.data();
+    int rc = be.coverage_statistics(ctx, &q, &out);
+    if (rc != RSQ_OK) throw HostError(rc == RSQ_ERR_INVALID ? 6 : -1, std::string("rsq_coverage_statistics failed: ") + be.last_error(ctx));
+    R.have_cov_stats = true;
+}
+
 int run_sample(const Backend& be, CliOptions& opt) {
     using clk = std::chrono::steady_clock;
     rsq_ctx* ctx = nullptr;
@@ -273,7 +288,8 @@ int run_sample(const Backend& be, CliOptions& opt) {
             std::cout << "Estimating library complexity..." << std::endl;
         }
         HostResults R;
-        fetch_results(be, ctx, A, true, R);
+        fetch_results(be, ctx, A, false, R);                     // counts only: the per-base coverage stays on the device
+        fetch_coverage_statistics(be, ctx, A, opt.run, R);
         StreamState st;
         st.read_length = decoder.read_length();
         st.alignment_count = decoder.alignment_count();

@@ -25,6 +25,7 @@ struct Backend {
     decltype(&rsq_submit) submit;
     decltype(&rsq_sync) sync;
     decltype(&rsq_finalize) finalize;
+    decltype(&rsq_coverage_statistics) coverage_statistics;
     decltype(&rsq_host_alloc) host_alloc;
     decltype(&rsq_host_free) host_free;
 };
@@ -49,5 +50,7 @@ int run_sample(const Backend& be, CliOptions& opt);
 
 // Pulls results out of a finalised ctx into HostResults sized for annotation A.
 void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool want_coverage, HostResults& R);
+// Per-gene coverage statistics from the backend (device kernel in the product) into R.cs_*.
+void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation& A, const RunOptions& opt, HostResults& R);
 
 }  // namespace rsqh

@@ -170,6 +170,26 @@ void compute_coverage_summary(const Annotation& A, const HostResults& R, const R
         }
     }
 
+    if (R.have_cov_stats) {
+        // statistics came from the device kernel (rsq_covstats.cu); only the ordering and the text are left
+        for (const GeneFeature* gf : order) {
+            const uint32_t g = gf->gene, fi = gf->flat;
+            out.five_end[g] = (uint64_t)((double)out.five_end[g] + (double)R.cs_five[fi]);
+            out.three_end[g] = (uint64_t)((double)out.three_end[g] + (double)R.cs_three[fi]);
+            std::string row = A.gene_ids[g] + "\t";
+            if (R.cs_mean[fi] != -1.0 || R.cs_std[fi] != -1.0) {
+                row += fmt_default(R.cs_mean[fi]) + "\t" + fmt_default(R.cs_std[fi]) + "\t" + fmt_default(R.cs_cv[fi]);
+                out.gene_means.push_back(R.cs_mean[fi]);
+                out.gene_stds.push_back(R.cs_std[fi]);
+                out.gene_cvs.push_back(R.cs_cv[fi]);
+            } else row += "0\t0\tnan";
+            out.rows.push_back(row);
+        }
+        for (size_t s = 0; s < R.cs_exon_cv.size(); ++s)
+            if (!std::isnan(R.cs_exon_cv[s])) out.exon_cvs.emplace_back(A.exon_ids[s], R.cs_exon_cv[s]);
+        return;
+    }
+
     // ---- computeCoverage per evicted gene (src/Metrics.cpp:265-337) ------------------------------------------
     std::vector<unsigned long> gene_cov;
     std::vector<uint32_t> zero_cov;

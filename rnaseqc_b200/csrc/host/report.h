@@ -42,6 +42,11 @@ struct HostResults {
     std::vector<uint32_t> coverage;       // per base, laid out by Annotation::exon_cov_off
     std::vector<uint64_t> fragment_hist;  // index = |isize|
     uint64_t fragment_samples_taken = 0;
+    // per-gene coverage statistics computed on the device (rsq_coverage_statistics), indexed by GeneFeature::flat;
+    // when present the per-base coverage array is not needed on the host at all
+    bool have_cov_stats = false;
+    std::vector<double> cs_mean, cs_std, cs_cv, cs_exon_cv;
+    std::vector<uint64_t> cs_five, cs_three;
 };
 
 // exact Q64.64 -> nearest double

@@ -484,11 +484,11 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
         if (out->exon_whole) CU_TRY(cudaMemcpyAsync(out->exon_whole, c->d_exon_out, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
         if (out->exon_frac) CU_TRY(cudaMemcpyAsync(out->exon_frac, c->d_exon_out + c->n_exons, 8ull * c->n_exons, cudaMemcpyDeviceToHost, st));
     }
-    if (c->cov_len && c->cfg.collect_coverage) {   // integrate the difference array on the device; copy out only on request
-        c->launches += launch_coverage_scan(a.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
-        if (out->coverage) CU_TRY(cudaMemcpyAsync(out->coverage, c->d_cov, 4ull * c->cov_len, cudaMemcpyDeviceToHost, st));
-    } else if (out->coverage && c->cov_len) {
-        memset(out->coverage, 0, 4ull * c->cov_len);
+    if (out->coverage && c->cov_len) {             // raw per-base coverage on request only (rsq_coverage_statistics
+        if (c->cfg.collect_coverage) {             // computes the per-gene statistics without it ever leaving the GPU)
+            c->launches += launch_coverage_scan(a.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
+            CU_TRY(cudaMemcpyAsync(out->coverage, c->d_cov, 4ull * c->cov_len, cudaMemcpyDeviceToHost, st));
+        } else memset(out->coverage, 0, 4ull * c->cov_len);
     }
     out->fragment_samples_taken = 0;
     if (out->fragment_hist && out->fragment_hist_len) {
@@ -516,6 +516,51 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
                  ((err_flag & 2) ? " mate table" : "") + ((err_flag & 4) ? " candidate list" : "") + " (raise rsq_config.max_records)";
         return RSQ_ERR_CAPACITY;
     }
+    return RSQ_OK;
+}
+
+int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage_stats* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !q || !out || !c->have_ann || q->struct_size != sizeof(rsq_transcripts) || out->struct_size != sizeof(rsq_coverage_stats))
+        return RSQ_ERR_INVALID;
+    if (q->bias_offset < 0 || q->bias_window < 1 || q->bias_window > 1024) { c->err = "bias offset/window out of range"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    cudaStream_t st = c->stream;
+    // request arrays -> device (a few MB, once per sample)
+    const size_t ng = q->n_genes, nr = q->n_exon_refs, ne = c->n_exons;
+    unsigned long long* d_off = nullptr; uint32_t *d_eoff = nullptr, *d_len = nullptr, *d_slot = nullptr; uint8_t* d_strand = nullptr;
+    double* d_out = nullptr; unsigned long long* d_ends = nullptr;
+    CU_TRY(cudaMalloc(&d_off, 8 * std::max<size_t>(ng, 1)));
+    CU_TRY(cudaMalloc(&d_eoff, 4 * (ng + 1)));
+    CU_TRY(cudaMalloc(&d_strand, std::max<size_t>(ng, 1)));
+    CU_TRY(cudaMalloc(&d_len, 4 * std::max<size_t>(nr, 1)));
+    CU_TRY(cudaMalloc(&d_slot, 4 * std::max<size_t>(nr, 1)));
+    CU_TRY(cudaMalloc(&d_out, 8 * (3 * std::max<size_t>(ng, 1) + std::max<size_t>(ne, 1))));
+    CU_TRY(cudaMalloc(&d_ends, 16 * std::max<size_t>(ng, 1)));
+    CU_TRY(cudaMemcpyAsync(d_off, q->gene_cov_off, 8 * ng, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_eoff, q->gene_exon_off, 4 * (ng + 1), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_strand, q->gene_strand, ng, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_len, q->exon_len, 4 * nr, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_slot, q->exon_slot, 4 * nr, cudaMemcpyHostToDevice, st));
+    if (c->cov_len && c->cfg.collect_coverage)
+        c->launches += launch_coverage_scan(c->acc.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
+    else
+        CU_TRY(cudaMemsetAsync(c->d_cov, 0, 4ull * (c->cov_len + 1), st));
+    double* d_mean = d_out; double* d_std = d_out + std::max<size_t>(ng, 1); double* d_cv = d_std + std::max<size_t>(ng, 1);
+    double* d_ecv = d_cv + std::max<size_t>(ng, 1);
+    c->launches += launch_coverage_stats(c->d_cov, (uint32_t)ng, d_off, d_eoff, d_strand, d_len, d_slot, q->coverage_mask, q->bias_offset,
+                                         q->bias_window, q->bias_gene_length, d_mean, d_std, d_cv, d_ends, d_ends + std::max<size_t>(ng, 1),
+                                         d_ecv, (uint32_t)ne, st);
+    CU_TRY(cudaMemcpyAsync(out->gene_mean, d_mean, 8 * ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->gene_std, d_std, 8 * ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->gene_cv, d_cv, 8 * ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->five_end, d_ends, 8 * ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->three_end, d_ends + std::max<size_t>(ng, 1), 8 * ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->exon_cv, d_ecv, 8 * ne, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+    cudaFree(d_off); cudaFree(d_eoff); cudaFree(d_strand); cudaFree(d_len); cudaFree(d_slot); cudaFree(d_out); cudaFree(d_ends);
     return RSQ_OK;
 }
 

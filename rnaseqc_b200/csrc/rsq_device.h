@@ -111,4 +111,10 @@ size_t pair_scan_scratch_elems(size_t n_reads);
 int launch_sample_histogram(const unsigned int* vals, unsigned long long n, unsigned long long* hist, unsigned long long hist_len,
                             cudaStream_t stream);
 
+// rsq_covstats.cu
+int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsigned long long* gene_cov_off, const uint32_t* gene_exon_off,
+                          const uint8_t* gene_strand, const uint32_t* exon_len, const uint32_t* exon_slot, uint32_t mask, int bias_offset,
+                          int bias_window, uint32_t bias_gene_length, double* gene_mean, double* gene_std, double* gene_cv,
+                          unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons, cudaStream_t stream);
+
 }  // namespace rsqd

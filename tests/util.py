@@ -51,7 +51,7 @@ def compare_outputs(dir_a, dir_b, rel_tol=1e-6):
             for u, v in zip(cx, cy):
                 if u == v:
                     continue
-                assert not (_is_int(u) or _is_int(v)), f"{f}:{i + 1}: integer field differs: {x!r} vs {y!r}"
+                assert not (_is_int(u) and _is_int(v)), f"{f}:{i + 1}: integer field differs: {x!r} vs {y!r}"
                 fu, fv = float(u), float(v)
                 assert math.isnan(fu) == math.isnan(fv), f"{f}:{i + 1}: {x!r} vs {y!r}"
                 if not math.isnan(fu):
