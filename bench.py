@@ -41,7 +41,7 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_annotation(wl, tmpdir):
+def build_annotation(wl, tmpdir, with_bed=False):
     from rnaseqc_b200 import api, synth
     if wl["full_genome"]:
         sa = synth.make_annotation(seed=20260925, n_genes=wl["n_genes"], contig_names=synth.GRCH38_NAMES, contig_lens=synth.GRCH38)
@@ -49,7 +49,11 @@ def build_annotation(wl, tmpdir):
         sa = synth.make_annotation(seed=20260925, n_genes=wl["n_genes"])
     gtf = os.path.join(tmpdir, "bench.gtf")
     synth.write_gtf(sa, gtf)
-    ann = api.Annotation(gtf)
+    bed = None
+    if with_bed:    # BASELINE.json configs[4]: the --bed fragment-size path on top (long, isolated exons as intervals)
+        bed = os.path.join(tmpdir, "bench.bed")
+        synth.write_bed(sa, bed, min_len=1000)
+    ann = api.Annotation(gtf, bed)
     return sa, ann, gtf
 
 
@@ -147,7 +151,7 @@ def run_ours(args):
     n_records = args.records or wl["records"]
     tmpdir = tempfile.mkdtemp(prefix="rsq_bench_")
     t0 = time.time()
-    sa, ann, gtf = build_annotation(wl, tmpdir)
+    sa, ann, gtf = build_annotation(wl, tmpdir, with_bed=args.bed)
     log(f"[rank {rank}] annotation: {ann.n_genes} genes, {ann.n_exons} exons, {ann.cov_len} exon bases ({time.time() - t0:.1f}s)")
     rb, bb = generate_on_device(sa, ann, n_records, device, rank, world)
     n_reads, n_blocks = rb.shape[0], bb.shape[0]
@@ -158,6 +162,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()          # the library runs on this stream, so torch's CUDA events bracket its kernels
     torch.cuda.set_stream(stream)
     ctx = be.create(api.make_config(device=local_rank, max_records=n_reads, user_stream=stream.cuda_stream,
+                                    fragment_samples=1000000 if args.bed else 0,
                                     collect_coverage=os.environ.get("RSQ_BENCH_COVERAGE", "1") != "0"))   # env: ablation runs only
     ctx.set_annotation(ann)
 
@@ -290,7 +295,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["label"] if not args.records else f"{wl['label']} [records overridden: {n_records}]",
                        "records_per_gpu": n_reads, "blocks_per_gpu": n_blocks, "genes": ann.n_genes, "exons": ann.n_exons,
-                       "exon_bases": ann.cov_len, "partitioning": "coordinate ranges cut at gene-free positions" if world > 1 else "none",
+                       "exon_bases": ann.cov_len, "bed_fragment_sizes": bool(args.bed), "partitioning": "coordinate ranges cut at gene-free positions" if world > 1 else "none",
                        "step": "reset + hot-path kernel + coverage integration + per-gene coverage/bias statistics kernel + count/statistics read-back" + (" + NCCL all-reduce" if world > 1 else ""),
                        "l2_policy": f"inputs ({(48 * n_reads + 8 * n_blocks) / 1e9:.1f} GB per GPU) larger than the 126 MB L2",
                        "not_in_step": "text formatting of the report files and the medians over genes (host, once per sample)"},
@@ -302,6 +307,7 @@ def run_ours(args):
             "sanity": {"mapped_reads": res.counter("Mapped Reads"), "exonic_reads": res.counter("Exonic Reads"),
                        "gene_reads_sum": int(res.gene_reads.sum()), "device_ms_events": ms_dev / args.steps,
                        "genes_with_coverage_stats": int((res.cov_stats["gene_mean"] > 0).sum()),
+                       "fragment_samples_taken": int(res.fragment_samples_taken),
                        "genes_in_3prime_bias": int(((res.cov_stats["five_end"] + res.cov_stats["three_end"]) > 0).sum())},
         }
         print(json.dumps(out), flush=True)
@@ -391,6 +397,7 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the record count per GPU (smoke runs)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000)
     ap.add_argument("--e2e-chunk", type=int, default=8_000_000)
+    ap.add_argument("--bed", action="store_true", help="also run the --bed fragment-size sampler (BASELINE.json configs[4])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

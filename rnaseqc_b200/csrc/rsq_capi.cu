@@ -38,6 +38,10 @@ struct Ctx {
     size_t scan_elems = 0;
     unsigned long long frag_cap = 0, pair_cap = 0;
     unsigned long long* d_export = nullptr;
+    // rsq_coverage_statistics buffers
+    unsigned long long* cs_off = nullptr; uint32_t *cs_eoff = nullptr, *cs_len = nullptr, *cs_slot = nullptr; uint8_t* cs_strand = nullptr;
+    double* cs_out = nullptr; unsigned long long* cs_ends = nullptr;
+    size_t cs_cap_genes = 0, cs_cap_refs = 0;
     size_t export_words = 0;
     unsigned long long* d_hist = nullptr;
     size_t hist_len = 0;
@@ -277,7 +281,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     Accum& a = c->acc;
     void* ptrs[] = {a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
-                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->d_hist, c->d_pair_scratch,
+                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_ends, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& t : c->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
@@ -527,17 +531,22 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
     CU_TRY(cudaSetDevice(c->cfg.device));
     CU_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaStream_t st = c->stream;
-    // request arrays -> device (a few MB, once per sample)
+    // request arrays -> device (a few MB); the buffers persist in the ctx and only grow
     const size_t ng = q->n_genes, nr = q->n_exon_refs, ne = c->n_exons;
-    unsigned long long* d_off = nullptr; uint32_t *d_eoff = nullptr, *d_len = nullptr, *d_slot = nullptr; uint8_t* d_strand = nullptr;
-    double* d_out = nullptr; unsigned long long* d_ends = nullptr;
-    CU_TRY(cudaMalloc(&d_off, 8 * std::max<size_t>(ng, 1)));
-    CU_TRY(cudaMalloc(&d_eoff, 4 * (ng + 1)));
-    CU_TRY(cudaMalloc(&d_strand, std::max<size_t>(ng, 1)));
-    CU_TRY(cudaMalloc(&d_len, 4 * std::max<size_t>(nr, 1)));
-    CU_TRY(cudaMalloc(&d_slot, 4 * std::max<size_t>(nr, 1)));
-    CU_TRY(cudaMalloc(&d_out, 8 * (3 * std::max<size_t>(ng, 1) + std::max<size_t>(ne, 1))));
-    CU_TRY(cudaMalloc(&d_ends, 16 * std::max<size_t>(ng, 1)));
+    if (ng > c->cs_cap_genes || nr > c->cs_cap_refs) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(c->cs_off); cudaFree(c->cs_eoff); cudaFree(c->cs_strand); cudaFree(c->cs_len); cudaFree(c->cs_slot); cudaFree(c->cs_out); cudaFree(c->cs_ends);
+        c->cs_cap_genes = std::max<size_t>(ng, 1); c->cs_cap_refs = std::max<size_t>(nr, 1);
+        CU_TRY(cudaMalloc(&c->cs_off, 8 * c->cs_cap_genes));
+        CU_TRY(cudaMalloc(&c->cs_eoff, 4 * (c->cs_cap_genes + 1)));
+        CU_TRY(cudaMalloc(&c->cs_strand, c->cs_cap_genes));
+        CU_TRY(cudaMalloc(&c->cs_len, 4 * c->cs_cap_refs));
+        CU_TRY(cudaMalloc(&c->cs_slot, 4 * c->cs_cap_refs));
+        CU_TRY(cudaMalloc(&c->cs_out, 8 * (3 * c->cs_cap_genes + std::max<size_t>(ne, 1))));
+        CU_TRY(cudaMalloc(&c->cs_ends, 16 * c->cs_cap_genes));
+    }
+    unsigned long long* d_off = c->cs_off; uint32_t *d_eoff = c->cs_eoff, *d_len = c->cs_len, *d_slot = c->cs_slot; uint8_t* d_strand = c->cs_strand;
+    double* d_out = c->cs_out; unsigned long long* d_ends = c->cs_ends;
     CU_TRY(cudaMemcpyAsync(d_off, q->gene_cov_off, 8 * ng, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_eoff, q->gene_exon_off, 4 * (ng + 1), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_strand, q->gene_strand, ng, cudaMemcpyHostToDevice, st));
@@ -547,20 +556,19 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
         c->launches += launch_coverage_scan(c->acc.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
     else
         CU_TRY(cudaMemsetAsync(c->d_cov, 0, 4ull * (c->cov_len + 1), st));
-    double* d_mean = d_out; double* d_std = d_out + std::max<size_t>(ng, 1); double* d_cv = d_std + std::max<size_t>(ng, 1);
-    double* d_ecv = d_cv + std::max<size_t>(ng, 1);
+    double* d_mean = d_out; double* d_std = d_out + c->cs_cap_genes; double* d_cv = d_std + c->cs_cap_genes;
+    double* d_ecv = d_cv + c->cs_cap_genes;
     c->launches += launch_coverage_stats(c->d_cov, (uint32_t)ng, d_off, d_eoff, d_strand, d_len, d_slot, q->coverage_mask, q->bias_offset,
-                                         q->bias_window, q->bias_gene_length, d_mean, d_std, d_cv, d_ends, d_ends + std::max<size_t>(ng, 1),
+                                         q->bias_window, q->bias_gene_length, d_mean, d_std, d_cv, d_ends, d_ends + c->cs_cap_genes,
                                          d_ecv, (uint32_t)ne, st);
     CU_TRY(cudaMemcpyAsync(out->gene_mean, d_mean, 8 * ng, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out->gene_std, d_std, 8 * ng, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out->gene_cv, d_cv, 8 * ng, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out->five_end, d_ends, 8 * ng, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(out->three_end, d_ends + std::max<size_t>(ng, 1), 8 * ng, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(out->three_end, d_ends + c->cs_cap_genes, 8 * ng, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out->exon_cv, d_ecv, 8 * ne, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
-    cudaFree(d_off); cudaFree(d_eoff); cudaFree(d_strand); cudaFree(d_len); cudaFree(d_slot); cudaFree(d_out); cudaFree(d_ends);
     return RSQ_OK;
 }
 
