@@ -286,6 +286,11 @@ def run_ours(args):
             octx.close()
 
     peak, peak_src = measured_peak()
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):   # DRAM bytes per record of the hot kernel from the committed ncu --set full capture, scaled to this launch
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["dram_bytes_per_record"] * n_reads, tj["source"]
     hot_ms_per_launch = hot_ms  # one step == one logical launch of the hot path (kSubBatch chunks are back to back)
     achieved = algo_bytes / (hot_ms_per_launch * 1e-3) / 1e9 if hot_ms_per_launch > 0 else None
     if rank == 0:
@@ -301,7 +306,7 @@ def run_ours(args):
                        "not_in_step": "text formatting of the report files and the medians over genes (host, once per sample)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
                          "hot_kernel_ms_per_step": hot_ms_per_launch},
             "cpu_baseline": cpu_baseline,
             "sanity": {"mapped_reads": res.counter("Mapped Reads"), "exonic_reads": res.counter("Exonic Reads"),
