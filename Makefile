@@ -11,7 +11,7 @@ BINDIR   := rnaseqc_b200/bin
 OBJDIR   := build
 ODIR     := oracle/_build
 
-HOST_SRCS := annotation.cpp alnreader.cpp report.cpp pipeline.cpp
+HOST_SRCS := annotation.cpp alnreader.cpp bamparallel.cpp report.cpp pipeline.cpp
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
@@ -30,18 +30,18 @@ $(LIBDIR)/librsq_b200.so: $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h include/rsq_
 
 $(LIBDIR)/librsq_host.so: $(HOST_OBJS) $(OBJDIR)/host/host_capi.o
 	@mkdir -p $(LIBDIR)
-	$(CXX) -shared -o $@ $^ -lz -ldl
+	$(CXX) -shared -o $@ $^ -lz -ldl -lpthread
 
 $(BINDIR)/rnaseqc: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(LIBDIR)/librsq_b200.so
 	@mkdir -p $(BINDIR)
-	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(LIBDIR) -lrsq_b200 -lz -Wl,-rpath,'$$ORIGIN/../lib'
+	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(LIBDIR) -lrsq_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../lib'
 
 $(ODIR)/librsq_oracle.so: oracle/rsq_oracle.cpp include/rsq_b200.h
 	@mkdir -p $(ODIR)
 	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Iinclude -shared -o $@ $<
 
 $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
-	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -Wl,-rpath,'$$ORIGIN'
+	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'
 
 clean:
 	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) $(ODIR)

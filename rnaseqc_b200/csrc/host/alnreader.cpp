@@ -336,7 +336,6 @@ bool Decoder::any_overlap_with(const std::vector<uint8_t>& contig_has_features) 
 }
 
 void Decoder::convert(const RawAln& a, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks) {
-    ++alignment_count_;
     rsq_read r;
     memset(&r, 0, sizeof(r));
     r.pos = a.pos;
@@ -410,24 +409,33 @@ void Decoder::convert(const RawAln& a, std::vector<rsq_read>& reads, std::vector
     if (a.l_qseq > 0) r.endpos = (!(a.flag & RSQ_F_UNMAP) && !a.cigar.empty()) ? (int32_t)(a.pos + rlen) : a.pos + 1;
     else r.endpos = (int32_t)(a.pos + qlen);
 
+    observe(r, a.tid);
+    reads.push_back(r);
+}
+
+void Decoder::observe(rsq_read& r, int32_t tid) {
+    ++alignment_count_;
+    const int n_refs = (int)tid_to_contig_.size();
+    const bool tid_ok = tid >= 0 && tid < n_refs;
+    const int chr = tid_ok ? tid_to_contig_[tid] : -1;
     // ---- order-dependent scalar state: the same gates as the loop, in the same order -----------------------
     const bool has_ch = r.aux & RSQ_AUX_CHIMERIC_TAG;
     bool reaches_metrics = false;
     do {
-        if ((a.flag & RSQ_F_SUPPLEMENTARY) && !has_ch && opt_.exclude_chimeric) break;           // :258-262
-        if (a.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) break;               // :263
-        if (a.flag & RSQ_F_UNMAP) break;                                                           // :268
+        if ((r.flag & RSQ_F_SUPPLEMENTARY) && !has_ch && opt_.exclude_chimeric) break;           // :258-262
+        if (r.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) break;               // :263
+        if (r.flag & RSQ_F_UNMAP) break;                                                           // :268
         const unsigned alignment_size = (unsigned)(r.endpos - r.pos);                              // :275
         if (!read_length_ && tid_ok) current_chrom_ = chr;                                         // :277
-        if (alignment_size > (unsigned)read_length_) read_length_ = a.l_qseq;                      // :278
+        if (alignment_size > (unsigned)read_length_) read_length_ = r.l_qseq;                      // :278
         if (has_ch && opt_.exclude_chimeric) break;                                                // :279-283
-        if ((a.flag & RSQ_F_PAIRED) && !(a.flag & RSQ_F_MUNMAP)) {                                 // :284-292
-            const bool chim = a.tid != a.mtid || std::abs(a.pos - a.mpos) > opt_.chimeric_distance;
+        if ((r.flag & RSQ_F_PAIRED) && !(r.flag & RSQ_F_MUNMAP)) {                                 // :284-292
+            const bool chim = (r.aux & RSQ_AUX_MATE_OTHER_CONTIG) || std::abs(r.pos - r.mpos) > opt_.chimeric_distance;
             if (chim && opt_.exclude_chimeric) break;
         }
         if (r.filter_mask) break;                                                                  // :319-328
         if (!tid_ok) {                                                                             // :333-337
-            if (opt_.verbosity) std::cerr << "Unrecognized RefID on alignment: " << a.qname << std::endl;
+            if (opt_.verbosity) std::cerr << "Unrecognized RefID on alignment #" << alignment_count_ << std::endl;
             break;
         }
         reaches_metrics = true;
@@ -441,15 +449,112 @@ void Decoder::convert(const RawAln& a, std::vector<rsq_read>& reads, std::vector
                 dropped_[current_chrom_] = 1;
             }
             current_chrom_ = chr;
-        } else if (last_position_ > a.pos && !warned_unsorted_) {                                  // :354-355
+        } else if (last_position_ > r.pos && !warned_unsorted_) {                                  // :354-355
             std::cerr << "Warning: The input bam does not appear to be sorted. An unsorted bam will yield incorrect results" << std::endl;
             warned_unsorted_ = true;
         }
-        last_position_ = a.pos;
+        last_position_ = r.pos;
         last_metrics_chrom_ = chr;
         if (dropped_[chr]) r.aux |= RSQ_AUX_CONTIG_DROPPED;
     }
-    reads.push_back(r);
+}
+
+// Pure conversion of one raw BAM record (no RawAln intermediate): same field semantics as convert(RawAln).
+void Decoder::convert_bam_bytes(const uint8_t* b, size_t n, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid_out) const {
+    if (n < 32) throw HostError(-1, "truncated BAM record");
+    auto i32 = [&](size_t o) { int32_t v; memcpy(&v, b + o, 4); return v; };
+    auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, b + o, 2); return v; };
+    memset(&r, 0, sizeof(r));
+    const int32_t tid = i32(0), mtid = i32(20);
+    tid_out = tid;
+    r.pos = i32(4);
+    const uint8_t l_read_name = b[8];
+    r.mapq = b[9];
+    const uint16_t n_cigar = u16(12);
+    r.flag = u16(14);
+    r.l_qseq = i32(16);
+    r.mpos = i32(24);
+    r.isize = i32(28);
+    size_t o = 32;
+    if (o + l_read_name + 4 * (size_t)n_cigar > n) throw HostError(-1, "truncated BAM record");
+    r.name_hash = hash_qname((const char*)b + o, l_read_name ? l_read_name - 1 : 0);
+    o += l_read_name;
+    // CIGAR -> blocks
+    r.block_off = (uint32_t)blocks.size();
+    int64_t start = (int64_t)r.pos + 1, rlen = 0, qlen = 0;
+    unsigned nb = 0;
+    for (unsigned k = 0; k < n_cigar; ++k) {
+        uint32_t c; memcpy(&c, b + o + 4 * k, 4);
+        const unsigned op = c & 0xf;
+        const int64_t len = c >> 4;
+        switch (op) {
+            case 0: case 7: case 8: blocks.push_back(rsq_block{(int32_t)start, (int32_t)len}); ++nb; start += len; rlen += len; qlen += len; break;
+            case 2: case 3: start += len; rlen += len; break;
+            case 1: case 4: qlen += len; break;
+            case 5: case 6: break;
+            default:
+                std::cerr << "Bad cigar operation: " << (op < 10 ? kCigarOps[op] : '?') << std::endl;
+                throw HostError(7, "Invalid argument type provided: Unrecognized Cigar Op ");
+        }
+    }
+    if (nb > 0xffff) throw HostError(-1, "alignment with more than 65535 aligned blocks");
+    r.n_blocks = (uint16_t)nb;
+    if (r.l_qseq > 0) r.endpos = (!(r.flag & RSQ_F_UNMAP) && n_cigar) ? (int32_t)(r.pos + rlen) : r.pos + 1;
+    else r.endpos = (int32_t)(r.pos + qlen);
+    o += 4 * (size_t)n_cigar;
+    o += ((size_t)r.l_qseq + 1) / 2 + (size_t)r.l_qseq;
+    // aux: first occurrence of each tag wins (bam_aux_get)
+    bool nm_seen = false, ch_seen = false;
+    unsigned filt_seen = 0;
+    const char c0 = opt_.chimeric_tag.size() == 2 ? opt_.chimeric_tag[0] : 0, c1 = opt_.chimeric_tag.size() == 2 ? opt_.chimeric_tag[1] : 0;
+    while (o + 3 <= n) {
+        const char t0 = (char)b[o], t1 = (char)b[o + 1], type = (char)b[o + 2];
+        o += 3;
+        int64_t ival = 0;
+        switch (type) {
+            case 'A': ival = b[o]; o += 1; break;
+            case 'c': ival = (int8_t)b[o]; o += 1; break;
+            case 'C': ival = b[o]; o += 1; break;
+            case 's': { int16_t v; memcpy(&v, b + o, 2); ival = v; o += 2; break; }
+            case 'S': { uint16_t v; memcpy(&v, b + o, 2); ival = v; o += 2; break; }
+            case 'i': { int32_t v; memcpy(&v, b + o, 4); ival = v; o += 4; break; }
+            case 'I': { uint32_t v; memcpy(&v, b + o, 4); ival = v; o += 4; break; }
+            case 'f': o += 4; break;
+            case 'd': o += 8; break;
+            case 'Z': case 'H': while (o < n && b[o]) ++o; ++o; break;
+            case 'B': {
+                if (o + 5 > n) throw HostError(-1, "corrupt BAM aux field");
+                const char sub = (char)b[o];
+                int32_t cnt; memcpy(&cnt, b + o + 1, 4);
+                const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                o += 5 + es * (size_t)cnt;
+                break;
+            }
+            default: throw HostError(-1, "corrupt BAM aux field");
+        }
+        const bool is_int = type == 'i' || type == 'C' || type == 'S' || type == 's' || type == 'I' || type == 'c';
+        if (!nm_seen && t0 == 'N' && t1 == 'M') {
+            nm_seen = true;
+            if (is_int) { r.aux |= RSQ_AUX_HAS_NM; r.nm = (int32_t)ival; }
+        }
+        if (!ch_seen && c0 && t0 == c0 && t1 == c1) {
+            ch_seen = true;
+            if (type == 'Z' || (type == 'A' && ival != 0)) r.aux |= RSQ_AUX_CHIMERIC_TAG;
+        }
+        for (size_t k = 0; k < opt_.filter_tags.size(); ++k) {
+            const std::string& t = opt_.filter_tags[k];
+            if (!(filt_seen & (1u << k)) && t.size() == 2 && t0 == t[0] && t1 == t[1]) {
+                filt_seen |= 1u << k;
+                if (type == 'Z' || is_int || type == 'f' || type == 'd') r.filter_mask |= (uint8_t)(1u << k);
+            }
+        }
+    }
+    if (tid != mtid) r.aux |= RSQ_AUX_MATE_OTHER_CONTIG;
+    const int n_refs = (int)tid_to_contig_.size();
+    const bool tid_ok = tid >= 0 && tid < n_refs;
+    if (!tid_ok) r.aux |= RSQ_AUX_TID_OUT_OF_RANGE;
+    const int chr = tid_ok ? tid_to_contig_[tid] : -1;
+    r.contig = (chr >= 0 && (size_t)chr < n_annotation_contigs_ && chr <= INT16_MAX) ? (int16_t)chr : (int16_t)-1;
 }
 
 }  // namespace rsqh

@@ -64,6 +64,12 @@ public:
     // Appends one record (and its blocks) to the batch vectors.  Throws HostError(7) on an unknown CIGAR op
     // (src/Expression.cpp:61-63).
     void convert(const RawAln& aln, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
+    // The two halves of convert() for the multi-threaded BAM path (bamparallel.cpp):
+    //  - convert_bam_bytes: PURE (thread-safe) conversion of one raw BAM record (the bytes after block_size);
+    //    r.block_off is relative to `blocks`; tid receives core.tid
+    //  - observe: the order-dependent scalar state, must be called in file order
+    void convert_bam_bytes(const uint8_t* rec, size_t len, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid) const;
+    void observe(rsq_read& r, int32_t tid);
 
     int read_length() const { return read_length_; }
     uint64_t alignment_count() const { return alignment_count_; }

@@ -1,0 +1,308 @@
+// bamparallel.cpp — multi-threaded BAM ingest (see bamparallel.h).
+//
+// Pipeline (all stages overlap):
+//   reader thread : sequential file read, BGZF block framing, groups ~4 MB of blocks into a job
+//   workers       : inflate a job (raw deflate per block)           -> job.out
+//                   FRAME the next job in file order (sequential, tiny: hops over block_size fields, carries the partial
+//                   record at the end of a job into the head-room of the next)
+//                   CONVERT a framed job: every whole BAM record -> rsq_read + rsq_block (Decoder::convert_bam_bytes, pure)
+//   consumer      : next_batch(): takes converted jobs in file order, runs Decoder::observe (readLength, contig-drop
+//                   state, unsorted warning: src/RNASeQC.cpp:275-278,346-356) and appends to the caller's batch
+#include "bamparallel.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace rsqh {
+
+namespace {
+constexpr size_t kJobUncompressed = 4u << 20;   // target decompressed bytes per job
+constexpr size_t kHeadroom = 256u << 10;        // room in front of a job's output for the previous job's partial record
+
+enum { ST_READ = 0, ST_INFLATING, ST_INFLATED, ST_FRAMING, ST_FRAMED, ST_CONVERTING, ST_CONVERTED };
+
+// Reads one BGZF block from fp into `dst` (appended).  Returns false at clean EOF.
+bool read_bgzf_block(FILE* fp, std::vector<uint8_t>& dst, uint32_t& payload_off, uint32_t& payload_len, uint32_t& isize) {
+    uint8_t h[12];
+    size_t r = std::fread(h, 1, 12, fp);
+    if (r == 0) return false;
+    if (r < 12 || h[0] != 0x1f || h[1] != 0x8b) throw HostError(-1, "corrupt BGZF block header");
+    const unsigned xlen = h[10] | (h[11] << 8);
+    uint8_t extra[256];
+    std::vector<uint8_t> big;
+    uint8_t* ex = extra;
+    if (xlen > sizeof(extra)) { big.resize(xlen); ex = big.data(); }
+    if (std::fread(ex, 1, xlen, fp) != xlen) throw HostError(-1, "truncated BGZF block");
+    int bsize = -1;
+    for (size_t i = 0; i + 4 <= xlen;) {
+        const unsigned slen = ex[i + 2] | (ex[i + 3] << 8);
+        if (ex[i] == 'B' && ex[i + 1] == 'C' && slen == 2) bsize = ex[i + 4] | (ex[i + 5] << 8);
+        i += 4 + slen;
+    }
+    if (bsize < 0) throw HostError(-1, "BGZF block without BC subfield");
+    const size_t cdata = (size_t)bsize + 1 - 12 - xlen - 8;
+    const size_t at = dst.size();
+    dst.resize(at + cdata + 8);
+    if (std::fread(dst.data() + at, 1, cdata + 8, fp) != cdata + 8) throw HostError(-1, "truncated BGZF block");
+    memcpy(&isize, dst.data() + at + cdata + 4, 4);
+    payload_off = (uint32_t)at;
+    payload_len = (uint32_t)cdata;
+    return true;
+}
+
+void inflate_block(const uint8_t* src, size_t n, uint8_t* dst, size_t isize) {
+    if (!isize) return;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) throw HostError(-1, "zlib init failed");
+    zs.next_in = const_cast<uint8_t*>(src);
+    zs.avail_in = (uInt)n;
+    zs.next_out = dst;
+    zs.avail_out = (uInt)isize;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) throw HostError(-1, "BGZF inflate failed");
+}
+}  // namespace
+
+struct ParallelBamDecoder::Job {
+    uint64_t id = 0;
+    std::vector<uint8_t> comp;
+    std::vector<uint32_t> c_off, c_len, u_len;
+    std::vector<uint8_t> out;          // [kHeadroom | inflated bytes]
+    size_t data_len = 0;
+    size_t rec_begin = 0, rec_end = 0; // whole records inside `out`
+    std::vector<uint8_t> big;          // only when the carried partial record exceeds the head-room
+    bool use_big = false;
+    std::vector<rsq_read> reads;
+    std::vector<rsq_block> rblocks;
+    std::vector<int32_t> tids;
+    std::string error;
+    int error_code = 0;
+    int state = ST_READ;
+};
+
+ParallelBamDecoder::ParallelBamDecoder(const std::string& path, int n_threads)
+    : path_(path), n_threads_(std::max(1, n_threads)) {
+    fp_ = std::fopen(path.c_str(), "rb");
+    if (!fp_) throw HostError(10, "Unable to open BAM file: " + path);
+    // header: sequential inflate of the first block(s)
+    {
+        std::vector<uint8_t> text;
+        auto need = [&](size_t n) {
+            while (text.size() < n) {
+                std::vector<uint8_t> comp;
+                uint32_t off, len, isize;
+                if (!read_bgzf_block(fp_, comp, off, len, isize)) throw HostError(-1, "truncated BAM header");
+                const size_t at = text.size();
+                text.resize(at + isize);
+                inflate_block(comp.data() + off, len, text.data() + at, isize);
+            }
+        };
+        need(12);
+        if (memcmp(text.data(), "BAM\1", 4) != 0) throw HostError(-1, "not a BAM file: " + path);
+        int32_t l_text; memcpy(&l_text, text.data() + 4, 4);
+        size_t p = 8 + (size_t)l_text;
+        need(p + 4);
+        int32_t n_ref; memcpy(&n_ref, text.data() + p, 4);
+        p += 4;
+        for (int i = 0; i < n_ref; ++i) {
+            need(p + 4);
+            int32_t l_name; memcpy(&l_name, text.data() + p, 4);
+            need(p + 4 + l_name + 4);
+            std::string name((const char*)text.data() + p + 4, l_name > 0 ? l_name - 1 : 0);
+            int32_t l_ref; memcpy(&l_ref, text.data() + p + 4 + l_name, 4);
+            hdr_.ref_names.push_back(name);
+            hdr_.ref_lens.push_back(l_ref);
+            p += 8 + (size_t)l_name;
+        }
+        skip_bytes_ = p;
+        std::fseek(fp_, 0, SEEK_SET);
+    }
+    max_jobs_in_flight_ = (size_t)n_threads_ * 3 + 4;
+}
+
+ParallelBamDecoder::~ParallelBamDecoder() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_work_.notify_all();
+    cv_reader_.notify_all();
+    cv_consumer_.notify_all();
+    if (reader_.joinable()) reader_.join();
+    for (auto& t : workers_) if (t.joinable()) t.join();
+    jobs_.clear();
+    if (fp_) std::fclose(fp_);
+}
+
+void ParallelBamDecoder::reader_loop() {
+    try {
+        bool eof = false;
+        while (!eof) {
+            auto job = std::make_shared<Job>();
+            size_t total = 0;
+            while (total < kJobUncompressed) {
+                uint32_t off, len, isize;
+                if (!read_bgzf_block(fp_, job->comp, off, len, isize)) { eof = true; break; }
+                job->c_off.push_back(off); job->c_len.push_back(len); job->u_len.push_back(isize);
+                total += isize;
+            }
+            if (job->c_off.empty()) break;
+            job->data_len = total;
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_reader_.wait(lk, [&] { return stop_ || jobs_.size() < max_jobs_in_flight_; });
+            if (stop_) return;
+            job->id = next_job_id_++;
+            jobs_.push_back(job);
+            lk.unlock();
+            cv_work_.notify_one();
+        }
+    } catch (HostError& e) {
+        auto job = std::make_shared<Job>();
+        job->error = e.what(); job->error_code = e.exit_code; job->state = ST_CONVERTED;
+        std::lock_guard<std::mutex> lk(mu_);
+        job->id = next_job_id_++;
+        jobs_.push_back(job);
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        reader_done_ = true;
+    }
+    cv_work_.notify_all();
+    cv_consumer_.notify_all();
+}
+
+void ParallelBamDecoder::worker_loop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+        if (stop_) return;
+        auto& q = jobs_;
+        std::shared_ptr<Job> todo;
+        int what = 0;   // 1 frame, 2 convert, 3 inflate
+        // 1. framing is sequential: only the job whose id is next_frame_id_, and only one framer at a time (carry_ is its state)
+        for (auto& j : q)
+            if (j->id == next_frame_id_ && j->state == ST_INFLATED) { todo = j; what = 1; j->state = ST_FRAMING; break; }
+        if (!todo) for (auto& j : q) if (j->state == ST_FRAMED) { todo = j; what = 2; j->state = ST_CONVERTING; break; }
+        if (!todo) for (auto& j : q) if (j->state == ST_READ) { todo = j; what = 3; j->state = ST_INFLATING; break; }
+        if (!todo) {
+            if (reader_done_ && q.empty()) return;
+            cv_work_.wait(lk);
+            continue;
+        }
+        lk.unlock();
+        try {
+            if (what == 3) {
+                todo->out.resize(kHeadroom + todo->data_len);
+                size_t o = kHeadroom;
+                for (size_t b = 0; b < todo->c_off.size(); ++b) {
+                    inflate_block(todo->comp.data() + todo->c_off[b], todo->c_len[b], todo->out.data() + o, todo->u_len[b]);
+                    o += todo->u_len[b];
+                }
+                std::vector<uint8_t>().swap(todo->comp);
+            } else if (what == 1) {
+                // frame: [carry | data] must be contiguous; then hop over whole records
+                uint8_t* base = todo->out.data();
+                size_t begin = kHeadroom, end = kHeadroom + todo->data_len;
+                if (skip_bytes_) {                           // BAM header bytes in front of the first record
+                    const size_t s = (size_t)std::min<uint64_t>(skip_bytes_, todo->data_len);
+                    begin += s; skip_bytes_ -= s;
+                }
+                if (!carry_.empty()) {
+                    if (carry_.size() <= begin) { begin -= carry_.size(); memcpy(base + begin, carry_.data(), carry_.size()); }
+                    else {
+                        todo->big.resize(carry_.size() + (end - begin));
+                        memcpy(todo->big.data(), carry_.data(), carry_.size());
+                        memcpy(todo->big.data() + carry_.size(), base + begin, end - begin);
+                        todo->use_big = true; base = todo->big.data(); begin = 0; end = todo->big.size();
+                    }
+                    carry_.clear();
+                }
+                size_t p = begin;
+                while (p + 4 <= end) {
+                    uint32_t bs; memcpy(&bs, base + p, 4);
+                    if (bs < 32) throw HostError(-1, "truncated BAM record");
+                    if (p + 4 + (size_t)bs > end) break;
+                    p += 4 + (size_t)bs;
+                }
+                todo->rec_begin = begin; todo->rec_end = p;
+                carry_.assign(base + p, base + end);
+            } else {
+                const uint8_t* base = todo->use_big ? todo->big.data() : todo->out.data();
+                size_t p = todo->rec_begin;
+                todo->reads.reserve((todo->rec_end - todo->rec_begin) / 200 + 16);
+                while (p < todo->rec_end) {
+                    uint32_t bs; memcpy(&bs, base + p, 4);
+                    rsq_read r; int32_t tid;
+                    dec_for_params_->convert_bam_bytes(base + p + 4, bs, r, todo->rblocks, tid);
+                    todo->reads.push_back(r);
+                    todo->tids.push_back(tid);
+                    p += 4 + (size_t)bs;
+                }
+                std::vector<uint8_t>().swap(todo->out);
+                std::vector<uint8_t>().swap(todo->big);
+            }
+        } catch (HostError& e) {
+            todo->error = e.what(); todo->error_code = e.exit_code ? e.exit_code : -1;
+        } catch (std::exception& e) {
+            todo->error = e.what(); todo->error_code = -1;
+        }
+        lk.lock();
+        if (!todo->error.empty()) {
+            // a failed job surfaces at the consumer when its turn comes; framing moves past it so earlier records still flow
+            if (todo->id == next_frame_id_) ++next_frame_id_;
+            todo->state = ST_CONVERTED;
+            cv_consumer_.notify_all();
+        } else if (what == 3) todo->state = ST_INFLATED;
+        else if (what == 1) { todo->state = ST_FRAMED; ++next_frame_id_; }
+        else { todo->state = ST_CONVERTED; cv_consumer_.notify_all(); }
+        cv_work_.notify_all();
+    }
+}
+
+bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks) {
+    reads.clear();
+    blocks.clear();
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (!params_set_) {
+            dec_for_params_ = &dec;
+            params_set_ = true;
+            reader_ = std::thread(&ParallelBamDecoder::reader_loop, this);
+            for (int t = 0; t < n_threads_; ++t) workers_.emplace_back(&ParallelBamDecoder::worker_loop, this);
+        }
+    }
+    while (reads.size() < max_records) {
+        std::shared_ptr<Job> job = cur_;
+        if (!job) {
+            std::unique_lock<std::mutex> lk(mu_);
+            auto& q = jobs_;
+            cv_consumer_.wait(lk, [&] { return stop_ || (!q.empty() && q.front()->state == ST_CONVERTED) || (reader_done_ && q.empty()); });
+            if (stop_ || q.empty()) break;
+            job = q.front();
+            q.pop_front();
+            lk.unlock();
+            cv_reader_.notify_one();
+            cv_work_.notify_all();
+            if (!job->error.empty()) throw HostError(job->error_code, job->error);
+            cur_ = job;
+            cur_read_ = 0;
+        }
+        const size_t n = std::min(job->reads.size() - cur_read_, max_records - reads.size());
+        for (size_t k = 0; k < n; ++k) {
+            rsq_read r = job->reads[cur_read_ + k];
+            const rsq_block* src = job->rblocks.data() + r.block_off;
+            r.block_off = (uint32_t)blocks.size();
+            blocks.insert(blocks.end(), src, src + r.n_blocks);
+            dec.observe(r, job->tids[cur_read_ + k]);
+            reads.push_back(r);
+        }
+        cur_read_ += n;
+        if (cur_read_ >= job->reads.size()) { cur_.reset(); cur_read_ = 0; }
+    }
+    return !reads.empty();
+}
+
+}  // namespace rsqh

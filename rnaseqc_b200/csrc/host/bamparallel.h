@@ -1,0 +1,61 @@
+// bamparallel.h — multi-threaded BAM ingest: BGZF blocks are inflated and BAM records are
+// converted to rsq_read/rsq_block by a pool of worker threads; only the cheap framing of the record stream and the
+// order-dependent scalar state of the reference loop (Decoder::observe) stay sequential.
+//
+// The reference decodes on the loop's own thread through SeqLib -> htslib sam_read1 (src/BamReader.cpp:12-27,
+// SeqLib/src/BamReader.cpp:233-256); htslib's thread pool exists there (SeqLib/src/BamReader.cpp:176-183) but rnaseqc
+// never enables it.  Here ingest scales with host cores so that the GPU hot path is fed at tens of M records/s.
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "alnreader.h"
+
+namespace rsqh {
+
+class ParallelBamDecoder {
+public:
+    // n_threads worker threads (>= 1) besides one file-reader thread; throws HostError(10) if the file cannot be opened
+    ParallelBamDecoder(const std::string& path, int n_threads);
+    ~ParallelBamDecoder();
+    const AlnHeader& header() const { return hdr_; }
+    // Appends up to max_records converted records (with their blocks) to the cleared vectors, in file order, running
+    // dec.observe() on each.  Returns false once the stream is exhausted and nothing was appended.
+    bool next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
+
+private:
+    struct Job;                        // one ~4 MB piece of the decompressed stream (bamparallel.cpp)
+    void reader_loop();
+    void worker_loop();
+
+    std::string path_;
+    AlnHeader hdr_;
+    uint64_t skip_bytes_ = 0;          // uncompressed bytes of the BAM header in front of the first record
+    FILE* fp_ = nullptr;
+    int n_threads_;
+    std::thread reader_;
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_consumer_, cv_reader_;
+    std::deque<std::shared_ptr<Job>> jobs_;        // in file order; front = oldest not yet consumed
+    uint64_t next_job_id_ = 0;
+    uint64_t next_frame_id_ = 0;       // framing is sequential: the next job id to frame
+    std::vector<uint8_t> carry_;       // partial record at the end of the last framed job
+    bool reader_done_ = false, stop_ = false;
+    size_t max_jobs_in_flight_;
+    // conversion parameters (copied from the Decoder at the first next_batch)
+    bool params_set_ = false;
+    const Decoder* dec_for_params_ = nullptr;
+    // consumer cursor
+    std::shared_ptr<Job> cur_;
+    size_t cur_read_ = 0;
+};
+
+}  // namespace rsqh

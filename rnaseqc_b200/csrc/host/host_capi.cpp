@@ -6,6 +6,7 @@
 #include <string>
 
 #include "alnreader.h"
+#include "bamparallel.h"
 #include "annotation.h"
 #include "pipeline.h"
 #include "report.h"
@@ -13,6 +14,7 @@
 using namespace rsqh;
 
 namespace {
+int g_decode_threads = 0;
 struct Handle {
     Annotation ann;
     BedModel bed;
@@ -97,12 +99,32 @@ int rsqh_decode_file(void* hv, const char* path, const char* chimeric_tag, const
         opt.exclude_chimeric = exclude_chimeric != 0;
         opt.chimeric_distance = chimeric_distance;
         const size_t n_ann_contigs = h->ann.genes_by_contig.size();
-        std::unique_ptr<AlnReader> rd = AlnReader::open(path);
-        Decoder dec(rd->header(), h->ann.contigs, n_ann_contigs, opt);
         std::vector<rsq_read> R;
         std::vector<rsq_block> B;
-        RawAln a;
-        while (rd->next(a)) dec.convert(a, R, B);
+        std::unique_ptr<AlnReader> rd;
+        std::unique_ptr<ParallelBamDecoder> pb;
+        const int threads = g_decode_threads;
+        if (threads > 0) {
+            FILE* fp = std::fopen(path, "rb");
+            unsigned char m[2] = {0, 0};
+            if (fp) { if (std::fread(m, 1, 2, fp) != 2) m[0] = 0; std::fclose(fp); }
+            if (m[0] == 0x1f && m[1] == 0x8b) pb.reset(new ParallelBamDecoder(path, threads));
+        }
+        if (!pb) rd = AlnReader::open(path);
+        Decoder dec(pb ? pb->header() : rd->header(), h->ann.contigs, n_ann_contigs, opt);
+        if (pb) {
+            std::vector<rsq_read> r1;
+            std::vector<rsq_block> b1;
+            while (pb->next_batch(dec, 1u << 20, r1, b1)) {
+                const uint32_t base = (uint32_t)B.size();
+                for (rsq_read& r : r1) r.block_off += base;
+                R.insert(R.end(), r1.begin(), r1.end());
+                B.insert(B.end(), b1.begin(), b1.end());
+            }
+        } else {
+            RawAln a;
+            while (rd->next(a)) dec.convert(a, R, B);
+        }
         *n_reads = R.size();
         *n_blocks = B.size();
         *reads = (rsq_read*)malloc(std::max<size_t>(R.size(), 1) * sizeof(rsq_read));
@@ -127,6 +149,8 @@ int rsqh_decode_file(void* hv, const char* path, const char* chimeric_tag, const
     }
 }
 void rsqh_free(void* p) { free(p); }
+// worker threads for BAM decode in rsqh_decode_file (0 = sequential reader)
+void rsqh_set_decode_threads(int n) { g_decode_threads = n; }
 
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
 

@@ -1,10 +1,13 @@
 // pipeline.cpp — host driver (see pipeline.h).
 #include "pipeline.h"
 
+#include "bamparallel.h"
+
 #include <chrono>
 #include <cstring>
 #include <filesystem>
 #include <iostream>
+#include <thread>
 
 namespace rsqh {
 
@@ -43,6 +46,8 @@ void usage(std::ostream& o) {
          "      --coverage-mask=[SIZE]            Bases masked at both transcript ends for coverage. Default: 500bp\n"
          "      -d[threshold], --detection-threshold=[threshold]  Counts on a gene to consider it detected. Default: 5\n"
          "      --batch-records=[N]               Records per device batch (this build). Default: 1048576\n"
+         "      --decode-threads=[N]              BAM inflate/convert worker threads (this build); 0 = sequential reader.\n"
+         "                                        Default: hardware threads, at most 32\n"
          "      --exact-complexity                Literal 1e9-iteration library-complexity scan (this build)\n";
 }
 
@@ -110,6 +115,7 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
             else if (is("coverage-mask")) opt.run.coverage_mask = (unsigned)std::stoul(value("coverage-mask", 0));
             else if (is("detection-threshold", 'd')) opt.run.detection_threshold = (unsigned)std::stoul(value("detection-threshold", 'd'));
             else if (is("batch-records")) opt.batch_records = std::stoul(value("batch-records", 0));
+            else if (is("decode-threads")) opt.decode_threads = std::stoi(value("decode-threads", 0));
             else if (is("device")) opt.cfg.device = std::stoi(value("device", 0));
             else if (a == "--exact-complexity") opt.run.exact_complexity_scan = true;
             else if (a.size() > 1 && a[0] == '-') throw ArgError{5, "Flag could not be matched: " + a};
@@ -148,6 +154,7 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
     }
     opt.cfg.n_filter_tags = (uint32_t)opt.decode.filter_tags.size();
     opt.cfg.fragment_samples = opt.bed.empty() ? 0u : fragment_samples;
+    if (opt.decode_threads < 0) opt.decode_threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
     opt.decode.exclude_chimeric = opt.cfg.exclude_chimeric;
     opt.decode.chimeric_distance = opt.cfg.chimeric_distance;
     opt.decode.verbosity = opt.verbosity;
@@ -221,8 +228,20 @@ int run_sample(const Backend& be, CliOptions& opt) {
             throw HostError(8, std::string("Filesystem error:  ") + e.what());
         }
 
-        std::unique_ptr<AlnReader> reader = AlnReader::open(opt.bam);
-        Decoder decoder(reader->header(), A.contigs, n_contigs, opt.decode);
+        // BAM goes through the multi-threaded ingest (bamparallel.cpp); SAM text through the sequential reader
+        std::unique_ptr<AlnReader> reader;
+        std::unique_ptr<ParallelBamDecoder> pbam;
+        {
+            FILE* fp = std::fopen(opt.bam.c_str(), "rb");
+            if (!fp) throw HostError(10, "Unable to open BAM file: " + opt.bam);
+            unsigned char m[2] = {0, 0};
+            const size_t got = std::fread(m, 1, 2, fp);
+            std::fclose(fp);
+            if (got == 2 && m[0] == 0x1f && m[1] == 0x8b && opt.decode_threads > 0) pbam.reset(new ParallelBamDecoder(opt.bam, opt.decode_threads));
+            else reader = AlnReader::open(opt.bam);
+        }
+        const AlnHeader& aln_header = pbam ? pbam->header() : reader->header();
+        Decoder decoder(aln_header, A.contigs, n_contigs, opt.decode);
         {
             std::vector<uint8_t> has_features(A.contigs.names.size(), 0);
             for (size_t c = 0; c < A.genes_by_contig.size(); ++c)
@@ -253,11 +272,16 @@ int run_sample(const Backend& be, CliOptions& opt) {
         int slot = 0;
         bool more = true;
         while (more) {
-            reads.clear();
-            blocks.clear();
-            while (reads.size() < opt.batch_records) {
-                if (!reader->next(aln)) { more = false; break; }
-                decoder.convert(aln, reads, blocks);
+            if (pbam) {
+                if (!pbam->next_batch(decoder, opt.batch_records, reads, blocks)) break;
+                more = reads.size() == opt.batch_records;
+            } else {
+                reads.clear();
+                blocks.clear();
+                while (reads.size() < opt.batch_records) {
+                    if (!reader->next(aln)) { more = false; break; }
+                    decoder.convert(aln, reads, blocks);
+                }
             }
             if (reads.empty()) break;
             // stage into page-locked buffers; a slot is reused only after the device drained it

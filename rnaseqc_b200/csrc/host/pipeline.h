@@ -38,6 +38,7 @@ struct CliOptions {
     bool legacy = false;
     std::string fasta;
     size_t batch_records = 1u << 20;
+    int decode_threads = -1;          // -1: hardware threads (<= 32); 0: sequential reader
     int verbosity = 0;
 };
 
