@@ -46,6 +46,14 @@ def compare_outputs(dir_a, dir_b, rel_tol=1e-6):
         for i, (x, y) in enumerate(zip(la, lb)):
             if x == y:
                 continue
+            if x.startswith("3' Bias, ") and "Percentile" in x:
+                # the reference indexes ratios[ceil(.75 n) (+1)] without a bounds check (src/RNASeQC.cpp:486-507): with 2-4
+                # bias genes it prints whatever lies past the vector.  A percentile of ratios outside [0, 1] is that garbage.
+                try:
+                    if not (0.0 <= float(_cells(x)[1]) <= 1.0):
+                        continue
+                except ValueError:
+                    pass
             cx, cy = _cells(x.replace("-nan", "nan")), _cells(y.replace("-nan", "nan"))
             assert len(cx) == len(cy), f"{f}:{i + 1}: {x!r} vs {y!r}"
             for u, v in zip(cx, cy):
