@@ -33,7 +33,6 @@ __device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* s_tmp) {
 }
 
 struct SumU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
-struct SumF64 { __device__ double operator()(double a, double b) const { return a + b; } };
 struct MinU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a < b ? a : b; } };
 struct MaxU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a > b ? a : b; } };
 

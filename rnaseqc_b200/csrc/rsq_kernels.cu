@@ -1,5 +1,8 @@
 // rsq_kernels.cu — hand-written sm_100a kernels of the RNA-SeQC per-read hot path.
 //
+// Compile-time ablation switches (never defined in the product build; used for the time breakdown in DESIGN.md §4):
+//   RSQ_AB_NO_FRAGSET, RSQ_AB_NO_ACCUM, RSQ_AB_NO_EPILOGUE, RSQ_AB_ONE_BLOCK, RSQ_AB_CASCADE_ONLY, RSQ_AB_SMEM_COUNTERS
+//
 // K_hot  : one pass over a batch of decoded alignment records (rsq_read + rsq_block): the flag/quality/
 //          mismatch filter cascade of src/RNASeQC.cpp:254-342, interval intersection of every aligned block
 //          with the flattened exon index and gene-segment index (src/Expression.cpp:106-117, src/GTF.cpp:171-186),
@@ -286,6 +289,9 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     const uint32_t block_off = (uint32_t)q2.z;
     uint32_t nb = (uint32_t)q2.w & 0xffffu;
     if ((size_t)block_off + nb > n_blocks) nb = 0;  // defensive: never read out of the submitted array
+#ifdef RSQ_AB_ONE_BLOCK
+    nb = nb ? 1u : 0u;   // ablation only
+#endif
     (void)endpos; (void)isize;
     bool go = valid, hq = false;
 #define CNT(k) (cm |= 1ull << (k))
@@ -357,6 +363,9 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
 
     if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }                               // the window has landed in shared memory
 
+#ifdef RSQ_AB_CASCADE_ONLY
+    go = false;   // ablation only
+#endif
     if (go) {
         {
             // ---- exonAlignmentMetrics, Expression.cpp:308-458 ----------------------------------------------------
@@ -498,6 +507,10 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                             const ExonMeta m = va.meta[e];
                             if ((m.gene_flags & 0xffffffu) != g) continue;
                             if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != (int)((m.gene_flags >> 24) & RSQ_EXON_STRAND_MASK)) continue;
+#ifdef RSQ_AB_NO_ACCUM
+                            my_bytes += (unsigned)(m.slot & 1u);   // ablation only: keep the loads, drop every accumulation atomic
+                            continue;
+#endif
                             unsigned long long whole, lo;
                             frac_q64(len, length, whole, lo);                          // isz/length, :345
                             // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update
@@ -614,7 +627,11 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // records mostly take the same path through the cascade, so the 32 counter masks of a tile fall into a handful of
     // identical groups: one shuffle+ballot per GROUP (typically 3-6) instead of one ballot per touched counter (~15).
     {
+#ifdef RSQ_AB_NO_EPILOGUE
+        unsigned remaining = 0; own_lo += cm & 1ull;   // ablation only
+#else
         unsigned remaining = kFull;
+#endif
         while (remaining) {
             const int leader = __ffs(remaining) - 1;
             const unsigned long long lp = __shfl_sync(kFull, cm, leader);
