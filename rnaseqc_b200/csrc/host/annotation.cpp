@@ -30,26 +30,47 @@ bool parse_u64(const std::string& s, unsigned long long& v) {
 // parseAttributes (src/GTF.cpp:146-161): split on every ';' (quotes are NOT honoured), key = text before
 // the first '"' minus its last character, left-trimmed of blanks/tabs; value = text up to the next '"'.
 // A piece with no quote at all leaves the value equal to the whole piece (std::getline does not clear its
-// target once eofbit is set).  Later duplicates overwrite earlier ones (std::map assignment).
-void parse_attributes(const std::string& text, std::map<std::string, std::string>& attrs) {
+// target once eofbit is set).  Later duplicates overwrite earlier ones (std::map assignment).  Only the five keys the
+// reference ever looks up are kept (no per-line std::map: this is the hot loop of GTF loading).
+struct Attrs {
+    bool has_gene_id = false, has_transcript_id = false, has_exon_id = false, has_transcript_type = false, has_gene_name = false;
+    std::string gene_id, transcript_id, exon_id, transcript_type, gene_name;
+};
+
+void parse_attributes(const std::string& text, Attrs& out) {
     size_t pos = 0;
     const size_t n = text.size();
     while (pos < n) {  // getline(tokenizer, buffer, ';') stops yielding once the input is exhausted
         size_t semi = text.find(';', pos);
-        std::string piece = text.substr(pos, semi == std::string::npos ? std::string::npos : semi - pos);
-        pos = (semi == std::string::npos) ? n : semi + 1;
-        std::string key, value;
-        size_t q1 = piece.find('"');
-        std::string head = piece.substr(0, q1 == std::string::npos ? std::string::npos : q1);
-        key = head.empty() ? std::string() : head.substr(0, head.size() - 1);
-        while (!key.empty() && (key[0] == ' ' || key[0] == '\t')) key = key.substr(1);
-        if (q1 == std::string::npos) {
-            value = piece.empty() ? std::string() : piece;  // stale `current` == the piece just read
-        } else {
-            size_t q2 = piece.find('"', q1 + 1);
-            value = piece.substr(q1 + 1, q2 == std::string::npos ? std::string::npos : q2 - q1 - 1);
+        const size_t pe = semi == std::string::npos ? n : semi;          // piece = [pos, pe)
+        const size_t q1 = text.find('"', pos);
+        const bool has_q = q1 != std::string::npos && q1 < pe;
+        size_t ks = pos, ke = has_q ? q1 : pe;                            // head = [ks, ke)
+        if (ke > ks) --ke;                                                // drop the last character of the head
+        while (ks < ke && (text[ks] == ' ' || text[ks] == '\t')) ++ks;
+        const size_t kl = ke - ks;
+        std::string* dst = nullptr;
+        bool* flag = nullptr;
+        switch (kl) {
+            case 7:
+                if (!text.compare(ks, 7, "gene_id")) { dst = &out.gene_id; flag = &out.has_gene_id; }
+                else if (!text.compare(ks, 7, "exon_id")) { dst = &out.exon_id; flag = &out.has_exon_id; }
+                break;
+            case 9: if (!text.compare(ks, 9, "gene_name")) { dst = &out.gene_name; flag = &out.has_gene_name; } break;
+            case 13: if (!text.compare(ks, 13, "transcript_id")) { dst = &out.transcript_id; flag = &out.has_transcript_id; } break;
+            case 15: if (!text.compare(ks, 15, "transcript_type")) { dst = &out.transcript_type; flag = &out.has_transcript_type; } break;
+            default: break;
         }
-        attrs[key] = value;
+        if (dst) {
+            *flag = true;
+            if (!has_q) dst->assign(text, pos, pe - pos);                 // stale `current` == the piece just read
+            else {
+                const size_t q2 = text.find('"', q1 + 1);
+                const size_t ve = (q2 == std::string::npos || q2 > pe) ? pe : q2;
+                dst->assign(text, q1 + 1, ve - q1 - 1);
+            }
+        }
+        pos = (semi == std::string::npos) ? n : semi + 1;
     }
 }
 
@@ -125,27 +146,26 @@ void load_gtf(const std::string& path, Annotation& A) {
         // attributes = the rest of the line, tabs included (getline with '\n')
         if (cur >= line.size()) throw HostError(11, "Failed to parse the GTF: Unable to parse attributes. Invalid GTF line: " + line);
         f_attr = line.substr(cur);
-        std::map<std::string, std::string> attrs;
-        parse_attributes(f_attr, attrs);
+        Attrs at;
+        parse_attributes(f_attr, at);
         const int64_t start = (int64_t)ustart, end = (int64_t)uend;
         if (end < start) std::cerr << "Bad feature range:" << start << " - " << end << std::endl;
 
-        auto has = [&](const char* k) { return attrs.find(k) != attrs.end(); };
-        if (type == T_GENE && has("gene_id")) {
-            cur_feature_id = attrs["gene_id"];
+        if (type == T_GENE && at.has_gene_id) {
+            cur_feature_id = at.gene_id;
             if (seen_gene_ids.count(cur_feature_id))
                 throw HostError(11, "Failed to parse the GTF: Detected non-unique Gene ID: " + cur_feature_id);
             seen_gene_ids.insert(cur_feature_id);
             A.gene_list.push_back(A.gene_universe(cur_feature_id));
         }
-        if (type == T_TRANSCRIPT && has("transcript_id")) cur_feature_id = attrs["transcript_id"];
-        if (has("gene_id")) cur_gene_id = attrs["gene_id"];
+        if (type == T_TRANSCRIPT && at.has_transcript_id) cur_feature_id = at.transcript_id;
+        if (at.has_gene_id) cur_gene_id = at.gene_id;
         uint32_t exon_slot = 0;
         if (type == T_EXON) {
-            if (has("exon_id")) {
-                cur_feature_id = attrs["exon_id"];
-            } else if (has("gene_id")) {
-                const std::string& gid = attrs["gene_id"];
+            if (at.has_exon_id) {
+                cur_feature_id = at.exon_id;
+            } else if (at.has_gene_id) {
+                const std::string& gid = at.gene_id;
                 cur_feature_id = gid + "_" + std::to_string(++unnamed_exon_counter[gid]);
                 std::cerr << "Unnamed exon: Gene: " << gid << " Position: [" << start << ", " << end
                           << "] Inferred Exon Name: " << cur_feature_id << std::endl;
@@ -161,9 +181,9 @@ void load_gtf(const std::string& path, Annotation& A) {
             uint32_t g = A.gene_universe(cur_gene_id);
             A.gene_coding_len[g] += 1 + (end - start);
         }
-        if (has("transcript_type")) cur_transcript_type = attrs["transcript_type"];
-        if (has("gene_name")) gene_names[cur_feature_id] = attrs["gene_name"];
-        else if (has("gene_id")) gene_names[cur_feature_id] = attrs["gene_id"];
+        if (at.has_transcript_type) cur_transcript_type = at.transcript_type;
+        if (at.has_gene_name) gene_names[cur_feature_id] = at.gene_name;
+        else if (at.has_gene_id) gene_names[cur_feature_id] = at.gene_id;
         const bool ribosomal = cur_transcript_type.find("rRNA") != std::string::npos;  // regex "rRNA", src/GTF.cpp:21,113
 
         // main(): keep genes and exons only (src/RNASeQC.cpp:137-139)

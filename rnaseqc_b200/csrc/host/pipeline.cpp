@@ -252,6 +252,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
             }
         }
 
+        auto t_setup = clk::now();
         int rc = be.create(&opt.cfg, &ctx);
         if (rc != RSQ_OK) throw HostError(rc == RSQ_ERR_NO_DEVICE ? 10 : -1, std::string("rsq_create failed: ") + be.last_error(nullptr));
         rsq_annotation av = A.view();
@@ -263,6 +264,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
             if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_bed failed: ") + be.last_error(ctx));
         }
 
+        if (opt.verbosity) std::cout << "Device context + annotation upload: " << std::chrono::duration<double>(clk::now() - t_setup).count() << " seconds" << std::endl;
         if (opt.verbosity) std::cout << "Parsing bam..." << std::endl;
         auto t1 = clk::now();
         std::vector<rsq_read> reads;
@@ -311,6 +313,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
             if (opt.verbosity > 1) std::cout << "Average Reads/Sec: " << (double)decoder.alignment_count() / dt << std::endl;
             std::cout << "Estimating library complexity..." << std::endl;
         }
+        auto t_fin = clk::now();
         HostResults R;
         fetch_results(be, ctx, A, false, R);                     // counts only: the per-base coverage stays on the device
         fetch_coverage_statistics(be, ctx, A, opt.run, R);
@@ -320,8 +323,11 @@ int run_sample(const Backend& be, CliOptions& opt) {
         st.dropped_order = decoder.dropped_order();
         st.final_contig = decoder.current_contig();
         st.final_position = decoder.trim_position();
+        if (opt.verbosity) std::cout << "Finalize + coverage statistics: " << std::chrono::duration<double>(clk::now() - t_fin).count() << " seconds" << std::endl;
         if (opt.verbosity) std::cout << "Generating report" << std::endl;
+        auto t_rep = clk::now();
         write_reports(A, R, opt.run, st);
+        if (opt.verbosity) std::cout << "Report files: " << std::chrono::duration<double>(clk::now() - t_rep).count() << " seconds" << std::endl;
     } catch (HostError& e) {
         std::cerr << e.what() << std::endl;
         exit_code = e.exit_code;

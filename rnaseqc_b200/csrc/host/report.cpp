@@ -343,8 +343,8 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
     {
         std::ofstream w(opt.write_coverage ? base + ".coverage.tsv" : std::string("/dev/null"));
         if (!w.is_open() && opt.write_coverage) throw HostError(-1, "Unable to open BaseCoverage output file");
-        w << "gene_id\tcoverage_mean\tcoverage_std\tcoverage_CV" << std::endl;     // src/Metrics.h:113
-        for (const std::string& r : cov.rows) w << r << std::endl;
+        w << "gene_id\tcoverage_mean\tcoverage_std\tcoverage_CV" << '\n';     // src/Metrics.h:113
+        for (const std::string& r : cov.rows) w << r << '\n';
     }
     const unsigned min_reads = library_complexity((double)C[RSQ_C_DUPLICATE_PAIRS], (double)C[RSQ_C_UNIQUE_FRAGMENTS],
                                                   opt.exact_complexity_scan);
@@ -356,27 +356,27 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         std::ofstream gene_report(base + ".gene_reads.gct");
         std::ofstream gene_rpkm(base + ".gene_" + (opt.use_rpkm ? "rpkm" : "tpm") + ".gct");
         std::ofstream fragment_report(base + ".gene_fragments.gct");
-        gene_report << "#1.2" << std::endl;
-        gene_rpkm << "#1.2" << std::endl;
-        fragment_report << "#1.2" << std::endl;
-        gene_report << A.gene_list.size() << "\t1" << std::endl;
-        gene_rpkm << A.gene_list.size() << "\t1" << std::endl;
-        fragment_report << A.gene_list.size() << "\t1" << std::endl;
-        gene_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << std::endl;
-        gene_rpkm << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : (opt.use_rpkm ? "RPKM" : "TPM")) << std::endl;
+        gene_report << "#1.2" << '\n';
+        gene_rpkm << "#1.2" << '\n';
+        fragment_report << "#1.2" << '\n';
+        gene_report << A.gene_list.size() << "\t1" << '\n';
+        gene_rpkm << A.gene_list.size() << "\t1" << '\n';
+        fragment_report << A.gene_list.size() << "\t1" << '\n';
+        gene_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << '\n';
+        gene_rpkm << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : (opt.use_rpkm ? "RPKM" : "TPM")) << '\n';
         gene_rpkm << std::fixed;
-        fragment_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Fragments") << std::endl;
+        fragment_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Fragments") << '\n';
         const double scale_rpkm = (double)C[RSQ_C_EXONIC_READS] / 1000000.0;
         double scale_tpm = 0.0;
         std::vector<double> tpms(A.gene_list.size(), 0.0);
         for (size_t i = 0; i < A.gene_list.size(); ++i) {
             const uint32_t g = A.gene_list[i];
             const double count = (double)R.gene_reads[g];
-            gene_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_reads[g] << std::endl;
-            fragment_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_fragments[g] << std::endl;
+            gene_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_reads[g] << '\n';
+            fragment_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_fragments[g] << '\n';
             if (opt.use_rpkm) {
                 double rpkm = (1000.0 * count / scale_rpkm) / (double)A.gene_coding_len[g];
-                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << rpkm << std::endl;
+                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << rpkm << '\n';
             } else {
                 double tpm = (1000.0 * count) / (double)A.gene_coding_len[g];
                 tpms[i] = tpm;
@@ -391,7 +391,7 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             scale_tpm /= 1000000.0;
             for (size_t i = 0; i < A.gene_list.size(); ++i) {
                 const uint32_t g = A.gene_list[i];
-                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << tpms[i] / scale_tpm << std::endl;
+                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << tpms[i] / scale_tpm << '\n';
             }
         }
     }
@@ -416,76 +416,76 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         std::ofstream exon_report(base + ".exon_reads.gct");
         size_t nonzero = 0;
         for (size_t e = 0; e < A.exon_ids.size(); ++e) if (R.exon_whole[e] || R.exon_frac[e]) ++nonzero;
-        exon_report << "#1.2" << std::endl;
-        exon_report << nonzero << "\t1" << std::endl;                                  // exonCounts.size(), :513
-        exon_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << std::endl;
+        exon_report << "#1.2" << '\n';
+        exon_report << nonzero << "\t1" << '\n';                                  // exonCounts.size(), :513
+        exon_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << '\n';
         exon_report << std::fixed;
         for (size_t e = 0; e < A.exon_ids.size(); ++e) {
             const double v = R.exon_seq.empty() ? exon_count_to_double(R.exon_whole[e], R.exon_frac[e]) : R.exon_seq[e];
-            exon_report << A.exon_ids[e] << "\t" << A.exon_desc[e] << "\t" << v << std::endl;
+            exon_report << A.exon_ids[e] << "\t" << A.exon_desc[e] << "\t" << v << '\n';
         }
     }
     // ---- metrics.tsv (src/RNASeQC.cpp:523-564, src/Metrics.cpp:381-410) -----------------------------------------
     std::ofstream output(base + ".metrics.tsv");
-    output << "Sample\t" << opt.sample_name << std::endl;
-    output << "Mapping Rate\t" << frac(RSQ_C_MAPPED_READS, RSQ_C_UMVQ) << std::endl;
-    output << "Unique Rate of Mapped\t" << frac(RSQ_C_MAPPED_UNIQUE_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Duplicate Rate of Mapped\t" << frac(RSQ_C_MAPPED_DUPLICATE_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Duplicate Rate of Mapped, excluding Globins\t" << frac(RSQ_C_NON_GLOBIN_DUPLICATE_READS, RSQ_C_NON_GLOBIN_READS) << std::endl;
-    output << "Base Mismatch\t" << frac(RSQ_C_MISMATCHED_BASES, RSQ_C_TOTAL_BASES) << std::endl;
-    output << "End 1 Mapping Rate\t" << 2.0 * frac(RSQ_C_END1_MAPPED_READS, RSQ_C_UMVQ) << std::endl;
-    output << "End 2 Mapping Rate\t" << 2.0 * frac(RSQ_C_END2_MAPPED_READS, RSQ_C_UMVQ) << std::endl;
-    output << "End 1 Mismatch Rate\t" << frac(RSQ_C_END1_MISMATCHES, RSQ_C_END1_BASES) << std::endl;
-    output << "End 2 Mismatch Rate\t" << frac(RSQ_C_END2_MISMATCHES, RSQ_C_END2_BASES) << std::endl;
-    output << "Expression Profiling Efficiency\t" << frac(RSQ_C_EXONIC_READS, RSQ_C_UMVQ) << std::endl;
-    output << "High Quality Rate\t" << frac(RSQ_C_HIGH_QUALITY_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Exonic Rate\t" << frac(RSQ_C_EXONIC_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Intronic Rate\t" << frac(RSQ_C_INTRONIC_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Intergenic Rate\t" << frac(RSQ_C_INTERGENIC_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Intragenic Rate\t" << frac(RSQ_C_INTRAGENIC_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "Ambiguous Alignment Rate\t" << frac(RSQ_C_AMBIGUOUS_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "High Quality Exonic Rate\t" << frac(RSQ_C_HQ_EXONIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
-    output << "High Quality Intronic Rate\t" << frac(RSQ_C_HQ_INTRONIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
-    output << "High Quality Intergenic Rate\t" << frac(RSQ_C_HQ_INTERGENIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
-    output << "High Quality Intragenic Rate\t" << frac(RSQ_C_HQ_INTRAGENIC_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
-    output << "High Quality Ambiguous Alignment Rate\t" << frac(RSQ_C_HQ_AMBIGUOUS_READS, RSQ_C_HIGH_QUALITY_READS) << std::endl;
-    output << "Discard Rate\t" << (double)(C[RSQ_C_MAPPED_READS] - C[RSQ_C_READS_USED]) / C[RSQ_C_MAPPED_READS] << std::endl;
-    output << "rRNA Rate\t" << frac(RSQ_C_RRNA_READS, RSQ_C_MAPPED_READS) << std::endl;
-    output << "End 1 Sense Rate\t" << (double)C[RSQ_C_END1_SENSE] / (C[RSQ_C_END1_SENSE] + C[RSQ_C_END1_ANTISENSE]) << std::endl;
-    output << "End 2 Sense Rate\t" << (double)C[RSQ_C_END2_SENSE] / (C[RSQ_C_END2_SENSE] + C[RSQ_C_END2_ANTISENSE]) << std::endl;
-    output << "Avg. Splits per Read\t" << frac(RSQ_C_ALIGNMENT_BLOCKS, RSQ_C_MAPPED_READS) - 1.0 << std::endl;
+    output << "Sample\t" << opt.sample_name << '\n';
+    output << "Mapping Rate\t" << frac(RSQ_C_MAPPED_READS, RSQ_C_UMVQ) << '\n';
+    output << "Unique Rate of Mapped\t" << frac(RSQ_C_MAPPED_UNIQUE_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Duplicate Rate of Mapped\t" << frac(RSQ_C_MAPPED_DUPLICATE_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Duplicate Rate of Mapped, excluding Globins\t" << frac(RSQ_C_NON_GLOBIN_DUPLICATE_READS, RSQ_C_NON_GLOBIN_READS) << '\n';
+    output << "Base Mismatch\t" << frac(RSQ_C_MISMATCHED_BASES, RSQ_C_TOTAL_BASES) << '\n';
+    output << "End 1 Mapping Rate\t" << 2.0 * frac(RSQ_C_END1_MAPPED_READS, RSQ_C_UMVQ) << '\n';
+    output << "End 2 Mapping Rate\t" << 2.0 * frac(RSQ_C_END2_MAPPED_READS, RSQ_C_UMVQ) << '\n';
+    output << "End 1 Mismatch Rate\t" << frac(RSQ_C_END1_MISMATCHES, RSQ_C_END1_BASES) << '\n';
+    output << "End 2 Mismatch Rate\t" << frac(RSQ_C_END2_MISMATCHES, RSQ_C_END2_BASES) << '\n';
+    output << "Expression Profiling Efficiency\t" << frac(RSQ_C_EXONIC_READS, RSQ_C_UMVQ) << '\n';
+    output << "High Quality Rate\t" << frac(RSQ_C_HIGH_QUALITY_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Exonic Rate\t" << frac(RSQ_C_EXONIC_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Intronic Rate\t" << frac(RSQ_C_INTRONIC_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Intergenic Rate\t" << frac(RSQ_C_INTERGENIC_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Intragenic Rate\t" << frac(RSQ_C_INTRAGENIC_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "Ambiguous Alignment Rate\t" << frac(RSQ_C_AMBIGUOUS_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "High Quality Exonic Rate\t" << frac(RSQ_C_HQ_EXONIC_READS, RSQ_C_HIGH_QUALITY_READS) << '\n';
+    output << "High Quality Intronic Rate\t" << frac(RSQ_C_HQ_INTRONIC_READS, RSQ_C_HIGH_QUALITY_READS) << '\n';
+    output << "High Quality Intergenic Rate\t" << frac(RSQ_C_HQ_INTERGENIC_READS, RSQ_C_HIGH_QUALITY_READS) << '\n';
+    output << "High Quality Intragenic Rate\t" << frac(RSQ_C_HQ_INTRAGENIC_READS, RSQ_C_HIGH_QUALITY_READS) << '\n';
+    output << "High Quality Ambiguous Alignment Rate\t" << frac(RSQ_C_HQ_AMBIGUOUS_READS, RSQ_C_HIGH_QUALITY_READS) << '\n';
+    output << "Discard Rate\t" << (double)(C[RSQ_C_MAPPED_READS] - C[RSQ_C_READS_USED]) / C[RSQ_C_MAPPED_READS] << '\n';
+    output << "rRNA Rate\t" << frac(RSQ_C_RRNA_READS, RSQ_C_MAPPED_READS) << '\n';
+    output << "End 1 Sense Rate\t" << (double)C[RSQ_C_END1_SENSE] / (C[RSQ_C_END1_SENSE] + C[RSQ_C_END1_ANTISENSE]) << '\n';
+    output << "End 2 Sense Rate\t" << (double)C[RSQ_C_END2_SENSE] / (C[RSQ_C_END2_SENSE] + C[RSQ_C_END2_ANTISENSE]) << '\n';
+    output << "Avg. Splits per Read\t" << frac(RSQ_C_ALIGNMENT_BLOCKS, RSQ_C_MAPPED_READS) - 1.0 << '\n';
     // operator<<(ofstream&, Metrics&)
-    output << "Total Alignments\t" << total_alignments << std::endl;
-    output << "Alternative Alignments\t" << C[RSQ_C_ALTERNATIVE_ALIGNMENTS] << std::endl;
-    output << "Supplementary Alignments\t" << C[RSQ_C_SUPPLEMENTARY_ALIGNMENTS] << std::endl;
-    output << "Total Reads\t" << total_alignments - C[RSQ_C_ALTERNATIVE_ALIGNMENTS] - C[RSQ_C_SUPPLEMENTARY_ALIGNMENTS] << std::endl;
+    output << "Total Alignments\t" << total_alignments << '\n';
+    output << "Alternative Alignments\t" << C[RSQ_C_ALTERNATIVE_ALIGNMENTS] << '\n';
+    output << "Supplementary Alignments\t" << C[RSQ_C_SUPPLEMENTARY_ALIGNMENTS] << '\n';
+    output << "Total Reads\t" << total_alignments - C[RSQ_C_ALTERNATIVE_ALIGNMENTS] - C[RSQ_C_SUPPLEMENTARY_ALIGNMENTS] << '\n';
     output << "Chimeric Fragments\t";
     if (C[RSQ_C_CHIMERIC_TAG]) {
-        output << C[RSQ_C_CHIMERIC_TAG] << std::endl;
-        output << "Chimeric Alignment Rate\t" << frac(RSQ_C_CHIMERIC_TAG, RSQ_C_TOTAL_MAPPED_PAIRS) << std::endl;
+        output << C[RSQ_C_CHIMERIC_TAG] << '\n';
+        output << "Chimeric Alignment Rate\t" << frac(RSQ_C_CHIMERIC_TAG, RSQ_C_TOTAL_MAPPED_PAIRS) << '\n';
     } else {
-        output << C[RSQ_C_CHIMERIC_AUTO] << std::endl;
-        output << "Chimeric Alignment Rate\t" << frac(RSQ_C_CHIMERIC_AUTO, RSQ_C_TOTAL_MAPPED_PAIRS) << std::endl;
+        output << C[RSQ_C_CHIMERIC_AUTO] << '\n';
+        output << "Chimeric Alignment Rate\t" << frac(RSQ_C_CHIMERIC_AUTO, RSQ_C_TOTAL_MAPPED_PAIRS) << '\n';
     }
     for (const CounterName& k : kDumpOrder)
-        if (k.idx != RSQ_C_SPLIT_READS || C[RSQ_C_SPLIT_READS]) output << k.name << "\t" << C[k.idx] << std::endl;
+        if (k.idx != RSQ_C_SPLIT_READS || C[RSQ_C_SPLIT_READS]) output << k.name << "\t" << C[k.idx] << '\n';
     {
         // "Filtered by tag: X" rows exist only for tags that fired, in std::map (lexicographic) order
         std::map<std::string, uint64_t> fired;
         for (size_t k = 0; k < opt.filter_tags.size() && k < 8; ++k)
             if (C[RSQ_C_FILTERED_BY_TAG0 + k]) fired["Filtered by tag: " + opt.filter_tags[k]] += C[RSQ_C_FILTERED_BY_TAG0 + k];
-        for (auto& kv : fired) output << kv.first << "\t" << kv.second << std::endl;
+        for (auto& kv : fired) output << kv.first << "\t" << kv.second << '\n';
     }
-    output << "Read Length\t" << st.read_length << std::endl;
-    output << "Genes Detected\t" << genes_detected << std::endl;
-    output << "Estimated Library Complexity\t" << min_reads << std::endl;
-    output << "Genes used in 3' bias\t" << bias_genes << std::endl;
-    output << "Mean 3' bias\t" << ratio_avg << std::endl;
-    output << "Median 3' bias\t" << ratio_median << std::endl;
-    output << "3' bias Std\t" << ratio_std << std::endl;
-    output << "3' bias MAD_Std\t" << ratio_mad << std::endl;
-    output << "3' Bias, 25th Percentile\t" << ratio25 << std::endl;
-    output << "3' Bias, 75th Percentile\t" << ratio75 << std::endl;
+    output << "Read Length\t" << st.read_length << '\n';
+    output << "Genes Detected\t" << genes_detected << '\n';
+    output << "Estimated Library Complexity\t" << min_reads << '\n';
+    output << "Genes used in 3' bias\t" << bias_genes << '\n';
+    output << "Mean 3' bias\t" << ratio_avg << '\n';
+    output << "Median 3' bias\t" << ratio_median << '\n';
+    output << "3' bias Std\t" << ratio_std << '\n';
+    output << "3' bias MAD_Std\t" << ratio_mad << '\n';
+    output << "3' Bias, 25th Percentile\t" << ratio25 << '\n';
+    output << "3' Bias, 75th Percentile\t" << ratio75 << '\n';
     // ---- fragment sizes (src/RNASeQC.cpp:570-607) ----------------------------------------------------------------
     {
         std::vector<std::pair<long long, unsigned long>> frag;  // fragmentSizes map contents, ascending
@@ -504,10 +504,10 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             };
             const double fragment_med = median_quirk((unsigned long)size, expanded_at);
             std::ofstream fragment_list(base + ".fragmentSizes.txt");
-            fragment_list << "Fragment Size\tCount" << std::endl;
+            fragment_list << "Fragment Size\tCount" << '\n';
             std::vector<double> deviations;
             for (auto& f : frag) {
-                fragment_list << f.first << "\t" << f.second << std::endl;
+                fragment_list << f.first << "\t" << f.second << '\n';
                 fragment_avg += (double)(f.first * (long long)f.second) / size;
                 double deviation = std::fabs((double)f.first - fragment_med);
                 for (unsigned long i = 0; i < f.second; ++i) deviations.push_back(deviation);
@@ -518,10 +518,10 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             for (auto& f : frag)
                 for (unsigned long i = 0; i < f.second; ++i) fragment_std += std::pow((double)f.first - fragment_avg, 2.0) / size;
             fragment_std = std::pow(fragment_std, 0.5);
-            output << "Average Fragment Length\t" << fragment_avg << std::endl;
-            output << "Fragment Length Median\t" << fragment_med << std::endl;
-            output << "Fragment Length Std\t" << fragment_std << std::endl;
-            output << "Fragment Length MAD_Std\t" << fragment_mad << std::endl;
+            output << "Average Fragment Length\t" << fragment_avg << '\n';
+            output << "Fragment Length Median\t" << fragment_med << '\n';
+            output << "Fragment Length Std\t" << fragment_std << '\n';
+            output << "Fragment Length MAD_Std\t" << fragment_mad << '\n';
         }
     }
     // ---- coverage medians and exon_cv.tsv (src/RNASeQC.cpp:609-659) --------------------------------------------
@@ -533,21 +533,21 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         for (double v : cov.gene_cvs) if (!(std::isnan(v) || std::isinf(v))) cvs.push_back(v);
         std::sort(cvs.begin(), cvs.end());
         const unsigned long n_cvs = cvs.size();
-        output << "Median of Avg Transcript Coverage\t" << median_quirk(n_transcripts, [&](unsigned long i) { return means[i]; }) << std::endl;
-        output << "Median of Transcript Coverage Std\t" << median_quirk(n_transcripts, [&](unsigned long i) { return stds[i]; }) << std::endl;
-        output << "Median of Transcript Coverage CV\t" << (n_cvs ? median_quirk(n_cvs, [&](unsigned long i) { return cvs[i]; }) : 0.0) << std::endl;
+        output << "Median of Avg Transcript Coverage\t" << median_quirk(n_transcripts, [&](unsigned long i) { return means[i]; }) << '\n';
+        output << "Median of Transcript Coverage Std\t" << median_quirk(n_transcripts, [&](unsigned long i) { return stds[i]; }) << '\n';
+        output << "Median of Transcript Coverage CV\t" << (n_cvs ? median_quirk(n_cvs, [&](unsigned long i) { return cvs[i]; }) : 0.0) << '\n';
         std::map<std::string, double> exon_cov;  // exonCoverage: later entries overwrite
         for (auto& kv : cov.exon_cvs) exon_cov[kv.first] = kv.second;
         std::ofstream cv_report(base + ".exon_cv.tsv");
-        cv_report << "Exon ID\tExon CV" << std::endl;
+        cv_report << "Exon ID\tExon CV" << '\n';
         std::vector<double> total_exon_cv;
         for (auto& kv : exon_cov) {
-            cv_report << kv.first << "\t" << kv.second << std::endl;
+            cv_report << kv.first << "\t" << kv.second << '\n';
             total_exon_cv.push_back(kv.second);
         }
         Stats cs = get_statistics(total_exon_cv);
-        output << "Median Exon CV\t" << cs.med << std::endl;
-        output << "Exon CV MAD\t" << cs.mad << std::endl;
+        output << "Median Exon CV\t" << cs.med << '\n';
+        output << "Exon CV MAD\t" << cs.mad << '\n';
     }
     output.close();
 }
