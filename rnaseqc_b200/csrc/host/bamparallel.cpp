@@ -142,7 +142,15 @@ void ParallelBamDecoder::reader_loop() {
     try {
         bool eof = false;
         while (!eof) {
-            auto job = std::make_shared<Job>();
+            std::shared_ptr<Job> job;
+            {   // recycle a consumed job: its buffers are already mapped (fresh 4 MB vectors cost a page fault per page)
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!pool_.empty()) { job = pool_.back(); pool_.pop_back(); }
+            }
+            if (!job) job = std::make_shared<Job>();
+            job->comp.clear(); job->c_off.clear(); job->c_len.clear(); job->u_len.clear();
+            job->reads.clear(); job->rblocks.clear(); job->tids.clear(); job->big.clear();
+            job->use_big = false; job->error.clear(); job->error_code = 0; job->state = ST_READ;
             size_t total = 0;
             while (total < kJobUncompressed) {
                 uint32_t off, len, isize;
@@ -195,13 +203,12 @@ void ParallelBamDecoder::worker_loop() {
         lk.unlock();
         try {
             if (what == 3) {
-                todo->out.resize(kHeadroom + todo->data_len);
+                if (todo->out.size() < kHeadroom + todo->data_len) todo->out.resize(kHeadroom + todo->data_len);
                 size_t o = kHeadroom;
                 for (size_t b = 0; b < todo->c_off.size(); ++b) {
                     inflate_block(todo->comp.data() + todo->c_off[b], todo->c_len[b], todo->out.data() + o, todo->u_len[b]);
                     o += todo->u_len[b];
                 }
-                std::vector<uint8_t>().swap(todo->comp);
             } else if (what == 1) {
                 // frame: [carry | data] must be contiguous; then hop over whole records
                 uint8_t* base = todo->out.data();
@@ -241,8 +248,6 @@ void ParallelBamDecoder::worker_loop() {
                     todo->tids.push_back(tid);
                     p += 4 + (size_t)bs;
                 }
-                std::vector<uint8_t>().swap(todo->out);
-                std::vector<uint8_t>().swap(todo->big);
             }
         } catch (HostError& e) {
             todo->error = e.what(); todo->error_code = e.exit_code ? e.exit_code : -1;
@@ -291,16 +296,27 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
             cur_read_ = 0;
         }
         const size_t n = std::min(job->reads.size() - cur_read_, max_records - reads.size());
-        for (size_t k = 0; k < n; ++k) {
-            rsq_read r = job->reads[cur_read_ + k];
-            const rsq_block* src = job->rblocks.data() + r.block_off;
-            r.block_off = (uint32_t)blocks.size();
-            blocks.insert(blocks.end(), src, src + r.n_blocks);
-            dec.observe(r, job->tids[cur_read_ + k]);
-            reads.push_back(r);
+        if (n) {
+            // bulk append: the records of a job and their blocks are contiguous and in file order
+            const rsq_read* first = job->reads.data() + cur_read_;
+            const uint32_t b_lo = first->block_off;
+            const uint32_t b_hi = first[n - 1].block_off + first[n - 1].n_blocks;
+            const uint32_t delta = (uint32_t)blocks.size() - b_lo;
+            const size_t at = reads.size();
+            reads.insert(reads.end(), first, first + n);
+            blocks.insert(blocks.end(), job->rblocks.data() + b_lo, job->rblocks.data() + b_hi);
+            const int32_t* tids = job->tids.data() + cur_read_;
+            rsq_read* out = reads.data() + at;
+            for (size_t k = 0; k < n; ++k) {
+                out[k].block_off += delta;
+                dec.observe(out[k], tids[k]);
+            }
         }
         cur_read_ += n;
-        if (cur_read_ >= job->reads.size()) { cur_.reset(); cur_read_ = 0; }
+        if (cur_read_ >= job->reads.size()) {
+            { std::lock_guard<std::mutex> lk(mu_); pool_.push_back(cur_); }
+            cur_.reset(); cur_read_ = 0;
+        }
     }
     return !reads.empty();
 }

@@ -45,6 +45,7 @@ private:
     std::mutex mu_;
     std::condition_variable cv_work_, cv_consumer_, cv_reader_;
     std::deque<std::shared_ptr<Job>> jobs_;        // in file order; front = oldest not yet consumed
+    std::vector<std::shared_ptr<Job>> pool_;       // consumed jobs whose buffers are reused
     uint64_t next_job_id_ = 0;
     uint64_t next_frame_id_ = 0;       // framing is sequential: the next job id to frame
     std::vector<uint8_t> carry_;       // partial record at the end of the last framed job
