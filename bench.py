@@ -37,8 +37,18 @@ WORKLOADS = {
 }
 
 
+# stdout carries exactly ONE JSON line: anything a library prints to fd 1 (NCCL's version banner, for one) is sent to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
 
 
 def build_annotation(wl, tmpdir, with_bed=False):
@@ -315,7 +325,7 @@ def run_ours(args):
                        "fragment_samples_taken": int(res.fragment_samples_taken),
                        "genes_in_3prime_bias": int(((res.cov_stats["five_end"] + res.cov_stats["three_end"]) > 0).sum())},
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -389,7 +399,7 @@ def run_reference(args):
            "config": {"workload": wl["label"], "sample_records": sr.n, "gtf_parse_seconds_subtracted": t_gtf},
            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
