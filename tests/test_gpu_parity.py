@@ -183,3 +183,31 @@ def test_device_coverage_statistics_match_oracle(libs, synth_case, kw):
         m = ~np.isnan(b)
         assert np.allclose(a[m], b[m], rtol=1e-9, atol=1e-12), (k, np.abs(a[m] - b[m]).max())
     assert (want["gene_mean"] > 0).sum() > 50
+
+
+def test_dense_annotation_forces_the_unstaged_path(libs, tmp_path):
+    """More exons / gene segments inside one tile window than the per-warp shared-memory stage holds (64 / 32): every tile
+    must fall back to the bucket-index path in L2 and still agree with the oracle bit for bit."""
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    n_genes, per_gene = 48, 6
+    g_start, g_end, ex_s, ex_e, ex_off, strand = [], [], [], [], [0], []
+    for g in range(n_genes):                       # 48 nested genes, exons of different genes interleaved every 7 bases
+        s0 = 5000 + 7 * g
+        for k in range(per_gene):
+            ex_s.append(s0 + 420 * k); ex_e.append(s0 + 420 * k + 260)
+        ex_off.append(len(ex_s)); g_start.append(s0); g_end.append(ex_e[-1]); strand.append(g % 2)
+    sa = synth.SynthAnnotation(["chrD"], [200000], np.zeros(n_genes, np.int32), np.array(g_start, np.int64), np.array(g_end, np.int64),
+                               np.array(strand, np.int8), [f"DENSE{g}" for g in range(n_genes)], np.zeros(n_genes, bool),
+                               np.array(ex_off, np.int64), np.array(ex_s, np.int64), np.array(ex_e, np.int64))
+    gtf = str(tmp_path / "dense.gtf")
+    synth.write_gtf(sa, gtf)
+    ann = api.Annotation(gtf)
+    sr = synth.simulate_reads(sa, 60000, seed=9, genomic_frac=0.3)
+    rb, bb = synth.pack(sr, [ann.contig_index("chrD")])
+    reads, blocks = synth.to_numpy(rb, bb)
+    for kw in (dict(), dict(strand_mode=1)):
+        want, _ = _run(api, libs["oracle"], ann, reads, blocks, api.make_config(max_records=len(reads), **kw))
+        got, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=len(reads), **kw))
+        assert_results_equal(got, want, f"dense {kw}")
+    assert want.counter("Ambiguous Reads") > 0 and want.gene_reads.sum() > 1000
