@@ -169,6 +169,7 @@ enum {
     RSQ_C_FILTERED_BY_TAG0,        /* .. +7: "Filtered by tag: X", src/RNASeQC.cpp:325 */
     RSQ_C_SPLIT_READS = RSQ_C_FILTERED_BY_TAG0 + 8, /* legacy only; always 0 here */
     RSQ_C_FRAGMENT_CANDIDATES,     /* diagnostics: reads that entered the fragment-size mate map */
+    RSQ_C_FRAGSET_ENTRIES,         /* diagnostics: distinct (gene, read name) pairs in the fragment tracker = sum of gene_fragments */
     RSQ_N_COUNTERS = 64
 };
 

@@ -30,7 +30,7 @@ COUNTER_NAMES = [
     "Intronic Reads", "Intragenic Reads", "HQ Intronic Reads", "HQ Intragenic Reads", "Intergenic Reads",
     "HQ Intergenic Reads", "Exonic Reads", "HQ Exonic Reads", "Ambiguous Reads", "HQ Ambiguous Reads", "rRNA Reads",
     "End 1 Sense", "End 1 Antisense", "End 2 Sense", "End 2 Antisense", "Total Alignments",
-] + [f"Filtered by tag {k}" for k in range(8)] + ["Split Reads", "Fragment Candidates"]
+] + [f"Filtered by tag {k}" for k in range(8)] + ["Split Reads", "Fragment Candidates", "Fragment Set Entries"]
 COUNTER_INDEX = {n: i for i, n in enumerate(COUNTER_NAMES)}
 
 READ_DTYPE = np.dtype([

@@ -37,6 +37,8 @@ struct Ctx {
     unsigned int* d_scan = nullptr;           // scan scratch
     size_t scan_elems = 0;
     unsigned long long frag_cap = 0, pair_cap = 0;
+    unsigned long long frag_known = 0, frag_pending = 0;   // entries read back from the device / upper bound of those in flight
+    unsigned long long exon_depth = 1;                     // deepest stack of overlapping exons (inserts per record <= this)
     unsigned long long* d_export = nullptr;
     // rsq_coverage_statistics buffers
     unsigned long long* cs_off = nullptr; uint32_t *cs_eoff = nullptr, *cs_len = nullptr, *cs_slot = nullptr; uint8_t* cs_strand = nullptr;
@@ -114,6 +116,7 @@ int zero_accumulators(Ctx* c) {
         CU_TRY(cudaMemsetAsync(a.sample_count, 0, 8, c->stream));
     }
     c->records_submitted = 0;
+    c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
     c->timers_used = 0;
     return RSQ_OK;
@@ -136,20 +139,32 @@ int ensure_bed_buffers(Ctx* c, size_t n_reads) {
     return RSQ_OK;
 }
 
-// grows the fragment-tracker set so that (records so far + n) <= capacity / 2
+// Keeps the fragment-tracker set at most half full.  A record inserts one entry per gene it counts toward, at most
+// `exon_depth` (the deepest stack of overlapping exons in the annotation).  The exact number of entries is a device
+// counter; the host only synchronises to read it when the pessimistic bound (known entries + depth x records in flight)
+// would exceed half the capacity, then grows the table (rehash) if the exact number still does.
 int ensure_frag_capacity(Ctx* c, size_t n) {
-    const unsigned long long need = 2ull * (c->records_submitted + n);
-    if (need <= c->frag_cap) return RSQ_OK;
-    const unsigned long long new_cap = next_pow2(need);
-    unsigned long long* nt = nullptr;
-    CU_TRY(cudaMalloc(&nt, 8ull * new_cap));
-    CU_TRY(cudaMemsetAsync(nt, 0, 8ull * new_cap, c->stream));
-    c->launches += launch_rehash(c->acc.frag_set, c->frag_cap, nt, new_cap - 1, c->acc.error_flag, c->stream);
+    const unsigned long long add = (unsigned long long)n * c->exon_depth;
+    if (2ull * (c->frag_known + c->frag_pending + add) <= c->frag_cap) { c->frag_pending += add; return RSQ_OK; }
     CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->acc.frag_set);
-    c->acc.frag_set = nt;
-    c->acc.frag_mask = new_cap - 1;
-    c->frag_cap = new_cap;
+    unsigned long long exact = 0;
+    CU_TRY(cudaMemcpy(&exact, c->acc.counters + RSQ_C_FRAGSET_ENTRIES, 8, cudaMemcpyDeviceToHost));
+    c->frag_known = exact;
+    c->frag_pending = 0;
+    const unsigned long long need = 2ull * (c->frag_known + add);
+    if (need > c->frag_cap) {
+        const unsigned long long new_cap = next_pow2(need);
+        unsigned long long* nt = nullptr;
+        CU_TRY(cudaMalloc(&nt, 8ull * new_cap));
+        CU_TRY(cudaMemsetAsync(nt, 0, 8ull * new_cap, c->stream));
+        c->launches += launch_rehash(c->acc.frag_set, c->frag_cap, nt, new_cap - 1, c->acc.error_flag, c->stream);
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->acc.frag_set);
+        c->acc.frag_set = nt;
+        c->acc.frag_mask = new_cap - 1;
+        c->frag_cap = new_cap;
+    }
+    c->frag_pending = add;
     return RSQ_OK;
 }
 
@@ -176,9 +191,7 @@ int ensure_pair_capacity(Ctx* c, size_t n) {
 }
 
 int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks, size_t n_blocks) {
-    int rc = ensure_frag_capacity(c, n_reads);
-    if (rc != RSQ_OK) return rc;
-    rc = ensure_pair_capacity(c, n_reads);
+    int rc = ensure_pair_capacity(c, n_reads);
     if (rc != RSQ_OK) return rc;
     rc = ensure_bed_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
@@ -193,6 +206,7 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     prm.collect_coverage = c->cfg.collect_coverage;
     prm.bed_enabled = (c->have_bed && c->cfg.fragment_samples) ? 1u : 0u;
     prm.fragment_samples = c->cfg.fragment_samples;
+    prm.cov_len_diag = c->cov_len + 1;
     // timing events around the kernels of this batch
     if (c->timers_used == c->timers.size()) {
         if (c->timers.size() >= 1024) {   // fold what is finished so far
@@ -214,6 +228,8 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     CU_TRY(cudaEventRecord(tm.first, c->stream));
     for (size_t base = 0; base < n_reads; base += kSubBatch) {
         const size_t n = std::min(kSubBatch, n_reads - base);
+        rc = ensure_frag_capacity(c, n);
+        if (rc != RSQ_OK) return rc;
         prm.record_base = c->records_submitted + base;
         if (prm.bed_enabled) {
             CU_TRY(cudaMemsetAsync(c->acc.cand_count, 0, 4, c->stream));
@@ -328,6 +344,18 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     c->ann_allocs.push_back(pmax);
     c->launches += launch_prefix_max(v.exon_se, v.exon_off, a->n_contigs, pmax, c->stream);
     v.exon_pmax = pmax;
+    // deepest stack of overlapping exons: bounds the fragment-set inserts of one record
+    {
+        unsigned long long depth = 1;
+        for (uint32_t k = 0; k < a->n_contigs; ++k) {
+            std::vector<std::pair<int32_t, int>> ev;
+            for (uint32_t i = a->exon_off[k]; i < a->exon_off[k + 1]; ++i) { ev.emplace_back(a->exon_start[i], +1); ev.emplace_back(a->exon_end[i] + 1, -1); }
+            std::sort(ev.begin(), ev.end());
+            long long cur = 0;
+            for (auto& e : ev) { cur += e.second; if (cur > (long long)depth) depth = (unsigned long long)cur; }
+        }
+        c->exon_depth = depth;
+    }
     // direct-address bucket index over each contig's annotated span
     {
         std::vector<uint32_t> boff(a->n_contigs + 1, 0);

@@ -88,6 +88,7 @@ struct Params {
     uint32_t bed_enabled;
     uint32_t fragment_samples;
     unsigned long long record_base;      // global index of reads[0] in the stream (ordering of fragment samples)
+    unsigned long long cov_len_diag;     // coverage array length (RSQ_AB_SCATTER diagnostic build only)
 };
 
 // launchers (rsq_kernels.cu); every launcher returns the number of kernels it launched

@@ -275,6 +275,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     unsigned int my_bytes = 0;
     uint32_t agg_gene = kNoGene;        // first gene this read counts toward (aggregated across the warp below)
     bool agg_unique = false, agg_frag = false;
+    int n_fresh = 0;                    // new fragment-set entries of this read (sizes the set's growth on the host)
 
     // ---- filter cascade, RNASeQC.cpp:254-342 (independent of the annotation: overlaps the bulk copies) ---------------------
     const int pos = q0.x, mpos = q0.y, endpos = q0.z, isize = q0.w;
@@ -480,6 +481,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
 #else
                         const bool fresh = set_insert(acc.frag_set, acc.frag_mask, key0 ? key0 : 1ull, acc.error_flag, 1u);  // :383-387
 #endif
+                        n_fresh += fresh ? 1 : 0;
                         if (agg_gene == kNoGene) { agg_gene = g; agg_unique = !(f & RSQ_F_DUP); agg_frag = fresh; }
                         else {
                             atomicAdd(&acc.gene_reads[g], 1ull);
@@ -515,6 +517,18 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                             frac_q64(len, length, whole, lo);                          // isz/length, :345
                             // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update
                             // is a fire-and-forget RED, nothing waits for an atomic's return value
+#ifdef RSQ_AB_SCATTER   // diagnostic only (wrong results): same instruction stream, but every lane/warp hits its own address
+                            const uint32_t sslot = (m.slot + (uint32_t)(i * 97u)) % ann.n_exons;
+                            if (whole) atomicAdd(&acc.exon_whole[sslot], whole);
+                            else { atomicAdd(&acc.exon_fhi[sslot], lo >> 32); atomicAdd(&acc.exon_flo[sslot], lo & 0xffffffffull); }
+                            my_bytes += 8u;
+                            if (prm.collect_coverage) {
+                                const unsigned long long o = (m.cov_off + (unsigned long long)(bs - x.x) + (unsigned long long)i * 4099ull) % (prm.cov_len_diag - 4096ull);
+                                atomicAdd(&acc.cov_diff[o], 1u);
+                                atomicAdd(&acc.cov_diff[o + len], 0xffffffffu);
+                                my_bytes += 8u;
+                            }
+#else
                             if (whole) atomicAdd(&acc.exon_whole[m.slot], whole);
                             else {
                                 atomicAdd(&acc.exon_fhi[m.slot], lo >> 32);
@@ -527,6 +541,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                                 atomicAdd(&acc.cov_diff[o + len], 0xffffffffu);
                                 my_bytes += 8u;
                             }
+#endif
                         }
                     }
                 }
@@ -649,6 +664,9 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         const int s_mm = __reduce_add_sync(kFull, (vflags & 4u) ? nm_raw : 0), s_tb = __reduce_add_sync(kFull, (vflags & 8u) ? l_qseq : 0);
         const int s_nb = __reduce_add_sync(kFull, (vflags & 16u) ? (int)nb : 0);
         const unsigned s_bytes_w = __reduce_add_sync(kFull, my_bytes);
+        const int s_fresh = __reduce_add_sync(kFull, n_fresh);
+        static_assert(RSQ_C_FRAGSET_ENTRIES >= 32 && RSQ_C_FRAGSET_ENTRIES < 64, "lives in own_hi");
+        if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_fresh;
         static_assert(RSQ_C_END1_MISMATCHES < 32 && RSQ_C_END1_BASES < 32 && RSQ_C_END2_MISMATCHES < 32 && RSQ_C_END2_BASES < 32 &&
                       RSQ_C_MISMATCHED_BASES < 32 && RSQ_C_TOTAL_BASES < 32 && RSQ_C_ALIGNMENT_BLOCKS < 32, "valued counters live in own_lo");
         int mine = 0;
