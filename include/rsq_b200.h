@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RSQ_ABI_VERSION 1u
+#define RSQ_ABI_VERSION 2u
 
 /* ---- status codes -------------------------------------------------------------------------------------- */
 enum {
@@ -48,8 +48,9 @@ enum {
     RSQ_AUX_CHIMERIC_TAG = 0x02,    /* readStringTag(chimeric_tag): src/RNASeQC.cpp:780-800                     */
     RSQ_AUX_MATE_OTHER_CONTIG = 0x04, /* ChrID() != MateChrID(): src/RNASeQC.cpp:287                           */
     RSQ_AUX_TID_OUT_OF_RANGE = 0x08,  /* ChrID()<0 || >= nChrs: src/RNASeQC.cpp:333                              */
-    RSQ_AUX_CONTIG_DROPPED = 0x10   /* features[chr] already cleared by dropFeatures (src/RNASeQC.cpp:346-349,
+    RSQ_AUX_CONTIG_DROPPED = 0x10,  /* features[chr] already cleared by dropFeatures (src/RNASeQC.cpp:346-349,
                                        src/Expression.cpp:96-103): a BAM that RETURNS to a contig finds nothing */
+    RSQ_AUX_TID_GT_127 = 0x20       /* ChrID() > 127: chimeric under --legacy only (src/RNASeQC.cpp:287)       */
 };
 
 /* One decoded alignment record: 48 bytes, 16-byte aligned.  Replaces the SeqLib::BamRecord accessors the
@@ -99,7 +100,9 @@ typedef struct rsq_config {
                                          fragment-tracker hash set); 0 = 1<<24                     */
     uint32_t collect_coverage;        /* 1: accumulate per-base exon coverage (always on in the
                                          reference; 0 only for ablation benchmarks)               */
-    uint32_t reserved0;
+    uint32_t legacy;                  /* --legacy counting rules (src/RNASeQC.cpp:55,90,258,276,279,287,364;
+                                         src/Expression.cpp:129-304); needs the gene-line arrays of
+                                         rsq_annotation                                             */
     uint64_t user_stream;             /* cudaStream_t to run the kernels on (0 = the ctx creates its
                                          own); lets the caller time the path with its own events   */
     uint32_t reserved[4];
@@ -120,9 +123,11 @@ typedef struct rsq_annotation {
     uint32_t struct_size;
     uint32_t n_contigs;
     uint32_t n_genes;           /* gene universe: every distinct gene_id on a Gene or Exon line          */
-    uint32_t n_exons;
+    uint32_t n_exons;           /* exon lines kept as intervals                                           */
     uint32_t n_segs;
-    uint32_t reserved;
+    uint32_t n_exon_slots;      /* output slots = size of exonList (src/GTF.cpp:106); 0 means n_exons.  Larger
+                                   than n_exons under --legacy, which drops single-base exons from the
+                                   interval list but not from the outputs (src/RNASeQC.cpp:129-135)       */
     const uint32_t* exon_off;   /* [n_contigs+1] exons of contig c are [exon_off[c], exon_off[c+1])       */
     const int32_t*  exon_start; /* [n_exons] 1-based closed, stable-sorted by start within a contig       */
     const int32_t*  exon_end;   /* [n_exons]                                                              */
@@ -136,6 +141,19 @@ typedef struct rsq_annotation {
     const uint8_t*  seg_flags;  /* [n_segs] RSQ_SEG_*                                                     */
     const uint8_t*  gene_flags; /* [n_genes] RSQ_GENE_*                                                   */
     uint64_t cov_len;           /* total exon bases (sum of exonLengths, src/GTF.cpp:108)                 */
+    /* Gene lines as intervals — read by the --legacy rules only, which walk the Gene features a whole read
+     * intersects in list order (src/Expression.cpp:143-159).  May be NULL / 0 when rsq_config.legacy == 0.   */
+    uint32_t n_gene_lines;
+    uint32_t reserved1;
+    const uint32_t* gline_off;   /* [n_contigs+1]                                                          */
+    const int32_t*  gline_start; /* [n_gene_lines] stable-sorted by start within a contig                  */
+    const int32_t*  gline_end;   /* [n_gene_lines]                                                         */
+    const uint32_t* gline_gene;  /* [n_gene_lines] gene index of the line's gene_id (compared with
+                                    exon_gene, src/Expression.cpp:175)                                     */
+    const uint8_t*  gline_flags; /* [n_gene_lines] RSQ_EXON_STRAND_MASK | RSQ_EXON_RIBOSOMAL                */
+    const uint32_t* gline_order; /* [n_gene_lines] position among the kept GTF lines: ties of the list's
+                                    stable sort by start (src/RNASeQC.cpp:150-152)                         */
+    const uint32_t* exon_order;  /* [n_exons] same, for the exon lines                                     */
 } rsq_annotation;
 
 /* BED intervals for the fragment-size sampler (src/BED.cpp:18-43, src/RNASeQC.cpp:172-187); intervals of a
@@ -167,7 +185,7 @@ enum {
     RSQ_C_END1_ANTISENSE, RSQ_C_END2_SENSE, RSQ_C_END2_ANTISENSE,
     RSQ_C_TOTAL_ALIGNMENTS,        /* alignmentCount, src/RNASeQC.cpp:245 (the int truncation of :397 is the writer's) */
     RSQ_C_FILTERED_BY_TAG0,        /* .. +7: "Filtered by tag: X", src/RNASeQC.cpp:325 */
-    RSQ_C_SPLIT_READS = RSQ_C_FILTERED_BY_TAG0 + 8, /* legacy only; always 0 here */
+    RSQ_C_SPLIT_READS = RSQ_C_FILTERED_BY_TAG0 + 8, /* --legacy only (src/Expression.cpp:279) */
     RSQ_C_FRAGMENT_CANDIDATES,     /* diagnostics: reads that entered the fragment-size mate map */
     RSQ_C_FRAGSET_ENTRIES,         /* diagnostics: distinct (gene, read name) pairs in the fragment tracker = sum of gene_fragments */
     RSQ_N_COUNTERS = 64

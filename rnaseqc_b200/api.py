@@ -45,16 +45,19 @@ class RsqConfig(C.Structure):
                 ("base_mismatch_threshold", C.c_uint32), ("chimeric_distance", C.c_int32), ("strand_mode", C.c_uint32),
                 ("unpaired", C.c_uint32), ("exclude_chimeric", C.c_uint32), ("n_filter_tags", C.c_uint32),
                 ("fragment_samples", C.c_uint32), ("max_records", C.c_uint64), ("collect_coverage", C.c_uint32),
-                ("reserved0", C.c_uint32), ("user_stream", C.c_uint64), ("reserved", C.c_uint32 * 4)]
+                ("legacy", C.c_uint32), ("user_stream", C.c_uint64), ("reserved", C.c_uint32 * 4)]
 
 
 class RsqAnnotation(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_contigs", C.c_uint32), ("n_genes", C.c_uint32), ("n_exons", C.c_uint32),
-                ("n_segs", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_segs", C.c_uint32), ("n_exon_slots", C.c_uint32),
                 ("exon_off", C.POINTER(C.c_uint32)), ("exon_start", C.POINTER(C.c_int32)), ("exon_end", C.POINTER(C.c_int32)),
                 ("exon_gene", C.POINTER(C.c_uint32)), ("exon_slot", C.POINTER(C.c_uint32)), ("exon_flags", C.POINTER(C.c_uint8)),
                 ("exon_cov_off", C.POINTER(C.c_uint64)), ("seg_off", C.POINTER(C.c_uint32)), ("seg_start", C.POINTER(C.c_int32)),
-                ("seg_flags", C.POINTER(C.c_uint8)), ("gene_flags", C.POINTER(C.c_uint8)), ("cov_len", C.c_uint64)]
+                ("seg_flags", C.POINTER(C.c_uint8)), ("gene_flags", C.POINTER(C.c_uint8)), ("cov_len", C.c_uint64),
+                ("n_gene_lines", C.c_uint32), ("reserved1", C.c_uint32), ("gline_off", C.POINTER(C.c_uint32)),
+                ("gline_start", C.POINTER(C.c_int32)), ("gline_end", C.POINTER(C.c_int32)), ("gline_gene", C.POINTER(C.c_uint32)),
+                ("gline_flags", C.POINTER(C.c_uint8)), ("gline_order", C.POINTER(C.c_uint32)), ("exon_order", C.POINTER(C.c_uint32))]
 
 
 class RsqBed(C.Structure):
@@ -105,7 +108,8 @@ ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_fre
 
 def make_config(device: int = 0, mapq: int = 255, mismatches: int = 6, chimeric_distance: int = 2000000,
                 strand_mode: int = 0, unpaired: bool = False, exclude_chimeric: bool = False, n_filter_tags: int = 0,
-                fragment_samples: int = 0, max_records: int = 0, collect_coverage: bool = True, user_stream: int = 0) -> RsqConfig:
+                fragment_samples: int = 0, max_records: int = 0, collect_coverage: bool = True, user_stream: int = 0,
+                legacy: bool = False) -> RsqConfig:
     cfg = RsqConfig()
     cfg.struct_size = C.sizeof(RsqConfig)
     cfg.device = device
@@ -120,6 +124,7 @@ def make_config(device: int = 0, mapq: int = 255, mismatches: int = 6, chimeric_
     cfg.max_records = max_records
     cfg.collect_coverage = int(collect_coverage)
     cfg.user_stream = user_stream
+    cfg.legacy = int(legacy)
     return cfg
 
 
@@ -229,7 +234,7 @@ class Context:
 
     def set_annotation(self, ann: "Annotation") -> None:
         v = ann.view
-        self.n_genes, self.n_exons, self.cov_len = v.n_genes, v.n_exons, v.cov_len
+        self.n_genes, self.n_exons, self.cov_len = v.n_genes, (v.n_exon_slots or v.n_exons), v.cov_len   # n_exons: output slots
         self._check(self.be.lib.rsq_set_annotation(self.h, C.byref(v)))
         if ann.bed_view is not None and self.cfg.fragment_samples:
             self._check(self.be.lib.rsq_set_bed(self.h, ann.bed_view))
@@ -351,8 +356,10 @@ def host_lib():
 class Annotation:
     """Flattened annotation parsed from GTF (+BED) text by the C++ host library."""
 
-    def __init__(self, gtf: str, bed: Optional[str] = None):
+    def __init__(self, gtf: str, bed: Optional[str] = None, legacy: bool = False):
         H = host_lib()
+        self.legacy = legacy
+        H.rsqh_set_legacy(int(legacy))
         self._h = C.c_void_p()
         err = C.create_string_buffer(1024)
         rc = H.rsqh_load_annotation(gtf.encode(), bed.encode() if bed else None, C.byref(self._h), err, 1024)
@@ -376,6 +383,11 @@ class Annotation:
 
     @property
     def n_exons(self) -> int:
+        """Output slots (exonList); under --legacy larger than the number of exon intervals kept."""
+        return self.view.n_exon_slots or self.view.n_exons
+
+    @property
+    def n_exon_intervals(self) -> int:
         return self.view.n_exons
 
     @property

@@ -373,6 +373,7 @@ void Decoder::convert(const RawAln& a, std::vector<rsq_read>& reads, std::vector
     const int n_refs = (int)tid_to_contig_.size();
     const bool tid_ok = a.tid >= 0 && a.tid < n_refs;
     if (!tid_ok) r.aux |= RSQ_AUX_TID_OUT_OF_RANGE;
+    if (a.tid > 127) r.aux |= RSQ_AUX_TID_GT_127;
     const int chr = tid_ok ? tid_to_contig_[a.tid] : -1;
     r.contig = (chr >= 0 && (size_t)chr < n_annotation_contigs_ && chr <= INT16_MAX) ? (int16_t)chr : (int16_t)-1;
 
@@ -422,15 +423,17 @@ void Decoder::observe(rsq_read& r, int32_t tid) {
     const bool has_ch = r.aux & RSQ_AUX_CHIMERIC_TAG;
     bool reaches_metrics = false;
     do {
-        if ((r.flag & RSQ_F_SUPPLEMENTARY) && !has_ch && opt_.exclude_chimeric) break;           // :258-262
+        if ((r.flag & RSQ_F_SUPPLEMENTARY) && !(opt_.legacy || has_ch) && opt_.exclude_chimeric) break;   // :258-262
         if (r.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) break;               // :263
         if (r.flag & RSQ_F_UNMAP) break;                                                           // :268
         const unsigned alignment_size = (unsigned)(r.endpos - r.pos);                              // :275
+        if (opt_.legacy && alignment_size > 100000u) break;                                        // :276 LEGACY_MAX_READ_LENGTH
         if (!read_length_ && tid_ok) current_chrom_ = chr;                                         // :277
         if (alignment_size > (unsigned)read_length_) read_length_ = r.l_qseq;                      // :278
-        if (has_ch && opt_.exclude_chimeric) break;                                                // :279-283
+        if (!opt_.legacy && has_ch && opt_.exclude_chimeric) break;                                // :279-283
         if ((r.flag & RSQ_F_PAIRED) && !(r.flag & RSQ_F_MUNMAP)) {                                 // :284-292
-            const bool chim = (r.aux & RSQ_AUX_MATE_OTHER_CONTIG) || std::abs(r.pos - r.mpos) > opt_.chimeric_distance;
+            const bool chim = (r.aux & RSQ_AUX_MATE_OTHER_CONTIG) || std::abs(r.pos - r.mpos) > opt_.chimeric_distance ||
+                              (opt_.legacy && tid > 127);
             if (chim && opt_.exclude_chimeric) break;
         }
         if (r.filter_mask) break;                                                                  // :319-328
@@ -553,6 +556,7 @@ void Decoder::convert_bam_bytes(const uint8_t* b, size_t n, rsq_read& r, std::ve
     const int n_refs = (int)tid_to_contig_.size();
     const bool tid_ok = tid >= 0 && tid < n_refs;
     if (!tid_ok) r.aux |= RSQ_AUX_TID_OUT_OF_RANGE;
+    if (tid > 127) r.aux |= RSQ_AUX_TID_GT_127;
     const int chr = tid_ok ? tid_to_contig_[tid] : -1;
     r.contig = (chr >= 0 && (size_t)chr < n_annotation_contigs_ && chr <= INT16_MAX) ? (int16_t)chr : (int16_t)-1;
 }

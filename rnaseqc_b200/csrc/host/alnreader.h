@@ -52,6 +52,7 @@ struct DecodeOptions {
     bool exclude_chimeric = false;
     int chimeric_distance = 2000000;
     int verbosity = 0;
+    bool legacy = false;                      // --legacy gates of the loop (src/RNASeQC.cpp:258,276,279,287)
 };
 
 // Converts records and carries the order-dependent scalar state of the reference loop that cannot be a

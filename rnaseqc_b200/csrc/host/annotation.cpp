@@ -106,7 +106,7 @@ uint32_t Annotation::gene_universe(const std::string& id) {
     return g;
 }
 
-void load_gtf(const std::string& path, Annotation& A) {
+void load_gtf(const std::string& path, Annotation& A, bool legacy) {
     std::ifstream in(path);
     if (!in.is_open()) throw HostError(10, "Unable to open GTF file: " + path);
 
@@ -186,9 +186,14 @@ void load_gtf(const std::string& path, Annotation& A) {
         else if (at.has_gene_id) gene_names[cur_feature_id] = at.gene_id;
         const bool ribosomal = cur_transcript_type.find("rRNA") != std::string::npos;  // regex "rRNA", src/GTF.cpp:21,113
 
+        if (legacy && end == start) {                                                  // src/RNASeQC.cpp:129-135
+            if (type == T_EXON) A.gene_coding_len[A.gene_universe(cur_gene_id)] -= 1;
+            continue;
+        }
         // main(): keep genes and exons only (src/RNASeQC.cpp:137-139)
         if (type == T_GENE) {
             GeneFeature gf{contig, start, end, strand, ribosomal, A.gene_universe(cur_feature_id), (uint32_t)kept_counter++};
+            gf.gid = A.gene_universe(cur_gene_id);
             kept_genes.push_back(gf);
         } else if (type == T_EXON) {
             ExonFeature ef{contig, start, end, strand, ribosomal, A.gene_universe(cur_gene_id), exon_slot, (uint32_t)kept_counter++};
@@ -249,7 +254,18 @@ void load_gtf(const std::string& path, Annotation& A) {
     // ---- flatten ------------------------------------------------------------------------------------------
     A.f_exon_off.assign(nc + 1, 0);
     A.f_seg_off.assign(nc + 1, 0);
+    A.f_gline_off.assign(nc + 1, 0);
     for (size_t c = 0; c < nc; ++c) {
+        A.f_gline_off[c] = (uint32_t)A.f_gline_start.size();
+        for (auto& g : A.genes_by_contig[c]) {
+            if (g.start > INT32_MAX - 2 || g.end > INT32_MAX - 2)
+                throw HostError(11, "Failed to parse the GTF: coordinate beyond 2^31");
+            A.f_gline_start.push_back((int32_t)g.start);
+            A.f_gline_end.push_back((int32_t)g.end);
+            A.f_gline_gene.push_back(g.gid);
+            A.f_gline_flags.push_back((uint8_t)(g.strand | (g.ribosomal ? RSQ_EXON_RIBOSOMAL : 0)));
+            A.f_gline_order.push_back(g.line_order);
+        }
         A.f_exon_off[c] = (uint32_t)A.f_exon_start.size();
         for (auto& e : A.exons_by_contig[c]) {
             if (e.start > INT32_MAX - 2 || e.end > INT32_MAX - 2)
@@ -260,6 +276,7 @@ void load_gtf(const std::string& path, Annotation& A) {
             A.f_exon_slot.push_back(e.slot);
             A.f_exon_flags.push_back((uint8_t)(e.strand | (e.ribosomal ? RSQ_EXON_RIBOSOMAL : 0)));
             A.f_exon_cov_off.push_back(A.exon_cov_off[e.slot]);
+            A.f_exon_order.push_back(e.line_order);
         }
         // Elementary gene segments: sweep over [start, end+1) of every Gene feature with one counter per
         // (strand, ribosomal) class; a segment's flags say which classes cover it.
@@ -293,6 +310,7 @@ void load_gtf(const std::string& path, Annotation& A) {
     }
     A.f_exon_off[nc] = (uint32_t)A.f_exon_start.size();
     A.f_seg_off[nc] = (uint32_t)A.f_seg_start.size();
+    A.f_gline_off[nc] = (uint32_t)A.f_gline_start.size();
     A.build_transcripts();
 }
 
@@ -301,6 +319,7 @@ void Annotation::pad_contigs(size_t n_contigs) {
         genes_by_contig.emplace_back();
         exons_by_contig.emplace_back();
         f_exon_off.push_back(f_exon_off.back());
+        f_gline_off.push_back(f_gline_off.back());
         f_seg_start.push_back(INT32_MIN);
         f_seg_flags.push_back(0);
         f_seg_off.push_back((uint32_t)f_seg_start.size());
@@ -340,6 +359,7 @@ rsq_annotation Annotation::view() const {
     v.n_genes = (uint32_t)gene_ids.size();
     v.n_exons = (uint32_t)f_exon_start.size();
     v.n_segs = (uint32_t)f_seg_start.size();
+    v.n_exon_slots = (uint32_t)exon_ids.size();
     v.exon_off = f_exon_off.data();
     v.exon_start = f_exon_start.data();
     v.exon_end = f_exon_end.data();
@@ -352,6 +372,14 @@ rsq_annotation Annotation::view() const {
     v.seg_flags = f_seg_flags.data();
     v.gene_flags = gene_flags.data();
     v.cov_len = cov_len;
+    v.n_gene_lines = (uint32_t)f_gline_start.size();
+    v.gline_off = f_gline_off.data();
+    v.gline_start = f_gline_start.data();
+    v.gline_end = f_gline_end.data();
+    v.gline_gene = f_gline_gene.data();
+    v.gline_flags = f_gline_flags.data();
+    v.gline_order = f_gline_order.data();
+    v.exon_order = f_exon_order.data();
     return v;
 }
 

@@ -46,6 +46,7 @@ struct GeneFeature {      // one kept line of type "gene" (src/RNASeQC.cpp:137-1
     bool ribosomal;
     uint32_t gene;        // gene-universe index of feature_id
     uint32_t line_order;  // position among kept lines (ties of the stable sort)
+    uint32_t gid = 0;     // gene-universe index of the line's gene_id (== gene unless the attribute was carried over)
     uint32_t flat = 0;    // index of this gene line in the rsq_transcripts request (contig order, then start order)
 };
 
@@ -85,6 +86,10 @@ struct Annotation {
     std::vector<int32_t> f_exon_start, f_exon_end, f_seg_start;
     std::vector<uint8_t> f_exon_flags, f_seg_flags;
     std::vector<uint64_t> f_exon_cov_off;
+    // gene lines as intervals + list-order ranks (read by the --legacy rules only)
+    std::vector<uint32_t> f_gline_off, f_gline_gene, f_gline_order, f_exon_order;
+    std::vector<int32_t> f_gline_start, f_gline_end;
+    std::vector<uint8_t> f_gline_flags;
 
     uint32_t n_feature_contigs() const { return (uint32_t)genes_by_contig.size(); }
     // Extends the contig index space (BED-only contigs) with empty slices.
@@ -103,7 +108,9 @@ struct Annotation {
 // Parses a GTF the way operator>>(ifstream&, Feature&) does (src/GTF.cpp:30-143) and builds the model.
 // Throws HostError(10) when the file cannot be opened, HostError(11) for the reference's gtfException
 // cases and for "no genes or no exons" (src/RNASeQC.cpp:158-164).
-void load_gtf(const std::string& path, Annotation& out);
+// legacy: single-base features are dropped from the interval lists after being recorded in the name lists, and a
+// single-base exon takes its base back from geneCodingLengths (src/RNASeQC.cpp:129-135).
+void load_gtf(const std::string& path, Annotation& out, bool legacy = false);
 
 struct BedModel {
     std::vector<std::vector<int64_t>> starts, ends;   // per contig id (sized to contigs.names.size())

@@ -15,6 +15,7 @@ using namespace rsqh;
 
 namespace {
 int g_decode_threads = 0;
+bool g_legacy = false;
 struct Handle {
     Annotation ann;
     BedModel bed;
@@ -56,7 +57,7 @@ struct rsqh_stream_state {
 int rsqh_load_annotation(const char* gtf, const char* bed, void** out, char* err, size_t errlen) {
     try {
         std::unique_ptr<Handle> h(new Handle());
-        load_gtf(gtf, h->ann);
+        load_gtf(gtf, h->ann, g_legacy);
         if (bed && *bed) { load_bed(bed, h->ann.contigs, h->bed); h->have_bed = true; }
         const size_t nc = h->ann.contigs.names.size();
         h->ann.pad_contigs(nc);
@@ -98,6 +99,7 @@ int rsqh_decode_file(void* hv, const char* path, const char* chimeric_tag, const
         for (int k = 0; k < n_tags; ++k) opt.filter_tags.push_back(filter_tags[k]);
         opt.exclude_chimeric = exclude_chimeric != 0;
         opt.chimeric_distance = chimeric_distance;
+        opt.legacy = g_legacy;
         const size_t n_ann_contigs = h->ann.genes_by_contig.size();
         std::vector<rsq_read> R;
         std::vector<rsq_block> B;
@@ -151,6 +153,8 @@ int rsqh_decode_file(void* hv, const char* path, const char* chimeric_tag, const
 void rsqh_free(void* p) { free(p); }
 // worker threads for BAM decode in rsqh_decode_file (0 = sequential reader)
 void rsqh_set_decode_threads(int n) { g_decode_threads = n; }
+// --legacy for the calls that follow: GTF filter (src/RNASeQC.cpp:129-135) and the decoder's loop gates
+void rsqh_set_legacy(int on) { g_legacy = on != 0; }
 
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
 

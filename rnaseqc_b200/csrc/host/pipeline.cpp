@@ -34,7 +34,7 @@ void usage(std::ostream& o) {
          "      --offset=[OFFSET]                 Offset into the gene for the 3' and 5' windows in bias calculation\n"
          "      --window-size=[SIZE]              Size of the 3' and 5' windows in bias calculation. Default: 100 [bp]\n"
          "      --gene-length=[LENGTH]            Minimum size of a gene for bias calculation\n"
-         "      --legacy                          (not supported by this build)\n"
+         "      --legacy                          Use legacy counting rules.  Gene and exon counts match output of RNA-SeQC 1.1.9\n"
          "      --stranded=[stranded]             Strand-specific metrics: 'RF', 'rf', 'FR', or 'fr'\n"
          "      -v, --verbose                     Give some feedback; twice for progress updates\n"
          "      -t[TAG...], --tag=[TAG...]        Filter out reads with the specified tag\n"
@@ -139,15 +139,15 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
     opt.output_dir = positional[2];
     opt.run.output_dir = opt.output_dir;
     if (!opt.run.sample_given) opt.run.sample_name = std::filesystem::path(opt.bam).filename().string();  // :99
-    if (opt.legacy) {
-        std::cerr << "--legacy counting rules are not implemented in this build (SURVEY.md §8f)" << std::endl;
-        return 6;
+    if (opt.legacy) {                                                  // src/RNASeQC.cpp:90: the default MAPQ gate drops to 4
+        opt.cfg.legacy = 1;
+        opt.decode.legacy = true;
+        if (!mapq_given) opt.cfg.mapq_threshold = 4;
     }
     if (!opt.fasta.empty()) {
         std::cerr << "--fasta (GC content / CRAM reference) is not implemented in this build (SURVEY.md §8f)" << std::endl;
         return 6;
     }
-    (void)mapq_given;
     if (opt.decode.filter_tags.size() > 8) {
         std::cerr << "At most 8 --tag filters are supported" << std::endl;
         return 6;
@@ -210,7 +210,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
         Annotation A;
         auto t0 = clk::now();
         if (opt.verbosity) std::cout << "Reading GTF Features..." << std::endl;
-        load_gtf(opt.gtf, A);
+        load_gtf(opt.gtf, A, opt.legacy);
         if (opt.verbosity)
             std::cout << "Finished processing GTF in " << std::chrono::duration<double>(clk::now() - t0).count() << " seconds" << std::endl;
         BedModel bed;

@@ -206,6 +206,7 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     prm.collect_coverage = c->cfg.collect_coverage;
     prm.bed_enabled = (c->have_bed && c->cfg.fragment_samples) ? 1u : 0u;
     prm.fragment_samples = c->cfg.fragment_samples;
+    prm.legacy = c->cfg.legacy;
     prm.cov_len_diag = c->cov_len + 1;
     // timing events around the kernels of this batch
     if (c->timers_used == c->timers.size()) {
@@ -317,7 +318,12 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     if (c->have_ann) { c->err = "annotation already set"; return RSQ_ERR_INVALID; }
     if (a->n_genes >= (1u << 24)) { c->err = "more than 2^24 genes"; return RSQ_ERR_INVALID; }
     CU_TRY(cudaSetDevice(c->cfg.device));
-    c->n_contigs = a->n_contigs; c->n_genes = a->n_genes; c->n_exons = a->n_exons; c->n_segs = a->n_segs; c->cov_len = a->cov_len;
+    c->n_contigs = a->n_contigs; c->n_genes = a->n_genes; c->n_segs = a->n_segs; c->cov_len = a->cov_len;
+    c->n_exons = a->n_exon_slots ? a->n_exon_slots : a->n_exons;   // accumulators and read-backs are per output slot
+    if (c->n_exons < a->n_exons) { c->err = "n_exon_slots smaller than n_exons"; return RSQ_ERR_INVALID; }
+    if (c->cfg.legacy && (!a->gline_off || !a->exon_order || (a->n_gene_lines && (!a->gline_start || !a->gline_end || !a->gline_gene || !a->gline_flags || !a->gline_order)))) {
+        c->err = "legacy mode needs the gene-line arrays of rsq_annotation"; return RSQ_ERR_INVALID;
+    }
     // repack host-side into the device layout: (start,end) pairs and 16-byte metadata
     std::vector<int2> se((size_t)a->n_exons + 4, make_int2(INT32_MAX, INT32_MAX));   // padded for the rounded-up bulk copies
     std::vector<ExonMeta> meta((size_t)a->n_exons + 4);
@@ -344,6 +350,27 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     c->ann_allocs.push_back(pmax);
     c->launches += launch_prefix_max(v.exon_se, v.exon_off, a->n_contigs, pmax, c->stream);
     v.exon_pmax = pmax;
+    // gene lines (--legacy rules)
+    v.gline_off = nullptr; v.gline_se = nullptr; v.gline_pmax = nullptr; v.gline_gf = nullptr; v.gline_order = nullptr; v.exon_order = nullptr;
+    if (c->cfg.legacy) {
+        std::vector<int2> gse((size_t)a->n_gene_lines);
+        std::vector<uint32_t> ggf((size_t)a->n_gene_lines);
+        for (uint32_t i = 0; i < a->n_gene_lines; ++i) {
+            gse[i] = make_int2(a->gline_start[i], a->gline_end[i]);
+            ggf[i] = (a->gline_gene[i] & 0xffffffu) | ((uint32_t)a->gline_flags[i] << 24);
+        }
+        if ((rc = upload(c, c->ann_allocs, a->gline_off, (size_t)a->n_contigs + 1, &v.gline_off))) return rc;
+        if ((rc = upload(c, c->ann_allocs, gse.data(), gse.size(), &v.gline_se))) return rc;
+        if ((rc = upload(c, c->ann_allocs, ggf.data(), ggf.size(), &v.gline_gf))) return rc;
+        if ((rc = upload(c, c->ann_allocs, a->gline_order, (size_t)a->n_gene_lines, &v.gline_order))) return rc;
+        if ((rc = upload(c, c->ann_allocs, a->exon_order, (size_t)a->n_exons, &v.exon_order))) return rc;
+        int32_t* gpmax = nullptr;
+        CU_TRY(cudaMalloc(&gpmax, std::max<size_t>(a->n_gene_lines, 1) * 4));
+        c->ann_allocs.push_back(gpmax);
+        c->launches += launch_prefix_max(v.gline_se, v.gline_off, a->n_contigs, gpmax, c->stream);
+        v.gline_pmax = gpmax;
+        CU_TRY(cudaStreamSynchronize(c->stream));   // gse / ggf are locals
+    }
     // deepest stack of overlapping exons: bounds the fragment-set inserts of one record
     {
         unsigned long long depth = 1;
@@ -379,10 +406,10 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     CU_TRY(cudaMalloc(&acc.gene_reads, 8ull * std::max(a->n_genes, 1u)));
     CU_TRY(cudaMalloc(&acc.gene_unique, 8ull * std::max(a->n_genes, 1u)));
     CU_TRY(cudaMalloc(&acc.gene_fragments, 8ull * std::max(a->n_genes, 1u)));
-    CU_TRY(cudaMalloc(&acc.exon_whole, 8ull * std::max(a->n_exons, 1u)));
-    CU_TRY(cudaMalloc(&acc.exon_fhi, 8ull * std::max(a->n_exons, 1u)));
-    CU_TRY(cudaMalloc(&acc.exon_flo, 8ull * std::max(a->n_exons, 1u)));
-    CU_TRY(cudaMalloc(&c->d_exon_out, 16ull * std::max(a->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_whole, 8ull * std::max(c->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_fhi, 8ull * std::max(c->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&acc.exon_flo, 8ull * std::max(c->n_exons, 1u)));
+    CU_TRY(cudaMalloc(&c->d_exon_out, 16ull * std::max(c->n_exons, 1u)));
     CU_TRY(cudaMalloc(&acc.cov_diff, 4ull * (a->cov_len + 1)));
     CU_TRY(cudaMalloc(&c->d_cov, 4ull * (a->cov_len + 1)));
     c->scan_elems = coverage_scan_scratch_elems(a->cov_len + 1);
@@ -392,7 +419,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     acc.frag_mask = c->frag_cap - 1;
     CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
     CU_TRY(cudaMalloc(&acc.error_flag, 4));
-    c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * a->n_exons;
+    c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * c->n_exons;
     CU_TRY(cudaMalloc(&c->d_export, 8ull * c->export_words));
     c->have_ann = true;
     rc = zero_accumulators(c);

@@ -29,6 +29,13 @@ struct AnnView {
     const int4*     buckets;      // per bucket: x = first exon with running-max end >= bucket start,
                                   //             y = first exon with start >= bucket start,
                                   //             z = last gene segment with start <= bucket start, w = unused
+    // gene lines as intervals in list order (--legacy rules only; null otherwise)
+    const uint32_t* gline_off;    // [n_contigs+1]
+    const int2*     gline_se;     // [n_gene_lines] (start, end), start-sorted per contig
+    const int32_t*  gline_pmax;   // [n_gene_lines] running max of end within the contig
+    const uint32_t* gline_gf;     // [n_gene_lines] gene index of the line's gene_id | (strand, ribosomal) << 24
+    const uint32_t* gline_order;  // [n_gene_lines] rank among the kept GTF lines (ties of the list's stable sort)
+    const uint32_t* exon_order;   // [n_exons] same for the exon lines
 };
 constexpr int kBucketShift = 10;
 
@@ -87,6 +94,7 @@ struct Params {
     uint32_t strand_mode, unpaired, exclude_chimeric, n_filter_tags, collect_coverage;
     uint32_t bed_enabled;
     uint32_t fragment_samples;
+    uint32_t legacy;                     // --legacy counting rules (rsq_legacy.cuh)
     unsigned long long record_base;      // global index of reads[0] in the stream (ordering of fragment samples)
     unsigned long long cov_len_diag;     // coverage array length (RSQ_AB_SCATTER diagnostic build only)
 };

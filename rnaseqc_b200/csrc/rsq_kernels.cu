@@ -181,7 +181,13 @@ __device__ __forceinline__ bool block_has_gene(const ExonArrays a, const BlockVi
 #ifndef RSQ_HOT_MIN_BLOCKS
 #define RSQ_HOT_MIN_BLOCKS 3
 #endif
-template <bool kBed>
+}  // namespace
+}  // namespace rsqd
+#include "rsq_legacy.cuh"
+namespace rsqd {
+namespace {
+
+template <bool kBed, bool kLegacy>
 __global__ void __launch_bounds__(kHotThreads, RSQ_HOT_MIN_BLOCKS)
 hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict__ blocks, size_t n_reads, size_t n_blocks,
                 const AnnView ann, const BedView bed, const Accum acc, const Params prm) {
@@ -304,7 +310,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         else if (f & RSQ_F_QCFAIL) CNT(RSQ_C_FAILED_VENDOR_QC);
         else if (mapq < prm.mapq_threshold) CNT(RSQ_C_LOW_MAPPING_QUALITY);
         const bool has_ch = aux & RSQ_AUX_CHIMERIC_TAG;
-        if ((f & RSQ_F_SUPPLEMENTARY) && !has_ch) {                                    // :258-262
+        if ((f & RSQ_F_SUPPLEMENTARY) && !(kLegacy || has_ch)) {                       // :258-262
             CNT(RSQ_C_CHIMERIC_AUTO);
             if (prm.exclude_chimeric) go = false;
         }
@@ -317,7 +323,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         if (go) {
             CNT(RSQ_C_MAPPED_READS);
             if (f & RSQ_F_DUP) CNT(RSQ_C_MAPPED_DUPLICATE_READS); else CNT(RSQ_C_MAPPED_UNIQUE_READS);
-            if (has_ch) {                                                              // :279-283
+            if (kLegacy && (unsigned)(endpos - pos) > 100000u) go = false;             // :275-276 LEGACY_MAX_READ_LENGTH
+            if (go && !kLegacy && has_ch) {                                            // :279-283
                 if (f & RSQ_F_READ1) CNT(RSQ_C_CHIMERIC_TAG);
                 if (prm.exclude_chimeric) go = false;
             }
@@ -325,7 +332,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         if (go && (f & RSQ_F_PAIRED) && !(f & RSQ_F_MUNMAP)) {                         // :284-292
             if (f & RSQ_F_READ1) CNT(RSQ_C_TOTAL_MAPPED_PAIRS);
             int d = pos - mpos; d = d < 0 ? -d : d;
-            if ((aux & RSQ_AUX_MATE_OTHER_CONTIG) || d > prm.chimeric_distance) {
+            if ((aux & RSQ_AUX_MATE_OTHER_CONTIG) || d > prm.chimeric_distance || (kLegacy && (aux & RSQ_AUX_TID_GT_127))) {
                 if (f & RSQ_F_READ1) CNT(RSQ_C_CHIMERIC_AUTO);
                 if (prm.exclude_chimeric) go = false;
             }
@@ -377,6 +384,13 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                 if ((prm.strand_mode == 1) != ((f & RSQ_F_READ1) != 0)) target = !target;
                 rstrand = target ? RSQ_STRAND_REV : RSQ_STRAND_FWD;
             }
+            const rsq_block* bp = blocks + block_off;
+            if constexpr (kLegacy) {                                                   // :364
+                LegacyRead lr;
+                lr.contig = contig; lr.pos = pos; lr.endpos = endpos; lr.l_qseq = l_qseq; lr.rstrand = rstrand;
+                lr.flag = f; lr.nb = nb; lr.cleared = cleared; lr.hq = hq; lr.name_hash = name_hash; lr.bp = bp;
+                legacy_metrics(ann, acc, prm, lr, cm, n_fresh, my_bytes);
+            } else {
             int c_lo = 0, c_hi = 0, s_hi = 0, bk_lo = 0, bk_n = 1;
             if (!cleared) {
                 c_lo = (int)__ldg(&ann.exon_off[contig]); c_hi = (int)__ldg(&ann.exon_off[contig + 1]);
@@ -403,7 +417,6 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             uint32_t length = 0;                                                       // extractBlocks' return, :359
             BlockView v0 = {0, 0, false}, v1 = v0;
             int bs0 = 0, be0 = 0, bs1 = 0, be1 = 0;
-            const rsq_block* bp = blocks + block_off;
             for (uint32_t b = 0; b < nb; ++b) {                                        // :325-361
                 const int2 blk = __ldg(reinterpret_cast<const int2*>(bp + b));
                 const int bs = blk.x, be = blk.x + blk.y;                              // closed end = start+len, :45
@@ -571,6 +584,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                 if (prm.unpaired || (f & RSQ_F_READ1)) { if (sense) CNT(RSQ_C_END1_SENSE); else CNT(RSQ_C_END1_ANTISENSE); }
                 else { if (sense) CNT(RSQ_C_END2_SENSE); else CNT(RSQ_C_END2_ANTISENSE); }
             }
+
+            }  // !kLegacy
 
             // ---- fragmentSizeMetrics candidate, RNASeQC.cpp:372 + Expression.cpp:482-516 ----------------------------
             if (kBed) {
@@ -948,20 +963,28 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
                     const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
     // persistent grid: every SM holds exactly as many CTAs as its register file admits
-    static int per_sm[2] = {0, 0}, sms = 0;
-    const int which = prm.bed_enabled ? 1 : 0;
+    static int per_sm[4] = {0, 0, 0, 0}, sms = 0;
+    const int which = (prm.bed_enabled ? 1 : 0) | (prm.legacy ? 2 : 0);
     if (!per_sm[which]) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (which) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], hot_path_kernel<true>, kHotThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], hot_path_kernel<false>, kHotThreads, 0);
+        switch (which) {
+            case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], hot_path_kernel<false, false>, kHotThreads, 0); break;
+            case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], hot_path_kernel<true, false>, kHotThreads, 0); break;
+            case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], hot_path_kernel<false, true>, kHotThreads, 0); break;
+            default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], hot_path_kernel<true, true>, kHotThreads, 0); break;
+        }
         if (per_sm[which] < 1) per_sm[which] = 1;
     }
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
-    if (prm.bed_enabled) hot_path_kernel<true><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm);
-    else hot_path_kernel<false><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm);
+    switch (which) {
+        case 0: hot_path_kernel<false, false><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
+        case 1: hot_path_kernel<true, false><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
+        case 2: hot_path_kernel<false, true><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
+        default: hot_path_kernel<true, true><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
+    }
     return 1;
 }
 

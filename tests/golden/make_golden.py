@@ -29,8 +29,15 @@ KAT_FLAGSETS = {
     "exclude_chimeric": ["--exclude-chimeric"],
     "tag_filter": ["-t", "XS", "-t", "XT"],
     "rpkm_sample": ["--rpkm", "-s", "mysample", "-q", "3", "--base-mismatch", "2", "--chimeric-distance", "1000"],
+    "legacy": ["--legacy", "--coverage"],
 }
-SYNTH_FLAGSETS = {"coverage_bed": ["--coverage", "--bed", "a.bed"]}
+KAT_LEGACY_FLAGSETS = {
+    "legacy": ["--legacy", "--coverage"],
+    "legacy_rf": ["--legacy", "--stranded", "rf"],
+    "legacy_fr_excl_u": ["--legacy", "--stranded", "fr", "--exclude-chimeric", "-u"],
+    "legacy_q255": ["--legacy", "-q", "255", "--base-mismatch", "2", "--coverage"],
+}
+SYNTH_FLAGSETS = {"coverage_bed": ["--coverage", "--bed", "a.bed"], "legacy": ["--legacy", "--coverage", "--bed", "a.bed"]}
 
 
 def run_ref(gtf, sam, out, flags, cwd):
@@ -179,6 +186,115 @@ def kat_sam():
     return "\n".join(lines) + "\n"
 
 
+def kat_legacy_gtf():
+    """Annotation for the --legacy known-answer cases (src/Expression.cpp:129-304, src/RNASeQC.cpp:129-135)."""
+    L = ["##kat legacy annotation"]
+
+    def line(chrom, kind, s, e, strand, attr):
+        L.append(f"{chrom}\tkat\t{kind}\t{s}\t{e}\t.\t{strand}\t.\t{attr}")
+
+    def gene(chrom, gid, name, strand, exons, ttype="protein_coding", span=None):
+        s, e = span if span else (min(x[0] for x in exons), max(x[1] for x in exons))
+        attr = GTF_ATTR.format(g=gid, t=ttype, n=name)
+        line(chrom, "gene", s, e, strand, attr)
+        line(chrom, "transcript", s, e, strand, attr)
+        for k, (a, b) in enumerate(exons):
+            line(chrom, "exon", a, b, strand, attr + f' exon_id "{gid}_{k + 1}";')
+
+    gene("chrA", "GA", "GeneA", "+", [(1000, 1199), (2000, 2199), (3000, 3499)])
+    gene("chrA", "GB", "GeneB", "-", [(2100, 2600)])
+    gene("chrA", "GS", "SingleBaseExon", "+", [(5000, 5000), (5100, 5300)])       # 1-base exon: dropped from the list, stays in exonList
+    gene("chrA", "GT", "SingleBaseGene", "-", [(6000, 6000)])                     # 1-base gene line and exon
+    gene("chrA", "GX", "Beyond", "+", [(8000, 8300)])
+    gene("chrA", "GO", "Outer", "+", [(8900, 9300)])
+    gene("chrA", "GN", "LateLine", "+", [(9600, 9900)], span=(9100, 9900))        # gene line starts after GO's exon: last list hit of a read at 8900
+    gene("chrA", "GR", "Ribo", "-", [(11000, 11400)], ttype="rRNA")
+    gene("chrA", "GD", "Dot", ".", [(12000, 12400), (12700, 12900)])
+    gene("chrA", "GW", "Wide", "+", [(20000, 20200), (130000, 130200)])           # intron > LEGACY_MAX_READ_LENGTH
+    # two exons of one gene overlapping each other (uncollapsed model): list order decides which one counts
+    gene("chrA", "GU", "Overlap", "+", [(14000, 14400), (14000, 14200), (14100, 14600)])
+    gene("c129", "GZ", "HighTid", "+", [(1000, 1500)])
+    return "\n".join(L) + "\n"
+
+
+def kat_legacy_sam():
+    H = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:chrA\tLN:5000000"] + [f"@SQ\tSN:c{k}\tLN:100000" for k in range(1, 130)]
+    R = []
+    n = [0]
+
+    def rd(chrom, pos, cigar, flag=99, mapq=255, nm=0, lq=150, rnext="=", pnext=None, tlen=300, tags=(), name=None):
+        n[0] += 1
+        name = name or f"L{n[0]}"
+        pnext = pos + 150 if pnext is None else pnext
+        t = list(tags)
+        if nm is not None:
+            t.insert(0, f"NM:i:{nm}")
+        R.append((chrom, pos, "\t".join([name, str(flag), chrom, str(pos), str(mapq), cigar, rnext, str(pnext), str(tlen), "A" * lq, "F" * lq] + t)))
+
+    rd("chrA", 1010, "150M")                               # one block in exon 1: counted whole
+    rd("chrA", 1010, "150M", flag=147, name="L1")          # mate: one fragment
+    rd("chrA", 1100, "100M800N50M")                        # split (gap 800 > 99): dosage 100/150 and 50/150 as floats
+    rd("chrA", 1150, "50M50N50M", lq=100)                  # gap 50: not split; second block intronic -> last block finds nothing: not counted
+    rd("chrA", 1100, "150M")                               # partial overlap with exon 1 only -> intron+no exon -> Intronic
+    rd("chrA", 1150, "50M800N100M")                        # first block inside, second inside exon 2: split
+    rd("chrA", 1150, "60M790N100M", lq=160)                # first block overruns exon 1 (partial), second full: junction -> Intronic
+    rd("chrA", 1010, "50M100N50M1790N50M")                 # blocks: exon1, intron, exon3 -> legacyNotSplit: exon 3 counted 1.0
+    rd("chrA", 3010, "40M2D40M1000N70M", flag=163)         # deletion: two blocks in exon 3 (floats summed) ... third block outside the gene's exons
+    rd("chrA", 3010, "40M2D40M100N70M")                    # split by the 100-base gap; three blocks all inside exon 3
+    rd("chrA", 2120, "50M", lq=50)                         # inside GA exon 2 and GB exon: both gene lines counted
+    rd("chrA", 2120, "50M", lq=50, flag=147 | 0x400)       # duplicate
+    rd("chrA", 2300, "100M", lq=100)                       # GB only; GA intragenic without exon
+    rd("chrA", 3400, "50M4550N100M")                       # second block starts beyond GA's end -> legacyNotExonic -> Intronic (block 2 in GX exon)
+    rd("chrA", 5000, "1M99N140M", lq=141)                  # first block on the dropped 1-base exon
+    rd("chrA", 5150, "100M", lq=100)                       # GS second exon
+    rd("chrA", 6000, "1M", lq=1)                           # the 1-base gene does not exist in legacy mode -> Intergenic
+    rd("chrA", 8900, "50M200N50M", lq=100)                 # GO split read; the last list hit is GN's gene line -> legacyNotSplit set: no 'Split Reads'
+    rd("chrA", 8900, "100M", lq=100)                       # GO only (GN line starts at 9100)
+    rd("chrA", 9650, "150M")                               # GN exon
+    rd("chrA", 11050, "150M")                              # rRNA
+    rd("chrA", 11050, "150M", flag=83)
+    rd("chrA", 12050, "150M")                              # '.' strand
+    rd("chrA", 12300, "100M300N50M", flag=163)
+    rd("chrA", 14000, "150M")                              # overlapping exons of GU: first in list order that contains the block
+    rd("chrA", 14120, "60M", lq=60)                        # contained by all three
+    rd("chrA", 14250, "100M", lq=100)                      # contained by exons 1 and 3 only
+    rd("chrA", 20050, "100M109850N50M")                    # PositionEnd - Position > 100000: skipped after 'Mapped Reads'
+    rd("chrA", 20050, "100M", lq=100)
+    rd("chrA", 3060, "150M", nm=None)                      # NM absent
+    rd("chrA", 3070, "150M", nm=7)                         # low quality: classified, not counted
+    rd("chrA", 3080, "150M", mapq=3)                       # below the legacy default of 4
+    rd("chrA", 3085, "150M", mapq=4)                       # at the legacy default
+    rd("chrA", 3090, "150M", flag=99 | 0x100)              # secondary
+    rd("chrA", 3100, "150M", flag=99 | 0x800)              # supplementary: never 'Chimeric Fragments_auto' in legacy
+    rd("chrA", 3110, "150M", flag=99 | 0x800, tags=["ch:A:1"])
+    rd("chrA", 3180, "150M", tags=["ch:Z:chimera"])        # chimeric tag ignored in legacy
+    rd("chrA", 3190, "150M", flag=97, pnext=4000000, tlen=0)   # mate too far
+    rd("chrA", 3200, "150M", flag=0)                       # unpaired
+    rd("chrA", 3210, "10S140M")                            # soft clip: Length() counts it
+    rd("chrA", 3215, "10S40M200N100M")                     # soft clip + split: dosage over Length()=150
+    rd("chrA", 70000, "150M")                              # intergenic
+    rd("c129", 1100, "150M")                               # ChrID 129 > 127: paired with mapped mate -> chimeric in legacy
+    rd("c129", 1100, "150M", flag=147, name="hz")
+    rd("c129", 1200, "150M", flag=0)                       # unpaired: unaffected
+    order = {"chrA": 0}
+    order.update({f"c{k}": k for k in range(1, 130)})
+    R.sort(key=lambda x: (order[x[0]], x[1]))
+    return "\n".join(H + [x[2] for x in R]) + "\n"
+
+
+def make_kat_legacy():
+    d = os.path.join(HERE, "kat_legacy")
+    os.makedirs(d, exist_ok=True)
+    open(os.path.join(d, "kat.gtf"), "w").write(kat_legacy_gtf())
+    sam = os.path.join(d, "kat.sam")
+    open(sam, "w").write(kat_legacy_sam())
+    for name, flags in KAT_LEGACY_FLAGSETS.items():
+        run_ref("kat.gtf", "kat.sam", os.path.join("expected", name), flags, d)
+    with open(sam, "rb") as fi, gzip.open(sam + ".gz", "wb", compresslevel=9) as fo:
+        shutil.copyfileobj(fi, fo)
+    os.remove(sam)
+
+
 def make_kat():
     d = os.path.join(HERE, "kat")
     os.makedirs(d, exist_ok=True)
@@ -197,4 +313,5 @@ if __name__ == "__main__":
         raise SystemExit("build the reference first: make ref")
     make_synth_small()
     make_kat()
+    make_kat_legacy()
     print("golden fixtures written under", HERE)

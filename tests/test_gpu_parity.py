@@ -10,7 +10,7 @@ import pytest
 from util import assert_results_equal, compare_outputs, run_cli, unpack_case
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_golden import KAT_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
+from make_golden import KAT_FLAGSETS, KAT_LEGACY_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -211,3 +211,55 @@ def test_dense_annotation_forces_the_unstaged_path(libs, tmp_path):
         got, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=len(reads), **kw))
         assert_results_equal(got, want, f"dense {kw}")
     assert want.counter("Ambiguous Reads") > 0 and want.gene_reads.sum() > 1000
+
+
+# ---- --legacy counting rules (src/Expression.cpp:129-304) ------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def legacy_case(libs, tmp_path_factory):
+    """Synthetic sample for the legacy rules: uncollapsed annotation quirks are covered by the KAT; this one brings volume
+    (split reads, multi-gene reads, duplicates, chimeras, tid > 127 through the aux bit)."""
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    d = str(tmp_path_factory.mktemp("legacy"))
+    sa = synth.make_annotation(seed=201, n_genes=400, contig_names=["chr1", "chr2", "chr3", "chrM"],
+                               contig_lens=[40_000_000, 30_000_000, 20_000_000, 16569])
+    synth.write_gtf(sa, os.path.join(d, "a.gtf"))
+    synth.write_bed(sa, os.path.join(d, "a.bed"), min_len=400)
+    ann = api.Annotation(os.path.join(d, "a.gtf"), os.path.join(d, "a.bed"), legacy=True)
+    sr = synth.simulate_reads(sa, 300000, seed=202)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    rng = np.random.default_rng(7)
+    reads["aux"] |= ((rng.random(len(reads)) < 0.01) * 0x20).astype(np.uint8)      # RSQ_AUX_TID_GT_127
+    return ann, reads, blocks
+
+
+LEGACY_CONFIGS = {
+    "legacy": dict(mapq=4),
+    "legacy_bed": dict(mapq=4, fragment_samples=100000),
+    "legacy_rf_excl": dict(mapq=4, strand_mode=2, exclude_chimeric=True),
+    "legacy_fr_unpaired_q255": dict(strand_mode=1, unpaired=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LEGACY_CONFIGS))
+def test_cuda_legacy_rules_match_oracle(libs, legacy_case, name):
+    api = libs["api"]
+    ann, reads, blocks = legacy_case
+    cfg = lambda: api.make_config(max_records=len(reads), legacy=True, **LEGACY_CONFIGS[name])
+    want, want_bytes = _run(api, libs["oracle"], ann, reads, blocks, cfg())
+    got, got_bytes = _run(api, libs["product"], ann, reads, blocks, cfg(), chunks=3)
+    assert_results_equal(got, want, name)
+    assert got_bytes == want_bytes
+    assert want.counter("Split Reads") > 10000 and want.gene_reads.sum() > 100000
+    assert want.counter("Chimeric Fragments_auto") > 0
+
+
+@pytest.mark.parametrize("flagset", sorted(KAT_LEGACY_FLAGSETS))
+def test_kat_legacy_product_cli_matches_reference(libs, tmp_path, flagset):
+    d = unpack_case("kat_legacy", tmp_path)
+    out = os.path.join(d, "out_" + flagset)
+    run_cli(libs["cli"], os.path.join(d, "kat.gtf"), os.path.join(d, "kat.sam"), out, *KAT_LEGACY_FLAGSETS[flagset])
+    identical = set(compare_outputs(os.path.join(d, "expected", flagset), out))
+    assert {"kat.sam.gene_reads.gct", "kat.sam.gene_fragments.gct", "kat.sam.exon_reads.gct"} <= identical, identical

@@ -15,6 +15,8 @@ CASES = [
     ("plain", 61, []),
     ("stranded_rf_bed", 62, ["--stranded", "rf", "--bed", "BED", "--fragment-samples", "500"]),
     ("unpaired_excl", 63, ["-u", "--exclude-chimeric", "--coverage", "--coverage-mask", "100"]),
+    ("legacy_coverage", 65, ["--legacy", "--coverage"]),
+    ("legacy_rf_bed_excl", 66, ["--legacy", "--stranded", "rf", "--bed", "BED", "--exclude-chimeric"]),
     ("loose", 64, ["-q", "3", "--base-mismatch", "3", "--chimeric-distance", "5000", "--detection-threshold", "2", "--gene-length", "150", "--window-size", "60"]),
 ]
 
