@@ -170,6 +170,18 @@ typedef struct rsq_bed {
     const uint8_t*  contig_present; /* [n_contigs] bedFeatures->find(chr) != end (src/RNASeQC.cpp:372)     */
 } rsq_bed;
 
+/* Reference genome as a G/C bit mask, for the fragment GC-content sampler of --fasta runs: replaces Fasta::hasContig /
+ * Fasta::getSeq + gc() on the path (src/Fasta.cpp:66-75,103-150, src/Expression.cpp:459-476).  Bit b of word w of a contig
+ * is set when base 32*w+b (0-based) is one of G, C, g, c. */
+typedef struct rsq_reference {
+    uint32_t struct_size;
+    uint32_t n_contigs;          /* same contig index space as rsq_annotation                                */
+    const uint8_t*  present;     /* [n_contigs] Fasta::hasContig                                              */
+    const uint64_t* length;      /* [n_contigs] bases (0 when absent)                                         */
+    const uint64_t* word_off;    /* [n_contigs+1] first 32-bit word of each contig in gc_bits                 */
+    const uint32_t* gc_bits;     /* [word_off[n_contigs]]                                                     */
+} rsq_reference;
+
 /* ---- counters: fixed indices replacing the string-keyed Metrics map (src/Metrics.h:31-41) --------------- */
 enum {
     RSQ_C_ALTERNATIVE_ALIGNMENTS = 0, RSQ_C_SUPPLEMENTARY_ALIGNMENTS, RSQ_C_FAILED_VENDOR_QC,
@@ -209,6 +221,7 @@ typedef struct rsq_results {
                                   the last bin collects |isize| >= fragment_hist_len-1                   */
     uint64_t  fragment_hist_len;
     uint64_t  fragment_samples_taken;
+    uint64_t* gc_hist;         /* [100] gcBins (src/RNASeQC.cpp:106,368); all zero without rsq_set_reference */
 } rsq_results;
 
 typedef struct rsq_ctx rsq_ctx;
@@ -230,6 +243,10 @@ const char* rsq_last_error(const rsq_ctx* ctx); /* ctx may be NULL: error of the
 int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* ann);
 /* Replaces bedFeatures (src/RNASeQC.cpp:169-187). */
 int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* bed);
+/* Enables the fragment GC-content sampler of --fasta runs (src/Expression.cpp:459-476; gcContentFragmentTracker,
+ * src/RNASeQC.cpp:170): after the annotation, before the first submit.  Ignored by the --legacy rules, which never
+ * sample (src/RNASeQC.cpp:364). */
+int rsq_set_reference(rsq_ctx* ctx, const rsq_reference* ref);
 
 /* Replaces one or more iterations of the loop body src/RNASeQC.cpp:242-382 (and everything it calls:
  * extractBlocks' output is the blocks array; trimFeatures/intersectBlock/exonAlignmentMetrics/
@@ -286,8 +303,8 @@ typedef struct rsq_coverage_stats {
 int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* req, rsq_coverage_stats* out);
 
 /* Device-resident count vector for the end-of-run all-reduce over NVLink (counters ‖ gene_reads ‖
- * gene_unique ‖ gene_fragments ‖ exon_whole ‖ exon_frac_hi32 ‖ exon_frac_lo32), all uint64, additive across
- * partitions.  Returns a DEVICE pointer and the number of uint64 words; valid until rsq_destroy.
+ * gene_unique ‖ gene_fragments ‖ exon_whole ‖ exon_frac_hi32 ‖ exon_frac_lo32 ‖ gc_hist[100]), all uint64, additive
+ * across partitions.  Returns a DEVICE pointer and the number of uint64 words; valid until rsq_destroy.
  * rsq_finalize must not have been called between rsq_export_counts and rsq_import_counts. */
 int rsq_export_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words);
 /* After the caller reduced the exported buffer in place (NCCL sum), fold it back into the ctx state. */

@@ -72,7 +72,12 @@ class RsqResults(C.Structure):
                 ("gene_fragments", C.POINTER(C.c_uint64)), ("exon_whole", C.POINTER(C.c_uint64)),
                 ("exon_frac", C.POINTER(C.c_uint64)), ("coverage", C.POINTER(C.c_uint32)),
                 ("fragment_hist", C.POINTER(C.c_uint64)), ("fragment_hist_len", C.c_uint64),
-                ("fragment_samples_taken", C.c_uint64)]
+                ("fragment_samples_taken", C.c_uint64), ("gc_hist", C.POINTER(C.c_uint64))]
+
+
+class RsqReference(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_contigs", C.c_uint32), ("present", C.POINTER(C.c_uint8)),
+                ("length", C.POINTER(C.c_uint64)), ("word_off", C.POINTER(C.c_uint64)), ("gc_bits", C.POINTER(C.c_uint32))]
 
 
 class RsqTranscripts(C.Structure):
@@ -101,7 +106,7 @@ class StreamStateC(C.Structure):
 
 
 ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
-               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_submit", "rsq_submit_device", "rsq_sync",
+               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_device", "rsq_sync",
                "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_export_counts", "rsq_import_counts", "rsq_algorithmic_bytes",
                "rsq_launch_count", "rsq_kernel_time_ms"]
 
@@ -147,6 +152,7 @@ class Results:
         self.coverage = np.zeros(cov_len + 1, np.uint32) if want_coverage else None
         self.fragment_hist = np.zeros(hist_len, np.uint64)
         self.fragment_samples_taken = 0
+        self.gc_hist = np.zeros(100, np.uint64)
 
     def struct(self) -> RsqResults:
         r = RsqResults()
@@ -158,6 +164,7 @@ class Results:
             r.coverage = self.coverage.ctypes.data_as(C.POINTER(C.c_uint32))
         r.fragment_hist = p64(self.fragment_hist)
         r.fragment_hist_len = len(self.fragment_hist)
+        r.gc_hist = p64(self.gc_hist)
         return r
 
     def counter(self, name: str) -> int:
@@ -238,6 +245,8 @@ class Context:
         self._check(self.be.lib.rsq_set_annotation(self.h, C.byref(v)))
         if ann.bed_view is not None and self.cfg.fragment_samples:
             self._check(self.be.lib.rsq_set_bed(self.h, ann.bed_view))
+        if ann.ref_view is not None:
+            self._check(self.be.lib.rsq_set_reference(self.h, ann.ref_view))
 
     def submit(self, reads: np.ndarray, blocks: np.ndarray) -> None:
         """host arrays (structured READ_DTYPE/BLOCK_DTYPE, or raw uint8/int32 views of the same bytes)"""
@@ -330,6 +339,9 @@ def host_lib():
         H.rsqh_annotation_view.argtypes = [C.c_void_p]
         H.rsqh_bed_view.restype = C.POINTER(RsqBed)
         H.rsqh_bed_view.argtypes = [C.c_void_p]
+        H.rsqh_reference_view.restype = C.POINTER(RsqReference)
+        H.rsqh_reference_view.argtypes = [C.c_void_p]
+        H.rsqh_set_fasta.argtypes = [C.c_char_p]
         H.rsqh_transcripts.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_ulong, C.POINTER(RsqTranscripts)]
         for f in ("rsqh_n_gene_list", "rsqh_n_contigs"):
             getattr(H, f).restype = C.c_uint
@@ -356,10 +368,11 @@ def host_lib():
 class Annotation:
     """Flattened annotation parsed from GTF (+BED) text by the C++ host library."""
 
-    def __init__(self, gtf: str, bed: Optional[str] = None, legacy: bool = False):
+    def __init__(self, gtf: str, bed: Optional[str] = None, legacy: bool = False, fasta: Optional[str] = None):
         H = host_lib()
         self.legacy = legacy
         H.rsqh_set_legacy(int(legacy))
+        H.rsqh_set_fasta(fasta.encode() if fasta else None)
         self._h = C.c_void_p()
         err = C.create_string_buffer(1024)
         rc = H.rsqh_load_annotation(gtf.encode(), bed.encode() if bed else None, C.byref(self._h), err, 1024)
@@ -368,6 +381,9 @@ class Annotation:
         self.view = H.rsqh_annotation_view(self._h).contents
         bv = H.rsqh_bed_view(self._h)
         self.bed_view = bv if bv else None
+        rv = H.rsqh_reference_view(self._h)
+        self.ref_view = rv if rv else None
+        H.rsqh_set_fasta(None)
 
     def __del__(self):
         try:

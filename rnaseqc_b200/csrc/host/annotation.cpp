@@ -178,6 +178,8 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
             exon_slot = (uint32_t)A.exon_ids.size();
             A.exon_ids.push_back(cur_feature_id);
             A.exon_len.push_back(1 + (end - start));
+            A.exon_start.push_back(start);
+            A.exon_contig.push_back(contig);
             uint32_t g = A.gene_universe(cur_gene_id);
             A.gene_coding_len[g] += 1 + (end - start);
         }

@@ -73,6 +73,8 @@ struct Annotation {
     std::vector<std::string> exon_ids;
     std::vector<std::string> exon_desc;      // geneNames[exon_id]
     std::vector<int64_t> exon_len;           // exonLengths[id].length (src/GTF.cpp:108)
+    std::vector<int64_t> exon_start;         // exonLengths[id].start
+    std::vector<uint32_t> exon_contig;       // exonLengths[id].chromosome
     std::vector<uint64_t> exon_cov_off;      // per slot: first base in the coverage array
     uint64_t cov_len = 0;
     // kept features per contig, stable-sorted by start (src/RNASeQC.cpp:150-152)

@@ -8,6 +8,7 @@
 #include "alnreader.h"
 #include "bamparallel.h"
 #include "annotation.h"
+#include "fasta.h"
 #include "pipeline.h"
 #include "report.h"
 
@@ -16,12 +17,15 @@ using namespace rsqh;
 namespace {
 int g_decode_threads = 0;
 bool g_legacy = false;
+std::string g_fasta;
 struct Handle {
     Annotation ann;
     BedModel bed;
     bool have_bed = false;
     rsq_annotation ann_view;
     rsq_bed bed_view;
+    ReferenceModel ref;
+    rsq_reference ref_view;
     StreamState state;
 };
 void set_err(char* err, size_t n, const std::string& s) {
@@ -57,12 +61,14 @@ struct rsqh_stream_state {
 int rsqh_load_annotation(const char* gtf, const char* bed, void** out, char* err, size_t errlen) {
     try {
         std::unique_ptr<Handle> h(new Handle());
+        if (!g_fasta.empty()) open_reference(g_fasta, h->ann.contigs, h->ref);   // before the GTF, src/RNASeQC.cpp:117-122
         load_gtf(gtf, h->ann, g_legacy);
         if (bed && *bed) { load_bed(bed, h->ann.contigs, h->bed); h->have_bed = true; }
         const size_t nc = h->ann.contigs.names.size();
         h->ann.pad_contigs(nc);
         if (h->have_bed) { flatten_bed(h->bed, nc); h->bed_view = h->bed.view(); }
         h->ann_view = h->ann.view();
+        if (h->ref.open) { load_reference_bits(h->ref, nc); h->ref_view = h->ref.view(); }
         *out = h.release();
         return 0;
     } catch (HostError& e) {
@@ -155,6 +161,9 @@ void rsqh_free(void* p) { free(p); }
 void rsqh_set_decode_threads(int n) { g_decode_threads = n; }
 // --legacy for the calls that follow: GTF filter (src/RNASeQC.cpp:129-135) and the decoder's loop gates
 void rsqh_set_legacy(int on) { g_legacy = on != 0; }
+// --fasta for the rsqh_load_annotation calls that follow (NULL or "" = none)
+void rsqh_set_fasta(const char* path) { g_fasta = path ? path : ""; }
+const rsq_reference* rsqh_reference_view(void* h) { Handle* H = static_cast<Handle*>(h); return H->ref.open ? &H->ref_view : nullptr; }
 
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
 
@@ -176,6 +185,7 @@ int rsqh_write_reports(void* hv, const rsq_results* res, const double* exon_seq_
         if (res->coverage) R.coverage.assign(res->coverage, res->coverage + A.cov_len);
         if (res->fragment_hist) R.fragment_hist.assign(res->fragment_hist, res->fragment_hist + res->fragment_hist_len);
         R.fragment_samples_taken = res->fragment_samples_taken;
+        if (res->gc_hist) memcpy(R.gc_hist, res->gc_hist, sizeof(R.gc_hist));
         RunOptions opt;
         opt.sample_name = o->sample_name; opt.sample_given = o->sample_given != 0; opt.output_dir = o->output_dir;
         opt.use_rpkm = o->use_rpkm != 0; opt.write_coverage = o->write_coverage != 0; opt.coverage_mask = o->coverage_mask;
@@ -186,7 +196,7 @@ int rsqh_write_reports(void* hv, const rsq_results* res, const double* exon_seq_
         S.read_length = st->read_length; S.alignment_count = st->alignment_count;
         S.final_contig = st->final_contig; S.final_position = st->final_position;
         S.dropped_order.assign(st->dropped, st->dropped + st->n_dropped);
-        write_reports(A, R, opt, S);
+        write_reports(A, R, opt, S, h->ref.open ? &h->ref : nullptr);
         return 0;
     } catch (HostError& e) {
         set_err(err, errlen, e.what());

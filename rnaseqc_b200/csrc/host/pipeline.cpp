@@ -26,7 +26,7 @@ void usage(std::ostream& o) {
          "      output                            Output directory\n"
          "      -s[sample], --sample=[sample]     The name of the current sample. Default: The bam's filename\n"
          "      --bed=[BEDFILE]                   BED file with non-overlapping exons used for fragment size calculations\n"
-         "      --fasta=[fasta]                   (not supported by this build)\n"
+         "      --fasta=[fasta]                   Reference genome FASTA (indexed, .fai): enables GC content statistics\n"
          "      --chimeric-distance=[DISTANCE]    Maximum accepted distance between read mates. Default: 2000000 [bp]\n"
          "      --fragment-samples=[SAMPLES]      Number of fragment size samples. Requires --bed. Default: 1000000\n"
          "      -q[QUALITY], --mapping-quality=[QUALITY]  Lower bound on read quality for exon coverage counting. Default: 255\n"
@@ -144,10 +144,6 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
         opt.decode.legacy = true;
         if (!mapq_given) opt.cfg.mapq_threshold = 4;
     }
-    if (!opt.fasta.empty()) {
-        std::cerr << "--fasta (GC content / CRAM reference) is not implemented in this build (SURVEY.md §8f)" << std::endl;
-        return 6;
-    }
     if (opt.decode.filter_tags.size() > 8) {
         std::cerr << "At most 8 --tag filters are supported" << std::endl;
         return 6;
@@ -175,6 +171,7 @@ void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool wa
     out.exon_whole = R.exon_whole.data(); out.exon_frac = R.exon_frac.data();
     out.coverage = want_coverage ? R.coverage.data() : nullptr;
     out.fragment_hist = R.fragment_hist.data(); out.fragment_hist_len = R.fragment_hist.size();
+    out.gc_hist = R.gc_hist;
     int rc = be.finalize(ctx, &out);
     if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_finalize failed: ") + be.last_error(ctx));
     memcpy(R.counters, out.counters, sizeof(R.counters));
@@ -208,6 +205,11 @@ int run_sample(const Backend& be, CliOptions& opt) {
     int exit_code = 0;
     try {
         Annotation A;
+        ReferenceModel ref;
+        if (!opt.fasta.empty()) {                                                  // src/RNASeQC.cpp:117-122: before the GTF
+            open_reference(opt.fasta, A.contigs, ref);
+            if (opt.verbosity > 1) std::cout << "A FASTA has been provided. This will enable GC-content statistics but adds additional runtime and memory costs" << std::endl;
+        }
         auto t0 = clk::now();
         if (opt.verbosity) std::cout << "Reading GTF Features..." << std::endl;
         load_gtf(opt.gtf, A, opt.legacy);
@@ -222,6 +224,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
         A.pad_contigs(n_contigs);
         if (!opt.bed.empty()) flatten_bed(bed, n_contigs);
         if (n_contigs > 32767) throw HostError(11, "more than 32767 annotated contigs");
+        if (ref.open) load_reference_bits(ref, n_contigs);
         try {
             if (!std::filesystem::exists(opt.output_dir)) std::filesystem::create_directories(opt.output_dir);
         } catch (std::filesystem::filesystem_error& e) {
@@ -262,6 +265,11 @@ int run_sample(const Backend& be, CliOptions& opt) {
             rsq_bed bv = bed.view();
             rc = be.set_bed(ctx, &bv);
             if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_bed failed: ") + be.last_error(ctx));
+        }
+        if (ref.open) {
+            rsq_reference rv = ref.view();
+            rc = be.set_reference(ctx, &rv);
+            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_reference failed: ") + be.last_error(ctx));
         }
 
         if (opt.verbosity) std::cout << "Device context + annotation upload: " << std::chrono::duration<double>(clk::now() - t_setup).count() << " seconds" << std::endl;
@@ -326,7 +334,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
         if (opt.verbosity) std::cout << "Finalize + coverage statistics: " << std::chrono::duration<double>(clk::now() - t_fin).count() << " seconds" << std::endl;
         if (opt.verbosity) std::cout << "Generating report" << std::endl;
         auto t_rep = clk::now();
-        write_reports(A, R, opt.run, st);
+        write_reports(A, R, opt.run, st, ref.open ? &ref : nullptr);
         if (opt.verbosity) std::cout << "Report files: " << std::chrono::duration<double>(clk::now() - t_rep).count() << " seconds" << std::endl;
     } catch (HostError& e) {
         std::cerr << e.what() << std::endl;

@@ -22,6 +22,7 @@ struct Backend {
     decltype(&rsq_last_error) last_error;
     decltype(&rsq_set_annotation) set_annotation;
     decltype(&rsq_set_bed) set_bed;
+    decltype(&rsq_set_reference) set_reference;
     decltype(&rsq_submit) submit;
     decltype(&rsq_sync) sync;
     decltype(&rsq_finalize) finalize;

@@ -323,7 +323,7 @@ const CounterName kDumpOrder[] = {
 
 }  // namespace
 
-void write_reports(const Annotation& A, const HostResults& R, const RunOptions& opt, const StreamState& st) {
+void write_reports(const Annotation& A, const HostResults& R, const RunOptions& opt, const StreamState& st, const ReferenceModel* ref) {
     namespace fs = std::filesystem;
     try {
         if (!fs::exists(opt.output_dir)) fs::create_directories(opt.output_dir);   // src/RNASeQC.cpp:190-193
@@ -536,18 +536,60 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         output << "Median of Avg Transcript Coverage\t" << median_quirk(n_transcripts, [&](unsigned long i) { return means[i]; }) << '\n';
         output << "Median of Transcript Coverage Std\t" << median_quirk(n_transcripts, [&](unsigned long i) { return stds[i]; }) << '\n';
         output << "Median of Transcript Coverage CV\t" << (n_cvs ? median_quirk(n_cvs, [&](unsigned long i) { return cvs[i]; }) : 0.0) << '\n';
+        const bool fasta = ref && ref->open;
+        std::map<std::string, uint32_t> slot_of;
+        if (fasta) for (size_t e = 0; e < A.exon_ids.size(); ++e) slot_of[A.exon_ids[e]] = (uint32_t)e;
         std::map<std::string, double> exon_cov;  // exonCoverage: later entries overwrite
         for (auto& kv : cov.exon_cvs) exon_cov[kv.first] = kv.second;
         std::ofstream cv_report(base + ".exon_cv.tsv");
-        cv_report << "Exon ID\tExon CV" << '\n';
+        cv_report << "Exon ID\tExon CV";
+        if (fasta) cv_report << "\tGC Content";
+        cv_report << '\n';
         std::vector<double> total_exon_cv;
         for (auto& kv : exon_cov) {
-            cv_report << kv.first << "\t" << kv.second << '\n';
+            cv_report << kv.first << "\t" << kv.second;
+            if (fasta) {
+                // gc(getSeq(chromosome, start, start + length)) with the 1-based GTF start used as a 0-based offset (src/Metrics.cpp:299-302)
+                const uint32_t s = slot_of[kv.first];
+                const double g = ref->present.size() > A.exon_contig[s] && ref->present[A.exon_contig[s]]
+                                     ? ref->gc_content(A.exon_contig[s], A.exon_start[s], A.exon_start[s] + A.exon_len[s]) : -1.0;
+                cv_report << "\t" << g;
+            }
+            cv_report << '\n';
             total_exon_cv.push_back(kv.second);
         }
         Stats cs = get_statistics(total_exon_cv);
         output << "Median Exon CV\t" << cs.med << '\n';
         output << "Exon CV MAD\t" << cs.mad << '\n';
+    }
+    if (ref && ref->open) {                                                          // src/RNASeQC.cpp:660-674
+        std::ofstream gc_report(base + ".gc_content.tsv");
+        gc_report << "Content Bin\tCount" << '\n';
+        // getAdvancedStatistics over the bins expanded in ascending order (src/Metrics.h:188-206)
+        double avg = 0.0, m2 = 0.0, m3 = 0.0, m4 = 0.0, count = 0.0;
+        for (unsigned i = 0; i < 100; ++i) {
+            gc_report << (double)i / 100.0 << "\t" << R.gc_hist[i] << '\n';
+            for (uint64_t j = 0; j < R.gc_hist[i]; ++j) {
+                const double prev_count = count++;
+                const double delta = (double)i - avg;
+                const double delta_n = delta / count;
+                const double delta_n2 = delta_n * delta_n;
+                const double t = delta * delta_n * prev_count;
+                avg += delta_n;
+                m4 += t * delta_n2 * (count * count - 3 * count + 3) + 6 * delta_n2 * m2 - 4 * delta_n * m3;
+                m3 += t * delta_n * (count - 2) - 3 * delta_n * m2;
+                m2 += t;
+            }
+        }
+        double s_avg = NAN, s_skew = NAN, s_std = NAN, s_kurt = NAN;
+        if (count > 0) {
+            s_std = std::pow(m2 / count, 0.5);
+            s_avg = avg; s_skew = m3 / count / std::pow(s_std, 3.0); s_kurt = (count * m4) / (m2 * m2) - 3;
+        }
+        output << "Fragment GC Content Mean\t" << s_avg / 100.0 << '\n';
+        output << "Fragment GC Content Std\t" << s_std / 100.0 << '\n';
+        output << "Fragment GC Content Skewness\t" << s_skew << '\n';
+        output << "Fragment GC Content Kurtosis\t" << s_kurt << '\n';
     }
     output.close();
 }

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "annotation.h"
+#include "fasta.h"
 #include "rsq_b200.h"
 
 namespace rsqh {
@@ -42,6 +43,7 @@ struct HostResults {
     std::vector<uint32_t> coverage;       // per base, laid out by Annotation::exon_cov_off
     std::vector<uint64_t> fragment_hist;  // index = |isize|
     uint64_t fragment_samples_taken = 0;
+    uint64_t gc_hist[100] = {0};          // gcBins (src/RNASeQC.cpp:106,368)
     // per-gene coverage statistics computed on the device (rsq_coverage_statistics), indexed by GeneFeature::flat;
     // when present the per-base coverage array is not needed on the host at all
     bool have_cov_stats = false;
@@ -62,8 +64,10 @@ struct CoverageSummary {
 void compute_coverage_summary(const Annotation& A, const HostResults& R, const RunOptions& opt,
                               const StreamState& st, CoverageSummary& out);
 
-// Writes every output file the reference writes for a non-legacy, no-FASTA run.  Throws HostError with the
-// reference's exit codes.
-void write_reports(const Annotation& A, const HostResults& R, const RunOptions& opt, const StreamState& st);
+// Writes every output file the reference writes.  `ref` (may be null) is the --fasta reference: adds the GC column of
+// exon_cv.tsv, gc_content.tsv and the four fragment-GC rows of metrics.tsv (src/RNASeQC.cpp:632-640,660-674).  Throws
+// HostError with the reference's exit codes.
+void write_reports(const Annotation& A, const HostResults& R, const RunOptions& opt, const StreamState& st,
+                   const ReferenceModel* ref = nullptr);
 
 }  // namespace rsqh

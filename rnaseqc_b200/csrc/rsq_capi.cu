@@ -29,7 +29,12 @@ struct Ctx {
     uint64_t cov_len = 0;
     AnnView ann{};
     BedView bed{};
-    std::vector<void*> ann_allocs, bed_allocs;
+    std::vector<void*> ann_allocs, bed_allocs, ref_allocs;
+    bool have_ref = false;
+    RefView ref{};
+    const uint8_t* d_ref_present = nullptr;
+    unsigned long long gc_cap = 0;
+    size_t gc_cand_cap = 0;
     // accumulators
     Accum acc{};
     unsigned int* d_cov = nullptr;            // integrated coverage (finalize)
@@ -115,6 +120,11 @@ int zero_accumulators(Ctx* c) {
         CU_TRY(cudaMemsetAsync(a.pair_first, 0xff, 8ull * c->pair_cap, c->stream));
         CU_TRY(cudaMemsetAsync(a.sample_count, 0, 8, c->stream));
     }
+    if (c->have_ref) {
+        CU_TRY(cudaMemsetAsync(a.gc_keys, 0, 8ull * c->gc_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.gc_first, 0xff, 8ull * c->gc_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.gc_hist, 0, 8 * 100, c->stream));
+    }
     c->records_submitted = 0;
     c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
@@ -190,8 +200,41 @@ int ensure_pair_capacity(Ctx* c, size_t n) {
     return RSQ_OK;
 }
 
+// same for the GC-content mate map (--fasta) and its per-batch candidate list
+int ensure_gc_capacity(Ctx* c, size_t n) {
+    if (!c->have_ref || c->cfg.legacy) return RSQ_OK;
+    const size_t need_cand = std::min(n, kSubBatch);
+    if (need_cand > c->gc_cand_cap) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->acc.gc_cand);
+        c->gc_cand_cap = need_cand;
+        CU_TRY(cudaMalloc(&c->acc.gc_cand, sizeof(GcCandidate) * need_cand));
+        c->acc.gc_cand_capacity = (unsigned int)need_cand;
+    }
+    const unsigned long long need = c->records_submitted + n;
+    if (need <= c->gc_cap / 4 * 3) return RSQ_OK;
+    const unsigned long long new_cap = next_pow2(need / 3 * 4 + 4);
+    unsigned long long *nk = nullptr, *nf = nullptr, *np = nullptr;
+    CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
+    CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
+    CU_TRY(cudaMalloc(&np, 8ull * new_cap));
+    CU_TRY(cudaMemsetAsync(nk, 0, 8ull * new_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(nf, 0xff, 8ull * new_cap, c->stream));
+    Accum as_pair = c->acc;             // the rehash kernel reads the table through the pair_* fields
+    as_pair.pair_keys = c->acc.gc_keys; as_pair.pair_first = c->acc.gc_first; as_pair.pair_payload = c->acc.gc_payload;
+    c->launches += launch_pair_rehash(as_pair, c->gc_cap, nk, nf, np, new_cap - 1, c->acc.error_flag, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->acc.gc_keys); cudaFree(c->acc.gc_first); cudaFree(c->acc.gc_payload);
+    c->acc.gc_keys = nk; c->acc.gc_first = nf; c->acc.gc_payload = np;
+    c->acc.gc_mask = new_cap - 1;
+    c->gc_cap = new_cap;
+    return RSQ_OK;
+}
+
 int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks, size_t n_blocks) {
     int rc = ensure_pair_capacity(c, n_reads);
+    if (rc != RSQ_OK) return rc;
+    rc = ensure_gc_capacity(c, n_reads);
     if (rc != RSQ_OK) return rc;
     rc = ensure_bed_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
@@ -207,6 +250,8 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     prm.bed_enabled = (c->have_bed && c->cfg.fragment_samples) ? 1u : 0u;
     prm.fragment_samples = c->cfg.fragment_samples;
     prm.legacy = c->cfg.legacy;
+    prm.gc_enabled = (c->have_ref && !c->cfg.legacy) ? 1u : 0u;
+    prm.ref_present = c->d_ref_present;
     prm.cov_len_diag = c->cov_len + 1;
     // timing events around the kernels of this batch
     if (c->timers_used == c->timers.size()) {
@@ -236,8 +281,10 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
             CU_TRY(cudaMemsetAsync(c->acc.cand_count, 0, 4, c->stream));
             CU_TRY(cudaMemsetAsync(c->acc.sample_flag, 0, n, c->stream));
         }
+        if (prm.gc_enabled) CU_TRY(cudaMemsetAsync(c->acc.gc_cand_count, 0, 4, c->stream));
         c->launches += launch_hot_path(d_reads + base, d_blocks, n, n_blocks, c->ann, c->bed, c->acc, prm, c->stream);
         if (prm.bed_enabled) c->launches += launch_pair_stages(n, c->acc, prm, c->d_pair_scratch, c->stream);
+        if (prm.gc_enabled) c->launches += launch_gc_stages(n, c->ref, c->acc, prm, c->stream);
     }
     CU_TRY(cudaEventRecord(tm.second, c->stream));
     CU_TRY(cudaGetLastError());
@@ -295,8 +342,9 @@ void rsq_destroy(rsq_ctx* ctx) {
     cudaDeviceSynchronize();
     free_list(c->ann_allocs);
     free_list(c->bed_allocs);
+    free_list(c->ref_allocs);
     Accum& a = c->acc;
-    void* ptrs[] = {a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
+    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_ends, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1]};
@@ -419,12 +467,44 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     acc.frag_mask = c->frag_cap - 1;
     CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
     CU_TRY(cudaMalloc(&acc.error_flag, 4));
-    c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * c->n_exons;
+    c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * c->n_exons + 100ull;   // ... | 100 GC-content bins
     CU_TRY(cudaMalloc(&c->d_export, 8ull * c->export_words));
     c->have_ann = true;
     rc = zero_accumulators(c);
     if (rc != RSQ_OK) return rc;
     CU_TRY(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+    return RSQ_OK;
+}
+
+int rsq_set_reference(rsq_ctx* ctx, const rsq_reference* r) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !r || r->struct_size != sizeof(rsq_reference)) return RSQ_ERR_INVALID;
+    if (!c->have_ann) { c->err = "set the annotation first"; return RSQ_ERR_INVALID; }
+    if (c->have_ref) { c->err = "reference already set"; return RSQ_ERR_INVALID; }
+    if (c->records_submitted) { c->err = "set the reference before the first submit"; return RSQ_ERR_INVALID; }
+    if (r->n_contigs != c->n_contigs) { c->err = "reference and annotation contig spaces differ"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    int rc;
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+    if ((rc = upload(c, c->ref_allocs, r->present, (size_t)r->n_contigs, &c->ref.present))) return rc;
+    if ((rc = upload(c, c->ref_allocs, reinterpret_cast<const unsigned long long*>(r->length), (size_t)r->n_contigs, &c->ref.length))) return rc;
+    if ((rc = upload(c, c->ref_allocs, reinterpret_cast<const unsigned long long*>(r->word_off), (size_t)r->n_contigs + 1, &c->ref.word_off))) return rc;
+    if ((rc = upload(c, c->ref_allocs, r->gc_bits, (size_t)r->word_off[r->n_contigs], &c->ref.bits))) return rc;
+    c->d_ref_present = c->ref.present;
+    Accum& acc = c->acc;
+    c->gc_cap = next_pow2((c->cfg.max_records ? c->cfg.max_records : (1ull << 24)) / 3 * 4 + 4);
+    CU_TRY(cudaMalloc(&acc.gc_keys, 8ull * c->gc_cap));
+    CU_TRY(cudaMalloc(&acc.gc_first, 8ull * c->gc_cap));
+    CU_TRY(cudaMalloc(&acc.gc_payload, 8ull * c->gc_cap));
+    acc.gc_mask = c->gc_cap - 1;
+    CU_TRY(cudaMalloc(&acc.gc_cand_count, 4));
+    CU_TRY(cudaMalloc(&acc.gc_hist, 8 * 100));
+    CU_TRY(cudaMemsetAsync(acc.gc_keys, 0, 8ull * c->gc_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(acc.gc_first, 0xff, 8ull * c->gc_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(acc.gc_hist, 0, 8 * 100, c->stream));
+    CU_TRY(cudaMemsetAsync(acc.gc_cand_count, 0, 4, c->stream));
+    c->have_ref = true;
+    CU_TRY(cudaStreamSynchronize(c->stream));
     return RSQ_OK;
 }
 
@@ -550,6 +630,10 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
         } else memset(out->coverage, 0, 4ull * c->cov_len);
     }
     out->fragment_samples_taken = 0;
+    if (out->gc_hist) {
+        memset(out->gc_hist, 0, 8 * 100);
+        if (c->have_ref) CU_TRY(cudaMemcpyAsync(out->gc_hist, c->acc.gc_hist, 8 * 100, cudaMemcpyDeviceToHost, st));
+    }
     if (out->fragment_hist && out->fragment_hist_len) {
         memset(out->fragment_hist, 0, 8 * out->fragment_hist_len);
         if (c->have_bed && c->cfg.fragment_samples) {

@@ -59,6 +59,27 @@ struct __align__(16) PairCandidate {
     uint32_t slot;         // table slot, filled by the hot kernel
 };
 
+// One read that entered the fragment GC-content mate map (src/Expression.cpp:459-467), emitted by the hot kernel.
+struct __align__(16) GcCandidate {
+    unsigned long long name_hash;
+    uint32_t local_idx;    // record index inside the batch
+    uint32_t exon_slot;    // the single exon every block aligned to (alignedExons, :319,348)
+    int32_t  endpos;
+    int32_t  l_qseq;
+    int32_t  contig;
+    uint32_t cond_ok;      // Position() != MatePosition() (:471, minus the end test)
+    uint32_t slot;         // table slot
+    uint32_t pad;
+};
+
+// Reference genome as G/C bits (rsq_reference).
+struct RefView {
+    const uint8_t*  present;     // [n_contigs]
+    const unsigned long long* length;
+    const unsigned long long* word_off;
+    const uint32_t* bits;
+};
+
 // Mutable accumulators in HBM.
 struct Accum {
     unsigned long long* counters;        // [RSQ_N_COUNTERS]
@@ -86,6 +107,15 @@ struct Accum {
     unsigned int*       sample_isize;    // [batch capacity]
     unsigned int*       sample_vals;     // [fragment_samples] |isize| of the k-th sample in stream order
     unsigned long long* sample_count;    // [1] samples found so far (may exceed fragment_samples)
+    // fragment GC-content sampler (--fasta): same mate-map scheme as the BED sampler, its own tables (gcContentFragmentTracker)
+    unsigned long long* gc_keys;
+    unsigned long long* gc_first;
+    unsigned long long* gc_payload;      // (exon slot << 32) | (uint32)endpos of the first candidate
+    unsigned long long  gc_mask;
+    GcCandidate*        gc_cand;
+    unsigned int*       gc_cand_count;   // [1]
+    unsigned int        gc_cand_capacity;
+    unsigned long long* gc_hist;         // [100] gcBins
 };
 
 struct Params {
@@ -95,6 +125,8 @@ struct Params {
     uint32_t bed_enabled;
     uint32_t fragment_samples;
     uint32_t legacy;                     // --legacy counting rules (rsq_legacy.cuh)
+    uint32_t gc_enabled;                 // fragment GC-content sampler (rsq_set_reference)
+    const uint8_t* ref_present;          // [n_contigs] Fasta::hasContig (gc_enabled only)
     unsigned long long record_base;      // global index of reads[0] in the stream (ordering of fragment samples)
     unsigned long long cov_len_diag;     // coverage array length (RSQ_AB_SCATTER diagnostic build only)
 };
@@ -102,6 +134,7 @@ struct Params {
 // launchers (rsq_kernels.cu); every launcher returns the number of kernels it launched
 int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann,
                     const BedView& bed, const Accum& acc, const Params& prm, cudaStream_t stream);
+int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream);
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
 int launch_build_buckets(const AnnView& ann, int4* buckets, uint32_t n_buckets, cudaStream_t stream);
 int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,

@@ -187,7 +187,7 @@ __device__ __forceinline__ bool block_has_gene(const ExonArrays a, const BlockVi
 namespace rsqd {
 namespace {
 
-template <bool kBed, bool kLegacy>
+template <bool kBed, bool kLegacy, bool kGc>
 __global__ void __launch_bounds__(kHotThreads, RSQ_HOT_MIN_BLOCKS)
 hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict__ blocks, size_t n_reads, size_t n_blocks,
                 const AnnView ann, const BedView bed, const Accum acc, const Params prm) {
@@ -585,6 +585,44 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                 else { if (sense) CNT(RSQ_C_END2_SENSE); else CNT(RSQ_C_END2_ANTISENSE); }
             }
 
+            // ---- fragment GC content candidate, Expression.cpp:459-467 --------------------------------------------------
+            if constexpr (kGc) {
+                const unsigned aisz = (unsigned)(isize < 0 ? -(long long)isize : (long long)isize);
+                if (hq && exonic && do_exon && nb == 1 && aisz > 100u && aisz < 1000u && !cleared && __ldg(&prm.ref_present[contig])) {
+                    // alignedExons (:319,348): exons of any gene that fully contain the block, read strand respected
+                    const ExonArrays a0 = arrays_of(v0);
+                    int n_full = 0;
+                    uint32_t the_slot = 0;
+                    for (int e0 = v0.lo; e0 < v0.hi; ++e0) {
+                        const int2 x0 = a0.se[e0];
+                        if (!(x0.x <= bs0 && be0 - 1 <= x0.y)) continue;
+                        const ExonMeta m0 = a0.meta[e0];
+                        if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != (int)((m0.gene_flags >> 24) & RSQ_EXON_STRAND_MASK)) continue;
+                        ++n_full; the_slot = m0.slot;
+                    }
+                    if (n_full == 1) {
+                        const unsigned long long key = name_hash ? name_hash : 1ull;
+                        unsigned long long slot = mix64(key) & acc.gc_mask;
+                        bool placed = false;
+                        for (int probe = 0; probe < 4096 && !placed; ++probe) {
+                            unsigned long long cur = acc.gc_keys[slot];
+                            if (cur == 0ull) cur = atomicCAS(&acc.gc_keys[slot], 0ull, key);
+                            if (cur == 0ull || cur == key) placed = true; else slot = (slot + 1) & acc.gc_mask;
+                        }
+                        if (!placed) atomicOr(acc.error_flag, 2u);
+                        else {
+                            atomicMin(&acc.gc_first[slot], prm.record_base + i);
+                            const unsigned int ci = atomicAdd(acc.gc_cand_count, 1u);
+                            if (ci < acc.gc_cand_capacity) {
+                                GcCandidate c;
+                                c.name_hash = key; c.local_idx = (uint32_t)i; c.exon_slot = the_slot; c.endpos = endpos; c.l_qseq = l_qseq;
+                                c.contig = contig; c.cond_ok = pos != mpos ? 1u : 0u; c.slot = (uint32_t)slot; c.pad = 0u;
+                                acc.gc_cand[ci] = c;
+                            } else atomicOr(acc.error_flag, 4u);
+                        }
+                    }
+                }
+            }
             }  // !kLegacy
 
             // ---- fragmentSizeMetrics candidate, RNASeQC.cpp:372 + Expression.cpp:482-516 ----------------------------
@@ -846,7 +884,7 @@ __global__ void rehash_kernel(const unsigned long long* __restrict__ old_tab, un
 // ---- count vector export for the NVLink all-reduce: counters | gene_reads | gene_unique | gene_fragments | exon_whole |
 //      exon_frac >> 32 | exon_frac & 0xffffffff   (the split keeps the u64 sum exact across ranks)
 __global__ void pack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* __restrict__ out) {
-    const unsigned long long total = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons;
+    const unsigned long long total = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long j = i, v;
         if (j < RSQ_N_COUNTERS) v = acc.counters[j];
@@ -855,12 +893,13 @@ __global__ void pack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n
         else if ((j -= n_genes) < n_genes) v = acc.gene_fragments[j];
         else if ((j -= n_genes) < n_exons) v = acc.exon_whole[j];
         else if ((j -= n_exons) < n_exons) v = acc.exon_fhi[j];
-        else { j -= n_exons; v = acc.exon_flo[j]; }
+        else if ((j -= n_exons) < n_exons) v = acc.exon_flo[j];
+        else { j -= n_exons; v = acc.gc_hist ? acc.gc_hist[j] : 0ull; }      // 100 GC-content bins (zeros without a reference)
         out[i] = v;
     }
 }
 __global__ void unpack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* __restrict__ in) {
-    const unsigned long long total = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons;
+    const unsigned long long total = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long j = i;
         if (j < RSQ_N_COUNTERS) acc.counters[j] = in[i];
@@ -869,7 +908,8 @@ __global__ void unpack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t
         else if ((j -= n_genes) < n_genes) acc.gene_fragments[j] = in[i];
         else if ((j -= n_genes) < n_exons) acc.exon_whole[j] = in[i];
         else if ((j -= n_exons) < n_exons) acc.exon_fhi[j] = in[i];
-        else { j -= n_exons; acc.exon_flo[j] = in[i]; }
+        else if ((j -= n_exons) < n_exons) acc.exon_flo[j] = in[i];
+        else { j -= n_exons; if (acc.gc_hist) acc.gc_hist[j] = in[i]; }
     }
 }
 // (whole, frac>>32 sums, frac&0xffffffff sums) -> canonical (whole, frac) with carries resolved
@@ -956,6 +996,50 @@ __global__ void sample_hist_kernel(const unsigned int* __restrict__ vals, unsign
     }
 }
 
+
+// ---- fragment GC content (--fasta) -----------------------------------------------------------------------------------------------
+// owner: the earliest candidate of a read name publishes (exon, PositionEnd)   (Expression.cpp:462-466)
+__global__ void gc_owner_kernel(const Accum acc, const Params prm) {
+    const unsigned int n = min(*acc.gc_cand_count, acc.gc_cand_capacity);
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const GcCandidate c = acc.gc_cand[k];
+    if (acc.gc_first[c.slot] == prm.record_base + c.local_idx)
+        acc.gc_payload[c.slot] = ((unsigned long long)c.exon_slot << 32) | (unsigned long long)(uint32_t)c.endpos;
+}
+// second: a later candidate on the same exon samples gc(getSeq(chr, stored end - Length(), PositionEnd()))   (:467-476)
+__global__ void gc_check_kernel(const Accum acc, const Params prm, const RefView ref) {
+    const unsigned int n = min(*acc.gc_cand_count, acc.gc_cand_capacity);
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const GcCandidate c = acc.gc_cand[k];
+    if (acc.gc_first[c.slot] >= prm.record_base + c.local_idx) return;
+    const unsigned long long p = acc.gc_payload[c.slot];
+    if ((uint32_t)(p >> 32) != c.exon_slot) return;
+    const int stored_end = (int32_t)(uint32_t)p;
+    if (!c.cond_ok || c.endpos <= stored_end) return;                      // :471
+    // 0-based, end-exclusive window, clipped to the contig (Fasta.cpp:116-150, bioio.hpp:300-309)
+    const long long len = (long long)ref.length[c.contig];
+    const long long start = (long long)stored_end - c.l_qseq;
+    if (start < 0 || start >= len) return;
+    const long long stop = min((long long)c.endpos, len);
+    if (stop <= start) return;
+    const uint32_t* w = ref.bits + ref.word_off[c.contig];
+    int gcs = 0;
+    for (long long wi = start >> 5; wi <= (stop - 1) >> 5; ++wi) {
+        uint32_t m = __ldg(&w[wi]);
+        if (wi == (start >> 5)) m &= 0xffffffffu << (start & 31);
+        if (wi == ((stop - 1) >> 5) && (stop & 31)) m &= 0xffffffffu >> (32 - (int)(stop & 31));
+        gcs += __popc(m);
+    }
+    // gc() adds 1.0/size once per G/C base (Fasta.cpp:66-75): the same sequence of double additions
+    const double inv = 1.0 / (double)(stop - start);
+    double content = 0.0;
+    for (int t = 0; t < gcs; ++t) content += inv;
+    const unsigned bin = (unsigned)(content * 100.0);                      // RNASeQC.cpp:368
+    if (bin < 100u) atomicAdd(&acc.gc_hist[bin], 1ull);
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------------------------------------------
@@ -963,28 +1047,23 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
                     const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
     // persistent grid: every SM holds exactly as many CTAs as its register file admits
-    static int per_sm[4] = {0, 0, 0, 0}, sms = 0;
-    const int which = (prm.bed_enabled ? 1 : 0) | (prm.legacy ? 2 : 0);
+    static int per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sms = 0;
+    const int which = (prm.bed_enabled ? 1 : 0) | (prm.legacy ? 2 : 0) | ((prm.gc_enabled && !prm.legacy) ? 4 : 0);
+    using Kernel = void (*)(const rsq_read*, const rsq_block*, size_t, size_t, const AnnView, const BedView, const Accum, const Params);
+    static const Kernel kernels[8] = {hot_path_kernel<false, false, false>, hot_path_kernel<true, false, false>,
+                                      hot_path_kernel<false, true, false>,  hot_path_kernel<true, true, false>,
+                                      hot_path_kernel<false, false, true>,  hot_path_kernel<true, false, true>,
+                                      nullptr, nullptr};
     if (!per_sm[which]) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        switch (which) {
-            case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], hot_path_kernel<false, false>, kHotThreads, 0); break;
-            case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], hot_path_kernel<true, false>, kHotThreads, 0); break;
-            case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], hot_path_kernel<false, true>, kHotThreads, 0); break;
-            default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], hot_path_kernel<true, true>, kHotThreads, 0); break;
-        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[which], kernels[which], kHotThreads, 0);
         if (per_sm[which] < 1) per_sm[which] = 1;
     }
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
-    switch (which) {
-        case 0: hot_path_kernel<false, false><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
-        case 1: hot_path_kernel<true, false><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
-        case 2: hot_path_kernel<false, true><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
-        default: hot_path_kernel<true, true><<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm); break;
-    }
+    kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm);
     return 1;
 }
 
@@ -1054,6 +1133,14 @@ int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsi
     sample_rank_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(acc.sample_flag, acc.sample_isize, n_reads, sums, acc, prm);
     sample_commit_kernel<<<1, 32, 0, stream>>>(sums, tiles, last, acc);
     return 7;
+}
+
+int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream) {
+    if (!n_reads) return 0;
+    const unsigned cgrid = (unsigned)((std::min<size_t>(n_reads, acc.gc_cand_capacity) + 255) / 256);
+    gc_owner_kernel<<<cgrid, 256, 0, stream>>>(acc, prm);
+    gc_check_kernel<<<cgrid, 256, 0, stream>>>(acc, prm, ref);
+    return 2;
 }
 
 int launch_sample_histogram(const unsigned int* vals, unsigned long long n, unsigned long long* hist, unsigned long long hist_len, cudaStream_t stream) {

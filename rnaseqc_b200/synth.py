@@ -15,7 +15,7 @@ The record layout is include/rsq_b200.h's rsq_read (48 B) / rsq_block (8 B).
 from __future__ import annotations
 
 import dataclasses
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -178,6 +178,43 @@ def write_bed(ann: SynthAnnotation, path: str, min_len: int = 1000) -> int:
             f.write(f"{ann.contig_names[contig[i]]}\t{s[i] - 1}\t{e[i]}\n")
             n += 1
     return n
+
+
+def write_fasta(ann: SynthAnnotation, path: str, seed: int = 0, line_len: int = 60, contigs: Optional[Sequence[int]] = None,
+                extra: Sequence[Tuple[str, int]] = ()) -> None:
+    """Random genome for the annotation's contigs (+ `extra` (name, length) contigs that no feature uses) and its .fai index.
+    GC content varies along each contig in 2 kb steps; a sprinkle of N and lower-case bases exercises gc()'s character
+    classes.  `contigs` selects which annotation contigs are written (default all), in the given order."""
+    rng = np.random.default_rng(seed)
+    todo = [(ann.contig_names[c], int(ann.contig_lens[c])) for c in (range(len(ann.contig_names)) if contigs is None else contigs)]
+    todo += [(n, int(l)) for n, l in extra]
+    with open(path, "wb") as f, open(path + ".fai", "w") as fai:
+        off = 0
+        for name, length in todo:
+            hdr = f">{name} synthetic\n".encode()
+            f.write(hdr)
+            off += len(hdr)
+            steps = (length + 1999) // 2000
+            gc_frac = np.repeat(rng.uniform(0.25, 0.75, steps), 2000)[:length]
+            u = rng.random(length)
+            is_gc = u < gc_frac
+            pick = rng.random(length) < 0.5
+            seq = np.where(is_gc, np.where(pick, ord("G"), ord("C")), np.where(pick, ord("A"), ord("T"))).astype(np.uint8)
+            seq[rng.random(length) < 0.002] = ord("N")
+            lower = rng.random(length) < 0.05
+            seq[lower] |= 0x20
+            full, rest = divmod(length, line_len)
+            body = bytearray()
+            if full:
+                lines = np.empty((full, line_len + 1), np.uint8)
+                lines[:, :line_len] = seq[:full * line_len].reshape(full, line_len)
+                lines[:, line_len] = 10
+                body += lines.tobytes()
+            if rest:
+                body += seq[full * line_len:].tobytes() + b"\n"
+            f.write(body)
+            fai.write(f"{name}\t{length}\t{off}\t{line_len}\t{line_len + 1}\n")
+            off += len(body)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -37,6 +37,8 @@ KAT_LEGACY_FLAGSETS = {
     "legacy_fr_excl_u": ["--legacy", "--stranded", "fr", "--exclude-chimeric", "-u"],
     "legacy_q255": ["--legacy", "-q", "255", "--base-mismatch", "2", "--coverage"],
 }
+SYNTH_FASTA_FLAGSETS = {"fasta": ["--fasta", "g.fa", "--coverage"], "fasta_rf_bed": ["--fasta", "g.fa", "--stranded", "rf", "--bed", "a.bed"],
+                        "fasta_legacy": ["--fasta", "g.fa", "--legacy"]}
 SYNTH_FLAGSETS = {"coverage_bed": ["--coverage", "--bed", "a.bed"], "legacy": ["--legacy", "--coverage", "--bed", "a.bed"]}
 
 
@@ -62,6 +64,28 @@ def make_synth_small():
     with open(sam, "rb") as fi, gzip.open(sam + ".gz", "wb", compresslevel=9) as fo:
         shutil.copyfileobj(fi, fo)
     os.remove(sam)
+
+
+def make_synth_fasta():
+    """--fasta: fragment GC-content sampler, exon GC column, gc_content.tsv (src/Expression.cpp:459-476, src/RNASeQC.cpp:632-674).
+    The FASTA lists its contigs in another order than the GTF (that order seeds the chromosome ids, src/Fasta.cpp:91-93), lacks
+    chrM and has a contig no feature uses."""
+    from rnaseqc_b200 import synth
+    d = os.path.join(HERE, "synth_fasta")
+    os.makedirs(d, exist_ok=True)
+    ann = synth.make_annotation(seed=51, n_genes=40, contig_names=["chr1", "chr2", "chrM"], contig_lens=[400_000, 250_000, 16569])
+    synth.write_gtf(ann, os.path.join(d, "a.gtf"))
+    synth.write_bed(ann, os.path.join(d, "a.bed"), min_len=400)
+    synth.write_fasta(ann, os.path.join(d, "g.fa"), seed=52, contigs=[1, 0], extra=[("chrUn", 3000)])
+    reads = synth.simulate_reads(ann, 20000, seed=53, dup_frac=0.0)
+    sam = os.path.join(d, "a.sam")
+    synth.write_sam(ann, reads, sam)
+    for name, flags in SYNTH_FASTA_FLAGSETS.items():
+        run_ref("a.gtf", "a.sam", os.path.join("expected", name), flags, d)
+    for f in (sam, os.path.join(d, "g.fa")):
+        with open(f, "rb") as fi, gzip.open(f + ".gz", "wb", compresslevel=9) as fo:
+            shutil.copyfileobj(fi, fo)
+        os.remove(f)
 
 
 GTF_ATTR = 'gene_id "{g}"; transcript_id "{g}"; gene_type "{t}"; gene_name "{n}"; transcript_type "{t}";'
@@ -314,4 +338,5 @@ if __name__ == "__main__":
     make_synth_small()
     make_kat()
     make_kat_legacy()
+    make_synth_fasta()
     print("golden fixtures written under", HERE)

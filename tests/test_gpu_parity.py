@@ -10,7 +10,7 @@ import pytest
 from util import assert_results_equal, compare_outputs, run_cli, unpack_case
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_golden import KAT_FLAGSETS, KAT_LEGACY_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
+from make_golden import KAT_FLAGSETS, KAT_LEGACY_FLAGSETS, SYNTH_FASTA_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -149,7 +149,7 @@ def test_device_resident_submit_and_export_roundtrip(libs, synth_case):
     db = torch.from_numpy(blocks.view(np.int32).reshape(-1, 2)).cuda()
     ctx.submit_device(dr.data_ptr(), len(reads), db.data_ptr(), len(blocks))
     ptr, n = ctx.export_counts()
-    assert n == api.RSQ_N_COUNTERS + 3 * ann.n_genes + 3 * ann.n_exons
+    assert n == api.RSQ_N_COUNTERS + 3 * ann.n_genes + 3 * ann.n_exons + 100
     ctx.import_counts()           # identity round trip through the all-reduce layout
     got = ctx.finalize()
     assert_results_equal(got, want, "device submit + export/import")
@@ -263,3 +263,45 @@ def test_kat_legacy_product_cli_matches_reference(libs, tmp_path, flagset):
     run_cli(libs["cli"], os.path.join(d, "kat.gtf"), os.path.join(d, "kat.sam"), out, *KAT_LEGACY_FLAGSETS[flagset])
     identical = set(compare_outputs(os.path.join(d, "expected", flagset), out))
     assert {"kat.sam.gene_reads.gct", "kat.sam.gene_fragments.gct", "kat.sam.exon_reads.gct"} <= identical, identical
+
+
+# ---- --fasta: fragment GC-content sampler (src/Expression.cpp:459-476) -----------------------------------------------------
+
+@pytest.fixture(scope="module")
+def fasta_case(libs, tmp_path_factory):
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    d = str(tmp_path_factory.mktemp("fasta"))
+    sa = synth.make_annotation(seed=301, n_genes=300, contig_names=["chr1", "chr2", "chr3", "chrM"],
+                               contig_lens=[6_000_000, 4_000_000, 3_000_000, 16569])
+    synth.write_gtf(sa, os.path.join(d, "a.gtf"))
+    synth.write_bed(sa, os.path.join(d, "a.bed"), min_len=400)
+    synth.write_fasta(sa, os.path.join(d, "g.fa"), seed=302, contigs=[2, 0, 1])        # chrM has no sequence
+    ann = api.Annotation(os.path.join(d, "a.gtf"), os.path.join(d, "a.bed"), fasta=os.path.join(d, "g.fa"))
+    sr = synth.simulate_reads(sa, 300000, seed=303)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    return ann, reads, blocks
+
+
+@pytest.mark.parametrize("name,kw,chunks", [("default", dict(), 1), ("bed_rf", dict(fragment_samples=50000, strand_mode=2), 4),
+                                            ("unpaired_small_tables", dict(unpaired=True), 9)])
+def test_cuda_fragment_gc_content_matches_oracle(libs, fasta_case, name, kw, chunks):
+    api = libs["api"]
+    ann, reads, blocks = fasta_case
+    max_records = 1000 if "small_tables" in name else len(reads)          # forces the mate map to grow between batches
+    want, _ = _run(api, libs["oracle"], ann, reads, blocks, api.make_config(max_records=len(reads), **kw))
+    got, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=max_records, **kw), chunks=chunks)
+    assert_results_equal(got, want, name)
+    assert np.array_equal(got.gc_hist, want.gc_hist), (got.gc_hist, want.gc_hist)
+    assert want.gc_hist.sum() > 10000 and (want.gc_hist > 0).sum() > 30
+
+
+@pytest.mark.parametrize("flagset", sorted(SYNTH_FASTA_FLAGSETS))
+def test_synth_fasta_product_cli_matches_reference(libs, tmp_path, flagset):
+    d = unpack_case("synth_fasta", tmp_path)
+    out = os.path.join(d, "out_" + flagset)
+    flags = [os.path.join(d, f) if f in ("a.bed", "g.fa") else f for f in SYNTH_FASTA_FLAGSETS[flagset]]
+    run_cli(libs["cli"], os.path.join(d, "a.gtf"), os.path.join(d, "a.sam"), out, *flags)
+    identical = set(compare_outputs(os.path.join(d, "expected", flagset), out))
+    assert {"a.sam.gene_reads.gct", "a.sam.gene_fragments.gct", "a.sam.gc_content.tsv"} <= identical, identical

@@ -17,6 +17,8 @@ CASES = [
     ("unpaired_excl", 63, ["-u", "--exclude-chimeric", "--coverage", "--coverage-mask", "100"]),
     ("legacy_coverage", 65, ["--legacy", "--coverage"]),
     ("legacy_rf_bed_excl", 66, ["--legacy", "--stranded", "rf", "--bed", "BED", "--exclude-chimeric"]),
+    ("fasta_coverage", 67, ["--fasta", "FASTA", "--coverage"]),
+    ("fasta_fr_bed_legacy", 68, ["--fasta", "FASTA", "--stranded", "fr", "--bed", "BED", "--legacy"]),
     ("loose", 64, ["-q", "3", "--base-mismatch", "3", "--chimeric-distance", "5000", "--detection-threshold", "2", "--gene-length", "150", "--window-size", "60"]),
 ]
 
@@ -31,10 +33,15 @@ def test_oracle_cli_vs_live_reference(libs, tmp_path, name, seed, flags):
     synth.write_bed(sa, bed, min_len=400)
     sr = synth.simulate_reads(sa, 40000, seed=seed + 100, dup_frac=0.0)   # no duplicates: skips the reference's 1e9-step complexity scan
     synth.write_sam(sa, sr, sam)
-    flags = [bed if f == "BED" else f for f in flags]
+    fasta = os.path.join(d, "g.fa")
+    if "FASTA" in flags:
+        synth.write_fasta(sa, fasta, seed=seed, contigs=[2, 0], extra=[("chrUn", 4000)])      # chr2 absent from the FASTA
+    flags = [bed if f == "BED" else fasta if f == "FASTA" else f for f in flags]
     run_cli(REF, gtf, sam, os.path.join(d, "ref"), *flags)
     run_cli(libs["oracle_cli"], gtf, sam, os.path.join(d, "ours"), *flags)
     identical = set(compare_outputs(os.path.join(d, "ref"), os.path.join(d, "ours")))
     # metrics.tsv: every integer row exact and every float row within 1e-6 is already enforced by compare_outputs; byte identity
     # is not required because of the reference's out-of-bounds percentile rows (see util.compare_outputs)
     assert {"a.sam.gene_reads.gct", "a.sam.gene_fragments.gct", "a.sam.exon_reads.gct"} <= identical, identical
+    if "FASTA" in CASES[[c[0] for c in CASES].index(name)][2]:
+        assert "a.sam.gc_content.tsv" in identical, identical
