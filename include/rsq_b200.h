@@ -50,7 +50,9 @@ enum {
     RSQ_AUX_TID_OUT_OF_RANGE = 0x08,  /* ChrID()<0 || >= nChrs: src/RNASeQC.cpp:333                              */
     RSQ_AUX_CONTIG_DROPPED = 0x10,  /* features[chr] already cleared by dropFeatures (src/RNASeQC.cpp:346-349,
                                        src/Expression.cpp:96-103): a BAM that RETURNS to a contig finds nothing */
-    RSQ_AUX_TID_GT_127 = 0x20       /* ChrID() > 127: chimeric under --legacy only (src/RNASeQC.cpp:287)       */
+    RSQ_AUX_TID_GT_127 = 0x20,      /* ChrID() > 127: chimeric under --legacy only (src/RNASeQC.cpp:287)       */
+    RSQ_AUX_IMPLICIT_BLOCK = 0x40   /* rsq_read_packed only: the record's single block is (pos+1, l_qseq) and is
+                                       not in the blocks stream                                                  */
 };
 
 /* One decoded alignment record: 48 bytes, 16-byte aligned.  Replaces the SeqLib::BamRecord accessors the
@@ -83,6 +85,31 @@ typedef struct rsq_block {
     int32_t start;
     int32_t len;
 } rsq_block;
+
+/* Compact wire format of one record for the host->device hop: 32 bytes, and no block entry at all for the common
+ * "one M run as long as the read" case, instead of 48 + 8 per block.  The end-to-end rate of this path is bounded by
+ * PCIe, so bytes per record are what matters there; the device expands packed records into
+ * rsq_read/rsq_block before the hot kernel.  Field meaning as in rsq_read.  Derived on the device:
+ *   endpos    = pos + 1                      when n_blocks == 0   (htslib bam_endpos of a record without reference span)
+ *             = pos + l_qseq                 when RSQ_AUX_IMPLICIT_BLOCK
+ *             = last block start - 1 + len   otherwise
+ *   block_off = running sum of n_blocks in record order
+ * Records that do not fit these rules (l_qseq or NM above 65535, more than 255 blocks, an end position that is not the
+ * end of the last block) cannot be packed: rsq_pack_records refuses the batch and the caller uses rsq_submit. */
+typedef struct rsq_read_packed {
+    int32_t  pos;
+    int32_t  mpos;
+    int32_t  isize;
+    uint16_t flag;
+    uint8_t  mapq;
+    uint8_t  aux;          /* RSQ_AUX_* incl. RSQ_AUX_IMPLICIT_BLOCK                                  */
+    uint64_t name_hash;
+    int16_t  contig;
+    uint16_t l_qseq;
+    uint16_t nm;
+    uint8_t  n_blocks;
+    uint8_t  filter_mask;
+} rsq_read_packed;
 
 /* ---- run constants: the locals of main() the loop captures (src/RNASeQC.cpp:78-100) --------------------- */
 typedef struct rsq_config {
@@ -257,6 +284,9 @@ int rsq_submit(rsq_ctx* ctx, const rsq_read* reads, size_t n_reads, const rsq_bl
 /* Same, for batches that already live in device memory of cfg.device (device pointers). */
 int rsq_submit_device(rsq_ctx* ctx, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks,
                       size_t n_blocks);
+/* Same as rsq_submit for a batch in the compact wire format: `blocks` holds, in record order, the blocks of every
+ * record that does not carry RSQ_AUX_IMPLICIT_BLOCK. */
+int rsq_submit_packed(rsq_ctx* ctx, const rsq_read_packed* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks);
 int rsq_sync(rsq_ctx* ctx);
 
 /* Clears all accumulators (annotation and BED stay): a new sample / a new timed step. */
@@ -321,4 +351,33 @@ int rsq_kernel_time_ms(rsq_ctx* ctx, double* ms);
 #ifdef __cplusplus
 }
 #endif
+
+/* Packs one rsq_submit batch (block_off relative to `blocks`) into the compact wire format.  out_reads: n_reads entries;
+ * out_blocks: room for n_blocks entries; *n_out_blocks receives the number written.  Returns RSQ_OK, or RSQ_ERR_INVALID
+ * when some record cannot be represented (nothing useful is left in the outputs then). */
+static inline int rsq_pack_records(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks,
+                                   rsq_read_packed* out_reads, rsq_block* out_blocks, size_t* n_out_blocks) {
+    size_t w = 0, i, b;
+    for (i = 0; i < n_reads; ++i) {
+        const rsq_read* r = &reads[i];
+        rsq_read_packed* p = &out_reads[i];
+        const rsq_block* rb = blocks + r->block_off;
+        if ((size_t)r->block_off + r->n_blocks > n_blocks) return RSQ_ERR_INVALID;
+        if (r->l_qseq < 0 || r->l_qseq > 65535 || r->nm < 0 || r->nm > 65535 || r->n_blocks > 255 ||
+            (r->aux & RSQ_AUX_IMPLICIT_BLOCK)) return RSQ_ERR_INVALID;
+        p->pos = r->pos; p->mpos = r->mpos; p->isize = r->isize; p->flag = r->flag; p->mapq = r->mapq; p->aux = r->aux;
+        p->name_hash = r->name_hash; p->contig = r->contig; p->l_qseq = (uint16_t)r->l_qseq; p->nm = (uint16_t)r->nm;
+        p->n_blocks = (uint8_t)r->n_blocks; p->filter_mask = r->filter_mask;
+        if (r->n_blocks == 0) {
+            if (r->endpos != r->pos + 1) return RSQ_ERR_INVALID;
+        } else if (r->n_blocks == 1 && rb[0].start == r->pos + 1 && rb[0].len == r->l_qseq && r->endpos == r->pos + r->l_qseq) {
+            p->aux |= RSQ_AUX_IMPLICIT_BLOCK;
+        } else {
+            if (r->endpos != rb[r->n_blocks - 1].start - 1 + rb[r->n_blocks - 1].len) return RSQ_ERR_INVALID;
+            for (b = 0; b < r->n_blocks; ++b) out_blocks[w++] = rb[b];
+        }
+    }
+    *n_out_blocks = w;
+    return RSQ_OK;
+}
 #endif /* RSQ_B200_H */

@@ -38,6 +38,11 @@ READ_DTYPE = np.dtype([
     ("flag", "<u2"), ("mapq", "u1"), ("aux", "u1"), ("contig", "<i2"), ("filter_mask", "u1"), ("reserved0", "u1"),
     ("name_hash", "<u8"), ("block_off", "<u4"), ("n_blocks", "<u2"), ("reserved1", "<u2")])
 BLOCK_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4")])
+# compact wire format (rsq_read_packed, 32 bytes)
+PACKED_DTYPE = np.dtype([
+    ("pos", "<i4"), ("mpos", "<i4"), ("isize", "<i4"), ("flag", "<u2"), ("mapq", "u1"), ("aux", "u1"), ("name_hash", "<u8"),
+    ("contig", "<i2"), ("l_qseq", "<u2"), ("nm", "<u2"), ("n_blocks", "u1"), ("filter_mask", "u1")])
+RSQ_AUX_IMPLICIT_BLOCK = 0x40
 
 
 class RsqConfig(C.Structure):
@@ -106,7 +111,7 @@ class StreamStateC(C.Structure):
 
 
 ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
-               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_device", "rsq_sync",
+               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_packed", "rsq_submit_device", "rsq_sync",
                "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_export_counts", "rsq_import_counts", "rsq_algorithmic_bytes",
                "rsq_launch_count", "rsq_kernel_time_ms"]
 
@@ -131,6 +136,21 @@ def make_config(device: int = 0, mapq: int = 255, mismatches: int = 6, chimeric_
     cfg.user_stream = user_stream
     cfg.legacy = int(legacy)
     return cfg
+
+
+def pack_records(reads: np.ndarray, blocks: np.ndarray, out_reads: Optional[np.ndarray] = None,
+                 out_blocks: Optional[np.ndarray] = None) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+    """rsq_pack_records: one submit batch (block_off relative to `blocks`) -> (packed records, remaining blocks), or None when
+    the batch does not fit the wire format.  out_* may be preallocated (e.g. pinned) arrays of at least the input sizes."""
+    H = host_lib()
+    n, nb = reads.nbytes // 48, blocks.nbytes // 8
+    pr = out_reads if out_reads is not None else np.empty(n, PACKED_DTYPE)
+    pb = out_blocks if out_blocks is not None else np.empty(max(nb, 1), BLOCK_DTYPE)
+    w = C.c_size_t(0)
+    rc = H.rsqh_pack_records(reads.ctypes.data, n, blocks.ctypes.data, nb, pr.ctypes.data, pb.ctypes.data, C.byref(w))
+    if rc != 0:
+        return None
+    return pr[:n], pb[:w.value]
 
 
 class RsqError(RuntimeError):
@@ -197,6 +217,8 @@ class Backend:
         L.rsq_set_bed.argtypes = [C.c_void_p, C.POINTER(RsqBed)]
         L.rsq_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.rsq_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.rsq_submit_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.rsq_set_reference.argtypes = [C.c_void_p, C.POINTER(RsqReference)]
         L.rsq_sync.argtypes = [C.c_void_p]
         L.rsq_reset.argtypes = [C.c_void_p]
         L.rsq_finalize.argtypes = [C.c_void_p, C.POINTER(RsqResults)]
@@ -257,6 +279,14 @@ class Context:
 
     def submit_ptr(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
         self._check(self.be.lib.rsq_submit(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
+
+    def submit_packed(self, reads: np.ndarray, blocks: np.ndarray) -> None:
+        """host arrays in the compact wire format (PACKED_DTYPE + the blocks of the records without an implicit block)"""
+        assert reads.flags["C_CONTIGUOUS"] and blocks.flags["C_CONTIGUOUS"]
+        self._check(self.be.lib.rsq_submit_packed(self.h, reads.ctypes.data, reads.nbytes // 32, blocks.ctypes.data, blocks.nbytes // 8))
+
+    def submit_packed_ptr(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
+        self._check(self.be.lib.rsq_submit_packed(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
 
     def submit_device(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
         self._check(self.be.lib.rsq_submit_device(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
@@ -357,6 +387,7 @@ def host_lib():
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                        C.POINTER(StreamStateC), C.c_char_p, C.c_size_t]
         H.rsqh_free.argtypes = [C.c_void_p]
+        H.rsqh_pack_records.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         H.rsqh_hash_qname.restype = C.c_uint64
         H.rsqh_hash_qname.argtypes = [C.c_char_p, C.c_size_t]
         H.rsqh_write_reports.argtypes = [C.c_void_p, C.POINTER(RsqResults), C.c_void_p, C.POINTER(RunOptionsC),

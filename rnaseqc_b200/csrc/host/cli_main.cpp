@@ -11,7 +11,7 @@ int main(int argc, char** argv) {
     int rc = rsqh::parse_cli(argc, argv, opt);
     if (rc >= 0) return rc;
     rsqh::Backend be{rsq_backend, rsq_create,  rsq_destroy,  rsq_last_error, rsq_set_annotation, rsq_set_bed,
-                     rsq_set_reference, rsq_submit,  rsq_sync,    rsq_finalize, rsq_coverage_statistics, rsq_host_alloc, rsq_host_free};
+                     rsq_set_reference, rsq_submit, rsq_submit_packed,  rsq_sync,    rsq_finalize, rsq_coverage_statistics, rsq_host_alloc, rsq_host_free};
     if (opt.verbosity) std::cout << "hot-path backend: " << be.backend() << std::endl;
     return rsqh::run_sample(be, opt);
 }

@@ -157,6 +157,11 @@ int rsqh_decode_file(void* hv, const char* path, const char* chimeric_tag, const
     }
 }
 void rsqh_free(void* p) { free(p); }
+// rsq_pack_records (include/rsq_b200.h) for the Python binding
+int rsqh_pack_records(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks, rsq_read_packed* out_reads,
+                      rsq_block* out_blocks, size_t* n_out_blocks) {
+    return rsq_pack_records(reads, n_reads, blocks, n_blocks, out_reads, out_blocks, n_out_blocks);
+}
 // worker threads for BAM decode in rsqh_decode_file (0 = sequential reader)
 void rsqh_set_decode_threads(int n) { g_decode_threads = n; }
 // --legacy for the calls that follow: GTF filter (src/RNASeQC.cpp:129-135) and the decoder's loop gates

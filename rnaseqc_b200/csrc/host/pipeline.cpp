@@ -47,6 +47,7 @@ void usage(std::ostream& o) {
          "      -d[threshold], --detection-threshold=[threshold]  Counts on a gene to consider it detected. Default: 5\n"
          "      --batch-records=[N]               Records per device batch (this build). Default: 1048576\n"
          "      --decode-threads=[N]              BAM inflate/convert worker threads (this build); 0 = sequential reader.\n"
+         "      --no-packed-submit                Send 48-byte records instead of the 32-byte wire format (this build)\n"
          "                                        Default: hardware threads, at most 32\n"
          "      --exact-complexity                Literal 1e9-iteration library-complexity scan (this build)\n";
 }
@@ -116,6 +117,7 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
             else if (is("detection-threshold", 'd')) opt.run.detection_threshold = (unsigned)std::stoul(value("detection-threshold", 'd'));
             else if (is("batch-records")) opt.batch_records = std::stoul(value("batch-records", 0));
             else if (is("decode-threads")) opt.decode_threads = std::stoi(value("decode-threads", 0));
+            else if (a == "--no-packed-submit") opt.packed_submit = false;
             else if (is("device")) opt.cfg.device = std::stoi(value("device", 0));
             else if (a == "--exact-complexity") opt.run.exact_complexity_scan = true;
             else if (a.size() > 1 && a[0] == '-') throw ArgError{5, "Flag could not be matched: " + a};
@@ -304,9 +306,18 @@ int run_sample(const Backend& be, CliOptions& opt) {
                     pinned[slot][k] = be.host_alloc(pinned_cap[slot][k]);
                     if (!pinned[slot][k]) throw HostError(10, "Memory allocation failure. Out of memory");
                 }
-            memcpy(pinned[slot][0], reads.data(), reads.size() * sizeof(rsq_read));
-            memcpy(pinned[slot][1], blocks.data(), blocks.size() * sizeof(rsq_block));
-            rc = be.submit(ctx, (const rsq_read*)pinned[slot][0], reads.size(), (const rsq_block*)pinned[slot][1], blocks.size());
+            // the compact wire format (32 B per record, no entry for a whole-read block) when the batch fits its rules; the
+            // packer writes straight into the pinned buffers, so it replaces the staging memcpy
+            size_t n_packed_blocks = 0;
+            if (opt.packed_submit && be.submit_packed &&
+                rsq_pack_records(reads.data(), reads.size(), blocks.data(), blocks.size(), (rsq_read_packed*)pinned[slot][0],
+                                 (rsq_block*)pinned[slot][1], &n_packed_blocks) == RSQ_OK) {
+                rc = be.submit_packed(ctx, (const rsq_read_packed*)pinned[slot][0], reads.size(), (const rsq_block*)pinned[slot][1], n_packed_blocks);
+            } else {
+                memcpy(pinned[slot][0], reads.data(), reads.size() * sizeof(rsq_read));
+                memcpy(pinned[slot][1], blocks.data(), blocks.size() * sizeof(rsq_block));
+                rc = be.submit(ctx, (const rsq_read*)pinned[slot][0], reads.size(), (const rsq_block*)pinned[slot][1], blocks.size());
+            }
             if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_submit failed: ") + be.last_error(ctx));
             slot ^= 1;
             if (opt.verbosity > 1)

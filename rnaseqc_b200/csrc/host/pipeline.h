@@ -24,6 +24,7 @@ struct Backend {
     decltype(&rsq_set_bed) set_bed;
     decltype(&rsq_set_reference) set_reference;
     decltype(&rsq_submit) submit;
+    decltype(&rsq_submit_packed) submit_packed;
     decltype(&rsq_sync) sync;
     decltype(&rsq_finalize) finalize;
     decltype(&rsq_coverage_statistics) coverage_statistics;
@@ -39,6 +40,7 @@ struct CliOptions {
     bool legacy = false;
     std::string fasta;
     size_t batch_records = 1u << 20;
+    bool packed_submit = true;        // send batches in the compact wire format (rsq_read_packed) when they fit it
     int decode_threads = -1;          // -1: hardware threads (<= 32); 0: sequential reader
     int verbosity = 0;
 };

@@ -59,6 +59,12 @@ struct Ctx {
     rsq_read* d_reads[2] = {nullptr, nullptr};
     rsq_block* d_blocks[2] = {nullptr, nullptr};
     size_t cap_reads[2] = {0, 0}, cap_blocks[2] = {0, 0};
+    // rsq_submit_packed: wire-format staging per slot, scan temporaries shared (compute stream only)
+    rsq_read_packed* d_packed[2] = {nullptr, nullptr};
+    rsq_block* d_xblocks[2] = {nullptr, nullptr};
+    size_t cap_packed[2] = {0, 0}, cap_xblocks[2] = {0, 0};
+    unsigned int *d_up_tot = nullptr, *d_up_expl = nullptr, *d_up_scan = nullptr;
+    size_t cap_up = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     bool slot_used[2] = {false, false};
     unsigned slot = 0;
@@ -347,7 +353,8 @@ void rsq_destroy(rsq_ctx* ctx) {
     void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_ends, c->d_hist, c->d_pair_scratch,
-                    c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1]};
+                    c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
+                    c->d_up_tot, c->d_up_expl, c->d_up_scan};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& t : c->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(c->ev_copied[k]); cudaEventDestroy(c->ev_done[k]); }
@@ -589,6 +596,65 @@ int rsq_submit(rsq_ctx* ctx, const rsq_read* reads, size_t n_reads, const rsq_bl
     return RSQ_OK;
 }
 
+int rsq_submit_packed(rsq_ctx* ctx, const rsq_read_packed* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann || (n_reads && !reads) || (n_blocks && !blocks)) return RSQ_ERR_INVALID;
+    if (!n_reads) return RSQ_OK;
+    if (n_reads + n_blocks >= (1ull << 32)) { c->err = "packed batch too large (block offsets are 32-bit)"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const unsigned s = c->slot;
+    c->slot ^= 1u;
+    const size_t total_blocks = n_reads + n_blocks;     // upper bound: every implicit block is materialised on the device
+    if (c->slot_used[s]) {
+        if (n_reads > c->cap_packed[s] || n_blocks > c->cap_xblocks[s] || n_reads > c->cap_reads[s] || total_blocks > c->cap_blocks[s] || n_reads > c->cap_up)
+            CU_TRY(cudaEventSynchronize(c->ev_done[s]));
+        else CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[s], 0));
+    }
+    if (n_reads > c->cap_packed[s]) {
+        cudaFree(c->d_packed[s]);
+        c->cap_packed[s] = n_reads + n_reads / 8;
+        CU_TRY(cudaMalloc(&c->d_packed[s], c->cap_packed[s] * sizeof(rsq_read_packed)));
+    }
+    if (std::max<size_t>(n_blocks, 1) > c->cap_xblocks[s]) {
+        cudaFree(c->d_xblocks[s]);
+        c->cap_xblocks[s] = std::max<size_t>(n_blocks, 1) + n_blocks / 8;
+        CU_TRY(cudaMalloc(&c->d_xblocks[s], c->cap_xblocks[s] * sizeof(rsq_block)));
+    }
+    if (n_reads > c->cap_reads[s]) {
+        cudaFree(c->d_reads[s]);
+        c->cap_reads[s] = n_reads + n_reads / 8;
+        CU_TRY(cudaMalloc(&c->d_reads[s], c->cap_reads[s] * sizeof(rsq_read)));
+    }
+    if (total_blocks > c->cap_blocks[s]) {
+        cudaFree(c->d_blocks[s]);
+        c->cap_blocks[s] = total_blocks + total_blocks / 8;
+        CU_TRY(cudaMalloc(&c->d_blocks[s], c->cap_blocks[s] * sizeof(rsq_block)));
+    }
+    if (n_reads > c->cap_up) {
+        CU_TRY(cudaStreamSynchronize(c->stream));          // the shared scan temporaries may still be in use by the other slot
+        cudaFree(c->d_up_tot); cudaFree(c->d_up_expl); cudaFree(c->d_up_scan);
+        c->cap_up = n_reads + n_reads / 8;
+        CU_TRY(cudaMalloc(&c->d_up_tot, 4 * c->cap_up));
+        CU_TRY(cudaMalloc(&c->d_up_expl, 4 * c->cap_up));
+        CU_TRY(cudaMalloc(&c->d_up_scan, 4 * coverage_scan_scratch_elems(c->cap_up)));
+    }
+    CU_TRY(cudaMemcpyAsync(c->d_packed[s], reads, n_reads * sizeof(rsq_read_packed), cudaMemcpyHostToDevice, c->copy_stream));
+    if (n_blocks) CU_TRY(cudaMemcpyAsync(c->d_xblocks[s], blocks, n_blocks * sizeof(rsq_block), cudaMemcpyHostToDevice, c->copy_stream));
+    CU_TRY(cudaEventRecord(c->ev_copied[s], c->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
+    // expand on the device: per-record block counts -> two inclusive scans -> records + blocks in the hot kernel's layout
+    c->launches += launch_unpack_counts_of(c->d_packed[s], n_reads, c->d_up_tot, c->d_up_expl, c->stream);
+    c->launches += launch_coverage_scan(c->d_up_tot, c->d_up_tot, n_reads, c->d_up_scan, c->stream);
+    c->launches += launch_coverage_scan(c->d_up_expl, c->d_up_expl, n_reads, c->d_up_scan, c->stream);
+    c->launches += launch_unpack_records(c->d_packed[s], n_reads, c->d_xblocks[s], n_blocks, c->d_up_tot, c->d_up_expl, c->d_reads[s], c->d_blocks[s],
+                                         c->acc.error_flag, c->stream);
+    int rc = run_batch(c, c->d_reads[s], n_reads, c->d_blocks[s], total_blocks);
+    if (rc != RSQ_OK) return rc;
+    CU_TRY(cudaEventRecord(c->ev_done[s], c->stream));
+    c->slot_used[s] = true;
+    return RSQ_OK;
+}
+
 int rsq_sync(rsq_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RSQ_ERR_INVALID;
@@ -654,6 +720,7 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
     }
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
+    if (err_flag & 8u) { c->err = "packed batch: blocks stream shorter than the records claim"; return RSQ_ERR_INVALID; }
     if (err_flag) {
         c->err = std::string("device table overflow:") + ((err_flag & 1) ? " fragment-tracker set" : "") +
                  ((err_flag & 2) ? " mate table" : "") + ((err_flag & 4) ? " candidate list" : "") + " (raise rsq_config.max_records)";

@@ -134,6 +134,10 @@ struct Params {
 // launchers (rsq_kernels.cu); every launcher returns the number of kernels it launched
 int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann,
                     const BedView& bed, const Accum& acc, const Params& prm, cudaStream_t stream);
+// compact wire format -> rsq_read / rsq_block (rsq_submit_packed): per-record block counts, then (after two scans) the records
+int launch_unpack_counts_of(const rsq_read_packed* packed, size_t n, unsigned int* tot, unsigned int* expl, cudaStream_t stream);
+int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_block* xblocks, size_t n_xblocks, const unsigned int* incl_tot,
+                          const unsigned int* incl_expl, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream);
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream);
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
 int launch_build_buckets(const AnnView& ann, int4* buckets, uint32_t n_buckets, cudaStream_t stream);

@@ -1040,6 +1040,54 @@ __global__ void gc_check_kernel(const Accum acc, const Params prm, const RefView
     if (bin < 100u) atomicAdd(&acc.gc_hist[bin], 1ull);
 }
 
+
+// ---- compact wire format (rsq_read_packed) -> device layout -------------------------------------------------------------------
+__global__ void unpack_counts_of_kernel(const rsq_read_packed* __restrict__ packed, size_t n, unsigned int* __restrict__ tot, unsigned int* __restrict__ expl) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(packed + i) + 1);     // name_hash | contig,l_qseq | nm,n_blocks,filter
+        const unsigned nb = (q.w >> 16) & 0xffu;
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(packed + i));
+        const bool implicit = (h.w >> 24) & RSQ_AUX_IMPLICIT_BLOCK;
+        tot[i] = nb;
+        expl[i] = implicit ? 0u : nb;
+    }
+}
+__global__ void unpack_records_kernel(const rsq_read_packed* __restrict__ packed, size_t n, const rsq_block* __restrict__ xblocks, size_t n_xblocks,
+                                      const unsigned int* __restrict__ incl_tot, const unsigned int* __restrict__ incl_expl,
+                                      rsq_read* __restrict__ reads, rsq_block* __restrict__ blocks, unsigned int* __restrict__ err) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 h = __ldcs(reinterpret_cast<const uint4*>(packed + i));        // pos | mpos | isize | flag,mapq,aux
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(packed + i) + 1);
+        const int pos = (int)h.x;
+        const unsigned aux = h.w >> 24;
+        const unsigned nb = (q.w >> 16) & 0xffu;
+        const int l_qseq = (int)(q.z >> 16);
+        const bool implicit = aux & RSQ_AUX_IMPLICIT_BLOCK;
+        const unsigned block_off = incl_tot[i] - nb;
+        int endpos = pos + 1;
+        if (implicit) {
+            endpos = pos + l_qseq;
+            blocks[block_off] = rsq_block{pos + 1, l_qseq};
+        } else if (nb) {
+            const size_t src = (size_t)incl_expl[i] - nb;
+            if (src + nb > n_xblocks) { atomicOr(err, 8u); }
+            else {
+                rsq_block last{0, 0};
+                for (unsigned b = 0; b < nb; ++b) { last = xblocks[src + b]; blocks[block_off + b] = last; }
+                endpos = last.start - 1 + last.len;
+            }
+        }
+        int4 o0, o1, o2;
+        o0.x = pos; o0.y = (int)h.y; o0.z = endpos; o0.w = (int)h.z;
+        o1.x = l_qseq; o1.y = (int)(q.w & 0xffffu);                                 // nm
+        o1.z = (int)((h.w & 0x00ffffffu) | ((aux & ~(unsigned)RSQ_AUX_IMPLICIT_BLOCK) << 24));   // flag | mapq << 16 | aux << 24
+        o1.w = (int)((q.z & 0xffffu) | ((q.w >> 24) << 16));                        // contig | filter_mask << 16
+        o2.x = (int)q.x; o2.y = (int)q.y; o2.z = (int)block_off; o2.w = (int)nb;
+        int4* out = reinterpret_cast<int4*>(reads + i);
+        out[0] = o0; out[1] = o1; out[2] = o2;
+    }
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------------------------------------------
@@ -1133,6 +1181,19 @@ int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsi
     sample_rank_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(acc.sample_flag, acc.sample_isize, n_reads, sums, acc, prm);
     sample_commit_kernel<<<1, 32, 0, stream>>>(sums, tiles, last, acc);
     return 7;
+}
+
+int launch_unpack_counts_of(const rsq_read_packed* packed, size_t n, unsigned int* tot, unsigned int* expl, cudaStream_t stream) {
+    if (!n) return 0;
+    unpack_counts_of_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(packed, n, tot, expl);
+    return 1;
+}
+int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_block* xblocks, size_t n_xblocks, const unsigned int* incl_tot,
+                          const unsigned int* incl_expl, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream) {
+    if (!n) return 0;
+    unpack_records_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(packed, n, xblocks, n_xblocks, incl_tot, incl_expl,
+                                                                                                        reads, blocks, error_flag);
+    return 1;
 }
 
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream) {

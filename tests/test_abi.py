@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "rsq_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"static inline .*?\n}\n", "", text, flags=re.S)      # header-only helpers (rsq_pack_records) are not exports
     return sorted(set(re.findall(r"\b(rsq_[a-z_]+)\s*\(", text)))
 
 
@@ -51,3 +52,50 @@ def test_product_does_not_link_the_oracle(libs):
     for f in (libs["product"], libs["cli"], libs["host"]):
         out = subprocess.run(["ldd", f], stdout=subprocess.PIPE, text=True).stdout
         assert "oracle" not in out, out
+
+
+def test_packed_wire_format_roundtrip_through_the_oracle(libs, tmp_path):
+    """rsq_pack_records + rsq_submit_packed (32-byte records, implicit whole-read blocks) give the same results as rsq_submit;
+    batches that break the format's rules are refused."""
+    import numpy as np
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    assert api.PACKED_DTYPE.itemsize == 32
+    sa = synth.make_annotation(seed=5, n_genes=60, contig_names=["chr1", "chr2"], contig_lens=[4_000_000, 2_000_000])
+    gtf = str(tmp_path / "a.gtf")
+    synth.write_gtf(sa, gtf)
+    ann = api.Annotation(gtf)
+    sr = synth.simulate_reads(sa, 30000, seed=6)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    packed = api.pack_records(reads, blocks)
+    assert packed is not None
+    pr, pb = packed
+    implicit = (pr["aux"] & api.RSQ_AUX_IMPLICIT_BLOCK) != 0
+    assert implicit.sum() > len(reads) // 3 and len(pb) == int(reads["n_blocks"][~implicit].sum())
+
+    def run(submit):
+        ctx = api.Backend(libs["oracle"]).create(api.make_config())
+        ctx.set_annotation(ann)
+        submit(ctx)
+        return ctx.finalize()
+
+    want = run(lambda c: c.submit(reads, blocks))
+    half = len(reads) // 2
+
+    def packed_two_calls(c):
+        for lo, hi in ((0, half), (half, len(reads))):
+            r = reads[lo:hi].copy()
+            b0 = int(r["block_off"][0]); b1 = int(r["block_off"][-1]) + int(r["n_blocks"][-1])
+            r["block_off"] -= b0
+            p = api.pack_records(r, blocks[b0:b1].copy())
+            c.submit_packed(np.ascontiguousarray(p[0]), np.ascontiguousarray(p[1]))
+    got = run(packed_two_calls)
+    from util import assert_results_equal
+    assert_results_equal(got, want, "packed vs unpacked")
+    bad = reads.copy()
+    bad["endpos"][7] += 3                      # end position that is not the end of the last block
+    assert api.pack_records(bad, blocks) is None
+    bad = reads.copy()
+    bad["nm"][11] = 70000
+    assert api.pack_records(bad, blocks) is None

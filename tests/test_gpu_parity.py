@@ -305,3 +305,28 @@ def test_synth_fasta_product_cli_matches_reference(libs, tmp_path, flagset):
     run_cli(libs["cli"], os.path.join(d, "a.gtf"), os.path.join(d, "a.sam"), out, *flags)
     identical = set(compare_outputs(os.path.join(d, "expected", flagset), out))
     assert {"a.sam.gene_reads.gct", "a.sam.gene_fragments.gct", "a.sam.gc_content.tsv"} <= identical, identical
+
+
+def test_packed_wire_format_matches_unpacked_submit(libs, synth_case):
+    """rsq_submit_packed: the device expands 32-byte records (implicit whole-read blocks, derived end positions and block
+    offsets) into the hot kernel's layout; results equal the rsq_submit ones bit for bit, also over several submits."""
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    want, want_bytes = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=len(reads), fragment_samples=20000))
+    ctx = api.Backend(libs["product"]).create(api.make_config(max_records=len(reads), fragment_samples=20000))
+    ctx.set_annotation(ann)
+    n, total_wire = len(reads), 0
+    for k in range(5):
+        lo, hi = n * k // 5, n * (k + 1) // 5
+        r = reads[lo:hi].copy()
+        b0 = int(r["block_off"][0]); b1 = int(r["block_off"][-1]) + int(r["n_blocks"][-1])
+        r["block_off"] -= b0
+        p = api.pack_records(r, blocks[b0:b1].copy())
+        assert p is not None
+        ctx.submit_packed(np.ascontiguousarray(p[0]), np.ascontiguousarray(p[1]))
+        total_wire += 32 * len(p[0]) + 8 * len(p[1])
+    got = ctx.finalize()
+    assert_results_equal(got, want, "packed submit")
+    assert ctx.algorithmic_bytes() == want_bytes
+    assert total_wire < 0.75 * (48 * len(reads) + 8 * len(blocks))
+    ctx.close()
