@@ -24,7 +24,7 @@ $(OBJDIR)/host/%.o: rnaseqc_b200/csrc/host/%.cpp $(wildcard rnaseqc_b200/csrc/ho
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
 CU_SRCS := rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_covstats.cu rnaseqc_b200/csrc/rsq_capi.cu
-$(LIBDIR)/librsq_b200.so: $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
+$(LIBDIR)/librsq_b200.so: $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h rnaseqc_b200/csrc/rsq_legacy.cuh include/rsq_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_SRCS) -lcudart 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 
