@@ -15,7 +15,7 @@ HOST_SRCS := annotation.cpp alnreader.cpp bamparallel.cpp fasta.cpp report.cpp p
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
-oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle
+oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so
 ref:
 	$(MAKE) -f oracle/Makefile.ref
 
@@ -24,7 +24,7 @@ $(OBJDIR)/host/%.o: rnaseqc_b200/csrc/host/%.cpp $(wildcard rnaseqc_b200/csrc/ho
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
 CU_SRCS := rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_covstats.cu rnaseqc_b200/csrc/rsq_capi.cu
-$(LIBDIR)/librsq_b200.so: $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h rnaseqc_b200/csrc/rsq_legacy.cuh include/rsq_b200.h
+$(LIBDIR)/librsq_b200.so: $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h rnaseqc_b200/csrc/rsq_legacy.cuh rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h include/rsq_b200.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_SRCS) -lcudart 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; false)
 
@@ -39,6 +39,11 @@ $(BINDIR)/rnaseqc: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(LIBDIR)/librsq_b200.
 $(ODIR)/librsq_oracle.so: oracle/rsq_oracle.cpp include/rsq_b200.h
 	@mkdir -p $(ODIR)
 	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Iinclude -shared -o $@ $<
+
+# test infrastructure: host emulation of the hot kernel's per-record logic + index builder (tests/test_hostcore.py)
+$(ODIR)/libhostcore.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
+	@mkdir -p $(ODIR)
+	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
 
 $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
 	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'

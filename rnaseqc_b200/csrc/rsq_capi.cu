@@ -11,6 +11,7 @@
 
 #include "rsq_b200.h"
 #include "rsq_device.h"
+#include "rsq_eit.h"
 
 namespace {
 
@@ -395,10 +396,6 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     if ((rc = upload(c, c->ann_allocs, a->exon_off, (size_t)a->n_contigs + 1, &v.exon_off))) return rc;
     if ((rc = upload(c, c->ann_allocs, se.data(), se.size(), &v.exon_se))) return rc;
     if ((rc = upload(c, c->ann_allocs, meta.data(), meta.size(), &v.exon_meta))) return rc;
-    if ((rc = upload(c, c->ann_allocs, a->seg_off, (size_t)a->n_contigs + 1, &v.seg_off))) return rc;
-    std::vector<int2> sf((size_t)a->n_segs + 4, make_int2(INT32_MAX, 0));   // padded: bulk copies round up to 16 bytes
-    for (uint32_t i = 0; i < a->n_segs; ++i) sf[i] = make_int2(a->seg_start[i], (int)a->seg_flags[i]);
-    if ((rc = upload(c, c->ann_allocs, sf.data(), sf.size(), &v.seg_sf))) return rc;
     if ((rc = upload(c, c->ann_allocs, a->gene_flags, (size_t)a->n_genes, &v.gene_flags))) return rc;
     int32_t* pmax = nullptr;
     CU_TRY(cudaMalloc(&pmax, std::max<size_t>(a->n_exons, 1) * 4));
@@ -438,22 +435,21 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         }
         c->exon_depth = depth;
     }
-    // direct-address bucket index over each contig's annotated span
-    {
-        std::vector<uint32_t> boff(a->n_contigs + 1, 0);
-        for (uint32_t k = 0; k < a->n_contigs; ++k) {
-            int64_t mx = 0;
-            for (uint32_t i = a->exon_off[k]; i < a->exon_off[k + 1]; ++i) mx = std::max<int64_t>(mx, a->exon_end[i]);
-            for (uint32_t i = a->seg_off[k]; i < a->seg_off[k + 1]; ++i) mx = std::max<int64_t>(mx, a->seg_start[i]);
-            boff[k + 1] = boff[k] + (uint32_t)(mx >> kBucketShift) + 2u;
-        }
-        if ((rc = upload(c, c->ann_allocs, boff.data(), boff.size(), &v.bucket_off))) return rc;
-        int4* buckets = nullptr;
-        CU_TRY(cudaMalloc(&buckets, std::max<size_t>(boff.back(), 1) * sizeof(int4)));
-        c->ann_allocs.push_back(buckets);
-        v.buckets = buckets;
-        CU_TRY(cudaStreamSynchronize(c->stream));   // boff is a local
-        c->launches += launch_build_buckets(v, buckets, boff.back(), c->stream);
+    // elementary-interval index (rsq_eit.h): what the hot path searches instead of the exon list
+    if (!c->cfg.legacy) {
+        EiIndex X;
+        const std::string why = build_ei_index(a, X);
+        if (!why.empty()) { c->err = "annotation cannot be indexed: " + why; return RSQ_ERR_INVALID; }
+        static_assert(sizeof(EiDesc) == sizeof(uint2), "descriptor is read as one 64-bit word");
+        if ((rc = upload(c, c->ann_allocs, X.ei_off.data(), X.ei_off.size(), &v.ei_off))) return rc;
+        if ((rc = upload(c, c->ann_allocs, X.ei_start.data(), X.ei_start.size(), &v.ei_start))) return rc;
+        if ((rc = upload(c, c->ann_allocs, reinterpret_cast<const uint2*>(X.ei_desc.data()), X.ei_desc.size(), &v.ei_desc))) return rc;
+        if ((rc = upload(c, c->ann_allocs, X.cover.data(), X.cover.size(), &v.cover))) return rc;
+        if ((rc = upload(c, c->ann_allocs, X.eib_off.data(), X.eib_off.size(), &v.eib_off))) return rc;
+        if ((rc = upload(c, c->ann_allocs, X.eib.data(), X.eib.size(), &v.eib))) return rc;
+        CU_TRY(cudaStreamSynchronize(c->stream));   // X is a local
+    } else {
+        v.ei_off = nullptr; v.ei_start = nullptr; v.ei_desc = nullptr; v.cover = nullptr; v.eib_off = nullptr; v.eib = nullptr;
     }
     // accumulators
     Accum& acc = c->acc;

@@ -14,21 +14,32 @@ struct __align__(16) ExonMeta {
     uint64_t cov_off;      // first base of this exon in the coverage array
 };
 
-// Annotation resident in HBM (replicated per GPU; <= ~10 MB at GENCODE scale, i.e. L2-resident).
+// ---- elementary-interval index (built by rsq_eit.h, read by rsq_hot_core.cuh) ------------------------------------------
+constexpr int kEiShift = 10;                 // direct-address table: one entry per 1 kb of contig
+constexpr int kEiPad = 512;                  // INT32_MAX entries behind the last interval: bulk copies may run past the end
+// class bits of an elementary interval: (kind << 0) for the forward strand, << 1 reverse, << 2 unknown
+enum : uint32_t { EI_GENE = 0x001, EI_GENE_RIBO = 0x008, EI_EXON = 0x040, EI_EXON_RIBO = 0x200,
+                  EI_ANY_GENE = 0x007, EI_ANY_GENE_RIBO = 0x038, EI_ANY_EXON = 0x1c0, EI_ANY_EXON_RIBO = 0xe00 };
+// CoverEntry::gene_flags, high byte: RSQ_EXON_STRAND_MASK | RSQ_EXON_RIBOSOMAL as in rsq_annotation.exon_flags, plus
+constexpr uint32_t kCoverGlobin = 0x8;       // geneNames[gene] is a blacklisted globin (src/Expression.cpp:24,396-399)
+// One exon covering an elementary interval, with everything the accumulation needs inlined.
+struct __align__(16) CoverEntry {
+    int32_t  start, end;       // the exon (closed)
+    uint32_t gene_flags;       // gene index in the low 24 bits, flags in the high 8
+    uint32_t slot;             // output slot (exonList order)
+    uint64_t cov_off;          // first base of this exon in the coverage array
+    uint64_t exon_index;       // position in rsq_annotation's exon arrays (diagnostics)
+};
+static_assert(sizeof(CoverEntry) == 32, "two 128-bit loads");
+
+// Annotation resident in HBM (replicated per GPU; a few tens of MB at GENCODE scale, i.e. L2-resident).
 struct AnnView {
     uint32_t n_contigs, n_genes, n_exons, n_segs;
     const uint32_t* exon_off;     // [n_contigs+1]
     const int2*     exon_se;      // [n_exons] (start, end), start-sorted per contig
     const int32_t*  exon_pmax;    // [n_exons] running max of end within the contig (monotone)
     const ExonMeta* exon_meta;    // [n_exons]
-    const uint32_t* seg_off;      // [n_contigs+1]
-    const int2*     seg_sf;       // [n_segs] (start, RSQ_SEG_* flags): elementary gene segments, start-sorted per contig
     const uint8_t*  gene_flags;   // [n_genes]
-    // direct-address bucket index: bucket b of contig c covers coordinates [b << kBucketShift, (b+1) << kBucketShift)
-    const uint32_t* bucket_off;   // [n_contigs+1] first bucket of each contig
-    const int4*     buckets;      // per bucket: x = first exon with running-max end >= bucket start,
-                                  //             y = first exon with start >= bucket start,
-                                  //             z = last gene segment with start <= bucket start, w = unused
     // gene lines as intervals in list order (--legacy rules only; null otherwise)
     const uint32_t* gline_off;    // [n_contigs+1]
     const int2*     gline_se;     // [n_gene_lines] (start, end), start-sorted per contig
@@ -36,8 +47,14 @@ struct AnnView {
     const uint32_t* gline_gf;     // [n_gene_lines] gene index of the line's gene_id | (strand, ribosomal) << 24
     const uint32_t* gline_order;  // [n_gene_lines] rank among the kept GTF lines (ties of the list's stable sort)
     const uint32_t* exon_order;   // [n_exons] same for the exon lines
+    // elementary-interval index (rsq_eit.h): what the non-legacy hot path reads
+    const uint32_t*   ei_off;     // [n_contigs+1] first interval of each contig (an INT32_MIN sentinel)
+    const int32_t*    ei_start;   // [n_ei + kEiPad] interval starts, ascending inside a contig
+    const uint2*      ei_desc;    // [n_ei + 1] x = first covering exon in `cover`, y = class bits | count << 16
+    const CoverEntry* cover;      // covering exons, interval-major, list order inside an interval
+    const uint32_t*   eib_off;    // [n_contigs+1] first table entry of each contig (n_buckets + 1 entries per contig)
+    const uint32_t*   eib;        // interval containing each bucket start; a contig's last entry = its last interval
 };
-constexpr int kBucketShift = 10;
 
 struct BedView {
     uint32_t n_intervals;
@@ -140,7 +157,6 @@ int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_blo
                           const unsigned int* incl_expl, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream);
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream);
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
-int launch_build_buckets(const AnnView& ann, int4* buckets, uint32_t n_buckets, cudaStream_t stream);
 int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,
                        unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream);
 int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned long long n, unsigned int* block_sums,

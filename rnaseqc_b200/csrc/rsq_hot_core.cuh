@@ -1,0 +1,362 @@
+// rsq_hot_core.cuh — the per-record logic of the hot path, written once for the device kernel (rsq_kernels.cu) and for
+// the host-side emulation that the CPU tests run against the oracle (tests/hostcore/): the filter cascade of
+// src/RNASeQC.cpp:254-342 and exonAlignmentMetrics of src/Expression.cpp:308-458 over the elementary-interval index
+// (rsq_eit.h).  Everything that needs a warp (staging, aggregation, counters) stays in the kernel; memory side effects go
+// through a `Mem` policy (device: RED/CAS atomics; host emulation: plain adds).
+#pragma once
+#include <stdint.h>
+
+#include "rsq_device.h"
+
+#if defined(__CUDACC__)
+#define RSQ_HD __device__ __forceinline__      // the CUDA build only ever needs the device instantiation
+#else
+#define RSQ_HD inline                          // host emulation (tests/hostcore), plain g++
+#endif
+
+namespace rsqd {
+
+template <class T> RSQ_HD T ldro(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+constexpr uint32_t kNoGene = 0xffffffffu;
+RSQ_HD int imin(int a, int b) { return a < b ? a : b; }
+RSQ_HD int imax(int a, int b) { return a > b ? a : b; }
+
+RSQ_HD unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+// floor(isz * 2^64 / length) for isz <= length (isz == length gives whole = 1).  Schoolbook long division in base 2^16
+// (four 32-bit divides, inlined) for aligned lengths below 65536; the generic 64-bit path only for longer reads.
+RSQ_HD void frac_q64(uint32_t isz, uint32_t length, unsigned long long& whole, unsigned long long& lo) {
+    if (isz >= length) { whole = 1ull; lo = 0ull; return; }
+    whole = 0ull;
+    if (length < 65536u) {
+        uint32_t r = isz, d0, d1, d2, d3;
+        r <<= 16; d3 = r / length; r -= d3 * length;
+        r <<= 16; d2 = r / length; r -= d2 * length;
+        r <<= 16; d1 = r / length; r -= d1 * length;
+        r <<= 16; d0 = r / length;
+        lo = ((unsigned long long)((d3 << 16) | d2) << 32) | (unsigned long long)((d1 << 16) | d0);
+        return;
+    }
+    unsigned long long r = isz;
+    const unsigned long long t1 = (r << 32) / length;
+    r = (r << 32) % length;
+    const unsigned long long t0 = (r << 32) / length;
+    lo = (t1 << 32) | t0;
+}
+
+// Warp-uniform description of the slice of ei_start the warp has staged in shared memory for its current tile.
+struct TileWin {
+    const int32_t* st;   // staged copy of ei_start[base .. ), shared memory on the device
+    int base;            // global interval index of st[0]
+    int k0;              // interval containing the first coordinate served (>= base)
+    int hi;              // one past the last staged interval that may be used (global index)
+    int wmin;            // blocks starting before this coordinate are not served
+    int lastv;           // start of interval hi-1, or INT32_MAX when hi is the end of the contig: blocks must end before it
+    bool on;
+};
+
+// last index in [lo, hi_incl] whose start <= key; starts[lo] <= key is given.  `starts` is indexed by global interval index.
+template <class P>
+RSQ_HD int ei_search(P starts, int lo, int hi_incl, int key) {
+    int len = hi_incl - lo + 1;
+    while (len > 1) {
+        const int half = len >> 1;
+        if (starts[lo + half] <= key) lo += half;
+        len -= half;
+    }
+    return lo;
+}
+
+struct StagedStarts {     // view of the staged slice under global indices
+    const int32_t* st; int base;
+    RSQ_HD int operator[](int k) const { return st[k - base]; }
+};
+struct GlobalStarts {
+    const int32_t* p;
+    RSQ_HD int operator[](int k) const { return ldro(p + k); }
+};
+
+// Interval of a block's start and the OR of the class bits of every interval the closed block [bs, be] touches
+// (intersectBlock + intersectInterval, src/Expression.cpp:106-117, src/GTF.cpp:171-179).  Returns the descriptor of k(bs).
+RSQ_HD uint2 block_lookup(const AnnView& ann, const TileWin& w, int c_hi, int bk_lo, int bk_n, int bs, int be, uint32_t& cls) {
+    uint2 d;
+    if (w.on && bs >= w.wmin && be < w.lastv) {
+        const StagedStarts s{w.st, w.base};
+        const int k = ei_search(s, w.k0, w.hi - 1, bs);
+        d = ldro(ann.ei_desc + k);
+        cls |= d.y & 0xffffu;
+        for (int kk = k + 1; kk < w.hi && s[kk] <= be; ++kk) cls |= ldro(&ann.ei_desc[kk].y) & 0xffffu;
+    } else {
+        const int b = imin(imax(bs, 0) >> kEiShift, bk_n - 1);
+        const int lo = (int)ldro(ann.eib + bk_lo + b), hi = (int)ldro(ann.eib + bk_lo + b + 1);
+        const GlobalStarts s{ann.ei_start};
+        const int k = ei_search(s, lo, hi, bs);
+        d = ldro(ann.ei_desc + k);
+        cls |= d.y & 0xffffu;
+        for (int kk = k + 1; kk < c_hi && s[kk] <= be; ++kk) cls |= ldro(&ann.ei_desc[kk].y) & 0xffffu;
+    }
+    return d;
+}
+
+// What one record contributes outside the exon tables; the kernel aggregates these across the warp.
+struct RecOut {
+    unsigned long long cm;   // bit k set: counter k += 1
+    unsigned vflags;         // bit0: End 1 sums, bit1: End 2 sums, bit2: Mismatched Bases, bit3: Total Bases, bit4: blocks
+    unsigned my_bytes;       // algorithmic bytes of this record
+    uint32_t agg_gene;       // first gene this read counts toward
+    bool agg_unique, agg_frag;
+    int n_fresh;             // new fragment-set entries of this read
+    bool go, hq;
+};
+
+#define RSQ_CNT(o, k) ((o).cm |= 1ull << (k))
+
+// ---- filter cascade, src/RNASeQC.cpp:254-342 ---------------------------------------------------------------------------
+template <bool kLegacy>
+RSQ_HD void filter_cascade(const Params& prm, bool valid, uint32_t f, uint32_t mapq, uint32_t aux, uint32_t filter_mask, int pos, int mpos,
+                           int endpos, int nm_raw, uint32_t nb, RecOut& o) {
+    o.cm = 0ull; o.vflags = 0u; o.my_bytes = 0u; o.agg_gene = kNoGene; o.agg_unique = false; o.agg_frag = false; o.n_fresh = 0;
+    bool go = valid, hq = false;
+    if (valid) {
+        RSQ_CNT(o, RSQ_C_TOTAL_ALIGNMENTS);                                              // RNASeQC.cpp:245
+        o.my_bytes = 40u + 8u * nb;
+        if (f & RSQ_F_SECONDARY) RSQ_CNT(o, RSQ_C_ALTERNATIVE_ALIGNMENTS);               // :254
+        if (f & RSQ_F_SUPPLEMENTARY) RSQ_CNT(o, RSQ_C_SUPPLEMENTARY_ALIGNMENTS);         // :255
+        else if (f & RSQ_F_QCFAIL) RSQ_CNT(o, RSQ_C_FAILED_VENDOR_QC);
+        else if (mapq < prm.mapq_threshold) RSQ_CNT(o, RSQ_C_LOW_MAPPING_QUALITY);
+        const bool has_ch = aux & RSQ_AUX_CHIMERIC_TAG;
+        if ((f & RSQ_F_SUPPLEMENTARY) && !(kLegacy || has_ch)) {                          // :258-262
+            RSQ_CNT(o, RSQ_C_CHIMERIC_AUTO);
+            if (prm.exclude_chimeric) go = false;
+        }
+        if (f & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) go = false;      // :263
+        if (go) {
+            RSQ_CNT(o, RSQ_C_UMVQ);
+            if (!(f & RSQ_F_PAIRED)) RSQ_CNT(o, RSQ_C_UNPAIRED_READS);
+            if (f & RSQ_F_UNMAP) go = false;                                             // :268
+        }
+        if (go) {
+            RSQ_CNT(o, RSQ_C_MAPPED_READS);
+            if (f & RSQ_F_DUP) RSQ_CNT(o, RSQ_C_MAPPED_DUPLICATE_READS); else RSQ_CNT(o, RSQ_C_MAPPED_UNIQUE_READS);
+            if (kLegacy && (unsigned)(endpos - pos) > 100000u) go = false;                // :275-276 LEGACY_MAX_READ_LENGTH
+            if (go && !kLegacy && has_ch) {                                               // :279-283
+                if (f & RSQ_F_READ1) RSQ_CNT(o, RSQ_C_CHIMERIC_TAG);
+                if (prm.exclude_chimeric) go = false;
+            }
+        }
+        if (go && (f & RSQ_F_PAIRED) && !(f & RSQ_F_MUNMAP)) {                            // :284-292
+            if (f & RSQ_F_READ1) RSQ_CNT(o, RSQ_C_TOTAL_MAPPED_PAIRS);
+            int d = pos - mpos; d = d < 0 ? -d : d;
+            if ((aux & RSQ_AUX_MATE_OTHER_CONTIG) || d > prm.chimeric_distance || (kLegacy && (aux & RSQ_AUX_TID_GT_127))) {
+                if (f & RSQ_F_READ1) RSQ_CNT(o, RSQ_C_CHIMERIC_AUTO);
+                if (prm.exclude_chimeric) go = false;
+            }
+        }
+        if (go) {
+            int mismatches = 0;
+            if (aux & RSQ_AUX_HAS_NM) {                                                   // :294-316
+                mismatches = nm_raw;
+                if (f & RSQ_F_PAIRED) {
+                    if (f & RSQ_F_READ1) {
+                        RSQ_CNT(o, RSQ_C_END1_MAPPED_READS);
+                        o.vflags |= 1u;
+                        if (f & RSQ_F_DUP) RSQ_CNT(o, RSQ_C_DUPLICATE_PAIRS); else RSQ_CNT(o, RSQ_C_UNIQUE_FRAGMENTS);
+                    } else {
+                        RSQ_CNT(o, RSQ_C_END2_MAPPED_READS);
+                        o.vflags |= 2u;
+                    }
+                }
+                o.vflags |= 4u;
+            }
+            o.vflags |= 8u;                                                               // :317
+            if (filter_mask) {                                                            // :319-328
+                for (uint32_t k = 0; k < prm.n_filter_tags && k < 8; ++k)
+                    if (filter_mask & (1u << k)) { RSQ_CNT(o, RSQ_C_FILTERED_BY_TAG0 + k); go = false; }
+            }
+            hq = (uint32_t)mismatches <= prm.base_mismatch_threshold && (prm.unpaired || (f & RSQ_F_PROPER)) &&
+                 mapq >= prm.mapq_threshold;                                              // :330
+            if (aux & RSQ_AUX_TID_OUT_OF_RANGE) go = false;                               // :333-337
+        }
+        if (go) {
+            if (hq) RSQ_CNT(o, RSQ_C_HIGH_QUALITY_READS); else RSQ_CNT(o, RSQ_C_LOW_QUALITY_READS);   // :340-342
+            RSQ_CNT(o, RSQ_C_READS_USED);
+            o.vflags |= 16u;                                                              // :360
+        }
+    }
+    o.go = go; o.hq = hq;
+}
+
+// A block and the covering-exon list of the interval its start falls into.
+struct BlockRef { int bs, be; uint32_t coff, cn; };
+
+// first 16 bytes of a CoverEntry
+struct CoverHead { int start, end; uint32_t gene_flags, slot; };
+RSQ_HD CoverHead cover_head(const AnnView& ann, uint32_t j) {
+    const int4 v = ldro(reinterpret_cast<const int4*>(ann.cover) + 2 * (size_t)j);
+    CoverHead h; h.start = v.x; h.end = v.y; h.gene_flags = (uint32_t)v.z; h.slot = (uint32_t)v.w;
+    return h;
+}
+RSQ_HD unsigned long long cover_cov_off(const AnnView& ann, uint32_t j) {
+    return ldro(reinterpret_cast<const unsigned long long*>(ann.cover) + 4 * (size_t)j + 2);
+}
+// does the exon fully contain the block (it covers the block's start by construction) and pass the strand filter?
+// partialIntersect == block length, src/Expression.cpp:341; strand test :331
+RSQ_HD bool cover_admits(const CoverHead& h, const BlockRef& r, int rstrand) {
+    if (h.end < r.be - 1) return false;
+    return rstrand == RSQ_STRAND_UNKNOWN || rstrand == (int)((h.gene_flags >> 24) & RSQ_EXON_STRAND_MASK);
+}
+// is the block inside an exon of `gene` among entries [0, upto) of its covering list?
+RSQ_HD bool ref_has_gene(const AnnView& ann, const BlockRef& r, uint32_t upto, uint32_t gene, int rstrand) {
+    for (uint32_t j = 0; j < upto; ++j) {
+        const CoverHead h = cover_head(ann, r.coff + j);
+        if (cover_admits(h, r, rstrand) && (h.gene_flags & 0xffffffu) == gene) return true;
+    }
+    return false;
+}
+
+struct ExonOut { bool exonic, do_exon; BlockRef r0; };
+
+// ---- exonAlignmentMetrics, src/Expression.cpp:308-458 --------------------------------------------------------------------
+// Mem: add64(ptr, v), add32(ptr, v), frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
+template <class Mem>
+RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const Params& prm, const Accum& acc, uint32_t f, bool hq, bool cleared,
+                         int contig, int rstrand, const rsq_block* bp, uint32_t nb, unsigned long long name_hash, RecOut& o, ExonOut& x) {
+    int c_hi = 0, bk_lo = 0, bk_n = 1;
+    if (!cleared) {
+        c_hi = (int)ldro(ann.ei_off + contig + 1);
+        bk_lo = (int)ldro(ann.eib_off + contig);
+        bk_n = (int)ldro(ann.eib_off + contig + 1) - bk_lo - 1;
+    }
+    auto ref_of = [&](uint32_t b) -> BlockRef {
+        const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
+        BlockRef r; r.bs = blk.x; r.be = blk.x + blk.y;
+        uint32_t dummy = 0;
+        const uint2 d = block_lookup(ann, w, c_hi, bk_lo, bk_n, r.bs, r.be, dummy);
+        r.coff = d.x; r.cn = d.y >> 16;
+        return r;
+    };
+    uint32_t length = 0, cls = 0;                                                          // extractBlocks' return, :359
+    BlockRef r0 = {0, 0, 0u, 0u}, r1 = r0;
+    for (uint32_t b = 0; b < nb; ++b) {                                                    // :325-361
+        const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
+        const int bs = blk.x, be = blk.x + blk.y;                                          // closed end = start+len, :45
+        length += (uint32_t)blk.y;
+        if (cleared) continue;
+        const uint2 d = block_lookup(ann, w, c_hi, bk_lo, bk_n, bs, be, cls);
+        if (b == 0) { r0.bs = bs; r0.be = be; r0.coff = d.x; r0.cn = d.y >> 16; }
+        else if (b == 1) { r1.bs = bs; r1.be = be; r1.coff = d.x; r1.cn = d.y >> 16; }
+    }
+    if (rstrand != RSQ_STRAND_UNKNOWN) cls &= (EI_GENE | EI_GENE_RIBO | EI_EXON | EI_EXON_RIBO) << rstrand;   // :331
+    const bool intragenic = cls & EI_ANY_GENE;                                              // :352-354
+    const bool exonic = cls & EI_ANY_EXON;                                                  // :335-337
+    const bool plus = cls & ((EI_GENE | EI_EXON) << RSQ_STRAND_FWD);                        // :332
+    const bool minus = cls & ((EI_GENE | EI_EXON) << RSQ_STRAND_REV);                       // :333
+    const bool ribosomal = cls & (EI_ANY_GENE_RIBO | EI_ANY_EXON_RIBO);                     // :358
+
+    bool globin = false, do_exon = false;
+    if (nb >= 1 && !cleared) {                                                             // :363-394
+        // `last` = intersection over blocks of {genes with an exon that fully contains the block}: enumerate the genes of
+        // block 0 (deduplicated by re-scanning its short covering list) and test each against every other block.
+        for (uint32_t j = 0; j < r0.cn; ++j) {
+            const CoverHead h0 = cover_head(ann, r0.coff + j);
+            if (!cover_admits(h0, r0, rstrand)) continue;                                  // isz == block length, :341
+            const uint32_t g = h0.gene_flags & 0xffffffu;
+            if (ref_has_gene(ann, r0, j, g, rstrand)) continue;                            // an earlier entry already gave this gene
+            bool in_all = true;
+            for (uint32_t b = 1; b < nb && in_all; ++b) {
+                if (b == 1) in_all = ref_has_gene(ann, r1, r1.cn, g, rstrand);
+                else { const BlockRef r = ref_of(b); in_all = ref_has_gene(ann, r, r.cn, g, rstrand); }
+            }
+            if (!in_all) continue;
+            // g is in `last` (:377)
+            do_exon = true;                                                                // :393
+            if ((h0.gene_flags >> 24) & kCoverGlobin) globin = true;                       // :396-398
+            if (!hq) continue;
+            if (length > 0) {                                                              // queryGene: some coverage > 0, :380
+                const unsigned long long key0 = mix64(name_hash ^ ((unsigned long long)(g + 1u) * 0x9E3779B97F4A7C15ull));
+                const bool fresh = mem.frag_insert(key0 ? key0 : 1ull);                    // :383-387
+                o.n_fresh += fresh ? 1 : 0;
+                if (o.agg_gene == kNoGene) { o.agg_gene = g; o.agg_unique = !(f & RSQ_F_DUP); o.agg_frag = fresh; }
+                else {
+                    mem.add64(&acc.gene_reads[g], 1ull);
+                    if (fresh) mem.add64(&acc.gene_fragments[g], 1ull);
+                    if (!(f & RSQ_F_DUP)) mem.add64(&acc.gene_unique[g], 1ull);
+                }
+                o.my_bytes += 8u;
+            }
+            // Collector::collect + BaseCoverage::commit for gene g: every (block, containing exon of g) pair
+            for (uint32_t b = 0; b < nb; ++b) {
+                const BlockRef r = b == 0 ? r0 : (b == 1 ? r1 : ref_of(b));
+                const uint32_t len = (uint32_t)(r.be - r.bs);
+                if (len == 0) continue;                                                    // Collector::add keeps coverage > 0, Metrics.cpp:51
+                for (uint32_t jj = 0; jj < r.cn; ++jj) {
+                    const CoverHead h = cover_head(ann, r.coff + jj);
+                    if (!cover_admits(h, r, rstrand) || (h.gene_flags & 0xffffffu) != g) continue;
+                    unsigned long long whole, lo;
+                    frac_q64(len, length, whole, lo);                                      // isz/length, :345
+                    // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update is a
+                    // fire-and-forget RED, nothing waits for an atomic's return value
+                    if (whole) mem.add64(&acc.exon_whole[h.slot], whole);
+                    else {
+                        mem.add64(&acc.exon_fhi[h.slot], lo >> 32);
+                        mem.add64(&acc.exon_flo[h.slot], lo & 0xffffffffull);
+                    }
+                    o.my_bytes += 8u;
+                    if (prm.collect_coverage) {                                            // add_range as +1/-1, Metrics.cpp:257-262
+                        const unsigned long long off = cover_cov_off(ann, r.coff + jj) + (unsigned long long)(r.bs - h.start);
+                        mem.add32(&acc.cov_diff[off], 1u);
+                        mem.add32(&acc.cov_diff[off + len], 0xffffffffu);
+                        o.my_bytes += 8u;
+                    }
+                }
+            }
+        }
+    }
+    if (nb >= 1 && !globin) {                                                              // :399-404
+        RSQ_CNT(o, RSQ_C_NON_GLOBIN_READS);
+        if (f & RSQ_F_DUP) RSQ_CNT(o, RSQ_C_NON_GLOBIN_DUPLICATE_READS);
+    }
+    if (!exonic) {                                                                         // :407-423
+        if (intragenic) {
+            RSQ_CNT(o, RSQ_C_INTRONIC_READS); RSQ_CNT(o, RSQ_C_INTRAGENIC_READS);
+            if (hq) { RSQ_CNT(o, RSQ_C_HQ_INTRONIC_READS); RSQ_CNT(o, RSQ_C_HQ_INTRAGENIC_READS); }
+        } else {
+            RSQ_CNT(o, RSQ_C_INTERGENIC_READS);
+            if (hq) RSQ_CNT(o, RSQ_C_HQ_INTERGENIC_READS);
+        }
+    } else if (do_exon) {                                                                  // :424-433
+        RSQ_CNT(o, RSQ_C_EXONIC_READS); RSQ_CNT(o, RSQ_C_INTRAGENIC_READS);
+        if (hq) { RSQ_CNT(o, RSQ_C_HQ_EXONIC_READS); RSQ_CNT(o, RSQ_C_HQ_INTRAGENIC_READS); }
+    } else {                                                                               // :434-441
+        RSQ_CNT(o, RSQ_C_AMBIGUOUS_READS);
+        if (hq) RSQ_CNT(o, RSQ_C_HQ_AMBIGUOUS_READS);
+    }
+    if (ribosomal) RSQ_CNT(o, RSQ_C_RRNA_READS);                                           // :442
+    if ((minus != plus) && (prm.unpaired || (f & RSQ_F_PAIRED))) {                         // :445-457
+        const bool sense = (f & RSQ_F_REVERSE) ? minus : plus;
+        if (prm.unpaired || (f & RSQ_F_READ1)) { if (sense) RSQ_CNT(o, RSQ_C_END1_SENSE); else RSQ_CNT(o, RSQ_C_END1_ANTISENSE); }
+        else { if (sense) RSQ_CNT(o, RSQ_C_END2_SENSE); else RSQ_CNT(o, RSQ_C_END2_ANTISENSE); }
+    }
+    x.exonic = exonic; x.do_exon = do_exon; x.r0 = r0;
+}
+
+RSQ_HD int read_strand(const Params& prm, uint32_t f) {                                    // feature_strand, src/Expression.cpp:119-125
+    if (!prm.strand_mode) return RSQ_STRAND_UNKNOWN;
+    bool target = f & RSQ_F_REVERSE;
+    if ((prm.strand_mode == 1) != ((f & RSQ_F_READ1) != 0)) target = !target;
+    return target ? RSQ_STRAND_REV : RSQ_STRAND_FWD;
+}
+
+}  // namespace rsqd

@@ -1,15 +1,16 @@
 // rsq_kernels.cu — hand-written sm_100a kernels of the RNA-SeQC per-read hot path.
 //
 // Compile-time ablation switches (never defined in the product build; used for the time breakdown in DESIGN.md §4):
-//   RSQ_AB_NO_FRAGSET, RSQ_AB_NO_ACCUM, RSQ_AB_NO_EPILOGUE, RSQ_AB_ONE_BLOCK, RSQ_AB_CASCADE_ONLY, RSQ_AB_SMEM_COUNTERS
+//   RSQ_AB_NO_FRAGSET, RSQ_AB_NO_ACCUM, RSQ_AB_NO_EPILOGUE, RSQ_AB_CASCADE_ONLY, RSQ_AB_NO_STAGE
 //
 // K_hot  : one pass over a batch of decoded alignment records (rsq_read + rsq_block): the flag/quality/
 //          mismatch filter cascade of src/RNASeQC.cpp:254-342, interval intersection of every aligned block
-//          with the flattened exon index and gene-segment index (src/Expression.cpp:106-117, src/GTF.cpp:171-186),
+//          with the elementary-interval index of the annotation (src/Expression.cpp:106-117, src/GTF.cpp:171-186),
 //          exon/intron classification and count accumulation (src/Expression.cpp:308-458, src/Metrics.cpp:49-66),
 //          per-base coverage as a difference array (src/Metrics.cpp:96-124,257-262), fragment-tracker set
 //          (src/Metrics.cpp:22, src/Expression.cpp:383-387) and, in BED mode, fragment-size candidates
-//          (src/Expression.cpp:482-516).
+//          (src/Expression.cpp:482-516).  The per-record logic lives in rsq_hot_core.cuh (shared with the host emulation
+//          the CPU tests check against the oracle); this file holds what needs a warp: staging, aggregation, counters.
 // There is no dense contraction anywhere on this path: no tensor cores.  The work is HBM/L2-bound integer work.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,6 +18,7 @@
 #include <algorithm>
 
 #include "rsq_device.h"
+#include "rsq_hot_core.cuh"
 
 namespace rsqd {
 
@@ -24,15 +26,6 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kHotThreads = 256;
-constexpr uint32_t kNoGene = 0xffffffffu;
-
-__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-    x ^= x >> 27; x *= 0x94d049bb133111ebull;
-    x ^= x >> 31;
-    return x;
-}
-
 // first index in [lo, hi) whose start > key
 __device__ __forceinline__ int upper_bound_start(const int2* __restrict__ se, int lo, int hi, int key) {
     while (lo < hi) {
@@ -49,37 +42,6 @@ __device__ __forceinline__ int lower_bound_pmax(const int32_t* __restrict__ pmax
     }
     return lo;
 }
-// last index in [lo, hi) whose start <= key (the slice begins with an INT32_MIN sentinel, so it exists)
-__device__ __forceinline__ int seg_find(const int2* __restrict__ ss, int lo, int hi, int key) {
-    int a = lo, b = hi;
-    while (a < b) {
-        const int mid = (a + b) >> 1;
-        if (__ldg(&ss[mid].x) > key) b = mid; else a = mid + 1;
-    }
-    return a - 1;
-}
-
-// floor(isz * 2^64 / length) for isz <= length (isz == length gives whole = 1).  Schoolbook long division in base 2^16
-// (four 32-bit divides, inlined) for aligned lengths below 65536; the generic 64-bit path only for longer reads.
-__device__ __forceinline__ void frac_q64(uint32_t isz, uint32_t length, unsigned long long& whole, unsigned long long& lo) {
-    if (isz >= length) { whole = 1ull; lo = 0ull; return; }
-    whole = 0ull;
-    if (length < 65536u) {
-        uint32_t r = isz, d0, d1, d2, d3;
-        r <<= 16; d3 = r / length; r -= d3 * length;
-        r <<= 16; d2 = r / length; r -= d2 * length;
-        r <<= 16; d1 = r / length; r -= d1 * length;
-        r <<= 16; d0 = r / length;
-        lo = ((unsigned long long)((d3 << 16) | d2) << 32) | (unsigned long long)((d1 << 16) | d0);
-        return;
-    }
-    unsigned long long r = isz;
-    const unsigned long long t1 = (r << 32) / length;
-    r = (r << 32) % length;
-    const unsigned long long t0 = (r << 32) / length;
-    lo = (t1 << 32) | t0;
-}
-
 // Open-addressing insert; returns true when the key was not present.
 __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab, unsigned long long mask, unsigned long long key,
                                            unsigned int* err, unsigned int err_bit) {
@@ -100,40 +62,15 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
     return false;
 }
 
-struct Window { int lo, hi; };
-
-// Exon window of a block through the direct-address bucket index (global/L2 path): two table reads (independent,
-// issued together) and two short forward scans replace two ~17-step dependent binary searches.
-__device__ __forceinline__ Window exon_window(const AnnView& ann, int c_lo, int c_hi, int bk_lo, int bk_n, int bs, int be) {
-    const int b0 = min(max(bs, 0) >> kBucketShift, bk_n - 1), b1 = min(max(be, 0) >> kBucketShift, bk_n - 1);
-    int lo = __ldg(&ann.buckets[bk_lo + b0].x);
-    int hi = __ldg(&ann.buckets[bk_lo + b1].y);
-    while (hi < c_hi && __ldg(&ann.exon_se[hi].x) <= be) ++hi;        // every i < hi has start <= block.end   (Expression.cpp:111)
-    while (lo < hi && __ldg(&ann.exon_pmax[lo]) < bs) ++lo;           // nothing before lo can reach block.start (GTF.cpp:171-179)
-    Window w; w.lo = lo; w.hi = hi;
-    return w;
-}
-// last gene segment whose start <= bs
-__device__ __forceinline__ int seg_lookup(const AnnView& ann, int s_hi, int bk_lo, int bk_n, int bs) {
-    const int b0 = min(max(bs, 0) >> kBucketShift, bk_n - 1);
-    int k = __ldg(&ann.buckets[bk_lo + b0].z);
-    while (k + 1 < s_hi && __ldg(&ann.seg_sf[k + 1].x) <= bs) ++k;
-    return k;
-}
-
-// ---- per-warp staging of the annotation window into shared memory (TMA bulk copies) -------------------------------------
-// A tile is 32 coordinate-sorted records, so all their first blocks fall into a window of a few hundred bases: the exon
-// entries, their metadata and the gene segments of that window are copied ONCE per tile into the warp's private slice
-// of shared memory by cp.async.bulk (1-D TMA, completion on an mbarrier); every overlap test, gene-set intersection and
-// accumulation address of an in-window block then costs shared-memory latency instead of a chain of L2 round trips.
-// Blocks outside the window (the far side of a splice junction) use the bucket-index path in L2.
-constexpr int kStageExons = 64;
-constexpr int kStageSegs = 32;
-constexpr int kWindowSlack = 512;     // first blocks end within this many bases of the last record's start
+// ---- per-warp staging of the interval starts into shared memory (TMA bulk copy) ----------------------------------------
+// A tile is 32 coordinate-sorted records, so their blocks fall into a short run of elementary intervals: the starts of the
+// kStageN intervals from the tile's lowest coordinate on are copied ONCE per tile into the warp's private slice of shared
+// memory by cp.async.bulk (1-D TMA, completion on an mbarrier; the filter cascade runs while the copy flies).  Every block
+// that ends before the last staged start is then located by a fixed-depth binary search in shared memory; blocks beyond it
+// (the far side of a long intron) go through the 1 kb direct-address table and search one bucket in L2.
+constexpr int kStageN = 128;
 struct __align__(16) WarpStage {
-    ExonMeta meta[kStageExons];
-    int2 se[kStageExons];
-    int2 seg[kStageSegs + 4];
+    int32_t starts[kStageN];
     unsigned long long mbar;
     unsigned long long pad;
 };
@@ -159,27 +96,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     } while (!ok);
 }
 
-// A block's exon candidates: entries [lo, hi) of se/meta — either the global arrays (narrowed by the bucket index) or the
-// warp's staged copy (every staged entry; the overlap test is applied per entry either way).
-struct BlockView { int lo, hi; bool in_smem; };
-struct ExonArrays { const int2* se; const ExonMeta* meta; };
-
-// does block (bs, be) lie fully inside an exon of `gene` (strand-admissible) among entries [v.lo, upto)?  Expression.cpp:341-344
-__device__ __forceinline__ bool block_has_gene(const ExonArrays a, const BlockView& v, int upto, int bs, int be, uint32_t gene, int rstrand) {
-    for (int i = v.lo; i < upto; ++i) {
-        const int2 x = a.se[i];
-        if (x.x <= bs && be - 1 <= x.y) {
-            const uint32_t gf = a.meta[i].gene_flags;
-            const int fs = (gf >> 24) & RSQ_EXON_STRAND_MASK;
-            if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != fs) continue;
-            if ((gf & 0xffffffu) == gene) return true;
-        }
+// Memory side effects of the per-record logic on the device: fire-and-forget REDs and the fragment-tracker CAS.
+struct DevMem {
+    const Accum& acc;
+    __device__ __forceinline__ void add64(unsigned long long* p, unsigned long long v) const {
+#ifndef RSQ_AB_NO_ACCUM
+        atomicAdd(p, v);
+#endif
     }
-    return false;
-}
+    __device__ __forceinline__ void add32(unsigned int* p, unsigned int v) const {
+#ifndef RSQ_AB_NO_ACCUM
+        atomicAdd(p, v);
+#endif
+    }
+    __device__ __forceinline__ bool frag_insert(unsigned long long key) const {
+#ifdef RSQ_AB_NO_FRAGSET
+        return (key & 1ull) != 0;   // ablation only: no hash-set traffic (results are wrong)
+#else
+        return set_insert(acc.frag_set, acc.frag_mask, key, acc.error_flag, 1u);
+#endif
+    }
+};
 
 #ifndef RSQ_HOT_MIN_BLOCKS
-#define RSQ_HOT_MIN_BLOCKS 3
+#define RSQ_HOT_MIN_BLOCKS 4
 #endif
 }  // namespace
 }  // namespace rsqd
@@ -224,66 +164,35 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(reads + (tile + warps_total) * 32) + lane * 128));
     }
 
-    // ---- stage this tile's annotation window (warp-uniform) ---------------------------------------------------------------
-    bool staged = false;
-    int wmin = 0, wmax = 0, LO = 0, HI = 0, SLO = 0, SHI = 0, t_shi = 0;
-    {
+    // ---- stage this tile's run of interval starts (warp-uniform) ----------------------------------------------------------
+    TileWin w;
+    w.st = st->starts; w.base = 0; w.k0 = 0; w.hi = 0; w.wmin = 0; w.lastv = 0; w.on = false;
+    bool to_end = false;
+#ifndef RSQ_AB_NO_STAGE
+    if constexpr (!kLegacy) {
         const int my_contig = (int)(int16_t)((uint32_t)q1.w & 0xffffu);
         const int pmin = __reduce_min_sync(kFull, valid ? q0.x : INT32_MAX);
-        const int pmax = __reduce_max_sync(kFull, valid ? q0.x : INT32_MIN);
         const int cmin = __reduce_min_sync(kFull, valid ? my_contig : INT32_MAX);
         const int cmax = __reduce_max_sync(kFull, valid ? my_contig : INT32_MIN);
-        if (cmin == cmax && cmin >= 0 && (uint32_t)cmin < ann.n_contigs && pmin >= 0 && pmax - pmin < (1 << 24)) {
-            wmin = pmin + 1; wmax = pmax + 1 + kWindowSlack;
-            const int c_lo = (int)__ldg(&ann.exon_off[cmin]), c_hi = (int)__ldg(&ann.exon_off[cmin + 1]);
-            const int s_hi = (int)__ldg(&ann.seg_off[cmin + 1]);
-            const int bk_lo = (int)__ldg(&ann.bucket_off[cmin]), bk_n = (int)__ldg(&ann.bucket_off[cmin + 1]) - bk_lo;
-            const int4 e0 = __ldg(&ann.buckets[bk_lo + min(wmin >> kBucketShift, bk_n - 1)]);
-            const int4 e1 = __ldg(&ann.buckets[bk_lo + min(wmax >> kBucketShift, bk_n - 1)]);
-            // lane-parallel forward probes: one round trip each instead of a dependent scan
-            int idx = e0.x + (int)lane;
-            unsigned m = __ballot_sync(kFull, idx >= c_hi || __ldg(&ann.exon_pmax[min(idx, c_hi - 1)]) >= wmin || c_hi == c_lo);
-            bool ok = m != 0;
-            LO = min(e0.x + __ffs(m) - 1, c_hi);
-            idx = e1.y + (int)lane;
-            m = __ballot_sync(kFull, idx >= c_hi || __ldg(&ann.exon_se[min(idx, c_hi - 1)].x) > wmax || c_hi == c_lo);
-            ok = ok && m != 0;
-            HI = max(min(e1.y + __ffs(m) - 1, c_hi), LO);
-            idx = e0.z + 1 + (int)lane;
-            m = __ballot_sync(kFull, idx >= s_hi || __ldg(&ann.seg_sf[min(idx, s_hi - 1)].x) > wmin);
-            ok = ok && m != 0;
-            SLO = e0.z + __ffs(m) - 1;                                  // last segment starting at or before wmin
-            idx = SLO + 1 + (int)lane;
-            m = __ballot_sync(kFull, idx >= s_hi || __ldg(&ann.seg_sf[min(idx, s_hi - 1)].x) > wmax);
-            ok = ok && m != 0;
-            SHI = min(SLO + __ffs(m), s_hi);                            // first segment starting after wmax (or the end)
-            t_shi = s_hi;
-            const int LOa = LO & ~1, SLOa = SLO & ~1;
-            const int n_ex = (HI - LOa + 1) & ~1;                        // even counts keep every bulk copy 16-byte granular
-            const int n_sg = (min(SHI + 1, s_hi) - SLOa + 1) & ~1;       // includes the start of the segment after the window
-            if (ok && n_ex <= kStageExons && n_sg <= kStageSegs + 2) {
-                staged = true;
-                __syncwarp();                                            // every lane is done with the previous tile's copy
-                if (lane == 0) {
-                    mbar_expect_tx(mbar, (uint32_t)(n_ex * 24 + n_sg * 8));
-                    if (n_ex) {
-                        tma_bulk_g2s(smem_u32(st->meta), ann.exon_meta + LOa, (uint32_t)(n_ex * 16), mbar);
-                        tma_bulk_g2s(smem_u32(st->se), ann.exon_se + LOa, (uint32_t)(n_ex * 8), mbar);
-                    }
-                    tma_bulk_g2s(smem_u32(st->seg), ann.seg_sf + SLOa, (uint32_t)(n_sg * 8), mbar);
-                }
+        if (cmin == cmax && cmin >= 0 && (uint32_t)cmin < ann.n_contigs && pmin >= 0 && pmin < INT32_MAX) {
+            const int c_hi = (int)__ldg(&ann.ei_off[cmin + 1]);
+            const int bk_lo = (int)__ldg(&ann.eib_off[cmin]), bk_n = (int)__ldg(&ann.eib_off[cmin + 1]) - bk_lo - 1;
+            w.wmin = pmin + 1;
+            w.k0 = (int)__ldg(&ann.eib[bk_lo + min(w.wmin >> kEiShift, bk_n - 1)]);
+            w.base = w.k0 & ~3;                                          // bulk copies are 16-byte granular
+            w.hi = min(w.base + kStageN, c_hi);
+            to_end = w.hi == c_hi;
+            w.on = true;
+            __syncwarp();                                                // every lane is done with the previous tile's copy
+            if (lane == 0) {
+                mbar_expect_tx(mbar, (uint32_t)(kStageN * 4));
+                tma_bulk_g2s(smem_u32(st->starts), ann.ei_start + w.base, (uint32_t)(kStageN * 4), mbar);   // the array is padded
             }
         }
     }
+#endif
 
-    unsigned long long cm = 0ull;       // bit k set: counter k += 1
-    unsigned vflags = 0;                // bit0: End 1 sums, bit1: End 2 sums, bit2: Mismatched Bases, bit3: Total Bases, bit4: blocks
-    unsigned int my_bytes = 0;
-    uint32_t agg_gene = kNoGene;        // first gene this read counts toward (aggregated across the warp below)
-    bool agg_unique = false, agg_frag = false;
-    int n_fresh = 0;                    // new fragment-set entries of this read (sizes the set's growth on the host)
-
-    // ---- filter cascade, RNASeQC.cpp:254-342 (independent of the annotation: overlaps the bulk copies) ---------------------
+    // ---- filter cascade, RNASeQC.cpp:254-342 (independent of the annotation: overlaps the bulk copy) ------------------------
     const int pos = q0.x, mpos = q0.y, endpos = q0.z, isize = q0.w;
     const int l_qseq = q1.x, nm_raw = q1.y;
     const uint32_t w6 = (uint32_t)q1.z, w7 = (uint32_t)q1.w;
@@ -296,309 +205,46 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     const uint32_t block_off = (uint32_t)q2.z;
     uint32_t nb = (uint32_t)q2.w & 0xffffu;
     if ((size_t)block_off + nb > n_blocks) nb = 0;  // defensive: never read out of the submitted array
-#ifdef RSQ_AB_ONE_BLOCK
-    nb = nb ? 1u : 0u;   // ablation only
-#endif
-    (void)endpos; (void)isize;
-    bool go = valid, hq = false;
-#define CNT(k) (cm |= 1ull << (k))
-    if (valid) {
-        CNT(RSQ_C_TOTAL_ALIGNMENTS);                                                  // RNASeQC.cpp:245
-        my_bytes = 40u + 8u * nb;
-        if (f & RSQ_F_SECONDARY) CNT(RSQ_C_ALTERNATIVE_ALIGNMENTS);                   // :254
-        if (f & RSQ_F_SUPPLEMENTARY) CNT(RSQ_C_SUPPLEMENTARY_ALIGNMENTS);             // :255
-        else if (f & RSQ_F_QCFAIL) CNT(RSQ_C_FAILED_VENDOR_QC);
-        else if (mapq < prm.mapq_threshold) CNT(RSQ_C_LOW_MAPPING_QUALITY);
-        const bool has_ch = aux & RSQ_AUX_CHIMERIC_TAG;
-        if ((f & RSQ_F_SUPPLEMENTARY) && !(kLegacy || has_ch)) {                       // :258-262
-            CNT(RSQ_C_CHIMERIC_AUTO);
-            if (prm.exclude_chimeric) go = false;
-        }
-        if (f & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) go = false;   // :263
-        if (go) {
-            CNT(RSQ_C_UMVQ);
-            if (!(f & RSQ_F_PAIRED)) CNT(RSQ_C_UNPAIRED_READS);
-            if (f & RSQ_F_UNMAP) go = false;                                          // :268
-        }
-        if (go) {
-            CNT(RSQ_C_MAPPED_READS);
-            if (f & RSQ_F_DUP) CNT(RSQ_C_MAPPED_DUPLICATE_READS); else CNT(RSQ_C_MAPPED_UNIQUE_READS);
-            if (kLegacy && (unsigned)(endpos - pos) > 100000u) go = false;             // :275-276 LEGACY_MAX_READ_LENGTH
-            if (go && !kLegacy && has_ch) {                                            // :279-283
-                if (f & RSQ_F_READ1) CNT(RSQ_C_CHIMERIC_TAG);
-                if (prm.exclude_chimeric) go = false;
-            }
-        }
-        if (go && (f & RSQ_F_PAIRED) && !(f & RSQ_F_MUNMAP)) {                         // :284-292
-            if (f & RSQ_F_READ1) CNT(RSQ_C_TOTAL_MAPPED_PAIRS);
-            int d = pos - mpos; d = d < 0 ? -d : d;
-            if ((aux & RSQ_AUX_MATE_OTHER_CONTIG) || d > prm.chimeric_distance || (kLegacy && (aux & RSQ_AUX_TID_GT_127))) {
-                if (f & RSQ_F_READ1) CNT(RSQ_C_CHIMERIC_AUTO);
-                if (prm.exclude_chimeric) go = false;
-            }
-        }
-        if (go) {
-            int mismatches = 0;
-            if (aux & RSQ_AUX_HAS_NM) {                                                // :294-316
-                mismatches = nm_raw;
-                if (f & RSQ_F_PAIRED) {
-                    if (f & RSQ_F_READ1) {
-                        CNT(RSQ_C_END1_MAPPED_READS);
-                        vflags |= 1u;
-                        if (f & RSQ_F_DUP) CNT(RSQ_C_DUPLICATE_PAIRS); else CNT(RSQ_C_UNIQUE_FRAGMENTS);
-                    } else {
-                        CNT(RSQ_C_END2_MAPPED_READS);
-                        vflags |= 2u;
-                    }
-                }
-                vflags |= 4u;
-            }
-            vflags |= 8u;                                                              // :317
-            if (filter_mask) {                                                         // :319-328
-                for (uint32_t k = 0; k < prm.n_filter_tags && k < 8; ++k)
-                    if (filter_mask & (1u << k)) { CNT(RSQ_C_FILTERED_BY_TAG0 + k); go = false; }
-            }
-            hq = (uint32_t)mismatches <= prm.base_mismatch_threshold && (prm.unpaired || (f & RSQ_F_PROPER)) &&
-                 mapq >= prm.mapq_threshold;                                           // :330
-            if (aux & RSQ_AUX_TID_OUT_OF_RANGE) go = false;                            // :333-337
-        }
-        if (go) {
-            if (hq) CNT(RSQ_C_HIGH_QUALITY_READS); else CNT(RSQ_C_LOW_QUALITY_READS);  // :340-342
-            CNT(RSQ_C_READS_USED);
-            vflags |= 16u;                                                             // :360
-        }
+    (void)isize; (void)l_qseq;
+    RecOut o;
+    filter_cascade<kLegacy>(prm, valid, f, mapq, aux, filter_mask, pos, mpos, endpos, nm_raw, nb, o);
+
+    if (w.on) {                                                                        // the starts have landed in shared memory
+        mbar_wait(mbar, phase); phase ^= 1u;
+        w.lastv = to_end ? INT32_MAX : st->starts[w.hi - 1 - w.base];
     }
 
-    if (staged) { mbar_wait(mbar, phase); phase ^= 1u; }                               // the window has landed in shared memory
-
 #ifdef RSQ_AB_CASCADE_ONLY
-    go = false;   // ablation only
+    o.go = false;   // ablation only
 #endif
-    if (go) {
+    const bool hq = o.hq;
+    if (o.go) {
         {
             // ---- exonAlignmentMetrics, Expression.cpp:308-458 ----------------------------------------------------
             const bool cleared = (aux & RSQ_AUX_CONTIG_DROPPED) || contig < 0 || (uint32_t)contig >= ann.n_contigs;
-            int rstrand = RSQ_STRAND_UNKNOWN;                                          // feature_strand, :119-125
-            if (prm.strand_mode) {
-                bool target = f & RSQ_F_REVERSE;
-                if ((prm.strand_mode == 1) != ((f & RSQ_F_READ1) != 0)) target = !target;
-                rstrand = target ? RSQ_STRAND_REV : RSQ_STRAND_FWD;
-            }
+            const int rstrand = read_strand(prm, f);                                   // feature_strand, :119-125
             const rsq_block* bp = blocks + block_off;
             if constexpr (kLegacy) {                                                   // :364
                 LegacyRead lr;
                 lr.contig = contig; lr.pos = pos; lr.endpos = endpos; lr.l_qseq = l_qseq; lr.rstrand = rstrand;
                 lr.flag = f; lr.nb = nb; lr.cleared = cleared; lr.hq = hq; lr.name_hash = name_hash; lr.bp = bp;
-                legacy_metrics(ann, acc, prm, lr, cm, n_fresh, my_bytes);
+                legacy_metrics(ann, acc, prm, lr, o.cm, o.n_fresh, o.my_bytes);
             } else {
-            int c_lo = 0, c_hi = 0, s_hi = 0, bk_lo = 0, bk_n = 1;
-            if (!cleared) {
-                c_lo = (int)__ldg(&ann.exon_off[contig]); c_hi = (int)__ldg(&ann.exon_off[contig + 1]);
-                s_hi = (int)__ldg(&ann.seg_off[contig + 1]);
-                bk_lo = (int)__ldg(&ann.bucket_off[contig]); bk_n = (int)__ldg(&ann.bucket_off[contig + 1]) - bk_lo;
-            }
-            // the exon candidates of a block: the staged window when the block lies inside it, else the L2 path
-            auto view_of = [&](int bs, int be) -> BlockView {
-                BlockView v;
-                if (staged && bs >= wmin && be <= wmax) { v.lo = LO - (LO & ~1); v.hi = HI - (LO & ~1); v.in_smem = true; }
-                else {
-                    const Window w = exon_window(ann, c_lo, c_hi, bk_lo, bk_n, bs, be);
-                    v.lo = w.lo; v.hi = w.hi; v.in_smem = false;
-                }
-                return v;
-            };
-            auto arrays_of = [&](const BlockView& v) -> ExonArrays {
-                ExonArrays a;
-                a.se = v.in_smem ? st->se : ann.exon_se;
-                a.meta = v.in_smem ? st->meta : ann.exon_meta;
-                return a;
-            };
-            bool intragenic = false, plus = false, minus = false, ribosomal = false, exonic = false, do_exon = false;
-            uint32_t length = 0;                                                       // extractBlocks' return, :359
-            BlockView v0 = {0, 0, false}, v1 = v0;
-            int bs0 = 0, be0 = 0, bs1 = 0, be1 = 0;
-            for (uint32_t b = 0; b < nb; ++b) {                                        // :325-361
-                const int2 blk = __ldg(reinterpret_cast<const int2*>(bp + b));
-                const int bs = blk.x, be = blk.x + blk.y;                              // closed end = start+len, :45
-                length += (uint32_t)blk.y;
-                if (b == 0) { bs0 = bs; be0 = be; } else if (b == 1) { bs1 = bs; be1 = be; }
-                if (cleared) continue;
-                // Gene features: elementary segments overlapping [bs, be]  (:352-358)
-                uint32_t gfl = 0;
-                if (staged && bs >= wmin && be <= wmax) {
-                    for (int k = SLO; k < SHI; ++k) {
-                        const int2 sg = st->seg[k - (SLO & ~1)];
-                        if (sg.x > be) break;
-                        const int nxt = (k + 1 < t_shi) ? st->seg[k + 1 - (SLO & ~1)].x : INT32_MAX;
-                        if (nxt > bs) gfl |= (uint32_t)sg.y;
-                    }
-                } else {
-                    for (int k = seg_lookup(ann, s_hi, bk_lo, bk_n, bs); k < s_hi; ++k) {
-                        const int2 sg = __ldg(&ann.seg_sf[k]);
-                        if (sg.x > be) break;
-                        gfl |= (uint32_t)sg.y;
-                    }
-                }
-                if (rstrand != RSQ_STRAND_UNKNOWN) gfl &= (RSQ_SEG_GENE_FWD | RSQ_SEG_RIBO_FWD) << rstrand;   // :331
-                if (gfl & (RSQ_SEG_GENE_FWD | RSQ_SEG_GENE_REV | RSQ_SEG_GENE_UNK)) intragenic = true;
-                if (gfl & RSQ_SEG_GENE_FWD) plus = true;
-                if (gfl & RSQ_SEG_GENE_REV) minus = true;
-                if (gfl & (RSQ_SEG_RIBO_FWD | RSQ_SEG_RIBO_REV | RSQ_SEG_RIBO_UNK)) ribosomal = true;
-                // Exon features (:335-351)
-                const BlockView v = view_of(bs, be);
-                const ExonArrays va = arrays_of(v);
-                if (b == 0) v0 = v; else if (b == 1) v1 = v;
-                for (int e = v.lo; e < v.hi; ++e) {
-                    const int2 x = va.se[e];
-                    if (x.y < bs || x.x > be) continue;                                // intersectInterval, GTF.cpp:176-179
-                    const uint32_t gf = va.meta[e].gene_flags;
-                    const int fs = (gf >> 24) & RSQ_EXON_STRAND_MASK;
-                    if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != fs) continue;      // :331
-                    if (fs == RSQ_STRAND_FWD) plus = true; else if (fs == RSQ_STRAND_REV) minus = true;
-                    exonic = true;                                                     // :337
-                    if ((gf >> 24) & RSQ_EXON_RIBOSOMAL) ribosomal = true;             // :358
-                }
-            }
-
-            bool globin = false;
-            if (nb >= 1 && !cleared) {                                                 // :363-394
-                // `last` = intersection over blocks of {genes with an exon that fully contains the block}.  Enumerate
-                // the candidates of block 0 (deduplicated by re-scanning the window: no per-thread set storage) and
-                // test each against every other block.
-                const ExonArrays a0 = arrays_of(v0);
-                for (int e0 = v0.lo; e0 < v0.hi; ++e0) {
-                    const int2 x0 = a0.se[e0];
-                    if (!(x0.x <= bs0 && be0 - 1 <= x0.y)) continue;                   // isz == block length, :341
-                    const uint32_t gf0 = a0.meta[e0].gene_flags;
-                    if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != (int)((gf0 >> 24) & RSQ_EXON_STRAND_MASK)) continue;
-                    const uint32_t g = gf0 & 0xffffffu;
-                    if (block_has_gene(a0, v0, e0, bs0, be0, g, rstrand)) continue;        // an earlier entry already gave this gene
-                    bool in_all = true;
-                    for (uint32_t b = 1; b < nb && in_all; ++b) {
-                        if (b == 1) in_all = block_has_gene(arrays_of(v1), v1, v1.hi, bs1, be1, g, rstrand);
-                        else {
-                            const int2 blk = __ldg(reinterpret_cast<const int2*>(bp + b));
-                            const BlockView v = view_of(blk.x, blk.x + blk.y);
-                            in_all = block_has_gene(arrays_of(v), v, v.hi, blk.x, blk.x + blk.y, g, rstrand);
-                        }
-                    }
-                    if (!in_all) continue;
-                    // g is in `last` (:377)
-                    do_exon = true;                                                    // :393
-                    if (__ldg(&ann.gene_flags[g]) & RSQ_GENE_GLOBIN) globin = true;    // :396-398
-                    if (!hq) continue;
-                    if (length > 0) {                                                  // queryGene: some coverage > 0, :380
-                        const unsigned long long key0 = mix64(name_hash ^ ((unsigned long long)(g + 1u) * 0x9E3779B97F4A7C15ull));
-#ifdef RSQ_AB_NO_FRAGSET
-                        const bool fresh = (key0 & 1ull) != 0;   // ablation only: no hash-set traffic (results are wrong)
-#else
-                        const bool fresh = set_insert(acc.frag_set, acc.frag_mask, key0 ? key0 : 1ull, acc.error_flag, 1u);  // :383-387
-#endif
-                        n_fresh += fresh ? 1 : 0;
-                        if (agg_gene == kNoGene) { agg_gene = g; agg_unique = !(f & RSQ_F_DUP); agg_frag = fresh; }
-                        else {
-                            atomicAdd(&acc.gene_reads[g], 1ull);
-                            if (fresh) atomicAdd(&acc.gene_fragments[g], 1ull);
-                            if (!(f & RSQ_F_DUP)) atomicAdd(&acc.gene_unique[g], 1ull);
-                        }
-                        my_bytes += 8u;
-                    }
-                    // Collector::collect + BaseCoverage::commit for gene g: every (block, containing exon of g) pair
-                    for (uint32_t b = 0; b < nb; ++b) {
-                        int bs, be; BlockView v;
-                        if (b == 0) { bs = bs0; be = be0; v = v0; }
-                        else if (b == 1) { bs = bs1; be = be1; v = v1; }
-                        else {
-                            const int2 blk = __ldg(reinterpret_cast<const int2*>(bp + b));
-                            bs = blk.x; be = blk.x + blk.y;
-                            v = view_of(bs, be);
-                        }
-                        const uint32_t len = (uint32_t)(be - bs);
-                        if (len == 0) continue;                                        // Collector::add keeps coverage > 0, Metrics.cpp:51
-                        const ExonArrays va = arrays_of(v);
-                        for (int e = v.lo; e < v.hi; ++e) {
-                            const int2 x = va.se[e];
-                            if (!(x.x <= bs && be - 1 <= x.y)) continue;
-                            const ExonMeta m = va.meta[e];
-                            if ((m.gene_flags & 0xffffffu) != g) continue;
-                            if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != (int)((m.gene_flags >> 24) & RSQ_EXON_STRAND_MASK)) continue;
-#ifdef RSQ_AB_NO_ACCUM
-                            my_bytes += (unsigned)(m.slot & 1u);   // ablation only: keep the loads, drop every accumulation atomic
-                            continue;
-#endif
-                            unsigned long long whole, lo;
-                            frac_q64(len, length, whole, lo);                          // isz/length, :345
-                            // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update
-                            // is a fire-and-forget RED, nothing waits for an atomic's return value
-#ifdef RSQ_AB_SCATTER   // diagnostic only (wrong results): same instruction stream, but every lane/warp hits its own address
-                            const uint32_t sslot = (m.slot + (uint32_t)(i * 97u)) % ann.n_exons;
-                            if (whole) atomicAdd(&acc.exon_whole[sslot], whole);
-                            else { atomicAdd(&acc.exon_fhi[sslot], lo >> 32); atomicAdd(&acc.exon_flo[sslot], lo & 0xffffffffull); }
-                            my_bytes += 8u;
-                            if (prm.collect_coverage) {
-                                const unsigned long long o = (m.cov_off + (unsigned long long)(bs - x.x) + (unsigned long long)i * 4099ull) % (prm.cov_len_diag - 4096ull);
-                                atomicAdd(&acc.cov_diff[o], 1u);
-                                atomicAdd(&acc.cov_diff[o + len], 0xffffffffu);
-                                my_bytes += 8u;
-                            }
-#else
-                            if (whole) atomicAdd(&acc.exon_whole[m.slot], whole);
-                            else {
-                                atomicAdd(&acc.exon_fhi[m.slot], lo >> 32);
-                                atomicAdd(&acc.exon_flo[m.slot], lo & 0xffffffffull);
-                            }
-                            my_bytes += 8u;
-                            if (prm.collect_coverage) {                                // add_range as +1/-1, Metrics.cpp:257-262
-                                const unsigned long long o = m.cov_off + (unsigned long long)(bs - x.x);
-                                atomicAdd(&acc.cov_diff[o], 1u);
-                                atomicAdd(&acc.cov_diff[o + len], 0xffffffffu);
-                                my_bytes += 8u;
-                            }
-#endif
-                        }
-                    }
-                }
-            }
-            if (nb >= 1 && !globin) {                                                  // :399-404
-                CNT(RSQ_C_NON_GLOBIN_READS);
-                if (f & RSQ_F_DUP) CNT(RSQ_C_NON_GLOBIN_DUPLICATE_READS);
-            }
-            if (!exonic) {                                                             // :407-423
-                if (intragenic) {
-                    CNT(RSQ_C_INTRONIC_READS); CNT(RSQ_C_INTRAGENIC_READS);
-                    if (hq) { CNT(RSQ_C_HQ_INTRONIC_READS); CNT(RSQ_C_HQ_INTRAGENIC_READS); }
-                } else {
-                    CNT(RSQ_C_INTERGENIC_READS);
-                    if (hq) CNT(RSQ_C_HQ_INTERGENIC_READS);
-                }
-            } else if (do_exon) {                                                      // :424-433
-                CNT(RSQ_C_EXONIC_READS); CNT(RSQ_C_INTRAGENIC_READS);
-                if (hq) { CNT(RSQ_C_HQ_EXONIC_READS); CNT(RSQ_C_HQ_INTRAGENIC_READS); }
-            } else {                                                                   // :434-441
-                CNT(RSQ_C_AMBIGUOUS_READS);
-                if (hq) CNT(RSQ_C_HQ_AMBIGUOUS_READS);
-            }
-            if (ribosomal) CNT(RSQ_C_RRNA_READS);                                      // :442
-            if ((minus != plus) && (prm.unpaired || (f & RSQ_F_PAIRED))) {             // :445-457
-                const bool sense = (f & RSQ_F_REVERSE) ? minus : plus;
-                if (prm.unpaired || (f & RSQ_F_READ1)) { if (sense) CNT(RSQ_C_END1_SENSE); else CNT(RSQ_C_END1_ANTISENSE); }
-                else { if (sense) CNT(RSQ_C_END2_SENSE); else CNT(RSQ_C_END2_ANTISENSE); }
-            }
+            const DevMem mem{acc};
+            ExonOut x;
+            exon_metrics(mem, ann, w, prm, acc, f, hq, cleared, contig, rstrand, bp, nb, name_hash, o, x);
 
             // ---- fragment GC content candidate, Expression.cpp:459-467 --------------------------------------------------
             if constexpr (kGc) {
                 const unsigned aisz = (unsigned)(isize < 0 ? -(long long)isize : (long long)isize);
-                if (hq && exonic && do_exon && nb == 1 && aisz > 100u && aisz < 1000u && !cleared && __ldg(&prm.ref_present[contig])) {
+                if (hq && x.exonic && x.do_exon && nb == 1 && aisz > 100u && aisz < 1000u && !cleared && __ldg(&prm.ref_present[contig])) {
                     // alignedExons (:319,348): exons of any gene that fully contain the block, read strand respected
-                    const ExonArrays a0 = arrays_of(v0);
                     int n_full = 0;
                     uint32_t the_slot = 0;
-                    for (int e0 = v0.lo; e0 < v0.hi; ++e0) {
-                        const int2 x0 = a0.se[e0];
-                        if (!(x0.x <= bs0 && be0 - 1 <= x0.y)) continue;
-                        const ExonMeta m0 = a0.meta[e0];
-                        if (rstrand != RSQ_STRAND_UNKNOWN && rstrand != (int)((m0.gene_flags >> 24) & RSQ_EXON_STRAND_MASK)) continue;
-                        ++n_full; the_slot = m0.slot;
+                    for (uint32_t j = 0; j < x.r0.cn; ++j) {
+                        const CoverHead h = cover_head(ann, x.r0.coff + j);
+                        if (!cover_admits(h, x.r0, rstrand)) continue;
+                        ++n_full; the_slot = h.slot;
                     }
                     if (n_full == 1) {
                         const unsigned long long key = name_hash ? name_hash : 1ull;
@@ -648,7 +294,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                         } else same = false;
                     }
                     if (same) {                                                        // :508-516: enters the mate map
-                        CNT(RSQ_C_FRAGMENT_CANDIDATES);
+                        RSQ_CNT(o, RSQ_C_FRAGMENT_CANDIDATES);
                         // claim the table slot of this read name and record the earliest candidate
                         unsigned long long key = name_hash ? name_hash : 1ull;
                         unsigned long long slot = mix64(key) & acc.pair_mask;
@@ -676,19 +322,18 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             }
         }
     }
-#undef CNT
 
     // ---- warp-converged epilogue: aggregate before touching HBM -------------------------------------------------------
     // gene counters: lanes that count toward the same gene elect one leader (sorted input => usually the whole warp)
     {
-        const unsigned peers = __match_any_sync(kFull, agg_gene);
-        const unsigned bu = __ballot_sync(kFull, agg_unique);
-        const unsigned bf = __ballot_sync(kFull, agg_frag);
-        if (agg_gene != kNoGene && lane == (unsigned)(__ffs(peers) - 1)) {
-            atomicAdd(&acc.gene_reads[agg_gene], (unsigned long long)__popc(peers));
+        const unsigned peers = __match_any_sync(kFull, o.agg_gene);
+        const unsigned bu = __ballot_sync(kFull, o.agg_unique);
+        const unsigned bf = __ballot_sync(kFull, o.agg_frag);
+        if (o.agg_gene != kNoGene && lane == (unsigned)(__ffs(peers) - 1)) {
+            atomicAdd(&acc.gene_reads[o.agg_gene], (unsigned long long)__popc(peers));
             const int nu = __popc(peers & bu), nf = __popc(peers & bf);
-            if (nu) atomicAdd(&acc.gene_unique[agg_gene], (unsigned long long)nu);
-            if (nf) atomicAdd(&acc.gene_fragments[agg_gene], (unsigned long long)nf);
+            if (nu) atomicAdd(&acc.gene_unique[o.agg_gene], (unsigned long long)nu);
+            if (nf) atomicAdd(&acc.gene_fragments[o.agg_gene], (unsigned long long)nf);
         }
     }
     // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  Neighbouring
@@ -696,14 +341,14 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // identical groups: one shuffle+ballot per GROUP (typically 3-6) instead of one ballot per touched counter (~15).
     {
 #ifdef RSQ_AB_NO_EPILOGUE
-        unsigned remaining = 0; own_lo += cm & 1ull;   // ablation only
+        unsigned remaining = 0; own_lo += o.cm & 1ull;   // ablation only
 #else
         unsigned remaining = kFull;
 #endif
         while (remaining) {
             const int leader = __ffs(remaining) - 1;
-            const unsigned long long lp = __shfl_sync(kFull, cm, leader);
-            const unsigned grp = __ballot_sync(kFull, cm == lp);
+            const unsigned long long lp = __shfl_sync(kFull, o.cm, leader);
+            const unsigned grp = __ballot_sync(kFull, o.cm == lp);
             const unsigned long long n = (unsigned long long)__popc(grp);
             if ((lp >> lane) & 1ull) own_lo += n;
             if ((lp >> (32 + lane)) & 1ull) own_hi += n;
@@ -712,12 +357,12 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     }
     // valued counters (Metrics::increment(key, int), Metrics.cpp:33-36): signed 32-bit warp sums, sign-extended
     {
-        const int s_mm1 = __reduce_add_sync(kFull, (vflags & 1u) ? nm_raw : 0), s_b1 = __reduce_add_sync(kFull, (vflags & 1u) ? l_qseq : 0);
-        const int s_mm2 = __reduce_add_sync(kFull, (vflags & 2u) ? nm_raw : 0), s_b2 = __reduce_add_sync(kFull, (vflags & 2u) ? l_qseq : 0);
-        const int s_mm = __reduce_add_sync(kFull, (vflags & 4u) ? nm_raw : 0), s_tb = __reduce_add_sync(kFull, (vflags & 8u) ? l_qseq : 0);
-        const int s_nb = __reduce_add_sync(kFull, (vflags & 16u) ? (int)nb : 0);
-        const unsigned s_bytes_w = __reduce_add_sync(kFull, my_bytes);
-        const int s_fresh = __reduce_add_sync(kFull, n_fresh);
+        const int s_mm1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? nm_raw : 0), s_b1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? l_qseq : 0);
+        const int s_mm2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? nm_raw : 0), s_b2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? l_qseq : 0);
+        const int s_mm = __reduce_add_sync(kFull, (o.vflags & 4u) ? nm_raw : 0), s_tb = __reduce_add_sync(kFull, (o.vflags & 8u) ? l_qseq : 0);
+        const int s_nb = __reduce_add_sync(kFull, (o.vflags & 16u) ? (int)nb : 0);
+        const unsigned s_bytes_w = __reduce_add_sync(kFull, o.my_bytes);
+        const int s_fresh = __reduce_add_sync(kFull, o.n_fresh);
         static_assert(RSQ_C_FRAGSET_ENTRIES >= 32 && RSQ_C_FRAGSET_ENTRIES < 64, "lives in own_hi");
         if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_fresh;
         static_assert(RSQ_C_END1_MISMATCHES < 32 && RSQ_C_END1_BASES < 32 && RSQ_C_END2_MISMATCHES < 32 && RSQ_C_END2_BASES < 32 &&
@@ -755,24 +400,6 @@ __global__ void prefix_max_kernel(const int2* __restrict__ se, const uint32_t* _
         m = max(m, se[i].y);
         pmax[i] = m;
     }
-}
-
-// direct-address bucket index (one thread per bucket, binary searches once per run)
-__global__ void build_buckets_kernel(const AnnView ann, int4* __restrict__ buckets, uint32_t n_buckets) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_buckets) return;
-    int a = 0, b = (int)ann.n_contigs;           // contig of this bucket: last c with bucket_off[c] <= g
-    while (a < b) { const int mid = (a + b) >> 1; if (ann.bucket_off[mid] > g) b = mid; else a = mid + 1; }
-    const int c = a - 1;
-    const long long x0 = (long long)(g - ann.bucket_off[c]) << kBucketShift;
-    const int key = (int)min(x0, (long long)INT32_MAX);
-    const int c_lo = (int)ann.exon_off[c], c_hi = (int)ann.exon_off[c + 1];
-    int4 e;
-    e.x = lower_bound_pmax(ann.exon_pmax, c_lo, c_hi, key);
-    e.y = upper_bound_start(ann.exon_se, c_lo, c_hi, key - 1);
-    e.z = seg_find(ann.seg_sf, (int)ann.seg_off[c], (int)ann.seg_off[c + 1], key);
-    e.w = 0;
-    buckets[g] = e;
 }
 
 // mate-map growth: re-insert (key, first index, payload) triples into a larger table
@@ -1121,11 +748,6 @@ int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, i
     return 1;
 }
 
-int launch_build_buckets(const AnnView& ann, int4* buckets, uint32_t n_buckets, cudaStream_t stream) {
-    if (!n_buckets) return 0;
-    build_buckets_kernel<<<(n_buckets + 255) / 256, 256, 0, stream>>>(ann, buckets, n_buckets);
-    return 1;
-}
 
 int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,
                        unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream) {

@@ -1,0 +1,188 @@
+"""CPU tests of the hot kernel's per-record logic and of the elementary-interval index, WITHOUT a GPU.
+
+`oracle/_build/libhostcore.so` (tests/hostcore/hostcore.cpp, test infrastructure) compiles the very sources the CUDA kernel
+is made of — rnaseqc_b200/csrc/rsq_hot_core.cuh (filter cascade, interval look-up, exonAlignmentMetrics) and
+rnaseqc_b200/csrc/rsq_eit.h (index builder) — for the host and drives them tile by tile as a warp does (32 records, a
+128-entry staged slice, the 1 kb table for blocks outside it).  Its tables must equal the CPU oracle's bit for bit:
+counters, gene tables, exact Q64.64 exon sums, every base of the coverage array, the algorithmic byte count."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOSTCORE = os.path.join(ROOT, "oracle", "_build", "libhostcore.so")
+
+
+def _hostcore():
+    lib = C.CDLL(HOSTCORE)
+    lib.hostcore_run.restype = C.c_int
+    return lib
+
+
+def run_hostcore(api, ann, reads, blocks, cfg):
+    lib = _hostcore()
+    G, E, L = ann.n_genes, ann.n_exons, ann.cov_len
+    out = {k: np.zeros(n, np.uint64) for k, n in (("counters", 64), ("gene_reads", G), ("gene_unique", G), ("gene_fragments", G),
+                                                   ("exon_whole", E), ("exon_fhi", E), ("exon_flo", E), ("bytes", 1), ("stats", 4))}
+    cov = np.zeros(L + 1, np.uint32)
+    reads = np.ascontiguousarray(reads)
+    blocks = np.ascontiguousarray(blocks)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.hostcore_run(C.byref(ann.view), C.byref(cfg), p(reads), C.c_size_t(len(reads)), p(blocks), C.c_size_t(len(blocks)),
+                          p(out["counters"]), p(out["gene_reads"]), p(out["gene_unique"]), p(out["gene_fragments"]), p(out["exon_whole"]),
+                          p(out["exon_fhi"]), p(out["exon_flo"]), p(cov), p(out["bytes"]), p(out["stats"]))
+    assert rc == 0
+    # combine_exon_kernel's carry-free fold and the coverage scan, in numpy
+    hi, lo = out["exon_fhi"], out["exon_flo"]
+    mid = hi + (lo >> np.uint64(32))
+    res = api.Results(G, E, L)
+    res.counters = out["counters"]
+    res.gene_reads, res.gene_unique, res.gene_fragments = out["gene_reads"], out["gene_unique"], out["gene_fragments"]
+    res.exon_frac = (mid << np.uint64(32)) | (lo & np.uint64(0xffffffff))
+    res.exon_whole = out["exon_whole"] + (mid >> np.uint64(32))
+    res.coverage = np.cumsum(cov, dtype=np.uint32)
+    return res, int(out["bytes"][0]), out["stats"]
+
+
+def run_oracle(api, lib, ann, reads, blocks, cfg):
+    ctx = api.Backend(lib).create(cfg)
+    ctx.set_annotation(ann)
+    ctx.submit(reads, blocks)
+    res = ctx.finalize()
+    nbytes = ctx.algorithmic_bytes()
+    ctx.close()
+    return res, nbytes
+
+
+def assert_same(api, got, want, what):
+    skip = {api.COUNTER_INDEX["Fragment Candidates"]}
+    bad = [(api.COUNTER_NAMES[i], int(got.counters[i]), int(want.counters[i])) for i in range(len(api.COUNTER_NAMES))
+           if got.counters[i] != want.counters[i] and i not in skip]
+    assert not bad, f"{what}: counters differ: {bad}"
+    for name in ("gene_reads", "gene_unique", "gene_fragments", "exon_whole", "exon_frac"):
+        x, y = getattr(got, name), getattr(want, name)
+        diff = np.nonzero(x != y)[0]
+        assert diff.size == 0, f"{what}: {name} differs at {diff[:10]}: {x[diff[:10]]} vs {y[diff[:10]]}"
+    n = min(len(got.coverage), len(want.coverage)) - 1
+    diff = np.nonzero(got.coverage[:n] != want.coverage[:n])[0]
+    assert diff.size == 0, f"{what}: coverage differs at {diff[:10]}"
+
+
+@pytest.fixture(scope="module")
+def synth_case(libs, tmp_path_factory):
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    d = str(tmp_path_factory.mktemp("hostcore"))
+    sa = synth.make_annotation(seed=101, n_genes=400, contig_names=["chr1", "chr2", "chr3", "chrM"],
+                               contig_lens=[40_000_000, 30_000_000, 20_000_000, 16569])
+    synth.write_gtf(sa, os.path.join(d, "a.gtf"))
+    ann = api.Annotation(os.path.join(d, "a.gtf"))
+    sr = synth.simulate_reads(sa, 200000, seed=102)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    return ann, reads, blocks
+
+
+CONFIGS = {
+    "default": dict(),
+    "stranded_fr": dict(strand_mode=1),
+    "stranded_rf": dict(strand_mode=2),
+    "unpaired": dict(unpaired=True),
+    "exclude_chimeric": dict(exclude_chimeric=True),
+    "loose": dict(mapq=3, mismatches=2, chimeric_distance=1000),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_record_logic_matches_oracle_on_synthetic_records(libs, synth_case, name):
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    cfg = lambda: api.make_config(max_records=len(reads), **CONFIGS[name])
+    want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+    got, got_bytes, stats = run_hostcore(api, ann, reads, blocks, cfg())
+    assert_same(api, got, want, name)
+    assert got_bytes == want_bytes
+    assert want.counter("Exonic Reads") > 50000 and want.gene_reads.sum() > 50000
+    assert stats[0] > 0, "the staged-slice look-up must be exercised"
+
+
+def test_record_logic_filter_tags_aux_bits_and_unsorted_input(libs, synth_case):
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    r = reads.copy()
+    rng = np.random.default_rng(5)
+    r["filter_mask"] = (rng.random(len(r)) < 0.05) * rng.integers(1, 4, len(r))
+    r["aux"] |= ((rng.random(len(r)) < 0.01) * 0x08).astype(np.uint8)     # tid out of range
+    r["aux"] |= ((rng.random(len(r)) < 0.02) * 0x10).astype(np.uint8)     # contig already dropped
+    r["contig"][rng.random(len(r)) < 0.01] = -1
+    r = r[rng.permutation(len(r))]                                        # tiles mix contigs and far-apart coordinates
+    cfg = lambda: api.make_config(n_filter_tags=2, max_records=len(r))
+    got, _, stats = run_hostcore(api, ann, r, blocks, cfg())
+    assert stats[1] > 0, "the 1 kb table look-up must be exercised"
+    # the oracle's sliding window drops features behind the stream position: only order-free tables compare on shuffled input
+    want_sorted, _ = run_oracle(api, libs["oracle"], ann, r[np.argsort(r, order=["contig", "pos"], kind="stable")], blocks, cfg())
+    got_sorted, got_bytes, _ = run_hostcore(api, ann, r[np.argsort(r, order=["contig", "pos"], kind="stable")], blocks, cfg())
+    assert_same(api, got_sorted, want_sorted, "filter tags, sorted")
+    # the data-parallel path is order-free: shuffled input gives the sorted answer
+    assert_same(api, got, got_sorted, "shuffled vs sorted")
+
+
+def test_dense_overlapping_annotation_and_edge_blocks(libs, tmp_path):
+    """Hand-made annotation with nested / abutting / identical exons of several genes on both strands, a ribosomal gene and
+    an exon ending at a bucket boundary; reads whose blocks start or end exactly on every cut, zero-length and overhanging
+    blocks, blocks beyond the last feature and before the first."""
+    api = libs["api"]
+    gtf = tmp_path / "dense.gtf"
+    rows = []
+
+    def gene(gid, start, end, strand, exons, ttype="protein_coding"):
+        rows.append(f'chr1\tt\tgene\t{start}\t{end}\t.\t{strand}\t.\tgene_id "{gid}"; transcript_id "{gid}"; gene_type "{ttype}"; gene_name "{gid}"; transcript_type "{ttype}";')
+        for k, (s, e) in enumerate(exons):
+            rows.append(f'chr1\tt\texon\t{s}\t{e}\t.\t{strand}\t.\tgene_id "{gid}"; transcript_id "{gid}"; gene_type "{ttype}"; gene_name "{gid}"; transcript_type "{ttype}"; exon_id "{gid}_{k}";')
+
+    gene("A", 1000, 5000, "+", [(1000, 1200), (2000, 2100), (4000, 5000)])
+    gene("B", 1100, 2050, "-", [(1100, 1200), (2000, 2050)])
+    gene("C", 1000, 1200, "+", [(1000, 1200)])                   # identical to A's first exon
+    gene("D", 2047, 2049, "+", [(2047, 2049)])                   # tiny exon across the 2048 bucket boundary
+    gene("R", 3000, 3500, "+", [(3000, 3500)], ttype="rRNA")
+    gene("E", 4500, 4800, "-", [(4500, 4600), (4601, 4800)])      # abutting exons
+    gene("F", 900000, 900500, ".", [(900000, 900500)])
+    gtf.write_text("\n".join(rows) + "\n")
+    ann = api.Annotation(str(gtf))
+    cuts = sorted({c for g in [(1000, 1200), (2000, 2100), (4000, 5000), (1100, 1200), (2000, 2050), (2047, 2049), (3000, 3500),
+                               (4500, 4600), (4601, 4800), (900000, 900500), (1000, 5000), (1100, 2050)] for c in (g[0], g[1], g[1] + 1)})
+    recs, blks = [], []
+    name = 1
+
+    def add(block_list, flag=99, nm=0):
+        nonlocal name
+        off = len(blks)
+        blks.extend(block_list)
+        pos = block_list[0][0] - 1 if block_list else 10
+        end = (block_list[-1][0] - 1 + block_list[-1][1]) if block_list else pos + 1
+        recs.append((pos, pos + 100, end, 200, 100, nm, flag, 255, 0x01, 0, 0, 0, name, off, len(block_list), 0))
+        name += 1
+
+    for c in cuts:
+        for d in (-2, -1, 0, 1):
+            for ln in (0, 1, 2, 50, 101, 1000):
+                if c + d >= 1:
+                    add([(c + d, ln)])
+                    add([(c + d, ln)], flag=147)
+            if c + d >= 1:
+                add([(c + d, 30), (c + d + 900, 30)])                                  # second block usually beyond the first's window
+                add([(max(1, c + d - 60), 40), (c + d, 40), (c + d + 2000, 20)], nm=7)  # three blocks, low quality
+    add([(1, 10)]); add([(5000000, 100)]); add([(899990, 20)]); add([(900490, 20)])
+    reads = np.array(recs, dtype=api.READ_DTYPE)
+    blocks = np.array(blks, dtype=api.BLOCK_DTYPE)
+    order = np.argsort(reads["pos"], kind="stable")
+    reads = reads[order]
+    for mode in (0, 1, 2):
+        cfg = lambda: api.make_config(strand_mode=mode, max_records=len(reads))
+        want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+        got, got_bytes, _ = run_hostcore(api, ann, reads, blocks, cfg())
+        assert_same(api, got, want, f"dense annotation, strand mode {mode}")
+        assert got_bytes == want_bytes
+        assert want.counter("Ambiguous Reads") > 0 and (mode == 2 or want.counter("rRNA Reads") > 0) and want.counter("Exonic Reads") > 0
