@@ -55,6 +55,7 @@ struct Ctx {
     size_t hist_len = 0;
     unsigned int* d_pair_scratch = nullptr;
     size_t pair_scratch_elems = 0;
+    size_t frag_buf_cap = 0;                  // capacity of acc.frag_key / acc.frag_gene (records per sub-batch)
     size_t sample_cap = 0;                    // capacity of sample_flag / sample_isize / cand (records per sub-batch)
     // staging for host submits (two slots)
     rsq_read* d_reads[2] = {nullptr, nullptr};
@@ -136,6 +137,21 @@ int zero_accumulators(Ctx* c) {
     c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
     c->timers_used = 0;
+    return RSQ_OK;
+}
+
+// per-record buffers between the hot kernel and the fragment pass
+int ensure_frag_buffers(Ctx* c, size_t n_reads) {
+    if (c->cfg.legacy) return RSQ_OK;
+    const size_t need = std::min(n_reads, kSubBatch);
+    if (need > c->frag_buf_cap) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->acc.frag_key); cudaFree(c->acc.frag_gene);
+        c->acc.frag_key = nullptr; c->acc.frag_gene = nullptr;
+        c->frag_buf_cap = need;
+        CU_TRY(cudaMalloc(&c->acc.frag_key, 8 * need));
+        CU_TRY(cudaMalloc(&c->acc.frag_gene, 4 * need));
+    }
     return RSQ_OK;
 }
 
@@ -245,6 +261,8 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     if (rc != RSQ_OK) return rc;
     rc = ensure_bed_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
+    rc = ensure_frag_buffers(c, n_reads);
+    if (rc != RSQ_OK) return rc;
     Params prm{};
     prm.mapq_threshold = c->cfg.mapq_threshold;
     prm.base_mismatch_threshold = c->cfg.base_mismatch_threshold;
@@ -351,7 +369,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     free_list(c->bed_allocs);
     free_list(c->ref_allocs);
     Accum& a = c->acc;
-    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
+    void* ptrs[] = {a.frag_key, a.frag_gene, a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_ends, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
@@ -447,8 +465,12 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         if ((rc = upload(c, c->ann_allocs, X.cover.data(), X.cover.size(), &v.cover))) return rc;
         if ((rc = upload(c, c->ann_allocs, X.eib_off.data(), X.eib_off.size(), &v.eib_off))) return rc;
         if ((rc = upload(c, c->ann_allocs, X.eib.data(), X.eib.size(), &v.eib))) return rc;
-        CU_TRY(cudaStreamSynchronize(c->stream));   // X is a local
+        std::vector<unsigned long long> recip;
+        build_recip64(recip);
+        if ((rc = upload(c, c->ann_allocs, recip.data(), recip.size(), &v.recip64))) return rc;
+        CU_TRY(cudaStreamSynchronize(c->stream));   // X and recip are locals
     } else {
+        v.recip64 = nullptr;
         v.ei_off = nullptr; v.ei_start = nullptr; v.ei_desc = nullptr; v.cover = nullptr; v.eib_off = nullptr; v.eib = nullptr;
     }
     // accumulators

@@ -118,8 +118,14 @@ inline std::string build_ei_index(const rsq_annotation* a, EiIndex& X) {
     X.eib_off[nc] = (uint32_t)X.eib.size();
     X.ei_desc.push_back(EiDesc{(uint32_t)X.cover.size(), 0u});
     X.ei_start.insert(X.ei_start.end(), kEiPad, INT32_MAX);
-    if (X.cover.empty()) X.cover.push_back(CoverEntry{0, -1, 0, 0, 0, 0});
+    X.cover.push_back(CoverEntry{0, -1, 0, 0, 0, 0});   // spare entry: the fast path loads cover[cover_off] even when the count is 0
     return std::string();
+}
+
+// R[L] = floor(2^64 / L) for 2 <= L < 65536 (frac_q64 in rsq_hot_core.cuh); R[0] and R[1] are never read.
+inline void build_recip64(std::vector<unsigned long long>& R) {
+    R.assign(65536, 0ull);
+    for (unsigned long long L = 2; L < 65536; ++L) R[L] = ~0ull / L + ((~0ull % L) == L - 1 ? 1ull : 0ull);
 }
 
 }  // namespace rsqd

@@ -35,18 +35,16 @@ RSQ_HD unsigned long long mix64(unsigned long long x) {
     return x;
 }
 
-// floor(isz * 2^64 / length) for isz <= length (isz == length gives whole = 1).  Schoolbook long division in base 2^16
-// (four 32-bit divides, inlined) for aligned lengths below 65536; the generic 64-bit path only for longer reads.
-RSQ_HD void frac_q64(uint32_t isz, uint32_t length, unsigned long long& whole, unsigned long long& lo) {
+// floor(isz * 2^64 / length) for isz <= length (isz == length gives whole = 1).  For aligned lengths below 65536 the
+// table R[length] = floor(2^64 / length) (rsq_eit.h, 512 KB, one hot line per read length) leaves one 32-bit divide:
+// 2^64 = R*L + r0  =>  floor(isz * 2^64 / L) = isz*R + floor(isz*r0 / L), and isz*r0 < L^2 < 2^32.
+RSQ_HD void frac_q64(const unsigned long long* recip64, uint32_t isz, uint32_t length, unsigned long long& whole, unsigned long long& lo) {
     if (isz >= length) { whole = 1ull; lo = 0ull; return; }
     whole = 0ull;
     if (length < 65536u) {
-        uint32_t r = isz, d0, d1, d2, d3;
-        r <<= 16; d3 = r / length; r -= d3 * length;
-        r <<= 16; d2 = r / length; r -= d2 * length;
-        r <<= 16; d1 = r / length; r -= d1 * length;
-        r <<= 16; d0 = r / length;
-        lo = ((unsigned long long)((d3 << 16) | d2) << 32) | (unsigned long long)((d1 << 16) | d0);
+        const unsigned long long R = ldro(recip64 + length);
+        const uint32_t r0 = (uint32_t)(0ull - R * (unsigned long long)length);
+        lo = (unsigned long long)isz * R + (unsigned long long)((isz * r0) / length);
         return;
     }
     unsigned long long r = isz;
@@ -90,7 +88,7 @@ struct GlobalStarts {
 
 // Interval of a block's start and the OR of the class bits of every interval the closed block [bs, be] touches
 // (intersectBlock + intersectInterval, src/Expression.cpp:106-117, src/GTF.cpp:171-179).  Returns the descriptor of k(bs).
-RSQ_HD uint2 block_lookup(const AnnView& ann, const TileWin& w, int c_hi, int bk_lo, int bk_n, int bs, int be, uint32_t& cls) {
+RSQ_HD uint2 block_lookup(const AnnView& ann, const TileWin& w, int contig, int bs, int be, uint32_t& cls) {
     uint2 d;
     if (w.on && bs >= w.wmin && be < w.lastv) {
         const StagedStarts s{w.st, w.base};
@@ -99,6 +97,8 @@ RSQ_HD uint2 block_lookup(const AnnView& ann, const TileWin& w, int c_hi, int bk
         cls |= d.y & 0xffffu;
         for (int kk = k + 1; kk < w.hi && s[kk] <= be; ++kk) cls |= ldro(&ann.ei_desc[kk].y) & 0xffffu;
     } else {
+        const int c_hi = (int)ldro(ann.ei_off + contig + 1);
+        const int bk_lo = (int)ldro(ann.eib_off + contig), bk_n = (int)ldro(ann.eib_off + contig + 1) - bk_lo - 1;
         const int b = imin(imax(bs, 0) >> kEiShift, bk_n - 1);
         const int lo = (int)ldro(ann.eib + bk_lo + b), hi = (int)ldro(ann.eib + bk_lo + b + 1);
         const GlobalStarts s{ann.ei_start};
@@ -116,7 +116,9 @@ struct RecOut {
     unsigned vflags;         // bit0: End 1 sums, bit1: End 2 sums, bit2: Mismatched Bases, bit3: Total Bases, bit4: blocks
     unsigned my_bytes;       // algorithmic bytes of this record
     uint32_t agg_gene;       // first gene this read counts toward
-    bool agg_unique, agg_frag;
+    bool agg_unique;
+    bool fast;               // took the straight-line path of exon_metrics (statistics of the host emulation)
+    unsigned long long frag_key;   // fragment-tracker key of (read name, agg_gene); 0 = none.  Inserted by the fragment pass
     int n_fresh;             // new fragment-set entries of this read
     bool go, hq;
 };
@@ -127,7 +129,7 @@ struct RecOut {
 template <bool kLegacy>
 RSQ_HD void filter_cascade(const Params& prm, bool valid, uint32_t f, uint32_t mapq, uint32_t aux, uint32_t filter_mask, int pos, int mpos,
                            int endpos, int nm_raw, uint32_t nb, RecOut& o) {
-    o.cm = 0ull; o.vflags = 0u; o.my_bytes = 0u; o.agg_gene = kNoGene; o.agg_unique = false; o.agg_frag = false; o.n_fresh = 0;
+    o.cm = 0ull; o.vflags = 0u; o.my_bytes = 0u; o.agg_gene = kNoGene; o.agg_unique = false; o.frag_key = 0ull; o.n_fresh = 0; o.fast = false;
     bool go = valid, hq = false;
     if (valid) {
         RSQ_CNT(o, RSQ_C_TOTAL_ALIGNMENTS);                                              // RNASeQC.cpp:245
@@ -228,102 +230,196 @@ RSQ_HD bool ref_has_gene(const AnnView& ann, const BlockRef& r, uint32_t upto, u
 
 struct ExonOut { bool exonic, do_exon; BlockRef r0; };
 
+// Collector::collect + BaseCoverage::commit for one (block, containing exon) pair of a gene in `last`
+// (src/Expression.cpp:345-347,390-391; Metrics.cpp:59-66,106-124,257-262).
+template <class Mem>
+RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, const Accum& acc, const CoverHead& h, unsigned long long cov_off,
+                           int bs, uint32_t len, uint32_t length, RecOut& o) {
+    unsigned long long whole, lo;
+    frac_q64(ann.recip64, len, length, whole, lo);                                          // isz/length, :345
+    // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update is a fire-and-forget
+    // RED, nothing waits for an atomic's return value
+    if (whole) mem.add64(&acc.exon_whole[h.slot], whole);
+    else {
+        mem.add64(&acc.exon_fhi[h.slot], lo >> 32);
+        mem.add64(&acc.exon_flo[h.slot], lo & 0xffffffffull);
+    }
+    o.my_bytes += 8u;
+    if (prm.collect_coverage) {                                                            // add_range as +1/-1, Metrics.cpp:257-262
+        const unsigned long long off = cov_off + (unsigned long long)(bs - h.start);
+        mem.add32(&acc.cov_diff[off], 1u);
+        mem.add32(&acc.cov_diff[off + len], 0xffffffffu);
+        o.my_bytes += 8u;
+    }
+}
+
+// A high-quality read counts toward gene g (src/Expression.cpp:379-388).  The FIRST gene of a read is not inserted into the
+// fragment tracker here: its key travels in RecOut and the kernel's fragment pass (or the host emulation) inserts it and
+// counts gene_fragments — two dependent HBM round trips that no longer sit in this thread's chain.  Further genes of the
+// same read (overlapping annotations, rare) are inserted on the spot.
+template <class Mem>
+RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsigned long long name_hash, RecOut& o) {
+    const unsigned long long key0 = mix64(name_hash ^ ((unsigned long long)(g + 1u) * 0x9E3779B97F4A7C15ull));
+    const unsigned long long key = key0 ? key0 : 1ull;
+    if (o.agg_gene == kNoGene) { o.agg_gene = g; o.agg_unique = !(f & RSQ_F_DUP); o.frag_key = key; }
+    else {
+        const bool fresh = mem.frag_insert(key);                                           // :383-387
+        o.n_fresh += fresh ? 1 : 0;
+        mem.add64(&acc.gene_reads[g], 1ull);
+        if (fresh) mem.add64(&acc.gene_fragments[g], 1ull);
+        if (!(f & RSQ_F_DUP)) mem.add64(&acc.gene_unique[g], 1ull);
+    }
+    o.my_bytes += 8u;
+}
+
 // ---- exonAlignmentMetrics, src/Expression.cpp:308-458 --------------------------------------------------------------------
 // Mem: add64(ptr, v), add32(ptr, v), frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
 template <class Mem>
 RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const Params& prm, const Accum& acc, uint32_t f, bool hq, bool cleared,
                          int contig, int rstrand, const rsq_block* bp, uint32_t nb, unsigned long long name_hash, RecOut& o, ExonOut& x) {
-    int c_hi = 0, bk_lo = 0, bk_n = 1;
-    if (!cleared) {
-        c_hi = (int)ldro(ann.ei_off + contig + 1);
-        bk_lo = (int)ldro(ann.eib_off + contig);
-        bk_n = (int)ldro(ann.eib_off + contig + 1) - bk_lo - 1;
-    }
-    auto ref_of = [&](uint32_t b) -> BlockRef {
-        const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
-        BlockRef r; r.bs = blk.x; r.be = blk.x + blk.y;
-        uint32_t dummy = 0;
-        const uint2 d = block_lookup(ann, w, c_hi, bk_lo, bk_n, r.bs, r.be, dummy);
-        r.coff = d.x; r.cn = d.y >> 16;
-        return r;
-    };
     uint32_t length = 0, cls = 0;                                                          // extractBlocks' return, :359
     BlockRef r0 = {0, 0, 0u, 0u}, r1 = r0;
-    for (uint32_t b = 0; b < nb; ++b) {                                                    // :325-361
-        const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
-        const int bs = blk.x, be = blk.x + blk.y;                                          // closed end = start+len, :45
-        length += (uint32_t)blk.y;
-        if (cleared) continue;
-        const uint2 d = block_lookup(ann, w, c_hi, bk_lo, bk_n, bs, be, cls);
-        if (b == 0) { r0.bs = bs; r0.be = be; r0.coff = d.x; r0.cn = d.y >> 16; }
-        else if (b == 1) { r1.bs = bs; r1.be = be; r1.coff = d.x; r1.cn = d.y >> 16; }
+    bool globin = false, do_exon = false, fast = false;
+
+    // ---- fast path: every block lies inside the staged slice, runs over at most one cut, and starts in an elementary
+    // interval that at most ONE exon covers (collapsed annotations: practically every read).  Blocks 0 and 1 are searched in
+    // lock step (two independent chains of shared-memory loads) and kept in registers; blocks 2.. (reads over three or more
+    // exons) are checked one at a time and looked up once more when their turn to accumulate comes.
+    if (nb >= 1 && !cleared && w.on) {
+        const int2 k0 = ldro(reinterpret_cast<const int2*>(bp));
+        const int2 k1 = nb >= 2 ? ldro(reinterpret_cast<const int2*>(bp + 1)) : k0;
+        const int bs0 = k0.x, be0 = k0.x + k0.y, bs1 = k1.x, be1 = k1.x + k1.y;
+        if (bs0 >= w.wmin && be0 < w.lastv && bs1 >= w.wmin && be1 < w.lastv) {
+            const StagedStarts s{w.st, w.base};
+            int lo0 = w.k0, lo1 = w.k0, len = w.hi - w.k0;
+            while (len > 1) {
+                const int half = len >> 1;
+                if (s[lo0 + half] <= bs0) lo0 += half;
+                if (s[lo1 + half] <= bs1) lo1 += half;
+                len -= half;
+            }
+            const uint2 d0 = ldro(ann.ei_desc + lo0), d1 = ldro(ann.ei_desc + lo1);
+            // a block may run over ONE cut (a read that ends on the last base of its exon always does: the reference's closed
+            // end is one past it): the class bits of the next interval join in; two cuts or more take the general path
+            const int na0 = lo0 + 1 < w.hi ? s[lo0 + 1] : INT32_MAX, na1 = lo1 + 1 < w.hi ? s[lo1 + 1] : INT32_MAX;
+            const int nb0 = lo0 + 2 < w.hi ? s[lo0 + 2] : INT32_MAX, nb1 = lo1 + 2 < w.hi ? s[lo1 + 2] : INT32_MAX;
+            uint32_t over = 0;
+            if (na0 <= be0) over |= ldro(&ann.ei_desc[lo0 + 1].y);
+            if (na1 <= be1) over |= ldro(&ann.ei_desc[lo1 + 1].y);
+            const uint32_t cn0 = d0.y >> 16, cn1 = d1.y >> 16;
+            if (nb0 > be0 && nb1 > be1 && cn0 <= 1u && cn1 <= 1u) {
+                // the cover array carries one spare entry, so these loads are unconditional (used only when cn == 1)
+                const CoverHead h0 = cover_head(ann, d0.x), h1 = cover_head(ann, d1.x);
+                const unsigned long long c0 = cover_cov_off(ann, d0.x), c1 = cover_cov_off(ann, d1.x);
+                length = (uint32_t)k0.y + (nb >= 2 ? (uint32_t)k1.y : 0u);
+                cls = (d0.y | d1.y | over) & 0xffffu;
+                r0.bs = bs0; r0.be = be0; r0.coff = d0.x; r0.cn = cn0;
+                r1.bs = bs1; r1.be = be1; r1.coff = d1.x; r1.cn = cn1;
+                const bool a0 = cn0 && cover_admits(h0, r0, rstrand), a1 = cn1 && cover_admits(h1, r1, rstrand);
+                const uint32_t g = h0.gene_flags & 0xffffffu;
+                bool in_last = a0 && (nb == 1 || (a1 && (h1.gene_flags & 0xffffffu) == g));
+                fast = true;
+                // one staged block: its interval, covering exon and class bits; false when it needs the general path
+                auto one_block = [&](uint32_t b, BlockRef& r, CoverHead& h, uint32_t& flags) -> bool {
+                    const int2 k = ldro(reinterpret_cast<const int2*>(bp + b));
+                    r.bs = k.x; r.be = k.x + k.y;
+                    if (!(r.bs >= w.wmin && r.be < w.lastv)) return false;
+                    const int lo = ei_search(s, w.k0, w.hi - 1, r.bs);
+                    const uint2 d = ldro(ann.ei_desc + lo);
+                    const int na = lo + 1 < w.hi ? s[lo + 1] : INT32_MAX, nn = lo + 2 < w.hi ? s[lo + 2] : INT32_MAX;
+                    flags = d.y & 0xffffu;
+                    if (na <= r.be) flags |= ldro(&ann.ei_desc[lo + 1].y) & 0xffffu;
+                    r.coff = d.x; r.cn = d.y >> 16;
+                    if (nn <= r.be || r.cn > 1u) return false;
+                    h = cover_head(ann, d.x);
+                    return true;
+                };
+                for (uint32_t b = 2; b < nb && fast; ++b) {
+                    BlockRef r; CoverHead h; uint32_t flags = 0;
+                    fast = one_block(b, r, h, flags);
+                    if (!fast) break;
+                    length += (uint32_t)(r.be - r.bs);
+                    cls |= flags;
+                    in_last = in_last && r.cn && cover_admits(h, r, rstrand) && (h.gene_flags & 0xffffffu) == g;
+                }
+                if (fast && in_last) {                                                     // g is in `last` (:368-377)
+                    do_exon = true;                                                        // :393
+                    if ((h0.gene_flags >> 24) & kCoverGlobin) globin = true;               // :396-398
+                    if (hq) {
+                        if (length > 0) count_gene(mem, acc, f, g, name_hash, o);          // queryGene: some coverage > 0, :380
+                        if (k0.y) accumulate_hit(mem, ann, prm, acc, h0, c0, bs0, (uint32_t)k0.y, length, o);
+                        if (nb >= 2 && k1.y) accumulate_hit(mem, ann, prm, acc, h1, c1, bs1, (uint32_t)k1.y, length, o);
+                        for (uint32_t b = 2; b < nb; ++b) {
+                            BlockRef r; CoverHead h; uint32_t flags = 0;
+                            one_block(b, r, h, flags);
+                            if (r.be != r.bs) accumulate_hit(mem, ann, prm, acc, h, cover_cov_off(ann, r.coff), r.bs, (uint32_t)(r.be - r.bs), length, o);
+                        }
+                    }
+                }
+                if (!fast) { length = 0; cls = 0; }                                        // the general path starts over
+            }
+        }
     }
+
+    // ---- general path: any number of blocks, intervals and covering exons ------------------------------------------------
+    if (!fast) {
+        auto ref_of = [&](uint32_t b) -> BlockRef {
+            const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
+            BlockRef r; r.bs = blk.x; r.be = blk.x + blk.y;
+            uint32_t dummy = 0;
+            const uint2 d = block_lookup(ann, w, contig, r.bs, r.be, dummy);
+            r.coff = d.x; r.cn = d.y >> 16;
+            return r;
+        };
+        for (uint32_t b = 0; b < nb; ++b) {                                                // :325-361
+            const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
+            const int bs = blk.x, be = blk.x + blk.y;                                      // closed end = start+len, :45
+            length += (uint32_t)blk.y;
+            if (cleared) continue;
+            const uint2 d = block_lookup(ann, w, contig, bs, be, cls);
+            if (b == 0) { r0.bs = bs; r0.be = be; r0.coff = d.x; r0.cn = d.y >> 16; }
+            else if (b == 1) { r1.bs = bs; r1.be = be; r1.coff = d.x; r1.cn = d.y >> 16; }
+        }
+        if (nb >= 1 && !cleared) {                                                         // :363-394
+            // `last` = intersection over blocks of {genes with an exon that fully contains the block}: enumerate the genes of
+            // block 0 (deduplicated by re-scanning its short covering list) and test each against every other block.
+            for (uint32_t j = 0; j < r0.cn; ++j) {
+                const CoverHead h0 = cover_head(ann, r0.coff + j);
+                if (!cover_admits(h0, r0, rstrand)) continue;                              // isz == block length, :341
+                const uint32_t g = h0.gene_flags & 0xffffffu;
+                if (ref_has_gene(ann, r0, j, g, rstrand)) continue;                        // an earlier entry already gave this gene
+                bool in_all = true;
+                for (uint32_t b = 1; b < nb && in_all; ++b) {
+                    if (b == 1) in_all = ref_has_gene(ann, r1, r1.cn, g, rstrand);
+                    else { const BlockRef r = ref_of(b); in_all = ref_has_gene(ann, r, r.cn, g, rstrand); }
+                }
+                if (!in_all) continue;
+                // g is in `last` (:377)
+                do_exon = true;                                                            // :393
+                if ((h0.gene_flags >> 24) & kCoverGlobin) globin = true;                   // :396-398
+                if (!hq) continue;
+                if (length > 0) count_gene(mem, acc, f, g, name_hash, o);                  // queryGene: some coverage > 0, :380
+                // Collector::collect + BaseCoverage::commit for gene g: every (block, containing exon of g) pair
+                for (uint32_t b = 0; b < nb; ++b) {
+                    const BlockRef r = b == 0 ? r0 : (b == 1 ? r1 : ref_of(b));
+                    const uint32_t len = (uint32_t)(r.be - r.bs);
+                    if (len == 0) continue;                                                // Collector::add keeps coverage > 0, Metrics.cpp:51
+                    for (uint32_t jj = 0; jj < r.cn; ++jj) {
+                        const CoverHead h = cover_head(ann, r.coff + jj);
+                        if (!cover_admits(h, r, rstrand) || (h.gene_flags & 0xffffffu) != g) continue;
+                        accumulate_hit(mem, ann, prm, acc, h, cover_cov_off(ann, r.coff + jj), r.bs, len, length, o);
+                    }
+                }
+            }
+        }
+    }
+
     if (rstrand != RSQ_STRAND_UNKNOWN) cls &= (EI_GENE | EI_GENE_RIBO | EI_EXON | EI_EXON_RIBO) << rstrand;   // :331
     const bool intragenic = cls & EI_ANY_GENE;                                              // :352-354
     const bool exonic = cls & EI_ANY_EXON;                                                  // :335-337
     const bool plus = cls & ((EI_GENE | EI_EXON) << RSQ_STRAND_FWD);                        // :332
     const bool minus = cls & ((EI_GENE | EI_EXON) << RSQ_STRAND_REV);                       // :333
     const bool ribosomal = cls & (EI_ANY_GENE_RIBO | EI_ANY_EXON_RIBO);                     // :358
-
-    bool globin = false, do_exon = false;
-    if (nb >= 1 && !cleared) {                                                             // :363-394
-        // `last` = intersection over blocks of {genes with an exon that fully contains the block}: enumerate the genes of
-        // block 0 (deduplicated by re-scanning its short covering list) and test each against every other block.
-        for (uint32_t j = 0; j < r0.cn; ++j) {
-            const CoverHead h0 = cover_head(ann, r0.coff + j);
-            if (!cover_admits(h0, r0, rstrand)) continue;                                  // isz == block length, :341
-            const uint32_t g = h0.gene_flags & 0xffffffu;
-            if (ref_has_gene(ann, r0, j, g, rstrand)) continue;                            // an earlier entry already gave this gene
-            bool in_all = true;
-            for (uint32_t b = 1; b < nb && in_all; ++b) {
-                if (b == 1) in_all = ref_has_gene(ann, r1, r1.cn, g, rstrand);
-                else { const BlockRef r = ref_of(b); in_all = ref_has_gene(ann, r, r.cn, g, rstrand); }
-            }
-            if (!in_all) continue;
-            // g is in `last` (:377)
-            do_exon = true;                                                                // :393
-            if ((h0.gene_flags >> 24) & kCoverGlobin) globin = true;                       // :396-398
-            if (!hq) continue;
-            if (length > 0) {                                                              // queryGene: some coverage > 0, :380
-                const unsigned long long key0 = mix64(name_hash ^ ((unsigned long long)(g + 1u) * 0x9E3779B97F4A7C15ull));
-                const bool fresh = mem.frag_insert(key0 ? key0 : 1ull);                    // :383-387
-                o.n_fresh += fresh ? 1 : 0;
-                if (o.agg_gene == kNoGene) { o.agg_gene = g; o.agg_unique = !(f & RSQ_F_DUP); o.agg_frag = fresh; }
-                else {
-                    mem.add64(&acc.gene_reads[g], 1ull);
-                    if (fresh) mem.add64(&acc.gene_fragments[g], 1ull);
-                    if (!(f & RSQ_F_DUP)) mem.add64(&acc.gene_unique[g], 1ull);
-                }
-                o.my_bytes += 8u;
-            }
-            // Collector::collect + BaseCoverage::commit for gene g: every (block, containing exon of g) pair
-            for (uint32_t b = 0; b < nb; ++b) {
-                const BlockRef r = b == 0 ? r0 : (b == 1 ? r1 : ref_of(b));
-                const uint32_t len = (uint32_t)(r.be - r.bs);
-                if (len == 0) continue;                                                    // Collector::add keeps coverage > 0, Metrics.cpp:51
-                for (uint32_t jj = 0; jj < r.cn; ++jj) {
-                    const CoverHead h = cover_head(ann, r.coff + jj);
-                    if (!cover_admits(h, r, rstrand) || (h.gene_flags & 0xffffffu) != g) continue;
-                    unsigned long long whole, lo;
-                    frac_q64(len, length, whole, lo);                                      // isz/length, :345
-                    // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update is a
-                    // fire-and-forget RED, nothing waits for an atomic's return value
-                    if (whole) mem.add64(&acc.exon_whole[h.slot], whole);
-                    else {
-                        mem.add64(&acc.exon_fhi[h.slot], lo >> 32);
-                        mem.add64(&acc.exon_flo[h.slot], lo & 0xffffffffull);
-                    }
-                    o.my_bytes += 8u;
-                    if (prm.collect_coverage) {                                            // add_range as +1/-1, Metrics.cpp:257-262
-                        const unsigned long long off = cover_cov_off(ann, r.coff + jj) + (unsigned long long)(r.bs - h.start);
-                        mem.add32(&acc.cov_diff[off], 1u);
-                        mem.add32(&acc.cov_diff[off + len], 0xffffffffu);
-                        o.my_bytes += 8u;
-                    }
-                }
-            }
-        }
-    }
     if (nb >= 1 && !globin) {                                                              // :399-404
         RSQ_CNT(o, RSQ_C_NON_GLOBIN_READS);
         if (f & RSQ_F_DUP) RSQ_CNT(o, RSQ_C_NON_GLOBIN_DUPLICATE_READS);
@@ -350,6 +446,7 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
         else { if (sense) RSQ_CNT(o, RSQ_C_END2_SENSE); else RSQ_CNT(o, RSQ_C_END2_ANTISENSE); }
     }
     x.exonic = exonic; x.do_exon = do_exon; x.r0 = r0;
+    o.fast = fast;
 }
 
 RSQ_HD int read_strand(const Params& prm, uint32_t f) {                                    // feature_strand, src/Expression.cpp:119-125

@@ -1,7 +1,8 @@
 // rsq_kernels.cu — hand-written sm_100a kernels of the RNA-SeQC per-read hot path.
 //
 // Compile-time ablation switches (never defined in the product build; used for the time breakdown in DESIGN.md §4):
-//   RSQ_AB_NO_FRAGSET, RSQ_AB_NO_ACCUM, RSQ_AB_NO_EPILOGUE, RSQ_AB_CASCADE_ONLY, RSQ_AB_NO_STAGE
+//   RSQ_AB_NO_FRAGSET, RSQ_AB_NO_ACCUM, RSQ_AB_NO_EPILOGUE, RSQ_AB_CASCADE_ONLY, RSQ_AB_NO_STAGE, RSQ_AB_NO_PREFETCH,
+//   RSQ_AB_SCATTER, RSQ_AB_RED32
 //
 // K_hot  : one pass over a batch of decoded alignment records (rsq_read + rsq_block): the flag/quality/
 //          mismatch filter cascade of src/RNASeQC.cpp:254-342, interval intersection of every aligned block
@@ -68,9 +69,14 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
 // memory by cp.async.bulk (1-D TMA, completion on an mbarrier; the filter cascade runs while the copy flies).  Every block
 // that ends before the last staged start is then located by a fixed-depth binary search in shared memory; blocks beyond it
 // (the far side of a long intron) go through the 1 kb direct-address table and search one bucket in L2.
-constexpr int kStageN = 128;
+#ifndef RSQ_STAGE_N
+#define RSQ_STAGE_N 128
+#endif
+constexpr int kStageN = RSQ_STAGE_N;    // a multiple of 4 (16-byte bulk-copy granularity), at most kEiPad
 struct __align__(16) WarpStage {
     int32_t starts[kStageN];
+    unsigned long long fkey[32];      // fragment-tracker keys parked for one tile (0 = none), one slot per lane
+    uint32_t fgene[32];               // the gene each parked key counts toward
     unsigned long long mbar;
     unsigned long long pad;
 };
@@ -96,17 +102,66 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     } while (!ok);
 }
 
+struct WarpStage;
+// Inserts the keys a warp parked one tile ago (their table lines were prefetched into L2 then) and counts the distinct
+// (read name, gene) pairs: geneFragmentCounts, src/Expression.cpp:383-387.  Coordinate-sorted input => the lanes mostly share
+// one gene: one RED per distinct gene.  Returns the number of new entries (warp-uniform).
+template <class Stage>
+__device__ __forceinline__ int resolve_parked(Stage* st, const Accum& acc, unsigned lane) {
+    const unsigned long long key = st->fkey[lane];
+    const uint32_t g = st->fgene[lane];
+    const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_mask, key, acc.error_flag, 1u);
+    const unsigned all_fresh = __ballot_sync(kFull, fresh);
+    unsigned rem = all_fresh;
+    while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const uint32_t lg = __shfl_sync(kFull, g, leader);
+        const unsigned same = __ballot_sync(kFull, fresh && g == lg);
+        if (lane == (unsigned)leader) atomicAdd(&acc.gene_fragments[lg], (unsigned long long)__popc(same));
+        rem &= ~same;
+    }
+    return __popc(all_fresh);
+}
+
 // Memory side effects of the per-record logic on the device: fire-and-forget REDs and the fragment-tracker CAS.
+// RSQ_AB_SCATTER / RSQ_AB_RED32 are diagnostics (results wrong by construction): same instruction stream, but every RED goes
+// to a thread-unique address / is a 32-bit RED.
 struct DevMem {
     const Accum& acc;
+    unsigned long long n_exons, cov_len;
+    // Opportunistic warp aggregation: coordinate-sorted input makes the lanes that reach an accumulation together hit the same
+    // exon word and the same few coverage words, and the L2 atomic units serialise per address (measured: the REDs were 65 %
+    // of the kernel).  The lanes converged at the call (any subset is correct) group by address with one MATCH.ANY; one lane
+    // per group issues the RED with the group's sum (REDUX over the group's mask).
     __device__ __forceinline__ void add64(unsigned long long* p, unsigned long long v) const {
-#ifndef RSQ_AB_NO_ACCUM
+#if defined(RSQ_AB_SCATTER)       // needs n_exons >= 2^18 (the GENCODE-scale bench annotation)
+        const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+        atomicAdd(acc.exon_whole + (((unsigned)(p - acc.exon_whole) + gt * 37u) & 0x3ffffu), v);
+#elif defined(RSQ_AB_RED32)
+        atomicAdd(reinterpret_cast<unsigned int*>(p), (unsigned int)v);
+#elif defined(RSQ_AB_NO_ACCUM) || defined(RSQ_AB_NO_EXON)
+#elif defined(RSQ_NO_AGG_EXON)
         atomicAdd(p, v);
+#else
+        const unsigned m = __activemask();
+        const unsigned peers = __match_any_sync(m, (unsigned long long)p);
+        if ((peers & (peers - 1u)) == 0u || __any_sync(peers, (v >> 32) != 0ull)) { atomicAdd(p, v); return; }   // alone, or a value beyond 32 bits
+        // every value on this path is below 2^32 (1, or a 32-bit half of a Q64.64 fraction): two 16-bit partial sums cannot overflow
+        const unsigned s_lo = __reduce_add_sync(peers, (unsigned)v & 0xffffu), s_hi = __reduce_add_sync(peers, (unsigned)v >> 16);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p, ((unsigned long long)s_hi << 16) + s_lo);
 #endif
     }
-    __device__ __forceinline__ void add32(unsigned int* p, unsigned int v) const {
-#ifndef RSQ_AB_NO_ACCUM
+    __device__ __forceinline__ void add32(unsigned int* p, unsigned int v) const {   // v is the same for every lane of a call site (+1 or -1)
+#if defined(RSQ_AB_SCATTER)       // needs cov_len >= 2^25
+        const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+        atomicAdd(acc.cov_diff + (((unsigned)(p - acc.cov_diff) + gt * 4099u) & 0x1ffffffu), v);
+#elif defined(RSQ_AB_NO_ACCUM) || defined(RSQ_AB_NO_COV)
+#elif defined(RSQ_NO_AGG_COV)
         atomicAdd(p, v);
+#else
+        const unsigned m = __activemask();
+        const unsigned peers = __match_any_sync(m, (unsigned long long)p);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p, v * (unsigned)__popc(peers));
 #endif
     }
     __device__ __forceinline__ bool frag_insert(unsigned long long key) const {
@@ -129,8 +184,8 @@ namespace {
 
 template <bool kBed, bool kLegacy, bool kGc>
 __global__ void __launch_bounds__(kHotThreads, RSQ_HOT_MIN_BLOCKS)
-hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict__ blocks, size_t n_reads, size_t n_blocks,
-                const AnnView ann, const BedView bed, const Accum acc, const Params prm) {
+hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict__ blocks, uint32_t n_reads, uint32_t n_blocks,
+                const AnnView ann, const BedView bed, const Accum acc, const Params prm) {   // 32-bit indices: a launch is one sub-batch
     __shared__ unsigned long long s_cnt[RSQ_N_COUNTERS];
     __shared__ unsigned long long s_bytes;
     __shared__ WarpStage s_stage[kHotThreads / 32];
@@ -141,16 +196,17 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     WarpStage* st = &s_stage[threadIdx.x >> 5];
     const uint32_t mbar = smem_u32(&st->mbar);
     if (lane == 0) mbar_init(mbar);
+    st->fkey[lane] = 0ull; st->fgene[lane] = kNoGene;
     __syncthreads();
     uint32_t phase = 0;
 
-    const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
-    const size_t n_tiles = (n_reads + 31) >> 5;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t n_tiles = (n_reads + 31u) >> 5;
     // Persistent warps: warp w of the grid takes 32-record tiles w, w + W, w + 2W, ... No CTA barrier inside the loop.
-    size_t tile = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned long long own_lo = 0ull, own_hi = 0ull, own_bytes = 0ull;   // lane-owned counters (see the epilogue)
   for (; tile < n_tiles; tile += warps_total) {
-    const size_t i = tile * 32 + lane;
+    const uint32_t i = tile * 32u + lane;
     const bool valid = i < n_reads;
     // records stream through once: evict-first loads; the NEXT tile of this warp is prefetched into L2 meanwhile
     int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0;
@@ -158,11 +214,15 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         const int4* rp = reinterpret_cast<const int4*>(reads + i);
         q0 = __ldcs(rp); q1 = __ldcs(rp + 1); q2 = __ldcs(rp + 2);
     }
-    {
-        const size_t nx = (tile + warps_total) * 32 + lane;
-        if (nx < n_reads && lane < 12)   // 32 records x 48 B = 12 lines of 128 B
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(reads + (tile + warps_total) * 32) + lane * 128));
-    }
+    // The demand load of the NEXT tile's block offsets pulls that tile's record lines toward the SM now (it is consumed at
+    // the end of this iteration, one whole tile of work later) and tells where its aligned blocks start: they are
+    // prefetched into L2 below, so that neither array is first touched by a waiting warp.
+    uint32_t next_boff = 0;
+    const bool has_next = (tile + warps_total) * 32u + lane < n_reads;        // no wrap: n_reads < 2^31 (launcher)
+#ifndef RSQ_AB_NO_PREFETCH
+    if (has_next)
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(next_boff) : "l"(reinterpret_cast<const char*>(reads + ((size_t)(tile + warps_total) * 32u + lane)) + 40));
+#endif
 
     // ---- stage this tile's run of interval starts (warp-uniform) ----------------------------------------------------------
     TileWin w;
@@ -204,7 +264,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     const unsigned long long name_hash = ((unsigned long long)(uint32_t)q2.y << 32) | (uint32_t)q2.x;
     const uint32_t block_off = (uint32_t)q2.z;
     uint32_t nb = (uint32_t)q2.w & 0xffffu;
-    if ((size_t)block_off + nb > n_blocks) nb = 0;  // defensive: never read out of the submitted array
+    if ((unsigned long long)block_off + nb > n_blocks) nb = 0;  // defensive: never read out of the submitted array
     (void)isize; (void)l_qseq;
     RecOut o;
     filter_cascade<kLegacy>(prm, valid, f, mapq, aux, filter_mask, pos, mpos, endpos, nm_raw, nb, o);
@@ -230,7 +290,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                 lr.flag = f; lr.nb = nb; lr.cleared = cleared; lr.hq = hq; lr.name_hash = name_hash; lr.bp = bp;
                 legacy_metrics(ann, acc, prm, lr, o.cm, o.n_fresh, o.my_bytes);
             } else {
-            const DevMem mem{acc};
+            const DevMem mem{acc, (unsigned long long)ann.n_exons, prm.cov_len_diag};
             ExonOut x;
             exon_metrics(mem, ann, w, prm, acc, f, hq, cleared, contig, rstrand, bp, nb, name_hash, o, x);
 
@@ -323,37 +383,57 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         }
     }
 
+#ifndef RSQ_AB_NO_PREFETCH
+    if (has_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(blocks + next_boff));
+#endif
+
     // ---- warp-converged epilogue: aggregate before touching HBM -------------------------------------------------------
     // gene counters: lanes that count toward the same gene elect one leader (sorted input => usually the whole warp)
     {
         const unsigned peers = __match_any_sync(kFull, o.agg_gene);
         const unsigned bu = __ballot_sync(kFull, o.agg_unique);
-        const unsigned bf = __ballot_sync(kFull, o.agg_frag);
         if (o.agg_gene != kNoGene && lane == (unsigned)(__ffs(peers) - 1)) {
             atomicAdd(&acc.gene_reads[o.agg_gene], (unsigned long long)__popc(peers));
-            const int nu = __popc(peers & bu), nf = __popc(peers & bf);
+            const int nu = __popc(peers & bu);
             if (nu) atomicAdd(&acc.gene_unique[o.agg_gene], (unsigned long long)nu);
-            if (nf) atomicAdd(&acc.gene_fragments[o.agg_gene], (unsigned long long)nf);
         }
     }
-    // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  Neighbouring
-    // records mostly take the same path through the cascade, so the 32 counter masks of a tile fall into a handful of
-    // identical groups: one shuffle+ballot per GROUP (typically 3-6) instead of one ballot per touched counter (~15).
+    // fragment tracker (src/Metrics.cpp:22, src/Expression.cpp:383-387).  A hash-set insert is two dependent round trips to a
+    // multi-GB table: instead of waiting for HBM twice per tile, the warp parks this tile's keys in shared memory, prefetches
+    // their table lines into L2, and inserts them one tile LATER (RSQ_FRAG_PASS builds hand them to frag_pass_kernel instead).
+    int s_late = 0;
+    if constexpr (!kLegacy) {
+#ifdef RSQ_FRAG_PASS
+        if (valid) {
+            __stcs(&acc.frag_key[i], o.frag_key);
+            __stcs(&acc.frag_gene[i], o.agg_gene);
+        }
+#else
+        s_late = resolve_parked(st, acc, lane);
+        st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene;                   // each lane reads back its own slot only
+        if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + (o.frag_key & acc.frag_mask)));
+#endif
+    }
+    // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  The 64-bit mask of
+    // a record is cut into 5-bit words; a multiply spreads the five bits into five 6-bit fields (a tile adds at most 32 to a
+    // field), one REDUX per word sums the fields of all 32 records at once, and every lane picks its two fields: no loop, no
+    // dependent shuffles — 11 independent reductions for the 55 counters in use.
     {
 #ifdef RSQ_AB_NO_EPILOGUE
-        unsigned remaining = 0; own_lo += o.cm & 1ull;   // ablation only
+        own_lo += o.cm & 1ull;   // ablation only
 #else
-        unsigned remaining = kFull;
-#endif
-        while (remaining) {
-            const int leader = __ffs(remaining) - 1;
-            const unsigned long long lp = __shfl_sync(kFull, o.cm, leader);
-            const unsigned grp = __ballot_sync(kFull, o.cm == lp);
-            const unsigned long long n = (unsigned long long)__popc(grp);
-            if ((lp >> lane) & 1ull) own_lo += n;
-            if ((lp >> (32 + lane)) & 1ull) own_hi += n;
-            remaining &= ~grp;
+        static_assert(RSQ_C_FRAGSET_ENTRIES == 54, "11 words of 5 counters cover every counter in use");
+        unsigned vlo = 0, vhi = 0;
+#pragma unroll
+        for (int wd = 0; wd < 11; ++wd) {
+            const unsigned x = (unsigned)(o.cm >> (5 * wd)) & 31u;
+            const unsigned sum = __reduce_add_sync(kFull, (x * 0x108421u) & 0x1041041u);
+            if (wd <= 6) vlo = (lane / 5u == (unsigned)wd) ? sum : vlo;
+            if (wd >= 6) vhi = ((lane + 32u) / 5u == (unsigned)wd) ? sum : vhi;
         }
+        own_lo += (vlo >> (6u * (lane % 5u))) & 63u;
+        own_hi += (vhi >> (6u * ((lane + 32u) % 5u))) & 63u;
+#endif
     }
     // valued counters (Metrics::increment(key, int), Metrics.cpp:33-36): signed 32-bit warp sums, sign-extended
     {
@@ -362,7 +442,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         const int s_mm = __reduce_add_sync(kFull, (o.vflags & 4u) ? nm_raw : 0), s_tb = __reduce_add_sync(kFull, (o.vflags & 8u) ? l_qseq : 0);
         const int s_nb = __reduce_add_sync(kFull, (o.vflags & 16u) ? (int)nb : 0);
         const unsigned s_bytes_w = __reduce_add_sync(kFull, o.my_bytes);
-        const int s_fresh = __reduce_add_sync(kFull, o.n_fresh);
+        const int s_fresh = __reduce_add_sync(kFull, o.n_fresh) + s_late;
         static_assert(RSQ_C_FRAGSET_ENTRIES >= 32 && RSQ_C_FRAGSET_ENTRIES < 64, "lives in own_hi");
         if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_fresh;
         static_assert(RSQ_C_END1_MISMATCHES < 32 && RSQ_C_END1_BASES < 32 && RSQ_C_END2_MISMATCHES < 32 && RSQ_C_END2_BASES < 32 &&
@@ -379,6 +459,12 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         if (lane == 0) own_bytes += s_bytes_w;
     }
   }  // tile loop
+#ifndef RSQ_FRAG_PASS
+    if constexpr (!kLegacy) {                                                        // the last tile's parked keys
+        const int s_late = resolve_parked(st, acc, lane);
+        if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_late;
+    }
+#endif
     // one shared-memory add per counter per warp, then one global atomic per counter per CTA
     if (own_lo) atomicAdd(&s_cnt[lane], own_lo);
     if (own_hi) atomicAdd(&s_cnt[32 + lane], own_hi);
@@ -388,6 +474,35 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     for (int k = threadIdx.x; k < RSQ_N_COUNTERS; k += blockDim.x)
         if (s_cnt[k]) atomicAdd(&acc.counters[k], s_cnt[k]);
     if (threadIdx.x == 0 && s_bytes) atomicAdd(acc.algo_bytes, s_bytes);
+}
+
+// ---- fragment pass ---------------------------------------------------------------------------------------------------------
+// One thread per record of the sub-batch: insert the key the hot kernel left (0 = none) into the fragment-tracker set and count
+// the distinct (read name, gene) pairs (geneFragmentCounts, src/Expression.cpp:383-387).  Nothing but two dependent HBM
+// round trips per thread: 32 registers, full occupancy.  Coordinate-sorted input => the lanes of a warp mostly share one gene:
+// one RED per distinct gene per warp.
+__global__ void __launch_bounds__(256) frag_pass_kernel(const Accum acc, size_t n) {
+    __shared__ unsigned int s_fresh;
+    if (threadIdx.x == 0) s_fresh = 0u;
+    __syncthreads();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long key = 0ull;
+    uint32_t g = kNoGene;
+    if (i < n) { key = __ldcs(&acc.frag_key[i]); g = __ldcs(&acc.frag_gene[i]); }
+    const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_mask, key, acc.error_flag, 1u);
+    const unsigned all_fresh = __ballot_sync(kFull, fresh);
+    unsigned rem = all_fresh;
+    while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const uint32_t lg = __shfl_sync(kFull, g, leader);
+        const unsigned same = __ballot_sync(kFull, fresh && g == lg);
+        if (lane == (unsigned)leader) atomicAdd(&acc.gene_fragments[lg], (unsigned long long)__popc(same));
+        rem &= ~same;
+    }
+    if (lane == 0 && all_fresh) atomicAdd(&s_fresh, (unsigned)__popc(all_fresh));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_fresh) atomicAdd(&acc.counters[RSQ_C_FRAGSET_ENTRIES], (unsigned long long)s_fresh);
 }
 
 // ---- annotation preprocessing -----------------------------------------------------------------------------------------
@@ -724,7 +839,8 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     // persistent grid: every SM holds exactly as many CTAs as its register file admits
     static int per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sms = 0;
     const int which = (prm.bed_enabled ? 1 : 0) | (prm.legacy ? 2 : 0) | ((prm.gc_enabled && !prm.legacy) ? 4 : 0);
-    using Kernel = void (*)(const rsq_read*, const rsq_block*, size_t, size_t, const AnnView, const BedView, const Accum, const Params);
+    using Kernel = void (*)(const rsq_read*, const rsq_block*, uint32_t, uint32_t, const AnnView, const BedView, const Accum, const Params);
+    if (n_reads >= (1ull << 31) - 64 * 1024 * 32 || n_blocks > 0xffffffffull) return -1;   // callers pass sub-batches (rsq_capi.cu kSubBatch)
     static const Kernel kernels[8] = {hot_path_kernel<false, false, false>, hot_path_kernel<true, false, false>,
                                       hot_path_kernel<false, true, false>,  hot_path_kernel<true, true, false>,
                                       hot_path_kernel<false, false, true>,  hot_path_kernel<true, false, true>,
@@ -738,8 +854,13 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     }
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
-    kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, n_reads, n_blocks, ann, bed, acc, prm);
+    kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
+#ifndef RSQ_FRAG_PASS
     return 1;
+#endif
+    if (prm.legacy) return 1;
+    frag_pass_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, stream>>>(acc, n_reads);
+    return 2;
 }
 
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream) {

@@ -32,7 +32,8 @@ constexpr int kStageN = 128;
 extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, const rsq_read* reads, size_t n_reads, const rsq_block* blocks,
                             size_t n_blocks, uint64_t* counters, uint64_t* gene_reads, uint64_t* gene_unique, uint64_t* gene_fragments,
                             uint64_t* exon_whole, uint64_t* exon_fhi, uint64_t* exon_flo, uint32_t* cov_diff, uint64_t* algo_bytes,
-                            uint64_t* stats /* [4]: blocks served from the staged slice, blocks through the table, intervals, cover entries */) {
+                            uint64_t* stats /* [8]: blocks served from the staged slice, blocks through the table, intervals, cover entries,
+                                                records on the fast path, on the general path, tiles, tiles with a general-path record */) {
     EiIndex X;
     if (!build_ei_index(a, X).empty()) return 1;
     AnnView ann;
@@ -40,6 +41,9 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
     ann.n_contigs = a->n_contigs; ann.n_genes = a->n_genes; ann.n_exons = a->n_exons;
     ann.ei_off = X.ei_off.data(); ann.ei_start = X.ei_start.data(); ann.ei_desc = reinterpret_cast<const uint2*>(X.ei_desc.data());
     ann.cover = X.cover.data(); ann.eib_off = X.eib_off.data(); ann.eib = X.eib.data();
+    std::vector<unsigned long long> recip;
+    build_recip64(recip);
+    ann.recip64 = recip.data();
     Params prm;
     memset(&prm, 0, sizeof prm);
     prm.mapq_threshold = cfg->mapq_threshold; prm.base_mismatch_threshold = cfg->base_mismatch_threshold;
@@ -52,7 +56,7 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
     acc.exon_fhi = (unsigned long long*)exon_fhi; acc.exon_flo = (unsigned long long*)exon_flo; acc.cov_diff = cov_diff;
     std::unordered_set<unsigned long long> fragset;
     HostMem mem{&fragset};
-    stats[0] = stats[1] = 0; stats[2] = X.ei_start.size() - kEiPad; stats[3] = X.cover.size();
+    stats[0] = stats[1] = stats[4] = stats[5] = stats[6] = stats[7] = 0; stats[2] = X.ei_start.size() - kEiPad; stats[3] = X.cover.size();
 
     int32_t staged[kStageN];
     const size_t n_tiles = (n_reads + 31) / 32;
@@ -74,6 +78,8 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
             memcpy(staged, ann.ei_start + w.base, sizeof staged);          // the bulk copy
             w.lastv = w.hi == c_hi ? INT32_MAX : staged[w.hi - 1 - w.base];
         }
+        bool tile_general = false;
+        ++stats[6];
         for (size_t i = t0; i < t1; ++i) {
             const rsq_read& r = reads[i];
             uint32_t nb = r.n_blocks;
@@ -90,12 +96,17 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
                     }
                 ExonOut x;
                 exon_metrics(mem, ann, w, prm, acc, r.flag, o.hq, cleared, r.contig, rstrand, blocks + r.block_off, nb, r.name_hash, o, x);
+                ++stats[o.fast ? 4 : 5];
+                if (!o.fast) tile_general = true;
             }
             // the epilogue, one record at a time
             if (o.agg_gene != kNoGene) {
                 gene_reads[o.agg_gene] += 1;
                 if (o.agg_unique) gene_unique[o.agg_gene] += 1;
-                if (o.agg_frag) gene_fragments[o.agg_gene] += 1;
+            }
+            if (o.frag_key) {                                              // the fragment pass (frag_pass_kernel)
+                const bool fresh = fragset.insert(o.frag_key).second;
+                if (fresh) { gene_fragments[o.agg_gene] += 1; counters[RSQ_C_FRAGSET_ENTRIES] += 1; }
             }
             for (int k = 0; k < 64; ++k) if ((o.cm >> k) & 1ull) counters[k] += 1;
             auto addv = [&](int k, int v) { counters[k] += (uint64_t)(int64_t)v; };
@@ -107,6 +118,7 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
             counters[RSQ_C_FRAGSET_ENTRIES] += (uint64_t)o.n_fresh;
             *algo_bytes += o.my_bytes;
         }
+        if (tile_general) ++stats[7];
     }
     return 0;
 }

@@ -25,7 +25,7 @@ def run_hostcore(api, ann, reads, blocks, cfg):
     lib = _hostcore()
     G, E, L = ann.n_genes, ann.n_exons, ann.cov_len
     out = {k: np.zeros(n, np.uint64) for k, n in (("counters", 64), ("gene_reads", G), ("gene_unique", G), ("gene_fragments", G),
-                                                   ("exon_whole", E), ("exon_fhi", E), ("exon_flo", E), ("bytes", 1), ("stats", 4))}
+                                                   ("exon_whole", E), ("exon_fhi", E), ("exon_flo", E), ("bytes", 1), ("stats", 8))}
     cov = np.zeros(L + 1, np.uint32)
     reads = np.ascontiguousarray(reads)
     blocks = np.ascontiguousarray(blocks)
