@@ -55,7 +55,6 @@ struct Ctx {
     size_t hist_len = 0;
     unsigned int* d_pair_scratch = nullptr;
     size_t pair_scratch_elems = 0;
-    size_t frag_buf_cap = 0;                  // capacity of acc.frag_key / acc.frag_gene (records per sub-batch)
     size_t sample_cap = 0;                    // capacity of sample_flag / sample_isize / cand (records per sub-batch)
     // staging for host submits (two slots)
     rsq_read* d_reads[2] = {nullptr, nullptr};
@@ -78,7 +77,11 @@ struct Ctx {
     double kernel_ms = 0.0;
 };
 
-constexpr size_t kSubBatch = 1u << 24;   // records per hot-kernel launch (bounds the BED candidate buffers)
+constexpr size_t kSubBatch = 1u << 24;   // records per hot-kernel launch with the BED / GC samplers on (bounds their candidate buffers)
+#ifndef RSQ_PLAIN_SUB_BATCH_LOG2
+#define RSQ_PLAIN_SUB_BATCH_LOG2 27
+#endif
+constexpr size_t kSubBatchPlain = (size_t)1 << RSQ_PLAIN_SUB_BATCH_LOG2;   // without them: fewer launches, fewer kernel tails
 
 #define CU_TRY(expr)                                                                                      \
     do {                                                                                                  \
@@ -137,21 +140,6 @@ int zero_accumulators(Ctx* c) {
     c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
     c->timers_used = 0;
-    return RSQ_OK;
-}
-
-// per-record buffers between the hot kernel and the fragment pass
-int ensure_frag_buffers(Ctx* c, size_t n_reads) {
-    if (c->cfg.legacy) return RSQ_OK;
-    const size_t need = std::min(n_reads, kSubBatch);
-    if (need > c->frag_buf_cap) {
-        CU_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(c->acc.frag_key); cudaFree(c->acc.frag_gene);
-        c->acc.frag_key = nullptr; c->acc.frag_gene = nullptr;
-        c->frag_buf_cap = need;
-        CU_TRY(cudaMalloc(&c->acc.frag_key, 8 * need));
-        CU_TRY(cudaMalloc(&c->acc.frag_gene, 4 * need));
-    }
     return RSQ_OK;
 }
 
@@ -261,8 +249,6 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     if (rc != RSQ_OK) return rc;
     rc = ensure_bed_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
-    rc = ensure_frag_buffers(c, n_reads);
-    if (rc != RSQ_OK) return rc;
     Params prm{};
     prm.mapq_threshold = c->cfg.mapq_threshold;
     prm.base_mismatch_threshold = c->cfg.base_mismatch_threshold;
@@ -297,8 +283,9 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     }
     auto& tm = c->timers[c->timers_used++];
     CU_TRY(cudaEventRecord(tm.first, c->stream));
-    for (size_t base = 0; base < n_reads; base += kSubBatch) {
-        const size_t n = std::min(kSubBatch, n_reads - base);
+    const size_t sub = (prm.bed_enabled || prm.gc_enabled) ? kSubBatch : kSubBatchPlain;
+    for (size_t base = 0; base < n_reads; base += sub) {
+        const size_t n = std::min(sub, n_reads - base);
         rc = ensure_frag_capacity(c, n);
         if (rc != RSQ_OK) return rc;
         prm.record_base = c->records_submitted + base;
@@ -369,7 +356,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     free_list(c->bed_allocs);
     free_list(c->ref_allocs);
     Accum& a = c->acc;
-    void* ptrs[] = {a.frag_key, a.frag_gene, a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
+    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_ends, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],

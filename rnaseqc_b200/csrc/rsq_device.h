@@ -111,8 +111,6 @@ struct Accum {
     unsigned int*       cov_diff;        // [cov_len+1] coverage difference array (wrapping u32)
     unsigned long long* frag_set;        // fragment-tracker hash set (open addressing), 0 = empty
     unsigned long long  frag_mask;       // capacity-1
-    unsigned long long* frag_key;        // [records per sub-batch] key of (read name, first gene counted) or 0: the hot kernel
-    uint32_t*           frag_gene;       //   writes them, the fragment pass inserts them and counts gene_fragments
     unsigned long long* algo_bytes;      // [1]
     unsigned int*       error_flag;      // [1] bit0: fragment set full, bit1: pair table full, bit2: candidate list full
     // fragment-size sampler (BED mode)

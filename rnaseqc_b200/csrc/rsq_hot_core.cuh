@@ -118,7 +118,7 @@ struct RecOut {
     uint32_t agg_gene;       // first gene this read counts toward
     bool agg_unique;
     bool fast;               // took the straight-line path of exon_metrics (statistics of the host emulation)
-    unsigned long long frag_key;   // fragment-tracker key of (read name, agg_gene); 0 = none.  Inserted by the fragment pass
+    unsigned long long frag_key;   // fragment-tracker key of (read name, agg_gene); 0 = none.  Inserted one tile later
     int n_fresh;             // new fragment-set entries of this read
     bool go, hq;
 };
@@ -246,17 +246,15 @@ RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, cons
     }
     o.my_bytes += 8u;
     if (prm.collect_coverage) {                                                            // add_range as +1/-1, Metrics.cpp:257-262
-        const unsigned long long off = cov_off + (unsigned long long)(bs - h.start);
-        mem.add32(&acc.cov_diff[off], 1u);
-        mem.add32(&acc.cov_diff[off + len], 0xffffffffu);
+        mem.cov_range(&acc.cov_diff[cov_off + (unsigned long long)(bs - h.start)], len);   // +1 at the first base, -1 behind the last
         o.my_bytes += 8u;
     }
 }
 
 // A high-quality read counts toward gene g (src/Expression.cpp:379-388).  The FIRST gene of a read is not inserted into the
-// fragment tracker here: its key travels in RecOut and the kernel's fragment pass (or the host emulation) inserts it and
-// counts gene_fragments — two dependent HBM round trips that no longer sit in this thread's chain.  Further genes of the
-// same read (overlapping annotations, rare) are inserted on the spot.
+// fragment tracker here: its key travels in RecOut; the kernel parks it for one tile while the table line is prefetched
+// into L2 and inserts it then (the host emulation inserts it right away) — two dependent HBM round trips that no longer sit
+// in this thread's chain.  Further genes of the same read (overlapping annotations, rare) are inserted on the spot.
 template <class Mem>
 RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsigned long long name_hash, RecOut& o) {
     const unsigned long long key0 = mix64(name_hash ^ ((unsigned long long)(g + 1u) * 0x9E3779B97F4A7C15ull));
@@ -273,7 +271,7 @@ RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsig
 }
 
 // ---- exonAlignmentMetrics, src/Expression.cpp:308-458 --------------------------------------------------------------------
-// Mem: add64(ptr, v), add32(ptr, v), frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
+// Mem: add64(ptr, v), cov_range(ptr, len), frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
 template <class Mem>
 RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const Params& prm, const Accum& acc, uint32_t f, bool hq, bool cleared,
                          int contig, int rstrand, const rsq_block* bp, uint32_t nb, unsigned long long name_hash, RecOut& o, ExonOut& x) {
@@ -362,7 +360,7 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
     }
 
     // ---- general path: any number of blocks, intervals and covering exons ------------------------------------------------
-    if (!fast) {
+    if (!fast) [[unlikely]] {
         auto ref_of = [&](uint32_t b) -> BlockRef {
             const int2 blk = ldro(reinterpret_cast<const int2*>(bp + b));
             BlockRef r; r.bs = blk.x; r.be = blk.x + blk.y;

@@ -102,7 +102,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     } while (!ok);
 }
 
-struct WarpStage;
 // Inserts the keys a warp parked one tile ago (their table lines were prefetched into L2 then) and counts the distinct
 // (read name, gene) pairs: geneFragmentCounts, src/Expression.cpp:383-387.  Coordinate-sorted input => the lanes mostly share
 // one gene: one RED per distinct gene.  Returns the number of new entries (warp-uniform).
@@ -151,17 +150,31 @@ struct DevMem {
         if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p, ((unsigned long long)s_hi << 16) + s_lo);
 #endif
     }
-    __device__ __forceinline__ void add32(unsigned int* p, unsigned int v) const {   // v is the same for every lane of a call site (+1 or -1)
+    // +1 at p, -1 at p + len (add_range as a difference array).  Reads with the same start AND length share both words: one
+    // MATCH.ANY on the pair groups them (RSQ_COV_TWO_MATCHES: one per word, merges more but costs a second match).
+    __device__ __forceinline__ void cov_range(unsigned int* p, unsigned int len) const {
 #if defined(RSQ_AB_SCATTER)       // needs cov_len >= 2^25
         const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-        atomicAdd(acc.cov_diff + (((unsigned)(p - acc.cov_diff) + gt * 4099u) & 0x1ffffffu), v);
+        unsigned int* q = acc.cov_diff + (((unsigned)(p - acc.cov_diff) + gt * 4099u) & 0x1ffffffu);
+        atomicAdd(q, 1u); atomicAdd(q + len, 0xffffffffu);
 #elif defined(RSQ_AB_NO_ACCUM) || defined(RSQ_AB_NO_COV)
 #elif defined(RSQ_NO_AGG_COV)
-        atomicAdd(p, v);
-#else
+        atomicAdd(p, 1u); atomicAdd(p + len, 0xffffffffu);
+#elif defined(RSQ_COV_TWO_MATCHES)
         const unsigned m = __activemask();
-        const unsigned peers = __match_any_sync(m, (unsigned long long)p);
-        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p, v * (unsigned)__popc(peers));
+        const unsigned pa = __match_any_sync(m, (unsigned long long)p), pb = __match_any_sync(m, (unsigned long long)(p + len));
+        const unsigned lane = threadIdx.x & 31u;
+        if (lane == (unsigned)(__ffs(pa) - 1)) atomicAdd(p, (unsigned)__popc(pa));
+        if (lane == (unsigned)(__ffs(pb) - 1)) atomicAdd(p + len, 0u - (unsigned)__popc(pb));
+#else
+        if (len >> 24 || (unsigned long long)(p - acc.cov_diff) >> 40) { atomicAdd(p, 1u); atomicAdd(p + len, 0xffffffffu); return; }   // the pair does not fit one key
+        const unsigned m = __activemask();
+        const unsigned long long key = (unsigned long long)(p - acc.cov_diff) | ((unsigned long long)len << 40);
+        const unsigned peers = __match_any_sync(m, key);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) {
+            const unsigned n = (unsigned)__popc(peers);
+            atomicAdd(p, n); atomicAdd(p + len, 0u - n);
+        }
 #endif
     }
     __device__ __forceinline__ bool frag_insert(unsigned long long key) const {
@@ -400,19 +413,12 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     }
     // fragment tracker (src/Metrics.cpp:22, src/Expression.cpp:383-387).  A hash-set insert is two dependent round trips to a
     // multi-GB table: instead of waiting for HBM twice per tile, the warp parks this tile's keys in shared memory, prefetches
-    // their table lines into L2, and inserts them one tile LATER (RSQ_FRAG_PASS builds hand them to frag_pass_kernel instead).
+    // their table lines into L2, and inserts them one tile LATER.
     int s_late = 0;
     if constexpr (!kLegacy) {
-#ifdef RSQ_FRAG_PASS
-        if (valid) {
-            __stcs(&acc.frag_key[i], o.frag_key);
-            __stcs(&acc.frag_gene[i], o.agg_gene);
-        }
-#else
         s_late = resolve_parked(st, acc, lane);
         st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene;                   // each lane reads back its own slot only
         if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + (o.frag_key & acc.frag_mask)));
-#endif
     }
     // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  The 64-bit mask of
     // a record is cut into 5-bit words; a multiply spreads the five bits into five 6-bit fields (a tile adds at most 32 to a
@@ -459,12 +465,10 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         if (lane == 0) own_bytes += s_bytes_w;
     }
   }  // tile loop
-#ifndef RSQ_FRAG_PASS
     if constexpr (!kLegacy) {                                                        // the last tile's parked keys
         const int s_late = resolve_parked(st, acc, lane);
         if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_late;
     }
-#endif
     // one shared-memory add per counter per warp, then one global atomic per counter per CTA
     if (own_lo) atomicAdd(&s_cnt[lane], own_lo);
     if (own_hi) atomicAdd(&s_cnt[32 + lane], own_hi);
@@ -474,35 +478,6 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     for (int k = threadIdx.x; k < RSQ_N_COUNTERS; k += blockDim.x)
         if (s_cnt[k]) atomicAdd(&acc.counters[k], s_cnt[k]);
     if (threadIdx.x == 0 && s_bytes) atomicAdd(acc.algo_bytes, s_bytes);
-}
-
-// ---- fragment pass ---------------------------------------------------------------------------------------------------------
-// One thread per record of the sub-batch: insert the key the hot kernel left (0 = none) into the fragment-tracker set and count
-// the distinct (read name, gene) pairs (geneFragmentCounts, src/Expression.cpp:383-387).  Nothing but two dependent HBM
-// round trips per thread: 32 registers, full occupancy.  Coordinate-sorted input => the lanes of a warp mostly share one gene:
-// one RED per distinct gene per warp.
-__global__ void __launch_bounds__(256) frag_pass_kernel(const Accum acc, size_t n) {
-    __shared__ unsigned int s_fresh;
-    if (threadIdx.x == 0) s_fresh = 0u;
-    __syncthreads();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long key = 0ull;
-    uint32_t g = kNoGene;
-    if (i < n) { key = __ldcs(&acc.frag_key[i]); g = __ldcs(&acc.frag_gene[i]); }
-    const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_mask, key, acc.error_flag, 1u);
-    const unsigned all_fresh = __ballot_sync(kFull, fresh);
-    unsigned rem = all_fresh;
-    while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const uint32_t lg = __shfl_sync(kFull, g, leader);
-        const unsigned same = __ballot_sync(kFull, fresh && g == lg);
-        if (lane == (unsigned)leader) atomicAdd(&acc.gene_fragments[lg], (unsigned long long)__popc(same));
-        rem &= ~same;
-    }
-    if (lane == 0 && all_fresh) atomicAdd(&s_fresh, (unsigned)__popc(all_fresh));
-    __syncthreads();
-    if (threadIdx.x == 0 && s_fresh) atomicAdd(&acc.counters[RSQ_C_FRAGSET_ENTRIES], (unsigned long long)s_fresh);
 }
 
 // ---- annotation preprocessing -----------------------------------------------------------------------------------------
@@ -855,12 +830,7 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
     kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
-#ifndef RSQ_FRAG_PASS
     return 1;
-#endif
-    if (prm.legacy) return 1;
-    frag_pass_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, stream>>>(acc, n_reads);
-    return 2;
 }
 
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream) {

@@ -23,7 +23,7 @@ namespace {
 struct HostMem {
     std::unordered_set<unsigned long long>* set;
     void add64(unsigned long long* p, unsigned long long v) const { *p += v; }
-    void add32(unsigned int* p, unsigned int v) const { *p += v; }
+    void cov_range(unsigned int* p, unsigned int len) const { p[0] += 1u; p[len] -= 1u; }
     bool frag_insert(unsigned long long key) const { return set->insert(key).second; }
 };
 constexpr int kStageN = 128;
@@ -104,7 +104,7 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
                 gene_reads[o.agg_gene] += 1;
                 if (o.agg_unique) gene_unique[o.agg_gene] += 1;
             }
-            if (o.frag_key) {                                              // the fragment pass (frag_pass_kernel)
+            if (o.frag_key) {                                              // resolve_parked, without the one-tile delay
                 const bool fresh = fragset.insert(o.frag_key).second;
                 if (fresh) { gene_fragments[o.agg_gene] += 1; counters[RSQ_C_FRAGSET_ENTRIES] += 1; }
             }
