@@ -162,17 +162,20 @@ class RsqError(RuntimeError):
 class Results:
     """Host copy of everything rsq_finalize returns."""
 
-    def __init__(self, n_genes: int, n_exons: int, cov_len: int, hist_len: int = 1 << 16, want_coverage: bool = True):
+    def __init__(self, n_genes: int, n_exons: int, cov_len: int, hist_len: int = 1 << 16, want_coverage: bool = True, alloc=None):
+        """alloc(n, dtype) -> zeroed array; default numpy (pageable).  Context.finalize(pinned=True) passes an allocator over
+        rsq_host_alloc, so the device->host copies of the result tables run at PCIe speed instead of through a bounce buffer."""
+        z = alloc or (lambda n, dt: np.zeros(n, dt))
         self.counters = np.zeros(RSQ_N_COUNTERS, np.uint64)
-        self.gene_reads = np.zeros(n_genes, np.uint64)
-        self.gene_unique = np.zeros(n_genes, np.uint64)
-        self.gene_fragments = np.zeros(n_genes, np.uint64)
-        self.exon_whole = np.zeros(n_exons, np.uint64)
-        self.exon_frac = np.zeros(n_exons, np.uint64)
-        self.coverage = np.zeros(cov_len + 1, np.uint32) if want_coverage else None
-        self.fragment_hist = np.zeros(hist_len, np.uint64)
+        self.gene_reads = z(n_genes, np.uint64)
+        self.gene_unique = z(n_genes, np.uint64)
+        self.gene_fragments = z(n_genes, np.uint64)
+        self.exon_whole = z(n_exons, np.uint64)
+        self.exon_frac = z(n_exons, np.uint64)
+        self.coverage = z(cov_len + 1, np.uint32) if want_coverage else None
+        self.fragment_hist = z(hist_len, np.uint64)
         self.fragment_samples_taken = 0
-        self.gc_hist = np.zeros(100, np.uint64)
+        self.gc_hist = z(100, np.uint64)
 
     def struct(self) -> RsqResults:
         r = RsqResults()
@@ -245,6 +248,7 @@ class Context:
     def __init__(self, be: Backend, handle: C.c_void_p, cfg: RsqConfig):
         self.be, self.h, self.cfg = be, handle, cfg
         self.n_genes = self.n_exons = self.cov_len = 0
+        self._pinned = {}          # name -> (pointer, numpy view): page-locked result buffers, reused by every pinned finalize
 
     def _check(self, rc: int) -> None:
         if rc != RSQ_OK:
@@ -252,8 +256,28 @@ class Context:
 
     def close(self) -> None:
         if self.h:
+            for ptr, _ in self._pinned.values():
+                self.be.lib.rsq_host_free(C.c_void_p(ptr))
+            self._pinned = {}
             self.be.lib.rsq_destroy(self.h)
             self.h = None
+
+    def _pinned_array(self, name: str, n: int, dtype) -> np.ndarray:
+        """Page-locked host array owned by this context (rsq_host_alloc), zeroed when first allocated; the SAME memory (with
+        the previous call's content, which rsq_finalize / rsq_coverage_statistics overwrite in full) is handed out again by
+        the next call with this name, so results that must survive the next finalize have to be copied."""
+        nbytes = max(int(n) * np.dtype(dtype).itemsize, 8)
+        have = self._pinned.get(name)
+        if have is None or have[1].nbytes < nbytes:
+            if have is not None:
+                self.be.lib.rsq_host_free(C.c_void_p(have[0]))
+            ptr = self.be.lib.rsq_host_alloc(nbytes)
+            if not ptr:
+                raise MemoryError("rsq_host_alloc failed")
+            have = (ptr, np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(ptr)))
+            have[1][:] = 0
+            self._pinned[name] = have
+        return have[1][:int(n) * np.dtype(dtype).itemsize].view(dtype)
 
     def __del__(self):
         try:
@@ -297,8 +321,15 @@ class Context:
     def reset(self) -> None:
         self._check(self.be.lib.rsq_reset(self.h))
 
-    def finalize(self, want_coverage: bool = True, hist_len: int = 1 << 16) -> Results:
-        res = Results(self.n_genes, self.n_exons, self.cov_len, hist_len, want_coverage)
+    def finalize(self, want_coverage: bool = True, hist_len: int = 1 << 16, pinned: bool = False) -> Results:
+        """pinned=True: the result tables live in page-locked buffers of this context and are overwritten by the next
+        pinned finalize (bench.py; a caller that keeps results copies them)."""
+        if pinned:
+            names = iter(range(1 << 30))
+            res = Results(self.n_genes, self.n_exons, self.cov_len, hist_len, want_coverage,
+                          alloc=lambda n, dt: self._pinned_array(f"fin{next(names)}", n, dt))
+        else:
+            res = Results(self.n_genes, self.n_exons, self.cov_len, hist_len, want_coverage)
         st = res.struct()
         self._check(self.be.lib.rsq_finalize(self.h, C.byref(st)))
         res.counters[:] = np.frombuffer(st.counters, dtype=np.uint64)
@@ -306,13 +337,14 @@ class Context:
         return res
 
     def coverage_statistics(self, ann: "Annotation", mask: int = 500, bias_offset: int = 0, bias_window: int = 100,
-                            bias_gene_length: int = 200) -> dict:
+                            bias_gene_length: int = 200, pinned: bool = False) -> dict:
         """per-gene-line coverage statistics (rsq_coverage_statistics); arrays indexed by gene line (contig, start order)"""
         q = RsqTranscripts()
         host_lib().rsqh_transcripts(ann._h, mask, bias_offset, bias_window, bias_gene_length, C.byref(q))
         n = q.n_genes
-        out = {"gene_mean": np.zeros(n), "gene_std": np.zeros(n), "gene_cv": np.zeros(n), "five_end": np.zeros(n, np.uint64),
-               "three_end": np.zeros(n, np.uint64), "exon_cv": np.zeros(self.n_exons)}
+        z = (lambda name, k, dt: self._pinned_array("cs_" + name, k, dt)) if pinned else (lambda name, k, dt: np.zeros(k, dt))
+        out = {"gene_mean": z("gene_mean", n, np.float64), "gene_std": z("gene_std", n, np.float64), "gene_cv": z("gene_cv", n, np.float64),
+               "five_end": z("five_end", n, np.uint64), "three_end": z("three_end", n, np.uint64), "exon_cv": z("exon_cv", self.n_exons, np.float64)}
         st = RsqCoverageStats()
         st.struct_size = C.sizeof(RsqCoverageStats)
         pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))

@@ -99,3 +99,31 @@ def test_packed_wire_format_roundtrip_through_the_oracle(libs, tmp_path):
     bad = reads.copy()
     bad["nm"][11] = 70000
     assert api.pack_records(bad, blocks) is None
+
+
+def test_pinned_result_buffers_match_plain_ones(libs, tmp_path):
+    """Context.finalize(pinned=True) / coverage_statistics(pinned=True): page-locked buffers from rsq_host_alloc, reused by
+    the next call, same content as the default numpy buffers (CPU twin of what bench.py does on the GPU)."""
+    import numpy as np
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    sa = synth.make_annotation(seed=3, n_genes=120, contig_names=["chr1", "chr2"], contig_lens=[20_000_000, 10_000_000])
+    synth.write_gtf(sa, str(tmp_path / "a.gtf"))
+    ann = api.Annotation(str(tmp_path / "a.gtf"))
+    sr = synth.simulate_reads(sa, 20000, seed=4)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    ctx = api.Backend(libs["oracle"]).create(api.make_config())
+    ctx.set_annotation(ann)
+    ctx.submit(reads, blocks)
+    plain = ctx.finalize(want_coverage=False)
+    pinned = ctx.finalize(want_coverage=False, hist_len=8, pinned=True)
+    for f in ("counters", "gene_reads", "gene_unique", "gene_fragments", "exon_whole", "exon_frac"):
+        assert np.array_equal(getattr(plain, f), getattr(pinned, f)), f
+    c1, c2 = ctx.coverage_statistics(ann), ctx.coverage_statistics(ann, pinned=True)
+    for k in c1:
+        assert np.array_equal(c1[k], c2[k], equal_nan=True), k
+    again = ctx.finalize(want_coverage=False, hist_len=8, pinned=True)
+    assert again.gene_reads.ctypes.data == pinned.gene_reads.ctypes.data      # the same page-locked memory
+    assert plain.gene_reads.sum() > 0
+    ctx.close()
