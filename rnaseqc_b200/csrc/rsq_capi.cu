@@ -12,6 +12,7 @@
 #include "rsq_b200.h"
 #include "rsq_device.h"
 #include "rsq_eit.h"
+#include "rsq_hot_core.cuh"
 
 namespace {
 
@@ -34,6 +35,7 @@ struct Ctx {
     bool have_ref = false;
     RefView ref{};
     const uint8_t* d_ref_present = nullptr;
+    const unsigned long long* d_cascade_lut = nullptr;   // the filter cascade as a table (rsq_hot_core.cuh), uploaded with the annotation
     unsigned long long gc_cap = 0;
     size_t gc_cand_cap = 0;
     // accumulators
@@ -161,29 +163,39 @@ int ensure_bed_buffers(Ctx* c, size_t n_reads) {
 }
 
 // Keeps the fragment-tracker set at most half full.  A record inserts one entry per gene it counts toward, at most
-// `exon_depth` (the deepest stack of overlapping exons in the annotation).  The exact number of entries is a device
-// counter; the host only synchronises to read it when the pessimistic bound (known entries + depth x records in flight)
-// would exceed half the capacity, then grows the table (rehash) if the exact number still does.
-int ensure_frag_capacity(Ctx* c, size_t n) {
-    const unsigned long long add = (unsigned long long)n * c->exon_depth;
-    if (2ull * (c->frag_known + c->frag_pending + add) <= c->frag_cap) { c->frag_pending += add; return RSQ_OK; }
+// `exon_depth` (the deepest stack of overlapping exons in the annotation).  The exact number of entries is a device counter;
+// the host only synchronises to read it when the pessimistic bound (known entries + depth x records in flight) would exceed
+// half of the capacity.  If the exact count still leaves too little room for the whole launch, the launch is cut down to what
+// fits (*n shrinks; the caller comes back with the rest) — and only when not even 4 M records fit is the table grown (rehash).
+// The table is sized 2 x max_records up front (any number of slots, not the next power of two: it is zeroed on every reset;
+// measured: at 1.5 x the longer probe chains cost the hot kernel 10 %, more than the smaller memset saves).
+int reserve_frag_capacity(Ctx* c, size_t* n) {
+    auto fits = [&](unsigned long long known, unsigned long long add) { return 2ull * (known + add) <= c->frag_cap; };
+    unsigned long long add = (unsigned long long)*n * c->exon_depth;
+    if (fits(c->frag_known + c->frag_pending, add)) { c->frag_pending += add; return RSQ_OK; }
     CU_TRY(cudaStreamSynchronize(c->stream));
     unsigned long long exact = 0;
     CU_TRY(cudaMemcpy(&exact, c->acc.counters + RSQ_C_FRAGSET_ENTRIES, 8, cudaMemcpyDeviceToHost));
     c->frag_known = exact;
     c->frag_pending = 0;
-    const unsigned long long need = 2ull * (c->frag_known + add);
-    if (need > c->frag_cap) {
-        const unsigned long long new_cap = next_pow2(need);
-        unsigned long long* nt = nullptr;
-        CU_TRY(cudaMalloc(&nt, 8ull * new_cap));
-        CU_TRY(cudaMemsetAsync(nt, 0, 8ull * new_cap, c->stream));
-        c->launches += launch_rehash(c->acc.frag_set, c->frag_cap, nt, new_cap - 1, c->acc.error_flag, c->stream);
-        CU_TRY(cudaStreamSynchronize(c->stream));
-        cudaFree(c->acc.frag_set);
-        c->acc.frag_set = nt;
-        c->acc.frag_mask = new_cap - 1;
-        c->frag_cap = new_cap;
+    if (!fits(exact, add)) {
+        const unsigned long long room = c->frag_cap / 2 > exact ? c->frag_cap / 2 - exact : 0ull;
+        const size_t n_fit = (size_t)(room / c->exon_depth);
+        if (n_fit >= std::min<size_t>(*n, (size_t)1 << 22)) {
+            *n = std::min(*n, n_fit);
+            add = (unsigned long long)*n * c->exon_depth;
+        } else {
+            const unsigned long long new_cap = (2ull * (exact + add) + 1024) & ~3ull;
+            unsigned long long* nt = nullptr;
+            CU_TRY(cudaMalloc(&nt, 8ull * new_cap));
+            CU_TRY(cudaMemsetAsync(nt, 0, 8ull * new_cap, c->stream));
+            c->launches += launch_rehash(c->acc.frag_set, c->frag_cap, nt, new_cap, c->acc.error_flag, c->stream);
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            cudaFree(c->acc.frag_set);
+            c->acc.frag_set = nt;
+            c->acc.frag_cap = new_cap;
+            c->frag_cap = new_cap;
+        }
     }
     c->frag_pending = add;
     return RSQ_OK;
@@ -263,6 +275,7 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     prm.legacy = c->cfg.legacy;
     prm.gc_enabled = (c->have_ref && !c->cfg.legacy) ? 1u : 0u;
     prm.ref_present = c->d_ref_present;
+    prm.cascade_lut = c->d_cascade_lut;
     prm.cov_len_diag = c->cov_len + 1;
     // timing events around the kernels of this batch
     if (c->timers_used == c->timers.size()) {
@@ -284,9 +297,9 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
     auto& tm = c->timers[c->timers_used++];
     CU_TRY(cudaEventRecord(tm.first, c->stream));
     const size_t sub = (prm.bed_enabled || prm.gc_enabled) ? kSubBatch : kSubBatchPlain;
-    for (size_t base = 0; base < n_reads; base += sub) {
-        const size_t n = std::min(sub, n_reads - base);
-        rc = ensure_frag_capacity(c, n);
+    for (size_t base = 0, n = 0; base < n_reads; base += n) {
+        n = std::min(sub, n_reads - base);
+        rc = reserve_frag_capacity(c, &n);      // may cut the launch down to the room left in the fragment-tracker set
         if (rc != RSQ_OK) return rc;
         prm.record_base = c->records_submitted + base;
         if (prm.bed_enabled) {
@@ -460,6 +473,14 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         v.recip64 = nullptr;
         v.ei_off = nullptr; v.ei_start = nullptr; v.ei_desc = nullptr; v.cover = nullptr; v.eib_off = nullptr; v.eib = nullptr;
     }
+#ifndef RSQ_NO_CASCADE_LUT
+    {   // the filter cascade as a pure function of 17 bits of a record: tabulated once per context
+        std::vector<unsigned long long> lut(kCascadeEntries);
+        for (uint32_t ix = 0; ix < kCascadeEntries; ++ix) lut[ix] = cascade_entry(c->cfg.legacy != 0, c->cfg.exclude_chimeric != 0, c->cfg.unpaired != 0, ix);
+        if ((rc = upload(c, c->ann_allocs, lut.data(), lut.size(), &c->d_cascade_lut))) return rc;
+        CU_TRY(cudaStreamSynchronize(c->stream));   // lut is a local
+    }
+#endif
     // accumulators
     Accum& acc = c->acc;
     CU_TRY(cudaMalloc(&acc.counters, 8 * RSQ_N_COUNTERS));
@@ -474,9 +495,19 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     CU_TRY(cudaMalloc(&c->d_cov, 4ull * (a->cov_len + 1)));
     c->scan_elems = coverage_scan_scratch_elems(a->cov_len + 1);
     CU_TRY(cudaMalloc(&c->d_scan, 4ull * c->scan_elems));
-    c->frag_cap = next_pow2(2ull * (c->cfg.max_records ? c->cfg.max_records : (1ull << 24)));
+    {   // fragment-tracker set: RSQ_FRAG_SLOTS_PER_RECORD_X2 / 2 slots per expected record (default 2.0), any number of slots
+#ifndef RSQ_FRAG_SLOTS_PER_RECORD_X2
+#define RSQ_FRAG_SLOTS_PER_RECORD_X2 4
+#endif
+        const unsigned long long recs = c->cfg.max_records ? c->cfg.max_records : (1ull << 24);
+        unsigned long long cap = std::max<unsigned long long>(recs * RSQ_FRAG_SLOTS_PER_RECORD_X2 / 2, 1ull << 12);
+#ifdef RSQ_FRAG_POW2
+        cap = next_pow2(cap);
+#endif
+        c->frag_cap = (cap + 3) & ~3ull;
+    }
     CU_TRY(cudaMalloc(&acc.frag_set, 8ull * c->frag_cap));
-    acc.frag_mask = c->frag_cap - 1;
+    acc.frag_cap = c->frag_cap;
     CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
     CU_TRY(cudaMalloc(&acc.error_flag, 4));
     c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * c->n_exons + 100ull;   // ... | 100 GC-content bins

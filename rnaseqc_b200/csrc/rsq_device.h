@@ -110,7 +110,7 @@ struct Accum {
     unsigned long long* exon_flo;        // [n_exons] sum of (frac & 0xffffffff)
     unsigned int*       cov_diff;        // [cov_len+1] coverage difference array (wrapping u32)
     unsigned long long* frag_set;        // fragment-tracker hash set (open addressing), 0 = empty
-    unsigned long long  frag_mask;       // capacity-1
+    unsigned long long  frag_cap;        // slots (any number, not a power of two)
     unsigned long long* algo_bytes;      // [1]
     unsigned int*       error_flag;      // [1] bit0: fragment set full, bit1: pair table full, bit2: candidate list full
     // fragment-size sampler (BED mode)
@@ -145,6 +145,7 @@ struct Params {
     uint32_t legacy;                     // --legacy counting rules (rsq_legacy.cuh)
     uint32_t gc_enabled;                 // fragment GC-content sampler (rsq_set_reference)
     const uint8_t* ref_present;          // [n_contigs] Fasta::hasContig (gc_enabled only)
+    const unsigned long long* cascade_lut;   // [2^17] the filter cascade as a table (cascade_entry, rsq_hot_core.cuh); null = compute
     unsigned long long record_base;      // global index of reads[0] in the stream (ordering of fragment samples)
     unsigned long long cov_len_diag;     // coverage array length (RSQ_AB_SCATTER diagnostic build only)
 };
@@ -164,7 +165,7 @@ int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned l
                          cudaStream_t stream);
 size_t coverage_scan_scratch_elems(unsigned long long n);
 int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap, unsigned long long* new_tab,
-                  unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream);
+                  unsigned long long new_cap, unsigned int* error_flag, cudaStream_t stream);
 int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* out, cudaStream_t stream);
 int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* in, cudaStream_t stream);
 int launch_combine_exon(const Accum& acc, uint32_t n_exons, unsigned long long* whole_out, unsigned long long* frac_out, cudaStream_t stream);

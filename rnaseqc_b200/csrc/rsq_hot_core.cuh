@@ -10,8 +10,10 @@
 
 #if defined(__CUDACC__)
 #define RSQ_HD __device__ __forceinline__      // the CUDA build only ever needs the device instantiation
+#define RSQ_HDX __host__ __device__ __forceinline__   // ... except for the pure functions the library's host side calls too
 #else
 #define RSQ_HD inline                          // host emulation (tests/hostcore), plain g++
+#define RSQ_HDX inline
 #endif
 
 namespace rsqd {
@@ -126,78 +128,117 @@ struct RecOut {
 #define RSQ_CNT(o, k) ((o).cm |= 1ull << (k))
 
 // ---- filter cascade, src/RNASeQC.cpp:254-342 ---------------------------------------------------------------------------
-template <bool kLegacy>
+// Everything the cascade reads of a record fits 17 bits: nine flag bits and eight predicates against the run constants.
+// cascade_index packs them; cascade_entry is the cascade as a pure function of that index (and of three run flags), so the
+// kernel can read it from a table built once per context (Params::cascade_lut, 2^17 x 8 bytes) — one load instead of ~170
+// branchy instructions — while the host emulation and the table builder call the very same function.
+enum : uint32_t { CI_PAIRED = 1u << 0, CI_PROPER = 1u << 1, CI_UNMAP = 1u << 2, CI_MUNMAP = 1u << 3, CI_READ1 = 1u << 4, CI_SECONDARY = 1u << 5,
+                  CI_QCFAIL = 1u << 6, CI_DUP = 1u << 7, CI_SUPP = 1u << 8, CI_LOW_MAPQ = 1u << 9, CI_HAS_CH = 1u << 10, CI_CHIMERIC = 1u << 11,
+                  CI_HAS_NM = 1u << 12, CI_NM_OK = 1u << 13, CI_LONG_SPAN = 1u << 14, CI_FILTERED = 1u << 15, CI_TID_OOR = 1u << 16 };
+constexpr uint32_t kCascadeEntries = 1u << 17;
+// entry: counter bits 0..51 | vflags << 56 | (a filter tag fired) << 61 | go << 62 | hq << 63
+constexpr int kCeVflagsShift = 56;
+constexpr unsigned long long kCeTagged = 1ull << 61, kCeGo = 1ull << 62, kCeHq = 1ull << 63, kCeCounterMask = (1ull << 52) - 1;
+
+RSQ_HDX uint32_t cascade_index(const Params& prm, uint32_t f, uint32_t mapq, uint32_t aux, uint32_t filter_mask, int pos, int mpos, int endpos, int nm_raw) {
+    static_assert(RSQ_F_PAIRED == 1 && RSQ_F_PROPER == 2 && RSQ_F_UNMAP == 4 && RSQ_F_MUNMAP == 8 && RSQ_F_READ1 == 0x40 && RSQ_F_SECONDARY == 0x100 &&
+                  RSQ_F_QCFAIL == 0x200 && RSQ_F_DUP == 0x400 && RSQ_F_SUPPLEMENTARY == 0x800, "flag bits move by shifts");
+    uint32_t ix = (f & 0xfu) | ((f >> 2) & 0x10u) | ((f >> 3) & 0x1e0u);
+    if (mapq < prm.mapq_threshold) ix |= CI_LOW_MAPQ;
+    if (aux & RSQ_AUX_CHIMERIC_TAG) ix |= CI_HAS_CH;
+    int d = pos - mpos; d = d < 0 ? -d : d;
+    if ((aux & RSQ_AUX_MATE_OTHER_CONTIG) || d > prm.chimeric_distance || (prm.legacy && (aux & RSQ_AUX_TID_GT_127))) ix |= CI_CHIMERIC;   // :287
+    const bool has_nm = aux & RSQ_AUX_HAS_NM;
+    if (has_nm) ix |= CI_HAS_NM;
+    if ((uint32_t)(has_nm ? nm_raw : 0) <= prm.base_mismatch_threshold) ix |= CI_NM_OK;                                                    // :294,330
+    if ((unsigned)(endpos - pos) > 100000u) ix |= CI_LONG_SPAN;                                                                            // :275-276
+    const uint32_t n_tags = prm.n_filter_tags < 8u ? prm.n_filter_tags : 8u;
+    if (filter_mask & ((1u << n_tags) - 1u)) ix |= CI_FILTERED;                                                                            // :319-328
+    if (aux & RSQ_AUX_TID_OUT_OF_RANGE) ix |= CI_TID_OOR;                                                                                  // :333
+    return ix;
+}
+
+RSQ_HDX unsigned long long cascade_entry(bool legacy, bool exclude_chimeric, bool unpaired, uint32_t ix) {
+    unsigned long long cm = 0ull;
+    unsigned vflags = 0u;
+    bool go = true, hq = false, tagged = false;
+#define CE_CNT(k) (cm |= 1ull << (k))
+    CE_CNT(RSQ_C_TOTAL_ALIGNMENTS);                                                      // RNASeQC.cpp:245
+    if (ix & CI_SECONDARY) CE_CNT(RSQ_C_ALTERNATIVE_ALIGNMENTS);                         // :254
+    if (ix & CI_SUPP) CE_CNT(RSQ_C_SUPPLEMENTARY_ALIGNMENTS);                            // :255
+    else if (ix & CI_QCFAIL) CE_CNT(RSQ_C_FAILED_VENDOR_QC);
+    else if (ix & CI_LOW_MAPQ) CE_CNT(RSQ_C_LOW_MAPPING_QUALITY);
+    const bool has_ch = ix & CI_HAS_CH;
+    if ((ix & CI_SUPP) && !(legacy || has_ch)) {                                         // :258-262
+        CE_CNT(RSQ_C_CHIMERIC_AUTO);
+        if (exclude_chimeric) go = false;
+    }
+    if (ix & (CI_SECONDARY | CI_QCFAIL | CI_SUPP)) go = false;                           // :263
+    if (go) {
+        CE_CNT(RSQ_C_UMVQ);
+        if (!(ix & CI_PAIRED)) CE_CNT(RSQ_C_UNPAIRED_READS);
+        if (ix & CI_UNMAP) go = false;                                                   // :268
+    }
+    if (go) {
+        CE_CNT(RSQ_C_MAPPED_READS);
+        if (ix & CI_DUP) CE_CNT(RSQ_C_MAPPED_DUPLICATE_READS); else CE_CNT(RSQ_C_MAPPED_UNIQUE_READS);
+        if (legacy && (ix & CI_LONG_SPAN)) go = false;                                   // :275-276 LEGACY_MAX_READ_LENGTH
+        if (go && !legacy && has_ch) {                                                   // :279-283
+            if (ix & CI_READ1) CE_CNT(RSQ_C_CHIMERIC_TAG);
+            if (exclude_chimeric) go = false;
+        }
+    }
+    if (go && (ix & CI_PAIRED) && !(ix & CI_MUNMAP)) {                                   // :284-292
+        if (ix & CI_READ1) CE_CNT(RSQ_C_TOTAL_MAPPED_PAIRS);
+        if (ix & CI_CHIMERIC) {
+            if (ix & CI_READ1) CE_CNT(RSQ_C_CHIMERIC_AUTO);
+            if (exclude_chimeric) go = false;
+        }
+    }
+    if (go) {
+        if (ix & CI_HAS_NM) {                                                            // :294-316
+            if (ix & CI_PAIRED) {
+                if (ix & CI_READ1) {
+                    CE_CNT(RSQ_C_END1_MAPPED_READS);
+                    vflags |= 1u;
+                    if (ix & CI_DUP) CE_CNT(RSQ_C_DUPLICATE_PAIRS); else CE_CNT(RSQ_C_UNIQUE_FRAGMENTS);
+                } else {
+                    CE_CNT(RSQ_C_END2_MAPPED_READS);
+                    vflags |= 2u;
+                }
+            }
+            vflags |= 4u;
+        }
+        vflags |= 8u;                                                                    // :317
+        if (ix & CI_FILTERED) { tagged = true; go = false; }                             // :319-328 (the caller adds the tag counters)
+        hq = (ix & CI_NM_OK) && (unpaired || (ix & CI_PROPER)) && !(ix & CI_LOW_MAPQ);   // :330
+        if (ix & CI_TID_OOR) go = false;                                                 // :333-337
+    }
+    if (go) {
+        if (hq) CE_CNT(RSQ_C_HIGH_QUALITY_READS); else CE_CNT(RSQ_C_LOW_QUALITY_READS);  // :340-342
+        CE_CNT(RSQ_C_READS_USED);
+        vflags |= 16u;                                                                   // :360
+    }
+#undef CE_CNT
+    return cm | ((unsigned long long)vflags << kCeVflagsShift) | (tagged ? kCeTagged : 0ull) | (go ? kCeGo : 0ull) | (hq ? kCeHq : 0ull);
+}
+
+// The cascade of one record: table look-up when the context carries one (the CUDA library always does), else computed.
 RSQ_HD void filter_cascade(const Params& prm, bool valid, uint32_t f, uint32_t mapq, uint32_t aux, uint32_t filter_mask, int pos, int mpos,
                            int endpos, int nm_raw, uint32_t nb, RecOut& o) {
     o.cm = 0ull; o.vflags = 0u; o.my_bytes = 0u; o.agg_gene = kNoGene; o.agg_unique = false; o.frag_key = 0ull; o.n_fresh = 0; o.fast = false;
-    bool go = valid, hq = false;
-    if (valid) {
-        RSQ_CNT(o, RSQ_C_TOTAL_ALIGNMENTS);                                              // RNASeQC.cpp:245
-        o.my_bytes = 40u + 8u * nb;
-        if (f & RSQ_F_SECONDARY) RSQ_CNT(o, RSQ_C_ALTERNATIVE_ALIGNMENTS);               // :254
-        if (f & RSQ_F_SUPPLEMENTARY) RSQ_CNT(o, RSQ_C_SUPPLEMENTARY_ALIGNMENTS);         // :255
-        else if (f & RSQ_F_QCFAIL) RSQ_CNT(o, RSQ_C_FAILED_VENDOR_QC);
-        else if (mapq < prm.mapq_threshold) RSQ_CNT(o, RSQ_C_LOW_MAPPING_QUALITY);
-        const bool has_ch = aux & RSQ_AUX_CHIMERIC_TAG;
-        if ((f & RSQ_F_SUPPLEMENTARY) && !(kLegacy || has_ch)) {                          // :258-262
-            RSQ_CNT(o, RSQ_C_CHIMERIC_AUTO);
-            if (prm.exclude_chimeric) go = false;
-        }
-        if (f & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) go = false;      // :263
-        if (go) {
-            RSQ_CNT(o, RSQ_C_UMVQ);
-            if (!(f & RSQ_F_PAIRED)) RSQ_CNT(o, RSQ_C_UNPAIRED_READS);
-            if (f & RSQ_F_UNMAP) go = false;                                             // :268
-        }
-        if (go) {
-            RSQ_CNT(o, RSQ_C_MAPPED_READS);
-            if (f & RSQ_F_DUP) RSQ_CNT(o, RSQ_C_MAPPED_DUPLICATE_READS); else RSQ_CNT(o, RSQ_C_MAPPED_UNIQUE_READS);
-            if (kLegacy && (unsigned)(endpos - pos) > 100000u) go = false;                // :275-276 LEGACY_MAX_READ_LENGTH
-            if (go && !kLegacy && has_ch) {                                               // :279-283
-                if (f & RSQ_F_READ1) RSQ_CNT(o, RSQ_C_CHIMERIC_TAG);
-                if (prm.exclude_chimeric) go = false;
-            }
-        }
-        if (go && (f & RSQ_F_PAIRED) && !(f & RSQ_F_MUNMAP)) {                            // :284-292
-            if (f & RSQ_F_READ1) RSQ_CNT(o, RSQ_C_TOTAL_MAPPED_PAIRS);
-            int d = pos - mpos; d = d < 0 ? -d : d;
-            if ((aux & RSQ_AUX_MATE_OTHER_CONTIG) || d > prm.chimeric_distance || (kLegacy && (aux & RSQ_AUX_TID_GT_127))) {
-                if (f & RSQ_F_READ1) RSQ_CNT(o, RSQ_C_CHIMERIC_AUTO);
-                if (prm.exclude_chimeric) go = false;
-            }
-        }
-        if (go) {
-            int mismatches = 0;
-            if (aux & RSQ_AUX_HAS_NM) {                                                   // :294-316
-                mismatches = nm_raw;
-                if (f & RSQ_F_PAIRED) {
-                    if (f & RSQ_F_READ1) {
-                        RSQ_CNT(o, RSQ_C_END1_MAPPED_READS);
-                        o.vflags |= 1u;
-                        if (f & RSQ_F_DUP) RSQ_CNT(o, RSQ_C_DUPLICATE_PAIRS); else RSQ_CNT(o, RSQ_C_UNIQUE_FRAGMENTS);
-                    } else {
-                        RSQ_CNT(o, RSQ_C_END2_MAPPED_READS);
-                        o.vflags |= 2u;
-                    }
-                }
-                o.vflags |= 4u;
-            }
-            o.vflags |= 8u;                                                               // :317
-            if (filter_mask) {                                                            // :319-328
-                for (uint32_t k = 0; k < prm.n_filter_tags && k < 8; ++k)
-                    if (filter_mask & (1u << k)) { RSQ_CNT(o, RSQ_C_FILTERED_BY_TAG0 + k); go = false; }
-            }
-            hq = (uint32_t)mismatches <= prm.base_mismatch_threshold && (prm.unpaired || (f & RSQ_F_PROPER)) &&
-                 mapq >= prm.mapq_threshold;                                              // :330
-            if (aux & RSQ_AUX_TID_OUT_OF_RANGE) go = false;                               // :333-337
-        }
-        if (go) {
-            if (hq) RSQ_CNT(o, RSQ_C_HIGH_QUALITY_READS); else RSQ_CNT(o, RSQ_C_LOW_QUALITY_READS);   // :340-342
-            RSQ_CNT(o, RSQ_C_READS_USED);
-            o.vflags |= 16u;                                                              // :360
-        }
+    o.go = false; o.hq = false;
+    if (!valid) return;
+    const uint32_t ix = cascade_index(prm, f, mapq, aux, filter_mask, pos, mpos, endpos, nm_raw);
+    const unsigned long long e = prm.cascade_lut ? ldro(prm.cascade_lut + ix) : cascade_entry(prm.legacy != 0, prm.exclude_chimeric != 0, prm.unpaired != 0, ix);
+    o.cm = e & kCeCounterMask;
+    if (e & kCeTagged) {
+        const uint32_t n_tags = prm.n_filter_tags < 8u ? prm.n_filter_tags : 8u;
+        o.cm |= (unsigned long long)(filter_mask & ((1u << n_tags) - 1u)) << RSQ_C_FILTERED_BY_TAG0;
     }
-    o.go = go; o.hq = hq;
+    o.vflags = (unsigned)(e >> kCeVflagsShift) & 31u;
+    o.my_bytes = 40u + 8u * nb;
+    o.go = (e & kCeGo) != 0ull; o.hq = (e & kCeHq) != 0ull;
 }
 
 // A block and the covering-exon list of the interval its start falls into.

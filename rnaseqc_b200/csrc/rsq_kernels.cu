@@ -43,10 +43,13 @@ __device__ __forceinline__ int lower_bound_pmax(const int32_t* __restrict__ pmax
     }
     return lo;
 }
-// Open-addressing insert; returns true when the key was not present.
-__device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab, unsigned long long mask, unsigned long long key,
+// Open-addressing insert; returns true when the key was not present.  The table has ANY capacity (not a power of two: it is
+// zeroed on every reset, so it is sized to 1.5 x the records, not rounded up to the next power): home slot = high half of
+// key x capacity, linear probing with wrap-around.
+__device__ __forceinline__ unsigned long long set_home(unsigned long long key, unsigned long long cap) { return __umul64hi(key, cap); }
+__device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab, unsigned long long cap, unsigned long long key,
                                            unsigned int* err, unsigned int err_bit) {
-    unsigned long long slot = key & mask;
+    unsigned long long slot = set_home(key, cap);
     for (int probe = 0; probe < 4096; ++probe) {
         // plain load first: measured 30 % faster than CAS-first on B200 (an L2 atomic on a missing line is far more
         // expensive than a load, and second mates find their key without any atomic)
@@ -57,7 +60,7 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
             if (cur == 0ull) return true;
             if (cur == key) return false;
         }
-        slot = (slot + 1) & mask;
+        slot = slot + 1 == cap ? 0ull : slot + 1;
     }
     atomicOr(err, err_bit);
     return false;
@@ -70,13 +73,14 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
 // that ends before the last staged start is then located by a fixed-depth binary search in shared memory; blocks beyond it
 // (the far side of a long intron) go through the 1 kb direct-address table and search one bucket in L2.
 #ifndef RSQ_STAGE_N
-#define RSQ_STAGE_N 128
+#define RSQ_STAGE_N 64
 #endif
 constexpr int kStageN = RSQ_STAGE_N;    // a multiple of 4 (16-byte bulk-copy granularity), at most kEiPad
 struct __align__(16) WarpStage {
     int32_t starts[kStageN];
     unsigned long long fkey[32];      // fragment-tracker keys parked for one tile (0 = none), one slot per lane
     uint32_t fgene[32];               // the gene each parked key counts toward
+    uint32_t fpeers[32];              // the lanes of that tile that counted toward the same gene (MATCH.ANY of the epilogue)
     unsigned long long mbar;
     unsigned long long pad;
 };
@@ -109,15 +113,13 @@ template <class Stage>
 __device__ __forceinline__ int resolve_parked(Stage* st, const Accum& acc, unsigned lane) {
     const unsigned long long key = st->fkey[lane];
     const uint32_t g = st->fgene[lane];
-    const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_mask, key, acc.error_flag, 1u);
+    const unsigned peers = st->fpeers[lane];
+    const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_cap, key, acc.error_flag, 1u);
     const unsigned all_fresh = __ballot_sync(kFull, fresh);
-    unsigned rem = all_fresh;
-    while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const uint32_t lg = __shfl_sync(kFull, g, leader);
-        const unsigned same = __ballot_sync(kFull, fresh && g == lg);
-        if (lane == (unsigned)leader) atomicAdd(&acc.gene_fragments[lg], (unsigned long long)__popc(same));
-        rem &= ~same;
+    // the gene groups of that tile are known from its epilogue: the lowest lane of each group adds the group's new entries
+    if (g != kNoGene && lane == (unsigned)(__ffs(peers) - 1)) {
+        const int n = __popc(peers & all_fresh);
+        if (n) atomicAdd(&acc.gene_fragments[g], (unsigned long long)n);
     }
     return __popc(all_fresh);
 }
@@ -181,7 +183,7 @@ struct DevMem {
 #ifdef RSQ_AB_NO_FRAGSET
         return (key & 1ull) != 0;   // ablation only: no hash-set traffic (results are wrong)
 #else
-        return set_insert(acc.frag_set, acc.frag_mask, key, acc.error_flag, 1u);
+        return set_insert(acc.frag_set, acc.frag_cap, key, acc.error_flag, 1u);
 #endif
     }
 };
@@ -209,7 +211,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     WarpStage* st = &s_stage[threadIdx.x >> 5];
     const uint32_t mbar = smem_u32(&st->mbar);
     if (lane == 0) mbar_init(mbar);
-    st->fkey[lane] = 0ull; st->fgene[lane] = kNoGene;
+    st->fkey[lane] = 0ull; st->fgene[lane] = kNoGene; st->fpeers[lane] = 0u;
     __syncthreads();
     uint32_t phase = 0;
 
@@ -221,8 +223,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
   for (; tile < n_tiles; tile += warps_total) {
     const uint32_t i = tile * 32u + lane;
     const bool valid = i < n_reads;
-    // records stream through once: evict-first loads; the NEXT tile of this warp is prefetched into L2 meanwhile
     int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    // records stream through once: evict-first loads; the NEXT tile of this warp is prefetched into L2 meanwhile
     if (valid) {
         const int4* rp = reinterpret_cast<const int4*>(reads + i);
         q0 = __ldcs(rp); q1 = __ldcs(rp + 1); q2 = __ldcs(rp + 2);
@@ -280,7 +282,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     if ((unsigned long long)block_off + nb > n_blocks) nb = 0;  // defensive: never read out of the submitted array
     (void)isize; (void)l_qseq;
     RecOut o;
-    filter_cascade<kLegacy>(prm, valid, f, mapq, aux, filter_mask, pos, mpos, endpos, nm_raw, nb, o);
+    filter_cascade(prm, valid, f, mapq, aux, filter_mask, pos, mpos, endpos, nm_raw, nb, o);
 
     if (w.on) {                                                                        // the starts have landed in shared memory
         mbar_wait(mbar, phase); phase ^= 1u;
@@ -402,8 +404,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
 
     // ---- warp-converged epilogue: aggregate before touching HBM -------------------------------------------------------
     // gene counters: lanes that count toward the same gene elect one leader (sorted input => usually the whole warp)
+    const unsigned peers = __match_any_sync(kFull, o.agg_gene);
     {
-        const unsigned peers = __match_any_sync(kFull, o.agg_gene);
         const unsigned bu = __ballot_sync(kFull, o.agg_unique);
         if (o.agg_gene != kNoGene && lane == (unsigned)(__ffs(peers) - 1)) {
             atomicAdd(&acc.gene_reads[o.agg_gene], (unsigned long long)__popc(peers));
@@ -417,8 +419,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     int s_late = 0;
     if constexpr (!kLegacy) {
         s_late = resolve_parked(st, acc, lane);
-        st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene;                   // each lane reads back its own slot only
-        if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + (o.frag_key & acc.frag_mask)));
+        st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene; st->fpeers[lane] = peers;   // each lane reads back its own slot only
+        if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + set_home(o.frag_key, acc.frag_cap)));
     }
     // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  The 64-bit mask of
     // a record is cut into 5-bit words; a multiply spreads the five bits into five 6-bit fields (a tile adds at most 32 to a
@@ -567,35 +569,65 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned int* __restric
     }
 }
 
+// Phase 3: every warp owns 512 consecutive elements of the tile and reads them as four fully coalesced 128-bit rows (one row =
+// 32 lanes x uint4 = 512 bytes); prefix inside the uint4, warp scan of the lane sums per row, carry from row to row; one
+// block barrier hands every warp the total of the warps before it.  HBM-bound: reads the difference array once, writes the
+// coverage once.
 __global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(const unsigned int* __restrict__ in, unsigned int* __restrict__ out, unsigned long long n,
                                                                  const unsigned int* __restrict__ sums) {
-    __shared__ unsigned int s_warp[33];
-    const unsigned long long base = (unsigned long long)blockIdx.x * kScanTile + (unsigned long long)threadIdx.x * kScanItems;
-    unsigned int vals[kScanItems];
-    unsigned int v = 0;
+    static_assert(kScanThreads == 256 && kScanItems == 16, "8 warps x 4 rows x 32 lanes x 4 elements");
+    __shared__ unsigned int s_tot[8];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const unsigned long long seg = (unsigned long long)blockIdx.x * kScanTile + (unsigned long long)wid * 512u;
+    uint4 x[4];
+    unsigned int carry = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const unsigned long long idx = base + k;
-        vals[k] = idx < n ? in[idx] : 0u;
-        v += vals[k];
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long idx = seg + (unsigned long long)j * 128u + lane * 4u;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (idx + 3 < n) v = *reinterpret_cast<const uint4*>(in + idx);          // the arrays are 256-byte aligned, idx a multiple of 4
+        else {
+            if (idx < n) v.x = in[idx];
+            if (idx + 1 < n) v.y = in[idx + 1];
+            if (idx + 2 < n) v.z = in[idx + 2];
+        }
+        v.y += v.x; v.z += v.y; v.w += v.z;                                      // inclusive inside the lane
+        unsigned int inc = v.w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int t = __shfl_up_sync(kFull, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        const unsigned int off = carry + inc - v.w;                              // everything before this lane in the warp's segment
+        v.x += off; v.y += off; v.z += off; v.w += off;
+        x[j] = v;
+        carry += __shfl_sync(kFull, inc, 31);
     }
-    unsigned int total;
-    unsigned int run = block_exclusive_scan(v, s_warp, total) + sums[blockIdx.x];
+    if (lane == 0) s_tot[wid] = carry;
+    __syncthreads();
+    unsigned int before = sums[blockIdx.x];
+    for (unsigned w = 0; w < wid; ++w) before += s_tot[w];
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        run += vals[k];                      // inclusive: coverage[i] = sum of diff[0..i]
-        const unsigned long long idx = base + k;
-        if (idx < n) out[idx] = run;
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long idx = seg + (unsigned long long)j * 128u + lane * 4u;
+        uint4 v = x[j];
+        v.x += before; v.y += before; v.z += before; v.w += before;              // inclusive: coverage[i] = sum of diff[0..i]
+        if (idx + 3 < n) *reinterpret_cast<uint4*>(out + idx) = v;
+        else {
+            if (idx < n) out[idx] = v.x;
+            if (idx + 1 < n) out[idx + 1] = v.y;
+            if (idx + 2 < n) out[idx + 2] = v.z;
+        }
     }
 }
 
 // ---- fragment-tracker set growth ----------------------------------------------------------------------------------------------
 __global__ void rehash_kernel(const unsigned long long* __restrict__ old_tab, unsigned long long old_cap, unsigned long long* __restrict__ new_tab,
-                              unsigned long long new_mask, unsigned int* err) {
+                              unsigned long long new_cap, unsigned int* err) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= old_cap) return;
     const unsigned long long key = old_tab[i];
-    if (key) set_insert(new_tab, new_mask, key, err, 1u);
+    if (key) set_insert(new_tab, new_cap, key, err, 1u);
 }
 
 // ---- count vector export for the NVLink all-reduce: counters | gene_reads | gene_unique | gene_fragments | exon_whole |
@@ -857,9 +889,9 @@ int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned l
     return 3;
 }
 
-int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap, unsigned long long* new_tab, unsigned long long new_mask,
+int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap, unsigned long long* new_tab, unsigned long long new_cap,
                   unsigned int* error_flag, cudaStream_t stream) {
-    rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_tab, old_cap, new_tab, new_mask, error_flag);
+    rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_tab, old_cap, new_tab, new_cap, error_flag);
     return 1;
 }
 

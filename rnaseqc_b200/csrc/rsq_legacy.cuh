@@ -151,7 +151,7 @@ __device__ __noinline__ void legacy_metrics(const AnnView& ann, const Accum& acc
                 }
                 atomicAdd(&acc.gene_reads[gid], 1ull);                                 // :226
                 const unsigned long long key0 = mix64(r.name_hash ^ ((unsigned long long)(gid + 1u) * 0x9E3779B97F4A7C15ull));
-                if (set_insert(acc.frag_set, acc.frag_mask, key0 ? key0 : 1ull, acc.error_flag, 1u)) {
+                if (set_insert(acc.frag_set, acc.frag_cap, key0 ? key0 : 1ull, acc.error_flag, 1u)) {
                     atomicAdd(&acc.gene_fragments[gid], 1ull);
                     ++n_fresh;
                 }

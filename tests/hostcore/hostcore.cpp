@@ -85,7 +85,7 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
             uint32_t nb = r.n_blocks;
             if ((size_t)r.block_off + nb > n_blocks) nb = 0;
             RecOut o;
-            filter_cascade<false>(prm, true, r.flag, r.mapq, r.aux, r.filter_mask, r.pos, r.mpos, r.endpos, r.nm, nb, o);
+            filter_cascade(prm, true, r.flag, r.mapq, r.aux, r.filter_mask, r.pos, r.mpos, r.endpos, r.nm, nb, o);
             if (o.go) {
                 const bool cleared = (r.aux & RSQ_AUX_CONTIG_DROPPED) || r.contig < 0 || (uint32_t)r.contig >= ann.n_contigs;
                 const int rstrand = read_strand(prm, r.flag);
