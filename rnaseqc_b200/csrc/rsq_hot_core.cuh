@@ -298,7 +298,9 @@ RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, cons
 // in this thread's chain.  Further genes of the same read (overlapping annotations, rare) are inserted on the spot.
 template <class Mem>
 RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsigned long long name_hash, RecOut& o) {
-    const unsigned long long key0 = mix64(name_hash ^ ((unsigned long long)(g + 1u) * 0x9E3779B97F4A7C15ull));
+    // name_hash is a mixed 64-bit hash already (rsq_read.name_hash); one odd multiply is a bijection that carries every bit of
+    // (name, gene) into the high half, where the table takes its home slot from
+    const unsigned long long key0 = (name_hash ^ ((unsigned long long)(g + 1u) << 40)) * 0x9E3779B97F4A7C15ull;
     const unsigned long long key = key0 ? key0 : 1ull;
     if (o.agg_gene == kNoGene) { o.agg_gene = g; o.agg_unique = !(f & RSQ_F_DUP); o.frag_key = key; }
     else {
