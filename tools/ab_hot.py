@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--bed", action="store_true")
     ap.add_argument("--no-coverage", action="store_true")
+    ap.add_argument("--max-records-factor", type=float, default=1.0, help="rsq_config.max_records = factor x records (2: the whole batch is ONE launch)")
     ap.add_argument("--cache", default="", help="directory to keep the generated records in between invocations (e.g. /dev/shm/ab)")
     ap.add_argument("--device", default="cuda:0", help="cpu only to smoke-test this script against the oracle library")
     args = ap.parse_args()
@@ -88,7 +89,7 @@ def main():
                     row["parity"] = "bit-exact"
                 except AssertionError as ex:
                     row["parity"] = "MISMATCH: " + str(ex)[:300]
-            ctx = be.create(api.make_config(max_records=n_reads, fragment_samples=1000000 if args.bed else 0,
+            ctx = be.create(api.make_config(max_records=int(n_reads * args.max_records_factor), fragment_samples=1000000 if args.bed else 0,
                                             collect_coverage=not args.no_coverage))
             ctx.set_annotation(ann)
             times = []
