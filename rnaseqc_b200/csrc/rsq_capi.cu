@@ -572,6 +572,30 @@ int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* b) {
     c->bed_allocs.push_back(pmax);
     c->launches += launch_prefix_max(v.se, v.off, b->n_contigs, pmax, c->stream);
     v.pmax = pmax;
+    {   // the same elementary-interval index as the annotation's, over the BED intervals (name id in the slot field): a block that
+        // lies between two cuts intersects exactly the intervals covering it (fragmentSizeMetrics, src/Expression.cpp:490-507)
+        rsq_annotation fake;
+        memset(&fake, 0, sizeof fake);
+        std::vector<uint32_t> gene(b->n_intervals, 0u), seg_off(b->n_contigs + 1);
+        std::vector<uint8_t> flags(b->n_intervals, 0), seg_flags(b->n_contigs, 0), gene_flags(1, 0);
+        std::vector<uint64_t> cov(b->n_intervals, 0);
+        std::vector<int32_t> seg_start(b->n_contigs, INT32_MIN);
+        for (uint32_t k = 0; k <= b->n_contigs; ++k) seg_off[k] = k;
+        fake.struct_size = sizeof fake; fake.n_contigs = b->n_contigs; fake.n_genes = 1; fake.n_exons = b->n_intervals; fake.n_segs = b->n_contigs;
+        fake.exon_off = b->off; fake.exon_start = b->start; fake.exon_end = b->end; fake.exon_gene = gene.data(); fake.exon_slot = b->name_id;
+        fake.exon_flags = flags.data(); fake.exon_cov_off = cov.data(); fake.seg_off = seg_off.data(); fake.seg_start = seg_start.data();
+        fake.seg_flags = seg_flags.data(); fake.gene_flags = gene_flags.data();
+        EiIndex X;
+        const std::string why = build_ei_index(&fake, X);
+        if (!why.empty()) { c->err = "BED intervals cannot be indexed: " + why; return RSQ_ERR_INVALID; }
+        if ((rc = upload(c, c->bed_allocs, X.ei_off.data(), X.ei_off.size(), &v.ei_off))) return rc;
+        if ((rc = upload(c, c->bed_allocs, X.ei_start.data(), X.ei_start.size(), &v.ei_start))) return rc;
+        if ((rc = upload(c, c->bed_allocs, reinterpret_cast<const uint2*>(X.ei_desc.data()), X.ei_desc.size(), &v.ei_desc))) return rc;
+        if ((rc = upload(c, c->bed_allocs, X.cover.data(), X.cover.size(), &v.cover))) return rc;
+        if ((rc = upload(c, c->bed_allocs, X.eib_off.data(), X.eib_off.size(), &v.eib_off))) return rc;
+        if ((rc = upload(c, c->bed_allocs, X.eib.data(), X.eib.size(), &v.eib))) return rc;
+        CU_TRY(cudaStreamSynchronize(c->stream));   // X is a local
+    }
     c->have_bed = true;
     if (c->cfg.fragment_samples) {
         Accum& acc = c->acc;

@@ -64,6 +64,13 @@ struct BedView {
     const int32_t*  pmax;         // [n_intervals]
     const uint32_t* name_id;      // [n_intervals]
     const uint8_t*  present;      // [n_contigs]
+    // elementary-interval index over the BED intervals (rsq_eit.h; CoverEntry::slot carries the interval's name id)
+    const uint32_t*   ei_off;
+    const int32_t*    ei_start;
+    const uint2*      ei_desc;
+    const CoverEntry* cover;
+    const uint32_t*   eib_off;
+    const uint32_t*   eib;
 };
 
 // One read that entered the fragment-size mate map (src/Expression.cpp:508-516), emitted by the hot kernel.
