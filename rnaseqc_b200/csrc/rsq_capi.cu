@@ -162,15 +162,18 @@ int ensure_bed_buffers(Ctx* c, size_t n_reads) {
     return RSQ_OK;
 }
 
-// Keeps the fragment-tracker set at most half full.  A record inserts one entry per gene it counts toward, at most
-// `exon_depth` (the deepest stack of overlapping exons in the annotation).  The exact number of entries is a device counter;
-// the host only synchronises to read it when the pessimistic bound (known entries + depth x records in flight) would exceed
-// half of the capacity.  If the exact count still leaves too little room for the whole launch, the launch is cut down to what
-// fits (*n shrinks; the caller comes back with the rest) — and only when not even 4 M records fit is the table grown (rehash).
-// The table is sized 2 x max_records up front (any number of slots, not the next power of two: it is zeroed on every reset;
-// measured: at 1.5 x the longer probe chains cost the hot kernel 10 %, more than the smaller memset saves).
+// Keeps the fragment-tracker set from filling up.  A record inserts one entry per gene it counts toward, at most `exon_depth`
+// (the deepest stack of overlapping exons in the annotation) — a bound that real data stays far below (0.7 entries per record
+// on the GENCODE-scale workload, where the depth is 3).  The table is sized 2 x max_records (any number of slots, not the next
+// power of two: it is zeroed on every reset; measured: at 1.5 x the longer probe chains cost the hot kernel 10 %, more than the
+// smaller memset saves), so typical data leaves it about one-third full.  The guarantee is against OVERFLOW: the host lets a
+// launch go while the pessimistic bound (known entries + depth x records in flight) stays below 80 % of the capacity; beyond
+// that it synchronises to read the exact entry count (a device counter), and if even that leaves too little room for the whole
+// launch, the launch is cut down to what fits (*n shrinks; the caller comes back with the rest) — only when not even 4 M records
+// fit is the table grown (rehash).
 int reserve_frag_capacity(Ctx* c, size_t* n) {
-    auto fits = [&](unsigned long long known, unsigned long long add) { return 2ull * (known + add) <= c->frag_cap; };
+    const unsigned long long limit = c->frag_cap / 5 * 4;
+    auto fits = [&](unsigned long long known, unsigned long long add) { return known + add <= limit; };
     unsigned long long add = (unsigned long long)*n * c->exon_depth;
     if (fits(c->frag_known + c->frag_pending, add)) { c->frag_pending += add; return RSQ_OK; }
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -179,7 +182,7 @@ int reserve_frag_capacity(Ctx* c, size_t* n) {
     c->frag_known = exact;
     c->frag_pending = 0;
     if (!fits(exact, add)) {
-        const unsigned long long room = c->frag_cap / 2 > exact ? c->frag_cap / 2 - exact : 0ull;
+        const unsigned long long room = limit > exact ? limit - exact : 0ull;
         const size_t n_fit = (size_t)(room / c->exon_depth);
         if (n_fit >= std::min<size_t>(*n, (size_t)1 << 22)) {
             *n = std::min(*n, n_fit);
