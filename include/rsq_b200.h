@@ -72,7 +72,10 @@ typedef struct rsq_read {
     uint8_t  filter_mask; /* bit k set: --tag k present (GetTag, SeqLib/src/BamRecord.cpp:474-497)  */
     uint8_t  reserved0;
     uint64_t name_hash;   /* 64-bit hash of Qname(): identity for fragmentTracker (src/Metrics.cpp:22)
-                             and the fragment-size mate map (src/Expression.cpp:511-531)            */
+                             and the fragment-size mate map (src/Expression.cpp:511-531).  Must be a
+                             MIXED hash (all 64 bits depend on the whole name; the host library's
+                             hash_qname ends with a splitmix64 finaliser): the device tables take their
+                             home slots from it after one multiply only                            */
     uint32_t block_off;   /* index of this read's first aligned block in the blocks array of the SAME
                              submit call                                                           */
     uint16_t n_blocks;    /* number of M/=/X blocks (extractBlocks, src/Expression.cpp:26-67)       */

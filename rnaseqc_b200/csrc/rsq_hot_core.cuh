@@ -280,11 +280,8 @@ RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, cons
     frac_q64(ann.recip64, len, length, whole, lo);                                          // isz/length, :345
     // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update is a fire-and-forget
     // RED, nothing waits for an atomic's return value
-    if (whole) mem.add64(&acc.exon_whole[h.slot], whole);
-    else {
-        mem.add64(&acc.exon_fhi[h.slot], lo >> 32);
-        mem.add64(&acc.exon_flo[h.slot], lo & 0xffffffffull);
-    }
+    if (whole) mem.exon_one(acc, h.slot);
+    else mem.exon_frac(acc, h.slot, (uint32_t)(lo >> 32), (uint32_t)lo);
     o.my_bytes += 8u;
     if (prm.collect_coverage) {                                                            // add_range as +1/-1, Metrics.cpp:257-262
         mem.cov_range(&acc.cov_diff[cov_off + (unsigned long long)(bs - h.start)], len);   // +1 at the first base, -1 behind the last
@@ -314,7 +311,8 @@ RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsig
 }
 
 // ---- exonAlignmentMetrics, src/Expression.cpp:308-458 --------------------------------------------------------------------
-// Mem: add64(ptr, v), cov_range(ptr, len), frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
+// Mem: exon_one(acc, slot), exon_frac(acc, slot, hi, lo), cov_range(ptr, len), add64(ptr, v) for the rare direct gene-table adds,
+// frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
 template <class Mem>
 RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const Params& prm, const Accum& acc, uint32_t f, bool hq, bool cleared,
                          int contig, int rstrand, const rsq_block* bp, uint32_t nb, unsigned long long name_hash, RecOut& o, ExonOut& x) {

@@ -2,7 +2,7 @@
 //
 // Compile-time ablation switches (never defined in the product build; used for the time breakdown in DESIGN.md §4):
 //   RSQ_AB_NO_FRAGSET, RSQ_AB_NO_ACCUM, RSQ_AB_NO_EPILOGUE, RSQ_AB_CASCADE_ONLY, RSQ_AB_NO_STAGE, RSQ_AB_NO_PREFETCH,
-//   RSQ_AB_SCATTER, RSQ_AB_RED32
+//   RSQ_AB_SCATTER, RSQ_AB_NO_EXON, RSQ_AB_NO_COV, RSQ_NO_AGG_EXON, RSQ_NO_AGG_COV, RSQ_COV_TWO_MATCHES
 //
 // K_hot  : one pass over a batch of decoded alignment records (rsq_read + rsq_block): the flag/quality/
 //          mismatch filter cascade of src/RNASeQC.cpp:254-342, interval intersection of every aligned block
@@ -138,31 +138,51 @@ __device__ __forceinline__ unsigned int warp_claim(unsigned int* counter) {
 }
 
 // Memory side effects of the per-record logic on the device: fire-and-forget REDs and the fragment-tracker CAS.
-// RSQ_AB_SCATTER / RSQ_AB_RED32 are diagnostics (results wrong by construction): same instruction stream, but every RED goes
-// to a thread-unique address / is a 32-bit RED.
+// RSQ_AB_SCATTER is a diagnostic (results wrong by construction): same instruction stream, but every RED goes
+// to a thread-unique address.
 struct DevMem {
     const Accum& acc;
     unsigned long long n_exons, cov_len;
     // Opportunistic warp aggregation: coordinate-sorted input makes the lanes that reach an accumulation together hit the same
-    // exon word and the same few coverage words, and the L2 atomic units serialise per address (measured: the REDs were 65 %
-    // of the kernel).  The lanes converged at the call (any subset is correct) group by address with one MATCH.ANY; one lane
-    // per group issues the RED with the group's sum (REDUX over the group's mask).
-    __device__ __forceinline__ void add64(unsigned long long* p, unsigned long long v) const {
+    // exon words and the same few coverage words, and the L2 atomic units serialise per address (measured: the REDs were 65 %
+    // of the kernel).  The lanes converged at the call (any subset is correct) group by target with one MATCH.ANY; one lane
+    // per group issues the RED with the group's sum (a population count, or REDUX over the group's mask).
+    // exonCounts[slot] += 1 (a read that lies in one exon with all its aligned bases): the group's size is the sum
+    __device__ __forceinline__ void exon_one(const Accum& a, uint32_t slot) const {
 #if defined(RSQ_AB_SCATTER)       // needs n_exons >= 2^18 (the GENCODE-scale bench annotation)
-        const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-        atomicAdd(acc.exon_whole + (((unsigned)(p - acc.exon_whole) + gt * 37u) & 0x3ffffu), v);
-#elif defined(RSQ_AB_RED32)
-        atomicAdd(reinterpret_cast<unsigned int*>(p), (unsigned int)v);
+        atomicAdd(a.exon_whole + ((slot + (blockIdx.x * blockDim.x + threadIdx.x) * 37u) & 0x3ffffu), 1ull);
 #elif defined(RSQ_AB_NO_ACCUM) || defined(RSQ_AB_NO_EXON)
 #elif defined(RSQ_NO_AGG_EXON)
-        atomicAdd(p, v);
+        atomicAdd(&a.exon_whole[slot], 1ull);
 #else
-        const unsigned m = __activemask();
-        const unsigned peers = __match_any_sync(m, (unsigned long long)p);
-        if ((peers & (peers - 1u)) == 0u || __any_sync(peers, (v >> 32) != 0ull)) { atomicAdd(p, v); return; }   // alone, or a value beyond 32 bits
-        // every value on this path is below 2^32 (1, or a 32-bit half of a Q64.64 fraction): two 16-bit partial sums cannot overflow
-        const unsigned s_lo = __reduce_add_sync(peers, (unsigned)v & 0xffffu), s_hi = __reduce_add_sync(peers, (unsigned)v >> 16);
-        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p, ((unsigned long long)s_hi << 16) + s_lo);
+        const unsigned peers = __match_any_sync(__activemask(), slot);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&a.exon_whole[slot], (unsigned long long)__popc(peers));
+#endif
+    }
+    // exonCounts[slot] += frac as the two 32-bit halves of its Q0.64 image: one MATCH.ANY on the slot serves both words; the
+    // halves are summed as 16-bit quarters so that no REDUX can overflow
+    __device__ __forceinline__ void exon_frac(const Accum& a, uint32_t slot, uint32_t hi, uint32_t lo) const {
+#if defined(RSQ_AB_SCATTER)
+        const uint32_t s2 = (slot + (blockIdx.x * blockDim.x + threadIdx.x) * 37u) & 0x3ffffu;
+        atomicAdd(&a.exon_fhi[s2], (unsigned long long)hi); atomicAdd(&a.exon_flo[s2], (unsigned long long)lo);
+#elif defined(RSQ_AB_NO_ACCUM) || defined(RSQ_AB_NO_EXON)
+#elif defined(RSQ_NO_AGG_EXON)
+        atomicAdd(&a.exon_fhi[slot], (unsigned long long)hi); atomicAdd(&a.exon_flo[slot], (unsigned long long)lo);
+#else
+        const unsigned peers = __match_any_sync(__activemask(), slot);
+        if ((peers & (peers - 1u)) == 0u) { atomicAdd(&a.exon_fhi[slot], (unsigned long long)hi); atomicAdd(&a.exon_flo[slot], (unsigned long long)lo); return; }
+        const unsigned h0 = __reduce_add_sync(peers, hi & 0xffffu), h1 = __reduce_add_sync(peers, hi >> 16);
+        const unsigned l0 = __reduce_add_sync(peers, lo & 0xffffu), l1 = __reduce_add_sync(peers, lo >> 16);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) {
+            atomicAdd(&a.exon_fhi[slot], ((unsigned long long)h1 << 16) + h0);
+            atomicAdd(&a.exon_flo[slot], ((unsigned long long)l1 << 16) + l0);
+        }
+#endif
+    }
+    // direct adds to the gene tables (second and further genes of one read: rare)
+    __device__ __forceinline__ void add64(unsigned long long* p, unsigned long long v) const {
+#if !defined(RSQ_AB_NO_ACCUM)
+        atomicAdd(p, v);
 #endif
     }
     // +1 at p, -1 at p + len (add_range as a difference array).  Reads with the same start AND length share both words: one

@@ -23,6 +23,8 @@ namespace {
 struct HostMem {
     std::unordered_set<unsigned long long>* set;
     void add64(unsigned long long* p, unsigned long long v) const { *p += v; }
+    void exon_one(const Accum& acc, uint32_t slot) const { acc.exon_whole[slot] += 1ull; }
+    void exon_frac(const Accum& acc, uint32_t slot, uint32_t hi, uint32_t lo) const { acc.exon_fhi[slot] += hi; acc.exon_flo[slot] += lo; }
     void cov_range(unsigned int* p, unsigned int len) const { p[0] += 1u; p[len] -= 1u; }
     bool frag_insert(unsigned long long key) const { return set->insert(key).second; }
 };

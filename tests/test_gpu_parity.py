@@ -330,3 +330,72 @@ def test_packed_wire_format_matches_unpacked_submit(libs, synth_case):
     assert ctx.algorithmic_bytes() == want_bytes
     assert total_wire < 0.75 * (48 * len(reads) + 8 * len(blocks))
     ctx.close()
+
+
+def test_full_size_properties_200m_records(libs):
+    """BASELINE.json configs[2] at full size (200 M synthetic records, GENCODE-scale annotation), where the oracle cannot follow:
+    size-independent properties instead — batching invariance (one submit vs three uneven ones: every table and every base of
+    the coverage identical), idempotence after reset, the conservation laws of the counters, exon sums vs gene counts, and a
+    300 k-record slice from the middle of the stream against the oracle."""
+    import torch
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    if torch.cuda.mem_get_info()[0] < 60 << 30:
+        pytest.skip("needs ~60 GB of free HBM")
+    import tempfile
+    n_records = 200_000_000
+    d = tempfile.mkdtemp(prefix="rsq_full_")
+    sa = synth.make_annotation(seed=20260925, n_genes=56202, contig_names=synth.GRCH38_NAMES, contig_lens=synth.GRCH38)
+    synth.write_gtf(sa, os.path.join(d, "a.gtf"))
+    ann = api.Annotation(os.path.join(d, "a.gtf"))
+    parts, done, k = [], 0, 0
+    while done < n_records:
+        sr = synth.simulate_reads(sa, min(20_000_000, n_records - done), seed=20260925 + k, device="cuda:0", sort=False, name_base=done)
+        parts.append(sr); done += sr.n; k += 1
+    sr = synth.sort_reads(synth.concat(parts))
+    del parts
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    del sr
+    torch.cuda.empty_cache()
+    n, nb = rb.shape[0], bb.shape[0]
+
+    def run(bounds):
+        ctx = api.Backend(libs["product"]).create(api.make_config(max_records=n))
+        ctx.set_annotation(ann)
+        out = []
+        for rep in range(2 if len(bounds) == 2 else 1):          # the single-submit context also checks idempotence after reset
+            ctx.reset()
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                ctx.submit_device(rb.data_ptr() + 48 * a, b - a, bb.data_ptr(), nb)
+            out.append(ctx.finalize())
+        ctx.close()
+        return out
+
+    whole, again = run([0, n])
+    (parts3,) = run([0, 61_234_567, 61_234_568, 150_000_001, n])
+    assert_results_equal(again, whole, "second pass after reset")
+    assert_results_equal(parts3, whole, "four uneven submits vs one")
+    assert np.array_equal(parts3.coverage, whole.coverage)
+
+    c = whole.counter
+    assert c("Total Alignments") == n
+    assert c("Mapped Reads") == c("Mapped Duplicate Reads") + c("Mapped Unique Reads")
+    assert c("Reads used for Intron/Exon counts") == c("High Quality Reads") + c("Low Quality Reads")
+    assert c("Exonic Reads") + c("Intronic Reads") + c("Intergenic Reads") + c("Ambiguous Reads") == c("Reads used for Intron/Exon counts")
+    assert c("Intragenic Reads") == c("Exonic Reads") + c("Intronic Reads")
+    assert c("HQ Exonic Reads") + c("HQ Intronic Reads") + c("HQ Intergenic Reads") + c("HQ Ambiguous Reads") == c("High Quality Reads")
+    assert c("End 1 Mapped Reads") + c("End 2 Mapped Reads") <= c("Mapped Reads")
+    assert int(whole.gene_fragments.sum()) == c("Fragment Set Entries")
+    assert (whole.gene_unique <= whole.gene_reads).all() and (whole.gene_fragments <= whole.gene_reads).all()
+    assert int(whole.gene_reads.sum()) >= c("HQ Exonic Reads") > 100_000_000
+    # every (read, gene) assignment spreads exactly 1 over the exons of the gene (each floor loses < 2^-64)
+    assert abs(float(whole.exon_counts().sum()) - float(whole.gene_reads.sum())) < 1e-3
+    # a slice from the middle of the stream against the oracle
+    a0 = n // 3
+    pr = np.frombuffer(rb[a0:a0 + 300_000].cpu().numpy().reshape(-1).data, dtype=api.READ_DTYPE).copy()
+    b0, b1 = int(pr["block_off"][0]), int(pr["block_off"][-1]) + int(pr["n_blocks"][-1])
+    pr["block_off"] -= np.uint32(b0)
+    pb = np.frombuffer(bb[b0:b1].cpu().numpy().reshape(-1).data, dtype=api.BLOCK_DTYPE).copy()
+    want, _ = _run(api, libs["oracle"], ann, pr, pb, api.make_config(max_records=len(pr)))
+    got, _ = _run(api, libs["product"], ann, pr, pb, api.make_config(max_records=len(pr)))
+    assert_results_equal(got, want, "300 k-record slice vs oracle")
