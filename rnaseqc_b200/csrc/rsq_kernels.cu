@@ -498,10 +498,12 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         const int s_mm2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? nm_raw : 0), s_b2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? l_qseq : 0);
         const int s_mm = __reduce_add_sync(kFull, (o.vflags & 4u) ? nm_raw : 0), s_tb = __reduce_add_sync(kFull, (o.vflags & 8u) ? l_qseq : 0);
         const int s_nb = __reduce_add_sync(kFull, (o.vflags & 16u) ? (int)nb : 0);
-        const unsigned s_bytes_w = __reduce_add_sync(kFull, o.my_bytes);
-        const int s_fresh = __reduce_add_sync(kFull, o.n_fresh) + s_late;
+        // algorithmic bytes: every lane keeps its own sum; new fragment-set entries: the parked ones are warp-uniform, the
+        // on-the-spot ones (second genes of a read) are rare enough for a shared-memory add
+        own_bytes += o.my_bytes;
         static_assert(RSQ_C_FRAGSET_ENTRIES >= 32 && RSQ_C_FRAGSET_ENTRIES < 64, "lives in own_hi");
-        if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_fresh;
+        if (lane == RSQ_C_FRAGSET_ENTRIES - 32) own_hi += (unsigned long long)s_late;
+        if (o.n_fresh) atomicAdd(&s_cnt[RSQ_C_FRAGSET_ENTRIES], (unsigned long long)o.n_fresh);
         static_assert(RSQ_C_END1_MISMATCHES < 32 && RSQ_C_END1_BASES < 32 && RSQ_C_END2_MISMATCHES < 32 && RSQ_C_END2_BASES < 32 &&
                       RSQ_C_MISMATCHED_BASES < 32 && RSQ_C_TOTAL_BASES < 32 && RSQ_C_ALIGNMENT_BLOCKS < 32, "valued counters live in own_lo");
         int mine = 0;
@@ -513,7 +515,6 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         mine = lane == RSQ_C_TOTAL_BASES ? s_tb : mine;
         mine = lane == RSQ_C_ALIGNMENT_BLOCKS ? s_nb : mine;
         own_lo += (unsigned long long)(long long)mine;
-        if (lane == 0) own_bytes += s_bytes_w;
     }
   }  // tile loop
     if constexpr (!kLegacy) {                                                        // the last tile's parked keys
@@ -523,7 +524,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // one shared-memory add per counter per warp, then one global atomic per counter per CTA
     if (own_lo) atomicAdd(&s_cnt[lane], own_lo);
     if (own_hi) atomicAdd(&s_cnt[32 + lane], own_hi);
-    if (lane == 0 && own_bytes) atomicAdd(&s_bytes, own_bytes);
+    if (own_bytes) atomicAdd(&s_bytes, own_bytes);
     __syncthreads();
     // one global atomic per counter per CTA
     for (int k = threadIdx.x; k < RSQ_N_COUNTERS; k += blockDim.x)
