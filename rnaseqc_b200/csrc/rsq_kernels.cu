@@ -115,7 +115,11 @@ __device__ __forceinline__ int resolve_parked(Stage* st, const Accum& acc, unsig
     const unsigned long long key = st->fkey[lane];
     const uint32_t g = st->fgene[lane];
     const unsigned peers = st->fpeers[lane];
+#ifdef RSQ_AB_NO_FRAGSET
+    const bool fresh = (key & 2ull) != 0ull;   // ablation only: no table traffic (results are wrong)
+#else
     const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_cap, key, acc.error_flag, 1u);
+#endif
     const unsigned all_fresh = __ballot_sync(kFull, fresh);
     // the gene groups of that tile are known from its epilogue: the lowest lane of each group adds the group's new entries
     if (g != kNoGene && lane == (unsigned)(__ffs(peers) - 1)) {
@@ -469,7 +473,9 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     if constexpr (!kLegacy) {
         s_late = resolve_parked(st, acc, lane);
         st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene; st->fpeers[lane] = peers;   // each lane reads back its own slot only
+#ifndef RSQ_AB_NO_FRAGSET
         if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + set_home(o.frag_key, acc.frag_cap)));
+#endif
     }
     // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  The 64-bit mask of
     // a record is cut into 5-bit words; a multiply spreads the five bits into five 6-bit fields (a tile adds at most 32 to a
