@@ -48,13 +48,13 @@ __device__ __forceinline__ int lower_bound_pmax(const int32_t* __restrict__ pmax
 // key x capacity, linear probing with wrap-around.  (A bucketed variant — four slots = one 32-byte sector fetched and examined
 // together — was measured slower: 14.2 vs 12.6 ms per 200 M records.)
 __device__ __forceinline__ unsigned long long set_home(unsigned long long key, unsigned long long cap) { return __umul64hi(key, cap); }
-__device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab, unsigned long long cap, unsigned long long key,
-                                           unsigned int* err, unsigned int err_bit) {
+// `seen`: what an EARLIER load of the key's home slot returned (the kernel fetches it asynchronously one tile ahead).  A stale value
+// is harmless: slots only ever change from empty to a key, so a stale "empty" is corrected by the CAS and a key is never stale.
+__device__ __forceinline__ bool set_insert_seen(unsigned long long* __restrict__ tab, unsigned long long cap, unsigned long long key,
+                                                unsigned long long seen, unsigned int* err, unsigned int err_bit) {
     unsigned long long slot = set_home(key, cap);
+    unsigned long long cur = seen;
     for (int probe = 0; probe < 65536; ++probe) {       // the host keeps the table below 80 % (rsq_capi.cu reserve_frag_capacity)
-        // plain load first: measured 30 % faster than CAS-first on B200 (an L2 atomic on a missing line is far more
-        // expensive than a load, and second mates find their key without any atomic)
-        unsigned long long cur = tab[slot];
         if (cur == key) return false;
         if (cur == 0ull) {
             cur = atomicCAS(&tab[slot], 0ull, key);
@@ -62,9 +62,16 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
             if (cur == key) return false;
         }
         slot = slot + 1 == cap ? 0ull : slot + 1;
+        cur = tab[slot];
     }
     atomicOr(err, err_bit);
     return false;
+}
+__device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab, unsigned long long cap, unsigned long long key,
+                                           unsigned int* err, unsigned int err_bit) {
+    // plain load first: measured 30 % faster than CAS-first on B200 (an L2 atomic on a missing line is far more
+    // expensive than a load, and second mates find their key without any atomic)
+    return set_insert_seen(tab, cap, key, tab[set_home(key, cap)], err, err_bit);
 }
 
 // ---- per-warp staging of the interval starts into shared memory (TMA bulk copy) ----------------------------------------
@@ -82,6 +89,7 @@ struct __align__(16) WarpStage {
     unsigned long long fkey[32];      // fragment-tracker keys parked for one tile (0 = none), one slot per lane
     uint32_t fgene[32];               // the gene each parked key counts toward
     uint32_t fpeers[32];              // the lanes of that tile that counted toward the same gene (MATCH.ANY of the epilogue)
+    unsigned long long fval[32];      // what the home slot of each parked key held (cp.async, lands during the next tile)
     unsigned long long mbar;
     unsigned long long pad;
 };
@@ -118,7 +126,12 @@ __device__ __forceinline__ int resolve_parked(Stage* st, const Accum& acc, unsig
 #ifdef RSQ_AB_NO_FRAGSET
     const bool fresh = (key & 2ull) != 0ull;   // ablation only: no table traffic (results are wrong)
 #else
+#ifdef RSQ_FRAG_PREFETCH_ONLY
     const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_cap, key, acc.error_flag, 1u);
+#else
+    asm volatile("cp.async.wait_group 0;" ::: "memory");               // the home slots fetched one tile ago have landed
+    const bool fresh = key != 0ull && set_insert_seen(acc.frag_set, acc.frag_cap, key, st->fval[lane], acc.error_flag, 1u);
+#endif
 #endif
     const unsigned all_fresh = __ballot_sync(kFull, fresh);
     // the gene groups of that tile are known from its epilogue: the lowest lane of each group adds the group's new entries
@@ -467,14 +480,22 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         }
     }
     // fragment tracker (src/Metrics.cpp:22, src/Expression.cpp:383-387).  A hash-set insert is two dependent round trips to a
-    // multi-GB table: instead of waiting for HBM twice per tile, the warp parks this tile's keys in shared memory, prefetches
-    // their table lines into L2, and inserts them one tile LATER.
+    // multi-GB table: instead of waiting for HBM twice per tile, the warp parks this tile's keys in shared memory, starts an
+    // asynchronous copy of their home slots, and inserts them one tile LATER.
     int s_late = 0;
     if constexpr (!kLegacy) {
         s_late = resolve_parked(st, acc, lane);
         st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene; st->fpeers[lane] = peers;   // each lane reads back its own slot only
-#ifndef RSQ_AB_NO_FRAGSET
+#if defined(RSQ_AB_NO_FRAGSET)
+#elif defined(RSQ_FRAG_PREFETCH_ONLY)
         if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + set_home(o.frag_key, acc.frag_cap)));
+#else
+        // asynchronous 8-byte copy of the key's home slot into the lane's parking place (LDGSTS): by the next tile the warp
+        // knows without any further global access whether the key is already there (the upper mate of a pair), the slot is
+        // free (one CAS on a line that is in L2 by then) or taken by another key (rare: probe on)
+        if (o.frag_key)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&st->fval[lane])), "l"(acc.frag_set + set_home(o.frag_key, acc.frag_cap)) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
     }
     // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  The 64-bit mask of
