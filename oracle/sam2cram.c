@@ -1,0 +1,36 @@
+/* sam2cram.c — TEST INFRASTRUCTURE.  Writes a CRAM from a SAM/BAM with the reference's own vendored htslib 1.5 (linked
+ * from the objects oracle/Makefile.ref builds into oracle/_ref/), so that the tests can feed the same CRAM to the unmodified
+ * reference binary and to this repo's own CRAM reader (rnaseqc_b200/csrc/host/cramreader.cpp).  Never part of the product.
+ *   usage: sam2cram in.sam ref.fa out.cram [records_per_slice [slices_per_container]]                                     */
+#include <stdio.h>
+#include <stdlib.h>
+#include "htslib/hts.h"
+#include "htslib/sam.h"
+
+int main(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: sam2cram in.sam ref.fa out.cram [records_per_slice [slices_per_container]]\n"); return 2; }
+    htsFile* in = hts_open(argv[1], "r");
+    if (!in) { perror(argv[1]); return 1; }
+    bam_hdr_t* h = sam_hdr_read(in);
+    if (!h) { fprintf(stderr, "no header\n"); return 1; }
+    htsFile* out = hts_open(argv[3], "wc");
+    if (!out) { perror(argv[3]); return 1; }
+    if (hts_set_fai_filename(out, argv[2]) != 0) { fprintf(stderr, "cannot use reference %s\n", argv[2]); return 1; }
+    if (argc > 4) { int n = atoi(argv[4]); hts_set_opt(out, CRAM_OPT_SEQS_PER_SLICE, n); }
+    if (argc > 5) { int n = atoi(argv[5]); hts_set_opt(out, CRAM_OPT_SLICES_PER_CONTAINER, n); }
+    if (sam_hdr_write(out, h) != 0) { fprintf(stderr, "header write failed\n"); return 1; }
+    bam1_t* b = bam_init1();
+    long n = 0;
+    int r;
+    while ((r = sam_read1(in, h, b)) >= 0) {
+        if (sam_write1(out, h, b) < 0) { fprintf(stderr, "write failed at record %ld\n", n); return 1; }
+        ++n;
+    }
+    if (r < -1) { fprintf(stderr, "read error after %ld records\n", n); return 1; }
+    bam_destroy1(b);
+    bam_hdr_destroy(h);
+    if (hts_close(out) != 0) { fprintf(stderr, "close failed\n"); return 1; }
+    hts_close(in);
+    fprintf(stderr, "sam2cram: %ld records\n", n);
+    return 0;
+}

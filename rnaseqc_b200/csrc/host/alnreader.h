@@ -1,8 +1,8 @@
-// alnreader.h — SAM/BAM decode into the device record format (rsq_read + rsq_block).
+// alnreader.h — SAM/BAM/CRAM decode into the device record format (rsq_read + rsq_block).
 //
 // Own implementation (BGZF via zlib + BAM record parse; SAM text parse): the reference decodes through
 // SeqLib::BamReader -> htslib sam_read1 (src/BamReader.cpp:12-27).  Only the fields the hot loop touches
-// are extracted.  CRAM is not supported.
+// are extracted.  CRAM: cramreader.cpp.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -40,8 +40,11 @@ public:
     virtual ~AlnReader() {}
     virtual const AlnHeader& header() const = 0;
     virtual bool next(RawAln& out) = 0;   // false at EOF; throws HostError(-1) on corrupt input
-    static std::unique_ptr<AlnReader> open(const std::string& path);  // throws HostError(10) if unreadable
+    // throws HostError(10) if unreadable; `fasta`: the reference genome, needed for CRAM input only (NM is regenerated)
+    static std::unique_ptr<AlnReader> open(const std::string& path, const std::string& fasta = std::string());
 };
+
+std::unique_ptr<AlnReader> open_cram(const std::string& path, const std::string& fasta);   // cramreader.cpp
 
 // 64-bit read-name identity (FNV-1a with a splitmix64 finaliser).
 uint64_t hash_qname(const char* s, size_t n);

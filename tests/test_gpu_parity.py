@@ -399,3 +399,12 @@ def test_full_size_properties_200m_records(libs):
     want, _ = _run(api, libs["oracle"], ann, pr, pb, api.make_config(max_records=len(pr)))
     got, _ = _run(api, libs["product"], ann, pr, pb, api.make_config(max_records=len(pr)))
     assert_results_equal(got, want, "300 k-record slice vs oracle")
+
+
+def test_product_cli_reads_cram_like_the_reference(libs, tmp_path):
+    """CRAM input through the product CLI (host-side reader, tests/test_cram.py has its CPU twins) against the reference's outputs."""
+    d = unpack_case("cram_small", tmp_path)
+    out = os.path.join(d, "out")
+    run_cli(libs["cli"], os.path.join(d, "c.gtf"), os.path.join(d, "c.cram"), out, "--fasta", os.path.join(d, "c.fa"),
+            "--coverage", "--bed", os.path.join(d, "c.bed"))
+    compare_outputs(out, os.path.join(d, "expected"))
