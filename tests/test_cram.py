@@ -43,10 +43,14 @@ def test_cram_without_a_reference_fails_like_the_reference(libs, tmp_path):
     assert p.returncode != 0 and "reference" in p.stderr.lower()
 
 
+# sam2cram arguments: records per slice, slices per container, version, lossy names, multi-reference slices, no rANS
 LIVE = [
     ("default_slices", [], ["--coverage"]),
     ("small_slices_stranded", ["333", "3"], ["--stranded", "rf", "--coverage", "--bed", "c.bed"]),
     ("one_slice_unpaired", ["100000", "1"], ["-u", "--exclude-chimeric"]),
+    ("cram_2_1", ["1000", "2", "2.1"], ["--coverage", "--bed", "c.bed"]),
+    ("lossy_names_multi_ref", ["700", "1", "3.0", "1", "1"], ["--bed", "c.bed"]),
+    ("gzip_only", ["1500", "1", "3.0", "0", "0", "1"], []),
 ]
 
 
