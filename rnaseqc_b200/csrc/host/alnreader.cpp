@@ -308,14 +308,14 @@ private:
 
 }  // namespace
 
-std::unique_ptr<AlnReader> AlnReader::open(const std::string& path, const std::string& fasta) {
+std::unique_ptr<AlnReader> AlnReader::open(const std::string& path, const std::string& fasta, int threads) {
     FILE* fp = std::fopen(path.c_str(), "rb");
     if (!fp) throw HostError(10, "Unable to open BAM file: " + path);
     unsigned char m[4] = {0, 0, 0, 0};
     size_t r = std::fread(m, 1, 4, fp);
     std::fclose(fp);
     if (r >= 2 && m[0] == 0x1f && m[1] == 0x8b) return std::unique_ptr<AlnReader>(new BamReader(path));
-    if (r >= 4 && memcmp(m, "CRAM", 4) == 0) return open_cram(path, fasta);
+    if (r >= 4 && memcmp(m, "CRAM", 4) == 0) return open_cram(path, fasta, threads);
     return std::unique_ptr<AlnReader>(new SamReader(path));
 }
 

@@ -40,11 +40,12 @@ public:
     virtual ~AlnReader() {}
     virtual const AlnHeader& header() const = 0;
     virtual bool next(RawAln& out) = 0;   // false at EOF; throws HostError(-1) on corrupt input
-    // throws HostError(10) if unreadable; `fasta`: the reference genome, needed for CRAM input only (NM is regenerated)
-    static std::unique_ptr<AlnReader> open(const std::string& path, const std::string& fasta = std::string());
+    // throws HostError(10) if unreadable; `fasta`: the reference genome, needed for CRAM input only (NM is regenerated);
+    // `threads`: CRAM containers decoded concurrently (records still come out in file order); 0 or 1 = on the caller's thread
+    static std::unique_ptr<AlnReader> open(const std::string& path, const std::string& fasta = std::string(), int threads = 0);
 };
 
-std::unique_ptr<AlnReader> open_cram(const std::string& path, const std::string& fasta);   // cramreader.cpp
+std::unique_ptr<AlnReader> open_cram(const std::string& path, const std::string& fasta, int threads);   // cramreader.cpp
 
 // 64-bit read-name identity (FNV-1a with a splitmix64 finaliser).
 uint64_t hash_qname(const char* s, size_t n);

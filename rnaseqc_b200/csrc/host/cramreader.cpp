@@ -26,9 +26,12 @@
 #include <array>
 #include <climits>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <future>
 #include <map>
 #include <memory>
+#include <mutex>
 
 #include "alnreader.h"
 
@@ -208,6 +211,7 @@ struct Codec {
     struct HuffEntry { int len; int32_t sym; uint32_t code; };
     std::vector<HuffEntry> huff;          // canonical, sorted by (len, sym)
     std::unique_ptr<Codec> len_codec, val_codec;
+    mutable Block* blk = nullptr;         // the external block of ext_id in the slice being decoded (bind_blocks)
 };
 
 std::unique_ptr<Codec> parse_codec(Cursor& c) {
@@ -247,12 +251,18 @@ std::unique_ptr<Codec> parse_codec(Cursor& c) {
 struct SliceCtx {
     Block* core = nullptr;
     std::map<int, Block*> ext;
-    Block& external(int id) { auto it = ext.find(id); if (it == ext.end()) bad("missing external block " + std::to_string(id)); return *it->second; }
+    Block& external(const Codec& e) { if (!e.blk) bad("missing external block " + std::to_string(e.ext_id)); return *e.blk; }
 };
+void bind_blocks(const Codec& e, const SliceCtx& s) {
+    auto it = s.ext.find(e.ext_id);
+    e.blk = (e.kind == E_EXTERNAL || e.kind == E_BYTE_ARRAY_STOP) && it != s.ext.end() ? it->second : nullptr;
+    if (e.len_codec) bind_blocks(*e.len_codec, s);
+    if (e.val_codec) bind_blocks(*e.val_codec, s);
+}
 
 int32_t decode_int(const Codec& e, SliceCtx& s) {
     switch (e.kind) {
-        case E_EXTERNAL: return s.external(e.ext_id).itf8();
+        case E_EXTERNAL: return s.external(e).itf8();
         case E_HUFFMAN: {
             if (e.huff.empty()) bad("empty huffman code");
             if (e.huff.size() == 1 && e.huff[0].len == 0) return e.huff[0].sym;
@@ -290,7 +300,7 @@ int32_t decode_int(const Codec& e, SliceCtx& s) {
 }
 
 uint8_t decode_byte(const Codec& e, SliceCtx& s) {
-    if (e.kind == E_EXTERNAL) return s.external(e.ext_id).byte();
+    if (e.kind == E_EXTERNAL) return s.external(e).byte();
     return (uint8_t)decode_int(e, s);
 }
 
@@ -302,12 +312,12 @@ void decode_bytes(const Codec& e, SliceCtx& s, int32_t n, std::vector<uint8_t>* 
         if (len < 0) bad("byte array length");
         decode_bytes(*e.val_codec, s, len, out);
     } else if (e.kind == E_BYTE_ARRAY_STOP) {
-        Block& b = s.external(e.ext_id);
+        Block& b = s.external(e);
         for (;;) { const uint8_t v = b.byte(); if (v == e.stop) break; if (out) out->push_back(v); }
     } else {
         if (n < 0) bad("byte array without a length");
         if (e.kind == E_EXTERNAL) {
-            Block& b = s.external(e.ext_id);
+            Block& b = s.external(e);
             if (b.pos + (size_t)n > b.data.size()) bad("external block exhausted");
             if (out) out->assign(b.data.begin() + (long)b.pos, b.data.begin() + (long)b.pos + n);
             b.pos += (size_t)n;
@@ -321,6 +331,17 @@ struct CompHeader {
     std::map<std::string, std::unique_ptr<Codec>> ds;               // data series by two-letter key
     std::map<int32_t, std::unique_ptr<Codec>> tags;                 // (tag0 << 16 | tag1 << 8 | type) -> value encoding
     const Codec* get(const char* key) const { auto it = ds.find(key); return it == ds.end() ? nullptr : it->second.get(); }
+    // the data series the record loop reads, looked up once per container
+    const Codec *BF = nullptr, *CF = nullptr, *RI = nullptr, *RL = nullptr, *AP = nullptr, *RG = nullptr, *RN = nullptr, *MF = nullptr, *NS = nullptr,
+                *NP = nullptr, *TS = nullptr, *NF = nullptr, *TL = nullptr, *TC = nullptr, *TN = nullptr, *FN = nullptr, *FC = nullptr, *FP = nullptr,
+                *DL = nullptr, *BA = nullptr, *BS = nullptr, *IN = nullptr, *SC = nullptr, *HC = nullptr, *PD = nullptr, *RS = nullptr, *BB = nullptr,
+                *QQ = nullptr, *MQ = nullptr, *QS = nullptr;
+    void resolve() {
+        BF = get("BF"); CF = get("CF"); RI = get("RI"); RL = get("RL"); AP = get("AP"); RG = get("RG"); RN = get("RN"); MF = get("MF"); NS = get("NS");
+        NP = get("NP"); TS = get("TS"); NF = get("NF"); TL = get("TL"); TC = get("TC"); TN = get("TN"); FN = get("FN"); FC = get("FC"); FP = get("FP");
+        DL = get("DL"); BA = get("BA"); BS = get("BS"); IN = get("IN"); SC = get("SC"); HC = get("HC"); PD = get("PD"); RS = get("RS"); BB = get("BB");
+        QQ = get("QQ"); MQ = get("MQ"); QS = get("QS");
+    }
 };
 
 CompHeader parse_comp_header(Block& b) {
@@ -362,11 +383,12 @@ CompHeader parse_comp_header(Block& b) {
         const int32_t n = c.itf8();
         for (int32_t i = 0; i < n; ++i) { const int32_t key = c.itf8(); h.tags[key] = parse_codec(c); }
     }
+    h.resolve();
     return h;
 }
 
 // ---- reference: where it is 'N' (the only thing NM regeneration needs of it) ----------------------------------------------
-struct NRuns { bool loaded = false, present = false; std::vector<std::pair<int64_t, int64_t>> runs; };   // [begin, end) 0-based
+struct NRuns { std::once_flag once; bool present = false; std::vector<std::pair<int64_t, int64_t>> runs; };   // [begin, end) 0-based
 
 class ReferenceNs {
 public:
@@ -380,10 +402,12 @@ public:
         while (in >> name >> len >> off >> lb >> lw) index_[name] = {len, off, lb, lw};
     }
     bool given() const { return !path_.empty(); }
+    // the contigs that will be asked for (the CRAM header's): after this the map is never modified, so the lazy per-contig
+    // loads below are safe from any number of decoding threads
+    void declare(const std::vector<std::string>& contigs) { for (const auto& c : contigs) runs_[c]; }
     // number of 'N' / 'n' reference bases in [a, b) of the named contig; -1 when the FASTA does not have it
     int64_t count(const std::string& contig, int64_t a, int64_t b) {
-        NRuns& r = runs_[contig];
-        if (!r.loaded) load(contig, r);
+        NRuns& r = slot(contig);
         if (!r.present) return -1;
         int64_t n = 0;
         auto it = std::upper_bound(r.runs.begin(), r.runs.end(), std::make_pair(a, (int64_t)INT64_MAX));
@@ -391,12 +415,17 @@ public:
         for (; it != r.runs.end() && it->first < b; ++it) n += std::max<int64_t>(0, std::min(b, it->second) - std::max(a, it->first));
         return n;
     }
-    bool has(const std::string& contig) { NRuns& r = runs_[contig]; if (!r.loaded) load(contig, r); return r.present; }
+    bool has(const std::string& contig) { return slot(contig).present; }
 
 private:
     struct Fai { uint64_t len, off, line_bases, line_width; };
+    NRuns& slot(const std::string& contig) {
+        auto it = runs_.find(contig);
+        if (it == runs_.end()) bad("contig outside the CRAM header: " + contig);
+        std::call_once(it->second.once, [&] { load(contig, it->second); });
+        return it->second;
+    }
     void load(const std::string& contig, NRuns& r) {
-        r.loaded = true;
         auto it = index_.find(contig);
         if (it == index_.end() || !it->second.line_bases) return;
         std::ifstream in(path_, std::ios::binary);
@@ -427,7 +456,7 @@ private:
 // ---- the reader ---------------------------------------------------------------------------------------------------------------
 class CramReader : public AlnReader {
 public:
-    CramReader(const std::string& path, const std::string& fasta) : ref_(fasta) {
+    CramReader(const std::string& path, const std::string& fasta, int threads) : ref_(fasta), threads_(std::max(threads, 1)) {
         fd_ = ::open(path.c_str(), O_RDONLY);
         if (fd_ < 0) throw HostError(10, "Unable to open BAM file: " + path);
         struct stat st;
@@ -441,14 +470,20 @@ public:
         if (major_ != 2 && major_ != 3) bad("version " + std::to_string(major_) + " (2.x and 3.x are supported)");
         cur_.take(20);
         read_sam_header();
+        ref_.declare(hdr_.ref_names);
     }
-    ~CramReader() override { if (map_ && map_ != MAP_FAILED) munmap(const_cast<uint8_t*>(map_), size_); if (fd_ >= 0) ::close(fd_); }
+    ~CramReader() override {
+        for (auto& f : inflight_) if (f.valid()) f.wait();   // they read the mapping
+        inflight_.clear(); if (map_ && map_ != MAP_FAILED) munmap(const_cast<uint8_t*>(map_), size_); if (fd_ >= 0) ::close(fd_); }
     const AlnHeader& header() const override { return hdr_; }
     bool next(RawAln& out) override {
         while (at_ >= ready_.size()) { ready_.clear(); at_ = 0; if (!next_container()) return false; }
         out = std::move(ready_[at_++]);
         return true;
     }
+    // Containers are self-contained (their own compression header, mates resolved within a slice), so with threads_ > 1 the
+    // caller's thread only walks the container headers and up to 2 x threads_ bodies are decoded ahead of it, handed back
+    // in file order.  An error inside a container surfaces when next() reaches that container, like the sequential reader.
 
 private:
     struct ContainerHeader { int32_t length, ref_id, start, span, n_records, n_blocks; int64_t counter; std::vector<int32_t> landmarks; };
@@ -500,20 +535,43 @@ private:
         bool named = false;
     };
 
-    bool next_container() {
-        if (cur_.p >= cur_.end) return false;
-        const ContainerHeader h = read_container_header();
-        const uint8_t* body = cur_.take((size_t)std::max(h.length, 0));
-        if (h.n_records == 0) return cur_.p < cur_.end;   // EOF marker / empty container
-        Cursor c{body, body + h.length};
+    // the next container with records in it: its body, or {nullptr, 0} at the end of the file
+    std::pair<const uint8_t*, size_t> scan_container() {
+        while (cur_.p < cur_.end) {
+            const ContainerHeader h = read_container_header();
+            const uint8_t* body = cur_.take((size_t)std::max(h.length, 0));
+            if (h.n_records != 0) return {body, (size_t)h.length};   // else the EOF marker / an empty container
+        }
+        return {nullptr, 0};
+    }
+    std::vector<RawAln> decode_container(const uint8_t* body, size_t length) const {
+        std::vector<RawAln> out;
+        Cursor c{body, body + length};
         Block chb = read_block(c, major_);
         if (chb.content_type != 1) bad("compression header expected");
         const CompHeader ch = parse_comp_header(chb);
-        while (c.p < c.end) decode_slice(c, ch);
+        while (c.p < c.end) decode_slice(c, ch, out);
+        return out;
+    }
+    bool next_container() {
+        if (threads_ <= 1) {
+            const auto b = scan_container();
+            if (!b.first) return false;
+            ready_ = decode_container(b.first, b.second);
+            return true;
+        }
+        while (!scanned_all_ && inflight_.size() < 2 * (size_t)threads_) {
+            const auto b = scan_container();
+            if (!b.first) { scanned_all_ = true; break; }
+            inflight_.push_back(std::async(std::launch::async, [this, b] { return decode_container(b.first, b.second); }));
+        }
+        if (inflight_.empty()) return false;
+        ready_ = inflight_.front().get();
+        inflight_.pop_front();
         return true;
     }
 
-    void decode_slice(Cursor& c, const CompHeader& ch) {
+    void decode_slice(Cursor& c, const CompHeader& ch, std::vector<RawAln>& out) const {
         Block shb = read_block(c, major_);
         if (shb.content_type != 2) bad("slice header expected");
         Cursor s{shb.data.data(), shb.data.data() + shb.data.size()};
@@ -533,6 +591,8 @@ private:
         SliceCtx ctx;
         for (Block& b : blocks) { if (b.content_type == 5) ctx.core = &b; else if (b.content_type == 4) ctx.ext[b.content_id] = &b; }
         if (!ctx.core) bad("slice without a core block");
+        for (const auto& kv : ch.ds) bind_blocks(*kv.second, ctx);
+        for (const auto& kv : ch.tags) bind_blocks(*kv.second, ctx);
 
         std::vector<Rec> recs((size_t)std::max(n_records, 0));
         int32_t last_apos = slice_start;          // AP deltas run from the slice's start (htslib: s->last_apos = hdr->ref_seq_start)
@@ -547,7 +607,7 @@ private:
             }
             x.a.pos = x.apos - 1;
             x.a.mtid = x.mate_ref; x.a.mpos = x.mate_pos - 1; x.a.isize = x.tlen == INT_MIN ? 0 : x.tlen;
-            ready_.push_back(std::move(x.a));
+            out.push_back(std::move(x.a));
         }
     }
 
@@ -557,36 +617,36 @@ private:
     }
 
     void decode_record(const CompHeader& ch, SliceCtx& ctx, int32_t slice_ref, Rec& x, int32_t /*index*/, int32_t& last_apos,
-                       std::vector<uint8_t>& scratch) {
-        auto need = [&](const char* k) -> const Codec& { const Codec* e = ch.get(k); if (!e) bad(std::string("data series ") + k + " missing"); return *e; };
+                       std::vector<uint8_t>& scratch) const {
+        auto need = [&](const Codec* e, const char* k) -> const Codec& { if (!e) bad(std::string("data series ") + k + " missing"); return *e; };
         RawAln& a = x.a;
         a = RawAln();
-        const int32_t bf = decode_int(need("BF"), ctx);
-        const int32_t cf = decode_int(need("CF"), ctx);
+        const int32_t bf = decode_int(need(ch.BF, "BF"), ctx);
+        const int32_t cf = decode_int(need(ch.CF, "CF"), ctx);
         a.flag = (uint16_t)bf;
-        a.tid = slice_ref == -2 ? decode_int(need("RI"), ctx) : slice_ref;
+        a.tid = slice_ref == -2 ? decode_int(need(ch.RI, "RI"), ctx) : slice_ref;
         if (a.tid < -1 || a.tid >= (int32_t)hdr_.ref_names.size()) bad("reference id");
-        int32_t len = decode_int(need("RL"), ctx);
+        int32_t len = decode_int(need(ch.RL, "RL"), ctx);
         if (len < 0) bad("read length");
-        x.apos = decode_int(need("AP"), ctx);
+        x.apos = decode_int(need(ch.AP, "AP"), ctx);
         if (ch.ap_delta) x.apos += last_apos;
         last_apos = x.apos;
-        const int32_t rg = decode_int(need("RG"), ctx);
-        if (ch.names_included) { decode_bytes(need("RN"), ctx, -1, &scratch); a.qname.assign(scratch.begin(), scratch.end()); x.named = !scratch.empty(); }
+        const int32_t rg = decode_int(need(ch.RG, "RG"), ctx);
+        if (ch.names_included) { decode_bytes(need(ch.RN, "RN"), ctx, -1, &scratch); a.qname.assign(scratch.begin(), scratch.end()); x.named = !scratch.empty(); }
         x.mate_line = -1; x.mate_ref = -1; x.mate_pos = 0; x.mate_flags = 0; x.tlen = INT_MIN;
         if (cf & 2) {                                   // detached: the mate's fields are stored
-            x.mate_flags = decode_int(need("MF"), ctx);
-            if (!ch.names_included) { decode_bytes(need("RN"), ctx, -1, &scratch); a.qname.assign(scratch.begin(), scratch.end()); x.named = !scratch.empty(); }
-            x.mate_ref = decode_int(need("NS"), ctx);
-            x.mate_pos = decode_int(need("NP"), ctx);
-            x.tlen = decode_int(need("TS"), ctx);
+            x.mate_flags = decode_int(need(ch.MF, "MF"), ctx);
+            if (!ch.names_included) { decode_bytes(need(ch.RN, "RN"), ctx, -1, &scratch); a.qname.assign(scratch.begin(), scratch.end()); x.named = !scratch.empty(); }
+            x.mate_ref = decode_int(need(ch.NS, "NS"), ctx);
+            x.mate_pos = decode_int(need(ch.NP, "NP"), ctx);
+            x.tlen = decode_int(need(ch.TS, "TS"), ctx);
         } else if (cf & 4) {                            // the mate follows in this slice
-            x.mate_line = decode_int(need("NF"), ctx);   // distance; made absolute by the caller's index below
+            x.mate_line = decode_int(need(ch.NF, "NF"), ctx);   // distance; made absolute by the caller's index below
             x.mate_line = -2 - x.mate_line;              // marker: resolved in resolve_mates (needs the record index)
         }
         // auxiliary tags
         bool has_nm = false, has_md = false;
-        if (const Codec* tl = ch.get("TL")) {
+        if (const Codec* tl = ch.TL) {
             const int32_t line = decode_int(*tl, ctx);
             if (line < 0 || line >= (int32_t)ch.tag_lines.size()) bad("tag line");
             for (const auto& t : ch.tag_lines[(size_t)line]) {
@@ -598,10 +658,10 @@ private:
                 if (t[0] == 'N' && t[1] == 'M') has_nm = true;
                 if (t[0] == 'M' && t[1] == 'D') has_md = true;
             }
-        } else if (const Codec* tc = ch.get("TC")) {    // CRAM 2.x: count + ids
+        } else if (const Codec* tc = ch.TC) {    // CRAM 2.x: count + ids
             const int32_t n = decode_int(*tc, ctx);
             for (int32_t i = 0; i < n; ++i) {
-                const int32_t key = decode_int(need("TN"), ctx);
+                const int32_t key = decode_int(need(ch.TN, "TN"), ctx);
                 auto it = ch.tags.find(key);
                 if (it == ch.tags.end()) bad("tag encoding");
                 decode_bytes(*it->second, ctx, -1, &scratch);
@@ -632,61 +692,61 @@ private:
                 push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)n);
                 ref_pos += n; seq_pos += n;
             };
-            const int32_t fn = decode_int(need("FN"), ctx);
+            const int32_t fn = decode_int(need(ch.FN, "FN"), ctx);
             for (int32_t f = 0; f < fn; ++f) {
-                const uint8_t op = decode_byte(need("FC"), ctx);
-                const int32_t pos = decode_int(need("FP"), ctx) + prev;
+                const uint8_t op = decode_byte(need(ch.FC, "FC"), ctx);
+                const int32_t pos = decode_int(need(ch.FP, "FP"), ctx) + prev;
                 if (pos <= 0 || pos > len + 1) bad("feature position");
                 if (pos > seq_pos) implicit_match(pos - seq_pos);
                 prev = pos;
                 switch (op) {
-                    case 'S': { decode_bytes(need("SC"), ctx, -1, &scratch);
+                    case 'S': { decode_bytes(need(ch.SC, "SC"), ctx, -1, &scratch);
                                 if (run_len) { a.cigar.push_back((run_len << 4) | (uint32_t)run_op); run_len = 0; }
                                 a.cigar.push_back(((uint32_t)scratch.size() << 4) | 4u); run_op = 4;
                                 seq_pos += (int32_t)scratch.size(); break; }
-                    case 'X': { decode_byte(need("BS"), ctx);
+                    case 'X': { decode_byte(need(ch.BS, "BS"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 0, 1);
                                 if (count_nm && ref_pos < ref_len) ++nm;
                                 ++seq_pos; ++ref_pos; break; }
-                    case 'D': { const int32_t n = decode_int(need("DL"), ctx);
+                    case 'D': { const int32_t n = decode_int(need(ch.DL, "DL"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 2, (uint32_t)n);
                                 if (count_nm) nm += (uint32_t)std::max<int64_t>(0, std::min<int64_t>(n, ref_len - ref_pos));
                                 ref_pos += n; break; }
-                    case 'I': { decode_bytes(need("IN"), ctx, -1, &scratch);
+                    case 'I': { decode_bytes(need(ch.IN, "IN"), ctx, -1, &scratch);
                                 push_cigar(a.cigar, run_len, run_op, 1, (uint32_t)scratch.size());
                                 seq_pos += (int32_t)scratch.size(); if (count_nm) nm += (uint32_t)scratch.size(); break; }
-                    case 'i': { decode_byte(need("BA"), ctx);
+                    case 'i': { decode_byte(need(ch.BA, "BA"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 1, 1);
                                 ++seq_pos; if (count_nm) ++nm; break; }
-                    case 'b': { decode_bytes(need("BB"), ctx, -1, &scratch);
+                    case 'b': { decode_bytes(need(ch.BB, "BB"), ctx, -1, &scratch);
                                 push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)scratch.size());
                                 if (count_nm) nm += (uint32_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)scratch.size(), ref_len - ref_pos));
                                 seq_pos += (int32_t)scratch.size(); ref_pos += (int64_t)scratch.size(); break; }
-                    case 'q': { decode_bytes(need("QQ"), ctx, -1, &scratch);
+                    case 'q': { decode_bytes(need(ch.QQ, "QQ"), ctx, -1, &scratch);
                                 push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)scratch.size());
                                 seq_pos += (int32_t)scratch.size(); ref_pos += (int64_t)scratch.size(); break; }
-                    case 'B': { decode_byte(need("BA"), ctx); decode_byte(need("QS"), ctx);
+                    case 'B': { decode_byte(need(ch.BA, "BA"), ctx); decode_byte(need(ch.QS, "QS"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 0, 1);
                                 if (count_nm && ref_pos < ref_len) ++nm;
                                 ++seq_pos; ++ref_pos; break; }
-                    case 'Q': decode_byte(need("QS"), ctx); break;
-                    case 'H': { const int32_t n = decode_int(need("HC"), ctx); push_cigar(a.cigar, run_len, run_op, 5, (uint32_t)n); break; }
-                    case 'P': { const int32_t n = decode_int(need("PD"), ctx); push_cigar(a.cigar, run_len, run_op, 6, (uint32_t)n); break; }
-                    case 'N': { const int32_t n = decode_int(need("RS"), ctx); push_cigar(a.cigar, run_len, run_op, 3, (uint32_t)n); ref_pos += n; break; }
+                    case 'Q': decode_byte(need(ch.QS, "QS"), ctx); break;
+                    case 'H': { const int32_t n = decode_int(need(ch.HC, "HC"), ctx); push_cigar(a.cigar, run_len, run_op, 5, (uint32_t)n); break; }
+                    case 'P': { const int32_t n = decode_int(need(ch.PD, "PD"), ctx); push_cigar(a.cigar, run_len, run_op, 6, (uint32_t)n); break; }
+                    case 'N': { const int32_t n = decode_int(need(ch.RS, "RS"), ctx); push_cigar(a.cigar, run_len, run_op, 3, (uint32_t)n); ref_pos += n; break; }
                     default: bad(std::string("feature code ") + (char)op);
                 }
             }
             if (len >= seq_pos) implicit_match(len - seq_pos + 1);
             if (run_len) a.cigar.push_back((run_len << 4) | (uint32_t)run_op);
             x.aend = (int32_t)ref_pos;
-            a.mapq = (uint8_t)decode_int(need("MQ"), ctx);
-            if (cf & 1) decode_bytes(need("QS"), ctx, len, nullptr);
+            a.mapq = (uint8_t)decode_int(need(ch.MQ, "MQ"), ctx);
+            if (cf & 1) decode_bytes(need(ch.QS, "QS"), ctx, len, nullptr);
             if (have_ref && !has_md && !(cf & 8)) { AuxField m; m.tag[0] = 'M'; m.tag[1] = 'D'; m.type = 'Z'; m.ival = 0; a.aux.push_back(m); }   // regenerated too
             if (count_nm) { AuxField f; f.tag[0] = 'N'; f.tag[1] = 'M'; f.type = 'I'; f.ival = nm; a.aux.push_back(f); }
             if (cf & 8) len = 0;
         } else {
-            if (len) decode_bytes(need("BA"), ctx, len, nullptr);
-            if (cf & 1) decode_bytes(need("QS"), ctx, len, nullptr);
+            if (len) decode_bytes(need(ch.BA, "BA"), ctx, len, nullptr);
+            if (cf & 1) decode_bytes(need(ch.QS, "QS"), ctx, len, nullptr);
         }
         a.l_qseq = len;
         if (rg >= 0 && rg < n_read_groups_) { AuxField f; f.tag[0] = 'R'; f.tag[1] = 'G'; f.type = 'Z'; f.ival = 0; a.aux.push_back(f); }
@@ -709,7 +769,7 @@ private:
     }
 
     // mate fields of the records that were not stored "detached" (htslib cram_decode_slice_xref)
-    void resolve_mates(std::vector<Rec>& recs) {
+    static void resolve_mates(std::vector<Rec>& recs) {
         const int32_t n = (int32_t)recs.size();
         for (int32_t r = 0; r < n; ++r) if (recs[(size_t)r].mate_line <= -2) recs[(size_t)r].mate_line = r + 1 + (-2 - recs[(size_t)r].mate_line);
         for (int32_t r = 0; r < n; ++r) {
@@ -761,15 +821,18 @@ private:
     int major_ = 3;
     int32_t n_read_groups_ = 0;
     AlnHeader hdr_;
-    ReferenceNs ref_;
+    mutable ReferenceNs ref_;   // lazily loaded per contig, under a once-flag
+    int threads_ = 1;
+    bool scanned_all_ = false;
+    std::deque<std::future<std::vector<RawAln>>> inflight_;
     std::vector<RawAln> ready_;
     size_t at_ = 0;
 };
 
 }  // namespace
 
-std::unique_ptr<AlnReader> open_cram(const std::string& path, const std::string& fasta) {
-    return std::unique_ptr<AlnReader>(new CramReader(path, fasta));
+std::unique_ptr<AlnReader> open_cram(const std::string& path, const std::string& fasta, int threads) {
+    return std::unique_ptr<AlnReader>(new CramReader(path, fasta, threads));
 }
 
 }  // namespace rsqh

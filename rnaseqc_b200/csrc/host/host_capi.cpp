@@ -118,7 +118,7 @@ int rsqh_decode_file(void* hv, const char* path, const char* chimeric_tag, const
             if (fp) { if (std::fread(m, 1, 2, fp) != 2) m[0] = 0; std::fclose(fp); }
             if (m[0] == 0x1f && m[1] == 0x8b) pb.reset(new ParallelBamDecoder(path, threads));
         }
-        if (!pb) rd = AlnReader::open(path, g_fasta);
+        if (!pb) rd = AlnReader::open(path, g_fasta, threads);
         Decoder dec(pb ? pb->header() : rd->header(), h->ann.contigs, n_ann_contigs, opt);
         if (pb) {
             std::vector<rsq_read> r1;

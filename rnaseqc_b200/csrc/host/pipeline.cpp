@@ -243,7 +243,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
             const size_t got = std::fread(m, 1, 2, fp);
             std::fclose(fp);
             if (got == 2 && m[0] == 0x1f && m[1] == 0x8b && opt.decode_threads > 0) pbam.reset(new ParallelBamDecoder(opt.bam, opt.decode_threads));
-            else reader = AlnReader::open(opt.bam, opt.fasta);
+            else reader = AlnReader::open(opt.bam, opt.fasta, opt.decode_threads);
         }
         const AlnHeader& aln_header = pbam ? pbam->header() : reader->header();
         Decoder decoder(aln_header, A.contigs, n_contigs, opt.decode);

@@ -37,6 +37,27 @@ def test_oracle_cli_reads_cram_like_the_reference(libs, tmp_path):
     assert int(metrics["High Quality Reads"]) > 1000 and int(metrics["Mismatched Bases"]) > 1000      # NM was regenerated
 
 
+@pytest.mark.parametrize("threads", [0, 1, 3, 16])
+def test_container_decode_threads_do_not_change_the_output(libs, tmp_path, threads):
+    # containers are decoded concurrently and handed back in file order: same bytes out for any thread count
+    d = _golden(tmp_path)
+    out = os.path.join(d, "out")
+    run_cli(libs["oracle_cli"], os.path.join(d, "c.gtf"), os.path.join(d, "c.cram"), out, "--fasta", os.path.join(d, "c.fa"),
+            "--coverage", "--bed", os.path.join(d, "c.bed"), "--decode-threads", str(threads))
+    same = compare_outputs(out, os.path.join(d, "expected"))
+    assert "c.cram.gene_reads.gct" in same and "c.cram.fragmentSizes.txt" in same
+
+
+@pytest.mark.parametrize("threads", [0, 4])
+def test_truncated_cram_is_an_error(libs, tmp_path, threads):
+    d = _golden(tmp_path)
+    raw = open(os.path.join(d, "c.cram"), "rb").read()
+    open(os.path.join(d, "t.cram"), "wb").write(raw[: len(raw) * 2 // 3])
+    p = run_cli(libs["oracle_cli"], os.path.join(d, "c.gtf"), os.path.join(d, "t.cram"), os.path.join(d, "out"), "--fasta",
+                os.path.join(d, "c.fa"), "--decode-threads", str(threads), check=False)
+    assert p.returncode != 0
+
+
 def test_cram_without_a_reference_fails_like_the_reference(libs, tmp_path):
     d = _golden(tmp_path)
     p = run_cli(libs["oracle_cli"], os.path.join(d, "c.gtf"), os.path.join(d, "c.cram"), os.path.join(d, "out"), check=False)
