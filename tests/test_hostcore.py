@@ -186,3 +186,80 @@ def test_dense_overlapping_annotation_and_edge_blocks(libs, tmp_path):
         assert_same(api, got, want, f"dense annotation, strand mode {mode}")
         assert got_bytes == want_bytes
         assert want.counter("Ambiguous Reads") > 0 and (mode == 2 or want.counter("rRNA Reads") > 0) and want.counter("Exonic Reads") > 0
+
+
+def _fuzz_case(api, tmp_path, seed):
+    """Random small annotation dense enough that most reads see several overlapping genes on both strands (nested, abutting and
+    identical exons, rRNA genes, a globin name, exons on 1 kb bucket boundaries), and random reads with 0-6 blocks whose ends fall
+    on / next to the cuts."""
+    rng = np.random.default_rng(seed)
+    contigs = ["chr1", "chr2", "chrM"][: int(rng.integers(1, 4))]
+    span = int(rng.choice([6000, 40000, 300000]))
+    rows, cuts = [], {c: [] for c in contigs}
+    n_genes = int(rng.integers(3, 60))
+    for g in range(n_genes):
+        chrom = contigs[int(rng.integers(0, len(contigs)))]
+        gs = int(rng.integers(1, span))
+        if rng.random() < 0.2:
+            gs = max(1, (gs >> 10 << 10) + int(rng.integers(-2, 3)))                 # near a 1 kb bucket boundary
+        ge = gs + int(rng.integers(1, max(2, span // 4)))
+        strand = "+-."[int(rng.choice([0, 0, 1, 1, 2]))]
+        ttype = "rRNA" if rng.random() < 0.1 else ("Mt_rRNA" if rng.random() < 0.05 else "protein_coding")
+        gname = "HBB" if rng.random() < 0.05 else f"N{g}"
+        common = f'gene_id "G{g}"; transcript_id "G{g}"; gene_type "{ttype}"; gene_name "{gname}"; transcript_type "{ttype}";'
+        rows.append(f"{chrom}\tf\tgene\t{gs}\t{ge}\t.\t{strand}\t.\t{common}")
+        k, p = 0, gs
+        while p <= ge and k < 12:
+            es = p
+            ee = min(ge, es + int(rng.integers(0, max(1, (ge - gs) // 3 + 1))))
+            rows.append(f'{chrom}\tf\texon\t{es}\t{ee}\t.\t{strand}\t.\t{common} exon_id "G{g}_{k}";')
+            cuts[chrom] += [es, ee, ee + 1]
+            k += 1
+            p = ee + 1 + int(rng.choice([0, 0, 1, 5, 100, 1000]))                     # abutting exons are common
+        cuts[chrom] += [gs, ge, ge + 1]
+    gtf = tmp_path / f"fuzz{seed}.gtf"
+    gtf.write_text("\n".join(rows) + "\n")
+    ann = api.Annotation(str(gtf))
+    recs, blks = [], []
+    n_reads = 1500
+    for i in range(n_reads):
+        ci = int(rng.integers(0, len(contigs)))
+        cs = cuts[contigs[ci]]
+        nb = int(rng.choice([0, 1, 1, 1, 1, 2, 2, 3, 6]))
+        if cs and rng.random() < 0.8:
+            p = max(1, int(cs[int(rng.integers(0, len(cs)))]) + int(rng.integers(-3, 4)) - int(rng.choice([0, 0, 10, 50, 100])))
+        else:
+            p = int(rng.integers(1, span + 3000))
+        off, first, bl = len(blks), p, []
+        for b in range(nb):
+            ln = int(rng.choice([0, 1, 2, 10, 25, 50, 76, 101, 400]))
+            bl.append((p, ln))
+            p += ln + int(rng.choice([0, 1, 30, 500, 2000, 20000]))
+        blks.extend(bl)
+        pos = first - 1
+        end = (bl[-1][0] - 1 + bl[-1][1]) if bl else pos + 1
+        flag = int(rng.choice([99, 147, 83, 163, 0, 16, 1024 + 99, 256 + 99, 512 + 147, 4, 2048 + 83, 65, 129, 73]))
+        mapq = int(rng.choice([255, 255, 255, 60, 3, 0]))
+        nm = int(rng.choice([0, 0, 1, 6, 7, 12]))
+        aux = int(rng.choice([1, 1, 1, 0, 3, 5, 9, 0x11, 0x21]))
+        contig = ann.contig_index(contigs[ci]) if rng.random() > 0.03 else -1
+        mpos = pos + int(rng.choice([150, -150, 0, 3_000_000]))
+        name = int(rng.integers(1, n_reads // 2 + 2)) * 0x9E3779B97F4A7C15 % (1 << 64)   # mates and repeats share names
+        recs.append((pos, mpos, end, 200, 101, nm, flag, mapq, aux, contig, int(rng.choice([0, 0, 0, 1, 2])), 0, name, off, nb, 0))
+    reads = np.array(recs, dtype=api.READ_DTYPE)
+    blocks = np.array(blks, dtype=api.BLOCK_DTYPE) if blks else np.zeros(0, api.BLOCK_DTYPE)
+    order = np.lexsort((reads["pos"], reads["contig"].astype(np.int64) % 70000))       # contig -1 last, then stream order
+    return ann, reads[order], blocks, rng
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_random_dense_annotations(libs, tmp_path, seed):
+    api = libs["api"]
+    ann, reads, blocks, rng = _fuzz_case(api, tmp_path, 7000 + seed)
+    kw = dict(strand_mode=int(rng.integers(0, 3)), unpaired=bool(rng.random() < 0.3), exclude_chimeric=bool(rng.random() < 0.3),
+              n_filter_tags=int(rng.choice([0, 0, 1, 2])), mapq=int(rng.choice([255, 255, 60, 3])), mismatches=int(rng.choice([6, 6, 0, 12])))
+    cfg = lambda: api.make_config(max_records=len(reads), **kw)
+    want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+    got, got_bytes, _ = run_hostcore(api, ann, reads, blocks, cfg())
+    assert_same(api, got, want, f"fuzz seed {seed} {kw}")
+    assert got_bytes == want_bytes
