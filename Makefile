@@ -15,7 +15,7 @@ HOST_SRCS := annotation.cpp alnreader.cpp cramreader.cpp bamparallel.cpp fasta.c
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
-oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so
+oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so
 ref:
 	$(MAKE) -f oracle/Makefile.ref
 
@@ -44,6 +44,10 @@ $(ODIR)/librsq_oracle.so: oracle/rsq_oracle.cpp include/rsq_b200.h
 $(ODIR)/libhostcore.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
 	@mkdir -p $(ODIR)
 	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
+# the same with the kernel's experimental compile-time variants that change the per-record logic (tools/ab_build.sh builds the CUDA side)
+$(ODIR)/libhostcore_sd.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
+	@mkdir -p $(ODIR)
+	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -DRSQ_STAGE_DESC -DRSQ_STAGE_N=64 -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
 
 $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
 	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'

@@ -27,7 +27,7 @@ struct EiDesc { uint32_t cover_off; uint32_t flags_n; };   // flags_n: class bit
 struct EiIndex {
     std::vector<uint32_t>   ei_off;     // [n_contigs+1] first interval of each contig (its INT32_MIN sentinel)
     std::vector<int32_t>    ei_start;   // [n_ei + kEiPad] interval starts, ascending inside a contig
-    std::vector<EiDesc>     ei_desc;    // [n_ei + 1]
+    std::vector<EiDesc>     ei_desc;    // [n_ei + 1 + kEiPad]
     std::vector<CoverEntry> cover;      // covering exons, interval-major, list order inside an interval
     std::vector<uint32_t>   eib_off;    // [n_contigs+1] first bucket entry of each contig (each contig has n_b + 1 entries)
     std::vector<uint32_t>   eib;        // interval containing the bucket start; last entry of a contig = its last interval
@@ -116,7 +116,7 @@ inline std::string build_ei_index(const rsq_annotation* a, EiIndex& X) {
     }
     X.ei_off[nc] = (uint32_t)X.ei_start.size();
     X.eib_off[nc] = (uint32_t)X.eib.size();
-    X.ei_desc.push_back(EiDesc{(uint32_t)X.cover.size(), 0u});
+    X.ei_desc.insert(X.ei_desc.end(), 1 + kEiPad, EiDesc{(uint32_t)X.cover.size(), 0u});   // padded like ei_start: staged by bulk copies too
     X.ei_start.insert(X.ei_start.end(), kEiPad, INT32_MAX);
     X.cover.push_back(CoverEntry{0, -1, 0, 0, 0, 0});   // spare entry: the fast path loads cover[cover_off] even when the count is 0
     return std::string();

@@ -59,6 +59,9 @@ RSQ_HD void frac_q64(const unsigned long long* recip64, uint32_t isz, uint32_t l
 // Warp-uniform description of the slice of ei_start the warp has staged in shared memory for its current tile.
 struct TileWin {
     const int32_t* st;   // staged copy of ei_start[base .. ), shared memory on the device
+#ifdef RSQ_STAGE_DESC
+    const uint2* sd;     // staged copy of ei_desc[base .. ) (experiment: the descriptor read leaves the dependent-load chain)
+#endif
     int base;            // global interval index of st[0]
     int k0;              // interval containing the first coordinate served (>= base)
     int hi;              // one past the last staged interval that may be used (global index)
@@ -88,6 +91,22 @@ struct GlobalStarts {
     RSQ_HD int operator[](int k) const { return ldro(p + k); }
 };
 
+// descriptor of a STAGED interval (base <= k < base + kStageN)
+RSQ_HD uint2 staged_desc(const AnnView& ann, const TileWin& w, int k) {
+#ifdef RSQ_STAGE_DESC
+    (void)ann; return w.sd[k - w.base];
+#else
+    (void)w; return ldro(ann.ei_desc + k);
+#endif
+}
+RSQ_HD uint32_t staged_desc_flags(const AnnView& ann, const TileWin& w, int k) {
+#ifdef RSQ_STAGE_DESC
+    (void)ann; return w.sd[k - w.base].y;
+#else
+    (void)w; return ldro(&ann.ei_desc[k].y);
+#endif
+}
+
 // Interval of a block's start and the OR of the class bits of every interval the closed block [bs, be] touches
 // (intersectBlock + intersectInterval, src/Expression.cpp:106-117, src/GTF.cpp:171-179).  Returns the descriptor of k(bs).
 RSQ_HD uint2 block_lookup(const AnnView& ann, const TileWin& w, int contig, int bs, int be, uint32_t& cls) {
@@ -95,9 +114,9 @@ RSQ_HD uint2 block_lookup(const AnnView& ann, const TileWin& w, int contig, int 
     if (w.on && bs >= w.wmin && be < w.lastv) {
         const StagedStarts s{w.st, w.base};
         const int k = ei_search(s, w.k0, w.hi - 1, bs);
-        d = ldro(ann.ei_desc + k);
+        d = staged_desc(ann, w, k);
         cls |= d.y & 0xffffu;
-        for (int kk = k + 1; kk < w.hi && s[kk] <= be; ++kk) cls |= ldro(&ann.ei_desc[kk].y) & 0xffffu;
+        for (int kk = k + 1; kk < w.hi && s[kk] <= be; ++kk) cls |= staged_desc_flags(ann, w, kk) & 0xffffu;
     } else {
         const int c_hi = (int)ldro(ann.ei_off + contig + 1);
         const int bk_lo = (int)ldro(ann.eib_off + contig), bk_n = (int)ldro(ann.eib_off + contig + 1) - bk_lo - 1;
@@ -337,14 +356,14 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
                 if (s[lo1 + half] <= bs1) lo1 += half;
                 len -= half;
             }
-            const uint2 d0 = ldro(ann.ei_desc + lo0), d1 = ldro(ann.ei_desc + lo1);
+            const uint2 d0 = staged_desc(ann, w, lo0), d1 = staged_desc(ann, w, lo1);
             // a block may run over ONE cut (a read that ends on the last base of its exon always does: the reference's closed
             // end is one past it): the class bits of the next interval join in; two cuts or more take the general path
             const int na0 = lo0 + 1 < w.hi ? s[lo0 + 1] : INT32_MAX, na1 = lo1 + 1 < w.hi ? s[lo1 + 1] : INT32_MAX;
             const int nb0 = lo0 + 2 < w.hi ? s[lo0 + 2] : INT32_MAX, nb1 = lo1 + 2 < w.hi ? s[lo1 + 2] : INT32_MAX;
             uint32_t over = 0;
-            if (na0 <= be0) over |= ldro(&ann.ei_desc[lo0 + 1].y);
-            if (na1 <= be1) over |= ldro(&ann.ei_desc[lo1 + 1].y);
+            if (na0 <= be0) over |= staged_desc_flags(ann, w, lo0 + 1);
+            if (na1 <= be1) over |= staged_desc_flags(ann, w, lo1 + 1);
             const uint32_t cn0 = d0.y >> 16, cn1 = d1.y >> 16;
             if (nb0 > be0 && nb1 > be1 && cn0 <= 1u && cn1 <= 1u) {
                 // the cover array carries one spare entry, so these loads are unconditional (used only when cn == 1)
@@ -364,10 +383,10 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
                     r.bs = k.x; r.be = k.x + k.y;
                     if (!(r.bs >= w.wmin && r.be < w.lastv)) return false;
                     const int lo = ei_search(s, w.k0, w.hi - 1, r.bs);
-                    const uint2 d = ldro(ann.ei_desc + lo);
+                    const uint2 d = staged_desc(ann, w, lo);
                     const int na = lo + 1 < w.hi ? s[lo + 1] : INT32_MAX, nn = lo + 2 < w.hi ? s[lo + 2] : INT32_MAX;
                     flags = d.y & 0xffffu;
-                    if (na <= r.be) flags |= ldro(&ann.ei_desc[lo + 1].y) & 0xffffu;
+                    if (na <= r.be) flags |= staged_desc_flags(ann, w, lo + 1) & 0xffffu;
                     r.coff = d.x; r.cn = d.y >> 16;
                     if (nn <= r.be || r.cn > 1u) return false;
                     h = cover_head(ann, d.x);

@@ -86,6 +86,9 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
 constexpr int kStageN = RSQ_STAGE_N;    // a multiple of 4 (16-byte bulk-copy granularity), at most kEiPad
 struct __align__(16) WarpStage {
     int32_t starts[kStageN];
+#ifdef RSQ_STAGE_DESC
+    uint2 descs[kStageN];             // experiment: the descriptors of the staged intervals ride along (second bulk copy, same barrier)
+#endif
     unsigned long long fkey[32];      // fragment-tracker keys parked for one tile (0 = none), one slot per lane
     uint32_t fgene[32];               // the gene each parked key counts toward
     uint32_t fpeers[32];              // the lanes of that tile that counted toward the same gene (MATCH.ANY of the epilogue)
@@ -292,6 +295,9 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // ---- stage this tile's run of interval starts (warp-uniform) ----------------------------------------------------------
     TileWin w;
     w.st = st->starts; w.base = 0; w.k0 = 0; w.hi = 0; w.wmin = 0; w.lastv = 0; w.on = false;
+#ifdef RSQ_STAGE_DESC
+    w.sd = st->descs;
+#endif
     bool to_end = false;
 #ifndef RSQ_AB_NO_STAGE
     if constexpr (!kLegacy) {
@@ -310,8 +316,14 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             w.on = true;
             __syncwarp();                                                // every lane is done with the previous tile's copy
             if (lane == 0) {
+#ifdef RSQ_STAGE_DESC
+                mbar_expect_tx(mbar, (uint32_t)(kStageN * 12));
+                tma_bulk_g2s(smem_u32(st->starts), ann.ei_start + w.base, (uint32_t)(kStageN * 4), mbar);   // both arrays are padded
+                tma_bulk_g2s(smem_u32(st->descs), ann.ei_desc + w.base, (uint32_t)(kStageN * 8), mbar);
+#else
                 mbar_expect_tx(mbar, (uint32_t)(kStageN * 4));
                 tma_bulk_g2s(smem_u32(st->starts), ann.ei_start + w.base, (uint32_t)(kStageN * 4), mbar);   // the array is padded
+#endif
             }
         }
     }

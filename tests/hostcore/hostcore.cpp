@@ -28,7 +28,10 @@ struct HostMem {
     void cov_range(unsigned int* p, unsigned int len) const { p[0] += 1u; p[len] -= 1u; }
     bool frag_insert(unsigned long long key) const { return set->insert(key).second; }
 };
-constexpr int kStageN = 128;
+#ifndef RSQ_STAGE_N
+#define RSQ_STAGE_N 128
+#endif
+constexpr int kStageN = RSQ_STAGE_N;
 }  // namespace
 
 extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, const rsq_read* reads, size_t n_reads, const rsq_block* blocks,
@@ -61,6 +64,9 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
     stats[0] = stats[1] = stats[4] = stats[5] = stats[6] = stats[7] = 0; stats[2] = X.ei_start.size() - kEiPad; stats[3] = X.cover.size();
 
     int32_t staged[kStageN];
+#ifdef RSQ_STAGE_DESC
+    uint2 staged_descs[kStageN];
+#endif
     const size_t n_tiles = (n_reads + 31) / 32;
     for (size_t tile = 0; tile < n_tiles; ++tile) {
         const size_t t0 = tile * 32, t1 = std::min(n_reads, t0 + 32);
@@ -68,6 +74,9 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
         int pmin = INT32_MAX, cmin = INT32_MAX, cmax = INT32_MIN;
         for (size_t i = t0; i < t1; ++i) { pmin = std::min(pmin, reads[i].pos); cmin = std::min<int>(cmin, reads[i].contig); cmax = std::max<int>(cmax, reads[i].contig); }
         TileWin w;
+#ifdef RSQ_STAGE_DESC
+        w.sd = staged_descs;
+#endif
         w.st = staged; w.base = 0; w.k0 = 0; w.hi = 0; w.wmin = 0; w.lastv = 0; w.on = false;
         if (cmin == cmax && cmin >= 0 && (uint32_t)cmin < ann.n_contigs && pmin >= 0 && pmin < INT32_MAX) {
             const int c_hi = (int)ann.ei_off[cmin + 1];
@@ -78,6 +87,9 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
             w.hi = std::min(w.base + kStageN, c_hi);
             w.on = true;
             memcpy(staged, ann.ei_start + w.base, sizeof staged);          // the bulk copy
+#ifdef RSQ_STAGE_DESC
+            memcpy(staged_descs, ann.ei_desc + w.base, sizeof staged_descs);
+#endif
             w.lastv = w.hi == c_hi ? INT32_MAX : staged[w.hi - 1 - w.base];
         }
         bool tile_general = false;

@@ -15,14 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOSTCORE = os.path.join(ROOT, "oracle", "_build", "libhostcore.so")
 
 
-def _hostcore():
-    lib = C.CDLL(HOSTCORE)
+VARIANTS = {"product": HOSTCORE, "stage_desc": os.path.join(ROOT, "oracle", "_build", "libhostcore_sd.so")}
+
+
+def _hostcore(path=HOSTCORE):
+    lib = C.CDLL(path)
     lib.hostcore_run.restype = C.c_int
     return lib
 
 
-def run_hostcore(api, ann, reads, blocks, cfg):
-    lib = _hostcore()
+def run_hostcore(api, ann, reads, blocks, cfg, variant="product"):
+    lib = _hostcore(VARIANTS[variant])
     G, E, L = ann.n_genes, ann.n_exons, ann.cov_len
     out = {k: np.zeros(n, np.uint64) for k, n in (("counters", 64), ("gene_reads", G), ("gene_unique", G), ("gene_fragments", G),
                                                    ("exon_whole", E), ("exon_fhi", E), ("exon_flo", E), ("bytes", 1), ("stats", 8))}
@@ -95,14 +98,15 @@ CONFIGS = {
 }
 
 
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_record_logic_matches_oracle_on_synthetic_records(libs, synth_case, name):
+def test_record_logic_matches_oracle_on_synthetic_records(libs, synth_case, name, variant):
     api = libs["api"]
     ann, reads, blocks = synth_case
     cfg = lambda: api.make_config(max_records=len(reads), **CONFIGS[name])
     want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
-    got, got_bytes, stats = run_hostcore(api, ann, reads, blocks, cfg())
-    assert_same(api, got, want, name)
+    got, got_bytes, stats = run_hostcore(api, ann, reads, blocks, cfg(), variant)
+    assert_same(api, got, want, name + " " + variant)
     assert got_bytes == want_bytes
     assert want.counter("Exonic Reads") > 50000 and want.gene_reads.sum() > 50000
     assert stats[0] > 0, "the staged-slice look-up must be exercised"
@@ -252,14 +256,15 @@ def _fuzz_case(api, tmp_path, seed):
     return ann, reads[order], blocks, rng
 
 
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
 @pytest.mark.parametrize("seed", range(24))
-def test_fuzz_random_dense_annotations(libs, tmp_path, seed):
+def test_fuzz_random_dense_annotations(libs, tmp_path, seed, variant):
     api = libs["api"]
     ann, reads, blocks, rng = _fuzz_case(api, tmp_path, 7000 + seed)
     kw = dict(strand_mode=int(rng.integers(0, 3)), unpaired=bool(rng.random() < 0.3), exclude_chimeric=bool(rng.random() < 0.3),
               n_filter_tags=int(rng.choice([0, 0, 1, 2])), mapq=int(rng.choice([255, 255, 60, 3])), mismatches=int(rng.choice([6, 6, 0, 12])))
     cfg = lambda: api.make_config(max_records=len(reads), **kw)
     want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
-    got, got_bytes, _ = run_hostcore(api, ann, reads, blocks, cfg())
-    assert_same(api, got, want, f"fuzz seed {seed} {kw}")
+    got, got_bytes, _ = run_hostcore(api, ann, reads, blocks, cfg(), variant)
+    assert_same(api, got, want, f"fuzz seed {seed} {kw} {variant}")
     assert got_bytes == want_bytes
