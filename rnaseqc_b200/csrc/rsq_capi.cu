@@ -512,7 +512,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     CU_TRY(cudaMalloc(&acc.frag_set, 8ull * c->frag_cap));
     acc.frag_cap = c->frag_cap;
     CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
-    CU_TRY(cudaMalloc(&acc.error_flag, 4));
+    CU_TRY(cudaMalloc(&acc.error_flag, 8));   // [0] the flag; [1] the tile counter of the RSQ_DYNAMIC_TILES experiment
     c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * c->n_exons + 100ull;   // ... | 100 GC-content bins
     CU_TRY(cudaMalloc(&c->d_export, 8ull * c->export_words));
     c->have_ann = true;

@@ -119,7 +119,7 @@ struct Accum {
     unsigned long long* frag_set;        // fragment-tracker hash set (open addressing), 0 = empty
     unsigned long long  frag_cap;        // slots (any number, not a power of two)
     unsigned long long* algo_bytes;      // [1]
-    unsigned int*       error_flag;      // [1] bit0: fragment set full, bit1: pair table full, bit2: candidate list full
+    unsigned int*       error_flag;      // [2] ([1]: scratch word, see launch_hot_path) bit0: fragment set full, bit1: pair table full, bit2: candidate list full
     // fragment-size sampler (BED mode)
     unsigned long long* pair_keys;       // mate map keys (name hash, 0 = empty)
     unsigned long long* pair_first;      // global record index of the FIRST candidate with this name (atomicMin)

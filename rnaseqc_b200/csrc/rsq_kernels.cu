@@ -273,7 +273,19 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // Persistent warps: warp w of the grid takes 32-record tiles w, w + W, w + 2W, ... No CTA barrier inside the loop.
     uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned long long own_lo = 0ull, own_hi = 0ull, own_bytes = 0ull;   // lane-owned counters (see the epilogue)
+#ifdef RSQ_DYNAMIC_TILES
+    // Experiment: after its first two tiles (static, so that the look-ahead below has something to look at) a warp takes the
+    // next unclaimed tile from a device counter, asked for one whole tile of work before it is needed: warps that drew cheap
+    // tiles (intergenic stretches) take more of them, and the end of the launch is not set by the unluckiest static stride.
+    uint32_t tile_after = tile + warps_total;
+  while (tile < n_tiles) {
+    uint32_t claimed = 0;
+    if (lane == 0) claimed = atomicAdd(acc.error_flag + 1, 1u) + 2u * warps_total;   // consumed at the bottom of the loop
+#define RSQ_TILE_NEXT tile_after
+#else
   for (; tile < n_tiles; tile += warps_total) {
+#define RSQ_TILE_NEXT (tile + warps_total)
+#endif
     const uint32_t i = tile * 32u + lane;
     const bool valid = i < n_reads;
     int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0;
@@ -286,10 +298,10 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // the end of this iteration, one whole tile of work later) and tells where its aligned blocks start: they are
     // prefetched into L2 below, so that neither array is first touched by a waiting warp.
     uint32_t next_boff = 0;
-    const bool has_next = (tile + warps_total) * 32u + lane < n_reads;        // no wrap: n_reads < 2^31 (launcher)
+    const bool has_next = RSQ_TILE_NEXT * 32u + lane < n_reads;               // no wrap: n_reads < 2^31 (launcher)
 #ifndef RSQ_AB_NO_PREFETCH
     if (has_next)
-        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(next_boff) : "l"(reinterpret_cast<const char*>(reads + ((size_t)(tile + warps_total) * 32u + lane)) + 40));
+        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(next_boff) : "l"(reinterpret_cast<const char*>(reads + ((size_t)RSQ_TILE_NEXT * 32u + lane)) + 40));
 #endif
 
     // ---- stage this tile's run of interval starts (warp-uniform) ----------------------------------------------------------
@@ -555,6 +567,10 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         mine = lane == RSQ_C_ALIGNMENT_BLOCKS ? s_nb : mine;
         own_lo += (unsigned long long)(long long)mine;
     }
+#ifdef RSQ_DYNAMIC_TILES
+    tile = tile_after;
+    tile_after = __shfl_sync(kFull, claimed, 0);
+#endif
   }  // tile loop
     if constexpr (!kLegacy) {                                                        // the last tile's parked keys
         const int s_late = resolve_parked(st, acc, lane);
@@ -950,6 +966,9 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     }
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
+#ifdef RSQ_DYNAMIC_TILES
+    cudaMemsetAsync(acc.error_flag + 1, 0, 4, stream);                               // the tile counter (second word of the allocation)
+#endif
     kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
     return 1;
 }
