@@ -4,8 +4,10 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include <set>
 #include <unordered_set>
 
@@ -17,10 +19,20 @@ namespace {
 const char* const kGlobins[] = {"HBA1", "HBA2", "HBB",  "HBD", "HBG1",  "HBG2",
                                 "HBE1", "HBM",  "HBQ1", "HBZ", "HBBP1", "HBZP1"};
 
+struct Span {      // a piece of the GTF text held in memory
+    const char* p; size_t n;
+    std::string str() const { return std::string(p, n); }
+    bool is(const char* lit, size_t ln) const { return n == ln && !memcmp(p, lit, ln); }
+};
+
 // std::stoull semantics as used at src/GTF.cpp:54,57: skip leading whitespace, optional sign, digits;
 // no digits -> invalid_argument (-> gtfException, exit 11).
-bool parse_u64(const std::string& s, unsigned long long& v) {
-    const char* p = s.c_str();
+bool parse_u64(Span s, unsigned long long& v) {
+    char tmp[48];
+    std::string big;
+    const char* p;
+    if (s.n < sizeof tmp) { memcpy(tmp, s.p, s.n); tmp[s.n] = 0; p = tmp; }   // bounded copy: strtoull must not run into the next field
+    else { big = s.str(); p = big.c_str(); }
     char* endp = nullptr;
     errno = 0;
     v = std::strtoull(p, &endp, 10);
@@ -35,60 +47,66 @@ bool parse_u64(const std::string& s, unsigned long long& v) {
 struct Attrs {
     bool has_gene_id = false, has_transcript_id = false, has_exon_id = false, has_transcript_type = false, has_gene_name = false;
     std::string gene_id, transcript_id, exon_id, transcript_type, gene_name;
+    void clear() { has_gene_id = has_transcript_id = has_exon_id = has_transcript_type = has_gene_name = false; }
 };
 
-void parse_attributes(const std::string& text, Attrs& out) {
+void parse_attributes(Span text, Attrs& out) {
     size_t pos = 0;
-    const size_t n = text.size();
+    const size_t n = text.n;
+    const char* t = text.p;
+    auto find = [&](char ch, size_t from) -> size_t {
+        if (from >= n) return std::string::npos;
+        const void* q = memchr(t + from, ch, n - from);
+        return q ? (size_t)((const char*)q - t) : std::string::npos;
+    };
+    size_t q1 = find('"', 0);                                            // the next quote at or after pos (kept across pieces)
     while (pos < n) {  // getline(tokenizer, buffer, ';') stops yielding once the input is exhausted
-        size_t semi = text.find(';', pos);
+        const size_t semi = find(';', pos);
         const size_t pe = semi == std::string::npos ? n : semi;          // piece = [pos, pe)
-        const size_t q1 = text.find('"', pos);
+        if (q1 != std::string::npos && q1 < pos) q1 = find('"', pos);
         const bool has_q = q1 != std::string::npos && q1 < pe;
         size_t ks = pos, ke = has_q ? q1 : pe;                            // head = [ks, ke)
         if (ke > ks) --ke;                                                // drop the last character of the head
-        while (ks < ke && (text[ks] == ' ' || text[ks] == '\t')) ++ks;
+        while (ks < ke && (t[ks] == ' ' || t[ks] == '\t')) ++ks;
         const size_t kl = ke - ks;
         std::string* dst = nullptr;
         bool* flag = nullptr;
         switch (kl) {
             case 7:
-                if (!text.compare(ks, 7, "gene_id")) { dst = &out.gene_id; flag = &out.has_gene_id; }
-                else if (!text.compare(ks, 7, "exon_id")) { dst = &out.exon_id; flag = &out.has_exon_id; }
+                if (!memcmp(t + ks, "gene_id", 7)) { dst = &out.gene_id; flag = &out.has_gene_id; }
+                else if (!memcmp(t + ks, "exon_id", 7)) { dst = &out.exon_id; flag = &out.has_exon_id; }
                 break;
-            case 9: if (!text.compare(ks, 9, "gene_name")) { dst = &out.gene_name; flag = &out.has_gene_name; } break;
-            case 13: if (!text.compare(ks, 13, "transcript_id")) { dst = &out.transcript_id; flag = &out.has_transcript_id; } break;
-            case 15: if (!text.compare(ks, 15, "transcript_type")) { dst = &out.transcript_type; flag = &out.has_transcript_type; } break;
+            case 9: if (!memcmp(t + ks, "gene_name", 9)) { dst = &out.gene_name; flag = &out.has_gene_name; } break;
+            case 13: if (!memcmp(t + ks, "transcript_id", 13)) { dst = &out.transcript_id; flag = &out.has_transcript_id; } break;
+            case 15: if (!memcmp(t + ks, "transcript_type", 15)) { dst = &out.transcript_type; flag = &out.has_transcript_type; } break;
             default: break;
         }
         if (dst) {
             *flag = true;
-            if (!has_q) dst->assign(text, pos, pe - pos);                 // stale `current` == the piece just read
+            if (!has_q) dst->assign(t + pos, pe - pos);                   // stale `current` == the piece just read
             else {
-                const size_t q2 = text.find('"', q1 + 1);
+                const size_t q2 = find('"', q1 + 1);
                 const size_t ve = (q2 == std::string::npos || q2 > pe) ? pe : q2;
-                dst->assign(text, q1 + 1, ve - q1 - 1);
+                dst->assign(t + q1 + 1, ve - q1 - 1);
             }
         }
         pos = (semi == std::string::npos) ? n : semi + 1;
     }
 }
 
-bool split_tab(const std::string& line, size_t& cursor, std::string& field) {
+bool parse_u64(const std::string& s, unsigned long long& v) { return parse_u64(Span{s.data(), s.size()}, v); }
+
+bool split_tab(Span line, size_t& cursor, Span& field) {
     // getline(tokenizer, buffer, '\t'): fails only when no characters remain at all
-    if (cursor > line.size()) return false;
-    if (cursor == line.size()) {
-        // stream exhausted: a previous read consumed the last char; getline extracts nothing -> fail
-        return false;
-    }
-    size_t tab = line.find('\t', cursor);
-    if (tab == std::string::npos) {
-        field = line.substr(cursor);
-        cursor = line.size() + 1;
+    if (cursor >= line.n) return false;   // stream exhausted: a previous read consumed the last char; getline extracts nothing
+    const void* q = memchr(line.p + cursor, '\t', line.n - cursor);
+    if (!q) {
+        field = Span{line.p + cursor, line.n - cursor};
+        cursor = line.n + 1;
     } else {
-        field = line.substr(cursor, tab - cursor);
-        cursor = tab + 1;
-        if (cursor == line.size()) cursor = line.size();  // trailing tab: next getline yields nothing
+        const size_t tab = (size_t)((const char*)q - line.p);
+        field = Span{line.p + cursor, tab - cursor};
+        cursor = tab + 1;                 // a trailing tab leaves cursor == size: the next getline yields nothing
     }
     return true;
 }
@@ -107,60 +125,92 @@ uint32_t Annotation::gene_universe(const std::string& id) {
 }
 
 void load_gtf(const std::string& path, Annotation& A, bool legacy) {
-    std::ifstream in(path);
-    if (!in.is_open()) throw HostError(10, "Unable to open GTF file: " + path);
+    // the whole file in memory, lines and fields as views into it (the loop below runs ~0.5 M times for a GENCODE-scale GTF)
+    std::string text;
+    {
+        std::ifstream in(path, std::ios::binary);
+        if (!in.is_open()) throw HostError(10, "Unable to open GTF file: " + path);
+        in.seekg(0, std::ios::end);
+        const std::streamoff sz = in.tellg();
+        if (sz > 0) {
+            text.resize((size_t)sz);
+            in.seekg(0, std::ios::beg);
+            in.read(&text[0], sz);
+            text.resize((size_t)std::max<std::streamsize>(in.gcount(), 0));
+        } else {                                                     // not seekable (a pipe): stream it
+            in.clear();
+            in.seekg(0, std::ios::beg);
+            in.clear();
+            text.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+        }
+    }
 
     // State of the single re-used Feature object (src/RNASeQC.cpp:109): these three survive from line to line
     // because operator>> only assigns them when the attribute exists (src/GTF.cpp:81,89,90,95,110).
     std::string cur_feature_id, cur_gene_id, cur_transcript_type;
-    std::unordered_set<std::string> seen_gene_ids, seen_exon_ids;
+    // One table over feature ids: geneNames (src/GTF.cpp:22, keyed by feature_id: gene, transcript and exon ids share it) and
+    // the set of exon ids seen so far (the uniqueness check, src/GTF.cpp:101-104).
+    struct IdInfo { std::string name; bool named = false, exon_seen = false; };
+    std::unordered_map<std::string, IdInfo> ids;
+    ids.reserve(text.size() / 200 + 16);
+    std::unordered_set<std::string> seen_gene_ids;
     std::map<std::string, unsigned> unnamed_exon_counter;            // exon_names (src/GTF.cpp:27)
-    std::unordered_map<std::string, std::string> gene_names;          // geneNames (src/GTF.cpp:22), keyed by feature_id
     std::vector<GeneFeature> kept_genes;
     std::vector<ExonFeature> kept_exons;
     size_t kept_counter = 0;
+    // gene_universe(cur_gene_id) is asked up to three times per line, and neighbouring lines share the gene
+    std::string memo_gene_id; uint32_t memo_gene = 0; bool memo_ok = false;
+    auto universe = [&](const std::string& id) -> uint32_t {
+        if (memo_ok && id == memo_gene_id) return memo_gene;
+        memo_gene = A.gene_universe(id); memo_gene_id = id; memo_ok = true;
+        return memo_gene;
+    };
 
-    std::string line;
-    while (std::getline(in, line)) {
-        if (!line.empty() && line[0] == '#') continue;
+    Attrs at;
+    size_t lp = 0;
+    while (lp < text.size()) {
+        const void* nl = memchr(text.data() + lp, '\n', text.size() - lp);
+        const size_t le = nl ? (size_t)((const char*)nl - text.data()) : text.size();
+        const Span line{text.data() + lp, le - lp};
+        lp = le + 1;
+        if (line.n && line.p[0] == '#') continue;
         size_t cur = 0;
-        std::string f_chr, f_track, f_type, f_start, f_end, f_score, f_strand, f_frame, f_attr;
-        if (!split_tab(line, cur, f_chr)) throw HostError(11, "Failed to parse the GTF: Unable to parse chromosome. Invalid GTF line: " + line);
-        uint32_t contig = A.contigs.get(f_chr);
-        if (!split_tab(line, cur, f_track)) throw HostError(11, "Failed to parse the GTF: Unable to parse track. Invalid GTF line: " + line);
-        if (!split_tab(line, cur, f_type)) throw HostError(11, "Failed to parse the GTF: Unable to parse feature type. Invalid GTF line: " + line);
+        Span f_chr, f_track, f_type, f_start, f_end, f_score, f_strand, f_frame;
+        if (!split_tab(line, cur, f_chr)) throw HostError(11, "Failed to parse the GTF: Unable to parse chromosome. Invalid GTF line: " + line.str());
+        uint32_t contig = A.contigs.get(f_chr.str());
+        if (!split_tab(line, cur, f_track)) throw HostError(11, "Failed to parse the GTF: Unable to parse track. Invalid GTF line: " + line.str());
+        if (!split_tab(line, cur, f_type)) throw HostError(11, "Failed to parse the GTF: Unable to parse feature type. Invalid GTF line: " + line.str());
         enum { T_GENE, T_TRANSCRIPT, T_EXON, T_OTHER } type =
-            f_type == "exon" ? T_EXON : f_type == "gene" ? T_GENE : f_type == "transcript" ? T_TRANSCRIPT : T_OTHER;
-        if (!split_tab(line, cur, f_start)) throw HostError(11, "Failed to parse the GTF: Unable to parse start. Invalid GTF line: " + line);
+            f_type.is("exon", 4) ? T_EXON : f_type.is("gene", 4) ? T_GENE : f_type.is("transcript", 10) ? T_TRANSCRIPT : T_OTHER;
+        if (!split_tab(line, cur, f_start)) throw HostError(11, "Failed to parse the GTF: Unable to parse start. Invalid GTF line: " + line.str());
         unsigned long long ustart = 0, uend = 0;
         if (!parse_u64(f_start, ustart)) throw HostError(11, "Failed to parse the GTF: GTF is in an invalid format: stoull");
-        if (!split_tab(line, cur, f_end)) throw HostError(11, "Failed to parse the GTF: Unable to parse end. Invalid GTF line: " + line);
+        if (!split_tab(line, cur, f_end)) throw HostError(11, "Failed to parse the GTF: Unable to parse end. Invalid GTF line: " + line.str());
         if (!parse_u64(f_end, uend)) throw HostError(11, "Failed to parse the GTF: GTF is in an invalid format: stoull");
-        if (!split_tab(line, cur, f_score)) throw HostError(11, "Failed to parse the GTF: Unable to parse score. Invalid GTF line: " + line);
-        if (!split_tab(line, cur, f_strand)) throw HostError(11, "Failed to parse the GTF: Unable to parse strand. Invalid GTF line: " + line);
-        uint8_t strand = f_strand.empty() ? RSQ_STRAND_UNKNOWN
-                         : f_strand[0] == '+' ? RSQ_STRAND_FWD
-                         : f_strand[0] == '-' ? RSQ_STRAND_REV
-                                              : RSQ_STRAND_UNKNOWN;
-        if (!split_tab(line, cur, f_frame)) throw HostError(11, "Failed to parse the GTF: Unable to parse frame. Invalid GTF line: " + line);
+        if (!split_tab(line, cur, f_score)) throw HostError(11, "Failed to parse the GTF: Unable to parse score. Invalid GTF line: " + line.str());
+        if (!split_tab(line, cur, f_strand)) throw HostError(11, "Failed to parse the GTF: Unable to parse strand. Invalid GTF line: " + line.str());
+        uint8_t strand = !f_strand.n ? RSQ_STRAND_UNKNOWN
+                         : f_strand.p[0] == '+' ? RSQ_STRAND_FWD
+                         : f_strand.p[0] == '-' ? RSQ_STRAND_REV
+                                                : RSQ_STRAND_UNKNOWN;
+        if (!split_tab(line, cur, f_frame)) throw HostError(11, "Failed to parse the GTF: Unable to parse frame. Invalid GTF line: " + line.str());
         // attributes = the rest of the line, tabs included (getline with '\n')
-        if (cur >= line.size()) throw HostError(11, "Failed to parse the GTF: Unable to parse attributes. Invalid GTF line: " + line);
-        f_attr = line.substr(cur);
-        Attrs at;
-        parse_attributes(f_attr, at);
+        if (cur >= line.n) throw HostError(11, "Failed to parse the GTF: Unable to parse attributes. Invalid GTF line: " + line.str());
+        at.clear();                                                                    // the strings keep their storage; only flagged ones are read
+        parse_attributes(Span{line.p + cur, line.n - cur}, at);
         const int64_t start = (int64_t)ustart, end = (int64_t)uend;
         if (end < start) std::cerr << "Bad feature range:" << start << " - " << end << std::endl;
 
         if (type == T_GENE && at.has_gene_id) {
             cur_feature_id = at.gene_id;
-            if (seen_gene_ids.count(cur_feature_id))
+            if (!seen_gene_ids.insert(cur_feature_id).second)
                 throw HostError(11, "Failed to parse the GTF: Detected non-unique Gene ID: " + cur_feature_id);
-            seen_gene_ids.insert(cur_feature_id);
-            A.gene_list.push_back(A.gene_universe(cur_feature_id));
+            A.gene_list.push_back(universe(cur_feature_id));
         }
         if (type == T_TRANSCRIPT && at.has_transcript_id) cur_feature_id = at.transcript_id;
         if (at.has_gene_id) cur_gene_id = at.gene_id;
         uint32_t exon_slot = 0;
+        IdInfo* info = nullptr;                                                        // the table entry of cur_feature_id, once looked up
         if (type == T_EXON) {
             if (at.has_exon_id) {
                 cur_feature_id = at.exon_id;
@@ -170,35 +220,39 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
                 std::cerr << "Unnamed exon: Gene: " << gid << " Position: [" << start << ", " << end
                           << "] Inferred Exon Name: " << cur_feature_id << std::endl;
             } else {
-                throw HostError(11, "Failed to parse the GTF: Exon missing exon_id and gene_id fields: " + line);
+                throw HostError(11, "Failed to parse the GTF: Exon missing exon_id and gene_id fields: " + line.str());
             }
-            if (seen_exon_ids.count(cur_feature_id))
+            info = &ids[cur_feature_id];
+            if (info->exon_seen)
                 throw HostError(11, "Failed to parse the GTF: Detected non-unique Exon ID: " + cur_feature_id);
-            seen_exon_ids.insert(cur_feature_id);
+            info->exon_seen = true;
             exon_slot = (uint32_t)A.exon_ids.size();
             A.exon_ids.push_back(cur_feature_id);
             A.exon_len.push_back(1 + (end - start));
             A.exon_start.push_back(start);
             A.exon_contig.push_back(contig);
-            uint32_t g = A.gene_universe(cur_gene_id);
+            uint32_t g = universe(cur_gene_id);
             A.gene_coding_len[g] += 1 + (end - start);
         }
         if (at.has_transcript_type) cur_transcript_type = at.transcript_type;
-        if (at.has_gene_name) gene_names[cur_feature_id] = at.gene_name;
-        else if (at.has_gene_id) gene_names[cur_feature_id] = at.gene_id;
+        if (at.has_gene_name || at.has_gene_id) {
+            if (!info) info = &ids[cur_feature_id];
+            info->name = at.has_gene_name ? at.gene_name : at.gene_id;
+            info->named = true;
+        }
         const bool ribosomal = cur_transcript_type.find("rRNA") != std::string::npos;  // regex "rRNA", src/GTF.cpp:21,113
 
         if (legacy && end == start) {                                                  // src/RNASeQC.cpp:129-135
-            if (type == T_EXON) A.gene_coding_len[A.gene_universe(cur_gene_id)] -= 1;
+            if (type == T_EXON) A.gene_coding_len[universe(cur_gene_id)] -= 1;
             continue;
         }
         // main(): keep genes and exons only (src/RNASeQC.cpp:137-139)
         if (type == T_GENE) {
-            GeneFeature gf{contig, start, end, strand, ribosomal, A.gene_universe(cur_feature_id), (uint32_t)kept_counter++};
-            gf.gid = A.gene_universe(cur_gene_id);
+            GeneFeature gf{contig, start, end, strand, ribosomal, universe(cur_feature_id), (uint32_t)kept_counter++};
+            gf.gid = universe(cur_gene_id);
             kept_genes.push_back(gf);
         } else if (type == T_EXON) {
-            ExonFeature ef{contig, start, end, strand, ribosomal, A.gene_universe(cur_gene_id), exon_slot, (uint32_t)kept_counter++};
+            ExonFeature ef{contig, start, end, strand, ribosomal, universe(cur_gene_id), exon_slot, (uint32_t)kept_counter++};
             kept_exons.push_back(ef);
         }
     }
@@ -214,15 +268,15 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
     A.gene_desc.assign(A.gene_ids.size(), std::string());
     A.gene_flags.assign(A.gene_ids.size(), 0);
     for (size_t g = 0; g < A.gene_ids.size(); ++g) {
-        auto it = gene_names.find(A.gene_ids[g]);
-        if (it != gene_names.end()) A.gene_desc[g] = it->second;
+        auto it = ids.find(A.gene_ids[g]);
+        if (it != ids.end() && it->second.named) A.gene_desc[g] = it->second.name;
         for (const char* glob : kGlobins)
             if (A.gene_desc[g] == glob) A.gene_flags[g] |= RSQ_GENE_GLOBIN;
     }
     A.exon_desc.assign(A.exon_ids.size(), std::string());
     for (size_t e = 0; e < A.exon_ids.size(); ++e) {
-        auto it = gene_names.find(A.exon_ids[e]);
-        if (it != gene_names.end()) A.exon_desc[e] = it->second;
+        auto it = ids.find(A.exon_ids[e]);
+        if (it != ids.end() && it->second.named) A.exon_desc[e] = it->second.name;
     }
 
     // Per contig, list.sort(compIntervalStart) — a stable sort by start over genes and exons interleaved
@@ -403,10 +457,16 @@ void load_bed(const std::string& path, ContigMap& contigs, BedModel& bed) {
             p = q;
             return true;
         };
+        // a failed `>>` leaves the buffer as it was: a missing end repeats the start, a missing start repeats the chromosome
+        // name (a number, or stoull throws), a blank line leaves the fresh buffer empty (stoull throws)
         std::string t_chr, t_start, t_end;
-        if (!next_tok(t_chr)) continue;  // blank line (the reference would re-use stale tokens; not reproduced)
+        next_tok(t_chr);
+        t_start = t_chr;
+        next_tok(t_start);
+        t_end = t_start;
+        next_tok(t_end);
         unsigned long long s = 0, e = 0;
-        if (!next_tok(t_start) || !parse_u64(t_start, s) || !next_tok(t_end) || !parse_u64(t_end, e))
+        if (!parse_u64(t_start, s) || !parse_u64(t_end, e))
             throw HostError(11, "Failed to parse the BED: Encountered an unknown error while parsing the BED: stoull");
         uint32_t c = contigs.get(t_chr);
         if (bed.starts.size() <= c) {

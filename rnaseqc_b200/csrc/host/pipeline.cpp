@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstring>
 #include <filesystem>
+#include <future>
 #include <iostream>
 #include <thread>
 
@@ -205,7 +206,11 @@ int run_sample(const Backend& be, CliOptions& opt) {
     void* pinned[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     size_t pinned_cap[2][2] = {{0, 0}, {0, 0}};
     int exit_code = 0;
+    // The device context comes up on a helper thread while the GTF is parsed (CUDA start-up costs about as much as the parse on
+    // a multi-GPU box); its outcome is looked at where rsq_create used to be called, so errors keep their order of precedence.
+    std::future<int> creating;
     try {
+        creating = std::async(std::launch::async, [&be, &opt, &ctx] { return be.create(&opt.cfg, &ctx); });
         Annotation A;
         ReferenceModel ref;
         if (!opt.fasta.empty()) {                                                  // src/RNASeQC.cpp:117-122: before the GTF
@@ -252,13 +257,21 @@ int run_sample(const Backend& be, CliOptions& opt) {
             for (size_t c = 0; c < A.genes_by_contig.size(); ++c)
                 has_features[c] = !A.genes_by_contig[c].empty() || !A.exons_by_contig[c].empty();
             if (!decoder.any_overlap_with(has_features)) {
-                std::cerr << "BAM file shares no contigs with GTF" << std::endl;   // src/RNASeQC.cpp:234-238
-                return 11;
+                throw HostError(11, "BAM file shares no contigs with GTF");       // src/RNASeQC.cpp:234-238
             }
         }
+        // An exon that ends before it starts has a "negative" length (1 + end - start in an unsigned type, src/GTF.cpp:108).  The
+        // reference meets it when the exon's gene leaves the window — every kept gene line does, at the latest after the loop
+        // (src/RNASeQC.cpp:385-386) — and sizes a coverage vector with it (src/Metrics.cpp:138): std::length_error, exit 1
+        // (src/RNASeQC.cpp:729-734).  Same outcome here, before any alignment is processed.
+        for (const auto& genes : A.genes_by_contig)
+            for (const GeneFeature& g : genes)
+                for (uint32_t slot : A.exons_for_gene[g.gene])
+                    if (A.exon_len[slot] < 0)
+                        throw HostError(1, "Unable to parse the GFT lines\ncannot create std::vector larger than max_size()");
 
         auto t_setup = clk::now();
-        int rc = be.create(&opt.cfg, &ctx);
+        int rc = creating.get();
         if (rc != RSQ_OK) throw HostError(rc == RSQ_ERR_NO_DEVICE ? 10 : -1, std::string("rsq_create failed: ") + be.last_error(nullptr));
         rsq_annotation av = A.view();
         rc = be.set_annotation(ctx, &av);
@@ -357,6 +370,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
         std::cerr << "Unknown error" << std::endl << e.what() << std::endl;
         exit_code = -1;
     }
+    if (creating.valid()) creating.wait();
     for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) if (pinned[s][k]) be.host_free(pinned[s][k]);
     if (ctx) be.destroy(ctx);
     return exit_code;
