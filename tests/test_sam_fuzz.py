@@ -152,3 +152,63 @@ def test_random_sam_records_match_the_reference(libs, tmp_path, seed):
         assert pr.returncode == 0, pr.stderr[-400:]
         identical = set(compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}")))
         assert {"f.sam.gene_reads.gct", "f.sam.gene_fragments.gct", "f.sam.exon_reads.gct"} <= identical, (flags, identical)
+
+
+SAM2CRAM = os.path.join(ROOT, "oracle", "_ref", "sam2cram")
+
+
+def _fasta(path, contigs):
+    """A genome for the fuzz contigs: a repeated 4-mer pattern with runs of N and lower-case stretches (+ .fai)."""
+    import numpy as np
+    with open(path, "w") as f, open(path + ".fai", "w") as fai:
+        for k, (name, ln) in enumerate(contigs):
+            rng = np.random.default_rng(77 + k)
+            seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, ln)].copy()
+            for s in rng.integers(0, max(ln - 400, 1), 40):
+                seq[s:s + int(rng.integers(1, 300))] = ord("N")
+            for s in rng.integers(0, max(ln - 400, 1), 40):
+                seq[s:s + 200] |= 0x20                                            # lower case
+            hdr = f">{name}\n"
+            f.write(hdr)
+            off = f.tell()
+            body = seq.tobytes().decode()
+            f.write("\n".join(body[i:i + 60] for i in range(0, ln, 60)) + "\n")
+            fai.write(f"{name}\t{ln}\t{off}\t60\t61\n")
+
+
+def _strip_nm_z(sam_in, sam_out):
+    # htslib's CRAM writer refuses NM tags of string type ("Unhandled type code for NM tag", cram_encode.c:2113-2125)
+    with open(sam_in) as f, open(sam_out, "w") as g:
+        for line in f:
+            g.write(line.replace("\tNM:Z:3", ""))
+
+
+@pytest.mark.skipif(not os.path.exists(SAM2CRAM), reason="reference htslib tool not built (make ref)")
+@pytest.mark.parametrize("seed", [4200, 4201, 5021])
+@pytest.mark.parametrize("fmt", ["bam", "cram", "cram_small_slices"])
+def test_random_records_as_bam_and_cram_match_the_reference(libs, tmp_path, seed, fmt):
+    """The same odd records written by the reference's htslib as BAM (sequential and multi-threaded readers) and CRAM (own reader;
+    NM regenerated from the read features against a genome with N runs)."""
+    import subprocess
+    rng = random.Random(seed)
+    d = str(tmp_path)
+    gtf, sam0, sam, fa = os.path.join(d, "f.gtf"), os.path.join(d, "f0.sam"), os.path.join(d, "f.sam"), os.path.join(d, "f.fa")
+    _gtf(gtf, rng)
+    _sam(sam0, rng, 2500, allow_dup=False)
+    _strip_nm_z(sam0, sam)
+    ext = "bam" if fmt == "bam" else "cram"
+    aln = os.path.join(d, "f." + ext)
+    extra = []
+    if fmt != "bam":
+        _fasta(fa, [("chr1", 3_000_000), ("chr2", 3_000_000), ("chrM", 3_000_000), ("chrUn", 3_000_000)])
+        extra = ["--fasta", fa]
+    slicing = ["97", "2"] if fmt == "cram_small_slices" else []
+    subprocess.run([SAM2CRAM, sam, fa, aln] + slicing, check=True, stderr=subprocess.DEVNULL)
+    for k, flags in enumerate([[], ["--legacy", "-u"], ["--stranded", "rf", "--coverage", "--exclude-chimeric"]]):
+        pr = run_cli(REF, gtf, aln, os.path.join(d, f"ref{k}"), *flags, *extra, check=False)
+        outs = []
+        for threads in ("0", "3"):
+            po = run_cli(libs["oracle_cli"], gtf, aln, os.path.join(d, f"ours{k}_{threads}"), *flags, *extra, "--decode-threads", threads, check=False)
+            assert pr.returncode == po.returncode == 0, (flags, pr.returncode, po.returncode, pr.stderr[-400:], po.stderr[-400:])
+            identical = set(compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}_{threads}")))
+            assert {f"f.{ext}.gene_reads.gct", f"f.{ext}.gene_fragments.gct", f"f.{ext}.exon_reads.gct"} <= identical, (flags, identical)
