@@ -212,3 +212,78 @@ def test_random_records_as_bam_and_cram_match_the_reference(libs, tmp_path, seed
             assert pr.returncode == po.returncode == 0, (flags, pr.returncode, po.returncode, pr.stderr[-400:], po.stderr[-400:])
             identical = set(compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}_{threads}")))
             assert {f"f.{ext}.gene_reads.gct", f"f.{ext}.gene_fragments.gct", f"f.{ext}.exon_reads.gct"} <= identical, (flags, identical)
+
+
+def _pairs_sam(path, rng, rows_gtf, n_pairs):
+    """High-quality pairs placed inside exons, then broken in every way the fragment-size and GC-content samplers care about: three
+    and four records under one name, both mates forward, same start, mates in different exons or genes, a mate missing or unmapped,
+    TLEN with the wrong sign or zero, spliced mates, insert sizes on the sampler's 100 / 1000 limits."""
+    ex = [r.split("\t") for r in rows_gtf if "\texon\t" in r]
+    ex = [(e[0], int(e[3]), int(e[4])) for e in ex if int(e[4]) - int(e[3]) > 120]
+    recs = []
+    for i in range(n_pairs):
+        chrom, s, e = ex[rng.randrange(len(ex))]
+        rl = rng.choice([36, 50, 76])
+        ins = rng.choice([rl, rl + 1, 99, 100, 101, 150, 226, 400, 999, 1000, 1001])
+        p1 = rng.randint(max(1, s - 20), max(s, e - rl))
+        p2 = p1 + max(0, ins - rl)
+        name = f"p{i}"
+        f1, f2 = rng.choice([(99, 147), (163, 83), (97, 145), (65, 129), (99, 147), (99, 147)])
+        t1, t2 = ins, -ins
+        odd = rng.random()
+        c1 = c2 = f"{rl}M"
+        if odd < 0.05:
+            f2 = f2 & ~16 | 32                      # both forward
+        elif odd < 0.10:
+            p2 = p1                                 # same start
+        elif odd < 0.15:
+            t1, t2 = -ins, ins                      # wrong signs
+        elif odd < 0.20:
+            t1 = t2 = 0
+        elif odd < 0.25:
+            c2 = f"{rl // 2}M{rng.choice([50, 300])}N{rl - rl // 2}M"   # spliced upper mate
+        elif odd < 0.30:
+            name = f"p{rng.randrange(max(i, 1))}"   # a name used before: three or four records share it
+        elif odd < 0.33:
+            f2 |= 4                                 # upper mate unmapped (keeps its coordinates)
+        elif odd < 0.36:
+            f1 |= 512                               # (no duplicate flags: they start the reference's 1e9-step complexity scan)
+        elif odd < 0.40:
+            chrom2, s2, e2 = ex[rng.randrange(len(ex))]
+            if chrom2 == chrom:
+                p2 = rng.randint(s2, max(s2, e2 - rl))                  # mate in another exon
+        nm = rng.choice([0, 0, 0, 1, 6, 7])
+        mq = rng.choice([255, 255, 255, 255, 60])
+        seq = "".join(rng.choice("ACGT") for _ in range(rl))
+        recs.append((chrom, p1, "\t".join([name, str(f1), chrom, str(p1), str(mq), c1, "=", str(p2), str(t1), seq, "*", f"NM:i:{nm}"])))
+        if odd < 0.43 or odd >= 0.46:               # else: the upper mate is missing
+            recs.append((chrom, p2, "\t".join([name, str(f2), chrom, str(p2), str(mq), c2, "=", str(p1), str(t2), seq, "*", f"NM:i:{nm}"])))
+    order = {"chr1": 0, "chr2": 1, "chrM": 2}
+    recs.sort(key=lambda r: (order[r[0]], r[1]))
+    hdr = ["@HD\tVN:1.0\tSO:coordinate", "@SQ\tSN:chr1\tLN:100000", "@SQ\tSN:chr2\tLN:100000", "@SQ\tSN:chrM\tLN:100000"]
+    open(path, "w").write("\n".join(hdr + [r[2] for r in recs]) + "\n")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_pairs_fragment_sizes_and_gc_match_the_reference(libs, tmp_path, seed):
+    rng = random.Random(4300 + seed)
+    d = str(tmp_path)
+    gtf, sam, bed, fa = (os.path.join(d, n) for n in ("f.gtf", "f.sam", "f.bed", "f.fa"))
+    rows = _gtf(gtf, rng)
+    _pairs_sam(sam, rng, rows, 1500)
+    ex = sorted({(e[0], int(e[3]), int(e[4])) for e in (r.split("\t") for r in rows if "\texon\t" in r)})
+    open(bed, "w").write("".join(f"{c}\t{s - 1}\t{e}\n" for c, s, e in ex))
+    _fasta(fa, [("chr1", 100000), ("chr2", 100000), ("chrM", 100000)])
+    for k, flags in enumerate([["--bed", bed], ["--bed", bed, "--fragment-samples", "25", "--fasta", fa], ["--fasta", fa, "--stranded", "fr", "--coverage"],
+                               ["--bed", bed, "--legacy", "--fasta", fa], ["--bed", bed, "-u", "-q", "60", "--base-mismatch", "0"]]):
+        pr = run_cli(REF, gtf, sam, os.path.join(d, f"ref{k}"), *flags, check=False)
+        po = run_cli(libs["oracle_cli"], gtf, sam, os.path.join(d, f"ours{k}"), *flags, check=False)
+        assert pr.returncode == po.returncode == 0, (flags, pr.returncode, po.returncode, pr.stderr[-400:], po.stderr[-400:])
+        identical = set(compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}")))
+        need = {"f.sam.gene_reads.gct", "f.sam.gene_fragments.gct", "f.sam.exon_reads.gct"}
+        if "--bed" in flags:
+            need.add("f.sam.fragmentSizes.txt")
+            assert sum(int(l.split("\t")[1]) for l in open(os.path.join(d, f"ref{k}", "f.sam.fragmentSizes.txt")).readlines()[1:]) >= 20
+        if "--fasta" in flags and "--legacy" not in flags:
+            need.add("f.sam.gc_content.tsv")
+        assert need <= identical, (flags, identical)
