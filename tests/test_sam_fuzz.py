@@ -214,7 +214,7 @@ def test_random_records_as_bam_and_cram_match_the_reference(libs, tmp_path, seed
             assert {f"f.{ext}.gene_reads.gct", f"f.{ext}.gene_fragments.gct", f"f.{ext}.exon_reads.gct"} <= identical, (flags, identical)
 
 
-def _pairs_sam(path, rng, rows_gtf, n_pairs):
+def _pairs_sam(path, rng, rows_gtf, n_pairs, shared_names=True):
     """High-quality pairs placed inside exons, then broken in every way the fragment-size and GC-content samplers care about: three
     and four records under one name, both mates forward, same start, mates in different exons or genes, a mate missing or unmapped,
     TLEN with the wrong sign or zero, spliced mates, insert sizes on the sampler's 100 / 1000 limits."""
@@ -242,7 +242,7 @@ def _pairs_sam(path, rng, rows_gtf, n_pairs):
             t1 = t2 = 0
         elif odd < 0.25:
             c2 = f"{rl // 2}M{rng.choice([50, 300])}N{rl - rl // 2}M"   # spliced upper mate
-        elif odd < 0.30:
+        elif odd < 0.30 and shared_names:
             name = f"p{rng.randrange(max(i, 1))}"   # a name used before: three or four records share it
         elif odd < 0.33:
             f2 |= 4                                 # upper mate unmapped (keeps its coordinates)

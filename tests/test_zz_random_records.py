@@ -10,7 +10,7 @@ import random
 import numpy as np
 import pytest
 
-from test_sam_fuzz import _gtf, _sam
+from test_sam_fuzz import _fasta, _gtf, _pairs_sam, _sam
 from util import assert_results_equal
 
 CONFIGS = {
@@ -84,3 +84,59 @@ def test_harness_and_packer_on_the_oracle(libs, tmp_path, name):
 @pytest.mark.parametrize("name", sorted(CONFIGS))
 def test_cuda_matches_oracle_on_random_sam_records(libs, tmp_path, name, seed):
     _check(libs, tmp_path, libs["product"], seed, name)
+
+
+PAIR_CONFIGS = {
+    "bed": dict(fragment_samples=1000000),
+    "bed_quota": dict(fragment_samples=25),
+    "bed_fasta_fr": dict(fragment_samples=300, strand_mode=1, fasta=True),
+    "fasta_unpaired_loose": dict(unpaired=True, mapq=60, mismatches=0, fasta=True),
+    "legacy_bed_fasta": dict(legacy=True, mapq=4, fragment_samples=1000000, fasta=True),
+}
+
+
+def _check_pairs(libs, tmp_path, lib, seed, name):
+    """Odd PAIRS (tests/test_sam_fuzz.py::_pairs_sam, names unique per pair: the device sampler's documented two-candidates-per-name
+    rule) through the fragment-size and GC-content samplers."""
+    api = libs["api"]
+    kw = dict(PAIR_CONFIGS[name])
+    legacy, fasta = kw.pop("legacy", False), kw.pop("fasta", False)
+    rng = random.Random(seed)
+    d = str(tmp_path)
+    gtf, sam, bed, fa = (os.path.join(d, n) for n in ("f.gtf", "f.sam", "f.bed", "f.fa"))
+    rows = _gtf(gtf, rng)
+    _pairs_sam(sam, rng, rows, 1500, shared_names=False)
+    ex = sorted({(e[0], int(e[3]), int(e[4])) for e in (r.split("\t") for r in rows if "\texon\t" in r)})
+    open(bed, "w").write("".join(f"{c}\t{s - 1}\t{e}\n" for c, s, e in ex))
+    if fasta:
+        _fasta(fa, [("chr1", 100000), ("chr2", 100000), ("chrM", 100000)])
+    ann = api.Annotation(gtf, bed, legacy=legacy, fasta=fa if fasta else None)
+    reads, blocks, _ = ann.decode(sam)
+    cfg = lambda: api.make_config(max_records=len(reads), legacy=legacy, **kw)
+    out = []
+    for which in (libs["oracle"], lib):
+        ctx = api.Backend(which).create(cfg())
+        ctx.set_annotation(ann)
+        ctx.submit(reads, blocks)
+        ctx.sync()
+        out.append(ctx.finalize())
+        ctx.close()
+    want, got = out
+    assert_results_equal(got, want, f"{name} seed {seed}")
+    assert np.array_equal(got.gc_hist, want.gc_hist), (name, seed, got.gc_hist, want.gc_hist)
+    if kw.get("fragment_samples"):
+        assert 20 <= int(want.fragment_hist.sum()) <= kw["fragment_samples"]
+    if fasta and not legacy:
+        assert int(want.gc_hist.sum()) > 20
+
+
+@pytest.mark.parametrize("name", ["bed_fasta_fr", "legacy_bed_fasta"])
+def test_pairs_harness_on_the_oracle(libs, tmp_path, name):
+    _check_pairs(libs, tmp_path, libs["oracle"], 4301, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [4300, 4301])
+@pytest.mark.parametrize("name", sorted(PAIR_CONFIGS))
+def test_cuda_samplers_match_oracle_on_odd_pairs(libs, tmp_path, name, seed):
+    _check_pairs(libs, tmp_path, libs["product"], seed, name)
