@@ -7,10 +7,12 @@
 #include "report.h"
 
 #include <algorithm>
+#include <charconv>
 #include <climits>
 #include <cmath>
 #include <filesystem>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <map>
 #include <sstream>
@@ -337,6 +339,33 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
     // src/Metrics.cpp:33-36)
     const uint64_t total_alignments = (uint64_t)(int64_t)(int)st.alignment_count;
     auto frac = [&](int a, int b) { return (double)C[a] / C[b]; };                   // Metrics::frac, src/Metrics.cpp:43-46
+    // ---- exon table (src/RNASeQC.cpp:510-521): the largest file and independent of everything below — written on a helper thread
+    std::future<void> exon_table = std::async(std::launch::async, [&A, &R, &opt, base] {
+        std::ofstream exon_report(base + ".exon_reads.gct");
+        size_t nonzero = 0;
+        for (size_t e = 0; e < A.exon_ids.size(); ++e) if (R.exon_whole[e] || R.exon_frac[e]) ++nonzero;
+        exon_report << "#1.2" << '\n';
+        exon_report << nonzero << "\t1" << '\n';                                  // exonCounts.size(), :513
+        exon_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << '\n';
+        // `<< std::fixed << v` is printf's %.6f; std::to_chars(fixed, 6) prints the same digits without the stream machinery
+        std::string buf;
+        buf.reserve(1 << 20);
+        char num[400];
+        for (size_t e = 0; e < A.exon_ids.size(); ++e) {
+            const double v = R.exon_seq.empty() ? exon_count_to_double(R.exon_whole[e], R.exon_frac[e]) : R.exon_seq[e];
+            buf += A.exon_ids[e]; buf += '\t'; buf += A.exon_desc[e]; buf += '\t';
+            if (std::isfinite(v)) {
+                const auto r = std::to_chars(num, num + sizeof num, v, std::chars_format::fixed, 6);
+                buf.append(num, r.ptr);
+            } else {
+                std::ostringstream o; o << std::fixed << v; buf += o.str();
+            }
+            buf += '\n';
+            if (buf.size() > (1 << 20) - 4096) { exon_report.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
+        }
+        exon_report.write(buf.data(), (std::streamsize)buf.size());
+    });
+    struct Join { std::future<void>& f; ~Join() { if (f.valid()) f.wait(); } } join_exon_table{exon_table};   // also on the error paths
     // ---- coverage statistics (the reference computes them as genes leave the window) -------------------------
     CoverageSummary cov;
     compute_coverage_summary(A, R, opt, st, cov);
@@ -410,20 +439,6 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         index = .75 * ratios.size();
         if (index > std::floor(index)) { index = std::ceil(index); ratio75 = at(index); }
         else { index = std::ceil(index); ratio75 = (at(index) + at(index + 1)) / 2.0; }
-    }
-    // ---- exon table (src/RNASeQC.cpp:510-521) -------------------------------------------------------------------
-    {
-        std::ofstream exon_report(base + ".exon_reads.gct");
-        size_t nonzero = 0;
-        for (size_t e = 0; e < A.exon_ids.size(); ++e) if (R.exon_whole[e] || R.exon_frac[e]) ++nonzero;
-        exon_report << "#1.2" << '\n';
-        exon_report << nonzero << "\t1" << '\n';                                  // exonCounts.size(), :513
-        exon_report << "Name\tDescription\t" << (opt.sample_given ? opt.sample_name : "Counts") << '\n';
-        exon_report << std::fixed;
-        for (size_t e = 0; e < A.exon_ids.size(); ++e) {
-            const double v = R.exon_seq.empty() ? exon_count_to_double(R.exon_whole[e], R.exon_frac[e]) : R.exon_seq[e];
-            exon_report << A.exon_ids[e] << "\t" << A.exon_desc[e] << "\t" << v << '\n';
-        }
     }
     // ---- metrics.tsv (src/RNASeQC.cpp:523-564, src/Metrics.cpp:381-410) -----------------------------------------
     std::ofstream output(base + ".metrics.tsv");
