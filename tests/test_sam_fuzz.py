@@ -287,3 +287,79 @@ def test_random_pairs_fragment_sizes_and_gc_match_the_reference(libs, tmp_path, 
         if "--fasta" in flags and "--legacy" not in flags:
             need.add("f.sam.gc_content.tsv")
         assert need <= identical, (flags, identical)
+
+
+def _wild_gtf(path, rng):
+    """Annotations no collapser would write: gene lines in any file order and on interleaved contigs, exons before their gene line,
+    overlapping / nested / duplicate-coordinate exons inside one gene, genes without exons, exons
+    whose gene has no gene line, transcript and CDS lines in between, one-base exons and genes, strands '.', rRNA by transcript_type."""
+    rows = []
+    g = 0
+    for chrom, span in (("chr1", 40000), ("chr2", 20000), ("chrM", 6000)):
+        for _ in range(rng.randint(6, 22)):
+            g += 1
+            strand = rng.choice("++--.")
+            ttype = rng.choice(["protein_coding"] * 5 + ["rRNA", "lincRNA", "Mt_rRNA"])
+            gs = rng.randint(1, span - 2000)
+            ge = gs + rng.choice([0, 1, 50, 400, 1500, 6000])
+            common = f'gene_id "G{g}"; transcript_id "T{g}"; gene_type "{ttype}"; gene_name "N{g % 7}"; transcript_type "{ttype}";'
+            lines = []
+            if rng.random() < 0.9:
+                lines.append(f"{chrom}\tw\tgene\t{gs}\t{ge}\t.\t{strand}\t.\t{common}")
+            if rng.random() < 0.5:
+                lines.append(f"{chrom}\tw\ttranscript\t{gs}\t{ge}\t.\t{strand}\t.\t{common}")
+            for k in range(rng.choice([0, 1, 1, 2, 3, 5, 8])):
+                # inside the gene's span: the reference integrates a gene's coverage when its gene line leaves the window, so reads
+                # on an exon that reaches past the gene line's end come too late for it (not reproduced: DESIGN.md §6)
+                es = rng.randint(gs, ge)
+                ee = min(ge, es + rng.choice([0, 1, 30, 120, 120, 500, 1200]))
+                if k and rng.random() < 0.2:
+                    es, ee = prev                                                   # same coordinates as the previous exon
+                prev = (es, ee)
+                estrand = strand if rng.random() < 0.9 else rng.choice("+-")
+                lines.append(f'{chrom}\tw\texon\t{es}\t{ee}\t.\t{estrand}\t.\t{common} exon_id "G{g}_e{k}";')
+                if rng.random() < 0.2:
+                    lines.append(f'{chrom}\tw\tCDS\t{es}\t{ee}\t.\t{estrand}\t0\t{common}')
+            if rng.random() < 0.3:
+                rng.shuffle(lines)                                                    # exons before their gene line
+            rows.append(lines)
+    rng.shuffle(rows)                                                                 # file order unrelated to coordinates
+    flat = [l for ls in rows for l in ls]
+    open(path, "w").write("\n".join(flat) + "\n")
+    return flat
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_wild_annotations_match_the_reference(libs, tmp_path, seed):
+    rng = random.Random(4400 + seed)
+    d = str(tmp_path)
+    gtf, sam = os.path.join(d, "f.gtf"), os.path.join(d, "f.sam")
+    rows = _wild_gtf(gtf, rng)
+    if not any("\texon\t" in r for r in rows) or not any("\tgene\t" in r for r in rows):
+        pytest.skip("no genes or no exons drawn")
+    # well-formed high-quality pairs over the exons (and 20 bases around them), plus the random records
+    ex = [r.split("\t") for r in rows if "\texon\t" in r]
+    recs = []
+    order = {"chr1": 0, "chr2": 1, "chrM": 2}
+    for i in range(2500):
+        e = ex[rng.randrange(len(ex))]
+        s, t = int(e[3]), int(e[4])
+        rl = rng.choice([25, 50, 76])
+        p1 = max(1, rng.randint(s - 20, max(s - 20, t - rl + 20)))
+        ins = rng.choice([rl, 120, 200, 350])
+        p2 = p1 + max(0, ins - rl)
+        cig = f"{rl}M" if rng.random() < 0.8 else f"{rl // 2}M{rng.choice([40, 150, 700])}N{rl - rl // 2}M"
+        seq = "A" * rl
+        for flag, pos, mpos, tl in ((99, p1, p2, ins), (147, p2, p1, -ins)):
+            recs.append((order[e[0]], pos, "\t".join([f"w{i}", str(flag), e[0], str(pos), "255", cig, "=", str(mpos), str(tl), seq, "*", f"NM:i:{rng.choice([0, 0, 2])}"])))
+    recs.sort(key=lambda r: (r[0], r[1]))
+    hdr = ["@HD\tVN:1.0\tSO:coordinate", "@SQ\tSN:chr1\tLN:100000", "@SQ\tSN:chr2\tLN:100000", "@SQ\tSN:chrM\tLN:100000"]
+    open(sam, "w").write("\n".join(hdr + [r[2] for r in recs]) + "\n")
+    for k, flags in enumerate([["--coverage"], ["--coverage", "--stranded", "rf", "--coverage-mask", "20", "--gene-length", "100", "--window-size", "30", "--detection-threshold", "1"],
+                               ["--legacy", "--coverage"], ["--coverage", "-u", "--offset", "10", "--window-size", "50", "--gene-length", "200"]]):
+        pr = run_cli(REF, gtf, sam, os.path.join(d, f"ref{k}"), *flags, check=False)
+        po = run_cli(libs["oracle_cli"], gtf, sam, os.path.join(d, f"ours{k}"), *flags, check=False)
+        assert pr.returncode == po.returncode, (flags, pr.returncode, po.returncode, pr.stderr[-400:], po.stderr[-400:])
+        if pr.returncode == 0:
+            identical = set(compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}")))
+            assert {"f.sam.gene_reads.gct", "f.sam.gene_fragments.gct", "f.sam.exon_reads.gct"} <= identical, (flags, identical)
