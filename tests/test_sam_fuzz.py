@@ -301,7 +301,7 @@ def _wild_gtf(path, rng):
             strand = rng.choice("++--.")
             ttype = rng.choice(["protein_coding"] * 5 + ["rRNA", "lincRNA", "Mt_rRNA"])
             gs = rng.randint(1, span - 2000)
-            ge = gs + rng.choice([0, 1, 50, 400, 1500, 6000])
+            ge = gs + rng.choice([0, 1, 50, 400, 800, 1500, 1500, 3000, 6000])
             common = f'gene_id "G{g}"; transcript_id "T{g}"; gene_type "{ttype}"; gene_name "N{g % 7}"; transcript_type "{ttype}";'
             lines = []
             if rng.random() < 0.9:
@@ -312,7 +312,7 @@ def _wild_gtf(path, rng):
                 # inside the gene's span: the reference integrates a gene's coverage when its gene line leaves the window, so reads
                 # on an exon that reaches past the gene line's end come too late for it (not reproduced: DESIGN.md §6)
                 es = rng.randint(gs, ge)
-                ee = min(ge, es + rng.choice([0, 1, 30, 120, 120, 500, 1200]))
+                ee = min(ge, es + rng.choice([0, 1, 30, 120, 120, 300, 500, 1200, 2500]))
                 if k and rng.random() < 0.2:
                     es, ee = prev                                                   # same coordinates as the previous exon
                 prev = (es, ee)
