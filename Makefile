@@ -15,7 +15,7 @@ HOST_SRCS := annotation.cpp alnreader.cpp cramreader.cpp bamparallel.cpp fasta.c
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
-oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so
+oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so $(ODIR)/libhostlegacy.so
 ref:
 	$(MAKE) -f oracle/Makefile.ref
 
@@ -42,6 +42,10 @@ $(ODIR)/librsq_oracle.so: oracle/rsq_oracle.cpp include/rsq_b200.h
 
 # test infrastructure: host emulation of the hot kernel's per-record logic + index builder (tests/test_hostcore.py)
 $(ODIR)/libhostcore.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
+	@mkdir -p $(ODIR)
+	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
+# host emulation of the --legacy device rules (rsq_legacy.cuh compiled for the CPU behind shims)
+$(ODIR)/libhostlegacy.so: tests/hostcore/hostlegacy.cpp rnaseqc_b200/csrc/rsq_legacy.cuh rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
 	@mkdir -p $(ODIR)
 	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
 # the same with the kernel's experimental compile-time variants that change the per-record logic (tools/ab_build.sh builds the CUDA side)

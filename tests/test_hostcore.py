@@ -268,3 +268,100 @@ def test_fuzz_random_dense_annotations(libs, tmp_path, seed, variant):
     got, got_bytes, _ = run_hostcore(api, ann, reads, blocks, cfg(), variant)
     assert_same(api, got, want, f"fuzz seed {seed} {kw} {variant}")
     assert got_bytes == want_bytes
+
+
+# ---- the --legacy device rules (rsq_legacy.cuh) on the host -------------------------------------------------------------------
+HOSTLEGACY = os.path.join(ROOT, "oracle", "_build", "libhostlegacy.so")
+
+
+def run_hostlegacy(api, ann, reads, blocks, cfg):
+    lib = C.CDLL(HOSTLEGACY)
+    lib.hostlegacy_run.restype = C.c_int
+    G, E, L = ann.n_genes, ann.n_exons, ann.cov_len
+    out = {k: np.zeros(n, np.uint64) for k, n in (("counters", 64), ("gene_reads", G), ("gene_unique", G), ("gene_fragments", G),
+                                                   ("exon_whole", E), ("exon_fhi", E), ("exon_flo", E), ("bytes", 1))}
+    cov = np.zeros(L + 1, np.uint32)
+    reads = np.ascontiguousarray(reads)
+    blocks = np.ascontiguousarray(blocks)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.hostlegacy_run(C.byref(ann.view), C.byref(cfg), p(reads), C.c_size_t(len(reads)), p(blocks), C.c_size_t(len(blocks)),
+                            p(out["counters"]), p(out["gene_reads"]), p(out["gene_unique"]), p(out["gene_fragments"]), p(out["exon_whole"]),
+                            p(out["exon_fhi"]), p(out["exon_flo"]), p(cov), p(out["bytes"]))
+    assert rc == 0
+    hi, lo = out["exon_fhi"], out["exon_flo"]
+    mid = hi + (lo >> np.uint64(32))
+    res = api.Results(G, E, L)
+    res.counters = out["counters"]
+    res.gene_reads, res.gene_unique, res.gene_fragments = out["gene_reads"], out["gene_unique"], out["gene_fragments"]
+    res.exon_frac = (mid << np.uint64(32)) | (lo & np.uint64(0xffffffff))
+    res.exon_whole = out["exon_whole"] + (mid >> np.uint64(32))
+    res.coverage = np.cumsum(cov, dtype=np.uint32)
+    return res, int(out["bytes"][0])
+
+
+LEGACY_CONFIGS = {
+    "legacy": dict(mapq=4),
+    "legacy_rf_excl": dict(mapq=4, strand_mode=2, exclude_chimeric=True),
+    "legacy_fr_unpaired_q255": dict(strand_mode=1, unpaired=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LEGACY_CONFIGS))
+def test_legacy_device_rules_match_oracle_on_synthetic_records(libs, tmp_path_factory, name):
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    d = str(tmp_path_factory.mktemp("hostlegacy"))
+    sa = synth.make_annotation(seed=201, n_genes=400, contig_names=["chr1", "chr2", "chr3", "chrM"], contig_lens=[40_000_000, 30_000_000, 20_000_000, 16569])
+    synth.write_gtf(sa, os.path.join(d, "a.gtf"))
+    ann = api.Annotation(os.path.join(d, "a.gtf"), legacy=True)
+    sr = synth.simulate_reads(sa, 120000, seed=202)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    rng = np.random.default_rng(7)
+    reads["aux"] |= ((rng.random(len(reads)) < 0.01) * 0x20).astype(np.uint8)      # RSQ_AUX_TID_GT_127
+    cfg = lambda: api.make_config(max_records=len(reads), legacy=True, **LEGACY_CONFIGS[name])
+    want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+    got, got_bytes = run_hostlegacy(api, ann, reads, blocks, cfg())
+    assert_same(api, got, want, name)
+    assert got_bytes == want_bytes
+    assert want.counter("Split Reads") > 3000 and want.gene_reads.sum() > 30000
+
+
+@pytest.mark.parametrize("seed", [4100, 4101, 4102, 5021, 5038, 5048])
+def test_legacy_device_rules_match_oracle_on_random_sam_records(libs, tmp_path, seed):
+    """The odd records of tests/test_sam_fuzz.py (pinned to the reference there) through the device's --legacy code on the host."""
+    import random
+    from test_sam_fuzz import _gtf, _sam
+    api = libs["api"]
+    rng = random.Random(seed)
+    d = str(tmp_path)
+    _gtf(os.path.join(d, "f.gtf"), rng)
+    _sam(os.path.join(d, "f.sam"), rng, 2500, allow_dup=True)
+    ann = api.Annotation(os.path.join(d, "f.gtf"), legacy=True)
+    for kw in (dict(mapq=4), dict(strand_mode=1, unpaired=True, exclude_chimeric=True), dict(mapq=0, mismatches=30, strand_mode=2)):
+        reads, blocks, _ = ann.decode(os.path.join(d, "f.sam"), exclude_chimeric=kw.get("exclude_chimeric", False))
+        cfg = lambda: api.make_config(max_records=len(reads), legacy=True, **kw)
+        want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+        got, got_bytes = run_hostlegacy(api, ann, reads, blocks, cfg())
+        assert_same(api, got, want, f"seed {seed} {kw}")
+        assert got_bytes == want_bytes
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_legacy_device_rules_fuzz_on_dense_annotations(libs, tmp_path, seed):
+    api = libs["api"]
+    _, reads, blocks, rng = _fuzz_case(api, tmp_path, 7100 + seed)
+    ann = api.Annotation(str(tmp_path / f"fuzz{7100 + seed}.gtf"), legacy=True)
+    # the ABI asks for MIXED name hashes (include/rsq_b200.h); the fuzz generator's are multiples of one constant, and the legacy key
+    # (name ^ gene * constant) collides structurally on those — splitmix64 finaliser, as hash_qname ends with
+    h = reads["name_hash"].astype(np.uint64)
+    h = (h ^ (h >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+    h = (h ^ (h >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+    reads["name_hash"] = h ^ (h >> np.uint64(31))
+    kw = dict(strand_mode=int(rng.integers(0, 3)), unpaired=bool(rng.random() < 0.3), exclude_chimeric=bool(rng.random() < 0.3),
+              mapq=int(rng.choice([255, 4, 60, 3])), mismatches=int(rng.choice([6, 6, 0, 12])))
+    cfg = lambda: api.make_config(max_records=len(reads), legacy=True, **kw)
+    want, want_bytes = run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+    got, got_bytes = run_hostlegacy(api, ann, reads, blocks, cfg())
+    assert_same(api, got, want, f"legacy fuzz seed {seed} {kw}")
+    assert got_bytes == want_bytes
