@@ -401,3 +401,41 @@ def test_contig_order_and_returning_contigs_match_the_reference(libs, tmp_path, 
         assert pr.returncode == po.returncode == 0, (flags, pr.returncode, po.returncode, pr.stderr[-400:], po.stderr[-400:])
         identical = set(compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}")))
         assert {"f.sam.gene_reads.gct", "f.sam.gene_fragments.gct", "f.sam.exon_reads.gct"} <= identical, (flags, identical)
+
+
+@pytest.mark.skipif(not os.path.exists(SAM2CRAM), reason="reference htslib tool not built (make ref)")
+def test_long_reads_spanning_many_bgzf_blocks(libs, tmp_path):
+    """Records of up to 1.2 M bases and hundreds of CIGAR operations (one record = up to ~19 BGZF blocks) among short ones: the
+    multi-threaded BAM ingest has to carry partial records across its jobs; all readers against the reference."""
+    import subprocess
+    rng = random.Random(3)
+    d = str(tmp_path)
+    gtf, sam, bam = os.path.join(d, "f.gtf"), os.path.join(d, "f.sam"), os.path.join(d, "f.bam")
+    _gtf(gtf, rng)
+    hdr = ["@HD\tVN:1.0\tSO:coordinate", "@SQ\tSN:chr1\tLN:3000000", "@SQ\tSN:chr2\tLN:3000000", "@SQ\tSN:chrM\tLN:3000000"]
+    recs = []
+    for i in range(400):
+        pos = rng.randint(1, 50000)
+        if rng.random() < 0.1:
+            left, q, ops = rng.choice([5000, 70000, 300000, 1200000]), 0, []
+            while left > 0:
+                m = min(left, rng.randint(50, 4000))
+                ops.append(f"{m}M")
+                q += m
+                left -= m
+                if left > 0:
+                    t, k = rng.choice("IDN"), rng.randint(1, 300)
+                    ops.append(f"{k}{t}")
+                    q += k if t == "I" else 0
+            cigar, seq = "".join(ops), "A" * q
+        else:
+            cigar, seq = "76M", "C" * 76
+        recs.append((pos, "\t".join([f"L{i}", str(rng.choice([0, 16])), "chr1", str(pos), "255", cigar, "*", "0", "0", seq, "*", "NM:i:0"])))
+    recs.sort()
+    open(sam, "w").write("\n".join(hdr + [r[1] for r in recs]) + "\n")
+    subprocess.run([SAM2CRAM, sam, "-", bam], check=True, stderr=subprocess.DEVNULL)
+    run_cli(REF, gtf, bam, os.path.join(d, "ref"), "-u")
+    for threads in ("0", "2", "8"):
+        run_cli(libs["oracle_cli"], gtf, bam, os.path.join(d, "ours" + threads), "-u", "--decode-threads", threads)
+        identical = set(compare_outputs(os.path.join(d, "ref"), os.path.join(d, "ours" + threads)))
+        assert {"f.bam.gene_reads.gct", "f.bam.exon_reads.gct", "f.bam.metrics.tsv"} <= identical, (threads, identical)
