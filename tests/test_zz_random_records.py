@@ -140,3 +140,24 @@ def test_pairs_harness_on_the_oracle(libs, tmp_path, name):
 @pytest.mark.parametrize("name", sorted(PAIR_CONFIGS))
 def test_cuda_samplers_match_oracle_on_odd_pairs(libs, tmp_path, name, seed):
     _check_pairs(libs, tmp_path, libs["product"], seed, name)
+
+
+@pytest.mark.parametrize("seed", [5021, 5038, 4100])
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_host_emulation_of_the_device_logic_on_the_same_records(libs, tmp_path, name, seed):
+    """What the -m gpu variant above feeds the CUDA kernels, through the kernels' own per-record sources compiled for the CPU
+    (tests/hostcore): whatever the GPU run may still find can only be in the warp plumbing."""
+    import test_hostcore as T
+    api = libs["api"]
+    kw = dict(CONFIGS[name])
+    legacy = kw.pop("legacy", False)
+    ann, sam = _case(api, str(tmp_path), seed, legacy)
+    reads, blocks, _ = ann.decode(sam, exclude_chimeric=kw.get("exclude_chimeric", False), chimeric_distance=kw.get("chimeric_distance", 2000000))
+    cfg = lambda: api.make_config(max_records=len(reads), legacy=legacy, **kw)
+    want, want_bytes = T.run_oracle(api, libs["oracle"], ann, reads, blocks, cfg())
+    if legacy:
+        got, got_bytes = T.run_hostlegacy(api, ann, reads, blocks, cfg())
+    else:
+        got, got_bytes, _ = T.run_hostcore(api, ann, reads, blocks, cfg())
+    T.assert_same(api, got, want, f"{name} seed {seed}")
+    assert got_bytes == want_bytes
