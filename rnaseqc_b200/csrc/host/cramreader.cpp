@@ -152,12 +152,21 @@ void rans_decode(const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
 // ---- blocks --------------------------------------------------------------------------------------------------------------
 struct Block {
     int method = 0, content_type = 0, content_id = 0;
+    // Blocks of a slice are decompressed on first READ: the record loop only SKIPS over the quality and base series (by far the
+    // largest blocks), so those are never inflated at all.
+    const uint8_t* comp = nullptr;
+    size_t comp_n = 0, raw_n = 0;
+    bool loaded = false;
     std::vector<uint8_t> data;
     size_t pos = 0;          // byte cursor (EXTERNAL / BYTE_ARRAY_STOP)
     size_t bit = 0;          // bit cursor (core block), counted from the start of data
-    uint8_t byte() { if (pos >= data.size()) bad("external block exhausted"); return data[pos++]; }
-    int32_t itf8() { Cursor c{data.data() + pos, data.data() + data.size()}; const int32_t v = c.itf8(); pos = (size_t)(c.p - data.data()); return v; }
+    void load();
+    void need() { if (!loaded) load(); }
+    uint8_t byte() { need(); if (pos >= data.size()) bad("external block exhausted"); return data[pos++]; }
+    void skip(size_t n) { if (pos + n > raw_n) bad("external block exhausted"); pos += n; }   // no data needed
+    int32_t itf8() { need(); Cursor c{data.data() + pos, data.data() + data.size()}; const int32_t v = c.itf8(); pos = (size_t)(c.p - data.data()); return v; }
     uint32_t bits(int n) {
+        need();
         uint32_t v = 0;
         for (int k = 0; k < n; ++k) {
             if ((bit >> 3) >= data.size()) bad("core block exhausted");
@@ -180,23 +189,34 @@ void inflate_gzip(const uint8_t* in, size_t n, size_t raw, std::vector<uint8_t>&
     if (rc != Z_STREAM_END && !(rc == Z_OK && z.avail_out == 0) && !(rc == Z_BUF_ERROR && z.avail_out == 0)) bad("gzip block");
 }
 
-Block read_block(Cursor& c, int major) {
+void Block::load() {
+    loaded = true;
+    switch (method) {
+        case 0: data.assign(comp, comp + comp_n); break;
+        case 1: inflate_gzip(comp, comp_n, raw_n, data); break;
+        case 4: rans_decode(comp, comp_n, data); break;
+        default: bad("block compression method " + std::to_string(method));
+    }
+    if (data.size() != raw_n) bad("block size differs from its header");   // skip() trusted the header
+}
+
+Block read_block(Cursor& c, int major, bool lazy = false) {
     Block b;
     b.method = c.u8();
     b.content_type = c.u8();
     b.content_id = c.itf8();
     const int32_t comp = c.itf8(), raw = c.itf8();
     if (comp < 0 || raw < 0) bad("block sizes");
-    const uint8_t* d = c.take((size_t)comp);
+    b.comp = c.take((size_t)comp);
+    b.comp_n = (size_t)comp; b.raw_n = (size_t)raw;
     switch (b.method) {
-        case 0: b.data.assign(d, d + comp); break;
-        case 1: inflate_gzip(d, (size_t)comp, (size_t)raw, b.data); break;
-        case 4: rans_decode(d, (size_t)comp, b.data); break;
+        case 0: case 1: case 4: break;
         case 2: bad("bzip2-compressed block (this build, like the reference's test build, has no bzip2)");
         case 3: bad("lzma-compressed block (this build, like the reference's test build, has no lzma)");
         default: bad("block compression method " + std::to_string(b.method));
     }
     if (major >= 3) c.take(4);   // CRC32
+    if (!lazy) b.load();
     return b;
 }
 
@@ -304,6 +324,12 @@ uint8_t decode_byte(const Codec& e, SliceCtx& s) {
     return (uint8_t)decode_int(e, s);
 }
 
+// one byte whose value is not needed
+void skip_byte(const Codec& e, SliceCtx& s) {
+    if (e.kind == E_EXTERNAL) s.external(e).skip(1);
+    else (void)decode_int(e, s);
+}
+
 // byte array; `n` < 0: the encoding knows the length (BYTE_ARRAY_LEN / BYTE_ARRAY_STOP), else n items of a byte encoding
 void decode_bytes(const Codec& e, SliceCtx& s, int32_t n, std::vector<uint8_t>* out) {
     if (out) out->clear();
@@ -318,11 +344,27 @@ void decode_bytes(const Codec& e, SliceCtx& s, int32_t n, std::vector<uint8_t>* 
         if (n < 0) bad("byte array without a length");
         if (e.kind == E_EXTERNAL) {
             Block& b = s.external(e);
-            if (b.pos + (size_t)n > b.data.size()) bad("external block exhausted");
-            if (out) out->assign(b.data.begin() + (long)b.pos, b.data.begin() + (long)b.pos + n);
-            b.pos += (size_t)n;
+            if (!out) b.skip((size_t)n);
+            else {
+                b.need();
+                if (b.pos + (size_t)n > b.data.size()) bad("external block exhausted");
+                out->assign(b.data.begin() + (long)b.pos, b.data.begin() + (long)b.pos + n);
+                b.pos += (size_t)n;
+            }
         } else for (int32_t i = 0; i < n; ++i) { const uint8_t v = decode_byte(e, s); if (out) out->push_back(v); }
     }
+}
+
+// length of a self-delimiting byte array whose content is not needed
+int32_t skip_bytes_len(const Codec& e, SliceCtx& s, std::vector<uint8_t>& scratch) {
+    if (e.kind == E_BYTE_ARRAY_LEN) {
+        const int32_t len = decode_int(*e.len_codec, s);
+        if (len < 0) bad("byte array length");
+        decode_bytes(*e.val_codec, s, len, nullptr);
+        return len;
+    }
+    decode_bytes(e, s, -1, &scratch);
+    return (int32_t)scratch.size();
 }
 
 struct CompHeader {
@@ -587,7 +629,7 @@ private:
         if (embedded >= 0) bad("slice with an embedded reference");
         std::vector<Block> blocks;
         blocks.reserve((size_t)std::max(n_blocks, 0));
-        for (int32_t i = 0; i < n_blocks; ++i) blocks.push_back(read_block(c, major_));
+        for (int32_t i = 0; i < n_blocks; ++i) blocks.push_back(read_block(c, major_, true));
         SliceCtx ctx;
         for (Block& b : blocks) { if (b.content_type == 5) ctx.core = &b; else if (b.content_type == 4) ctx.ext[b.content_id] = &b; }
         if (!ctx.core) bad("slice without a core block");
@@ -700,11 +742,11 @@ private:
                 if (pos > seq_pos) implicit_match(pos - seq_pos);
                 prev = pos;
                 switch (op) {
-                    case 'S': { decode_bytes(need(ch.SC, "SC"), ctx, -1, &scratch);
+                    case 'S': { const int32_t n = skip_bytes_len(need(ch.SC, "SC"), ctx, scratch);
                                 if (run_len) { a.cigar.push_back((run_len << 4) | (uint32_t)run_op); run_len = 0; }
-                                a.cigar.push_back(((uint32_t)scratch.size() << 4) | 4u); run_op = 4;
-                                seq_pos += (int32_t)scratch.size(); break; }
-                    case 'X': { decode_byte(need(ch.BS, "BS"), ctx);
+                                a.cigar.push_back(((uint32_t)n << 4) | 4u); run_op = 4;
+                                seq_pos += n; break; }
+                    case 'X': { skip_byte(need(ch.BS, "BS"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 0, 1);
                                 if (count_nm && ref_pos < ref_len) ++nm;
                                 ++seq_pos; ++ref_pos; break; }
@@ -712,24 +754,24 @@ private:
                                 push_cigar(a.cigar, run_len, run_op, 2, (uint32_t)n);
                                 if (count_nm) nm += (uint32_t)std::max<int64_t>(0, std::min<int64_t>(n, ref_len - ref_pos));
                                 ref_pos += n; break; }
-                    case 'I': { decode_bytes(need(ch.IN, "IN"), ctx, -1, &scratch);
-                                push_cigar(a.cigar, run_len, run_op, 1, (uint32_t)scratch.size());
-                                seq_pos += (int32_t)scratch.size(); if (count_nm) nm += (uint32_t)scratch.size(); break; }
-                    case 'i': { decode_byte(need(ch.BA, "BA"), ctx);
+                    case 'I': { const int32_t n = skip_bytes_len(need(ch.IN, "IN"), ctx, scratch);
+                                push_cigar(a.cigar, run_len, run_op, 1, (uint32_t)n);
+                                seq_pos += n; if (count_nm) nm += (uint32_t)n; break; }
+                    case 'i': { skip_byte(need(ch.BA, "BA"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 1, 1);
                                 ++seq_pos; if (count_nm) ++nm; break; }
-                    case 'b': { decode_bytes(need(ch.BB, "BB"), ctx, -1, &scratch);
-                                push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)scratch.size());
-                                if (count_nm) nm += (uint32_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)scratch.size(), ref_len - ref_pos));
-                                seq_pos += (int32_t)scratch.size(); ref_pos += (int64_t)scratch.size(); break; }
-                    case 'q': { decode_bytes(need(ch.QQ, "QQ"), ctx, -1, &scratch);
-                                push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)scratch.size());
-                                seq_pos += (int32_t)scratch.size(); ref_pos += (int64_t)scratch.size(); break; }
-                    case 'B': { decode_byte(need(ch.BA, "BA"), ctx); decode_byte(need(ch.QS, "QS"), ctx);
+                    case 'b': { const int32_t n = skip_bytes_len(need(ch.BB, "BB"), ctx, scratch);
+                                push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)n);
+                                if (count_nm) nm += (uint32_t)std::max<int64_t>(0, std::min<int64_t>((int64_t)n, ref_len - ref_pos));
+                                seq_pos += n; ref_pos += (int64_t)n; break; }
+                    case 'q': { const int32_t n = skip_bytes_len(need(ch.QQ, "QQ"), ctx, scratch);
+                                push_cigar(a.cigar, run_len, run_op, 0, (uint32_t)n);
+                                seq_pos += n; ref_pos += (int64_t)n; break; }
+                    case 'B': { skip_byte(need(ch.BA, "BA"), ctx); skip_byte(need(ch.QS, "QS"), ctx);
                                 push_cigar(a.cigar, run_len, run_op, 0, 1);
                                 if (count_nm && ref_pos < ref_len) ++nm;
                                 ++seq_pos; ++ref_pos; break; }
-                    case 'Q': decode_byte(need(ch.QS, "QS"), ctx); break;
+                    case 'Q': skip_byte(need(ch.QS, "QS"), ctx); break;
                     case 'H': { const int32_t n = decode_int(need(ch.HC, "HC"), ctx); push_cigar(a.cigar, run_len, run_op, 5, (uint32_t)n); break; }
                     case 'P': { const int32_t n = decode_int(need(ch.PD, "PD"), ctx); push_cigar(a.cigar, run_len, run_op, 6, (uint32_t)n); break; }
                     case 'N': { const int32_t n = decode_int(need(ch.RS, "RS"), ctx); push_cigar(a.cigar, run_len, run_op, 3, (uint32_t)n); ref_pos += n; break; }
