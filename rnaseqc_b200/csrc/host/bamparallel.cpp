@@ -3,9 +3,17 @@
 // Pipeline (all stages overlap):
 //   reader thread : sequential file read, BGZF block framing, groups ~4 MB of blocks into a job
 //   workers       : inflate a job (raw deflate per block)           -> job.out
-//                   FRAME the next job in file order (sequential, tiny: hops over block_size fields, carries the partial
-//                   record at the end of a job into the head-room of the next)
-//                   CONVERT a framed job: every whole BAM record -> rsq_read + rsq_block (Decoder::convert_bam_bytes, pure)
+//                   and SPECULATE while its bytes are still in this core's cache: guess where the first record of the job
+//                   starts (the first offset from which several plausible records follow one another), hop to the end of
+//                   the job along block_size fields and convert every record on that chain
+//                   FRAME the next job in file order (sequential): the true start of the job's first fresh record follows
+//                   from the partial record carried over from the previous job; if it lies on the speculated chain (hopping
+//                   is deterministic, so the chain from there on IS the record stream) the job is done but for the one carried
+//                   record — O(1) sequential work per job.  Otherwise (wrong guess, corrupt bytes, a record longer than a job,
+//                   the BAM header) the sequential hop over block_size fields of the first version runs, followed by
+//                   CONVERT of the framed job: every whole BAM record -> rsq_read + rsq_block (Decoder::convert_bam_bytes, pure)
+//                   (the dependent hop through 4 MB another core had just written cost ~100 ns per record and capped ingest
+//                   at ~10 M records/s whatever the number of workers)
 //   consumer      : next_batch(): takes converted jobs in file order, runs Decoder::observe (readLength, contig-drop
 //                   state, unsorted warning: src/RNASeQC.cpp:275-278,346-356) and appends to the caller's batch
 #include "bamparallel.h"
@@ -13,6 +21,9 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 namespace rsqh {
@@ -20,6 +31,11 @@ namespace rsqh {
 namespace {
 constexpr size_t kJobUncompressed = 4u << 20;   // target decompressed bytes per job
 constexpr size_t kHeadroom = 256u << 10;        // room in front of a job's output for the previous job's partial record
+
+using clk = std::chrono::steady_clock;
+inline double since(clk::time_point t) { return std::chrono::duration<double>(clk::now() - t).count(); }
+
+std::atomic<unsigned long long> g_last_hits{0}, g_last_misses{0};
 
 enum { ST_READ = 0, ST_INFLATING, ST_INFLATED, ST_FRAMING, ST_FRAMED, ST_CONVERTING, ST_CONVERTED };
 
@@ -65,6 +81,27 @@ void inflate_block(const uint8_t* src, size_t n, uint8_t* dst, size_t isize) {
     inflateEnd(&zs);
     if (rc != Z_STREAM_END) throw HostError(-1, "BGZF inflate failed");
 }
+
+// One BAM record at base[p..): 1 = whole and plausible, 2 = incomplete tail (to be carried), 0 = not a record as far as the
+// fixed fields can tell (SAM spec 4.2: field sizes must add up inside block_size, reference ids in range, NUL-terminated
+// name, CIGAR operations 0-8).  Only used to pick and vet a speculated chain; a chain that fails is simply not used.
+int plausible_record(const uint8_t* base, size_t p, size_t end, int32_t n_ref) {
+    if (p + 4 > end) return 2;
+    uint32_t bs; memcpy(&bs, base + p, 4);
+    if (bs < 32 || bs > (1u << 28)) return 0;
+    if (p + 36 > end) return 2;
+    const uint8_t* b = base + p + 4;
+    int32_t tid, mtid, l_seq; uint16_t n_cigar;
+    memcpy(&tid, b, 4); memcpy(&mtid, b + 20, 4); memcpy(&l_seq, b + 16, 4); memcpy(&n_cigar, b + 12, 2);
+    const size_t l_name = b[8];
+    if (tid < -1 || tid >= n_ref || mtid < -1 || mtid >= n_ref || l_seq < 0 || l_name == 0) return 0;
+    const size_t fixed = 32 + l_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+    if (fixed > bs) return 0;
+    if (p + 4 + (size_t)bs > end) return 2;
+    if (b[32 + l_name - 1] != 0) return 0;
+    for (size_t k = 0; k < n_cigar; ++k) if ((b[32 + l_name + 4 * k] & 0xf) > 8) return 0;
+    return 1;
+}
 }  // namespace
 
 struct ParallelBamDecoder::Job {
@@ -79,6 +116,16 @@ struct ParallelBamDecoder::Job {
     std::vector<rsq_read> reads;
     std::vector<rsq_block> rblocks;
     std::vector<int32_t> tids;
+    // speculation (inflate stage): record starts of the guessed chain inside `out`, ascending; reads[k] belongs to chain[k]
+    std::vector<uint32_t> chain;
+    size_t chain_end = 0;              // first byte after the last whole record of the chain
+    bool spec_ok = false;
+    size_t first_read = 0;             // the consumer starts at reads[first_read]
+    // the record carried over from the previous job, converted by the framer (speculation hit only)
+    bool has_head = false;
+    rsq_read head_read;
+    int32_t head_tid = 0;
+    std::vector<rsq_block> head_blocks;
     std::string error;
     int error_code = 0;
     int state = ST_READ;
@@ -122,6 +169,7 @@ ParallelBamDecoder::ParallelBamDecoder(const std::string& path, int n_threads)
         std::fseek(fp_, 0, SEEK_SET);
     }
     max_jobs_in_flight_ = (size_t)n_threads_ * 3 + 4;
+    speculate_ = !std::getenv("RSQ_INGEST_NO_SPECULATION");
 }
 
 ParallelBamDecoder::~ParallelBamDecoder() {
@@ -136,7 +184,15 @@ ParallelBamDecoder::~ParallelBamDecoder() {
     for (auto& t : workers_) if (t.joinable()) t.join();
     jobs_.clear();
     if (fp_) std::fclose(fp_);
+    g_last_hits = n_chain_hits_; g_last_misses = n_chain_misses_;
+    if (std::getenv("RSQ_INGEST_STATS"))
+        std::fprintf(stderr, "ingest busy seconds: reader %.3f, frame %.3f, inflate %.3f + convert %.3f over %d workers, consumer %.3f (+ %.3f waiting); jobs framed on the speculated chain %llu, by the sequential hop %llu\n",
+                     t_reader_, t_frame_, t_inflate_, t_convert_, n_threads_, t_consumer_, t_consumer_wait_,
+                     (unsigned long long)n_chain_hits_, (unsigned long long)n_chain_misses_);
 }
+
+unsigned long long ParallelBamDecoder::last_chain_hits() { return g_last_hits; }
+unsigned long long ParallelBamDecoder::last_chain_misses() { return g_last_misses; }
 
 void ParallelBamDecoder::reader_loop() {
     try {
@@ -151,7 +207,9 @@ void ParallelBamDecoder::reader_loop() {
             job->comp.clear(); job->c_off.clear(); job->c_len.clear(); job->u_len.clear();
             job->reads.clear(); job->rblocks.clear(); job->tids.clear(); job->big.clear();
             job->use_big = false; job->error.clear(); job->error_code = 0; job->state = ST_READ;
+            job->chain.clear(); job->chain_end = 0; job->spec_ok = false; job->first_read = 0; job->has_head = false; job->head_blocks.clear();
             size_t total = 0;
+            const auto t_job = clk::now();
             while (total < kJobUncompressed) {
                 uint32_t off, len, isize;
                 if (!read_bgzf_block(fp_, job->comp, off, len, isize)) { eof = true; break; }
@@ -160,6 +218,7 @@ void ParallelBamDecoder::reader_loop() {
             }
             if (job->c_off.empty()) break;
             job->data_len = total;
+            t_reader_ += since(t_job);
             std::unique_lock<std::mutex> lk(mu_);
             cv_reader_.wait(lk, [&] { return stop_ || jobs_.size() < max_jobs_in_flight_; });
             if (stop_) return;
@@ -183,6 +242,71 @@ void ParallelBamDecoder::reader_loop() {
     cv_consumer_.notify_all();
 }
 
+// Inflate stage, on the worker that has just written the job's bytes: pick the first offset from which four plausible records
+// follow one another, hop to the end of the job, convert every record on the way.  Pure (no shared state).
+void ParallelBamDecoder::speculate(Job& j) const {
+    const uint8_t* base = j.out.data();
+    const size_t begin = kHeadroom, end = kHeadroom + j.data_len;
+    const int32_t n_ref = (int32_t)hdr_.ref_names.size();
+    const size_t scan_end = std::min(end, begin + (64u << 10));
+    for (size_t s = begin; s < scan_end; ++s) {
+        size_t p = s;
+        int k = 0, v = 1;
+        for (; k < 4 && (v = plausible_record(base, p, end, n_ref)) == 1; ++k) { uint32_t bs; memcpy(&bs, base + p, 4); p += 4 + (size_t)bs; }
+        if (v == 0 || k == 0) continue;
+        // the chain from s
+        j.chain.clear(); j.reads.clear(); j.rblocks.clear(); j.tids.clear();
+        j.reads.reserve(j.data_len / 200 + 16);
+        p = s;
+        try {
+            while ((v = plausible_record(base, p, end, n_ref)) == 1) {
+                uint32_t bs; memcpy(&bs, base + p, 4);
+                rsq_read r; int32_t tid;
+                dec_for_params_->convert_bam_bytes(base + p + 4, bs, r, j.rblocks, tid);
+                j.chain.push_back((uint32_t)p);
+                j.reads.push_back(r);
+                j.tids.push_back(tid);
+                p += 4 + (size_t)bs;
+            }
+        } catch (...) { v = 0; }
+        if (v == 2) { j.chain_end = p; j.spec_ok = true; }
+        else { j.chain.clear(); j.reads.clear(); j.rblocks.clear(); j.tids.clear(); }
+        return;                                  // one guess per job: a second would cost a second conversion
+    }
+}
+
+// Frame stage (sequential): does the job's first fresh record start on the speculated chain?  Then the chain from there on is
+// the record stream; only the record carried over from the previous job is left to convert.  Returns false (nothing changed)
+// when the sequential hop has to run instead.
+bool ParallelBamDecoder::frame_on_chain(Job& j, size_t begin, size_t end) {
+    uint8_t* base = j.out.data();
+    const size_t c = carry_.size();
+    size_t fresh = begin;
+    uint32_t bs = 0;
+    if (c) {
+        if (c > begin || c + (end - begin) < 4) return false;
+        uint8_t len4[4];
+        for (size_t k = 0; k < 4; ++k) len4[k] = k < c ? carry_[k] : base[begin + (k - c)];
+        memcpy(&bs, len4, 4);
+        if (bs < 32 || 4 + (size_t)bs < c) return false;
+        const size_t need = 4 + (size_t)bs - c;
+        if (begin + need > end) return false;
+        fresh = begin + need;
+    }
+    const auto it = std::lower_bound(j.chain.begin(), j.chain.end(), (uint32_t)fresh);
+    if (it == j.chain.end() || *it != fresh) return false;
+    if (c) {
+        memcpy(base + begin - c, carry_.data(), c);
+        j.head_blocks.clear();
+        dec_for_params_->convert_bam_bytes(base + begin - c + 4, bs, j.head_read, j.head_blocks, j.head_tid);   // may throw: the job's error, as in CONVERT
+        j.head_read.block_off = 0;
+        j.has_head = true;
+    }
+    j.first_read = (size_t)(it - j.chain.begin());
+    carry_.assign(base + j.chain_end, base + end);
+    return true;
+}
+
 void ParallelBamDecoder::worker_loop() {
     std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
@@ -201,14 +325,17 @@ void ParallelBamDecoder::worker_loop() {
             continue;
         }
         lk.unlock();
+        const auto t_stage = clk::now();
+        bool framed_by_chain = false;
         try {
             if (what == 3) {
-                if (todo->out.size() < kHeadroom + todo->data_len) todo->out.resize(kHeadroom + todo->data_len);
+                if (todo->out.size() < kHeadroom + todo->data_len + 16) todo->out.resize(kHeadroom + todo->data_len + 16);
                 size_t o = kHeadroom;
                 for (size_t b = 0; b < todo->c_off.size(); ++b) {
                     inflate_block(todo->comp.data() + todo->c_off[b], todo->c_len[b], todo->out.data() + o, todo->u_len[b]);
                     o += todo->u_len[b];
                 }
+                if (speculate_) speculate(*todo);
             } else if (what == 1) {
                 // frame: [carry | data] must be contiguous; then hop over whole records
                 uint8_t* base = todo->out.data();
@@ -217,6 +344,10 @@ void ParallelBamDecoder::worker_loop() {
                     const size_t s = (size_t)std::min<uint64_t>(skip_bytes_, todo->data_len);
                     begin += s; skip_bytes_ -= s;
                 }
+                if (todo->spec_ok && !skip_bytes_ && frame_on_chain(*todo, begin, end)) {
+                    framed_by_chain = true;
+                } else {
+                todo->reads.clear(); todo->rblocks.clear(); todo->tids.clear(); todo->first_read = 0; todo->has_head = false;
                 if (!carry_.empty()) {
                     if (carry_.size() <= begin) { begin -= carry_.size(); memcpy(base + begin, carry_.data(), carry_.size()); }
                     else {
@@ -236,6 +367,7 @@ void ParallelBamDecoder::worker_loop() {
                 }
                 todo->rec_begin = begin; todo->rec_end = p;
                 carry_.assign(base + p, base + end);
+                }
             } else {
                 const uint8_t* base = todo->use_big ? todo->big.data() : todo->out.data();
                 size_t p = todo->rec_begin;
@@ -254,14 +386,20 @@ void ParallelBamDecoder::worker_loop() {
         } catch (std::exception& e) {
             todo->error = e.what(); todo->error_code = -1;
         }
+        const double dt_stage = since(t_stage);
         lk.lock();
+        (what == 3 ? t_inflate_ : what == 1 ? t_frame_ : t_convert_) += dt_stage;
         if (!todo->error.empty()) {
             // a failed job surfaces at the consumer when its turn comes; framing moves past it so earlier records still flow
             if (todo->id == next_frame_id_) ++next_frame_id_;
             todo->state = ST_CONVERTED;
             cv_consumer_.notify_all();
         } else if (what == 3) todo->state = ST_INFLATED;
-        else if (what == 1) { todo->state = ST_FRAMED; ++next_frame_id_; }
+        else if (what == 1) {
+            ++next_frame_id_;
+            if (framed_by_chain) { todo->state = ST_CONVERTED; ++n_chain_hits_; cv_consumer_.notify_all(); }
+            else { todo->state = ST_FRAMED; ++n_chain_misses_; }
+        }
         else { todo->state = ST_CONVERTED; cv_consumer_.notify_all(); }
         cv_work_.notify_all();
     }
@@ -284,7 +422,9 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
         if (!job) {
             std::unique_lock<std::mutex> lk(mu_);
             auto& q = jobs_;
+            const auto t_wait = clk::now();
             cv_consumer_.wait(lk, [&] { return stop_ || (!q.empty() && q.front()->state == ST_CONVERTED) || (reader_done_ && q.empty()); });
+            t_consumer_wait_ += since(t_wait);
             if (stop_ || q.empty()) break;
             job = q.front();
             q.pop_front();
@@ -293,9 +433,19 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
             cv_work_.notify_all();
             if (!job->error.empty()) throw HostError(job->error_code, job->error);
             cur_ = job;
-            cur_read_ = 0;
+            cur_read_ = job->first_read;
+            if (job->has_head) {                 // the record that straddles the previous job's end comes first
+                rsq_read r = job->head_read;
+                r.block_off = (uint32_t)blocks.size();
+                blocks.insert(blocks.end(), job->head_blocks.begin(), job->head_blocks.end());
+                reads.push_back(r);
+                dec.observe(reads.back(), job->head_tid);
+                job->has_head = false;
+                if (reads.size() >= max_records) continue;
+            }
         }
         const size_t n = std::min(job->reads.size() - cur_read_, max_records - reads.size());
+        const auto t_copy = clk::now();
         if (n) {
             // bulk append: the records of a job and their blocks are contiguous and in file order
             const rsq_read* first = job->reads.data() + cur_read_;
@@ -312,6 +462,7 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
                 dec.observe(out[k], tids[k]);
             }
         }
+        t_consumer_ += since(t_copy);
         cur_read_ += n;
         if (cur_read_ >= job->reads.size()) {
             { std::lock_guard<std::mutex> lk(mu_); pool_.push_back(cur_); }

@@ -29,11 +29,16 @@ public:
     // Appends up to max_records converted records (with their blocks) to the cleared vectors, in file order, running
     // dec.observe() on each.  Returns false once the stream is exhausted and nothing was appended.
     bool next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
+    // framing statistics of the decoder destroyed last (tests, diagnostics)
+    static unsigned long long last_chain_hits();
+    static unsigned long long last_chain_misses();
 
 private:
     struct Job;                        // one ~4 MB piece of the decompressed stream (bamparallel.cpp)
     void reader_loop();
     void worker_loop();
+    void speculate(Job& j) const;                              // inflate stage: guessed record chain, converted
+    bool frame_on_chain(Job& j, size_t begin, size_t end);     // frame stage: O(1) when the true start lies on that chain
 
     std::string path_;
     AlnHeader hdr_;
@@ -57,6 +62,11 @@ private:
     // consumer cursor
     std::shared_ptr<Job> cur_;
     size_t cur_read_ = 0;
+    // busy seconds per stage, printed by the destructor when RSQ_INGEST_STATS is set (reader and consumer: one thread each;
+    // frame: one worker at a time; inflate and convert: summed over the workers)
+    bool speculate_ = true;            // RSQ_INGEST_NO_SPECULATION=1: the sequential hop for every job (A/B, tests)
+    uint64_t n_chain_hits_ = 0, n_chain_misses_ = 0;
+    double t_reader_ = 0, t_frame_ = 0, t_inflate_ = 0, t_convert_ = 0, t_consumer_ = 0, t_consumer_wait_ = 0;
 };
 
 }  // namespace rsqh
