@@ -414,54 +414,6 @@ void Decoder::convert(const RawAln& a, std::vector<rsq_read>& reads, std::vector
     reads.push_back(r);
 }
 
-void Decoder::observe(rsq_read& r, int32_t tid) {
-    ++alignment_count_;
-    const int n_refs = (int)tid_to_contig_.size();
-    const bool tid_ok = tid >= 0 && tid < n_refs;
-    const int chr = tid_ok ? tid_to_contig_[tid] : -1;
-    // ---- order-dependent scalar state: the same gates as the loop, in the same order -----------------------
-    const bool has_ch = r.aux & RSQ_AUX_CHIMERIC_TAG;
-    bool reaches_metrics = false;
-    do {
-        if ((r.flag & RSQ_F_SUPPLEMENTARY) && !(opt_.legacy || has_ch) && opt_.exclude_chimeric) break;   // :258-262
-        if (r.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) break;               // :263
-        if (r.flag & RSQ_F_UNMAP) break;                                                           // :268
-        const unsigned alignment_size = (unsigned)(r.endpos - r.pos);                              // :275
-        if (opt_.legacy && alignment_size > 100000u) break;                                        // :276 LEGACY_MAX_READ_LENGTH
-        if (!read_length_ && tid_ok) current_chrom_ = chr;                                         // :277
-        if (alignment_size > (unsigned)read_length_) read_length_ = r.l_qseq;                      // :278
-        if (!opt_.legacy && has_ch && opt_.exclude_chimeric) break;                                // :279-283
-        if ((r.flag & RSQ_F_PAIRED) && !(r.flag & RSQ_F_MUNMAP)) {                                 // :284-292
-            const bool chim = (r.aux & RSQ_AUX_MATE_OTHER_CONTIG) || std::abs(r.pos - r.mpos) > opt_.chimeric_distance ||
-                              (opt_.legacy && tid > 127);
-            if (chim && opt_.exclude_chimeric) break;
-        }
-        if (r.filter_mask) break;                                                                  // :319-328
-        if (!tid_ok) {                                                                             // :333-337
-            if (opt_.verbosity) std::cerr << "Unrecognized RefID on alignment #" << alignment_count_ << std::endl;
-            break;
-        }
-        reaches_metrics = true;
-    } while (false);
-    if (reaches_metrics) {
-        if ((size_t)chr >= dropped_.size()) dropped_.resize(chr + 1, 0);
-        if (chr != current_chrom_) {                                                               // :346-353
-            if (current_chrom_ >= 0) {
-                if ((size_t)current_chrom_ >= dropped_.size()) dropped_.resize(current_chrom_ + 1, 0);
-                if (!dropped_[current_chrom_]) dropped_order_.push_back((uint32_t)current_chrom_);
-                dropped_[current_chrom_] = 1;
-            }
-            current_chrom_ = chr;
-        } else if (last_position_ > r.pos && !warned_unsorted_) {                                  // :354-355
-            std::cerr << "Warning: The input bam does not appear to be sorted. An unsorted bam will yield incorrect results" << std::endl;
-            warned_unsorted_ = true;
-        }
-        last_position_ = r.pos;
-        last_metrics_chrom_ = chr;
-        if (dropped_[chr]) r.aux |= RSQ_AUX_CONTIG_DROPPED;
-    }
-}
-
 // Pure conversion of one raw BAM record (no RawAln intermediate): same field semantics as convert(RawAln).
 void Decoder::convert_bam_bytes(const uint8_t* b, size_t n, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid_out) const {
     if (n < 32) throw HostError(-1, "truncated BAM record");

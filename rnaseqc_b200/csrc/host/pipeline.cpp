@@ -290,13 +290,32 @@ int run_sample(const Backend& be, CliOptions& opt) {
         if (opt.verbosity) std::cout << "Device context + annotation upload: " << std::chrono::duration<double>(clk::now() - t_setup).count() << " seconds" << std::endl;
         if (opt.verbosity) std::cout << "Parsing bam..." << std::endl;
         auto t1 = clk::now();
-        std::vector<rsq_read> reads;
-        std::vector<rsq_block> blocks;
-        reads.reserve(opt.batch_records);
+        // Two batch buffers: while a helper thread packs batch i into its page-locked slot (the wire format, or the plain copy
+        // when the batch does not fit its rules), this thread already collects batch i+1 from the decoder; submits stay on this
+        // thread, in order.  (Packing was a third of this thread's time per record once the decoder's framing stopped being
+        // the sequential bottleneck.)
+        std::vector<rsq_read> reads_buf[2];
+        std::vector<rsq_block> blocks_buf[2];
+        reads_buf[0].reserve(opt.batch_records);
+        reads_buf[1].reserve(opt.batch_records);
         RawAln aln;
-        int slot = 0;
+        struct Staged { bool active = false; int slot = 0; size_t n_reads = 0, n_blocks = 0, n_packed_blocks = 0; std::future<int> packed; } staged;
+        auto submit_staged = [&]() {            // waits for the packer of the previous batch, then submits it
+            if (!staged.active) return;
+            staged.active = false;
+            const int how = staged.packed.get();
+            const int s = staged.slot;
+            int r2;
+            if (how == 1) r2 = be.submit_packed(ctx, (const rsq_read_packed*)pinned[s][0], staged.n_reads, (const rsq_block*)pinned[s][1], staged.n_packed_blocks);
+            else r2 = be.submit(ctx, (const rsq_read*)pinned[s][0], staged.n_reads, (const rsq_block*)pinned[s][1], staged.n_blocks);
+            if (r2 != RSQ_OK) throw HostError(-1, std::string("rsq_submit failed: ") + be.last_error(ctx));
+        };
+        int slot = 0, cur = 0;
         bool more = true;
+        try {
         while (more) {
+            std::vector<rsq_read>& reads = reads_buf[cur];
+            std::vector<rsq_block>& blocks = blocks_buf[cur];
             if (pbam) {
                 if (!pbam->next_batch(decoder, opt.batch_records, reads, blocks)) break;
                 more = reads.size() == opt.batch_records;
@@ -309,6 +328,7 @@ int run_sample(const Backend& be, CliOptions& opt) {
                 }
             }
             if (reads.empty()) break;
+            submit_staged();
             // stage into page-locked buffers; a slot is reused only after the device drained it
             const size_t need[2] = {reads.size() * sizeof(rsq_read), std::max<size_t>(blocks.size(), 1) * sizeof(rsq_block)};
             if (pinned_cap[slot][0]) { rc = be.sync(ctx); if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(ctx)); }
@@ -321,21 +341,30 @@ int run_sample(const Backend& be, CliOptions& opt) {
                 }
             // the compact wire format (32 B per record, no entry for a whole-read block) when the batch fits its rules; the
             // packer writes straight into the pinned buffers, so it replaces the staging memcpy
-            size_t n_packed_blocks = 0;
-            if (opt.packed_submit && be.submit_packed &&
-                rsq_pack_records(reads.data(), reads.size(), blocks.data(), blocks.size(), (rsq_read_packed*)pinned[slot][0],
-                                 (rsq_block*)pinned[slot][1], &n_packed_blocks) == RSQ_OK) {
-                rc = be.submit_packed(ctx, (const rsq_read_packed*)pinned[slot][0], reads.size(), (const rsq_block*)pinned[slot][1], n_packed_blocks);
-            } else {
-                memcpy(pinned[slot][0], reads.data(), reads.size() * sizeof(rsq_read));
-                memcpy(pinned[slot][1], blocks.data(), blocks.size() * sizeof(rsq_block));
-                rc = be.submit(ctx, (const rsq_read*)pinned[slot][0], reads.size(), (const rsq_block*)pinned[slot][1], blocks.size());
-            }
-            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_submit failed: ") + be.last_error(ctx));
+            staged.active = true; staged.slot = slot; staged.n_reads = reads.size(); staged.n_blocks = blocks.size(); staged.n_packed_blocks = 0;
+            const bool try_pack = opt.packed_submit && be.submit_packed;
+            void* dst_reads = pinned[slot][0];
+            void* dst_blocks = pinned[slot][1];
+            size_t* n_packed = &staged.n_packed_blocks;
+            const std::vector<rsq_read>* src_reads = &reads;
+            const std::vector<rsq_block>* src_blocks = &blocks;
+            staged.packed = std::async(std::launch::async, [=]() -> int {
+                if (try_pack && rsq_pack_records(src_reads->data(), src_reads->size(), src_blocks->data(), src_blocks->size(),
+                                                 (rsq_read_packed*)dst_reads, (rsq_block*)dst_blocks, n_packed) == RSQ_OK) return 1;
+                memcpy(dst_reads, src_reads->data(), src_reads->size() * sizeof(rsq_read));
+                memcpy(dst_blocks, src_blocks->data(), src_blocks->size() * sizeof(rsq_block));
+                return 0;
+            });
             slot ^= 1;
+            cur ^= 1;
             if (opt.verbosity > 1)
                 std::cout << "Time elapsed: " << std::chrono::duration<double>(clk::now() - t1).count()
                           << "; Alignments processed: " << decoder.alignment_count() << std::endl;
+        }
+        submit_staged();
+        } catch (...) {
+            if (staged.active && staged.packed.valid()) staged.packed.wait();   // the packer still reads the batch buffers
+            throw;
         }
         rc = be.sync(ctx);
         if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(ctx));

@@ -35,8 +35,20 @@ int main(int argc, char** argv) {
         std::vector<rsq_read> R; std::vector<rsq_block> B;
         auto t0 = clk::now();
         size_t n = 0;
-        while (pb.next_batch(dec, 1u << 20, R, B)) n += R.size();
+        std::vector<rsq_read_packed> P(1u << 20);
+        std::vector<rsq_block> PB;
+        double t_pack = 0;
+        while (pb.next_batch(dec, 1u << 20, R, B)) {
+            n += R.size();
+            // what the CLI's main thread does next with the batch (pipeline.cpp): the wire-format packer
+            PB.resize(B.size() + 1);
+            size_t nb = 0;
+            auto tp = clk::now();
+            rsq_pack_records(R.data(), R.size(), B.data(), B.size(), P.data(), PB.data(), &nb);
+            t_pack += std::chrono::duration<double>(clk::now() - tp).count();
+        }
         const double dt = std::chrono::duration<double>(clk::now() - t0).count();
+        std::printf("                  (of which %.3f s packing the batches into the wire format on the calling thread)\n", t_pack);
         std::printf("parallel x%-2d    : %zu records in %.3f s -> %.2f M records/s (read length %d)\n", threads, n, dt, n / dt / 1e6, dec.read_length());
     }
     return 0;
