@@ -351,10 +351,11 @@ void ParallelBamDecoder::worker_loop() {
                 if (!carry_.empty()) {
                     if (carry_.size() <= begin) { begin -= carry_.size(); memcpy(base + begin, carry_.data(), carry_.size()); }
                     else {
-                        todo->big.resize(carry_.size() + (end - begin));
+                        const size_t joined = carry_.size() + (end - begin);
+                        todo->big.resize(joined + 16);                     // slack: the aux walk may look a few bytes past a corrupt record
                         memcpy(todo->big.data(), carry_.data(), carry_.size());
                         memcpy(todo->big.data() + carry_.size(), base + begin, end - begin);
-                        todo->use_big = true; base = todo->big.data(); begin = 0; end = todo->big.size();
+                        todo->use_big = true; base = todo->big.data(); begin = 0; end = joined;
                     }
                     carry_.clear();
                 }
