@@ -12,7 +12,8 @@ from rnaseqc_b200 import synth  # noqa: E402
 
 def run(cmd):
     t = time.perf_counter()
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # RSQ_INGEST_STATS=1: the ingest's per-stage busy times (bamparallel.cpp) go to this process's stderr
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=None if os.environ.get("RSQ_INGEST_STATS") else subprocess.DEVNULL)
     return time.perf_counter() - t
 
 
