@@ -65,6 +65,18 @@ struct DecodeOptions {
 // commutative device reduction: readLength (src/RNASeQC.cpp:277-278), current_chrom / dropFeatures
 // (:346-353), the unsorted warning (:354-356), alignmentCount (:245) and the contig visit order that fixes
 // the row order of coverage.tsv.
+struct RunSummary {
+    size_t n = 0;                        // records in the run
+    bool any_read_length_line = false;   // some record gets to src/RNASeQC.cpp:277-278 ...
+    bool l_qseq_uniform = true;          // ... and all of those have the same l_qseq
+    int32_t l_qseq = 0;
+    bool bad_tid = false;                // some record stops at the reference-id check (a message under -v)
+    size_t n_reaching = 0;               // records that reach trimFeatures / dropFeatures
+    bool single_chr = true, sorted = true;
+    int chr = -1;
+    int32_t first_pos = 0, last_pos = 0;
+};
+
 class Decoder {
 public:
     Decoder(const AlnHeader& hdr, ContigMap& contigs, size_t n_annotation_contigs, const DecodeOptions& opt);
@@ -77,6 +89,9 @@ public:
     //  - observe: the order-dependent scalar state, must be called in file order
     void convert_bam_bytes(const uint8_t* rec, size_t len, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid) const;
     void observe(rsq_read& r, int32_t tid);
+    //  - summarise (pure) + observe_run: observe() for a whole run of records in O(1) when its digest allows (see below)
+    RunSummary summarise(const rsq_read* r, const int32_t* tids, size_t n) const;
+    bool observe_run(const RunSummary& s);
 
     int read_length() const { return read_length_; }
     uint64_t alignment_count() const { return alignment_count_; }
@@ -90,6 +105,7 @@ public:
     int32_t trim_position() const { return last_metrics_chrom_ == current_chrom_ ? last_position_ : INT32_MIN; }
 
 private:
+    unsigned gates(const rsq_read& r, int32_t tid, bool tid_ok) const;
     DecodeOptions opt_;
     std::vector<int> tid_to_contig_;        // BAM tid -> ContigMap id (always valid: names are added)
     size_t n_annotation_contigs_;
@@ -103,38 +119,42 @@ private:
     bool warned_unsorted_ = false;
 };
 
-// In the header: the multi-threaded ingest runs it once per record on its single consumer thread (bamparallel.cpp), where the
-// call and the reloads of the run constants were a third of that thread's time.
+// The gates of the loop in front of the order-dependent state, as a pure function of one record (same order as the loop; none of
+// them reads that state): bit 0 = the record gets to the read-length lines (:275-278), bit 1 = it reaches the metrics
+// (trimFeatures / dropFeatures, :346-356), bit 2 = it stopped at the reference-id check (:333-337).
+inline unsigned Decoder::gates(const rsq_read& r, int32_t tid, bool tid_ok) const {
+    const bool has_ch = r.aux & RSQ_AUX_CHIMERIC_TAG;
+    if ((r.flag & RSQ_F_SUPPLEMENTARY) && !(opt_.legacy || has_ch) && opt_.exclude_chimeric) return 0;   // :258-262
+    if (r.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) return 0;               // :263
+    if (r.flag & RSQ_F_UNMAP) return 0;                                                           // :268
+    const unsigned alignment_size = (unsigned)(r.endpos - r.pos);                                 // :275
+    if (opt_.legacy && alignment_size > 100000u) return 0;                                        // :276 LEGACY_MAX_READ_LENGTH
+    if (!opt_.legacy && has_ch && opt_.exclude_chimeric) return 1;                                // :279-283
+    if ((r.flag & RSQ_F_PAIRED) && !(r.flag & RSQ_F_MUNMAP)) {                                    // :284-292
+        const bool chim = (r.aux & RSQ_AUX_MATE_OTHER_CONTIG) || std::abs(r.pos - r.mpos) > opt_.chimeric_distance ||
+                          (opt_.legacy && tid > 127);
+        if (chim && opt_.exclude_chimeric) return 1;
+    }
+    if (r.filter_mask) return 1;                                                                  // :319-328
+    if (!tid_ok) return 1 | 4;                                                                    // :333-337
+    return 1 | 2;
+}
+
+// In the header: the multi-threaded ingest runs it on its single consumer thread (bamparallel.cpp).
 inline void Decoder::observe(rsq_read& r, int32_t tid) {
     ++alignment_count_;
     const int n_refs = (int)tid_to_contig_.size();
     const bool tid_ok = tid >= 0 && tid < n_refs;
     const int chr = tid_ok ? tid_to_contig_[tid] : -1;
     // ---- order-dependent scalar state: the same gates as the loop, in the same order -----------------------
-    const bool has_ch = r.aux & RSQ_AUX_CHIMERIC_TAG;
-    bool reaches_metrics = false;
-    do {
-        if ((r.flag & RSQ_F_SUPPLEMENTARY) && !(opt_.legacy || has_ch) && opt_.exclude_chimeric) break;   // :258-262
-        if (r.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) break;               // :263
-        if (r.flag & RSQ_F_UNMAP) break;                                                           // :268
+    const unsigned g = gates(r, tid, tid_ok);
+    if (g & 1) {
         const unsigned alignment_size = (unsigned)(r.endpos - r.pos);                              // :275
-        if (opt_.legacy && alignment_size > 100000u) break;                                        // :276 LEGACY_MAX_READ_LENGTH
         if (!read_length_ && tid_ok) current_chrom_ = chr;                                         // :277
         if (alignment_size > (unsigned)read_length_) read_length_ = r.l_qseq;                      // :278
-        if (!opt_.legacy && has_ch && opt_.exclude_chimeric) break;                                // :279-283
-        if ((r.flag & RSQ_F_PAIRED) && !(r.flag & RSQ_F_MUNMAP)) {                                 // :284-292
-            const bool chim = (r.aux & RSQ_AUX_MATE_OTHER_CONTIG) || std::abs(r.pos - r.mpos) > opt_.chimeric_distance ||
-                              (opt_.legacy && tid > 127);
-            if (chim && opt_.exclude_chimeric) break;
-        }
-        if (r.filter_mask) break;                                                                  // :319-328
-        if (!tid_ok) {                                                                             // :333-337
-            if (opt_.verbosity) std::cerr << "Unrecognized RefID on alignment #" << alignment_count_ << std::endl;
-            break;
-        }
-        reaches_metrics = true;
-    } while (false);
-    if (reaches_metrics) {
+    }
+    if ((g & 4) && opt_.verbosity) std::cerr << "Unrecognized RefID on alignment #" << alignment_count_ << std::endl;
+    if (g & 2) {
         if ((size_t)chr >= dropped_.size()) dropped_.resize(chr + 1, 0);
         if (chr != current_chrom_) {                                                               // :346-353
             if (current_chrom_ >= 0) {
@@ -151,6 +171,49 @@ inline void Decoder::observe(rsq_read& r, int32_t tid) {
         last_metrics_chrom_ = chr;
         if (dropped_[chr]) r.aux |= RSQ_AUX_CONTIG_DROPPED;
     }
+}
+
+// Order-independent digest of a run of consecutive records (pure; the ingest workers compute it per job).
+inline RunSummary Decoder::summarise(const rsq_read* r, const int32_t* tids, size_t n) const {
+    RunSummary s;
+    s.n = n;
+    const int n_refs = (int)tid_to_contig_.size();
+    for (size_t k = 0; k < n; ++k) {
+        const int32_t tid = tids[k];
+        const bool tid_ok = tid >= 0 && tid < n_refs;
+        const unsigned g = gates(r[k], tid, tid_ok);
+        if (g & 1) {
+            if (!s.any_read_length_line) { s.any_read_length_line = true; s.l_qseq = r[k].l_qseq; }
+            else if (r[k].l_qseq != s.l_qseq) s.l_qseq_uniform = false;
+        }
+        if (g & 4) s.bad_tid = true;
+        if (g & 2) {
+            const int chr = tid_to_contig_[tid];
+            if (!s.n_reaching) { s.chr = chr; s.first_pos = r[k].pos; }
+            else { if (chr != s.chr) s.single_chr = false; if (r[k].pos < s.last_pos) s.sorted = false; }
+            s.last_pos = r[k].pos;
+            ++s.n_reaching;
+        }
+    }
+    return s;
+}
+
+// observe() for every record of the run at once, when the digest proves that none of them changes the order-dependent state
+// except the position of the last one (and none gets an aux bit): same contig as the stream is on, not a dropped one, positions
+// non-decreasing from the last seen, read length already settled at the run's only l_qseq.  false = nothing done, observe() each.
+inline bool Decoder::observe_run(const RunSummary& s) {
+    if (s.any_read_length_line && !(s.l_qseq_uniform && read_length_ != 0 && s.l_qseq == read_length_)) return false;
+    if (s.bad_tid && opt_.verbosity) return false;
+    if (s.n_reaching) {
+        if (!s.single_chr || (int64_t)s.chr != current_chrom_) return false;
+        if ((size_t)s.chr < dropped_.size() && dropped_[s.chr]) return false;
+        if (!warned_unsorted_ && !(s.sorted && last_position_ <= s.first_pos)) return false;
+        if ((size_t)s.chr >= dropped_.size()) dropped_.resize(s.chr + 1, 0);
+        last_position_ = s.last_pos;
+        last_metrics_chrom_ = s.chr;
+    }
+    alignment_count_ += s.n;
+    return true;
 }
 
 }  // namespace rsqh

@@ -35,7 +35,7 @@ constexpr size_t kHeadroom = 256u << 10;        // room in front of a job's outp
 using clk = std::chrono::steady_clock;
 inline double since(clk::time_point t) { return std::chrono::duration<double>(clk::now() - t).count(); }
 
-std::atomic<unsigned long long> g_last_hits{0}, g_last_misses{0};
+std::atomic<unsigned long long> g_last_hits{0}, g_last_misses{0}, g_last_summarised{0};
 
 enum { ST_READ = 0, ST_INFLATING, ST_INFLATED, ST_FRAMING, ST_FRAMED, ST_CONVERTING, ST_CONVERTED };
 
@@ -121,6 +121,8 @@ struct ParallelBamDecoder::Job {
     size_t chain_end = 0;              // first byte after the last whole record of the chain
     bool spec_ok = false;
     size_t first_read = 0;             // the consumer starts at reads[first_read]
+    RunSummary summary;                // Decoder::summarise over reads[0..): lets the consumer skip the per-record observe()
+    bool has_summary = false;
     // the record carried over from the previous job, converted by the framer (speculation hit only)
     bool has_head = false;
     rsq_read head_read;
@@ -170,6 +172,7 @@ ParallelBamDecoder::ParallelBamDecoder(const std::string& path, int n_threads)
     }
     max_jobs_in_flight_ = (size_t)n_threads_ * 3 + 4;
     speculate_ = !std::getenv("RSQ_INGEST_NO_SPECULATION");
+    summarise_ = !std::getenv("RSQ_INGEST_NO_SUMMARY");
 }
 
 ParallelBamDecoder::~ParallelBamDecoder() {
@@ -184,15 +187,16 @@ ParallelBamDecoder::~ParallelBamDecoder() {
     for (auto& t : workers_) if (t.joinable()) t.join();
     jobs_.clear();
     if (fp_) std::fclose(fp_);
-    g_last_hits = n_chain_hits_; g_last_misses = n_chain_misses_;
+    g_last_hits = n_chain_hits_; g_last_misses = n_chain_misses_; g_last_summarised = n_runs_summarised_;
     if (std::getenv("RSQ_INGEST_STATS"))
-        std::fprintf(stderr, "ingest busy seconds: reader %.3f, frame %.3f, inflate %.3f + convert %.3f over %d workers, consumer %.3f (+ %.3f waiting); jobs framed on the speculated chain %llu, by the sequential hop %llu\n",
+        std::fprintf(stderr, "ingest busy seconds: reader %.3f, frame %.3f, inflate %.3f + convert %.3f over %d workers, consumer %.3f (+ %.3f waiting); jobs framed on the speculated chain %llu, by the sequential hop %llu; jobs observed through their digest %llu\n",
                      t_reader_, t_frame_, t_inflate_, t_convert_, n_threads_, t_consumer_, t_consumer_wait_,
-                     (unsigned long long)n_chain_hits_, (unsigned long long)n_chain_misses_);
+                     (unsigned long long)n_chain_hits_, (unsigned long long)n_chain_misses_, (unsigned long long)n_runs_summarised_);
 }
 
 unsigned long long ParallelBamDecoder::last_chain_hits() { return g_last_hits; }
 unsigned long long ParallelBamDecoder::last_chain_misses() { return g_last_misses; }
+unsigned long long ParallelBamDecoder::last_runs_summarised() { return g_last_summarised; }
 
 void ParallelBamDecoder::reader_loop() {
     try {
@@ -207,7 +211,7 @@ void ParallelBamDecoder::reader_loop() {
             job->comp.clear(); job->c_off.clear(); job->c_len.clear(); job->u_len.clear();
             job->reads.clear(); job->rblocks.clear(); job->tids.clear(); job->big.clear();
             job->use_big = false; job->error.clear(); job->error_code = 0; job->state = ST_READ;
-            job->chain.clear(); job->chain_end = 0; job->spec_ok = false; job->first_read = 0; job->has_head = false; job->head_blocks.clear();
+            job->chain.clear(); job->chain_end = 0; job->spec_ok = false; job->first_read = 0; job->has_head = false; job->head_blocks.clear(); job->has_summary = false;
             size_t total = 0;
             const auto t_job = clk::now();
             while (total < kJobUncompressed) {
@@ -269,7 +273,10 @@ void ParallelBamDecoder::speculate(Job& j) const {
                 p += 4 + (size_t)bs;
             }
         } catch (...) { v = 0; }
-        if (v == 2) { j.chain_end = p; j.spec_ok = true; }
+        if (v == 2) {
+            j.chain_end = p; j.spec_ok = true;
+            if (summarise_) { j.summary = dec_for_params_->summarise(j.reads.data(), j.tids.data(), j.reads.size()); j.has_summary = true; }
+        }
         else { j.chain.clear(); j.reads.clear(); j.rblocks.clear(); j.tids.clear(); }
         return;                                  // one guess per job: a second would cost a second conversion
     }
@@ -347,7 +354,7 @@ void ParallelBamDecoder::worker_loop() {
                 if (todo->spec_ok && !skip_bytes_ && frame_on_chain(*todo, begin, end)) {
                     framed_by_chain = true;
                 } else {
-                todo->reads.clear(); todo->rblocks.clear(); todo->tids.clear(); todo->first_read = 0; todo->has_head = false;
+                todo->reads.clear(); todo->rblocks.clear(); todo->tids.clear(); todo->first_read = 0; todo->has_head = false; todo->has_summary = false;
                 if (!carry_.empty()) {
                     if (carry_.size() <= begin) { begin -= carry_.size(); memcpy(base + begin, carry_.data(), carry_.size()); }
                     else {
@@ -381,6 +388,7 @@ void ParallelBamDecoder::worker_loop() {
                     todo->tids.push_back(tid);
                     p += 4 + (size_t)bs;
                 }
+                if (summarise_) { todo->summary = dec_for_params_->summarise(todo->reads.data(), todo->tids.data(), todo->reads.size()); todo->has_summary = true; }
             }
         } catch (HostError& e) {
             todo->error = e.what(); todo->error_code = e.exit_code ? e.exit_code : -1;
@@ -458,9 +466,15 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
             blocks.insert(blocks.end(), job->rblocks.data() + b_lo, job->rblocks.data() + b_hi);
             const int32_t* tids = job->tids.data() + cur_read_;
             rsq_read* out = reads.data() + at;
-            for (size_t k = 0; k < n; ++k) {
-                out[k].block_off += delta;
-                dec.observe(out[k], tids[k]);
+            // a whole job whose digest shows that no record moves the order-dependent state (but for the last position): O(1)
+            if (job->has_summary && cur_read_ == 0 && n == job->reads.size() && dec.observe_run(job->summary)) {
+                ++n_runs_summarised_;
+                for (size_t k = 0; k < n; ++k) out[k].block_off += delta;
+            } else {
+                for (size_t k = 0; k < n; ++k) {
+                    out[k].block_off += delta;
+                    dec.observe(out[k], tids[k]);
+                }
             }
         }
         t_consumer_ += since(t_copy);

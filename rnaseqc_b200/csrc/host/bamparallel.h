@@ -32,6 +32,7 @@ public:
     // framing statistics of the decoder destroyed last (tests, diagnostics)
     static unsigned long long last_chain_hits();
     static unsigned long long last_chain_misses();
+    static unsigned long long last_runs_summarised();          // jobs whose records went through Decoder::observe_run
 
 private:
     struct Job;                        // one ~4 MB piece of the decompressed stream (bamparallel.cpp)
@@ -65,7 +66,8 @@ private:
     // busy seconds per stage, printed by the destructor when RSQ_INGEST_STATS is set (reader and consumer: one thread each;
     // frame: one worker at a time; inflate and convert: summed over the workers)
     bool speculate_ = true;            // RSQ_INGEST_NO_SPECULATION=1: the sequential hop for every job (A/B, tests)
-    uint64_t n_chain_hits_ = 0, n_chain_misses_ = 0;
+    bool summarise_ = true;            // RSQ_INGEST_NO_SUMMARY=1: Decoder::observe per record on the consumer thread (A/B, tests)
+    uint64_t n_chain_hits_ = 0, n_chain_misses_ = 0, n_runs_summarised_ = 0;
     double t_reader_ = 0, t_frame_ = 0, t_inflate_ = 0, t_convert_ = 0, t_consumer_ = 0, t_consumer_wait_ = 0;
 };
 

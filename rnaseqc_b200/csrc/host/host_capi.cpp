@@ -165,6 +165,7 @@ int rsqh_pack_records(const rsq_read* reads, size_t n_reads, const rsq_block* bl
 // worker threads for BAM decode in rsqh_decode_file (0 = sequential reader)
 void rsqh_set_decode_threads(int n) { g_decode_threads = n; }
 // jobs of the last finished multi-threaded BAM decode that were framed on the speculated record chain / by the sequential hop
+unsigned long long rsqh_last_ingest_runs_summarised(void) { return rsqh::ParallelBamDecoder::last_runs_summarised(); }
 void rsqh_last_ingest_framing(unsigned long long* on_chain, unsigned long long* by_hop) {
     *on_chain = rsqh::ParallelBamDecoder::last_chain_hits();
     *by_hop = rsqh::ParallelBamDecoder::last_chain_misses();

@@ -33,6 +33,7 @@ int main(int argc, char** argv) {
         ParallelBamDecoder pb(argv[1], threads);
         Decoder dec(pb.header(), contigs, contigs.names.size(), opt);
         std::vector<rsq_read> R; std::vector<rsq_block> B;
+        R.resize(1u << 20); B.resize(3u << 20); R.clear(); B.clear();     // like the CLI's batch buffers after their first batch: mapped
         auto t0 = clk::now();
         size_t n = 0;
         std::vector<rsq_read_packed> P(1u << 20);

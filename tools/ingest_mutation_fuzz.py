@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Byte-mutation fuzz of the multi-threaded BAM ingest (csrc/host/bamparallel.cpp): every mutant of a several-job BAM must give the
-same exit code and the same report files whether its jobs are framed on the speculated record chain (default) or by the sequential
-hop (RSQ_INGEST_NO_SPECULATION=1), and, when the file is still readable, as the sequential reader (--decode-threads 0).
+same exit code and the same report files whether its jobs are framed on the speculated record chain and observed through their
+digests (default) or framed by the sequential hop and observed record by record (RSQ_INGEST_NO_SPECULATION=1
+RSQ_INGEST_NO_SUMMARY=1), and, when the file is still readable, as the sequential reader (--decode-threads 0).
 CPU only (oracle-backed CLI, test infrastructure).   python tools/ingest_mutation_fuzz.py [--mutants 150] [--seed 1]"""
 import argparse, filecmp, os, random, shutil, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -33,7 +34,8 @@ def main():
     sr = synth.simulate_reads(sa, a.records, seed=8, dup_frac=0.0)
     rng = random.Random(a.seed)
     env_on = dict(os.environ); env_on.pop("RSQ_INGEST_NO_SPECULATION", None)
-    env_off = dict(env_on, RSQ_INGEST_NO_SPECULATION="1")
+    env_on.pop("RSQ_INGEST_NO_SUMMARY", None)
+    env_off = dict(env_on, RSQ_INGEST_NO_SPECULATION="1", RSQ_INGEST_NO_SUMMARY="1")
     bad = 0
     codes = {}
     for level in (0, 6):                       # stored blocks: mutations land in record bytes; deflated: mostly in the framing
