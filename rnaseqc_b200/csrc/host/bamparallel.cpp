@@ -68,17 +68,26 @@ bool read_bgzf_block(FILE* fp, std::vector<uint8_t>& dst, uint32_t& payload_off,
     return true;
 }
 
+// One raw-deflate stream per thread, reset between blocks (inflateInit2 allocates and clears ~40 KB of state each time).
+struct ThreadInflater {
+    z_stream zs;
+    bool ready = false;
+    ~ThreadInflater() { if (ready) inflateEnd(&zs); }
+};
+
 void inflate_block(const uint8_t* src, size_t n, uint8_t* dst, size_t isize) {
     if (!isize) return;
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) throw HostError(-1, "zlib init failed");
-    zs.next_in = const_cast<uint8_t*>(src);
-    zs.avail_in = (uInt)n;
-    zs.next_out = dst;
-    zs.avail_out = (uInt)isize;
-    const int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
+    thread_local ThreadInflater ti;
+    if (!ti.ready) {
+        memset(&ti.zs, 0, sizeof(ti.zs));
+        if (inflateInit2(&ti.zs, -15) != Z_OK) throw HostError(-1, "zlib init failed");
+        ti.ready = true;
+    } else if (inflateReset(&ti.zs) != Z_OK) throw HostError(-1, "zlib init failed");
+    ti.zs.next_in = const_cast<uint8_t*>(src);
+    ti.zs.avail_in = (uInt)n;
+    ti.zs.next_out = dst;
+    ti.zs.avail_out = (uInt)isize;
+    const int rc = inflate(&ti.zs, Z_FINISH);
     if (rc != Z_STREAM_END) throw HostError(-1, "BGZF inflate failed");
 }
 
