@@ -317,12 +317,12 @@ def run_ours(args):
         except Exception as ex:  # pinned allocation can fail on a small host
             e2e = {"value": None, "unit": "reads/s", "error": repr(ex)}
 
-    # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0 only ---------------------------------------
+    # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only ---------------------------------------
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:     # N=1 only: the other ranks of a multi-GPU run would wait ~10 s for it
         oracle_lib = os.path.join(ROOT, "oracle", "_build", "librsq_oracle.so")
         if os.path.exists(oracle_lib):
-            n_s = min(n_reads, args.cpu_sample)
+            n_s = min(n_reads, args.port_sample)
             sr = np.frombuffer(rb[:n_s].cpu().numpy().reshape(-1).data, dtype=api.READ_DTYPE).copy()
             nb_s = int(sr["block_off"][-1]) + int(sr["n_blocks"][-1])
             sb = bb[:nb_s].cpu().numpy().copy()
@@ -451,7 +451,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gencode200m", choices=sorted(WORKLOADS))
     ap.add_argument("--records", type=int, default=0, help="override the record count per GPU (smoke runs)")
-    ap.add_argument("--cpu-sample", type=int, default=3_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=3_000_000,
+                    help="records per step of `--impl reference` (the reference binary does ~0.2-0.4 M records/s: ~10 s)")
+    ap.add_argument("--port-sample", type=int, default=30_000_000,
+                    help="records of the cpu_baseline leg (the oracle port does ~3 M records/s on one core: ~10 s)")
     ap.add_argument("--e2e-chunk", type=int, default=8_000_000)
     ap.add_argument("--bed", action="store_true", help="also run the --bed fragment-size sampler (BASELINE.json configs[4])")
     ap.add_argument("--no-e2e", action="store_true")
