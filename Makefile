@@ -56,6 +56,11 @@ $(ODIR)/libhostcore_sd.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot
 $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
 	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'
 
+# host-side measurement tool: BAM ingest records/s by thread count (RSQ_INGEST_STATS=1 prints the busy time of every stage)
+tools: $(OBJDIR)/decode_bench
+$(OBJDIR)/decode_bench: tools/decode_bench.cpp $(HOST_OBJS)
+	$(CXX) $(CXXFLAGS) -o $@ tools/decode_bench.cpp $(filter-out $(OBJDIR)/host/report.o $(OBJDIR)/host/pipeline.o,$(HOST_OBJS)) -lz -lpthread
+
 clean:
 	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) $(ODIR)
-.PHONY: all oracle ref clean
+.PHONY: all oracle ref tools clean
