@@ -1,15 +1,22 @@
 #!/usr/bin/env python
 """bench.py — reads/s of the RNA-SeQC per-read hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --gpus 1 --steps K --warmup W                   # this repo's CUDA path
     python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference's own CPU implementation
-    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, coordinate-partitioned records
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # one rank per GPU, coordinate-partitioned records
+         [--scaling strong]   BASELINE.json configs[3]: the 200 M records of the workload split over the N GPUs
+         [--bed]              BASELINE.json configs[4]: fragment-size sampler + per-base coverage on top
 
 A "step" is one whole pass of the hot path over the synthetic records of the workload: accumulator reset, the fused
-filter/intersect/accumulate kernel over every record, integration of the coverage difference array, and the read-back
-of the count vectors (after the NCCL all-reduce when N > 1).  `value` = records processed by all ranks / step time with
-the records already resident in HBM; `e2e` = the same through rsq_submit with pinned HOST buffers (H2D inside the timed
-region).  One JSON line on stdout (rank 0).
+filter/intersect/accumulate kernel over every record, the end-of-run exchange over NCCL when N > 1 (inside the library:
+rsq_exchange — count vectors, ordered first-N fragment-size cut), integration of the coverage difference array, the per-gene
+coverage / 3' bias statistics of the genes the rank owns (gathered over NCCL), and the read-back of every result table.
+`value` = records processed by all ranks / step time with the records already resident in HBM; `e2e` = the same through
+rsq_submit_packed with pinned HOST buffers (H2D inside the timed region).  One JSON line on stdout (rank 0).
+
+At N > 1 a PRE-FLIGHT runs first: one 2 M-record sorted stream is split at gene-free cuts, every rank runs its slice, the
+exchange runs, and every rank's results must equal bit for bit the single-GPU run of the whole stream on rank 0 and the CPU
+oracle's (counters, gene and exon tables, fragment-size histogram, coverage statistics).  A failed pre-flight aborts the run.
 """
 from __future__ import annotations
 
@@ -35,6 +42,8 @@ WORKLOADS = {
     "chr1_10m": dict(n_genes=5234, full_genome=False, records=10_000_000,
                      label="synthetic 10M 150bp PE records, chr1-only collapsed GTF (5234 genes)"),
 }
+METRIC = "reads/sec (150bp PE, GENCODE-scale GTF)"
+SEED = 20260925
 
 
 # stdout carries exactly ONE JSON line: anything a library prints to fd 1 (NCCL's version banner, for one) is sent to stderr
@@ -51,12 +60,16 @@ def emit(obj):
     _JSON_OUT.flush()
 
 
+def make_synth_annotation(wl):
+    from rnaseqc_b200 import synth
+    if wl["full_genome"]:
+        return synth.make_annotation(seed=SEED, n_genes=wl["n_genes"], contig_names=synth.GRCH38_NAMES, contig_lens=synth.GRCH38)
+    return synth.make_annotation(seed=SEED, n_genes=wl["n_genes"])
+
+
 def build_annotation(wl, tmpdir, with_bed=False):
     from rnaseqc_b200 import api, synth
-    if wl["full_genome"]:
-        sa = synth.make_annotation(seed=20260925, n_genes=wl["n_genes"], contig_names=synth.GRCH38_NAMES, contig_lens=synth.GRCH38)
-    else:
-        sa = synth.make_annotation(seed=20260925, n_genes=wl["n_genes"])
+    sa = make_synth_annotation(wl)
     gtf = os.path.join(tmpdir, "bench.gtf")
     synth.write_gtf(sa, gtf)
     bed = None
@@ -68,7 +81,9 @@ def build_annotation(wl, tmpdir, with_bed=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (B200_PROFILING.md).  Started BEFORE the warm-up
+    steps (nvidia-smi needs about a second to deliver its first row) and read after the timed region: warm-up and timed steps
+    are one uninterrupted stretch of the same work."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -77,7 +92,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -86,18 +101,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def n_rows(self):
+        return len(self.rows)
+
+    def stop(self, since=0.0):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < since:
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
@@ -106,7 +126,7 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": "warm-up + timed steps (continuous load)"}
 
 
 def measured_peak():
@@ -116,12 +136,44 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def generate_on_device(sa, ann, n_records, device, rank, world, seed=20260925):
-    """Coordinate-sorted packed records on `device`.  With world > 1 every rank draws its own n_records from its own
-    coordinate slice of the genome (slices cut at gene-free positions): weak scaling."""
+def bind_to_gpu_cores(local_rank, world):
+    """Pins this rank to the host cores NVML reports as local to its GPU — BEFORE any pinned buffer is allocated, so that
+    first-touch places the staging memory on the GPU's NUMA node.  When every GPU reports the same core set (a VM with one
+    NUMA node), the set is split evenly among the ranks so that the copy threads do not share cores.  Returns a description."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < n_cpu]
+        info["gpu_local_cores"] = f"{cores[0]}-{cores[-1]}" if cores else ""
+        try:
+            info["numa_node"] = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            info["numa_node"] = None
+        allowed = sorted(os.sched_getaffinity(0))
+        cores = [c for c in cores if c in allowed] or allowed
+        if world > 1:
+            same = True
+            for r in range(world):
+                w2 = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), (n_cpu + 63) // 64)
+                same = same and list(w2) == list(words)
+            if same and len(cores) >= world:       # one shared core set: give every rank its own slice of it
+                per = len(cores) // world
+                cores = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, cores)
+        info.update(bound=True, cores=f"{cores[0]}-{cores[-1]}", n_cores=len(cores))
+    except Exception as ex:
+        info["error"] = repr(ex)[:200]
+    return info
+
+
+def generate_on_device(sa, ann, n_records, device, region, rank, seed=SEED):
+    """Coordinate-sorted packed records on `device`, drawn from `region` of the genome (None = all of it)."""
     import torch
-    from rnaseqc_b200 import shard, synth
-    region = shard.rank_region(sa, rank, world) if world > 1 else None
+    from rnaseqc_b200 import synth
     chunk = 20_000_000
     parts = []
     done = 0
@@ -143,71 +195,173 @@ def generate_on_device(sa, ann, n_records, device, rank, world, seed=20260925):
     return rb, bb
 
 
+RESULT_FIELDS = ("counters", "gene_reads", "gene_unique", "gene_fragments", "exon_whole", "exon_frac", "fragment_hist", "gc_hist")
+STAT_FIELDS = ("gene_mean", "gene_std", "gene_cv", "five_end", "three_end", "exon_cv")
+DIAG_COUNTER = 53      # RSQ_C_FRAGMENT_CANDIDATES: a diagnostic, counted only while the sample quota lasts (tests/util.py)
+
+
+def snapshot(res, cs):
+    out = {k: np.array(getattr(res, k), copy=True) for k in RESULT_FIELDS}
+    out["counters"][DIAG_COUNTER] = 0
+    out["taken"] = np.array([res.fragment_samples_taken], np.uint64)
+    for k in STAT_FIELDS:
+        out[k] = np.array(cs[k], copy=True).view(np.uint64)      # bit patterns: NaN == NaN
+    return out
+
+
+def preflight(be, ann, sa, device_index, rank, world, with_bed, n_records=2_000_000, quota=20000, log_fn=log):
+    """N>1 parity on the hardware the bench runs on (see the module docstring).  Returns a summary dict (rank 0) or raises."""
+    import torch
+    import torch.distributed as dist
+    from rnaseqc_b200 import api, shard, synth
+    device = f"cuda:{device_index}"
+    sr = synth.simulate_reads(sa, n_records, seed=SEED + 77, device=device)           # the same stream on every rank
+    contig, pos = sr.contig.cpu().numpy(), sr.pos.cpu().numpy()
+    ranges, cuts = shard.split_sorted_records(sa, contig, pos, world, return_cuts=True)
+    shard.assert_cuts_legal(ann, sa, cuts)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    lo, hi = ranges[rank]
+    r = reads[lo:hi].copy()
+    b0 = int(r["block_off"][0]) if len(r) else 0
+    b1 = int(r["block_off"][-1]) + int(r["n_blocks"][-1]) if len(r) else 0
+    r["block_off"] -= np.uint32(b0)
+    fs = quota if with_bed else 0
+    ctx = be.create(api.make_config(device=device_index, max_records=max(len(r), 1024), fragment_samples=fs))
+    ctx.set_annotation(ann)
+    ids = [be.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(ids[0], rank, world)
+    ctx.submit(r, blocks[b0:b1].copy())
+    ctx.exchange()
+    res = ctx.finalize(want_coverage=False)
+    cs = ctx.coverage_statistics(ann, owned=shard.owned_gene_lines(ann, sa, cuts, rank))
+    mine = snapshot(res, cs)
+    ctx.close()
+    want = [None]
+    summary = None
+    if rank == 0:
+        one = be.create(api.make_config(device=device_index, max_records=len(reads), fragment_samples=fs))
+        one.set_annotation(ann)
+        one.submit(reads, blocks)
+        ref = one.finalize(want_coverage=False)
+        want[0] = snapshot(ref, one.coverage_statistics(ann))
+        one.close()
+        summary = {"records": int(len(reads)), "partition_sizes": [int(b - a) for a, b in ranges], "fragment_sample_quota": fs,
+                   "fragment_samples_taken": int(want[0]["taken"][0]), "gene_reads_sum": int(want[0]["gene_reads"].sum()),
+                   "compared": list(RESULT_FIELDS) + ["fragment_samples_taken"] + list(STAT_FIELDS), "vs_single_gpu": "bit-identical on every rank"}
+        oracle_lib = os.path.join(ROOT, "oracle", "_build", "librsq_oracle.so")
+        if os.path.exists(oracle_lib):            # the checker (test infrastructure), never the thing measured
+            octx = api.Backend(oracle_lib).create(api.make_config(fragment_samples=fs))
+            octx.set_annotation(ann)
+            octx.submit(reads, blocks)
+            ores = octx.finalize(want_coverage=False)
+            osnap = snapshot(ores, octx.coverage_statistics(ann))
+            octx.close()
+            for k in list(RESULT_FIELDS) + ["taken"]:
+                assert np.array_equal(osnap[k], want[0][k]), f"pre-flight: single-GPU run differs from the CPU oracle in {k}"
+            for k in STAT_FIELDS:      # block-reduced fp64 on the device vs sequential fp64: 1e-9 (tests/test_gpu_parity.py), u64 ends exact
+                a, b = osnap[k].view(np.float64 if k not in ("five_end", "three_end") else np.uint64), want[0][k].view(np.float64 if k not in ("five_end", "three_end") else np.uint64)
+                if k in ("five_end", "three_end"):
+                    assert np.array_equal(a, b), f"pre-flight: {k} differs from the CPU oracle"
+                else:
+                    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=1e-9, atol=0), f"pre-flight: {k} differs from the CPU oracle"
+            summary["vs_cpu_oracle"] = "integers bit-identical, coverage statistics within 1e-9"
+    dist.broadcast_object_list(want, src=0)
+    bad = [k for k in want[0] if not np.array_equal(want[0][k], mine[k])]
+    flags = [None] * world
+    dist.all_gather_object(flags, bad)
+    if any(flags):
+        raise SystemExit(f"pre-flight FAILED: sharded != single-GPU run: {flags}")
+    if rank == 0:
+        log_fn(f"[pre-flight] {world} partitions of {len(reads)} records == single-GPU run == oracle: {summary}")
+    return summary
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from rnaseqc_b200 import api
+    from rnaseqc_b200 import api, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    binding = bind_to_gpu_cores(local_rank, world) if not args.no_bind else {"bound": False}
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     wl = WORKLOADS[args.workload]
-    n_records = args.records or wl["records"]
+    total_target = args.records or wl["records"]
+    strong = args.scaling == "strong" and world > 1
+    n_records = (total_target + world - 1) // world if strong else total_target
     tmpdir = tempfile.mkdtemp(prefix="rsq_bench_")
     t0 = time.time()
     sa, ann, gtf = build_annotation(wl, tmpdir, with_bed=args.bed)
-    log(f"[rank {rank}] annotation: {ann.n_genes} genes, {ann.n_exons} exons, {ann.cov_len} exon bases ({time.time() - t0:.1f}s)")
-    rb, bb = generate_on_device(sa, ann, n_records, device, rank, world)
+    log(f"[rank {rank}] annotation: {ann.n_genes} genes, {ann.n_exons} exons, {ann.cov_len} exon bases ({time.time() - t0:.1f}s); cpu binding {binding}")
+    be = api.default_backend()
+
+    pre = None
+    if world > 1 and not args.no_preflight:
+        pre = preflight(be, ann, sa, local_rank, rank, world, with_bed=True)
+
+    # this rank's coordinate slice of the genome (cut where no gene lies): it draws its records there and owns those genes
+    region, owned = None, None
+    if world > 1:
+        regions = [shard.rank_region(sa, r, world) for r in range(world)]
+        region = regions[rank]
+        cut_lins = [rg["lin_lo"] for rg in regions[1:]]
+        shard.assert_cuts_legal(ann, sa, cut_lins)
+        owned = shard.owned_gene_lines(ann, sa, cut_lins, rank)
+    rb, bb = generate_on_device(sa, ann, n_records, device, region, rank)
     n_reads, n_blocks = rb.shape[0], bb.shape[0]
     torch.cuda.synchronize()
     log(f"[rank {rank}] records: {n_reads} reads, {n_blocks} blocks resident in HBM ({time.time() - t0:.1f}s)")
 
-    be = api.default_backend()
     stream = torch.cuda.Stream()          # the library runs on this stream, so torch's CUDA events bracket its kernels
     torch.cuda.set_stream(stream)
     ctx = be.create(api.make_config(device=local_rank, max_records=n_reads, user_stream=stream.cuda_stream,
                                     fragment_samples=1000000 if args.bed else 0,
                                     collect_coverage=os.environ.get("RSQ_BENCH_COVERAGE", "1") != "0"))   # env: ablation runs only
     ctx.set_annotation(ann)
+    if world > 1:
+        ids = [be.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)            # NCCL communicator inside the library (rsq_exchange / rsq_coverage_statistics)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allreduce_counts():
-        ptr, n_words = ctx.export_counts()
-        if world > 1:
-            # alias the library's export buffer as a torch tensor (no copy) and sum it over NVLink
-            t = _alias_int64(ptr, n_words, local_rank)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            torch.cuda.current_stream().synchronize()
-        ctx.import_counts()
-
     hist_len = (1 << 16) if args.bed else 8      # the fragment-size histogram is only filled by the --bed sampler
+
+    def finish():
+        if world > 1:
+            ctx.exchange()                                                     # collective, on the ctx stream, no host round trip
+        res = ctx.finalize(want_coverage=False, hist_len=hist_len, pinned=True)   # result tables into page-locked host buffers
+        res.cov_stats = ctx.coverage_statistics(ann, pinned=True, owned=owned)    # own genes only; gathered over NCCL when N > 1
+        return res
 
     def step_resident():
         ctx.reset()
         ctx.submit_device(rb.data_ptr(), n_reads, bb.data_ptr(), n_blocks)
-        if world > 1:
-            allreduce_counts()
-        res = ctx.finalize(want_coverage=False, hist_len=hist_len, pinned=True)      # result tables into page-locked host buffers
-        res.cov_stats = ctx.coverage_statistics(ann, pinned=True)   # coverage integration + per-gene statistics kernel + 5 MB read-back
-        return res
+        return finish()
 
     # ---------------- device-resident timing -----------------------------------------------------------------------
-    for _ in range(args.warmup):
-        res = step_resident()
-    algo_bytes = ctx.algorithmic_bytes()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_load = time.perf_counter()
+    res = None
+    k = 0
+    while k < args.warmup or (time.perf_counter() - t_load < args.min_warmup_s and k < 1000):
+        res = step_resident()
+        k += 1
+    warm_done = k
+    algo_bytes = ctx.algorithmic_bytes()
+    barrier()
     l0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -218,23 +372,26 @@ def run_ours(args):
     ev1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
+    clocks = sampler.stop(since=t_load + 0.2)
     ms_dev = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - l0
-    ref_counters, ref_gene_reads = res.counters.copy(), res.gene_reads.copy()   # the pinned result buffers are reused by the next finalize
+    ref_snap = snapshot(res, res.cov_stats)       # the pinned result buffers are reused by the next finalize
     # the dominant kernel's own time (CUDA events recorded by the library around the hot-path launches of one step)
     ctx.reset(); ctx.submit_device(rb.data_ptr(), n_reads, bb.data_ptr(), n_blocks); ctx.sync()
     hot_ms = ctx.kernel_time_ms()
-    ms_step = max(ms_dev, t_wall * 1e3) / args.steps
+    finish()
+    ms_step_local = max(ms_dev, t_wall * 1e3) / args.steps
+    ms_step = ms_step_local
     if world > 1:
         t = torch.tensor([ms_step], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
-    total_records = n_reads * world if world == 1 else int(_allsum(n_reads, device))
+    total_records = n_reads if world == 1 else int(_allsum(n_reads, device))
     value = total_records / (ms_step * 1e-3)
 
     # ---------------- end to end from pinned host buffers ------------------------------------------------------------
     e2e = None
+    e2e_rank = {}
     if not args.no_e2e:
         try:
             h_reads = torch.empty(rb.shape, dtype=rb.dtype, pin_memory=True)
@@ -278,44 +435,59 @@ def run_ours(args):
                 else:
                     for a, b, lo, hi in zip(bounds[:-1], bounds[1:], block_lo[:-1], block_lo[1:]):
                         ctx.submit_ptr(h_reads.data_ptr() + 48 * a, b - a, h_blocks.data_ptr() + 8 * lo, hi - lo)
-                if world > 1:
-                    ctx.sync(); allreduce_counts()
-                res = ctx.finalize(want_coverage=False, hist_len=hist_len, pinned=True)
-                res.cov_stats = ctx.coverage_statistics(ann, pinned=True)
-                return res
+                return finish()
 
             def time_e2e(use_packed):
-                for _ in range(max(1, args.warmup - 1)):
+                for _ in range(max(1, min(args.warmup, 3) - 1)):
                     r = step_e2e(use_packed)
                 barrier()
                 t0 = time.perf_counter()
-                for _ in range(args.steps):
+                for _ in range(args.e2e_steps):
                     r = step_e2e(use_packed)
+                local = (time.perf_counter() - t0) / args.e2e_steps       # before the barrier: this rank's own time
                 barrier()
-                dt = (time.perf_counter() - t0) / args.steps
+                dt = (time.perf_counter() - t0) / args.e2e_steps
                 if world > 1:
                     t = torch.tensor([dt], device=device, dtype=torch.float64)
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                     dt = float(t.item())
-                assert np.array_equal(r.counters, ref_counters) and np.array_equal(r.gene_reads, ref_gene_reads), "e2e != resident"
-                return dt
+                got = snapshot(r, r.cov_stats)
+                bad = [k for k in ref_snap if not np.array_equal(ref_snap[k], got[k])]
+                assert not bad, f"e2e != resident in {bad}"
+                return dt, local
 
-            t_plain = time_e2e(False)
             d2h = 8 * (api.RSQ_N_COUNTERS + 3 * ann.n_genes + 2 * ann.n_exons) + 8 * (5 * len(res.cov_stats["gene_mean"]) + ann.n_exons)
-            e2e = {"value": total_records / t_plain, "unit": "reads/s", "h2d_bytes_per_step": int(48 * n_reads + 8 * n_blocks),
-                   "d2h_bytes_per_step": int(d2h), "ms_per_step": t_plain * 1e3, "wire_format": "rsq_read (48 B + 8 B per block)"}
             if packed:
-                t_packed = time_e2e(True)
+                t_packed, t_local = time_e2e(True)
                 n_wire_blocks = sum(p[3] for p in packed)
-                e2e = {"value": total_records / t_packed, "unit": "reads/s", "h2d_bytes_per_step": int(32 * n_reads + 8 * n_wire_blocks),
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": t_packed * 1e3,
+                h2d = int(32 * n_reads + 8 * n_wire_blocks)
+                e2e = {"value": total_records / t_packed, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": t_packed * 1e3, "steps": args.e2e_steps,
                        "wire_format": "rsq_read_packed (32 B + 8 B per block of the records that are not one whole-read run)",
-                       "unpacked": {"value": total_records / t_plain, "ms_per_step": t_plain * 1e3,
-                                    "h2d_bytes_per_step": int(48 * n_reads + 8 * n_blocks)}}
+                       "same_results_as_resident": True}
+                e2e_rank = {"e2e_ms": t_local * 1e3, "h2d_gb_per_s": h2d / t_local / 1e9}
+                if args.e2e_unpacked:
+                    t_plain, _ = time_e2e(False)
+                    e2e["unpacked"] = {"value": total_records / t_plain, "ms_per_step": t_plain * 1e3,
+                                       "h2d_bytes_per_step": int(48 * n_reads + 8 * n_blocks)}
                 del h_pk, h_pb
+            else:
+                t_plain, t_local = time_e2e(False)
+                h2d = int(48 * n_reads + 8 * n_blocks)
+                e2e = {"value": total_records / t_plain, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": t_plain * 1e3, "steps": args.e2e_steps,
+                       "wire_format": "rsq_read (48 B + 8 B per block)", "same_results_as_resident": True}
+                e2e_rank = {"e2e_ms": t_local * 1e3, "h2d_gb_per_s": h2d / t_local / 1e9}
             del h_reads, h_blocks
-        except Exception as ex:  # pinned allocation can fail on a small host
+        except MemoryError as ex:  # pinned allocation can fail on a small host
             e2e = {"value": None, "unit": "reads/s", "error": repr(ex)}
+
+    # ---------------- per-rank facts (every rank, gathered on rank 0) --------------------------------------------------------
+    mine = {"rank": rank, "records": int(n_reads), "hot_kernel_ms": hot_ms, "step_ms": ms_step_local, "cpu_binding": binding, **e2e_rank}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
 
     # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0 at N=1 only ---------------------------------------
     cpu_baseline = None
@@ -330,11 +502,19 @@ def run_ours(args):
             octx.set_annotation(ann)
             t_c = time.perf_counter()
             octx.submit(sr, sb)
-            ores = octx.finalize(want_coverage=False)
+            octx.finalize(want_coverage=False)
             t_c = time.perf_counter() - t_c
             cpu_baseline = {"value": n_s / t_c, "unit": "reads/s", "cores": 1, "kind": "port",
                             "sample": f"first {n_s} records of the same workload, oracle/rsq_oracle.cpp single thread"}
             octx.close()
+
+    # ---------------- BAM -> report files through the product CLI (ingest included), rank 0 at N=1 only --------------------------
+    e2e_cli = None
+    if rank == 0 and world == 1 and args.cli_records > 0:
+        try:
+            e2e_cli = run_cli_leg(sa, gtf, tmpdir, args.cli_records, device)
+        except Exception as ex:
+            e2e_cli = {"error": repr(ex)[:300]}
 
     peak, peak_src = measured_peak()
     traffic, traffic_src = None, None
@@ -342,29 +522,32 @@ def run_ours(args):
     if os.path.exists(tp):   # DRAM bytes per record of the hot kernel from the committed ncu --set full capture, scaled to this launch
         tj = json.load(open(tp))
         traffic, traffic_src = tj["dram_bytes_per_record"] * n_reads, tj["source"]
-    hot_ms_per_launch = hot_ms  # one step == one logical launch of the hot path (kSubBatch chunks are back to back)
-    achieved = algo_bytes / (hot_ms_per_launch * 1e-3) / 1e9 if hot_ms_per_launch > 0 else None
+    achieved = algo_bytes / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
     if rank == 0:
+        cs = res.cov_stats
         out = {
-            "metric": "reads/sec (150bp PE, GENCODE-scale GTF)", "value": value, "unit": "reads/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": wl["label"] if not args.records else f"{wl['label']} [records overridden: {n_records}]",
-                       "records_per_gpu": n_reads, "blocks_per_gpu": n_blocks, "genes": ann.n_genes, "exons": ann.n_exons,
-                       "exon_bases": ann.cov_len, "bed_fragment_sizes": bool(args.bed), "partitioning": "coordinate ranges cut at gene-free positions" if world > 1 else "none",
-                       "step": "reset + hot-path kernel + coverage integration + per-gene coverage/bias statistics kernel + count/statistics read-back" + (" + NCCL all-reduce" if world > 1 else ""),
+            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm_done, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": wl["label"] if not args.records else f"{wl['label']} [records overridden: {total_target}]",
+                       "records_total": int(total_records), "records_per_gpu": n_reads, "blocks_per_gpu": n_blocks, "genes": ann.n_genes, "exons": ann.n_exons,
+                       "exon_bases": ann.cov_len, "bed_fragment_sizes": bool(args.bed),
+                       "partitioning": ("coordinate ranges cut at gene-free positions; " + ("the workload's records split over the GPUs (BASELINE configs[3])" if strong else "every GPU draws the workload's record count from its own range")) if world > 1 else "none",
+                       "step": "reset + hot-path kernel" + (" + rsq_exchange (NCCL inside the library: count vectors, ordered first-N fragment-size cut)" if world > 1 else "") +
+                               " + coverage integration + per-gene coverage/bias statistics kernel" + (" of the rank's own genes + NCCL gather" if world > 1 else "") + " + count/statistics read-back",
                        "l2_policy": f"inputs ({(48 * n_reads + 8 * n_blocks) / 1e9:.1f} GB per GPU) larger than the 126 MB L2",
+                       "timed_seconds": ms_step * args.steps / 1e3,
                        "not_in_step": "text formatting of the report files and the medians over genes (host, once per sample)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
-                         "hot_kernel_ms_per_step": hot_ms_per_launch},
-            "cpu_baseline": cpu_baseline,
+                         "hot_kernel_ms_per_step": hot_ms, "kernel": "hot_path_kernel (rank 0; every rank's time is in per_rank)"},
+            "cpu_baseline": cpu_baseline, "e2e_cli": e2e_cli, "per_rank": per_rank, "preflight": pre,
             "sanity": {"mapped_reads": res.counter("Mapped Reads"), "exonic_reads": res.counter("Exonic Reads"),
                        "gene_reads_sum": int(res.gene_reads.sum()), "device_ms_events": ms_dev / args.steps,
-                       "genes_with_coverage_stats": int((res.cov_stats["gene_mean"] > 0).sum()),
+                       "genes_with_coverage_stats": int((cs["gene_mean"] > 0).sum()),
                        "fragment_samples_taken": int(res.fragment_samples_taken),
-                       "genes_in_3prime_bias": int(((res.cov_stats["five_end"] + res.cov_stats["three_end"]) > 0).sum())},
+                       "genes_in_3prime_bias": int(((cs["five_end"] + cs["three_end"]) > 0).sum())},
         }
         emit(out)
     ctx.close()
@@ -372,12 +555,43 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _alias_int64(ptr, n, device):
-    import torch
-
-    class _CAI:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-    return torch.as_tensor(_CAI(), device=f"cuda:{device}")
+def run_cli_leg(sa, gtf, tmpdir, n_records, device):
+    """The number a drop-in user sees: BAM file -> the nine report files through rnaseqc_b200/bin/rnaseqc (multi-threaded
+    BGZF/BAM ingest + CUDA path + report writers), wall clock of the whole process, against the reference binary on a bounded
+    sample of the same BAM's records."""
+    from rnaseqc_b200 import synth
+    cli = os.path.join(ROOT, "rnaseqc_b200", "bin", "rnaseqc")
+    if not os.path.exists(cli):
+        return {"error": "rnaseqc_b200/bin/rnaseqc is not built"}
+    sr = synth.simulate_reads(sa, n_records, seed=SEED + 5, device=device, dup_frac=0.0)
+    bam = os.path.join(tmpdir, "cli.bam")
+    t = time.perf_counter()
+    synth.write_bam(sa, sr, bam, level=1)
+    t_write = time.perf_counter() - t
+    out = {"records": int(sr.n), "bam_bytes": os.path.getsize(bam), "bam_write_seconds": t_write, "host_cores": os.cpu_count(), "flags": "--coverage"}
+    env = dict(os.environ, RSQ_INGEST_STATS="1")
+    best = None
+    for rep in range(2):
+        t = time.perf_counter()
+        p = subprocess.run([cli, gtf, bam, os.path.join(tmpdir, f"cli_out{rep}"), "--coverage", "-v"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        dt = time.perf_counter() - t
+        if p.returncode != 0:
+            return dict(out, error=f"exit {p.returncode}: {p.stderr[-300:]}")
+        if best is None or dt < best[0]:
+            best = (dt, p.stdout, p.stderr)
+    stages = {}
+    for line in best[1].splitlines():
+        for key, name in (("Finished processing GTF in", "gtf_parse_s"), ("Device context + annotation upload:", "device_setup_s"),
+                          ("Time Elapsed:", "bam_loop_s"), ("Finalize + coverage statistics:", "finalize_s"), ("Report files:", "report_s")):
+            if line.startswith(key):
+                try:
+                    stages[name] = float(line[len(key):].split()[0].rstrip(";"))
+                except ValueError:
+                    pass
+    out.update(seconds=best[0], records_per_s=sr.n / best[0], stages=stages,
+               bam_loop_records_per_s=(sr.n / stages["bam_loop_s"]) if stages.get("bam_loop_s") else None,
+               ingest_stats=[l for l in best[2].splitlines() if l.startswith("[ingest]")][-12:])
+    return out
 
 
 def _allsum(v, device):
@@ -390,35 +604,47 @@ def _allsum(v, device):
 
 def run_reference(args):
     """The reference's own CPU implementation of the path, timed on this box's host cores (single-threaded by
-    construction, src/BamReader.cpp:14-15), on a bounded sample of the same workload."""
+    construction, src/BamReader.cpp:14-15), on a bounded sample of the same workload.  Nothing of this repo's product is
+    loaded here: the GTF and the BAM are written by the synthetic generator (rnaseqc_b200.synth; the BAM through htslib-free
+    Python/zlib code), the timed part is a subprocess of oracle/_ref/rnaseqc."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from rnaseqc_b200 import api, synth
+    from rnaseqc_b200 import synth
     wl = WORKLOADS[args.workload]
     tmpdir = tempfile.mkdtemp(prefix="rsq_ref_")
-    sa, ann, gtf = build_annotation(wl, tmpdir)
+    sa = make_synth_annotation(wl)
+    gtf = os.path.join(tmpdir, "bench.gtf")
+    synth.write_gtf(sa, gtf)
+    flags = ["--coverage"]
+    if args.bed:
+        bed = os.path.join(tmpdir, "bench.bed")
+        synth.write_bed(sa, bed, min_len=1000)
+        flags += ["--bed", bed]
     n_s = args.cpu_sample
-    sr = synth.simulate_reads(sa, n_s, seed=20260925, device="cpu", dup_frac=0.0)   # no duplicates: keeps the 1e9-iteration
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "rnaseqc")                      # library-complexity scan (outside the path) out
+    sr = synth.simulate_reads(sa, n_s, seed=SEED, device="cpu", dup_frac=0.0)   # no duplicates: keeps the 1e9-iteration
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "rnaseqc")                  # library-complexity scan (outside the path) out
     times = []
     if os.path.exists(ref_bin):
         bam = os.path.join(tmpdir, "sample.bam")
-        synth.write_bam(sa, sr, bam)
-        kind, sample = "reference", f"{sr.n} records of the same workload as BAM, unmodified reference binary, 1 thread"
+        synth.write_bam_python(sa, sr, bam)
+        kind, sample = "reference", f"{sr.n} records of the same workload as BAM, unmodified reference binary ({' '.join(flags)}), 1 thread"
         for k in range(args.warmup + args.steps):
             t = time.perf_counter()
-            subprocess.run([ref_bin, gtf, bam, os.path.join(tmpdir, f"out{k}")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            subprocess.run([ref_bin, gtf, bam, os.path.join(tmpdir, f"out{k}")] + flags, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             times.append(time.perf_counter() - t)
         # GTF parse time is outside the path: measure it with an empty-ish BAM and subtract
         empty = synth.simulate_reads(sa, 2, seed=1, device="cpu")
         ebam = os.path.join(tmpdir, "empty.bam")
-        synth.write_bam(sa, empty, ebam)
+        synth.write_bam_python(sa, empty, ebam)
         t = time.perf_counter()
-        subprocess.run([ref_bin, gtf, ebam, os.path.join(tmpdir, "oute")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.run([ref_bin, gtf, ebam, os.path.join(tmpdir, "oute")] + flags, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         t_gtf = time.perf_counter() - t
     else:
+        # the reference did not build here: the oracle port stands in (the one other place bench.py may execute oracle/)
+        from rnaseqc_b200 import api
+        ann = api.Annotation(gtf)
         kind, sample = "port", f"{sr.n} records of the same workload, oracle/rsq_oracle.cpp, 1 thread"
         rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
         reads, blocks = synth.to_numpy(rb, bb)
@@ -434,10 +660,11 @@ def run_reference(args):
     timed = times[args.warmup:]
     per_step = max(sum(timed) / len(timed) - t_gtf, 1e-9)
     value = sr.n / per_step
-    out = {"impl": "reference", "metric": "reads/sec (150bp PE, GENCODE-scale GTF)", "value": value, "unit": "reads/s",
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": wl["label"], "sample_records": sr.n, "gtf_parse_seconds_subtracted": t_gtf},
+           "config": {"workload": wl["label"], "sample_records": sr.n, "gtf_parse_seconds_subtracted": t_gtf, "flags": flags[:1] + (["--bed"] if args.bed else []),
+                      "includes": "BGZF inflate + BAM record parse (about 10 % of the reference's time, SURVEY.md §6) — the GPU arm's e2e starts from decoded, packed records; bench.py's e2e_cli leg is the BAM-to-files comparison"},
            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -446,22 +673,32 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=150, help="timed steps (150 x ~14 ms: more than 2 s of timed work at the default workload)")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--min-warmup-s", type=float, default=1.5, help="warm-up goes on until this many seconds have passed (clock sampling needs load)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="gencode200m", choices=sorted(WORKLOADS))
-    ap.add_argument("--records", type=int, default=0, help="override the record count per GPU (smoke runs)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU gets the workload's record count; strong = the workload's records are split (configs[3])")
+    ap.add_argument("--records", type=int, default=0, help="override the workload's record count (smoke runs)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000,
                     help="records per step of `--impl reference` (the reference binary does ~0.2-0.4 M records/s: ~10 s)")
     ap.add_argument("--port-sample", type=int, default=30_000_000,
                     help="records of the cpu_baseline leg (the oracle port does ~3 M records/s on one core: ~10 s)")
     ap.add_argument("--e2e-chunk", type=int, default=8_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-unpacked", action="store_true", help="also time the 48-byte rsq_submit path")
+    ap.add_argument("--cli-records", type=int, default=60_000_000,
+                    help="records of the BAM the e2e_cli leg runs the product CLI on (N=1 only; 0 = skip)")
     ap.add_argument("--bed", action="store_true", help="also run the --bed fragment-size sampler (BASELINE.json configs[4])")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-preflight", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's host cores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     if args.impl == "reference":
+        args.steps = min(args.steps, 3) if args.steps == 150 else args.steps     # a step is ~10 s of one host core
         run_reference(args)
     else:
         run_ours(args)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RSQ_ABI_VERSION 2u
+#define RSQ_ABI_VERSION 3u
 
 /* ---- status codes -------------------------------------------------------------------------------------- */
 enum {
@@ -319,6 +319,11 @@ typedef struct rsq_transcripts {
     const uint8_t*  gene_strand;   /* [n_genes] RSQ_STRAND_*                                                  */
     const uint32_t* exon_len;      /* [n_exon_refs]                                                           */
     const uint32_t* exon_slot;     /* [n_exon_refs]                                                           */
+    const uint8_t*  gene_owned;    /* [n_genes] or NULL (= all).  Coordinate-partitioned runs (rsq_set_partition): 1 when the
+                                      gene's reads are in THIS partition.  Genes that are not owned are skipped and every
+                                      output of theirs is written as all-zero BITS, so the bitwise u64 sum of the outputs
+                                      over the partitions is the owner's value (the owner-gather of SURVEY.md §8e); exon
+                                      slots that no listed gene references hold NaN on partition 0 and zero bits elsewhere */
 } rsq_transcripts;
 
 typedef struct rsq_coverage_stats {
@@ -332,16 +337,48 @@ typedef struct rsq_coverage_stats {
     double*   exon_cv;             /* [n_exons by slot] NaN = no exonCoverage entry (src/Metrics.cpp:298-304)  */
 } rsq_coverage_stats;
 
-/* Runs after all records are submitted (integrates the coverage difference array itself). */
+/* Runs after all records are submitted (integrates the coverage difference array itself).  With a communicator attached
+ * (rsq_comm_init) and req->gene_owned given, the call is COLLECTIVE: the per-partition results are summed over NVLink before
+ * they are copied out, so every rank receives the statistics of all genes. */
 int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* req, rsq_coverage_stats* out);
 
-/* Device-resident count vector for the end-of-run all-reduce over NVLink (counters ‖ gene_reads ‖
- * gene_unique ‖ gene_fragments ‖ exon_whole ‖ exon_frac_hi32 ‖ exon_frac_lo32 ‖ gc_hist[100]), all uint64, additive
- * across partitions.  Returns a DEVICE pointer and the number of uint64 words; valid until rsq_destroy.
- * rsq_finalize must not have been called between rsq_export_counts and rsq_import_counts. */
+/* ---- coordinate-partitioned runs ------------------------------------------------------------------------
+ * The sorted record stream is cut into `world` contiguous coordinate ranges, one ctx (one GPU) per range, cut only where no gene,
+ * exon or BED interval lies: the fragment tracker (src/Metrics.cpp:22), both mate maps (src/Expression.cpp:461-474,511-533) and
+ * every gene's coverage then have one owner.  What is left to exchange at the end of the run:
+ *   - the additive tables: counters, the three gene tables, exon sums, GC-content bins;
+ *   - the fragment-size samples: the reference keeps the FIRST fragment_samples pairs of the stream (src/RNASeQC.cpp:372,
+ *     src/Expression.cpp:532).  Partition r ranks its own samples in stream order; with the per-partition sample counts known,
+ *     it keeps those whose GLOBAL rank (samples of partitions 0..r-1 before its own) is below the quota;
+ *   - the per-gene coverage statistics (rsq_transcripts.gene_owned).
+ * Two ways to run the exchange: (a) the caller moves the buffers (any transport; the CPU tests use gloo):
+ *       rsq_set_partition -> ... submits ... -> rsq_export_sample_counts -> all-reduce(sum) -> rsq_export_counts ->
+ *       all-reduce(sum) -> rsq_import_counts -> rsq_finalize
+ *   or (b) the library does, over NCCL (product only): rsq_comm_init -> ... submits ... -> rsq_exchange -> rsq_finalize.
+ * After either, every partition holds the state of the equivalent single-GPU run (per-base coverage excepted: it stays with
+ * its owner). */
+int rsq_set_partition(rsq_ctx* ctx, uint32_t rank, uint32_t world);
+/* Phase 1 (only needed when the fragment-size sampler is on): `world` uint64 words, zero except [rank] = samples this
+ * partition found.  DEVICE pointer in the product, host pointer in the oracle; the caller sum-reduces it in place. */
+int rsq_export_sample_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words);
+/* Phase 2: count vector for the end-of-run all-reduce (counters ‖ gene_reads ‖ gene_unique ‖ gene_fragments ‖ exon_whole ‖
+ * exon_frac_hi32 ‖ exon_frac_lo32 ‖ gc_hist[100] ‖ total samples found ‖ the kept fragment-size samples at their global
+ * ranks, two 32-bit values per word), all uint64, additive across partitions without carries.  Returns a DEVICE pointer and
+ * the number of uint64 words; valid until rsq_destroy.  rsq_finalize must not have been called between rsq_export_counts and
+ * rsq_import_counts. */
 int rsq_export_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words);
-/* After the caller reduced the exported buffer in place (NCCL sum), fold it back into the ctx state. */
+/* After the caller reduced the exported buffer in place (sum), fold it back into the ctx state. */
 int rsq_import_counts(rsq_ctx* ctx);
+
+/* NCCL inside the product (the north_star's "final NCCL allreduce of the per-gene/per-exon count vectors over NVLink").  The
+ * library binds libnccl at run time (dlopen; the copy a host process has already loaded — e.g. PyTorch's — is reused).
+ * rsq_comm_unique_id: one caller creates the id and hands it to every rank (any transport).  rsq_comm_init: collective over
+ * all `world` contexts (one per GPU; threads of one process or one process each); implies rsq_set_partition(rank, world).
+ * rsq_exchange: collective; runs phases 1 and 2 above on the ctx stream without a host round trip. */
+#define RSQ_COMM_ID_BYTES 128
+int rsq_comm_unique_id(uint8_t id[RSQ_COMM_ID_BYTES]);
+int rsq_comm_init(rsq_ctx* ctx, const uint8_t id[RSQ_COMM_ID_BYTES], uint32_t rank, uint32_t world);
+int rsq_exchange(rsq_ctx* ctx);
 
 /* Algorithmic HBM bytes of everything submitted since the last reset, by the definition of
  * 40 + 8*nb per record, + (8 + 8*nb_a) for HQ assigned reads, + 8*nb_a coverage. */

@@ -89,7 +89,7 @@ class RsqTranscripts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_genes", C.c_uint32), ("n_exon_refs", C.c_uint32), ("coverage_mask", C.c_uint32),
                 ("bias_offset", C.c_int32), ("bias_window", C.c_int32), ("bias_gene_length", C.c_uint32), ("reserved", C.c_uint32),
                 ("gene_cov_off", C.POINTER(C.c_uint64)), ("gene_exon_off", C.POINTER(C.c_uint32)), ("gene_strand", C.POINTER(C.c_uint8)),
-                ("exon_len", C.POINTER(C.c_uint32)), ("exon_slot", C.POINTER(C.c_uint32))]
+                ("exon_len", C.POINTER(C.c_uint32)), ("exon_slot", C.POINTER(C.c_uint32)), ("gene_owned", C.POINTER(C.c_uint8))]
 
 
 class RsqCoverageStats(C.Structure):
@@ -112,8 +112,10 @@ class StreamStateC(C.Structure):
 
 ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
                "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_packed", "rsq_submit_device", "rsq_sync",
-               "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_export_counts", "rsq_import_counts", "rsq_algorithmic_bytes",
+               "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_set_partition", "rsq_export_sample_counts", "rsq_export_counts",
+               "rsq_import_counts", "rsq_comm_unique_id", "rsq_comm_init", "rsq_exchange", "rsq_algorithmic_bytes",
                "rsq_launch_count", "rsq_kernel_time_ms"]
+RSQ_COMM_ID_BYTES = 128
 
 
 def make_config(device: int = 0, mapq: int = 255, mismatches: int = 6, chimeric_distance: int = 2000000,
@@ -228,6 +230,11 @@ class Backend:
         L.rsq_coverage_statistics.argtypes = [C.c_void_p, C.POINTER(RsqTranscripts), C.POINTER(RsqCoverageStats)]
         L.rsq_export_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.rsq_import_counts.argtypes = [C.c_void_p]
+        L.rsq_set_partition.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.rsq_export_sample_counts.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.rsq_comm_unique_id.argtypes = [C.c_void_p]
+        L.rsq_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.rsq_exchange.argtypes = [C.c_void_p]
         L.rsq_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rsq_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.rsq_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -235,6 +242,14 @@ class Backend:
     @property
     def name(self) -> str:
         return self.lib.rsq_backend().decode()
+
+    def comm_unique_id(self) -> bytes:
+        """rsq_comm_unique_id: created by ONE rank and handed to all (bench.py broadcasts it through torch.distributed)"""
+        buf = C.create_string_buffer(RSQ_COMM_ID_BYTES)
+        rc = self.lib.rsq_comm_unique_id(buf)
+        if rc != RSQ_OK:
+            raise RsqError(rc, self.lib.rsq_last_error(None).decode())
+        return buf.raw
 
     def create(self, cfg: RsqConfig) -> "Context":
         h = C.c_void_p()
@@ -337,10 +352,15 @@ class Context:
         return res
 
     def coverage_statistics(self, ann: "Annotation", mask: int = 500, bias_offset: int = 0, bias_window: int = 100,
-                            bias_gene_length: int = 200, pinned: bool = False) -> dict:
-        """per-gene-line coverage statistics (rsq_coverage_statistics); arrays indexed by gene line (contig, start order)"""
+                            bias_gene_length: int = 200, pinned: bool = False, owned: Optional[np.ndarray] = None) -> dict:
+        """per-gene-line coverage statistics (rsq_coverage_statistics); arrays indexed by gene line (contig, start order).
+        owned: uint8 per gene line (rsq_transcripts.gene_owned) in coordinate-partitioned runs."""
         q = RsqTranscripts()
         host_lib().rsqh_transcripts(ann._h, mask, bias_offset, bias_window, bias_gene_length, C.byref(q))
+        if owned is not None:
+            owned = np.ascontiguousarray(owned, np.uint8)
+            assert len(owned) == q.n_genes
+            q.gene_owned = owned.ctypes.data_as(C.POINTER(C.c_uint8))
         n = q.n_genes
         z = (lambda name, k, dt: self._pinned_array("cs_" + name, k, dt)) if pinned else (lambda name, k, dt: np.zeros(k, dt))
         out = {"gene_mean": z("gene_mean", n, np.float64), "gene_std": z("gene_std", n, np.float64), "gene_cv": z("gene_cv", n, np.float64),
@@ -353,6 +373,23 @@ class Context:
         st.three_end = out["three_end"].ctypes.data_as(C.POINTER(C.c_uint64))
         self._check(self.be.lib.rsq_coverage_statistics(self.h, C.byref(q), C.byref(st)))
         return out
+
+    def set_partition(self, rank: int, world: int) -> None:
+        self._check(self.be.lib.rsq_set_partition(self.h, rank, world))
+
+    def export_sample_counts(self) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.be.lib.rsq_export_sample_counts(self.h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def comm_init(self, comm_id: bytes, rank: int, world: int) -> None:
+        """collective over all ranks (NCCL inside the library)"""
+        assert len(comm_id) == RSQ_COMM_ID_BYTES
+        self._check(self.be.lib.rsq_comm_init(self.h, C.c_char_p(comm_id), rank, world))
+
+    def exchange(self) -> None:
+        """collective: the end-of-run exchange of a partitioned run, on the context's stream"""
+        self._check(self.be.lib.rsq_exchange(self.h))
 
     def export_counts(self) -> Tuple[int, int]:
         p, n = C.c_void_p(), C.c_size_t()
@@ -405,6 +442,9 @@ def host_lib():
         H.rsqh_reference_view.argtypes = [C.c_void_p]
         H.rsqh_set_fasta.argtypes = [C.c_char_p]
         H.rsqh_transcripts.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_ulong, C.POINTER(RsqTranscripts)]
+        H.rsqh_gene_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        H.rsqh_islands.restype = C.c_size_t
+        H.rsqh_islands.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         for f in ("rsqh_n_gene_list", "rsqh_n_contigs"):
             getattr(H, f).restype = C.c_uint
             getattr(H, f).argtypes = [C.c_void_p]
@@ -422,7 +462,7 @@ def host_lib():
         H.rsqh_pack_records.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
         H.rsqh_hash_qname.restype = C.c_uint64
         H.rsqh_hash_qname.argtypes = [C.c_char_p, C.c_size_t]
-        H.rsqh_write_reports.argtypes = [C.c_void_p, C.POINTER(RsqResults), C.c_void_p, C.POINTER(RunOptionsC),
+        H.rsqh_write_reports.argtypes = [C.c_void_p, C.POINTER(RsqResults), C.c_void_p, C.POINTER(RsqCoverageStats), C.POINTER(RunOptionsC),
                                          C.POINTER(StreamStateC), C.c_char_p, C.c_size_t]
         _host = H
     return _host
@@ -476,6 +516,27 @@ class Annotation:
     def contig_index(self, name: str) -> int:
         return host_lib().rsqh_contig_index(self._h, name.encode())
 
+    def contig_names(self) -> List[str]:
+        H = host_lib()
+        return [H.rsqh_contig_name(self._h, c).decode() for c in range(H.rsqh_n_contigs(self._h))]
+
+    def gene_lines(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(annotation contig id, start, end) of the kept gene lines, in the order of the coverage-statistics request"""
+        q = RsqTranscripts()
+        host_lib().rsqh_transcripts(self._h, 500, 0, 100, 200, C.byref(q))
+        c, s, e = np.zeros(q.n_genes, np.uint32), np.zeros(q.n_genes, np.int64), np.zeros(q.n_genes, np.int64)
+        host_lib().rsqh_gene_lines(self._h, c.ctypes.data, s.ctypes.data, e.ctypes.data)
+        return c, s, e
+
+    def islands(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(annotation contig id, start, end) of the merged gene hulls + BED intervals: a partitioned stream may be cut
+        between two islands and nowhere else (csrc/host/annotation.h)"""
+        H = host_lib()
+        n = H.rsqh_islands(self._h, None, None, None)
+        c, s, e = np.zeros(n, np.uint32), np.zeros(n, np.int64), np.zeros(n, np.int64)
+        H.rsqh_islands(self._h, c.ctypes.data, s.ctypes.data, e.ctypes.data)
+        return c, s, e
+
     def gene_ids(self) -> List[str]:
         H = host_lib()
         return [H.rsqh_gene_id(self._h, g).decode() for g in range(self.n_genes)]
@@ -503,7 +564,7 @@ class Annotation:
         H.rsqh_free(pb)
         return reads, blocks, st
 
-    def write_reports(self, res: Results, out_dir: str, sample: str, state: StreamStateC, sample_given: bool = False,
+    def write_reports(self, res: Results, cov_stats: dict, out_dir: str, sample: str, state: StreamStateC, sample_given: bool = False,
                       write_coverage: bool = False, use_rpkm: bool = False, filter_tags: Sequence[str] = (),
                       exon_seq: Optional[np.ndarray] = None, coverage_mask: int = 500, detection_threshold: int = 5) -> None:
         H = host_lib()
@@ -516,8 +577,14 @@ class Annotation:
         st = res.struct()
         C.memmove(st.counters, res.counters.ctypes.data, 8 * RSQ_N_COUNTERS)
         st.fragment_samples_taken = res.fragment_samples_taken
+        cs = RsqCoverageStats()
+        cs.struct_size = C.sizeof(RsqCoverageStats)
+        pd = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        cs.gene_mean, cs.gene_std, cs.gene_cv, cs.exon_cv = pd(cov_stats["gene_mean"]), pd(cov_stats["gene_std"]), pd(cov_stats["gene_cv"]), pd(cov_stats["exon_cv"])
+        cs.five_end = cov_stats["five_end"].ctypes.data_as(C.POINTER(C.c_uint64))
+        cs.three_end = cov_stats["three_end"].ctypes.data_as(C.POINTER(C.c_uint64))
         err = C.create_string_buffer(1024)
-        rc = H.rsqh_write_reports(self._h, C.byref(st), exon_seq.ctypes.data if exon_seq is not None else None, C.byref(o),
+        rc = H.rsqh_write_reports(self._h, C.byref(st), exon_seq.ctypes.data if exon_seq is not None else None, C.byref(cs), C.byref(o),
                                   C.byref(state), err, 1024)
         if rc != 0:
             raise RuntimeError(f"write_reports failed (exit code {rc}): {err.value.decode()}")

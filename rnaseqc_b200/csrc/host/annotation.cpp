@@ -527,4 +527,59 @@ rsq_bed BedModel::view() const {
     return v;
 }
 
+void build_islands(const Annotation& A, const BedModel* bed, Islands& out) {
+    const size_t nc = A.genes_by_contig.size();
+    out.by_contig.assign(nc, {});
+    // hull of every gene-universe entry per contig (a gene id may, in odd annotations, have lines on several contigs)
+    std::vector<std::unordered_map<uint32_t, std::pair<int64_t, int64_t>>> hull(nc);
+    auto grow = [&](uint32_t contig, uint32_t gene, int64_t s, int64_t e) {
+        if (e < s) std::swap(s, e);
+        auto it = hull[contig].find(gene);
+        if (it == hull[contig].end()) hull[contig].emplace(gene, std::make_pair(s, e));
+        else { it->second.first = std::min(it->second.first, s); it->second.second = std::max(it->second.second, e); }
+    };
+    for (size_t c = 0; c < nc; ++c) {
+        for (const GeneFeature& g : A.genes_by_contig[c]) { grow((uint32_t)c, g.gene, g.start, g.end); if (g.gid != g.gene) grow((uint32_t)c, g.gid, g.start, g.end); }
+        for (const ExonFeature& e : A.exons_by_contig[c]) grow((uint32_t)c, e.gene, e.start, e.end);
+    }
+    for (size_t c = 0; c < nc; ++c) {
+        std::vector<std::pair<int64_t, int64_t>> iv;
+        iv.reserve(hull[c].size());
+        for (auto& kv : hull[c]) iv.push_back(kv.second);
+        if (bed && c < bed->starts.size())
+            for (size_t i = 0; i < bed->starts[c].size(); ++i) iv.emplace_back(std::min(bed->starts[c][i], bed->ends[c][i]), std::max(bed->starts[c][i], bed->ends[c][i]));
+        std::sort(iv.begin(), iv.end());
+        auto& m = out.by_contig[c];
+        for (auto& x : iv) {
+            // the reference's closed block end is one past the last base (src/Expression.cpp:45): keep one base of slack
+            if (!m.empty() && x.first <= m.back().second + 1) m.back().second = std::max(m.back().second, x.second);
+            else m.push_back(x);
+        }
+    }
+}
+
+int64_t Islands::next_cut(uint32_t contig, int64_t pos1) const {
+    if (contig >= by_contig.size()) return pos1;
+    const auto& m = by_contig[contig];
+    // last island starting at or before pos1
+    auto it = std::upper_bound(m.begin(), m.end(), std::make_pair(pos1, INT64_MAX));
+    if (it == m.begin()) return pos1;
+    --it;
+    return pos1 <= it->second + 1 ? it->second + 2 : pos1;
+}
+
+void gene_ownership(const Annotation& A, const std::vector<StreamCut>& cuts, const std::vector<int64_t>& contig_rank, uint32_t rank,
+                    std::vector<uint8_t>& owned) {
+    owned.assign(A.t_gene_strand.size(), 0);
+    for (size_t c = 0; c < A.genes_by_contig.size(); ++c) {
+        const int64_t cr = c < contig_rank.size() ? contig_rank[c] : -1;
+        for (const GeneFeature& g : A.genes_by_contig[c]) {
+            uint32_t owner = 0;
+            if (cr >= 0)
+                for (const StreamCut& k : cuts) if (cr > k.contig_rank || (cr == k.contig_rank && g.start >= k.pos1)) ++owner;
+            owned[g.flat] = owner == rank;
+        }
+    }
+}
+
 }  // namespace rsqh

@@ -132,4 +132,22 @@ void load_bed(const std::string& path, ContigMap& contigs, BedModel& out);
 // (Re)builds the flattened arrays after all contigs are known.
 void flatten_bed(BedModel& bed, size_t n_contigs);
 
+// ---- coordinate partitioning across GPUs ----------------------------------------------------------------
+// "Islands": per contig, the merged union of (a) the hull of every gene — its gene line and all of its exon lines, wherever
+// they lie — and (b) every BED interval.  A record stream may be cut between two islands and nowhere else: all records that
+// count toward a gene (every aligned block inside exons of that gene, src/Expression.cpp:363-377), both mates the fragment
+// tracker and the two mate maps pair up, and the gene's per-base coverage then belong to one partition.
+struct Islands {
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> by_contig;   // annotation contig id -> sorted, disjoint [start, end] (1-based closed)
+    // first coordinate >= pos1 (1-based) on the contig that lies in no island: a legal cut (records with pos+1 >= cut go right)
+    int64_t next_cut(uint32_t contig, int64_t pos1) const;
+};
+void build_islands(const Annotation& A, const BedModel* bed, Islands& out);
+// One cut of a partitioned stream: records at (stream rank of the contig, 1-based start) >= (contig_rank, pos1) lie right of it.
+struct StreamCut { int64_t contig_rank; int64_t pos1; };
+// rsq_transcripts.gene_owned of partition `rank`: gene line i (the request's order) is owned by the partition its start falls
+// into; contig_rank maps an annotation contig id to its rank in the stream's contig order (-1: no records -> partition 0).
+void gene_ownership(const Annotation& A, const std::vector<StreamCut>& cuts, const std::vector<int64_t>& contig_rank, uint32_t rank,
+                    std::vector<uint8_t>& owned);
+
 }  // namespace rsqh

@@ -85,6 +85,25 @@ const rsq_bed* rsqh_bed_view(void* h) { Handle* H = static_cast<Handle*>(h); ret
 void rsqh_transcripts(void* h, unsigned mask, int bias_offset, int bias_window, unsigned long bias_gene_length, rsq_transcripts* out) {
     *out = static_cast<Handle*>(h)->ann.transcripts(mask, bias_offset, bias_window, bias_gene_length);
 }
+// gene lines in the order of the rsq_transcripts request: annotation contig id, 1-based start and end (arrays of n_genes entries)
+void rsqh_gene_lines(void* h, uint32_t* contig, int64_t* start, int64_t* end) {
+    const rsqh::Annotation& A = static_cast<Handle*>(h)->ann;
+    for (size_t c = 0; c < A.genes_by_contig.size(); ++c)
+        for (const rsqh::GeneFeature& g : A.genes_by_contig[c]) { contig[g.flat] = (uint32_t)c; start[g.flat] = g.start; end[g.flat] = g.end; }
+}
+// islands of the loaded annotation (+ BED): call with NULL arrays for the count, then with arrays of that size
+size_t rsqh_islands(void* h, uint32_t* contig, int64_t* start, int64_t* end) {
+    Handle* H = static_cast<Handle*>(h);
+    rsqh::Islands I;
+    rsqh::build_islands(H->ann, H->have_bed ? &H->bed : nullptr, I);
+    size_t n = 0;
+    for (size_t c = 0; c < I.by_contig.size(); ++c)
+        for (auto& iv : I.by_contig[c]) {
+            if (contig) { contig[n] = (uint32_t)c; start[n] = iv.first; end[n] = iv.second; }
+            ++n;
+        }
+    return n;
+}
 unsigned rsqh_n_gene_list(void* h) { return (unsigned)static_cast<Handle*>(h)->ann.gene_list.size(); }
 unsigned rsqh_gene_list_index(void* h, unsigned i) { return static_cast<Handle*>(h)->ann.gene_list[i]; }
 const char* rsqh_gene_id(void* h, unsigned g) { return static_cast<Handle*>(h)->ann.gene_ids[g].c_str(); }
@@ -179,7 +198,7 @@ const rsq_reference* rsqh_reference_view(void* h) { Handle* H = static_cast<Hand
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
 
 // Writes the reference's output files from finalised results.
-int rsqh_write_reports(void* hv, const rsq_results* res, const double* exon_seq_or_null, const rsqh_run_options* o,
+int rsqh_write_reports(void* hv, const rsq_results* res, const double* exon_seq_or_null, const rsq_coverage_stats* cs, const rsqh_run_options* o,
                        const rsqh_stream_state* st, char* err, size_t errlen) {
     Handle* h = static_cast<Handle*>(hv);
     try {
@@ -193,7 +212,13 @@ int rsqh_write_reports(void* hv, const rsq_results* res, const double* exon_seq_
         R.exon_whole.assign(res->exon_whole, res->exon_whole + ne);
         R.exon_frac.assign(res->exon_frac, res->exon_frac + ne);
         if (exon_seq_or_null) R.exon_seq.assign(exon_seq_or_null, exon_seq_or_null + ne);
-        if (res->coverage) R.coverage.assign(res->coverage, res->coverage + A.cov_len);
+        if (cs) {                       // what rsq_coverage_statistics returned for the request of rsqh_transcripts
+            const size_t nl = A.t_gene_strand.size();
+            R.cs_mean.assign(cs->gene_mean, cs->gene_mean + nl); R.cs_std.assign(cs->gene_std, cs->gene_std + nl);
+            R.cs_cv.assign(cs->gene_cv, cs->gene_cv + nl); R.cs_five.assign(cs->five_end, cs->five_end + nl);
+            R.cs_three.assign(cs->three_end, cs->three_end + nl); R.cs_exon_cv.assign(cs->exon_cv, cs->exon_cv + ne);
+            R.have_cov_stats = true;
+        }
         if (res->fragment_hist) R.fragment_hist.assign(res->fragment_hist, res->fragment_hist + res->fragment_hist_len);
         R.fragment_samples_taken = res->fragment_samples_taken;
         if (res->gc_hist) memcpy(R.gc_hist, res->gc_hist, sizeof(R.gc_hist));

@@ -61,60 +61,6 @@ Stats get_statistics(std::vector<double>& data) {
     return Stats{avg, median, sd, med_dev};
 }
 
-// BiasCounter::computeBias (src/Metrics.cpp:160-235).  `cov` is mutated exactly as the reference mutates the
-// caller's vector (low-coverage flanks are erased when the peak-window value is >= 100).
-void compute_bias(std::vector<unsigned long>& cov, uint8_t strand, const RunOptions& opt, uint64_t& five_end,
-                  uint64_t& three_end) {
-    if (cov.size() < opt.bias_gene_length) return;                                   // :163
-    unsigned long peak = 0;
-    size_t peak_pos = 0;
-    for (size_t i = 0; i < cov.size(); ++i)
-        if (cov[i] > peak) { peak_pos = i; peak = cov[i]; }                          // :166-170 (first maximum)
-    // :171-176 — half a window right (clamped at end()), then back one window (clamped at begin()); only the
-    // NUMBER of entries collected is used afterwards (the sorted list itself is ignored).
-    size_t p1 = peak_pos;
-    for (int i = 0; i < opt.bias_window / 2 && p1 != cov.size(); ++i) ++p1;
-    size_t n = 0, it = p1;
-    for (int i = 0; i < opt.bias_window && it != 0; ++i) { ++n; --it; }
-    // :178 — computeMedian(n, iterator into the UNSORTED coverage vector)
-    auto at = [&](unsigned long i) -> double {
-        size_t idx = it + i;
-        return idx < cov.size() ? (double)cov[idx] : 0.0;
-    };
-    if (n == 0) return;  // cannot happen for size >= 1 (the reference would throw range_error)
-    const double peak_median = median_quirk(n, at);
-    if (!(peak_median >= 100)) return;                                                // :181
-    std::vector<unsigned long> pct(cov);                                              // :182-188
-    std::sort(pct.begin(), pct.end());
-    pct.erase(pct.begin(), std::find_if(pct.begin(), pct.end(), [](unsigned long v) { return v != 0ul; }));
-    const unsigned long lower = pct[(size_t)(pct.size() * 0.05)];                     // :189
-    {
-        size_t k = 0;
-        while (k < cov.size() && cov[k] <= lower) ++k;                                // :193-199
-        cov.erase(cov.begin(), cov.begin() + k);
-    }
-    while (!cov.empty() && cov.back() <= lower) cov.pop_back();                       // :202-205
-    if (cov.size() < opt.bias_gene_length) return;                                    // :208
-    std::vector<double> lcov, rcov;
-    const unsigned offset = (unsigned)opt.bias_offset, window = (unsigned)opt.bias_window;
-    for (unsigned i = offset; i < offset + window && i < cov.size(); ++i) lcov.push_back((double)cov[i]);   // :214
-    for (int i = (int)(cov.size() - (size_t)(opt.bias_window + opt.bias_offset));
-         i >= 0 && (size_t)i < cov.size() - (size_t)opt.bias_offset; ++i)
-        rcov.push_back((double)cov[i]);                                               // :216
-    std::sort(lcov.begin(), lcov.end());
-    std::sort(rcov.begin(), rcov.end());
-    const double ml = median_quirk(lcov.size(), [&](unsigned long i) { return lcov[i]; });
-    const double mr = median_quirk(rcov.size(), [&](unsigned long i) { return rcov[i]; });
-    // :220-228 — the maps hold unsigned long: `+=` with a double truncates
-    if (strand == RSQ_STRAND_FWD) {
-        three_end = (uint64_t)((double)three_end + mr);
-        five_end = (uint64_t)((double)five_end + ml);
-    } else {
-        three_end = (uint64_t)((double)three_end + ml);
-        five_end = (uint64_t)((double)five_end + mr);
-    }
-}
-
 std::string fmt_default(double v) {
     std::ostringstream s;
     s << v;
@@ -128,7 +74,6 @@ void compute_coverage_summary(const Annotation& A, const HostResults& R, const R
     const size_t ng = A.gene_ids.size();
     out.five_end.assign(ng, 0);
     out.three_end.assign(ng, 0);
-    const unsigned M = opt.coverage_mask;
 
     // ---- eviction order -------------------------------------------------------------------
     // trimFeatures evicts from the FRONT of the start-sorted list (src/Expression.cpp:80-93) and dropFeatures
@@ -172,83 +117,24 @@ void compute_coverage_summary(const Annotation& A, const HostResults& R, const R
         }
     }
 
-    if (R.have_cov_stats) {
-        // statistics came from the device kernel (rsq_covstats.cu); only the ordering and the text are left
-        for (const GeneFeature* gf : order) {
-            const uint32_t g = gf->gene, fi = gf->flat;
-            out.five_end[g] = (uint64_t)((double)out.five_end[g] + (double)R.cs_five[fi]);
-            out.three_end[g] = (uint64_t)((double)out.three_end[g] + (double)R.cs_three[fi]);
-            std::string row = A.gene_ids[g] + "\t";
-            if (R.cs_mean[fi] != -1.0 || R.cs_std[fi] != -1.0) {
-                row += fmt_default(R.cs_mean[fi]) + "\t" + fmt_default(R.cs_std[fi]) + "\t" + fmt_default(R.cs_cv[fi]);
-                out.gene_means.push_back(R.cs_mean[fi]);
-                out.gene_stds.push_back(R.cs_std[fi]);
-                out.gene_cvs.push_back(R.cs_cv[fi]);
-            } else row += "0\t0\tnan";
-            out.rows.push_back(row);
-        }
-        for (size_t s = 0; s < R.cs_exon_cv.size(); ++s)
-            if (!std::isnan(R.cs_exon_cv[s])) out.exon_cvs.emplace_back(A.exon_ids[s], R.cs_exon_cv[s]);
-        return;
-    }
-
-    // ---- computeCoverage per evicted gene (src/Metrics.cpp:265-337) ------------------------------------------
-    std::vector<unsigned long> gene_cov;
-    std::vector<uint32_t> zero_cov;
-    if (R.coverage.size() < A.cov_len) zero_cov.assign(A.cov_len + 1, 0);
-    const uint32_t* cov_base = R.coverage.size() < A.cov_len ? zero_cov.data() : R.coverage.data();
+    // The statistics themselves (BaseCoverage::compute / computeCoverage / computeBias, src/Metrics.cpp:132-337) come from
+    // rsq_coverage_statistics — the device kernel rsq_covstats.cu in the product; only the ordering and the text are left.
+    if (!R.have_cov_stats) throw HostError(-1, "coverage statistics missing: rsq_coverage_statistics must run before the report writer");
     for (const GeneFeature* gf : order) {
-        const uint32_t g = gf->gene;
-        const auto& slots = A.exons_for_gene[g];
-        uint64_t T = 0;
-        for (uint32_t s : slots) T += (uint64_t)std::max<int64_t>(A.exon_len[s], 0);
-        // unmasked transcript positions are [M, T-M): the first M and the last M bases are masked (:267-279)
-        const uint64_t lo = M, hi = T > M ? T - M : 0;
-        gene_cov.clear();
-        gene_cov.reserve(T);
-        uint64_t o = 0;
-        for (uint32_t s : slots) {
-            const uint64_t L = (uint64_t)std::max<int64_t>(A.exon_len[s], 0);
-            const uint32_t* cov = cov_base + A.exon_cov_off[s];
-            double exon_mean = 0.0, exon_std = 0.0, exon_size = 0.0;
-            for (uint64_t j = 0; j < L; ++j) if (o + j >= lo && o + j < hi) exon_size += 1.0;                 // :286
-            if (exon_size > 0) {
-                for (uint64_t j = 0; j < L; ++j)
-                    if (o + j >= lo && o + j < hi) exon_mean += (double)cov[j] / exon_size;                  // :290-291
-                for (uint64_t j = 0; j < L; ++j)
-                    if (o + j >= lo && o + j < hi) exon_std += std::pow((double)cov[j] - exon_mean, 2.0) / exon_size;  // :293-294
-                exon_std = std::pow(exon_std, 0.5);
-                exon_std /= exon_mean;                                                                       // :296 (now a CV)
-                if (!(std::isnan(exon_std) || std::isinf(exon_std))) out.exon_cvs.emplace_back(A.exon_ids[s], exon_std);
-            }
-            for (uint64_t j = 0; j < L; ++j) gene_cov.push_back(cov[j]);                                     // :307-308
-            o += L;
-        }
-        compute_bias(gene_cov, gf->strand, opt, out.five_end[g], out.three_end[g]);                          // :311
-        double avg = 0.0, sd = 0.0;
-        if (M) {                                                                                             // :314-322
-            if (M > gene_cov.size()) gene_cov.clear();
-            else gene_cov.erase(gene_cov.end() - M, gene_cov.end());
-            if (!gene_cov.empty()) {
-                if (M > gene_cov.size()) gene_cov.clear();
-                else gene_cov.erase(gene_cov.begin(), gene_cov.begin() + M);
-            }
-        }
-        const double size = (double)gene_cov.size();
+        const uint32_t g = gf->gene, fi = gf->flat;
+        out.five_end[g] = (uint64_t)((double)out.five_end[g] + (double)R.cs_five[fi]);
+        out.three_end[g] = (uint64_t)((double)out.three_end[g] + (double)R.cs_three[fi]);
         std::string row = A.gene_ids[g] + "\t";
-        if (size > 0) {
-            for (unsigned long v : gene_cov) avg += (double)v / size;
-            for (unsigned long v : gene_cov) sd += std::pow((double)v - avg, 2.0) / size;
-            sd = std::pow(sd, 0.5);
-            row += fmt_default(avg) + "\t" + fmt_default(sd) + "\t" + fmt_default(sd / avg);
-            out.gene_means.push_back(avg);
-            out.gene_stds.push_back(sd);
-            out.gene_cvs.push_back(sd / avg);
-        } else {
-            row += "0\t0\tnan";                                                                              // :335
-        }
+        if (R.cs_mean[fi] != -1.0 || R.cs_std[fi] != -1.0) {
+            row += fmt_default(R.cs_mean[fi]) + "\t" + fmt_default(R.cs_std[fi]) + "\t" + fmt_default(R.cs_cv[fi]);
+            out.gene_means.push_back(R.cs_mean[fi]);
+            out.gene_stds.push_back(R.cs_std[fi]);
+            out.gene_cvs.push_back(R.cs_cv[fi]);
+        } else row += "0\t0\tnan";
         out.rows.push_back(row);
     }
+    for (size_t s = 0; s < R.cs_exon_cv.size(); ++s)
+        if (!std::isnan(R.cs_exon_cv[s])) out.exon_cvs.emplace_back(A.exon_ids[s], R.cs_exon_cv[s]);
 }
 
 namespace {

@@ -2,6 +2,8 @@
 // One rsq_ctx drives one GPU.  There is no CPU fallback: without a CUDA device rsq_create fails with
 // RSQ_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types and enums only: the library is bound at run time (dlopen), never linked
 
 #include <algorithm>
 #include <cstdio>
@@ -48,9 +50,15 @@ struct Ctx {
     unsigned long long frag_known = 0, frag_pending = 0;   // entries read back from the device / upper bound of those in flight
     unsigned long long exon_depth = 1;                     // deepest stack of overlapping exons (inserts per record <= this)
     unsigned long long* d_export = nullptr;
+    // coordinate-partitioned runs (rsq_set_partition / rsq_comm_init)
+    uint32_t part_rank = 0, part_world = 1;
+    unsigned long long* d_found = nullptr;    // [part_world] per-partition sample counts (phase 1 of the exchange)
+    bool found_valid = false;                 // d_found holds the reduced counts of the current run
+    ncclComm_t comm = nullptr;
     // rsq_coverage_statistics buffers
     unsigned long long* cs_off = nullptr; uint32_t *cs_eoff = nullptr, *cs_len = nullptr, *cs_slot = nullptr; uint8_t* cs_strand = nullptr;
-    double* cs_out = nullptr; unsigned long long* cs_ends = nullptr;
+    double* cs_out = nullptr; unsigned long long* cs_ends = nullptr;   // one allocation: mean | std | cv | exon_cv | five | three
+    uint8_t* cs_owned = nullptr;
     size_t cs_cap_genes = 0, cs_cap_refs = 0;
     size_t export_words = 0;
     unsigned long long* d_hist = nullptr;
@@ -94,6 +102,50 @@ constexpr size_t kSubBatchPlain = (size_t)1 << RSQ_PLAIN_SUB_BATCH_LOG2;   // wi
         }                                                                                                 \
     } while (0)
 
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------------------
+// A host process that already carries a libnccl (PyTorch does) must not get a second copy: RTLD_NOLOAD finds the loaded one by
+// its soname first; only then is the system library opened.  RSQ_NCCL_LIB overrides both.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char* env = getenv("RSQ_NCCL_LIB");
+    if (env && *env) api.handle = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!api.handle) { const char* e = dlerror(); api.why = std::string("libnccl not found: ") + (e ? e : "?"); return api; }
+    auto sym = [&](const char* n) { void* p = dlsym(api.handle, n); if (!p) api.why = std::string("libnccl lacks ") + n; return p; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!api.why.empty()) api.handle = nullptr;
+    return api;
+}
+static_assert(sizeof(ncclUniqueId) == RSQ_COMM_ID_BYTES, "rsq_comm_unique_id hands out a whole ncclUniqueId");
+#define NCCL_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        ncclResult_t r__ = (expr);                                                                        \
+        if (r__ != ncclSuccess) {                                                                         \
+            c->err = std::string(#expr) + ": " + nccl_api().GetErrorString(r__);                          \
+            return RSQ_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+unsigned long long sample_quota(const struct Ctx* c);
+
 unsigned long long next_pow2(unsigned long long v) {
     unsigned long long p = 1;
     while (p < v) p <<= 1;
@@ -109,6 +161,8 @@ int upload(Ctx* c, std::vector<void*>& owner, const T* host, size_t n, const T**
     *out = d;
     return RSQ_OK;
 }
+
+unsigned long long sample_quota(const Ctx* c) { return (c->have_bed && c->cfg.fragment_samples) ? c->cfg.fragment_samples : 0ull; }
 
 void free_list(std::vector<void*>& v) {
     for (void* p : v) cudaFree(p);
@@ -139,6 +193,7 @@ int zero_accumulators(Ctx* c) {
         CU_TRY(cudaMemsetAsync(a.gc_hist, 0, 8 * 100, c->stream));
     }
     c->records_submitted = 0;
+    c->found_valid = false;
     c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
     c->timers_used = 0;
@@ -368,13 +423,14 @@ void rsq_destroy(rsq_ctx* ctx) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
+    if (c->comm && nccl_api().handle) nccl_api().CommDestroy(c->comm);
     free_list(c->ann_allocs);
     free_list(c->bed_allocs);
     free_list(c->ref_allocs);
     Accum& a = c->acc;
     void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
-                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_ends, c->d_hist, c->d_pair_scratch,
+                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_owned, c->d_found, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
                     c->d_up_tot, c->d_up_expl, c->d_up_scan};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -513,8 +569,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     acc.frag_cap = c->frag_cap;
     CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
     CU_TRY(cudaMalloc(&acc.error_flag, 8));   // [0] the flag; [1] the tile counter of the RSQ_DYNAMIC_TILES experiment
-    c->export_words = RSQ_N_COUNTERS + 3ull * a->n_genes + 3ull * c->n_exons + 100ull;   // ... | 100 GC-content bins
-    CU_TRY(cudaMalloc(&c->d_export, 8ull * c->export_words));
+    // the export buffer of the end-of-run exchange is sized on first use (its tail depends on rsq_set_bed)
     c->have_ann = true;
     rc = zero_accumulators(c);
     if (rc != RSQ_OK) return rc;
@@ -802,34 +857,46 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
     cudaStream_t st = c->stream;
     // request arrays -> device (a few MB); the buffers persist in the ctx and only grow
     const size_t ng = q->n_genes, nr = q->n_exon_refs, ne = c->n_exons;
-    if (ng > c->cs_cap_genes || nr > c->cs_cap_refs) {
+    if (std::max<size_t>(ng, 1) != c->cs_cap_genes || nr > c->cs_cap_refs) {   // exact per-gene stride: the all-reduce below spans the block
         CU_TRY(cudaStreamSynchronize(st));
-        cudaFree(c->cs_off); cudaFree(c->cs_eoff); cudaFree(c->cs_strand); cudaFree(c->cs_len); cudaFree(c->cs_slot); cudaFree(c->cs_out); cudaFree(c->cs_ends);
-        c->cs_cap_genes = std::max<size_t>(ng, 1); c->cs_cap_refs = std::max<size_t>(nr, 1);
+        cudaFree(c->cs_off); cudaFree(c->cs_eoff); cudaFree(c->cs_strand); cudaFree(c->cs_len); cudaFree(c->cs_slot); cudaFree(c->cs_out); cudaFree(c->cs_owned);
+        c->cs_cap_genes = std::max<size_t>(ng, 1); c->cs_cap_refs = std::max(c->cs_cap_refs, std::max<size_t>(nr, 1));
         CU_TRY(cudaMalloc(&c->cs_off, 8 * c->cs_cap_genes));
         CU_TRY(cudaMalloc(&c->cs_eoff, 4 * (c->cs_cap_genes + 1)));
         CU_TRY(cudaMalloc(&c->cs_strand, c->cs_cap_genes));
+        CU_TRY(cudaMalloc(&c->cs_owned, c->cs_cap_genes));
         CU_TRY(cudaMalloc(&c->cs_len, 4 * c->cs_cap_refs));
         CU_TRY(cudaMalloc(&c->cs_slot, 4 * c->cs_cap_refs));
-        CU_TRY(cudaMalloc(&c->cs_out, 8 * (3 * c->cs_cap_genes + std::max<size_t>(ne, 1))));
-        CU_TRY(cudaMalloc(&c->cs_ends, 16 * c->cs_cap_genes));
+        CU_TRY(cudaMalloc(&c->cs_out, 8 * (5 * c->cs_cap_genes + std::max<size_t>(ne, 1))));   // mean | std | cv | exon_cv | five | three
     }
     unsigned long long* d_off = c->cs_off; uint32_t *d_eoff = c->cs_eoff, *d_len = c->cs_len, *d_slot = c->cs_slot; uint8_t* d_strand = c->cs_strand;
-    double* d_out = c->cs_out; unsigned long long* d_ends = c->cs_ends;
+    double* d_out = c->cs_out;
+    double* d_mean = d_out; double* d_std = d_out + c->cs_cap_genes; double* d_cv = d_std + c->cs_cap_genes;
+    double* d_ecv = d_cv + c->cs_cap_genes;
+    unsigned long long* d_ends = reinterpret_cast<unsigned long long*>(d_ecv + std::max<size_t>(ne, 1));
+    c->cs_ends = d_ends;
     CU_TRY(cudaMemcpyAsync(d_off, q->gene_cov_off, 8 * ng, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_eoff, q->gene_exon_off, 4 * (ng + 1), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_strand, q->gene_strand, ng, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_len, q->exon_len, 4 * nr, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_slot, q->exon_slot, 4 * nr, cudaMemcpyHostToDevice, st));
+    const uint8_t* d_owned = nullptr;
+    if (q->gene_owned) { CU_TRY(cudaMemcpyAsync(c->cs_owned, q->gene_owned, ng, cudaMemcpyHostToDevice, st)); d_owned = c->cs_owned; }
     if (c->cov_len && c->cfg.collect_coverage)
         c->launches += launch_coverage_scan(c->acc.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
     else
         CU_TRY(cudaMemsetAsync(c->d_cov, 0, 4ull * (c->cov_len + 1), st));
-    double* d_mean = d_out; double* d_std = d_out + c->cs_cap_genes; double* d_cv = d_std + c->cs_cap_genes;
-    double* d_ecv = d_cv + c->cs_cap_genes;
     c->launches += launch_coverage_stats(c->d_cov, (uint32_t)ng, d_off, d_eoff, d_strand, d_len, d_slot, q->coverage_mask, q->bias_offset,
                                          q->bias_window, q->bias_gene_length, d_mean, d_std, d_cv, d_ends, d_ends + c->cs_cap_genes,
-                                         d_ecv, (uint32_t)ne, st);
+                                         d_ecv, (uint32_t)ne, d_owned, !d_owned || c->part_rank == 0, st);
+    if (d_owned && c->comm) {   // owner-gather as a bitwise sum: every value has exactly one non-zero contributor
+        if (ng < c->cs_cap_genes) {            // the unused tails of the five per-gene arrays travel too: keep them defined
+            for (int k = 0; k < 3; ++k) CU_TRY(cudaMemsetAsync(d_out + k * c->cs_cap_genes + ng, 0, 8 * (c->cs_cap_genes - ng), st));
+            for (int k = 0; k < 2; ++k) CU_TRY(cudaMemsetAsync(d_ends + k * c->cs_cap_genes + ng, 0, 8 * (c->cs_cap_genes - ng), st));
+        }
+        NcclApi& N = nccl_api();
+        NCCL_TRY(N.AllReduce(d_out, d_out, 5 * c->cs_cap_genes + std::max<size_t>(ne, 1), ncclUint64, ncclSum, c->comm, st));
+    }
     CU_TRY(cudaMemcpyAsync(out->gene_mean, d_mean, 8 * ng, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out->gene_std, d_std, 8 * ng, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(out->gene_cv, d_cv, 8 * ng, cudaMemcpyDeviceToHost, st));
@@ -841,11 +908,60 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
     return RSQ_OK;
 }
 
+int rsq_set_partition(rsq_ctx* ctx, uint32_t rank, uint32_t world) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RSQ_ERR_INVALID;
+    if (!world || rank >= world || world > 4096) { c->err = "bad partition rank / world"; return RSQ_ERR_INVALID; }
+    if (c->comm && (rank != c->part_rank || world != c->part_world)) { c->err = "the partition is fixed by rsq_comm_init"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    if (world != c->part_world || !c->d_found) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_found);
+        c->d_found = nullptr;
+        CU_TRY(cudaMalloc(&c->d_found, 8ull * world));
+    }
+    c->part_rank = rank; c->part_world = world;
+    c->found_valid = false;
+    return RSQ_OK;
+}
+
+static int ensure_export_buffer(Ctx* c) {
+    const size_t words = export_count_words(c->n_genes, c->n_exons, sample_quota(c));
+    if (words != c->export_words || !c->d_export) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_export);
+        c->d_export = nullptr;
+        CU_TRY(cudaMalloc(&c->d_export, 8ull * words));
+        c->export_words = words;
+    }
+    return RSQ_OK;
+}
+
+int rsq_export_sample_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !d_words || !n_words || !c->have_ann) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    if (!c->d_found) { int rc = rsq_set_partition(ctx, c->part_rank, c->part_world); if (rc != RSQ_OK) return rc; }
+    Accum a = c->acc;
+    if (!sample_quota(c)) a.sample_count = nullptr;
+    c->launches += launch_pack_sample_counts(a, c->part_rank, c->part_world, c->d_found, c->stream);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    c->found_valid = true;             // ... once the caller has reduced it
+    *d_words = reinterpret_cast<uint64_t*>(c->d_found);
+    *n_words = c->part_world;
+    return RSQ_OK;
+}
+
 int rsq_export_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !d_words || !n_words || !c->have_ann) return RSQ_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->cfg.device));
-    c->launches += launch_pack_counts(c->acc, c->n_genes, c->n_exons, c->d_export, c->stream);
+    int rc = ensure_export_buffer(c);
+    if (rc != RSQ_OK) return rc;
+    const unsigned long long quota = sample_quota(c);
+    if (quota && c->part_world > 1 && !c->found_valid) { c->err = "rsq_export_sample_counts (and its all-reduce) must precede rsq_export_counts"; return RSQ_ERR_INVALID; }
+    c->launches += launch_pack_counts(c->acc, c->n_genes, c->n_exons, quota, c->part_world > 1 ? c->d_found : nullptr, c->part_rank, c->part_world,
+                                      c->d_export, c->stream);
     CU_TRY(cudaStreamSynchronize(c->stream));
     *d_words = reinterpret_cast<uint64_t*>(c->d_export);
     *n_words = c->export_words;
@@ -854,10 +970,60 @@ int rsq_export_counts(rsq_ctx* ctx, uint64_t** d_words, size_t* n_words) {
 
 int rsq_import_counts(rsq_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (!c || !c->have_ann) return RSQ_ERR_INVALID;
+    if (!c || !c->have_ann || !c->d_export) return RSQ_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->cfg.device));
-    c->launches += launch_unpack_counts(c->acc, c->n_genes, c->n_exons, c->d_export, c->stream);
+    c->launches += launch_unpack_counts(c->acc, c->n_genes, c->n_exons, sample_quota(c), c->d_export, c->stream);
     CU_TRY(cudaStreamSynchronize(c->stream));
+    return RSQ_OK;
+}
+
+int rsq_comm_unique_id(uint8_t id[RSQ_COMM_ID_BYTES]) {
+    NcclApi& N = nccl_api();
+    if (!id) return RSQ_ERR_INVALID;
+    if (!N.handle) { g_create_error = N.why; return RSQ_ERR_NO_DEVICE; }
+    ncclUniqueId u;
+    const ncclResult_t r = N.GetUniqueId(&u);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + N.GetErrorString(r); return RSQ_ERR_CUDA; }
+    memcpy(id, &u, RSQ_COMM_ID_BYTES);
+    return RSQ_OK;
+}
+
+int rsq_comm_init(rsq_ctx* ctx, const uint8_t id[RSQ_COMM_ID_BYTES], uint32_t rank, uint32_t world) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !id) return RSQ_ERR_INVALID;
+    if (c->comm) { c->err = "communicator already attached"; return RSQ_ERR_INVALID; }
+    NcclApi& N = nccl_api();
+    if (!N.handle) { c->err = N.why; return RSQ_ERR_NO_DEVICE; }
+    int rc = rsq_set_partition(ctx, rank, world);
+    if (rc != RSQ_OK) return rc;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    ncclUniqueId u;
+    memcpy(&u, id, RSQ_COMM_ID_BYTES);
+    NCCL_TRY(N.CommInitRank(&c->comm, (int)world, u, (int)rank));
+    return RSQ_OK;
+}
+
+// The whole end-of-run exchange on the ctx stream: sample counts -> all-reduce -> count vector (with the kept samples at their
+// global ranks) -> all-reduce -> fold back.  No host synchronisation: rsq_finalize's is the first one.
+int rsq_exchange(rsq_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann) return RSQ_ERR_INVALID;
+    if (!c->comm) { c->err = "rsq_exchange needs rsq_comm_init"; return RSQ_ERR_INVALID; }
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));      // every submit's copy has been consumed by kernels queued on c->stream
+    NcclApi& N = nccl_api();
+    int rc = ensure_export_buffer(c);
+    if (rc != RSQ_OK) return rc;
+    const unsigned long long quota = sample_quota(c);
+    if (quota) {
+        c->launches += launch_pack_sample_counts(c->acc, c->part_rank, c->part_world, c->d_found, c->stream);
+        NCCL_TRY(N.AllReduce(c->d_found, c->d_found, c->part_world, ncclUint64, ncclSum, c->comm, c->stream));
+        c->found_valid = true;
+    }
+    c->launches += launch_pack_counts(c->acc, c->n_genes, c->n_exons, quota, c->d_found, c->part_rank, c->part_world, c->d_export, c->stream);
+    NCCL_TRY(N.AllReduce(c->d_export, c->d_export, c->export_words, ncclUint64, ncclSum, c->comm, c->stream));
+    c->launches += launch_unpack_counts(c->acc, c->n_genes, c->n_exons, quota, c->d_export, c->stream);
+    CU_TRY(cudaGetLastError());
     return RSQ_OK;
 }
 

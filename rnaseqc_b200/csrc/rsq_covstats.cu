@@ -77,14 +77,25 @@ coverage_stats_kernel(const unsigned int* __restrict__ cov, uint32_t n_genes, co
                       const uint32_t* __restrict__ exon_len, const uint32_t* __restrict__ exon_slot, uint32_t mask, int bias_offset,
                       int bias_window, uint32_t bias_gene_length, double* __restrict__ gene_mean, double* __restrict__ gene_std,
                       double* __restrict__ gene_cv, unsigned long long* __restrict__ five_end, unsigned long long* __restrict__ three_end,
-                      double* __restrict__ exon_cv) {
+                      double* __restrict__ exon_cv, const uint8_t* __restrict__ gene_owned) {
     __shared__ unsigned long long s_u64[kThreads / 32];
     __shared__ double s_win[2][kMaxWindow];
     const uint32_t g = blockIdx.x;
     if (g >= n_genes) return;
     const uint32_t e0 = gene_exon_off[g], e1 = gene_exon_off[g + 1];
+    if (gene_owned && !gene_owned[g]) {
+        // another partition owns this gene's reads (rsq_transcripts.gene_owned): all-zero bits, so that the u64 sum over the
+        // partitions is the owner's value
+        for (uint32_t e = e0 + threadIdx.x; e < e1; e += kThreads) exon_cv[exon_slot[e]] = 0.0;
+        if (threadIdx.x == 0) { gene_mean[g] = 0.0; gene_std[g] = 0.0; gene_cv[g] = 0.0; five_end[g] = 0ull; three_end[g] = 0ull; }
+        return;
+    }
     const unsigned int* tc = cov + gene_cov_off[g];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (gene_owned) {   // the slots this gene does not write below must read "no entry" (NaN) whatever the prefill of this partition was
+        for (uint32_t e = e0 + threadIdx.x; e < e1; e += kThreads) exon_cv[exon_slot[e]] = CUDART_NAN;
+        __syncthreads();
+    }
 
     // ---- per-exon masked statistics (one warp per exon), src/Metrics.cpp:280-305 ---------------------------------------
     unsigned long long T = 0;
@@ -219,13 +230,17 @@ __global__ void fill_nan_kernel(double* p, uint32_t n) {
 int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsigned long long* gene_cov_off, const uint32_t* gene_exon_off,
                           const uint8_t* gene_strand, const uint32_t* exon_len, const uint32_t* exon_slot, uint32_t mask, int bias_offset,
                           int bias_window, uint32_t bias_gene_length, double* gene_mean, double* gene_std, double* gene_cv,
-                          unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons, cudaStream_t stream) {
+                          unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons,
+                          const uint8_t* gene_owned, bool nan_prefill, cudaStream_t stream) {
     int n = 0;
-    if (n_exons) { fill_nan_kernel<<<(n_exons + 255) / 256, 256, 0, stream>>>(exon_cv, n_exons); ++n; }
+    if (n_exons) {
+        if (nan_prefill) { fill_nan_kernel<<<(n_exons + 255) / 256, 256, 0, stream>>>(exon_cv, n_exons); ++n; }
+        else cudaMemsetAsync(exon_cv, 0, 8ull * n_exons, stream);       // partitions other than the first: zero bits
+    }
     if (n_genes) {
         coverage_stats_kernel<<<n_genes, kThreads, 0, stream>>>(cov, n_genes, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask,
                                                               bias_offset, bias_window, bias_gene_length, gene_mean, gene_std, gene_cv,
-                                                              five_end, three_end, exon_cv);
+                                                              five_end, three_end, exon_cv, gene_owned);
         ++n;
     }
     return n;

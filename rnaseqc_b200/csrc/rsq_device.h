@@ -173,8 +173,12 @@ int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned l
 size_t coverage_scan_scratch_elems(unsigned long long n);
 int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap, unsigned long long* new_tab,
                   unsigned long long new_cap, unsigned int* error_flag, cudaStream_t stream);
-int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* out, cudaStream_t stream);
-int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* in, cudaStream_t stream);
+// end-of-run exchange of a coordinate-partitioned run (include/rsq_b200.h): `quota` = fragment_samples when the sampler is on, else 0
+size_t export_count_words(uint32_t n_genes, uint32_t n_exons, unsigned long long quota);
+int launch_pack_sample_counts(const Accum& acc, uint32_t rank, uint32_t world, unsigned long long* out, cudaStream_t stream);
+int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* found, uint32_t rank,
+                       uint32_t world, unsigned long long* out, cudaStream_t stream);
+int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* in, cudaStream_t stream);
 int launch_combine_exon(const Accum& acc, uint32_t n_exons, unsigned long long* whole_out, unsigned long long* frac_out, cudaStream_t stream);
 // BED mode, after launch_hot_path of the same batch: owners publish, seconds test, samples are ranked in stream order
 int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsigned int* scan_scratch, cudaStream_t stream);
@@ -186,6 +190,7 @@ int launch_sample_histogram(const unsigned int* vals, unsigned long long n, unsi
 int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsigned long long* gene_cov_off, const uint32_t* gene_exon_off,
                           const uint8_t* gene_strand, const uint32_t* exon_len, const uint32_t* exon_slot, uint32_t mask, int bias_offset,
                           int bias_window, uint32_t bias_gene_length, double* gene_mean, double* gene_std, double* gene_cv,
-                          unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons, cudaStream_t stream);
+                          unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons,
+                          const uint8_t* gene_owned, bool nan_prefill, cudaStream_t stream);
 
 }  // namespace rsqd

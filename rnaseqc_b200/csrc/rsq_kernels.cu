@@ -736,9 +736,29 @@ __global__ void rehash_kernel(const unsigned long long* __restrict__ old_tab, un
 }
 
 // ---- count vector export for the NVLink all-reduce: counters | gene_reads | gene_unique | gene_fragments | exon_whole |
-//      exon_frac >> 32 | exon_frac & 0xffffffff   (the split keeps the u64 sum exact across ranks)
-__global__ void pack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* __restrict__ out) {
-    const unsigned long long total = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull;
+//      exon_frac >> 32 | exon_frac & 0xffffffff | gc_hist[100] | samples found | kept fragment-size samples, two per word
+//      (the split keeps the u64 sum exact across ranks)
+// Fragment-size samples (first-N cut across partitions, src/RNASeQC.cpp:372, src/Expression.cpp:532): `found` holds the sample
+// counts of all partitions (all-reduced phase-1 buffer; null = one partition).  This partition's k-th sample has global rank
+// before + k, before = samples of the partitions ahead of it in the stream; it is kept when that rank is below the quota.
+__device__ __forceinline__ void sample_window(const unsigned long long* __restrict__ found, uint32_t rank, uint32_t world, unsigned long long own,
+                                              unsigned long long quota, unsigned long long& before, unsigned long long& kept) {
+    before = 0ull;
+    if (found) for (uint32_t r = 0; r < rank && r < world; ++r) before += found[r];
+    const unsigned long long have = own < quota ? own : quota;            // sample_vals holds at most `quota` of them
+    kept = before >= quota ? 0ull : (quota - before < have ? quota - before : have);
+}
+__global__ void pack_sample_counts_kernel(const Accum acc, uint32_t rank, uint32_t world, unsigned long long* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < world) out[i] = (i == rank && acc.sample_count) ? *acc.sample_count : 0ull;
+}
+__global__ void pack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* __restrict__ found,
+                                   uint32_t rank, uint32_t world, unsigned long long* __restrict__ out) {
+    const unsigned long long fixed = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull;
+    const unsigned long long total = fixed + 1ull + (quota + 1ull) / 2ull;
+    unsigned long long before = 0ull, kept = 0ull;
+    const unsigned long long own = (quota && acc.sample_count) ? *acc.sample_count : 0ull;
+    if (quota) sample_window(found, rank, world, own, quota, before, kept);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long j = i, v;
         if (j < RSQ_N_COUNTERS) v = acc.counters[j];
@@ -748,12 +768,21 @@ __global__ void pack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n
         else if ((j -= n_genes) < n_exons) v = acc.exon_whole[j];
         else if ((j -= n_exons) < n_exons) v = acc.exon_fhi[j];
         else if ((j -= n_exons) < n_exons) v = acc.exon_flo[j];
-        else { j -= n_exons; v = acc.gc_hist ? acc.gc_hist[j] : 0ull; }      // 100 GC-content bins (zeros without a reference)
+        else if ((j -= n_exons) < 100ull) v = acc.gc_hist ? acc.gc_hist[j] : 0ull;      // 100 GC-content bins (zeros without a reference)
+        else if ((j -= 100ull) == 0ull) v = own;                                           // samples found (may exceed the quota)
+        else {
+            j -= 1ull;
+            const unsigned long long k0 = 2ull * j, k1 = k0 + 1ull;                        // global ranks of the word's two halves
+            const unsigned long long a = (k0 >= before && k0 - before < kept) ? acc.sample_vals[k0 - before] : 0u;
+            const unsigned long long b = (k1 < quota && k1 >= before && k1 - before < kept) ? acc.sample_vals[k1 - before] : 0u;
+            v = a | (b << 32);
+        }
         out[i] = v;
     }
 }
-__global__ void unpack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* __restrict__ in) {
-    const unsigned long long total = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull;
+__global__ void unpack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* __restrict__ in) {
+    const unsigned long long fixed = RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull;
+    const unsigned long long total = fixed + 1ull + (quota + 1ull) / 2ull;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long j = i;
         if (j < RSQ_N_COUNTERS) acc.counters[j] = in[i];
@@ -763,7 +792,13 @@ __global__ void unpack_counts_kernel(const Accum acc, uint32_t n_genes, uint32_t
         else if ((j -= n_genes) < n_exons) acc.exon_whole[j] = in[i];
         else if ((j -= n_exons) < n_exons) acc.exon_fhi[j] = in[i];
         else if ((j -= n_exons) < n_exons) acc.exon_flo[j] = in[i];
-        else { j -= n_exons; if (acc.gc_hist) acc.gc_hist[j] = in[i]; }
+        else if ((j -= n_exons) < 100ull) { if (acc.gc_hist) acc.gc_hist[j] = in[i]; }
+        else if ((j -= 100ull) == 0ull) { if (quota && acc.sample_count) *acc.sample_count = in[i]; }
+        else if (quota) {
+            j -= 1ull;
+            acc.sample_vals[2ull * j] = (unsigned int)in[i];
+            if (2ull * j + 1ull < quota) acc.sample_vals[2ull * j + 1ull] = (unsigned int)(in[i] >> 32);
+        }
     }
 }
 // (whole, frac>>32 sums, frac&0xffffffff sums) -> canonical (whole, frac) with carries resolved
@@ -1003,12 +1038,20 @@ int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap,
     return 1;
 }
 
-int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long* out, cudaStream_t stream) {
-    pack_counts_kernel<<<148 * 4, 256, 0, stream>>>(acc, n_genes, n_exons, out);
+size_t export_count_words(uint32_t n_genes, uint32_t n_exons, unsigned long long quota) {
+    return (size_t)(RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull + 1ull + (quota + 1ull) / 2ull);
+}
+int launch_pack_sample_counts(const Accum& acc, uint32_t rank, uint32_t world, unsigned long long* out, cudaStream_t stream) {
+    pack_sample_counts_kernel<<<(world + 63) / 64, 64, 0, stream>>>(acc, rank, world, out);
     return 1;
 }
-int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, const unsigned long long* in, cudaStream_t stream) {
-    unpack_counts_kernel<<<148 * 4, 256, 0, stream>>>(acc, n_genes, n_exons, in);
+int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* found, uint32_t rank,
+                       uint32_t world, unsigned long long* out, cudaStream_t stream) {
+    pack_counts_kernel<<<148 * 4, 256, 0, stream>>>(acc, n_genes, n_exons, quota, found, rank, world, out);
+    return 1;
+}
+int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* in, cudaStream_t stream) {
+    unpack_counts_kernel<<<148 * 4, 256, 0, stream>>>(acc, n_genes, n_exons, quota, in);
     return 1;
 }
 

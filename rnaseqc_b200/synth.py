@@ -564,3 +564,128 @@ def write_bam(ann: SynthAnnotation, reads: SynthReads, path: str, level: int = 1
                           p(arrs["ls"]), p(arrs["il"]), 150, level)
     if rc != 0:
         raise RuntimeError(f"rsqh_write_bam failed: {rc}")
+
+
+def write_bam_python(ann: SynthAnnotation, reads: SynthReads, path: str, level: int = 1, l_qseq: int = 150, chunk: int = 100_000) -> None:
+    """The same BAM as write_bam, byte for byte before compression, written with numpy + zlib only: `bench.py --impl reference`
+    uses it so that the reference arm loads none of this repo's native libraries."""
+    import struct
+    import zlib
+    c = lambda t: np.ascontiguousarray(t.cpu().numpy().astype(np.int64))
+    tid, pos, mtid, mpos, isize, flag, mapq = c(reads.contig), c(reads.pos), c(reads.mate_contig), c(reads.mpos), c(reads.isize), c(reads.flag), c(reads.mapq)
+    nm, aux, name_id, nb, ls, il = c(reads.nm), c(reads.aux), c(reads.name_id), c(reads.n_blocks), c(reads.lead_soft), c(reads.ins_len)
+    bs_all, bl_all = c(reads.blk_start), c(reads.blk_len)
+    stride = bs_all.shape[1]
+
+    out = open(path, "wb")
+    pending = bytearray()
+
+    def bgzf_block(data: bytes) -> bytes:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(data) + co.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+    def put(data, flush=False):
+        pending.extend(data)
+        lim = 0xff00
+        k = 0
+        while len(pending) - k >= lim or (flush and k < len(pending)):
+            out.write(bgzf_block(bytes(pending[k:k + lim])))
+            k += lim
+        del pending[:min(k, len(pending))]
+
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in zip(ann.contig_names, ann.contig_lens))
+    hdr = b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(ann.contig_names))
+    for n, l in zip(ann.contig_names, ann.contig_lens):
+        hdr += struct.pack("<i", len(n) + 1) + n.encode() + b"\x00" + struct.pack("<i", int(l))
+    put(hdr)
+
+    seq_qual = np.concatenate([np.full((l_qseq + 1) // 2, 0x11, np.uint8), np.full(l_qseq, ord("F") - 33, np.uint8)])
+    for a in range(0, reads.n, chunk):
+        b = min(reads.n, a + chunk)
+        n = b - a
+        sl = slice(a, b)
+        bs, bl, k_nb, k_ls = bs_all[sl], bl_all[sl], nb[sl], ls[sl]
+        # CIGAR: [S] M (I|D|N M)*
+        max_ops = 2 * stride
+        ops = np.zeros((n, max_ops), np.uint32)
+        has_s = (k_ls > 0).astype(np.int64)
+        ops[np.arange(n)[has_s > 0], 0] = ((k_ls[has_s > 0] << 4) | 4).astype(np.uint32)
+        ref_end = pos[sl].copy()
+        for j in range(stride):
+            m = k_nb > j
+            if not m.any():
+                break
+            idx = np.nonzero(m)[0]
+            ops[idx, has_s[idx] + 2 * j] = ((bl[idx, j] << 4) | 0).astype(np.uint32)
+            ref_end[idx] = bs[idx, j] - 1 + bl[idx, j]
+            if j + 1 < stride:
+                m2 = k_nb > j + 1
+                idx2 = np.nonzero(m2)[0]
+                if len(idx2):
+                    gap = bs[idx2, j + 1] - (bs[idx2, j] + bl[idx2, j])
+                    op = np.where(gap == 0, (il[sl][idx2] << 4) | 1, np.where(gap <= 3, (gap << 4) | 2, (gap << 4) | 3))
+                    ops[idx2, has_s[idx2] + 2 * j + 1] = op.astype(np.uint32)
+        n_cig = has_s + np.where(k_nb > 0, 2 * k_nb - 1, 0)
+        names = np.char.add("r", name_id[sl].astype(str)).astype("S")
+        l_name = np.char.str_len(names) + 1
+        wname = names.dtype.itemsize + 1
+        name_bytes = np.zeros((n, wname), np.uint8)
+        name_bytes[:, :wname - 1] = np.frombuffer(names.tobytes(), np.uint8).reshape(n, wname - 1)
+        has_nm = (aux[sl] & AUX_HAS_NM) != 0
+        has_ch = (aux[sl] & AUX_CHIMERIC_TAG) != 0
+        size = 32 + l_name + 4 * n_cig + len(seq_qual) + 4 * has_nm + 4 * has_ch
+        off = np.concatenate([[0], np.cumsum(size + 4)])
+        buf = np.zeros(int(off[-1]) + 256, np.uint8)
+        # bin (reg2bin of [pos, max(ref_end, pos + 1)))
+        beg, end = pos[sl], np.maximum(ref_end, pos[sl] + 1) - 1
+        bin_ = np.zeros(n, np.int64)
+        done = np.zeros(n, bool)
+        for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+            hit = ~done & ((beg >> shift) == (end >> shift))
+            bin_[hit] = base + (beg[hit] >> shift)
+            done |= hit
+        fixed = np.zeros(n, np.dtype([("block_size", "<i4"), ("tid", "<i4"), ("pos", "<i4"), ("l_name", "u1"), ("mapq", "u1"), ("bin", "<u2"),
+                                      ("n_cig", "<u2"), ("flag", "<u2"), ("l_seq", "<i4"), ("mtid", "<i4"), ("mpos", "<i4"), ("isize", "<i4")]))
+        fixed["block_size"] = size; fixed["tid"] = tid[sl]; fixed["pos"] = pos[sl]; fixed["l_name"] = l_name; fixed["mapq"] = mapq[sl]
+        fixed["bin"] = bin_; fixed["n_cig"] = n_cig; fixed["flag"] = flag[sl]; fixed["l_seq"] = l_qseq; fixed["mtid"] = mtid[sl]
+        fixed["mpos"] = mpos[sl]; fixed["isize"] = isize[sl]
+
+        def scatter(at, rows):
+            w = rows.shape[1]
+            buf[(at[:, None] + np.arange(w)[None, :]).ravel()] = rows.ravel()
+
+        # written in record order of the fields, so that the zero padding of a variable-width field is overwritten by the next one
+        scatter(off[:-1], np.frombuffer(fixed.tobytes(), np.uint8).reshape(n, 36))
+        p = off[:-1] + 36
+        scatter(p, name_bytes)
+        p = p + l_name
+        scatter(p, np.frombuffer(ops.astype("<u4").tobytes(), np.uint8).reshape(n, 4 * max_ops))
+        p = p + 4 * n_cig
+        scatter(p, np.broadcast_to(seq_qual, (n, len(seq_qual))))
+        p = p + len(seq_qual)
+        tail = np.zeros((n, 8), np.uint8)                       # aux fields; the spill of the last record lands in the slack of `buf`
+        nm_rows = np.stack([np.full(n, ord("N")), np.full(n, ord("M")), np.full(n, ord("C")), nm[sl] & 0xff], axis=1).astype(np.uint8)
+        ch_rows = np.broadcast_to(np.frombuffer(b"chA1", np.uint8), (n, 4))
+        tail[has_nm, 0:4] = nm_rows[has_nm]
+        only_ch = has_ch & ~has_nm
+        tail[only_ch, 0:4] = ch_rows[only_ch]
+        both = has_ch & has_nm
+        tail[both, 4:8] = ch_rows[both]
+        # a record's aux bytes may be 0, 4 or 8 long: write 8 and let the NEXT record's fixed part overwrite the rest — so write the
+        # tails first in a second pass over a copy of the starts
+        keep = buf.copy()
+        scatter(p, tail)
+        # restore everything that belongs to following records
+        w_aux = 4 * has_nm.astype(np.int64) + 4 * has_ch.astype(np.int64)
+        for extra in (0, 4):
+            sel = w_aux <= extra
+            if sel.any():
+                at = p[sel] + extra
+                idx = (at[:, None] + np.arange(4)[None, :]).ravel()
+                buf[idx] = keep[idx]
+        put(buf[:int(off[-1])].tobytes())
+    put(b"", flush=True)
+    out.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))   # BGZF EOF marker
+    out.close()

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(libs, which):
         assert hasattr(lib, sym), f"{libs[which]} does not export {sym}"
     lib.rsq_backend.restype = ctypes.c_char_p
     lib.rsq_abi_version.restype = ctypes.c_uint32
-    assert lib.rsq_abi_version() == 2
+    assert lib.rsq_abi_version() == 3
     assert lib.rsq_backend().decode() == {"product": "cuda-sm_100a", "oracle": "oracle-cpu"}[which]
 
 
