@@ -12,7 +12,7 @@ filter/intersect/accumulate kernel over every record, the end-of-run exchange ov
 rsq_exchange — count vectors, ordered first-N fragment-size cut), integration of the coverage difference array, the per-gene
 coverage / 3' bias statistics of the genes the rank owns (gathered over NCCL), and the read-back of every result table.
 `value` = records processed by all ranks / step time with the records already resident in HBM; `e2e` = the same through
-rsq_submit_packed with pinned HOST buffers (H2D inside the timed region).  One JSON line on stdout (rank 0).
+rsq_submit_compact (16-byte wire format) with pinned HOST buffers (H2D inside the timed region).  One JSON line on stdout (rank 0).
 
 At N > 1 a PRE-FLIGHT runs first: one 2 M-record sorted stream is split at gene-free cuts, every rank runs its slice, the
 exchange runs, and every rank's results must equal bit for bit the single-GPU run of the whole stream on rank 0 and the CPU
@@ -260,12 +260,19 @@ def preflight(be, ann, sa, device_index, rank, world, with_bed, n_records=2_000_
             octx.close()
             for k in list(RESULT_FIELDS) + ["taken"]:
                 assert np.array_equal(osnap[k], want[0][k]), f"pre-flight: single-GPU run differs from the CPU oracle in {k}"
-            for k in STAT_FIELDS:      # block-reduced fp64 on the device vs sequential fp64: 1e-9 (tests/test_gpu_parity.py), u64 ends exact
-                a, b = osnap[k].view(np.float64 if k not in ("five_end", "three_end") else np.uint64), want[0][k].view(np.float64 if k not in ("five_end", "three_end") else np.uint64)
-                if k in ("five_end", "three_end"):
-                    assert np.array_equal(a, b), f"pre-flight: {k} differs from the CPU oracle"
-                else:
-                    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=1e-9, atol=0), f"pre-flight: {k} differs from the CPU oracle"
+            # block-reduced fp64 from exact integer moments on the device vs the reference's sequential fp64: same rule as
+            # tests/test_gpu_parity.py::test_coverage_statistics_match_oracle (1e-9 relative, a flat profile's std is exactly 0 on
+            # the device and rounding noise in the reference); the u64 bias ends and the NaN pattern exactly
+            f64 = lambda snap, k: snap[k].view(np.float64)
+            for k in ("five_end", "three_end"):
+                assert np.array_equal(osnap[k], want[0][k]), f"pre-flight: {k} differs from the CPU oracle"
+            g_mean, w_mean = f64(osnap, "gene_mean"), f64(want[0], "gene_mean")
+            assert np.array_equal(g_mean == -1.0, w_mean == -1.0) and np.allclose(w_mean, g_mean, rtol=1e-9, atol=0), "pre-flight: gene_mean differs from the CPU oracle"
+            assert np.allclose(f64(want[0], "gene_std"), f64(osnap, "gene_std"), rtol=1e-9, atol=1e-9 * np.maximum(np.abs(w_mean), 1e-300)), "pre-flight: gene_std differs from the CPU oracle"
+            a, b = f64(want[0], "gene_cv"), f64(osnap, "gene_cv")
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-9, atol=1e-9), "pre-flight: gene_cv differs from the CPU oracle"
+            a, b = f64(want[0], "exon_cv"), f64(osnap, "exon_cv")
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-9, atol=1e-9), "pre-flight: exon_cv differs from the CPU oracle"
             summary["vs_cpu_oracle"] = "integers bit-identical, coverage statistics within 1e-9"
     dist.broadcast_object_list(want, src=0)
     bad = [k for k in want[0] if not np.array_equal(want[0][k], mine[k])]
@@ -406,16 +413,33 @@ def run_ours(args):
             for a, b, lo in zip(bounds[:-1], bounds[1:], block_lo[:-1]):
                 off["block_off"][a:b] -= np.uint32(lo)
 
-            # compact wire format (rsq_read_packed: 32 B per record, no entry for whole-read blocks): packed once per chunk,
-            # outside the timed region, exactly as a decoder would hand the batches over
-            packed = []
-            try:
-                hb_np = np.frombuffer(h_blocks.numpy().reshape(-1).data, dtype=api.BLOCK_DTYPE)
+            hb_np = np.frombuffer(h_blocks.numpy().reshape(-1).data, dtype=api.BLOCK_DTYPE)
+            # the wire formats: every chunk is packed ONCE, outside the timed region, into page-locked memory — exactly as a
+            # decoder hands its batches over (the CLI's ingest workers pack while the previous batch is on the wire)
+            compact, packed = None, None
+            if args.e2e_format == "compact":        # rsq_batch16: 16-byte records + tile headers + dictionary + 32-bit blocks
+                try:
+                    cap = sum(api.compact_bound(b - a, hi - lo) for a, b, lo, hi in zip(bounds[:-1], bounds[1:], block_lo[:-1], block_lo[1:]))
+                    h_cp = torch.empty((cap + 64,), dtype=torch.uint8, pin_memory=True)
+                    cp_np = h_cp.numpy()
+                    compact, w = [], (-cp_np.ctypes.data) % 16
+                    for a, b, lo, hi in zip(bounds[:-1], bounds[1:], block_lo[:-1], block_lo[1:]):
+                        room = api.compact_bound(b - a, hi - lo)
+                        got = api.pack_compact(off[a:b], hb_np[lo:hi], cp_np[w:w + room])
+                        if got is None:
+                            compact = None
+                            break
+                        compact.append((cp_np.ctypes.data + w, got.nbytes))
+                        w += (got.nbytes + 15) & ~15          # the chunks lie back to back: what is not used of `room` is reused
+                except Exception as ex:
+                    log(f"[rank {rank}] compact wire format unavailable: {ex!r}")
+                    compact = None
+            if compact is None and args.e2e_format in ("compact", "packed"):   # rsq_read_packed: 32 B per record, implicit whole-read blocks
                 h_pk = torch.empty((n_reads, 32), dtype=torch.uint8, pin_memory=True)
                 h_pb = torch.empty((max(n_blocks, 1), 8), dtype=torch.uint8, pin_memory=True)
                 pk_np = np.frombuffer(h_pk.numpy().reshape(-1).data, dtype=api.PACKED_DTYPE)
                 pb_np = np.frombuffer(h_pb.numpy().reshape(-1).data, dtype=api.BLOCK_DTYPE)
-                w = 0
+                packed, w = [], 0
                 for a, b, lo, hi in zip(bounds[:-1], bounds[1:], block_lo[:-1], block_lo[1:]):
                     got = api.pack_records(off[a:b], hb_np[lo:hi], pk_np[a:b], pb_np[w:w + max(hi - lo, 1)])
                     if got is None:
@@ -423,13 +447,13 @@ def run_ours(args):
                         break
                     packed.append((a, b, w, len(got[1])))
                     w += len(got[1])
-            except Exception as ex:
-                log(f"[rank {rank}] packed wire format unavailable: {ex!r}")
-                packed = None
 
-            def step_e2e(use_packed):
+            def step_e2e(fmt):
                 ctx.reset()
-                if use_packed:
+                if fmt == "compact":
+                    for ptr, nbytes in compact:
+                        ctx.submit_compact_ptr(ptr, nbytes)
+                elif fmt == "packed":
                     for a, b, w0, nw in packed:
                         ctx.submit_packed_ptr(h_pk.data_ptr() + 32 * a, b - a, h_pb.data_ptr() + 8 * w0, nw)
                 else:
@@ -437,13 +461,13 @@ def run_ours(args):
                         ctx.submit_ptr(h_reads.data_ptr() + 48 * a, b - a, h_blocks.data_ptr() + 8 * lo, hi - lo)
                 return finish()
 
-            def time_e2e(use_packed):
+            def time_e2e(fmt):
                 for _ in range(max(1, min(args.warmup, 3) - 1)):
-                    r = step_e2e(use_packed)
+                    r = step_e2e(fmt)
                 barrier()
                 t0 = time.perf_counter()
                 for _ in range(args.e2e_steps):
-                    r = step_e2e(use_packed)
+                    r = step_e2e(fmt)
                 local = (time.perf_counter() - t0) / args.e2e_steps       # before the barrier: this rank's own time
                 barrier()
                 dt = (time.perf_counter() - t0) / args.e2e_steps
@@ -453,31 +477,27 @@ def run_ours(args):
                     dt = float(t.item())
                 got = snapshot(r, r.cov_stats)
                 bad = [k for k in ref_snap if not np.array_equal(ref_snap[k], got[k])]
-                assert not bad, f"e2e != resident in {bad}"
+                assert not bad, f"e2e ({fmt}) != resident in {bad}"
                 return dt, local
 
             d2h = 8 * (api.RSQ_N_COUNTERS + 3 * ann.n_genes + 2 * ann.n_exons) + 8 * (5 * len(res.cov_stats["gene_mean"]) + ann.n_exons)
-            if packed:
-                t_packed, t_local = time_e2e(True)
-                n_wire_blocks = sum(p[3] for p in packed)
-                h2d = int(32 * n_reads + 8 * n_wire_blocks)
-                e2e = {"value": total_records / t_packed, "unit": "reads/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": t_packed * 1e3, "steps": args.e2e_steps,
-                       "wire_format": "rsq_read_packed (32 B + 8 B per block of the records that are not one whole-read run)",
-                       "same_results_as_resident": True}
-                e2e_rank = {"e2e_ms": t_local * 1e3, "h2d_gb_per_s": h2d / t_local / 1e9}
-                if args.e2e_unpacked:
-                    t_plain, _ = time_e2e(False)
-                    e2e["unpacked"] = {"value": total_records / t_plain, "ms_per_step": t_plain * 1e3,
-                                       "h2d_bytes_per_step": int(48 * n_reads + 8 * n_blocks)}
-                del h_pk, h_pb
-            else:
-                t_plain, t_local = time_e2e(False)
-                h2d = int(48 * n_reads + 8 * n_blocks)
-                e2e = {"value": total_records / t_plain, "unit": "reads/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": t_plain * 1e3, "steps": args.e2e_steps,
-                       "wire_format": "rsq_read (48 B + 8 B per block)", "same_results_as_resident": True}
-                e2e_rank = {"e2e_ms": t_local * 1e3, "h2d_gb_per_s": h2d / t_local / 1e9}
+            fmt = "compact" if compact else ("packed" if packed else "plain")
+            wire = {"compact": lambda: int(sum(nb_ for _, nb_ in compact)),
+                    "packed": lambda: int(32 * n_reads + 8 * sum(p[3] for p in packed)),
+                    "plain": lambda: int(48 * n_reads + 8 * n_blocks)}
+            names = {"compact": "rsq_batch16 (16-byte records, tile headers, per-batch dictionary, 32-bit blocks, exception list; one copy per batch)",
+                     "packed": "rsq_read_packed (32 B + 8 B per block of the records that are not one whole-read run)",
+                     "plain": "rsq_read (48 B + 8 B per block)"}
+            t_e, t_local = time_e2e(fmt)
+            h2d = wire[fmt]()
+            e2e = {"value": total_records / t_e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": t_e * 1e3, "steps": args.e2e_steps, "wire_format": names[fmt], "wire_bytes_per_record": h2d / n_reads,
+                   "same_results_as_resident": True}
+            e2e_rank = {"e2e_ms": t_local * 1e3, "h2d_gb_per_s": h2d / t_local / 1e9}
+            for other in args.e2e_also:
+                if other != fmt and (other != "packed" or packed) and (other != "compact" or compact):
+                    t_o, _ = time_e2e(other)
+                    e2e[other] = {"value": total_records / t_o, "ms_per_step": t_o * 1e3, "h2d_bytes_per_step": wire[other]()}
             del h_reads, h_blocks
         except MemoryError as ex:  # pinned allocation can fail on a small host
             e2e = {"value": None, "unit": "reads/s", "error": repr(ex)}
@@ -687,7 +707,8 @@ def main():
                     help="records of the cpu_baseline leg (the oracle port does ~3 M records/s on one core: ~10 s)")
     ap.add_argument("--e2e-chunk", type=int, default=8_000_000)
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-unpacked", action="store_true", help="also time the 48-byte rsq_submit path")
+    ap.add_argument("--e2e-format", default="compact", choices=["compact", "packed", "plain"], help="wire format of the e2e leg")
+    ap.add_argument("--e2e-also", nargs="*", default=[], choices=["packed", "plain"], help="also time these formats (reported beside the headline one)")
     ap.add_argument("--cli-records", type=int, default=60_000_000,
                     help="records of the BAM the e2e_cli leg runs the product CLI on (N=1 only; 0 = skip)")
     ap.add_argument("--bed", action="store_true", help="also run the --bed fragment-size sampler (BASELINE.json configs[4])")

@@ -18,6 +18,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -113,6 +114,60 @@ typedef struct rsq_read_packed {
     uint8_t  n_blocks;
     uint8_t  filter_mask;
 } rsq_read_packed;
+
+/* ---- 16-byte wire format ("compact batch") --------------------------------------------------------------------------------------
+ * The end-to-end rate of this path is PCIe-bound, so bytes per record set it.  A compact batch is ONE contiguous
+ * buffer (one host->device copy per submit):  rsq_batch16 header | tiles | reads | combos | blocks | exception reads | exception blocks.
+ *   - records travel in tiles of 32 consecutive records; a tile header carries what its records share or what a data-parallel
+ *     expansion needs to know where a tile's variable-length parts start;
+ *   - a record is 16 bytes: the 64-bit read-name hash, its position as a 16-bit offset from the tile's lowest position, the mate
+ *     position and the insert size as signed 16-bit offsets, and a 16-bit index into the batch's DICTIONARY of the distinct
+ *     (flag, MAPQ, aux bits, read length, NM, block count, filter mask) combinations (a few thousand per batch in practice);
+ *   - aligned blocks of records that are not one whole-read run travel as one 32-bit word each (offset from the read start in the
+ *     high 21 bits, length in the low 11);
+ *   - whatever these fields cannot express (mate more than 32 kb away, an intron above 2 Mb, a block of 2048 bases or more,
+ *     another contig inside the tile, a 65,536th combination ...) travels as an EXCEPTION: the record's 16-byte slot carries
+ *     combo 0xFFFF and the full rsq_read (+ rsq_block entries) sits in the exception lists.  Results never depend on the format:
+ *     rsq_pack_compact refuses a batch with more than 1/8 exceptions and the caller falls back to rsq_submit_packed / rsq_submit.
+ * Workload of BASELINE.json: 21 bytes per record on the wire instead of 40 (rsq_read_packed) or 60 (rsq_read + rsq_block). */
+#define RSQ_BATCH16_MAGIC 0x36314252u   /* "RB16" */
+#define RSQ_COMBO_EXCEPTION 0xFFFFu
+typedef struct rsq_tile16 {
+    int32_t  base_pos;        /* lowest pos among the tile's non-exception records                                  */
+    uint32_t block_base;      /* first entry of the tile in `blocks` (explicit blocks of non-exception records)       */
+    uint32_t out_block_base;  /* first block of the tile in the expanded rsq_block array (implicit and exception
+                                 blocks included): lets every tile be expanded independently                          */
+    uint32_t exc_base;        /* first entry of the tile in the exception reads                                       */
+    int16_t  contig;          /* contig of every non-exception record of the tile                                     */
+    uint16_t reserved;
+    uint32_t reserved2;
+} rsq_tile16;                 /* 24 bytes per 32 records */
+typedef struct rsq_read16 {
+    uint64_t name_hash;
+    uint16_t dpos;            /* pos - tile.base_pos                                                                  */
+    int16_t  dmate;           /* mpos - pos                                                                           */
+    int16_t  isize;
+    uint16_t combo;           /* dictionary index, or RSQ_COMBO_EXCEPTION                                             */
+} rsq_read16;
+typedef struct rsq_combo16 {  /* one dictionary entry: field meaning as in rsq_read / rsq_read_packed                 */
+    uint16_t flag;
+    uint8_t  mapq;
+    uint8_t  aux;             /* RSQ_AUX_* incl. RSQ_AUX_IMPLICIT_BLOCK                                               */
+    uint16_t l_qseq;
+    uint16_t nm;
+    uint8_t  n_blocks;
+    uint8_t  filter_mask;
+    uint16_t reserved;
+    uint32_t reserved2;
+} rsq_combo16;                /* 16 bytes */
+typedef struct rsq_batch16 {  /* header of the buffer; every offset is in bytes from the start of the buffer, 16-byte aligned */
+    uint32_t magic, struct_size;
+    uint32_t n_reads, n_tiles, n_combos, n_blocks, n_exc, n_exc_blocks;
+    uint32_t total_blocks;    /* blocks of the expanded batch                                                         */
+    uint32_t reserved;
+    uint64_t off_tiles, off_reads, off_combos, off_blocks, off_exc, off_exc_blocks, total_bytes;
+} rsq_batch16;
+#define RSQ_BLOCK16_LEN_BITS 11u
 
 /* ---- run constants: the locals of main() the loop captures (src/RNASeQC.cpp:78-100) --------------------- */
 typedef struct rsq_config {
@@ -290,6 +345,8 @@ int rsq_submit_device(rsq_ctx* ctx, const rsq_read* d_reads, size_t n_reads, con
 /* Same as rsq_submit for a batch in the compact wire format: `blocks` holds, in record order, the blocks of every
  * record that does not carry RSQ_AUX_IMPLICIT_BLOCK. */
 int rsq_submit_packed(rsq_ctx* ctx, const rsq_read_packed* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks);
+/* Same for a compact batch (rsq_batch16 and what follows it in one buffer of `bytes` bytes, written by rsq_pack_compact). */
+int rsq_submit_compact(rsq_ctx* ctx, const void* batch, size_t bytes);
 int rsq_sync(rsq_ctx* ctx);
 
 /* Clears all accumulators (annotation and BED stay): a new sample / a new timed step. */
@@ -418,6 +475,111 @@ static inline int rsq_pack_records(const rsq_read* reads, size_t n_reads, const 
         }
     }
     *n_out_blocks = w;
+    return RSQ_OK;
+}
+
+/* Upper bound of the buffer rsq_pack_compact may need for a batch (exceptions are capped at n_reads / 8 + 32). */
+static inline size_t rsq_compact_bound(size_t n_reads, size_t n_blocks) {
+    const size_t n_tiles = (n_reads + 31) / 32, max_exc = n_reads / 8 + 32;
+    return 256 + 24 * n_tiles + 16 * n_reads + 16 * 65536 + 4 * n_blocks + 48 * max_exc + 8 * n_blocks + 7 * 16;
+}
+
+/* Packs one rsq_submit batch (block_off relative to `blocks`) into a compact batch at `out` (capacity `cap` bytes, 16-byte
+ * aligned; rsq_compact_bound says how much is enough).  `scratch` must hold 131072 uint32_t (the dictionary's hash table).
+ * Returns RSQ_OK and the bytes written, or RSQ_ERR_INVALID when the batch does not suit the format (too many exceptions, too
+ * many blocks for 32-bit offsets, capacity): the caller then uses rsq_submit_packed / rsq_submit. */
+static inline int rsq_pack_compact(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks, void* out, size_t cap,
+                                   uint32_t* scratch, size_t* bytes_out) {
+    const size_t n_tiles = (n_reads + 31) / 32, max_exc = n_reads / 8 + 32;
+    unsigned char* base = (unsigned char*)out;
+    rsq_batch16* H = (rsq_batch16*)out;
+    size_t off = 0, t, i, b, n_combos = 0, n_xb = 0, n_exc = 0, n_eb = 0, out_blocks = 0;
+    rsq_tile16* tiles; rsq_read16* R; rsq_combo16* D; uint32_t* XB; rsq_read* E; rsq_block* EB;
+    if (n_reads >= 0xffffffffu || n_blocks >= 0xffffffffu || cap < rsq_compact_bound(n_reads, n_blocks) || ((size_t)out & 15u)) return RSQ_ERR_INVALID;
+#define RSQ_P16_ALIGN(x) (((x) + 15u) & ~(size_t)15u)
+    off = RSQ_P16_ALIGN(sizeof(rsq_batch16));
+    tiles = (rsq_tile16*)(base + off); H->off_tiles = off; off = RSQ_P16_ALIGN(off + 24 * n_tiles);
+    R = (rsq_read16*)(base + off); H->off_reads = off; off = RSQ_P16_ALIGN(off + 16 * n_reads);
+    D = (rsq_combo16*)(base + off); H->off_combos = off;
+    /* the dictionary grows while packing: blocks and exceptions are staged behind its maximum size and moved up at the end */
+    XB = (uint32_t*)(base + RSQ_P16_ALIGN(off + 16 * 65536));
+    E = (rsq_read*)((unsigned char*)XB + RSQ_P16_ALIGN(4 * n_blocks));
+    EB = (rsq_block*)((unsigned char*)E + RSQ_P16_ALIGN(48 * max_exc));
+    for (i = 0; i < 131072; ++i) scratch[i] = 0xffffffffu;
+    for (t = 0; t < n_tiles; ++t) {
+        const size_t lo = 32 * t, hi = lo + 32 < n_reads ? lo + 32 : n_reads;
+        rsq_tile16* T = &tiles[t];
+        int32_t bp = 0x7fffffff;
+        const int16_t contig = reads[lo].contig;
+        for (i = lo; i < hi; ++i) if (reads[i].contig == contig && reads[i].pos < bp) bp = reads[i].pos;
+        T->base_pos = bp; T->block_base = (uint32_t)n_xb; T->out_block_base = (uint32_t)out_blocks; T->exc_base = (uint32_t)n_exc;
+        T->contig = contig; T->reserved = 0; T->reserved2 = 0;
+        for (i = lo; i < hi; ++i) {
+            const rsq_read* r = &reads[i];
+            const rsq_block* rb = blocks + r->block_off;
+            rsq_read16* p = &R[i];
+            int ok, implicit = 0;
+            const long long dpos = (long long)r->pos - bp, dm = (long long)r->mpos - r->pos;
+            if ((size_t)r->block_off + r->n_blocks > n_blocks) return RSQ_ERR_INVALID;
+            ok = r->contig == contig && dpos >= 0 && dpos <= 65535 && dm >= -32768 && dm <= 32767 && r->isize >= -32768 && r->isize <= 32767 &&
+                 r->l_qseq >= 0 && r->l_qseq <= 65535 && r->nm >= 0 && r->nm <= 65535 && r->n_blocks <= 255 && !(r->aux & RSQ_AUX_IMPLICIT_BLOCK);
+            if (ok) {
+                if (r->n_blocks == 0) ok = r->endpos == r->pos + 1;
+                else if (r->n_blocks == 1 && rb[0].start == r->pos + 1 && rb[0].len == r->l_qseq && r->endpos == r->pos + r->l_qseq) implicit = 1;
+                else {
+                    ok = r->endpos == rb[r->n_blocks - 1].start - 1 + rb[r->n_blocks - 1].len;
+                    for (b = 0; ok && b < r->n_blocks; ++b) {
+                        const long long o = (long long)rb[b].start - ((long long)r->pos + 1);
+                        ok = o >= 0 && o < (1ll << 21) && rb[b].len >= 0 && rb[b].len < (1 << RSQ_BLOCK16_LEN_BITS);
+                    }
+                }
+            }
+            p->name_hash = r->name_hash;
+            if (ok) {      /* dictionary look-up (open addressing over `scratch`) */
+                rsq_combo16 c;
+                uint32_t h, slot;
+                c.flag = r->flag; c.mapq = r->mapq; c.aux = (uint8_t)(r->aux | (implicit ? RSQ_AUX_IMPLICIT_BLOCK : 0)); c.l_qseq = (uint16_t)r->l_qseq;
+                c.nm = (uint16_t)r->nm; c.n_blocks = (uint8_t)r->n_blocks; c.filter_mask = r->filter_mask; c.reserved = 0; c.reserved2 = 0;
+                h = (uint32_t)c.flag * 0x9E3779B1u ^ ((uint32_t)c.mapq << 8 | c.aux) * 0x85EBCA77u ^ ((uint32_t)c.l_qseq << 16 | c.nm) * 0xC2B2AE3Du ^
+                    ((uint32_t)c.n_blocks << 8 | c.filter_mask) * 0x27D4EB2Fu;
+                h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+                for (slot = h & 131071u;; slot = (slot + 1) & 131071u) {
+                    const uint32_t k = scratch[slot];
+                    if (k == 0xffffffffu) {
+                        if (n_combos >= 0xFFFF) { ok = 0; break; }
+                        scratch[slot] = (uint32_t)n_combos; D[n_combos] = c; p->combo = (uint16_t)n_combos++;
+                        break;
+                    }
+                    if (D[k].flag == c.flag && D[k].mapq == c.mapq && D[k].aux == c.aux && D[k].l_qseq == c.l_qseq && D[k].nm == c.nm &&
+                        D[k].n_blocks == c.n_blocks && D[k].filter_mask == c.filter_mask) { p->combo = (uint16_t)k; break; }
+                }
+            }
+            if (ok) {
+                p->dpos = (uint16_t)dpos; p->dmate = (int16_t)dm; p->isize = (int16_t)r->isize;
+                if (!implicit)
+                    for (b = 0; b < r->n_blocks; ++b)
+                        XB[n_xb++] = ((uint32_t)(rb[b].start - (r->pos + 1)) << RSQ_BLOCK16_LEN_BITS) | (uint32_t)rb[b].len;
+            } else {
+                if (n_exc >= max_exc) return RSQ_ERR_INVALID;
+                p->dpos = 0; p->dmate = 0; p->isize = 0; p->combo = RSQ_COMBO_EXCEPTION;
+                E[n_exc] = *r; E[n_exc].block_off = (uint32_t)n_eb; ++n_exc;
+                for (b = 0; b < r->n_blocks; ++b) EB[n_eb++] = rb[b];
+            }
+            out_blocks += r->n_blocks;
+        }
+    }
+    if (n_exc * 8 > n_reads + 256) return RSQ_ERR_INVALID;
+    /* close the gaps behind the dictionary */
+    off = RSQ_P16_ALIGN(H->off_combos + 16 * n_combos);
+    H->off_blocks = off; memmove(base + off, XB, 4 * n_xb); off = RSQ_P16_ALIGN(off + 4 * n_xb);
+    H->off_exc = off; memmove(base + off, E, 48 * n_exc); off = RSQ_P16_ALIGN(off + 48 * n_exc);
+    H->off_exc_blocks = off; memmove(base + off, EB, 8 * n_eb); off = RSQ_P16_ALIGN(off + 8 * n_eb);
+#undef RSQ_P16_ALIGN
+    H->magic = RSQ_BATCH16_MAGIC; H->struct_size = (uint32_t)sizeof(rsq_batch16);
+    H->n_reads = (uint32_t)n_reads; H->n_tiles = (uint32_t)n_tiles; H->n_combos = (uint32_t)n_combos; H->n_blocks = (uint32_t)n_xb;
+    H->n_exc = (uint32_t)n_exc; H->n_exc_blocks = (uint32_t)n_eb; H->total_blocks = (uint32_t)out_blocks; H->reserved = 0;
+    H->total_bytes = off;
+    *bytes_out = off;
     return RSQ_OK;
 }
 #endif /* RSQ_B200_H */

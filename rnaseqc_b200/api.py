@@ -111,7 +111,7 @@ class StreamStateC(C.Structure):
 
 
 ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
-               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_packed", "rsq_submit_device", "rsq_sync",
+               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_packed", "rsq_submit_compact", "rsq_submit_device", "rsq_sync",
                "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_set_partition", "rsq_export_sample_counts", "rsq_export_counts",
                "rsq_import_counts", "rsq_comm_unique_id", "rsq_comm_init", "rsq_exchange", "rsq_algorithmic_bytes",
                "rsq_launch_count", "rsq_kernel_time_ms"]
@@ -153,6 +153,29 @@ def pack_records(reads: np.ndarray, blocks: np.ndarray, out_reads: Optional[np.n
     if rc != 0:
         return None
     return pr[:n], pb[:w.value]
+
+
+def compact_bound(n_reads: int, n_blocks: int) -> int:
+    return int(host_lib().rsqh_compact_bound(n_reads, n_blocks))
+
+
+def pack_compact(reads: np.ndarray, blocks: np.ndarray, out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+    """rsq_pack_compact: one submit batch (block_off relative to `blocks`) -> the compact batch as a uint8 array (a view of
+    `out` when given: a 16-byte aligned uint8 buffer of at least compact_bound bytes, e.g. pinned), or None when the batch does
+    not suit the format."""
+    H = host_lib()
+    n, nb = reads.nbytes // 48, blocks.nbytes // 8
+    cap = compact_bound(n, nb)
+    if out is None:
+        raw = np.empty(cap + 16, np.uint8)
+        a = (-raw.ctypes.data) % 16
+        out = raw[a:a + cap]
+    assert out.nbytes >= cap and out.ctypes.data % 16 == 0
+    w = C.c_size_t(0)
+    rc = H.rsqh_pack_compact(reads.ctypes.data, n, blocks.ctypes.data, nb, out.ctypes.data, out.nbytes, C.byref(w))
+    if rc != 0:
+        return None
+    return out[:w.value]
 
 
 class RsqError(RuntimeError):
@@ -223,6 +246,7 @@ class Backend:
         L.rsq_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.rsq_submit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.rsq_submit_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.rsq_submit_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.rsq_set_reference.argtypes = [C.c_void_p, C.POINTER(RsqReference)]
         L.rsq_sync.argtypes = [C.c_void_p]
         L.rsq_reset.argtypes = [C.c_void_p]
@@ -326,6 +350,14 @@ class Context:
 
     def submit_packed_ptr(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
         self._check(self.be.lib.rsq_submit_packed(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
+
+    def submit_compact(self, batch: np.ndarray) -> None:
+        """one compact batch (pack_compact): the 16-byte wire format"""
+        assert batch.flags["C_CONTIGUOUS"]
+        self._check(self.be.lib.rsq_submit_compact(self.h, batch.ctypes.data, batch.nbytes))
+
+    def submit_compact_ptr(self, ptr: int, nbytes: int) -> None:
+        self._check(self.be.lib.rsq_submit_compact(self.h, ptr, nbytes))
 
     def submit_device(self, reads_ptr: int, n_reads: int, blocks_ptr: int, n_blocks: int) -> None:
         self._check(self.be.lib.rsq_submit_device(self.h, reads_ptr, n_reads, blocks_ptr, n_blocks))
@@ -460,6 +492,9 @@ def host_lib():
                                        C.POINTER(StreamStateC), C.c_char_p, C.c_size_t]
         H.rsqh_free.argtypes = [C.c_void_p]
         H.rsqh_pack_records.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]
+        H.rsqh_compact_bound.restype = C.c_size_t
+        H.rsqh_compact_bound.argtypes = [C.c_size_t, C.c_size_t]
+        H.rsqh_pack_compact.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         H.rsqh_hash_qname.restype = C.c_uint64
         H.rsqh_hash_qname.argtypes = [C.c_char_p, C.c_size_t]
         H.rsqh_write_reports.argtypes = [C.c_void_p, C.POINTER(RsqResults), C.c_void_p, C.POINTER(RsqCoverageStats), C.POINTER(RunOptionsC),

@@ -104,6 +104,12 @@ size_t rsqh_islands(void* h, uint32_t* contig, int64_t* start, int64_t* end) {
         }
     return n;
 }
+// rsq_pack_compact (include/rsq_b200.h) with its own scratch; out: 16-byte aligned, rsqh_compact_bound bytes
+size_t rsqh_compact_bound(size_t n_reads, size_t n_blocks) { return rsq_compact_bound(n_reads, n_blocks); }
+int rsqh_pack_compact(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks, void* out, size_t cap, size_t* bytes_out) {
+    std::vector<uint32_t> scratch(131072);
+    return rsq_pack_compact(reads, n_reads, blocks, n_blocks, out, cap, scratch.data(), bytes_out);
+}
 unsigned rsqh_n_gene_list(void* h) { return (unsigned)static_cast<Handle*>(h)->ann.gene_list.size(); }
 unsigned rsqh_gene_list_index(void* h, unsigned i) { return static_cast<Handle*>(h)->ann.gene_list[i]; }
 const char* rsqh_gene_id(void* h, unsigned g) { return static_cast<Handle*>(h)->ann.gene_ids[g].c_str(); }

@@ -74,6 +74,8 @@ struct Ctx {
     rsq_read_packed* d_packed[2] = {nullptr, nullptr};
     rsq_block* d_xblocks[2] = {nullptr, nullptr};
     size_t cap_packed[2] = {0, 0}, cap_xblocks[2] = {0, 0};
+    unsigned char* d_compact[2] = {nullptr, nullptr};   // rsq_submit_compact: the batch buffer as it came over the wire
+    size_t cap_compact[2] = {0, 0};
     unsigned int *d_up_tot = nullptr, *d_up_expl = nullptr, *d_up_scan = nullptr;
     size_t cap_up = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -432,7 +434,7 @@ void rsq_destroy(rsq_ctx* ctx) {
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_owned, c->d_found, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
-                    c->d_up_tot, c->d_up_expl, c->d_up_scan};
+                    c->d_up_tot, c->d_up_expl, c->d_up_scan, c->d_compact[0], c->d_compact[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& t : c->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(c->ev_copied[k]); cudaEventDestroy(c->ev_done[k]); }
@@ -773,6 +775,55 @@ int rsq_submit_packed(rsq_ctx* ctx, const rsq_read_packed* reads, size_t n_reads
     return RSQ_OK;
 }
 
+int rsq_submit_compact(rsq_ctx* ctx, const void* batch, size_t bytes) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !c->have_ann || !batch || bytes < sizeof(rsq_batch16)) return RSQ_ERR_INVALID;
+    rsq_batch16 H;
+    memcpy(&H, batch, sizeof H);
+    // the header is input: every section must lie inside the buffer before anything is launched on it
+    auto inside = [&](uint64_t off, uint64_t count, uint64_t size) { return (off & 15u) == 0 && off <= bytes && count * size <= bytes - off; };
+    if (H.magic != RSQ_BATCH16_MAGIC || H.struct_size != sizeof(rsq_batch16) || H.total_bytes > bytes || H.n_tiles != (H.n_reads + 31u) / 32u ||
+        !inside(H.off_tiles, H.n_tiles, sizeof(rsq_tile16)) || !inside(H.off_reads, H.n_reads, sizeof(rsq_read16)) ||
+        !inside(H.off_combos, H.n_combos, sizeof(rsq_combo16)) || !inside(H.off_blocks, H.n_blocks, 4) ||
+        !inside(H.off_exc, H.n_exc, sizeof(rsq_read)) || !inside(H.off_exc_blocks, H.n_exc_blocks, sizeof(rsq_block))) {
+        c->err = "compact batch: bad header";
+        return RSQ_ERR_INVALID;
+    }
+    if (!H.n_reads) return RSQ_OK;
+    const size_t n_reads = H.n_reads, total_blocks = std::max<size_t>(H.total_blocks, 1), wire = (size_t)H.total_bytes;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    const unsigned s = c->slot;
+    c->slot ^= 1u;
+    if (c->slot_used[s]) {
+        if (wire > c->cap_compact[s] || n_reads > c->cap_reads[s] || total_blocks > c->cap_blocks[s]) CU_TRY(cudaEventSynchronize(c->ev_done[s]));
+        else CU_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_done[s], 0));
+    }
+    if (wire > c->cap_compact[s]) {
+        cudaFree(c->d_compact[s]);
+        c->cap_compact[s] = wire + wire / 8;
+        CU_TRY(cudaMalloc(&c->d_compact[s], c->cap_compact[s]));
+    }
+    if (n_reads > c->cap_reads[s]) {
+        cudaFree(c->d_reads[s]);
+        c->cap_reads[s] = n_reads + n_reads / 8;
+        CU_TRY(cudaMalloc(&c->d_reads[s], c->cap_reads[s] * sizeof(rsq_read)));
+    }
+    if (total_blocks > c->cap_blocks[s]) {
+        cudaFree(c->d_blocks[s]);
+        c->cap_blocks[s] = total_blocks + total_blocks / 8;
+        CU_TRY(cudaMalloc(&c->d_blocks[s], c->cap_blocks[s] * sizeof(rsq_block)));
+    }
+    CU_TRY(cudaMemcpyAsync(c->d_compact[s], batch, wire, cudaMemcpyHostToDevice, c->copy_stream));     // ONE copy per batch
+    CU_TRY(cudaEventRecord(c->ev_copied[s], c->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
+    c->launches += launch_expand_compact(c->d_compact[s], H, c->d_reads[s], c->d_blocks[s], c->acc.error_flag, c->stream);
+    int rc = run_batch(c, c->d_reads[s], n_reads, c->d_blocks[s], H.total_blocks);
+    if (rc != RSQ_OK) return rc;
+    CU_TRY(cudaEventRecord(c->ev_done[s], c->stream));
+    c->slot_used[s] = true;
+    return RSQ_OK;
+}
+
 int rsq_sync(rsq_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return RSQ_ERR_INVALID;
@@ -838,7 +889,7 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
     }
     CU_TRY(cudaStreamSynchronize(st));
     CU_TRY(cudaGetLastError());
-    if (err_flag & 8u) { c->err = "packed batch: blocks stream shorter than the records claim"; return RSQ_ERR_INVALID; }
+    if (err_flag & 8u) { c->err = "packed / compact batch: the records claim more blocks, combinations or exceptions than the batch carries"; return RSQ_ERR_INVALID; }
     if (err_flag) {
         c->err = std::string("device table overflow:") + ((err_flag & 1) ? " fragment-tracker set" : "") +
                  ((err_flag & 2) ? " mate table" : "") + ((err_flag & 4) ? " candidate list" : "") + " (raise rsq_config.max_records)";

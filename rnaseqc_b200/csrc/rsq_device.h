@@ -164,6 +164,8 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
 int launch_unpack_counts_of(const rsq_read_packed* packed, size_t n, unsigned int* tot, unsigned int* expl, cudaStream_t stream);
 int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_block* xblocks, size_t n_xblocks, const unsigned int* incl_tot,
                           const unsigned int* incl_expl, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream);
+// 16-byte wire format (rsq_batch16 in one device buffer) -> rsq_read / rsq_block
+int launch_expand_compact(const unsigned char* buf, const rsq_batch16& hdr, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream);
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream);
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
 int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,

@@ -977,6 +977,95 @@ __global__ void unpack_records_kernel(const rsq_read_packed* __restrict__ packed
     }
 }
 
+// ---- 16-byte wire format (rsq_batch16) -> device layout: one warp per tile of 32 records ----------------------------------------------
+// Every tile header says where the tile's variable-length parts start (explicit blocks, exceptions, expanded blocks), so tiles
+// expand independently: two warp scans give each record its offsets.  HBM-bound: reads ~21 bytes, writes ~60 bytes per record.
+__global__ void __launch_bounds__(256) expand_compact_kernel(const unsigned char* __restrict__ buf, const rsq_batch16 H, rsq_read* __restrict__ reads,
+                                                             rsq_block* __restrict__ blocks, unsigned int* __restrict__ err) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= H.n_tiles) return;
+    const rsq_tile16* T = reinterpret_cast<const rsq_tile16*>(buf + H.off_tiles) + tile;
+    const int base_pos = __ldg(&T->base_pos);
+    const uint32_t block_base = __ldg(&T->block_base), out_base = __ldg(&T->out_block_base), exc_base = __ldg(&T->exc_base);
+    const int contig = (int)__ldg(&T->contig);
+    const uint32_t i = tile * 32u + lane;
+    const bool valid = i < H.n_reads;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) r = __ldcs(reinterpret_cast<const uint4*>(buf + H.off_reads) + i);
+    const uint32_t combo = r.w >> 16;
+    const bool exc = valid && combo == RSQ_COMBO_EXCEPTION;
+    bool bad = valid && !exc && combo >= H.n_combos;
+    uint4 c = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && !exc && !bad) c = __ldg(reinterpret_cast<const uint4*>(buf + H.off_combos) + combo);
+    // exception records: the full rsq_read, ranked inside the tile by a ballot
+    const unsigned excm = __ballot_sync(kFull, exc);
+    int4 e0 = make_int4(0, 0, 0, 0), e1 = e0, e2 = e0;
+    if (exc) {
+        const uint32_t e = exc_base + (uint32_t)__popc(excm & ((1u << lane) - 1u));
+        if (e >= H.n_exc) bad = true;
+        else {
+            const int4* ep = reinterpret_cast<const int4*>(buf + H.off_exc) + 3 * (size_t)e;
+            e0 = __ldg(ep); e1 = __ldg(ep + 1); e2 = __ldg(ep + 2);
+        }
+    }
+    const uint32_t aux = exc ? ((uint32_t)e1.z >> 24) : ((c.x >> 24) & 0xffu);
+    const bool implicit = !exc && (aux & RSQ_AUX_IMPLICIT_BLOCK);
+    uint32_t nb = exc ? ((uint32_t)e2.w & 0xffffu) : (c.z & 0xffu);
+    if (bad) nb = 0;
+    const uint32_t expl = (exc || implicit) ? 0u : nb;
+    // exclusive warp scans of the block counts
+    uint32_t s_tot = nb, s_expl = expl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(kFull, s_tot, d), b = __shfl_up_sync(kFull, s_expl, d);
+        if ((int)lane >= d) { s_tot += a; s_expl += b; }
+    }
+    const uint32_t out_off = out_base + s_tot - nb, x_off = block_base + s_expl - expl;
+    if (valid && (unsigned long long)out_off + nb > H.total_blocks) { bad = true; nb = 0; }
+    int4 o0, o1, o2;
+    if (exc && !bad) {
+        const uint32_t src = (uint32_t)e2.z;                                      // block_off into the exception blocks
+        if ((unsigned long long)src + nb > H.n_exc_blocks) { bad = true; nb = 0; }
+        const rsq_block* eb = reinterpret_cast<const rsq_block*>(buf + H.off_exc_blocks) + src;
+        for (uint32_t b = 0; b < nb; ++b) blocks[out_off + b] = eb[b];
+        o0 = e0; o1 = e1; o2 = e2;
+        o2.z = (int)out_off; o2.w = (int)nb;
+    } else {
+        const int pos = base_pos + (int)(r.z & 0xffffu);
+        const int dmate = (int)(int16_t)(r.z >> 16), isize = (int)(int16_t)(r.w & 0xffffu);
+        const int l_qseq = (int)(c.y & 0xffffu), nm = (int)(c.y >> 16);
+        int endpos = pos + 1;
+        if (implicit) {
+            endpos = pos + l_qseq;
+            if (!bad) blocks[out_off] = rsq_block{pos + 1, l_qseq};
+        } else if (nb) {
+            if ((unsigned long long)x_off + nb > H.n_blocks) { bad = true; nb = 0; }
+            const uint32_t* xb = reinterpret_cast<const uint32_t*>(buf + H.off_blocks) + x_off;
+            rsq_block last{0, 0};
+            for (uint32_t b = 0; b < nb; ++b) {
+                const uint32_t w = __ldg(xb + b);
+                last = rsq_block{pos + 1 + (int)(w >> RSQ_BLOCK16_LEN_BITS), (int)(w & ((1u << RSQ_BLOCK16_LEN_BITS) - 1u))};
+                blocks[out_off + b] = last;
+            }
+            if (nb) endpos = last.start - 1 + last.len;
+        }
+        o0.x = pos; o0.y = pos + dmate; o0.z = endpos; o0.w = isize;
+        o1.x = l_qseq; o1.y = nm;
+        o1.z = (int)((c.x & 0x00ffffffu) | ((aux & ~(uint32_t)RSQ_AUX_IMPLICIT_BLOCK) << 24));   // flag | mapq << 16 | aux << 24
+        o1.w = (int)(((uint32_t)contig & 0xffffu) | (((c.z >> 8) & 0xffu) << 16));               // contig | filter_mask << 16
+        o2.x = (int)r.x; o2.y = (int)r.y; o2.z = (int)out_off; o2.w = (int)nb;
+    }
+    if (bad) {                      // a batch that contradicts itself: flag it, and leave a record that touches nothing
+        atomicOr(err, 8u);
+        o0 = make_int4(0, 0, 1, 0); o1 = make_int4(0, 0, (int)RSQ_F_UNMAP, 0xffff); o2 = make_int4(0, 0, 0, 0);
+    }
+    if (valid) {
+        int4* out = reinterpret_cast<int4*>(reads + i);
+        out[0] = o0; out[1] = o1; out[2] = o2;
+    }
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------------------------------------------
@@ -1089,6 +1178,12 @@ int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_blo
     if (!n) return 0;
     unpack_records_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(packed, n, xblocks, n_xblocks, incl_tot, incl_expl,
                                                                                                         reads, blocks, error_flag);
+    return 1;
+}
+
+int launch_expand_compact(const unsigned char* buf, const rsq_batch16& hdr, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream) {
+    if (!hdr.n_tiles) return 0;
+    expand_compact_kernel<<<(hdr.n_tiles + 7) / 8, 256, 0, stream>>>(buf, hdr, reads, blocks, error_flag);
     return 1;
 }
 

@@ -101,6 +101,82 @@ def test_packed_wire_format_roundtrip_through_the_oracle(libs, tmp_path):
     assert api.pack_records(bad, blocks) is None
 
 
+def _compact_cases(api, tmp_path):
+    """(annotation, reads, blocks) of a synthetic sample, plus a copy with records the 16-byte format cannot express"""
+    import numpy as np
+    from rnaseqc_b200 import synth
+    sa = synth.make_annotation(seed=5, n_genes=60, contig_names=["chr1", "chr2"], contig_lens=[4_000_000, 2_000_000])
+    gtf = str(tmp_path / "a.gtf")
+    synth.write_gtf(sa, gtf)
+    ann = api.Annotation(gtf)
+    sr = synth.simulate_reads(sa, 30000, seed=6)
+    rb, bb = synth.pack(sr, [ann.contig_index(n) for n in sa.contig_names])
+    reads, blocks = synth.to_numpy(rb, bb)
+    odd = reads.copy()
+    rng = np.random.default_rng(1)
+    k = rng.choice(len(odd), 600, replace=False)
+    odd["mpos"][k[:100]] += 1_000_000                  # mate far away
+    odd["isize"][k[100:200]] = 400_000                 # insert size beyond 16 bits
+    odd["nm"][k[200:250]] = 70_000                     # NM beyond 16 bits
+    odd["contig"][k[250:300]] = 1 - odd["contig"][k[250:300]]   # another contig inside a tile
+    odd["l_qseq"][k[300:350]] = 100_000
+    odd["flag"][k[350:600]] ^= rng.integers(0, 1 << 12, 250).astype(np.uint16)   # many distinct combinations
+    return ann, reads, blocks, odd
+
+
+def test_compact_wire_format_roundtrip_through_the_oracle(libs, tmp_path):
+    """rsq_pack_compact + rsq_submit_compact (16-byte records, tile headers, dictionary, 32-bit blocks, exception list) give the
+    same results as rsq_submit — also for records the format cannot express (they travel as exceptions) and over several
+    submits; batches with too many exceptions and corrupted batches are refused."""
+    import numpy as np
+    from util import assert_results_equal
+    api = libs["api"]
+    ann, reads, blocks, odd = _compact_cases(api, tmp_path)
+
+    def run(submit):
+        ctx = api.Backend(libs["oracle"]).create(api.make_config())
+        ctx.set_annotation(ann)
+        submit(ctx)
+        return ctx.finalize()
+
+    for name, rr in (("plain", reads), ("odd", odd)):
+        want = run(lambda c: c.submit(rr, blocks))
+        whole = api.pack_compact(rr, blocks)
+        assert whole is not None
+        hdr = np.frombuffer(whole[:96].tobytes(), np.uint32)
+        n_exc = int(hdr[6])
+        if name == "plain":
+            assert n_exc < len(rr) // 50 and whole.nbytes < 24 * len(rr), (n_exc, whole.nbytes / len(rr))
+        else:
+            assert 250 <= n_exc <= 700
+        assert_results_equal(run(lambda c: c.submit_compact(whole)), want, f"compact vs unpacked ({name})")
+
+        def three_calls(c):
+            n = len(rr)
+            for lo, hi in ((0, n // 3), (n // 3, n // 3 + 33), (n // 3 + 33, n)):
+                r = rr[lo:hi].copy()
+                b0 = int(r["block_off"][0]); b1 = int(r["block_off"][-1]) + int(r["n_blocks"][-1])
+                r["block_off"] -= b0
+                c.submit_compact(api.pack_compact(r, blocks[b0:b1].copy()))
+        assert_results_equal(run(three_calls), want, f"compact in three calls ({name})")
+    # too many exceptions: every record's mate is far away
+    far = reads.copy()
+    far["mpos"] += 5_000_000
+    assert api.pack_compact(far, blocks) is None
+    # a corrupted header or a record that points outside the batch is an error, not a crash
+    whole = api.pack_compact(reads, blocks).copy()
+    bad = whole.copy(); bad[0] ^= 0xff
+    ctx = api.Backend(libs["oracle"]).create(api.make_config()); ctx.set_annotation(ann)
+    with pytest.raises(api.RsqError):
+        ctx.submit_compact(bad)
+    hdr = np.frombuffer(whole[:96].tobytes(), np.uint32).copy()
+    off_reads = int(np.frombuffer(whole[48:56].tobytes(), np.uint64)[0])
+    bad = whole.copy()
+    bad[off_reads + 14:off_reads + 16] = np.frombuffer(np.uint16(hdr[4] + 5).tobytes(), np.uint8)     # combo index past the dictionary
+    with pytest.raises(api.RsqError):
+        ctx.submit_compact(bad)
+
+
 def test_pinned_result_buffers_match_plain_ones(libs, tmp_path):
     """Context.finalize(pinned=True) / coverage_statistics(pinned=True): page-locked buffers from rsq_host_alloc, reused by
     the next call, same content as the default numpy buffers (CPU twin of what bench.py does on the GPU)."""

@@ -142,15 +142,17 @@ def test_device_resident_submit_and_export_roundtrip(libs, synth_case):
     import torch
     api = libs["api"]
     ann, reads, blocks = synth_case
-    want, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=len(reads)))
-    ctx = api.Backend(libs["product"]).create(api.make_config(max_records=len(reads)))
+    quota = 5000
+    want, _ = _run(api, libs["product"], ann, reads, blocks, api.make_config(max_records=len(reads), fragment_samples=quota))
+    ctx = api.Backend(libs["product"]).create(api.make_config(max_records=len(reads), fragment_samples=quota))
     ctx.set_annotation(ann)
     dr = torch.from_numpy(reads.view(np.uint8).reshape(-1, 48)).cuda()
     db = torch.from_numpy(blocks.view(np.int32).reshape(-1, 2)).cuda()
     ctx.submit_device(dr.data_ptr(), len(reads), db.data_ptr(), len(blocks))
     ptr, n = ctx.export_counts()
-    assert n == api.RSQ_N_COUNTERS + 3 * ann.n_genes + 3 * ann.n_exons + 100
-    ctx.import_counts()           # identity round trip through the all-reduce layout
+    # counters | 3 gene tables | 3 exon words | GC bins | samples found | the kept fragment-size samples, two per word
+    assert n == api.RSQ_N_COUNTERS + 3 * ann.n_genes + 3 * ann.n_exons + 100 + 1 + (quota + 1) // 2
+    ctx.import_counts()           # identity round trip through the all-reduce layout (one partition: every sample is kept)
     got = ctx.finalize()
     assert_results_equal(got, want, "device submit + export/import")
     assert ctx.launch_count() > 0 and ctx.kernel_time_ms() > 0
@@ -330,6 +332,51 @@ def test_packed_wire_format_matches_unpacked_submit(libs, synth_case):
     assert ctx.algorithmic_bytes() == want_bytes
     assert total_wire < 0.75 * (48 * len(reads) + 8 * len(blocks))
     ctx.close()
+
+
+def test_compact_wire_format_matches_unpacked_submit(libs, synth_case, tmp_path):
+    """rsq_submit_compact: the device expands the 16-byte wire format (tile headers, dictionary, 32-bit blocks, exceptions) into
+    the hot kernel's layout; results equal the rsq_submit ones bit for bit — plain sample over several submits, a sample with
+    records the format cannot express, and a corrupted batch is reported instead of processed."""
+    from test_abi import _compact_cases
+    api = libs["api"]
+    ann, reads, blocks = synth_case
+    cfg = lambda: api.make_config(max_records=len(reads), fragment_samples=20000)
+    want, want_bytes = _run(api, libs["product"], ann, reads, blocks, cfg())
+    ctx = api.Backend(libs["product"]).create(cfg())
+    ctx.set_annotation(ann)
+    n, total_wire, keep = len(reads), 0, []
+    for k in range(5):
+        lo, hi = n * k // 5, n * (k + 1) // 5
+        r = reads[lo:hi].copy()
+        b0 = int(r["block_off"][0]); b1 = int(r["block_off"][-1]) + int(r["n_blocks"][-1])
+        r["block_off"] -= b0
+        p = api.pack_compact(r, blocks[b0:b1].copy())
+        assert p is not None
+        keep.append(p)                      # the buffers belong to the caller until rsq_sync
+        ctx.submit_compact(p)
+        total_wire += p.nbytes
+    got = ctx.finalize()
+    assert_results_equal(got, want, "compact submit")
+    assert ctx.algorithmic_bytes() == want_bytes
+    assert total_wire < 0.45 * (48 * len(reads) + 8 * len(blocks)), total_wire / len(reads)
+    ctx.close()
+    ann2, reads2, blocks2, odd = _compact_cases(api, tmp_path)
+    want2, _ = _run(api, libs["oracle"], ann2, odd, blocks2, api.make_config())
+    c2 = api.Backend(libs["product"]).create(api.make_config(max_records=len(odd)))
+    c2.set_annotation(ann2)
+    whole = api.pack_compact(odd, blocks2)
+    c2.submit_compact(whole)
+    assert_results_equal(c2.finalize(), want2, "compact submit with exceptions vs oracle")
+    off_reads = int(np.frombuffer(whole[48:56].tobytes(), np.uint64)[0])
+    n_combos = int(np.frombuffer(whole[:96].tobytes(), np.uint32)[4])
+    bad = whole.copy()
+    bad[off_reads + 14:off_reads + 16] = np.frombuffer(np.uint16(n_combos + 5).tobytes(), np.uint8)
+    c2.reset()
+    c2.submit_compact(bad)
+    with pytest.raises(api.RsqError):
+        c2.finalize()
+    c2.close()
 
 
 def test_full_size_properties_200m_records(libs):
