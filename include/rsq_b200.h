@@ -348,6 +348,9 @@ int rsq_submit_packed(rsq_ctx* ctx, const rsq_read_packed* reads, size_t n_reads
 /* Same for a compact batch (rsq_batch16 and what follows it in one buffer of `bytes` bytes, written by rsq_pack_compact). */
 int rsq_submit_compact(rsq_ctx* ctx, const void* batch, size_t bytes);
 int rsq_sync(rsq_ctx* ctx);
+/* Returns once the HOST buffers of every submit so far may be reused (their copies have left the host); the kernels that
+ * consume them may still be running.  A pipelined caller waits on this, not on rsq_sync, before it refills a buffer. */
+int rsq_sync_inputs(rsq_ctx* ctx);
 
 /* Clears all accumulators (annotation and BED stay): a new sample / a new timed step. */
 int rsq_reset(rsq_ctx* ctx);

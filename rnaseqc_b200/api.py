@@ -111,7 +111,7 @@ class StreamStateC(C.Structure):
 
 
 ABI_SYMBOLS = ["rsq_backend", "rsq_abi_version", "rsq_host_alloc", "rsq_host_free", "rsq_create", "rsq_destroy",
-               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_packed", "rsq_submit_compact", "rsq_submit_device", "rsq_sync",
+               "rsq_last_error", "rsq_set_annotation", "rsq_set_bed", "rsq_set_reference", "rsq_submit", "rsq_submit_packed", "rsq_submit_compact", "rsq_submit_device", "rsq_sync", "rsq_sync_inputs",
                "rsq_reset", "rsq_finalize", "rsq_coverage_statistics", "rsq_set_partition", "rsq_export_sample_counts", "rsq_export_counts",
                "rsq_import_counts", "rsq_comm_unique_id", "rsq_comm_init", "rsq_exchange", "rsq_algorithmic_bytes",
                "rsq_launch_count", "rsq_kernel_time_ms"]
@@ -249,6 +249,7 @@ class Backend:
         L.rsq_submit_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.rsq_set_reference.argtypes = [C.c_void_p, C.POINTER(RsqReference)]
         L.rsq_sync.argtypes = [C.c_void_p]
+        L.rsq_sync_inputs.argtypes = [C.c_void_p]
         L.rsq_reset.argtypes = [C.c_void_p]
         L.rsq_finalize.argtypes = [C.c_void_p, C.POINTER(RsqResults)]
         L.rsq_coverage_statistics.argtypes = [C.c_void_p, C.POINTER(RsqTranscripts), C.POINTER(RsqCoverageStats)]

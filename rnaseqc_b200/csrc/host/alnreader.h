@@ -93,6 +93,7 @@ public:
     RunSummary summarise(const rsq_read* r, const int32_t* tids, size_t n) const;
     bool observe_run(const RunSummary& s);
 
+    bool saw_unsorted() const { return warned_unsorted_; }
     int read_length() const { return read_length_; }
     uint64_t alignment_count() const { return alignment_count_; }
     // contigs in the order their feature lists were dropped during the stream (dropFeatures calls)

@@ -146,6 +146,8 @@ ParallelBamDecoder::ParallelBamDecoder(const std::string& path, int n_threads)
     : path_(path), n_threads_(std::max(1, n_threads)) {
     fp_ = std::fopen(path.c_str(), "rb");
     if (!fp_) throw HostError(10, "Unable to open BAM file: " + path);
+    if (std::fseek(fp_, 0, SEEK_END) == 0) { const long sz = std::ftell(fp_); if (sz > 0) file_bytes_ = (uint64_t)sz; }
+    std::rewind(fp_);
     // header: sequential inflate of the first block(s)
     {
         std::vector<uint8_t> text;
@@ -489,6 +491,7 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
         t_consumer_ += since(t_copy);
         cur_read_ += n;
         if (cur_read_ >= job->reads.size()) {
+            compressed_consumed_ += cur_->comp.size();
             { std::lock_guard<std::mutex> lk(mu_); pool_.push_back(cur_); }
             cur_.reset(); cur_read_ = 0;
         }

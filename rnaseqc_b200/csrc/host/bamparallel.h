@@ -29,6 +29,9 @@ public:
     // Appends up to max_records converted records (with their blocks) to the cleared vectors, in file order, running
     // dec.observe() on each.  Returns false once the stream is exhausted and nothing was appended.
     bool next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
+    // compressed bytes of the jobs handed out so far / size of the file: lets a caller extrapolate the record count
+    uint64_t compressed_consumed() const { return compressed_consumed_; }
+    uint64_t file_bytes() const { return file_bytes_; }
     // framing statistics of the decoder destroyed last (tests, diagnostics)
     static unsigned long long last_chain_hits();
     static unsigned long long last_chain_misses();
@@ -65,6 +68,7 @@ private:
     size_t cur_read_ = 0;
     // busy seconds per stage, printed by the destructor when RSQ_INGEST_STATS is set (reader and consumer: one thread each;
     // frame: one worker at a time; inflate and convert: summed over the workers)
+    uint64_t compressed_consumed_ = 0, file_bytes_ = 0;
     bool speculate_ = true;            // RSQ_INGEST_NO_SPECULATION=1: the sequential hop for every job (A/B, tests)
     bool summarise_ = true;            // RSQ_INGEST_NO_SUMMARY=1: Decoder::observe per record on the consumer thread (A/B, tests)
     uint64_t n_chain_hits_ = 0, n_chain_misses_ = 0, n_runs_summarised_ = 0;

@@ -10,8 +10,10 @@ int main(int argc, char** argv) {
     rsqh::CliOptions opt;
     int rc = rsqh::parse_cli(argc, argv, opt);
     if (rc >= 0) return rc;
-    rsqh::Backend be{rsq_backend, rsq_create,  rsq_destroy,  rsq_last_error, rsq_set_annotation, rsq_set_bed,
-                     rsq_set_reference, rsq_submit, rsq_submit_packed,  rsq_sync,    rsq_finalize, rsq_coverage_statistics, rsq_host_alloc, rsq_host_free};
+    rsqh::Backend be{rsq_backend, rsq_create, rsq_destroy, rsq_last_error, rsq_set_annotation, rsq_set_bed, rsq_set_reference, rsq_submit,
+                     rsq_submit_packed, rsq_submit_compact, rsq_sync, rsq_sync_inputs, rsq_finalize, rsq_coverage_statistics, rsq_host_alloc,
+                     rsq_host_free, rsq_set_partition, rsq_export_sample_counts, rsq_export_counts, rsq_import_counts, rsq_comm_unique_id,
+                     rsq_comm_init, rsq_exchange};
     if (opt.verbosity) std::cout << "hot-path backend: " << be.backend() << std::endl;
     return rsqh::run_sample(be, opt);
 }

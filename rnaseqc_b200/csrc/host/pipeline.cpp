@@ -48,7 +48,13 @@ void usage(std::ostream& o) {
          "      -d[threshold], --detection-threshold=[threshold]  Counts on a gene to consider it detected. Default: 5\n"
          "      --batch-records=[N]               Records per device batch (this build). Default: 1048576\n"
          "      --decode-threads=[N]              BAM inflate/convert worker threads (this build); 0 = sequential reader.\n"
-         "      --no-packed-submit                Send 48-byte records instead of the 32-byte wire format (this build)\n"
+         "      --no-packed-submit                Send 48-byte records instead of the 16- / 32-byte wire formats (this build)\n"
+         "      --no-compact-submit               Do not use the 16-byte wire format (this build)\n"
+         "      --gpus=[N]                        Range-partition the records by coordinate over N GPUs (this build); results are\n"
+         "                                        identical to a single-GPU run.  Needs a coordinate-sorted alignment file\n"
+         "      --devices=[a,b,..]                The same with explicit CUDA device ordinals (this build)\n"
+         "      --records-per-gpu=[N]             Records a GPU takes before the stream moves on to the next one (this build).\n"
+         "                                        Default: the file's estimated record count / GPUs\n"
          "                                        Default: hardware threads, at most 32\n"
          "      --exact-complexity                Literal 1e9-iteration library-complexity scan (this build)\n";
 }
@@ -120,6 +126,18 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
             else if (is("decode-threads")) opt.decode_threads = std::stoi(value("decode-threads", 0));
             else if (a == "--no-packed-submit") opt.packed_submit = false;
             else if (is("device")) opt.cfg.device = std::stoi(value("device", 0));
+            else if (is("gpus")) { const int n = std::stoi(value("gpus", 0)); if (n < 1 || n > 64) throw ArgError{6, "--gpus must be between 1 and 64"}; opt.devices.clear(); for (int k = 0; k < n; ++k) opt.devices.push_back(k); }
+            else if (is("devices")) {
+                opt.devices.clear();
+                std::string v = value("devices", 0), tok;
+                for (size_t p0 = 0; p0 <= v.size(); ++p0) {
+                    if (p0 == v.size() || v[p0] == ',') { if (!tok.empty()) opt.devices.push_back(std::stoi(tok)); tok.clear(); }
+                    else tok += v[p0];
+                }
+                if (opt.devices.empty()) throw ArgError{6, "--devices needs a comma-separated list of CUDA device ordinals"};
+            }
+            else if (is("records-per-gpu")) opt.records_per_gpu = std::stoul(value("records-per-gpu", 0));
+            else if (a == "--no-compact-submit") opt.compact_submit = false;
             else if (a == "--exact-complexity") opt.run.exact_complexity_scan = true;
             else if (a.size() > 1 && a[0] == '-') throw ArgError{5, "Flag could not be matched: " + a};
             else positional.push_back(a);
@@ -185,8 +203,10 @@ void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool wa
     R.fragment_hist.resize(last);
 }
 
-void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation& A, const RunOptions& opt, HostResults& R) {
+void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation& A, const RunOptions& opt, HostResults& R,
+                               const std::vector<uint8_t>* owned) {
     rsq_transcripts q = A.transcripts(opt.coverage_mask, opt.bias_offset, opt.bias_window, opt.bias_gene_length);
+    if (owned) q.gene_owned = owned->data();
     R.cs_mean.assign(q.n_genes, 0); R.cs_std.assign(q.n_genes, 0); R.cs_cv.assign(q.n_genes, 0);
     R.cs_five.assign(q.n_genes, 0); R.cs_three.assign(q.n_genes, 0);
     R.cs_exon_cv.assign(A.exon_ids.size(), 0);
@@ -200,17 +220,74 @@ void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation
     R.have_cov_stats = true;
 }
 
+namespace {
+
+// One GPU of the run: its context, three page-locked staging buffers (a batch is packed into one while the previous two are on
+// the wire or waiting for their copy) and the route its records take.  A single-GPU run is the one-lane case of the same code.
+struct Lane {
+    const Backend* be = nullptr;
+    rsq_ctx* ctx = nullptr;
+    int device = 0;
+    std::future<int> creating;
+    static constexpr int kSlots = 3;
+    void* pinned[kSlots] = {nullptr, nullptr, nullptr};
+    size_t cap[kSlots] = {0, 0, 0};
+    bool in_flight[kSlots] = {false, false, false};
+    int next_slot = 0;
+    uint64_t records = 0, batches = 0, wire_bytes = 0;
+    std::vector<uint8_t> owned;
+
+    // a staging buffer of at least `bytes` bytes whose previous content has left the host
+    int acquire(size_t bytes) {
+        const int s = next_slot;
+        next_slot = (next_slot + 1) % kSlots;
+        if (in_flight[s]) {
+            const int rc = be->sync_inputs(ctx);
+            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync_inputs failed: ") + be->last_error(ctx));
+            for (bool& f : in_flight) f = false;
+        }
+        if (cap[s] < bytes) {
+            if (pinned[s]) be->host_free(pinned[s]);
+            cap[s] = bytes + bytes / 4;
+            pinned[s] = be->host_alloc(cap[s]);
+            if (!pinned[s]) { cap[s] = 0; throw HostError(10, "Memory allocation failure. Out of memory"); }
+        }
+        return s;
+    }
+    void release() {
+        for (int s = 0; s < kSlots; ++s) if (pinned[s]) { be->host_free(pinned[s]); pinned[s] = nullptr; }
+        if (ctx) { be->destroy(ctx); ctx = nullptr; }
+    }
+};
+
+// One piece of a decoded batch on its way to one lane: packed on a helper thread, submitted on the main thread, in order.
+struct Staged {
+    int lane = 0, slot = 0;
+    size_t n_reads = 0, n_blocks = 0, n_packed_blocks = 0, compact_bytes = 0, blocks_off = 0;
+    std::future<int> how;        // 2 = rsq_batch16, 1 = rsq_read_packed, 0 = rsq_read
+};
+
+}  // namespace
+
 int run_sample(const Backend& be, CliOptions& opt) {
     using clk = std::chrono::steady_clock;
-    rsq_ctx* ctx = nullptr;
-    void* pinned[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    size_t pinned_cap[2][2] = {{0, 0}, {0, 0}};
+    if (opt.devices.empty()) opt.devices.push_back(opt.cfg.device);
+    const size_t n_lanes = opt.devices.size();
+    std::vector<Lane> lanes(n_lanes);
     int exit_code = 0;
-    // The device context comes up on a helper thread while the GTF is parsed (CUDA start-up costs about as much as the parse on
-    // a multi-GPU box); its outcome is looked at where rsq_create used to be called, so errors keep their order of precedence.
-    std::future<int> creating;
+    std::vector<Staged> staged;
     try {
-        creating = std::async(std::launch::async, [&be, &opt, &ctx] { return be.create(&opt.cfg, &ctx); });
+        // The device contexts come up on helper threads while the GTF is parsed (CUDA start-up costs about as much as the parse
+        // on a multi-GPU box); their outcome is looked at where rsq_create used to be called, so errors keep their precedence.
+        for (size_t k = 0; k < n_lanes; ++k) {
+            Lane& L = lanes[k];
+            L.be = &be; L.device = opt.devices[k];
+            L.creating = std::async(std::launch::async, [&be, &opt, &L] {
+                rsq_config cfg = opt.cfg;
+                cfg.device = L.device;
+                return be.create(&cfg, &L.ctx);
+            });
+        }
         Annotation A;
         ReferenceModel ref;
         if (!opt.fasta.empty()) {                                                  // src/RNASeQC.cpp:117-122: before the GTF
@@ -271,46 +348,141 @@ int run_sample(const Backend& be, CliOptions& opt) {
                         throw HostError(1, "Unable to parse the GFT lines\ncannot create std::vector larger than max_size()");
 
         auto t_setup = clk::now();
-        int rc = creating.get();
-        if (rc != RSQ_OK) throw HostError(rc == RSQ_ERR_NO_DEVICE ? 10 : -1, std::string("rsq_create failed: ") + be.last_error(nullptr));
-        rsq_annotation av = A.view();
-        rc = be.set_annotation(ctx, &av);
-        if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_annotation failed: ") + be.last_error(ctx));
-        if (!opt.bed.empty()) {
-            rsq_bed bv = bed.view();
-            rc = be.set_bed(ctx, &bv);
-            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_bed failed: ") + be.last_error(ctx));
+        for (Lane& L : lanes) {
+            int rc = L.creating.get();
+            if (rc != RSQ_OK) throw HostError(rc == RSQ_ERR_NO_DEVICE ? 10 : -1, std::string("rsq_create failed: ") + be.last_error(nullptr));
         }
-        if (ref.open) {
-            rsq_reference rv = ref.view();
-            rc = be.set_reference(ctx, &rv);
-            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_set_reference failed: ") + be.last_error(ctx));
+        {   // annotation / BED / reference upload: one thread per GPU
+            rsq_annotation av = A.view();
+            rsq_bed bv{};
+            if (!opt.bed.empty()) bv = bed.view();
+            rsq_reference rv{};
+            if (ref.open) rv = ref.view();
+            std::vector<std::future<std::string>> ups;
+            for (Lane& L : lanes)
+                ups.push_back(std::async(n_lanes > 1 ? std::launch::async : std::launch::deferred, [&, ctx = L.ctx]() -> std::string {
+                    if (be.set_annotation(ctx, &av) != RSQ_OK) return std::string("rsq_set_annotation failed: ") + be.last_error(ctx);
+                    if (!opt.bed.empty() && be.set_bed(ctx, &bv) != RSQ_OK) return std::string("rsq_set_bed failed: ") + be.last_error(ctx);
+                    if (ref.open && be.set_reference(ctx, &rv) != RSQ_OK) return std::string("rsq_set_reference failed: ") + be.last_error(ctx);
+                    return std::string();
+                }));
+            std::string why;
+            for (auto& f : ups) { const std::string w = f.get(); if (why.empty()) why = w; }
+            if (!why.empty()) throw HostError(-1, why);
+        }
+        // Several GPUs: the communicator of the end-of-run exchange.  NCCL inside the library when the backend has it (the CUDA
+        // product); the CPU oracle backend of the test harness has none, and the exchange buffers travel through host memory.
+        bool nccl = false;
+        if (n_lanes > 1) {
+            uint8_t id[RSQ_COMM_ID_BYTES];
+            if (be.comm_unique_id(id) == RSQ_OK) {
+                std::vector<std::future<int>> inits;
+                for (size_t k = 0; k < n_lanes; ++k)
+                    inits.push_back(std::async(std::launch::async, [&, k] { return be.comm_init(lanes[k].ctx, id, (uint32_t)k, (uint32_t)n_lanes); }));
+                int bad = RSQ_OK;
+                for (auto& f : inits) { const int r = f.get(); if (r != RSQ_OK) bad = r; }
+                if (bad != RSQ_OK) throw HostError(-1, std::string("rsq_comm_init failed: ") + be.last_error(lanes[0].ctx));
+                nccl = true;
+            } else if (std::string(be.backend()) == "oracle-cpu") {
+                for (size_t k = 0; k < n_lanes; ++k)
+                    if (be.set_partition(lanes[k].ctx, (uint32_t)k, (uint32_t)n_lanes) != RSQ_OK) throw HostError(-1, "rsq_set_partition failed");
+            } else throw HostError(-1, std::string("--gpus needs NCCL: ") + be.last_error(nullptr));
         }
 
         if (opt.verbosity) std::cout << "Device context + annotation upload: " << std::chrono::duration<double>(clk::now() - t_setup).count() << " seconds" << std::endl;
         if (opt.verbosity) std::cout << "Parsing bam..." << std::endl;
         auto t1 = clk::now();
-        // Two batch buffers: while a helper thread packs batch i into its page-locked slot (the wire format, or the plain copy
-        // when the batch does not fit its rules), this thread already collects batch i+1 from the decoder; submits stay on this
-        // thread, in order.  (Packing was a third of this thread's time per record once the decoder's framing stopped being
-        // the sequential bottleneck.)
+
+        // ---- routing of the coordinate-sorted stream over the lanes -------------------------------------------
+        // Lane g takes records until it has its share, then the stream moves on to lane g + 1 at the next position that lies in no
+        // island (gene hull or BED interval): all records that count toward a gene, and both mates of a pair, stay on one GPU.
+        Islands islands;
+        std::vector<int64_t> contig_rank(n_contigs, -1);          // annotation contig id -> rank in the stream's (header's) order
+        if (n_lanes > 1) {
+            build_islands(A, opt.bed.empty() ? nullptr : &bed, islands);
+            const std::vector<int>& t2c = decoder.tid_to_contig();
+            for (size_t t = 0; t < t2c.size(); ++t)
+                if (t2c[t] >= 0 && (size_t)t2c[t] < n_contigs && contig_rank[t2c[t]] < 0) contig_rank[t2c[t]] = (int64_t)t;
+        }
+        std::vector<StreamCut> cuts;          // cuts[g] = first coordinate of lane g + 1
+        bool have_pending = false;
+        StreamCut pending{0, 0};
+        size_t g = 0;
+        auto key_of = [&](const rsq_read& r, StreamCut& k) -> bool {     // false: the record carries no usable coordinate
+            if (r.contig < 0 || (size_t)r.contig >= n_contigs || contig_rank[r.contig] < 0) return false;
+            k.contig_rank = contig_rank[r.contig]; k.pos1 = (int64_t)r.pos + 1;
+            return true;
+        };
+        auto before = [](const StreamCut& a, const StreamCut& b) { return a.contig_rank < b.contig_rank || (a.contig_rank == b.contig_rank && a.pos1 < b.pos1); };
+        auto share = [&]() -> uint64_t {                                 // records a lane takes before the stream moves on
+            if (opt.records_per_gpu) return opt.records_per_gpu;
+            if (pbam && pbam->compressed_consumed() > 0 && pbam->file_bytes() > 0) {
+                const double est = (double)decoder.alignment_count() * (double)pbam->file_bytes() / (double)pbam->compressed_consumed();
+                return (uint64_t)(est / (double)n_lanes) + 1;
+            }
+            return (uint64_t)1 << 24;
+        };
+
+        // Two batch buffers: while helper threads pack batch i into page-locked slots (16-byte wire format, else the 32-byte
+        // one, else the plain copy), this thread already collects batch i+1 from the decoder; submits stay on this thread, in order.
         std::vector<rsq_read> reads_buf[2];
         std::vector<rsq_block> blocks_buf[2];
         reads_buf[0].reserve(opt.batch_records);
         reads_buf[1].reserve(opt.batch_records);
         RawAln aln;
-        struct Staged { bool active = false; int slot = 0; size_t n_reads = 0, n_blocks = 0, n_packed_blocks = 0; std::future<int> packed; } staged;
-        auto submit_staged = [&]() {            // waits for the packer of the previous batch, then submits it
-            if (!staged.active) return;
-            staged.active = false;
-            const int how = staged.packed.get();
-            const int s = staged.slot;
-            int r2;
-            if (how == 1) r2 = be.submit_packed(ctx, (const rsq_read_packed*)pinned[s][0], staged.n_reads, (const rsq_block*)pinned[s][1], staged.n_packed_blocks);
-            else r2 = be.submit(ctx, (const rsq_read*)pinned[s][0], staged.n_reads, (const rsq_block*)pinned[s][1], staged.n_blocks);
-            if (r2 != RSQ_OK) throw HostError(-1, std::string("rsq_submit failed: ") + be.last_error(ctx));
+        auto submit_staged = [&]() {            // waits for the packers of the previous batch, then submits its pieces
+            std::vector<Staged> todo;
+            todo.swap(staged);
+            std::string why;
+            for (Staged& st : todo) {
+                const int how = st.how.get();
+                if (!why.empty()) continue;
+                Lane& L = lanes[st.lane];
+                unsigned char* buf = (unsigned char*)L.pinned[st.slot];
+                int r2;
+                if (how == 2) { r2 = be.submit_compact(L.ctx, buf, st.compact_bytes); L.wire_bytes += st.compact_bytes; }
+                else if (how == 1) { r2 = be.submit_packed(L.ctx, (const rsq_read_packed*)buf, st.n_reads, (const rsq_block*)(buf + st.blocks_off), st.n_packed_blocks); L.wire_bytes += 32 * st.n_reads + 8 * st.n_packed_blocks; }
+                else { r2 = be.submit(L.ctx, (const rsq_read*)buf, st.n_reads, (const rsq_block*)(buf + st.blocks_off), st.n_blocks); L.wire_bytes += 48 * st.n_reads + 8 * st.n_blocks; }
+                L.in_flight[st.slot] = true;
+                L.records += st.n_reads; ++L.batches;
+                if (r2 != RSQ_OK) why = std::string("rsq_submit failed: ") + be.last_error(L.ctx);
+            }
+            if (!why.empty()) throw HostError(-1, why);
         };
-        int slot = 0, cur = 0;
+        auto stage = [&](size_t lane, const std::vector<rsq_read>& reads, const std::vector<rsq_block>& blocks, size_t i0, size_t i1) {
+            if (i1 <= i0) return;
+            Lane& L = lanes[lane];
+            const size_t n = i1 - i0;
+            const size_t b0 = reads[i0].block_off, b1 = (size_t)reads[i1 - 1].block_off + reads[i1 - 1].n_blocks, nb = b1 - b0;
+            const size_t blocks_off = (48 * n + 15) & ~(size_t)15;
+            const size_t need = std::max(rsq_compact_bound(n, nb), blocks_off + 8 * std::max<size_t>(nb, 1));
+            Staged st;
+            st.lane = (int)lane; st.slot = L.acquire(need); st.n_reads = n; st.n_blocks = nb; st.blocks_off = blocks_off;
+            staged.push_back(std::move(st));
+            Staged* sp = &staged.back();
+            unsigned char* dst = (unsigned char*)L.pinned[sp->slot];
+            const size_t cap = L.cap[sp->slot];
+            const rsq_read* src_reads = reads.data() + i0;
+            const rsq_block* src_blocks = blocks.data();        // block_off of the records stays relative to the whole batch
+            const size_t n_all_blocks = blocks.size();
+            const bool try_compact = opt.packed_submit && opt.compact_submit && be.submit_compact;
+            const bool try_packed = opt.packed_submit && be.submit_packed;
+            size_t* compact_bytes = &sp->compact_bytes;
+            size_t* n_packed = &sp->n_packed_blocks;
+            sp->how = std::async(std::launch::async, [=]() -> int {
+                if (try_compact) {
+                    std::vector<uint32_t> scratch(131072);
+                    if (rsq_pack_compact(src_reads, n, src_blocks, n_all_blocks, dst, cap, scratch.data(), compact_bytes) == RSQ_OK) return 2;
+                }
+                if (try_packed && rsq_pack_records(src_reads, n, src_blocks, n_all_blocks, (rsq_read_packed*)dst, (rsq_block*)(dst + blocks_off), n_packed) == RSQ_OK) return 1;
+                rsq_read* out = (rsq_read*)dst;
+                memcpy(out, src_reads, n * sizeof(rsq_read));
+                for (size_t i = 0; i < n; ++i) out[i].block_off -= (uint32_t)b0;
+                memcpy(dst + blocks_off, src_blocks + b0, nb * sizeof(rsq_block));
+                return 0;
+            });
+        };
+        int cur = 0;
         bool more = true;
         try {
         while (more) {
@@ -329,33 +501,39 @@ int run_sample(const Backend& be, CliOptions& opt) {
             }
             if (reads.empty()) break;
             submit_staged();
-            // stage into page-locked buffers; a slot is reused only after the device drained it
-            const size_t need[2] = {reads.size() * sizeof(rsq_read), std::max<size_t>(blocks.size(), 1) * sizeof(rsq_block)};
-            if (pinned_cap[slot][0]) { rc = be.sync(ctx); if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(ctx)); }
-            for (int k = 0; k < 2; ++k)
-                if (pinned_cap[slot][k] < need[k]) {
-                    if (pinned[slot][k]) be.host_free(pinned[slot][k]);
-                    pinned_cap[slot][k] = need[k] + need[k] / 4;
-                    pinned[slot][k] = be.host_alloc(pinned_cap[slot][k]);
-                    if (!pinned[slot][k]) throw HostError(10, "Memory allocation failure. Out of memory");
+            staged.reserve(n_lanes + 1);           // `stage` keeps pointers into the vector
+            if (n_lanes > 1 && decoder.saw_unsorted())
+                throw HostError(6, "--gpus needs a coordinate-sorted alignment file: records are range-partitioned by coordinate");
+            // split the batch where the stream crosses the pending cut (at most one crossing per lane)
+            size_t i = 0;
+            const size_t n = reads.size();
+            while (i < n) {
+                if (g + 1 >= n_lanes || !have_pending) { stage(g, reads, blocks, i, n); break; }
+                size_t j = i;
+                StreamCut k;
+                while (j < n && !(key_of(reads[j], k) && !before(k, pending))) ++j;
+                stage(g, reads, blocks, i, j);
+                if (j == n) break;
+                cuts.push_back(pending);
+                have_pending = false;
+                ++g;
+                i = j;
+            }
+            if (g + 1 < n_lanes && !have_pending) {
+                uint64_t on_lane = lanes[g].records;
+                for (const Staged& st : staged) if ((size_t)st.lane == g) on_lane += st.n_reads;
+                if (on_lane >= share()) {
+                    // the cut: the first island-free coordinate behind the last record of this batch
+                    StreamCut k;
+                    size_t j = n;
+                    while (j > 0 && !key_of(reads[j - 1], k)) --j;
+                    if (j > 0) {
+                        pending.contig_rank = k.contig_rank;
+                        pending.pos1 = islands.next_cut((uint32_t)reads[j - 1].contig, k.pos1 + 1);
+                        have_pending = true;
+                    }
                 }
-            // the compact wire format (32 B per record, no entry for a whole-read block) when the batch fits its rules; the
-            // packer writes straight into the pinned buffers, so it replaces the staging memcpy
-            staged.active = true; staged.slot = slot; staged.n_reads = reads.size(); staged.n_blocks = blocks.size(); staged.n_packed_blocks = 0;
-            const bool try_pack = opt.packed_submit && be.submit_packed;
-            void* dst_reads = pinned[slot][0];
-            void* dst_blocks = pinned[slot][1];
-            size_t* n_packed = &staged.n_packed_blocks;
-            const std::vector<rsq_read>* src_reads = &reads;
-            const std::vector<rsq_block>* src_blocks = &blocks;
-            staged.packed = std::async(std::launch::async, [=]() -> int {
-                if (try_pack && rsq_pack_records(src_reads->data(), src_reads->size(), src_blocks->data(), src_blocks->size(),
-                                                 (rsq_read_packed*)dst_reads, (rsq_block*)dst_blocks, n_packed) == RSQ_OK) return 1;
-                memcpy(dst_reads, src_reads->data(), src_reads->size() * sizeof(rsq_read));
-                memcpy(dst_blocks, src_blocks->data(), src_blocks->size() * sizeof(rsq_block));
-                return 0;
-            });
-            slot ^= 1;
+            }
             cur ^= 1;
             if (opt.verbosity > 1)
                 std::cout << "Time elapsed: " << std::chrono::duration<double>(clk::now() - t1).count()
@@ -363,21 +541,86 @@ int run_sample(const Backend& be, CliOptions& opt) {
         }
         submit_staged();
         } catch (...) {
-            if (staged.active && staged.packed.valid()) staged.packed.wait();   // the packer still reads the batch buffers
+            for (Staged& st : staged) if (st.how.valid()) st.how.wait();   // the packers still read the batch buffers
             throw;
         }
-        rc = be.sync(ctx);
-        if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(ctx));
+        for (Lane& L : lanes) {
+            int rc = be.sync(L.ctx);
+            if (rc != RSQ_OK) throw HostError(-1, std::string("rsq_sync failed: ") + be.last_error(L.ctx));
+        }
         if (opt.verbosity) {
             const double dt = std::chrono::duration<double>(clk::now() - t1).count();
             std::cout << "Time Elapsed: " << dt << "; Alignments processed: " << decoder.alignment_count() << std::endl;
             if (opt.verbosity > 1) std::cout << "Average Reads/Sec: " << (double)decoder.alignment_count() / dt << std::endl;
+            if (n_lanes > 1)
+                for (size_t k = 0; k < n_lanes; ++k)
+                    std::cout << "GPU " << lanes[k].device << ": " << lanes[k].records << " records in " << lanes[k].batches << " batches, "
+                              << lanes[k].wire_bytes << " bytes over the wire" << std::endl;
             std::cout << "Estimating library complexity..." << std::endl;
         }
         auto t_fin = clk::now();
         HostResults R;
-        fetch_results(be, ctx, A, false, R);                     // counts only: the per-base coverage stays on the device
-        fetch_coverage_statistics(be, ctx, A, opt.run, R);
+        if (n_lanes == 1) {
+            fetch_results(be, lanes[0].ctx, A, false, R);            // counts only: the per-base coverage stays on the device
+            fetch_coverage_statistics(be, lanes[0].ctx, A, opt.run, R);
+        } else {
+            // ---- end-of-run exchange (include/rsq_b200.h): afterwards every context holds the single-GPU state -------------
+            if (nccl) {
+                std::vector<std::future<int>> xs;
+                for (Lane& L : lanes) xs.push_back(std::async(std::launch::async, [&be, ctx = L.ctx] { return be.exchange(ctx); }));
+                int bad = RSQ_OK;
+                for (auto& f : xs) { const int r = f.get(); if (r != RSQ_OK) bad = r; }
+                if (bad != RSQ_OK) throw HostError(-1, std::string("rsq_exchange failed: ") + be.last_error(lanes[0].ctx));
+            } else {
+                auto reduce = [&](decltype(be.export_counts) exporter) {
+                    std::vector<uint64_t*> ptr(n_lanes);
+                    size_t words = 0;
+                    for (size_t k = 0; k < n_lanes; ++k)
+                        if (exporter(lanes[k].ctx, &ptr[k], &words) != RSQ_OK) throw HostError(-1, std::string("exchange export failed: ") + be.last_error(lanes[k].ctx));
+                    for (size_t w = 0; w < words; ++w) {
+                        uint64_t sum = 0;
+                        for (size_t k = 0; k < n_lanes; ++k) sum += ptr[k][w];
+                        for (size_t k = 0; k < n_lanes; ++k) ptr[k][w] = sum;
+                    }
+                };
+                reduce(be.export_sample_counts);
+                reduce(be.export_counts);
+                for (Lane& L : lanes) if (be.import_counts(L.ctx) != RSQ_OK) throw HostError(-1, "rsq_import_counts failed");
+            }
+            fetch_results(be, lanes[0].ctx, A, false, R);
+            // per-gene coverage statistics: every GPU evaluates the genes whose reads it holds; gathered as bitwise sums
+            for (size_t k = 0; k < n_lanes; ++k) gene_ownership(A, cuts, contig_rank, (uint32_t)k, lanes[k].owned);
+            std::vector<HostResults> parts(n_lanes);
+            std::vector<std::future<std::string>> cs;
+            for (size_t k = 0; k < n_lanes; ++k)
+                cs.push_back(std::async(std::launch::async, [&, k]() -> std::string {
+                    try { fetch_coverage_statistics(be, lanes[k].ctx, A, opt.run, parts[k], &lanes[k].owned); }
+                    catch (HostError& e) { return std::string(e.what()); }
+                    return std::string();
+                }));
+            std::string why;
+            for (auto& f : cs) { const std::string w = f.get(); if (why.empty()) why = w; }
+            if (!why.empty()) throw HostError(-1, why);
+            if (!nccl) {               // host transport: sum the bit patterns
+                auto fold = [&](auto member) {
+                    auto& dst = parts[0].*member;
+                    for (size_t k = 1; k < n_lanes; ++k) {
+                        auto& src = parts[k].*member;
+                        for (size_t i2 = 0; i2 < dst.size(); ++i2) {
+                            uint64_t a2, b2;
+                            memcpy(&a2, &dst[i2], 8); memcpy(&b2, &src[i2], 8);
+                            a2 += b2;
+                            memcpy(&dst[i2], &a2, 8);
+                        }
+                    }
+                };
+                fold(&HostResults::cs_mean); fold(&HostResults::cs_std); fold(&HostResults::cs_cv); fold(&HostResults::cs_exon_cv);
+                fold(&HostResults::cs_five); fold(&HostResults::cs_three);
+            }
+            R.cs_mean = parts[0].cs_mean; R.cs_std = parts[0].cs_std; R.cs_cv = parts[0].cs_cv; R.cs_exon_cv = parts[0].cs_exon_cv;
+            R.cs_five = parts[0].cs_five; R.cs_three = parts[0].cs_three;
+            R.have_cov_stats = true;
+        }
         StreamState st;
         st.read_length = decoder.read_length();
         st.alignment_count = decoder.alignment_count();
@@ -399,9 +642,11 @@ int run_sample(const Backend& be, CliOptions& opt) {
         std::cerr << "Unknown error" << std::endl << e.what() << std::endl;
         exit_code = -1;
     }
-    if (creating.valid()) creating.wait();
-    for (int s = 0; s < 2; ++s) for (int k = 0; k < 2; ++k) if (pinned[s][k]) be.host_free(pinned[s][k]);
-    if (ctx) be.destroy(ctx);
+    for (Staged& st : staged) if (st.how.valid()) st.how.wait();
+    for (Lane& L : lanes) {
+        if (L.creating.valid()) L.creating.wait();
+        L.release();
+    }
     return exit_code;
 }
 

@@ -25,11 +25,21 @@ struct Backend {
     decltype(&rsq_set_reference) set_reference;
     decltype(&rsq_submit) submit;
     decltype(&rsq_submit_packed) submit_packed;
+    decltype(&rsq_submit_compact) submit_compact;
     decltype(&rsq_sync) sync;
+    decltype(&rsq_sync_inputs) sync_inputs;
     decltype(&rsq_finalize) finalize;
     decltype(&rsq_coverage_statistics) coverage_statistics;
     decltype(&rsq_host_alloc) host_alloc;
     decltype(&rsq_host_free) host_free;
+    // coordinate-partitioned runs on several GPUs (--gpus N): the exchange protocol of include/rsq_b200.h
+    decltype(&rsq_set_partition) set_partition;
+    decltype(&rsq_export_sample_counts) export_sample_counts;
+    decltype(&rsq_export_counts) export_counts;
+    decltype(&rsq_import_counts) import_counts;
+    decltype(&rsq_comm_unique_id) comm_unique_id;
+    decltype(&rsq_comm_init) comm_init;
+    decltype(&rsq_exchange) exchange;
 };
 
 struct CliOptions {
@@ -40,7 +50,10 @@ struct CliOptions {
     bool legacy = false;
     std::string fasta;
     size_t batch_records = 1u << 20;
-    bool packed_submit = true;        // send batches in the compact wire format (rsq_read_packed) when they fit it
+    bool packed_submit = true;        // send batches in the wire formats (rsq_batch16, else rsq_read_packed) when they fit them
+    bool compact_submit = true;       // ... the 16-byte one first (--no-compact-submit: A/B)
+    std::vector<int> devices;         // --gpus N / --devices a,b,c: one context per GPU, records range-partitioned by coordinate
+    size_t records_per_gpu = 0;       // --records-per-gpu: records a GPU takes before the stream moves on to the next (0 = by file size)
     int decode_threads = -1;          // -1: hardware threads (<= 32); 0: sequential reader
     int verbosity = 0;
 };
@@ -55,6 +68,8 @@ int run_sample(const Backend& be, CliOptions& opt);
 // Pulls results out of a finalised ctx into HostResults sized for annotation A.
 void fetch_results(const Backend& be, rsq_ctx* ctx, const Annotation& A, bool want_coverage, HostResults& R);
 // Per-gene coverage statistics from the backend (device kernel in the product) into R.cs_*.
-void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation& A, const RunOptions& opt, HostResults& R);
+// `owned` (may be null): rsq_transcripts.gene_owned of a partitioned run.
+void fetch_coverage_statistics(const Backend& be, rsq_ctx* ctx, const Annotation& A, const RunOptions& opt, HostResults& R,
+                               const std::vector<uint8_t>* owned = nullptr);
 
 }  // namespace rsqh

@@ -833,6 +833,14 @@ int rsq_sync(rsq_ctx* ctx) {
     return RSQ_OK;
 }
 
+int rsq_sync_inputs(rsq_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return RSQ_ERR_INVALID;
+    CU_TRY(cudaSetDevice(c->cfg.device));
+    CU_TRY(cudaStreamSynchronize(c->copy_stream));
+    return RSQ_OK;
+}
+
 int rsq_reset(rsq_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !c->have_ann) return RSQ_ERR_INVALID;

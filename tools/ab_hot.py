@@ -44,7 +44,7 @@ def main():
     if cache and os.path.exists(cache):
         rb, bb = [t.to(args.device) for t in torch.load(cache)]
     else:
-        rb, bb = bench.generate_on_device(sa, ann, args.records, args.device, 0, 1)
+        rb, bb = bench.generate_on_device(sa, ann, args.records, args.device, None, 0)
         if cache:
             os.makedirs(args.cache, exist_ok=True)
             torch.save([rb.cpu(), bb.cpu()], cache)
