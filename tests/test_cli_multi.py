@@ -59,5 +59,5 @@ def test_multi_gpu_product_cli_equals_single_gpu(libs, tmp_path):
     flags = ["--coverage", "--bed", os.path.join(d, "a.bed"), "--fragment-samples", "300"]
     lanes = _run_and_compare(libs["cli"], d, flags, ["--gpus", str(n), "--records-per-gpu", str(20000 // n), "--batch-records", "1500"], 8)
     assert len(lanes) == n and sum(int(l.split()[2]) > 0 for l in lanes) >= min(n, 3), lanes
-    identical = set(compare_outputs(os.path.join(d, "expected", "coverage_bed"), os.path.join(d, "out_one")))
-    assert {"a.sam.gene_reads.gct", "a.sam.gene_fragments.gct"} <= identical
+    for f in ("a.sam.gene_reads.gct", "a.sam.gene_fragments.gct"):      # and the reference's golden (the tables the quota does not touch)
+        assert open(os.path.join(d, "expected", "coverage_bed", f)).read() == open(os.path.join(d, "out_many", f)).read(), f
