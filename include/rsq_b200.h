@@ -239,6 +239,12 @@ typedef struct rsq_annotation {
     const uint32_t* gline_order; /* [n_gene_lines] position among the kept GTF lines: ties of the list's
                                     stable sort by start (src/RNASeQC.cpp:150-152)                         */
     const uint32_t* exon_order;  /* [n_exons] same, for the exon lines                                     */
+    /* Gene index of each gene line's feature_id (it differs from gline_gene only when the line's gene_id was carried over
+     * from another line, src/GTF.cpp:90).  With the gene-line arrays and this one given, the path reproduces what happens once
+     * a gene line has left the reference's sliding window while one of the gene's exons reaches past it (trimFeatures,
+     * src/Expression.cpp:80-93: BaseCoverage::compute marks the gene "seen", fragmentTracker.erase): later reads of the gene
+     * start a new fragment set and their coverage is dropped (src/Metrics.cpp:108-112).  NULL: no gene is ever treated so. */
+    const uint32_t* gline_fid;   /* [n_gene_lines]                                                         */
 } rsq_annotation;
 
 /* BED intervals for the fragment-size sampler (src/BED.cpp:18-43, src/RNASeQC.cpp:172-187); intervals of a

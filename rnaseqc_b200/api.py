@@ -62,7 +62,8 @@ class RsqAnnotation(C.Structure):
                 ("seg_flags", C.POINTER(C.c_uint8)), ("gene_flags", C.POINTER(C.c_uint8)), ("cov_len", C.c_uint64),
                 ("n_gene_lines", C.c_uint32), ("reserved1", C.c_uint32), ("gline_off", C.POINTER(C.c_uint32)),
                 ("gline_start", C.POINTER(C.c_int32)), ("gline_end", C.POINTER(C.c_int32)), ("gline_gene", C.POINTER(C.c_uint32)),
-                ("gline_flags", C.POINTER(C.c_uint8)), ("gline_order", C.POINTER(C.c_uint32)), ("exon_order", C.POINTER(C.c_uint32))]
+                ("gline_flags", C.POINTER(C.c_uint8)), ("gline_order", C.POINTER(C.c_uint32)), ("exon_order", C.POINTER(C.c_uint32)),
+                ("gline_fid", C.POINTER(C.c_uint32))]
 
 
 class RsqBed(C.Structure):

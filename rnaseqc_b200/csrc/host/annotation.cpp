@@ -319,6 +319,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
             A.f_gline_start.push_back((int32_t)g.start);
             A.f_gline_end.push_back((int32_t)g.end);
             A.f_gline_gene.push_back(g.gid);
+            A.f_gline_fid.push_back(g.gene);
             A.f_gline_flags.push_back((uint8_t)(g.strand | (g.ribosomal ? RSQ_EXON_RIBOSOMAL : 0)));
             A.f_gline_order.push_back(g.line_order);
         }
@@ -436,6 +437,7 @@ rsq_annotation Annotation::view() const {
     v.gline_flags = f_gline_flags.data();
     v.gline_order = f_gline_order.data();
     v.exon_order = f_exon_order.data();
+    v.gline_fid = f_gline_fid.data();
     return v;
 }
 

@@ -89,7 +89,7 @@ struct Annotation {
     std::vector<uint8_t> f_exon_flags, f_seg_flags;
     std::vector<uint64_t> f_exon_cov_off;
     // gene lines as intervals + list-order ranks (read by the --legacy rules only)
-    std::vector<uint32_t> f_gline_off, f_gline_gene, f_gline_order, f_exon_order;
+    std::vector<uint32_t> f_gline_off, f_gline_gene, f_gline_order, f_exon_order, f_gline_fid;
     std::vector<int32_t> f_gline_start, f_gline_end;
     std::vector<uint8_t> f_gline_flags;
 

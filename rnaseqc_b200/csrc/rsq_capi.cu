@@ -570,7 +570,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     CU_TRY(cudaMalloc(&acc.frag_set, 8ull * c->frag_cap));
     acc.frag_cap = c->frag_cap;
     CU_TRY(cudaMalloc(&acc.algo_bytes, 8));
-    CU_TRY(cudaMalloc(&acc.error_flag, 8));   // [0] the flag; [1] the tile counter of the RSQ_DYNAMIC_TILES experiment
+    CU_TRY(cudaMalloc(&acc.error_flag, 8));   // [0] the flag; [1] spare
     // the export buffer of the end-of-run exchange is sized on first use (its tail depends on rsq_set_bed)
     c->have_ann = true;
     rc = zero_accumulators(c);

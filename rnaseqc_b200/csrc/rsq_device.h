@@ -28,7 +28,9 @@ struct __align__(16) CoverEntry {
     uint32_t gene_flags;       // gene index in the low 24 bits, flags in the high 8
     uint32_t slot;             // output slot (exonList order)
     uint64_t cov_off;          // first base of this exon in the coverage array
-    uint64_t exon_index;       // position in rsq_annotation's exon arrays (diagnostics)
+    int32_t  late_after;       // reads that start (0-based) beyond this coordinate find the gene already evicted from the reference's
+                               // sliding window (rsq_eit.h, gene_eviction_bounds); INT32_MAX = never
+    uint32_t reserved;
 };
 static_assert(sizeof(CoverEntry) == 32, "two 128-bit loads");
 

@@ -34,6 +34,31 @@ struct EiIndex {
     uint32_t                max_cover = 0;
 };
 
+// The reference keeps, per chromosome, ONE list of gene and exon lines, stable-sorted by start (src/RNASeQC.cpp:150-152), and pops
+// its front while front.end < Position() for every read that reaches the metrics (trimFeatures, src/Expression.cpp:80-93).  A
+// gene line therefore leaves the window at the first such read that starts beyond the largest end of everything at or before the
+// line in that list — its prefix maximum.  From then on the gene is "seen": BaseCoverage::commit drops its coverage
+// (src/Metrics.cpp:108-112) and its fragmentTracker set has been erased, so read names count again.  Only a gene with an exon
+// that reaches past that bound (not a collapsed-annotation shape) can still be hit afterwards.  Per gene index: the bound, or
+// INT32_MAX when the annotation carries no gene-line arrays or the gene has no line.
+inline void gene_eviction_bounds(const rsq_annotation* a, std::vector<int32_t>& bound) {
+    bound.assign(a->n_genes, INT32_MAX);
+    if (!a->gline_off || !a->gline_fid || !a->gline_order || !a->exon_order || !a->n_gene_lines) return;
+    struct Item { int32_t start, end; uint32_t order; uint32_t fid; };
+    std::vector<Item> list;
+    for (uint32_t c = 0; c < a->n_contigs; ++c) {
+        list.clear();
+        for (uint32_t i = a->gline_off[c]; i < a->gline_off[c + 1]; ++i) list.push_back(Item{a->gline_start[i], a->gline_end[i], a->gline_order[i], a->gline_fid[i]});
+        for (uint32_t i = a->exon_off[c]; i < a->exon_off[c + 1]; ++i) list.push_back(Item{a->exon_start[i], a->exon_end[i], a->exon_order[i], 0xffffffffu});
+        std::sort(list.begin(), list.end(), [](const Item& x, const Item& y) { return x.start != y.start ? x.start < y.start : x.order < y.order; });
+        int32_t pmax = INT32_MIN;
+        for (const Item& it : list) {
+            pmax = std::max(pmax, it.end);
+            if (it.fid != 0xffffffffu && it.fid < a->n_genes) bound[it.fid] = std::min(bound[it.fid], pmax);   // a second line of the id (another contig) cannot exist
+        }
+    }
+}
+
 // Returns an empty string on success, else the reason the index cannot be built.
 inline std::string build_ei_index(const rsq_annotation* a, EiIndex& X) {
     const uint32_t nc = a->n_contigs;
@@ -41,6 +66,8 @@ inline std::string build_ei_index(const rsq_annotation* a, EiIndex& X) {
     X.ei_start.clear(); X.ei_desc.clear(); X.cover.clear(); X.eib.clear();
     std::vector<int64_t> cuts;
     std::vector<uint32_t> cnt, fill;
+    std::vector<int32_t> late_after;
+    gene_eviction_bounds(a, late_after);
     for (uint32_t c = 0; c < nc; ++c) {
         const uint32_t e0 = a->exon_off[c], e1 = a->exon_off[c + 1], s0 = a->seg_off[c], s1 = a->seg_off[c + 1];
         cuts.clear();
@@ -95,7 +122,7 @@ inline std::string build_ei_index(const rsq_annotation* a, EiIndex& X) {
             uint32_t fl = a->exon_flags[i] & (RSQ_EXON_STRAND_MASK | RSQ_EXON_RIBOSOMAL);
             if (g < a->n_genes && (a->gene_flags[g] & RSQ_GENE_GLOBIN)) fl |= kCoverGlobin;
             ce.gene_flags = (g & 0xffffffu) | (fl << 24);
-            ce.slot = a->exon_slot[i]; ce.cov_off = a->exon_cov_off[i]; ce.exon_index = i;
+            ce.slot = a->exon_slot[i]; ce.cov_off = a->exon_cov_off[i]; ce.late_after = g < a->n_genes ? late_after[g] : INT32_MAX; ce.reserved = 0;
             for (size_t k = k0; k <= k1; ++k) X.cover[first[k] + fill[k]++] = ce;
         }
         for (size_t k = 0; k < n; ++k) {
@@ -118,7 +145,7 @@ inline std::string build_ei_index(const rsq_annotation* a, EiIndex& X) {
     X.eib_off[nc] = (uint32_t)X.eib.size();
     X.ei_desc.insert(X.ei_desc.end(), 1 + kEiPad, EiDesc{(uint32_t)X.cover.size(), 0u});   // padded like ei_start: staged by bulk copies too
     X.ei_start.insert(X.ei_start.end(), kEiPad, INT32_MAX);
-    X.cover.push_back(CoverEntry{0, -1, 0, 0, 0, 0});   // spare entry: the fast path loads cover[cover_off] even when the count is 0
+    X.cover.push_back(CoverEntry{0, -1, 0, 0, 0, INT32_MAX, 0});   // spare entry: the fast path loads cover[cover_off] even when the count is 0
     return std::string();
 }
 

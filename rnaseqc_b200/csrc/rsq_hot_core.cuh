@@ -30,6 +30,14 @@ constexpr uint32_t kNoGene = 0xffffffffu;
 RSQ_HD int imin(int a, int b) { return a < b ? a : b; }
 RSQ_HD int imax(int a, int b) { return a > b ? a : b; }
 
+RSQ_HD unsigned long long umulhi64(unsigned long long a, unsigned long long b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
 RSQ_HD unsigned long long mix64(unsigned long long x) {
     x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
     x ^= x >> 27; x *= 0x94d049bb133111ebull;
@@ -46,7 +54,14 @@ RSQ_HD void frac_q64(const unsigned long long* recip64, uint32_t isz, uint32_t l
     if (length < 65536u) {
         const unsigned long long R = ldro(recip64 + length);
         const uint32_t r0 = (uint32_t)(0ull - R * (unsigned long long)length);
+#ifdef RSQ_FRAC_DIVIDE
         lo = (unsigned long long)isz * R + (unsigned long long)((isz * r0) / length);
+#else
+        // floor(x / L) for x = isz * r0 < L^2 < 2^32 without a divide: with c = R + 1 = 2^64 / L + d, 0 < d <= 1, the product
+        // x * c / 2^64 = x / L + x * d / 2^64 exceeds x / L by less than 2^-32, and x / L lies at least 1 / L >= 2^-16 below the
+        // next integer unless it is one: the high word is the exact quotient
+        lo = (unsigned long long)isz * R + umulhi64((unsigned long long)(isz * r0), R + 1ull);
+#endif
         return;
     }
     unsigned long long r = isz;
@@ -270,8 +285,13 @@ RSQ_HD CoverHead cover_head(const AnnView& ann, uint32_t j) {
     CoverHead h; h.start = v.x; h.end = v.y; h.gene_flags = (uint32_t)v.z; h.slot = (uint32_t)v.w;
     return h;
 }
-RSQ_HD unsigned long long cover_cov_off(const AnnView& ann, uint32_t j) {
-    return ldro(reinterpret_cast<const unsigned long long*>(ann.cover) + 4 * (size_t)j + 2);
+// second 16 bytes of a CoverEntry: where the exon's bases start in the coverage array, and the coordinate beyond which reads find
+// the exon's gene already evicted from the reference's sliding window (rsq_eit.h, gene_eviction_bounds)
+struct CoverTail { unsigned long long cov_off; int late_after; };
+RSQ_HD CoverTail cover_tail(const AnnView& ann, uint32_t j) {
+    const int4 v = ldro(reinterpret_cast<const int4*>(ann.cover) + 2 * (size_t)j + 1);
+    CoverTail t; t.cov_off = ((unsigned long long)(uint32_t)v.y << 32) | (uint32_t)v.x; t.late_after = v.z;
+    return t;
 }
 // does the exon fully contain the block (it covers the block's start by construction) and pass the strand filter?
 // partialIntersect == block length, src/Expression.cpp:341; strand test :331
@@ -292,9 +312,11 @@ struct ExonOut { bool exonic, do_exon; BlockRef r0; };
 
 // Collector::collect + BaseCoverage::commit for one (block, containing exon) pair of a gene in `last`
 // (src/Expression.cpp:345-347,390-391; Metrics.cpp:59-66,106-124,257-262).
+// `late`: the gene has left the reference's window (BaseCoverage::commit returns at "Gene encountered after computing coverage",
+// src/Metrics.cpp:108-112): the exon count is still collected, the coverage is not.
 template <class Mem>
 RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, const Accum& acc, const CoverHead& h, unsigned long long cov_off,
-                           int bs, uint32_t len, uint32_t length, RecOut& o) {
+                           bool late, int bs, uint32_t len, uint32_t length, RecOut& o) {
     unsigned long long whole, lo;
     frac_q64(ann.recip64, len, length, whole, lo);                                          // isz/length, :345
     // exact Q64.64 sum kept as three carry-free words (whole, frac>>32, frac&0xffffffff): every update is a fire-and-forget
@@ -302,7 +324,7 @@ RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, cons
     if (whole) mem.exon_one(acc, h.slot);
     else mem.exon_frac(acc, h.slot, (uint32_t)(lo >> 32), (uint32_t)lo);
     o.my_bytes += 8u;
-    if (prm.collect_coverage) {                                                            // add_range as +1/-1, Metrics.cpp:257-262
+    if (prm.collect_coverage && !late) {                                                   // add_range as +1/-1, Metrics.cpp:257-262
         mem.cov_range(&acc.cov_diff[cov_off + (unsigned long long)(bs - h.start)], len);   // +1 at the first base, -1 behind the last
         o.my_bytes += 8u;
     }
@@ -312,11 +334,13 @@ RSQ_HD void accumulate_hit(Mem& mem, const AnnView& ann, const Params& prm, cons
 // fragment tracker here: its key travels in RecOut; the kernel parks it for one tile while the table line is prefetched
 // into L2 and inserts it then (the host emulation inserts it right away) — two dependent HBM round trips that no longer sit
 // in this thread's chain.  Further genes of the same read (overlapping annotations, rare) are inserted on the spot.
+// `late`: the gene's fragmentTracker set was erased when its gene line left the window (trimFeatures, src/Expression.cpp:86-90); the
+// reads that still reach the gene afterwards fill a second set, so the key carries that epoch.
 template <class Mem>
-RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsigned long long name_hash, RecOut& o) {
+RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, bool late, unsigned long long name_hash, RecOut& o) {
     // name_hash is a mixed 64-bit hash already (rsq_read.name_hash); one odd multiply is a bijection that carries every bit of
-    // (name, gene) into the high half, where the table takes its home slot from
-    const unsigned long long key0 = (name_hash ^ ((unsigned long long)(g + 1u) << 40)) * 0x9E3779B97F4A7C15ull;
+    // (name, gene, epoch) into the high half, where the table takes its home slot from
+    const unsigned long long key0 = (name_hash ^ ((unsigned long long)(g + 1u) << 40) ^ (late ? 1ull << 39 : 0ull)) * 0x9E3779B97F4A7C15ull;
     const unsigned long long key = key0 ? key0 : 1ull;
     if (o.agg_gene == kNoGene) { o.agg_gene = g; o.agg_unique = !(f & RSQ_F_DUP); o.frag_key = key; }
     else {
@@ -334,7 +358,7 @@ RSQ_HD void count_gene(Mem& mem, const Accum& acc, uint32_t f, uint32_t g, unsig
 // frag_insert(key) -> bool (true when the key was not in the fragment tracker yet).
 template <class Mem>
 RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const Params& prm, const Accum& acc, uint32_t f, bool hq, bool cleared,
-                         int contig, int rstrand, const rsq_block* bp, uint32_t nb, unsigned long long name_hash, RecOut& o, ExonOut& x) {
+                         int contig, int pos0, int rstrand, const rsq_block* bp, uint32_t nb, unsigned long long name_hash, RecOut& o, ExonOut& x) {
     uint32_t length = 0, cls = 0;                                                          // extractBlocks' return, :359
     BlockRef r0 = {0, 0, 0u, 0u}, r1 = r0;
     bool globin = false, do_exon = false, fast = false;
@@ -368,7 +392,7 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
             if (nb0 > be0 && nb1 > be1 && cn0 <= 1u && cn1 <= 1u) {
                 // the cover array carries one spare entry, so these loads are unconditional (used only when cn == 1)
                 const CoverHead h0 = cover_head(ann, d0.x), h1 = cover_head(ann, d1.x);
-                const unsigned long long c0 = cover_cov_off(ann, d0.x), c1 = cover_cov_off(ann, d1.x);
+                const CoverTail t0 = cover_tail(ann, d0.x), t1 = cover_tail(ann, d1.x);
                 length = (uint32_t)k0.y + (nb >= 2 ? (uint32_t)k1.y : 0u);
                 cls = (d0.y | d1.y | over) & 0xffffu;
                 r0.bs = bs0; r0.be = be0; r0.coff = d0.x; r0.cn = cn0;
@@ -404,13 +428,14 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
                     do_exon = true;                                                        // :393
                     if ((h0.gene_flags >> 24) & kCoverGlobin) globin = true;               // :396-398
                     if (hq) {
-                        if (length > 0) count_gene(mem, acc, f, g, name_hash, o);          // queryGene: some coverage > 0, :380
-                        if (k0.y) accumulate_hit(mem, ann, prm, acc, h0, c0, bs0, (uint32_t)k0.y, length, o);
-                        if (nb >= 2 && k1.y) accumulate_hit(mem, ann, prm, acc, h1, c1, bs1, (uint32_t)k1.y, length, o);
+                        const bool late = pos0 > t0.late_after;                            // a property of the gene: the same for every block
+                        if (length > 0) count_gene(mem, acc, f, g, late, name_hash, o);    // queryGene: some coverage > 0, :380
+                        if (k0.y) accumulate_hit(mem, ann, prm, acc, h0, t0.cov_off, late, bs0, (uint32_t)k0.y, length, o);
+                        if (nb >= 2 && k1.y) accumulate_hit(mem, ann, prm, acc, h1, t1.cov_off, late, bs1, (uint32_t)k1.y, length, o);
                         for (uint32_t b = 2; b < nb; ++b) {
                             BlockRef r; CoverHead h; uint32_t flags = 0;
                             one_block(b, r, h, flags);
-                            if (r.be != r.bs) accumulate_hit(mem, ann, prm, acc, h, cover_cov_off(ann, r.coff), r.bs, (uint32_t)(r.be - r.bs), length, o);
+                            if (r.be != r.bs) accumulate_hit(mem, ann, prm, acc, h, cover_tail(ann, r.coff).cov_off, late, r.bs, (uint32_t)(r.be - r.bs), length, o);
                         }
                     }
                 }
@@ -456,7 +481,8 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
                 do_exon = true;                                                            // :393
                 if ((h0.gene_flags >> 24) & kCoverGlobin) globin = true;                   // :396-398
                 if (!hq) continue;
-                if (length > 0) count_gene(mem, acc, f, g, name_hash, o);                  // queryGene: some coverage > 0, :380
+                const bool late = pos0 > cover_tail(ann, r0.coff + j).late_after;
+                if (length > 0) count_gene(mem, acc, f, g, late, name_hash, o);            // queryGene: some coverage > 0, :380
                 // Collector::collect + BaseCoverage::commit for gene g: every (block, containing exon of g) pair
                 for (uint32_t b = 0; b < nb; ++b) {
                     const BlockRef r = b == 0 ? r0 : (b == 1 ? r1 : ref_of(b));
@@ -465,7 +491,7 @@ RSQ_HD void exon_metrics(Mem& mem, const AnnView& ann, const TileWin& w, const P
                     for (uint32_t jj = 0; jj < r.cn; ++jj) {
                         const CoverHead h = cover_head(ann, r.coff + jj);
                         if (!cover_admits(h, r, rstrand) || (h.gene_flags & 0xffffffu) != g) continue;
-                        accumulate_hit(mem, ann, prm, acc, h, cover_cov_off(ann, r.coff + jj), r.bs, len, length, o);
+                        accumulate_hit(mem, ann, prm, acc, h, cover_tail(ann, r.coff + jj).cov_off, late, r.bs, len, length, o);
                     }
                 }
             }

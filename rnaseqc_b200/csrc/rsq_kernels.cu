@@ -273,19 +273,13 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     // Persistent warps: warp w of the grid takes 32-record tiles w, w + W, w + 2W, ... No CTA barrier inside the loop.
     uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     unsigned long long own_lo = 0ull, own_hi = 0ull, own_bytes = 0ull;   // lane-owned counters (see the epilogue)
-#ifdef RSQ_DYNAMIC_TILES
-    // Experiment: after its first two tiles (static, so that the look-ahead below has something to look at) a warp takes the
-    // next unclaimed tile from a device counter, asked for one whole tile of work before it is needed: warps that drew cheap
-    // tiles (intergenic stretches) take more of them, and the end of the launch is not set by the unluckiest static stride.
-    uint32_t tile_after = tile + warps_total;
-  while (tile < n_tiles) {
-    uint32_t claimed = 0;
-    if (lane == 0) claimed = atomicAdd(acc.error_flag + 1, 1u) + 2u * warps_total;   // consumed at the bottom of the loop
-#define RSQ_TILE_NEXT tile_after
-#else
+#if defined(RSQ_PEEK2) && !defined(RSQ_AB_NO_PREFETCH)
+    uint32_t peek_boff = 0;                                              // block offset of this lane's record in the NEXT tile
+    if ((size_t)(tile + warps_total) * 32u + lane < n_reads)
+        peek_boff = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(reads + ((size_t)(tile + warps_total) * 32u + lane)) + 40));
+#endif
   for (; tile < n_tiles; tile += warps_total) {
 #define RSQ_TILE_NEXT (tile + warps_total)
-#endif
     const uint32_t i = tile * 32u + lane;
     const bool valid = i < n_reads;
     int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0;
@@ -300,8 +294,22 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     uint32_t next_boff = 0;
     const bool has_next = RSQ_TILE_NEXT * 32u + lane < n_reads;               // no wrap: n_reads < 2^31 (launcher)
 #ifndef RSQ_AB_NO_PREFETCH
+#ifdef RSQ_PEEK2
+    // Two tiles ahead: the block offsets asked for during the PREVIOUS tile are used now (they had a whole tile of work to
+    // arrive: the prefetch below never waits), and the records of the tile after the next are pulled into L2 whole (twelve
+    // 128-byte lines per tile) instead of the two sectors out of three that the offset loads happen to touch.
+    next_boff = peek_boff;
+    {
+        const size_t t2 = (size_t)tile + 2u * (size_t)warps_total;
+        if (t2 * 32u + lane < n_reads)
+            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(peek_boff) : "l"(reinterpret_cast<const char*>(reads + (t2 * 32u + lane)) + 40));
+        if (lane < 12u && t2 * 32u < n_reads)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(reads + t2 * 32u) + 128u * lane));
+    }
+#else
     if (has_next)
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(next_boff) : "l"(reinterpret_cast<const char*>(reads + ((size_t)RSQ_TILE_NEXT * 32u + lane)) + 40));
+#endif
 #endif
 
     // ---- stage this tile's run of interval starts (warp-uniform) ----------------------------------------------------------
@@ -381,7 +389,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             } else {
             const DevMem mem{acc, (unsigned long long)ann.n_exons, prm.cov_len_diag};
             ExonOut x;
-            exon_metrics(mem, ann, w, prm, acc, f, hq, cleared, contig, rstrand, bp, nb, name_hash, o, x);
+            exon_metrics(mem, ann, w, prm, acc, f, hq, cleared, contig, pos, rstrand, bp, nb, name_hash, o, x);
 
             // ---- fragment GC content candidate, Expression.cpp:459-467 --------------------------------------------------
             if constexpr (kGc) {
@@ -532,8 +540,16 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
 #else
         static_assert(RSQ_C_FRAGSET_ENTRIES == 54, "11 words of 5 counters cover every counter in use");
         unsigned vlo = 0, vhi = 0;
+#ifdef RSQ_SKIP_RARE_WORDS
+        // words 9 and 10 hold the counters 45..53 (filter tags 1..7, Split Reads, Fragment Candidates): zero for whole tiles
+        // on most inputs — one vote instead of two reductions
+        const bool rare = __any_sync(kFull, (o.cm >> 45) != 0ull);
+#else
+        constexpr bool rare = true;
+#endif
 #pragma unroll
         for (int wd = 0; wd < 11; ++wd) {
+            if (wd >= 9 && !rare) break;
             const unsigned x = (unsigned)(o.cm >> (5 * wd)) & 31u;
             const unsigned sum = __reduce_add_sync(kFull, (x * 0x108421u) & 0x1041041u);
             if (wd <= 6) vlo = (lane / 5u == (unsigned)wd) ? sum : vlo;
@@ -545,10 +561,29 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     }
     // valued counters (Metrics::increment(key, int), Metrics.cpp:33-36): signed 32-bit warp sums, sign-extended
     {
+#ifdef RSQ_PACK_VALUED
+        // short reads: every addend is below 2^11, so two 32-lane sums fit one word (16 bits each) — four reductions instead of
+        // seven; one vote sends tiles with a longer read, a larger NM or a negative value down the exact general path
+        int s_mm1, s_b1, s_mm2, s_b2, s_mm, s_tb, s_nb;
+        if (!__any_sync(kFull, ((unsigned)l_qseq | (unsigned)nm_raw | nb) >> 11)) {
+            const unsigned both = (unsigned)nm_raw | ((unsigned)l_qseq << 16);
+            const unsigned a1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? both : 0u), a2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? both : 0u);
+            const unsigned a3 = __reduce_add_sync(kFull, ((o.vflags & 4u) ? (unsigned)nm_raw : 0u) | ((o.vflags & 8u) ? (unsigned)l_qseq << 16 : 0u));
+            s_nb = (int)__reduce_add_sync(kFull, (o.vflags & 16u) ? nb : 0u);
+            s_mm1 = (int)(a1 & 0xffffu); s_b1 = (int)(a1 >> 16); s_mm2 = (int)(a2 & 0xffffu); s_b2 = (int)(a2 >> 16);
+            s_mm = (int)(a3 & 0xffffu); s_tb = (int)(a3 >> 16);
+        } else {
+            s_mm1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? nm_raw : 0); s_b1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? l_qseq : 0);
+            s_mm2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? nm_raw : 0); s_b2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? l_qseq : 0);
+            s_mm = __reduce_add_sync(kFull, (o.vflags & 4u) ? nm_raw : 0); s_tb = __reduce_add_sync(kFull, (o.vflags & 8u) ? l_qseq : 0);
+            s_nb = __reduce_add_sync(kFull, (o.vflags & 16u) ? (int)nb : 0);
+        }
+#else
         const int s_mm1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? nm_raw : 0), s_b1 = __reduce_add_sync(kFull, (o.vflags & 1u) ? l_qseq : 0);
         const int s_mm2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? nm_raw : 0), s_b2 = __reduce_add_sync(kFull, (o.vflags & 2u) ? l_qseq : 0);
         const int s_mm = __reduce_add_sync(kFull, (o.vflags & 4u) ? nm_raw : 0), s_tb = __reduce_add_sync(kFull, (o.vflags & 8u) ? l_qseq : 0);
         const int s_nb = __reduce_add_sync(kFull, (o.vflags & 16u) ? (int)nb : 0);
+#endif
         // algorithmic bytes: every lane keeps its own sum; new fragment-set entries: the parked ones are warp-uniform, the
         // on-the-spot ones (second genes of a read) are rare enough for a shared-memory add
         own_bytes += o.my_bytes;
@@ -567,10 +602,6 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         mine = lane == RSQ_C_ALIGNMENT_BLOCKS ? s_nb : mine;
         own_lo += (unsigned long long)(long long)mine;
     }
-#ifdef RSQ_DYNAMIC_TILES
-    tile = tile_after;
-    tile_after = __shfl_sync(kFull, claimed, 0);
-#endif
   }  // tile loop
     if constexpr (!kLegacy) {                                                        // the last tile's parked keys
         const int s_late = resolve_parked(st, acc, lane);
@@ -1090,9 +1121,6 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     }
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
-#ifdef RSQ_DYNAMIC_TILES
-    cudaMemsetAsync(acc.error_flag + 1, 0, 4, stream);                               // the tile counter (second word of the allocation)
-#endif
     kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
     return 1;
 }

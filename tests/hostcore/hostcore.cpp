@@ -109,7 +109,7 @@ extern "C" int hostcore_run(const rsq_annotation* a, const rsq_config* cfg, cons
                         ++stats[(w.on && k.start >= w.wmin && k.start + k.len < w.lastv) ? 0 : 1];
                     }
                 ExonOut x;
-                exon_metrics(mem, ann, w, prm, acc, r.flag, o.hq, cleared, r.contig, rstrand, blocks + r.block_off, nb, r.name_hash, o, x);
+                exon_metrics(mem, ann, w, prm, acc, r.flag, o.hq, cleared, r.contig, r.pos, rstrand, blocks + r.block_off, nb, r.name_hash, o, x);
                 ++stats[o.fast ? 4 : 5];
                 if (!o.fast) tile_general = true;
             }

@@ -216,6 +216,8 @@ def _fuzz_case(api, tmp_path, seed):
         while p <= ge and k < 12:
             es = p
             ee = min(ge, es + int(rng.integers(0, max(1, (ge - gs) // 3 + 1))))
+            if rng.random() < 0.12:                                                   # an exon that reaches past its gene line: reads on the
+                ee = es + int(rng.integers(0, max(2, span // 6)))                     # far side find the gene evicted (rsq_eit.h, gene_eviction_bounds)
             rows.append(f'{chrom}\tf\texon\t{es}\t{ee}\t.\t{strand}\t.\t{common} exon_id "G{g}_{k}";')
             cuts[chrom] += [es, ee, ee + 1]
             k += 1

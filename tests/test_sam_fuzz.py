@@ -309,10 +309,13 @@ def _wild_gtf(path, rng):
             if rng.random() < 0.5:
                 lines.append(f"{chrom}\tw\ttranscript\t{gs}\t{ge}\t.\t{strand}\t.\t{common}")
             for k in range(rng.choice([0, 1, 1, 2, 3, 5, 8])):
-                # inside the gene's span: the reference integrates a gene's coverage when its gene line leaves the window, so reads
-                # on an exon that reaches past the gene line's end come too late for it (not reproduced: DESIGN.md §6)
+                # mostly inside the gene's span; one exon in six reaches past the gene line's end: the reference integrates a gene's
+                # coverage and erases its fragment set when the gene line leaves the window, so reads on the far side come too late
+                # for the coverage and count their fragments anew (rsq_eit.h, gene_eviction_bounds)
                 es = rng.randint(gs, ge)
-                ee = min(ge, es + rng.choice([0, 1, 30, 120, 120, 300, 500, 1200, 2500]))
+                ee = es + rng.choice([0, 1, 30, 120, 120, 300, 500, 1200, 2500])
+                if rng.random() < 0.84:
+                    ee = min(ge, ee)
                 if k and rng.random() < 0.2:
                     es, ee = prev                                                   # same coordinates as the previous exon
                 prev = (es, ee)
