@@ -83,6 +83,7 @@ struct Ctx {
     unsigned slot = 0;
     // bookkeeping
     unsigned long long records_submitted = 0;
+    unsigned long long mate_launches = 0;     // launches with a mate map on: numbers the rounds of the mate-map stages
     unsigned long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;
     size_t timers_used = 0;
@@ -186,15 +187,20 @@ int zero_accumulators(Ctx* c) {
     CU_TRY(cudaMemsetAsync(a.error_flag, 0, 4, c->stream));
     if (c->have_bed && c->cfg.fragment_samples) {
         CU_TRY(cudaMemsetAsync(a.pair_keys, 0, 8ull * c->pair_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(a.pair_first, 0xff, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.pair_first, 0, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.pair_second, 0, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.pair_payload, 0xff, 8ull * c->pair_cap, c->stream));      // kMateEmpty
         CU_TRY(cudaMemsetAsync(a.sample_count, 0, 8, c->stream));
     }
     if (c->have_ref) {
         CU_TRY(cudaMemsetAsync(a.gc_keys, 0, 8ull * c->gc_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(a.gc_first, 0xff, 8ull * c->gc_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.gc_first, 0, 8ull * c->gc_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.gc_second, 0, 8ull * c->gc_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(a.gc_payload, 0xff, 8ull * c->gc_cap, c->stream));
         CU_TRY(cudaMemsetAsync(a.gc_hist, 0, 8 * 100, c->stream));
     }
     c->records_submitted = 0;
+    c->mate_launches = 0;
     c->found_valid = false;
     c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
@@ -268,16 +274,19 @@ int ensure_pair_capacity(Ctx* c, size_t n) {
     const unsigned long long need = c->records_submitted + n;
     if (need <= c->pair_cap / 4 * 3) return RSQ_OK;
     const unsigned long long new_cap = next_pow2(need / 3 * 4 + 4);
-    unsigned long long *nk = nullptr, *nf = nullptr, *np = nullptr;
+    unsigned long long *nk = nullptr, *nf = nullptr, *ns = nullptr, *np = nullptr;
     CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
     CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
+    CU_TRY(cudaMalloc(&ns, 8ull * new_cap));
     CU_TRY(cudaMalloc(&np, 8ull * new_cap));
     CU_TRY(cudaMemsetAsync(nk, 0, 8ull * new_cap, c->stream));
-    CU_TRY(cudaMemsetAsync(nf, 0xff, 8ull * new_cap, c->stream));
-    c->launches += launch_pair_rehash(c->acc, c->pair_cap, nk, nf, np, new_cap - 1, c->acc.error_flag, c->stream);
+    CU_TRY(cudaMemsetAsync(nf, 0, 8ull * new_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(ns, 0, 8ull * new_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(np, 0xff, 8ull * new_cap, c->stream));
+    c->launches += launch_pair_rehash(c->acc.pair_keys, c->acc.pair_payload, c->pair_cap, nk, np, new_cap - 1, c->acc.error_flag, c->stream);
     CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->acc.pair_keys); cudaFree(c->acc.pair_first); cudaFree(c->acc.pair_payload);
-    c->acc.pair_keys = nk; c->acc.pair_first = nf; c->acc.pair_payload = np;
+    cudaFree(c->acc.pair_keys); cudaFree(c->acc.pair_first); cudaFree(c->acc.pair_second); cudaFree(c->acc.pair_payload);
+    c->acc.pair_keys = nk; c->acc.pair_first = nf; c->acc.pair_second = ns; c->acc.pair_payload = np;
     c->acc.pair_mask = new_cap - 1;
     c->pair_cap = new_cap;
     return RSQ_OK;
@@ -297,18 +306,19 @@ int ensure_gc_capacity(Ctx* c, size_t n) {
     const unsigned long long need = c->records_submitted + n;
     if (need <= c->gc_cap / 4 * 3) return RSQ_OK;
     const unsigned long long new_cap = next_pow2(need / 3 * 4 + 4);
-    unsigned long long *nk = nullptr, *nf = nullptr, *np = nullptr;
+    unsigned long long *nk = nullptr, *nf = nullptr, *ns = nullptr, *np = nullptr;
     CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
     CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
+    CU_TRY(cudaMalloc(&ns, 8ull * new_cap));
     CU_TRY(cudaMalloc(&np, 8ull * new_cap));
     CU_TRY(cudaMemsetAsync(nk, 0, 8ull * new_cap, c->stream));
-    CU_TRY(cudaMemsetAsync(nf, 0xff, 8ull * new_cap, c->stream));
-    Accum as_pair = c->acc;             // the rehash kernel reads the table through the pair_* fields
-    as_pair.pair_keys = c->acc.gc_keys; as_pair.pair_first = c->acc.gc_first; as_pair.pair_payload = c->acc.gc_payload;
-    c->launches += launch_pair_rehash(as_pair, c->gc_cap, nk, nf, np, new_cap - 1, c->acc.error_flag, c->stream);
+    CU_TRY(cudaMemsetAsync(nf, 0, 8ull * new_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(ns, 0, 8ull * new_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(np, 0xff, 8ull * new_cap, c->stream));
+    c->launches += launch_pair_rehash(c->acc.gc_keys, c->acc.gc_payload, c->gc_cap, nk, np, new_cap - 1, c->acc.error_flag, c->stream);
     CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->acc.gc_keys); cudaFree(c->acc.gc_first); cudaFree(c->acc.gc_payload);
-    c->acc.gc_keys = nk; c->acc.gc_first = nf; c->acc.gc_payload = np;
+    cudaFree(c->acc.gc_keys); cudaFree(c->acc.gc_first); cudaFree(c->acc.gc_second); cudaFree(c->acc.gc_payload);
+    c->acc.gc_keys = nk; c->acc.gc_first = nf; c->acc.gc_second = ns; c->acc.gc_payload = np;
     c->acc.gc_mask = new_cap - 1;
     c->gc_cap = new_cap;
     return RSQ_OK;
@@ -362,6 +372,11 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
         rc = reserve_frag_capacity(c, &n);      // may cut the launch down to the room left in the fragment-tracker set
         if (rc != RSQ_OK) return rc;
         prm.record_base = c->records_submitted + base;
+        if (prm.bed_enabled || prm.gc_enabled) {
+            if (++c->mate_launches >= (1ull << 23)) { c->err = "too many launches for the mate-map round tags"; return RSQ_ERR_CAPACITY; }
+            prm.mate_round = c->mate_launches << 17;
+            CU_TRY(cudaMemsetAsync(c->acc.mate_left_count, 0, 8, c->stream));
+        }
         if (prm.bed_enabled) {
             CU_TRY(cudaMemsetAsync(c->acc.cand_count, 0, 4, c->stream));
             CU_TRY(cudaMemsetAsync(c->acc.sample_flag, 0, n, c->stream));
@@ -430,7 +445,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     free_list(c->bed_allocs);
     free_list(c->ref_allocs);
     Accum& a = c->acc;
-    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_payload, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
+    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_second, a.gc_payload, a.pair_second, a.mate_left, a.mate_left_count, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_owned, c->d_found, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
@@ -598,12 +613,16 @@ int rsq_set_reference(rsq_ctx* ctx, const rsq_reference* r) {
     c->gc_cap = next_pow2((c->cfg.max_records ? c->cfg.max_records : (1ull << 24)) / 3 * 4 + 4);
     CU_TRY(cudaMalloc(&acc.gc_keys, 8ull * c->gc_cap));
     CU_TRY(cudaMalloc(&acc.gc_first, 8ull * c->gc_cap));
+    CU_TRY(cudaMalloc(&acc.gc_second, 8ull * c->gc_cap));
     CU_TRY(cudaMalloc(&acc.gc_payload, 8ull * c->gc_cap));
     acc.gc_mask = c->gc_cap - 1;
+    if (!acc.mate_left) { CU_TRY(cudaMalloc(&acc.mate_left, 4ull * 2 * kMateLeftCap)); CU_TRY(cudaMalloc(&acc.mate_left_count, 8)); }
     CU_TRY(cudaMalloc(&acc.gc_cand_count, 4));
     CU_TRY(cudaMalloc(&acc.gc_hist, 8 * 100));
     CU_TRY(cudaMemsetAsync(acc.gc_keys, 0, 8ull * c->gc_cap, c->stream));
-    CU_TRY(cudaMemsetAsync(acc.gc_first, 0xff, 8ull * c->gc_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(acc.gc_first, 0, 8ull * c->gc_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(acc.gc_second, 0, 8ull * c->gc_cap, c->stream));
+    CU_TRY(cudaMemsetAsync(acc.gc_payload, 0xff, 8ull * c->gc_cap, c->stream));
     CU_TRY(cudaMemsetAsync(acc.gc_hist, 0, 8 * 100, c->stream));
     CU_TRY(cudaMemsetAsync(acc.gc_cand_count, 0, 4, c->stream));
     c->have_ref = true;
@@ -662,13 +681,17 @@ int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* b) {
         c->pair_cap = next_pow2((c->cfg.max_records ? c->cfg.max_records : (1ull << 24)) / 3 * 4 + 4);
         CU_TRY(cudaMalloc(&acc.pair_keys, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_first, 8ull * c->pair_cap));
+        CU_TRY(cudaMalloc(&acc.pair_second, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_payload, 8ull * c->pair_cap));
         acc.pair_mask = c->pair_cap - 1;
+        if (!acc.mate_left) { CU_TRY(cudaMalloc(&acc.mate_left, 4ull * 2 * kMateLeftCap)); CU_TRY(cudaMalloc(&acc.mate_left_count, 8)); }
         CU_TRY(cudaMalloc(&acc.cand_count, 4));
         CU_TRY(cudaMalloc(&acc.sample_vals, 4ull * c->cfg.fragment_samples));
         CU_TRY(cudaMalloc(&acc.sample_count, 8));
         CU_TRY(cudaMemsetAsync(acc.pair_keys, 0, 8ull * c->pair_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(acc.pair_first, 0xff, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(acc.pair_first, 0, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(acc.pair_second, 0, 8ull * c->pair_cap, c->stream));
+        CU_TRY(cudaMemsetAsync(acc.pair_payload, 0xff, 8ull * c->pair_cap, c->stream));
         CU_TRY(cudaMemsetAsync(acc.sample_count, 0, 8, c->stream));
     }
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -900,7 +923,8 @@ int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {
     if (err_flag & 8u) { c->err = "packed / compact batch: the records claim more blocks, combinations or exceptions than the batch carries"; return RSQ_ERR_INVALID; }
     if (err_flag) {
         c->err = std::string("device table overflow:") + ((err_flag & 1) ? " fragment-tracker set" : "") +
-                 ((err_flag & 2) ? " mate table" : "") + ((err_flag & 4) ? " candidate list" : "") + " (raise rsq_config.max_records)";
+                 ((err_flag & 2) ? " mate table" : "") + ((err_flag & 4) ? " candidate list" : "") +
+                 ((err_flag & 16) ? " more than 65536 records beyond the second of their read name in one launch" : "") + " (raise rsq_config.max_records)";
         return RSQ_ERR_CAPACITY;
     }
     return RSQ_OK;

@@ -107,6 +107,13 @@ struct RefView {
     const uint32_t* bits;
 };
 
+constexpr unsigned long long kMateEmpty = ~0ull;
+constexpr unsigned int kMateLeftCap = 65536;     // candidates beyond the second of their name in one launch, per map
+// tag of a candidate in round r of a launch: later rounds beat earlier ones, earlier records beat later ones (atomicMax)
+__host__ __device__ inline unsigned long long mate_tag(unsigned long long mate_round, unsigned r, uint32_t local_idx) {
+    return ((mate_round + r) << 24) | (unsigned long long)(0xffffffu - (local_idx & 0xffffffu));
+}
+
 // Mutable accumulators in HBM.
 struct Accum {
     unsigned long long* counters;        // [RSQ_N_COUNTERS]
@@ -124,9 +131,17 @@ struct Accum {
     unsigned int*       error_flag;      // [2] ([1]: scratch word, see launch_hot_path) bit0: fragment set full, bit1: pair table full, bit2: candidate list full
     // fragment-size sampler (BED mode)
     unsigned long long* pair_keys;       // mate map keys (name hash, 0 = empty)
-    unsigned long long* pair_first;      // global record index of the FIRST candidate with this name (atomicMin)
-    unsigned long long* pair_payload;    // (name_id << 32) | (uint32)endpos of that first candidate
+    // State per read name = what the reference's map holds for it (src/Expression.cpp:511-533): nothing (kMateEmpty) or the
+    // (interval, PositionEnd) of the pending mate.  The candidates of one launch are applied to it in stream order: the earliest
+    // candidate of a name wins pair_first (atomicMax of a tag that grows with every round and falls with the record index), the
+    // earliest of the others pair_second, further ones (three or more records of one name in one launch: malformed input) queue up
+    // in mate_left and are replayed round by round (rsq_kernels.cu, mate_* kernels).
+    unsigned long long* pair_first;      // scratch: tag of the earliest candidate of the current round
+    unsigned long long* pair_second;     // scratch: tag of the earliest candidate among the others
+    unsigned long long* pair_payload;    // (name_id << 32) | (uint32)endpos of the pending mate, or kMateEmpty
     unsigned long long  pair_mask;
+    unsigned int*       mate_left;       // [2 * kMateLeftCap] candidate indices still to be replayed (BED half, GC half)
+    unsigned int*       mate_left_count; // [2]
     PairCandidate*      cand;            // per-batch candidate list
     unsigned int*       cand_count;      // [1]
     unsigned int        cand_capacity;
@@ -137,7 +152,8 @@ struct Accum {
     // fragment GC-content sampler (--fasta): same mate-map scheme as the BED sampler, its own tables (gcContentFragmentTracker)
     unsigned long long* gc_keys;
     unsigned long long* gc_first;
-    unsigned long long* gc_payload;      // (exon slot << 32) | (uint32)endpos of the first candidate
+    unsigned long long* gc_second;
+    unsigned long long* gc_payload;      // (exon slot << 32) | (uint32)endpos of the pending mate, or kMateEmpty
     unsigned long long  gc_mask;
     GcCandidate*        gc_cand;
     unsigned int*       gc_cand_count;   // [1]
@@ -156,6 +172,7 @@ struct Params {
     const uint8_t* ref_present;          // [n_contigs] Fasta::hasContig (gc_enabled only)
     const unsigned long long* cascade_lut;   // [2^17] the filter cascade as a table (cascade_entry, rsq_hot_core.cuh); null = compute
     unsigned long long record_base;      // global index of reads[0] in the stream (ordering of fragment samples)
+    unsigned long long mate_round;       // (launch number << 17): base of the round tags of this launch's mate-map stages
     unsigned long long cov_len_diag;     // coverage array length (RSQ_AB_SCATTER diagnostic build only)
 };
 
@@ -170,7 +187,7 @@ int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_blo
 int launch_expand_compact(const unsigned char* buf, const rsq_batch16& hdr, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream);
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream);
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream);
-int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,
+int launch_pair_rehash(const unsigned long long* old_keys, const unsigned long long* old_payload, unsigned long long old_cap, unsigned long long* nk,
                        unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream);
 int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned long long n, unsigned int* block_sums,
                          cudaStream_t stream);

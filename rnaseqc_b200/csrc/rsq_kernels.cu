@@ -414,7 +414,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                         }
                         if (!placed) atomicOr(acc.error_flag, 2u);
                         else {
-                            atomicMin(&acc.gc_first[slot], prm.record_base + i);
+                            atomicMax(&acc.gc_first[slot], mate_tag(prm.mate_round, 1u, i));             // round 1: the earliest candidate of the name
                             const unsigned int ci = warp_claim(acc.gc_cand_count);
                             if (ci < acc.gc_cand_capacity) {
                                 GcCandidate c;
@@ -479,7 +479,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
                         }
                         if (!placed) atomicOr(acc.error_flag, 2u);
                         else {
-                            atomicMin(&acc.pair_first[slot], prm.record_base + i);
+                            atomicMax(&acc.pair_first[slot], mate_tag(prm.mate_round, 1u, i));           // round 1: the earliest candidate of the name
                             const unsigned int ci = warp_claim(acc.cand_count);
                             if (ci < acc.cand_capacity) {
                                 PairCandidate c;
@@ -630,18 +630,17 @@ __global__ void prefix_max_kernel(const int2* __restrict__ se, const uint32_t* _
     }
 }
 
-// mate-map growth: re-insert (key, first index, payload) triples into a larger table
-__global__ void pair_rehash_kernel(const Accum old_acc, unsigned long long old_cap, unsigned long long* __restrict__ nk,
-                                   unsigned long long* __restrict__ nf, unsigned long long* __restrict__ np, unsigned long long new_mask,
-                                   unsigned int* err) {
+// mate-map growth: re-insert (key, pending mate) pairs into a larger table (the round scratch of the new table starts at zero)
+__global__ void pair_rehash_kernel(const unsigned long long* __restrict__ old_keys, const unsigned long long* __restrict__ old_payload, unsigned long long old_cap,
+                                   unsigned long long* __restrict__ nk, unsigned long long* __restrict__ np, unsigned long long new_mask, unsigned int* err) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= old_cap) return;
-    const unsigned long long key = old_acc.pair_keys[i];
+    const unsigned long long key = old_keys[i];
     if (!key) return;
     unsigned long long slot = mix64(key) & new_mask;
     for (int probe = 0; probe < 4096; ++probe) {
         const unsigned long long cur = atomicCAS(&nk[slot], 0ull, key);
-        if (cur == 0ull) { nf[slot] = old_acc.pair_first[i]; np[slot] = old_acc.pair_payload[i]; return; }
+        if (cur == 0ull) { np[slot] = old_payload[i]; return; }
         slot = (slot + 1) & new_mask;
     }
     atomicOr(err, 2u);
@@ -842,28 +841,128 @@ __global__ void combine_exon_kernel(const Accum acc, uint32_t n_exons, unsigned 
     whole_out[j] = acc.exon_whole[j] + (mid >> 32);
 }
 
-// ---- fragment-size pairing (BED mode) ----------------------------------------------------------------------------------------------
-// owner: the earliest candidate of a read name publishes (interval, PositionEnd)   (Expression.cpp:512-516)
-__global__ void pair_owner_kernel(const Accum acc, const Params prm) {
-    const unsigned int n = min(*acc.cand_count, acc.cand_capacity);
-    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const PairCandidate c = acc.cand[k];
-    if (acc.pair_first[c.slot] == prm.record_base + c.local_idx)
-        acc.pair_payload[c.slot] = ((unsigned long long)c.name_id << 32) | (unsigned long long)(uint32_t)c.endpos;
+// ---- mate maps: fragment-size pairing (BED mode) and fragment GC content (--fasta) ---------------------------------------------------
+// Both replay, per read name, what the reference does to its map entry when the candidates arrive in stream order
+// (fragmentSizeMetrics, src/Expression.cpp:508-533; the FASTA tail of exonAlignmentMetrics, :459-476):
+//   no entry                      -> store (interval, PositionEnd)
+//   entry with the same interval  -> if the pair's conditions hold: take the sample and ERASE the entry; else leave it
+//   entry with another interval   -> leave it
+// The hot kernel has given every name's earliest candidate of this launch the round-1 tag (atomicMax).  mate_first: those apply
+// their transition; every other candidate bids for round 2.  mate_second: the round-2 winners apply theirs; what is left (a
+// third record of one name inside one launch) queues up and is replayed by one CTA, one candidate per name and round.
+struct BedMap {
+    using Cand = PairCandidate;
+    static constexpr int kWhich = 0;
+    __device__ static const Cand* list(const Accum& a) { return a.cand; }
+    __device__ static unsigned int count(const Accum& a) { return min(*a.cand_count, a.cand_capacity); }
+    __device__ static unsigned long long* first(const Accum& a) { return a.pair_first; }
+    __device__ static unsigned long long* second(const Accum& a) { return a.pair_second; }
+    __device__ static unsigned long long* payload(const Accum& a) { return a.pair_payload; }
+    __device__ static uint32_t where(const Cand& c) { return c.name_id; }
+    // this candidate meets the pending mate (same name, same interval) whose read ended at stored_end: the four conditions of :528
+    __device__ static bool complete(const Accum& a, const RefView&, const Cand& c, int stored_end) {
+        if (!c.cond_ok || c.endpos <= stored_end) return false;
+        a.sample_flag[c.local_idx] = 1;
+        a.sample_isize[c.local_idx] = c.abs_isize;                       // fragmentSizes[abs(InsertSize())], :530
+        return true;
+    }
+};
+struct GcMap {
+    using Cand = GcCandidate;
+    static constexpr int kWhich = 1;
+    __device__ static const Cand* list(const Accum& a) { return a.gc_cand; }
+    __device__ static unsigned int count(const Accum& a) { return min(*a.gc_cand_count, a.gc_cand_capacity); }
+    __device__ static unsigned long long* first(const Accum& a) { return a.gc_first; }
+    __device__ static unsigned long long* second(const Accum& a) { return a.gc_second; }
+    __device__ static unsigned long long* payload(const Accum& a) { return a.gc_payload; }
+    __device__ static uint32_t where(const Cand& c) { return c.exon_slot; }
+    // :471-475: the end test and pos != mpos, then gc(getSeq(chr, stored end - Length(), PositionEnd())); the entry is erased even
+    // when the window yields no sequence
+    __device__ static bool complete(const Accum& a, const RefView& ref, const Cand& c, int stored_end) {
+        if (!c.cond_ok || c.endpos <= stored_end) return false;
+        // 0-based, end-exclusive window, clipped to the contig (Fasta.cpp:116-150, bioio.hpp:300-309)
+        const long long len = (long long)ref.length[c.contig];
+        const long long start = (long long)stored_end - c.l_qseq;
+        if (start < 0 || start >= len) return true;
+        const long long stop = min((long long)c.endpos, len);
+        if (stop <= start) return true;
+        const uint32_t* w = ref.bits + ref.word_off[c.contig];
+        int gcs = 0;
+        for (long long wi = start >> 5; wi <= (stop - 1) >> 5; ++wi) {
+            uint32_t m = __ldg(&w[wi]);
+            if (wi == (start >> 5)) m &= 0xffffffffu << (start & 31);
+            if (wi == ((stop - 1) >> 5) && (stop & 31)) m &= 0xffffffffu >> (32 - (int)(stop & 31));
+            gcs += __popc(m);
+        }
+        // gc() adds 1.0/size once per G/C base (Fasta.cpp:66-75): the same sequence of double additions
+        const double inv = 1.0 / (double)(stop - start);
+        double content = 0.0;
+        for (int t = 0; t < gcs; ++t) content += inv;
+        const unsigned bin = (unsigned)(content * 100.0);                      // RNASeQC.cpp:368
+        if (bin < 100u) atomicAdd(&a.gc_hist[bin], 1ull);
+        return true;
+    }
+};
+
+template <class M>
+__device__ __forceinline__ void mate_apply(const Accum& acc, const RefView& ref, const typename M::Cand& c) {
+    unsigned long long* pay = M::payload(acc) + c.slot;
+    const unsigned long long s = *pay;
+    if (s == kMateEmpty) { *pay = ((unsigned long long)M::where(c) << 32) | (unsigned long long)(uint32_t)c.endpos; return; }   // :512-516
+    if ((uint32_t)(s >> 32) != M::where(c)) return;                                                                          // :517
+    if (M::complete(acc, ref, c, (int32_t)(uint32_t)s)) *pay = kMateEmpty;                                                     // fragments.erase
 }
-// second: a later candidate with the same name tests the four conditions   (Expression.cpp:517-533)
-__global__ void pair_check_kernel(const Accum acc, const Params prm) {
-    const unsigned int n = min(*acc.cand_count, acc.cand_capacity);
+template <class M>
+__global__ void mate_first_kernel(const Accum acc, const Params prm, const RefView ref) {
     const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const PairCandidate c = acc.cand[k];
-    if (acc.pair_first[c.slot] >= prm.record_base + c.local_idx) return;
-    const unsigned long long p = acc.pair_payload[c.slot];
-    if ((uint32_t)(p >> 32) != c.name_id) return;                       // exonName == stored exon, :517
-    if (!c.cond_ok || c.endpos <= (int32_t)(uint32_t)p) return;         // :528
-    acc.sample_flag[c.local_idx] = 1;
-    acc.sample_isize[c.local_idx] = c.abs_isize;                        // fragmentSizes[abs(InsertSize())], :530
+    if (k >= M::count(acc)) return;
+    const typename M::Cand c = M::list(acc)[k];
+    if (M::first(acc)[c.slot] == mate_tag(prm.mate_round, 1u, c.local_idx)) mate_apply<M>(acc, ref, c);
+    else atomicMax(&M::second(acc)[c.slot], mate_tag(prm.mate_round, 2u, c.local_idx));
+}
+template <class M>
+__global__ void mate_second_kernel(const Accum acc, const Params prm, const RefView ref) {
+    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M::count(acc)) return;
+    const typename M::Cand c = M::list(acc)[k];
+    if (M::first(acc)[c.slot] == mate_tag(prm.mate_round, 1u, c.local_idx)) return;                 // applied in round 1
+    if (M::second(acc)[c.slot] == mate_tag(prm.mate_round, 2u, c.local_idx)) { mate_apply<M>(acc, ref, c); return; }
+    const unsigned int at = atomicAdd(&acc.mate_left_count[M::kWhich], 1u);
+    if (at < kMateLeftCap) acc.mate_left[M::kWhich * kMateLeftCap + at] = k;
+    else atomicOr(acc.error_flag, 16u);
+}
+// one CTA: the queued candidates, one per name and round, until none is left (rounds 3, 4, ...)
+template <class M>
+__global__ void __launch_bounds__(1024) mate_rest_kernel(const Accum acc, const Params prm, const RefView ref) {
+    __shared__ unsigned int s_left;
+    const unsigned int n = min(acc.mate_left_count[M::kWhich], kMateLeftCap);
+    if (n == 0) return;
+    unsigned int* left = acc.mate_left + M::kWhich * kMateLeftCap;
+    if (threadIdx.x == 0) s_left = n;
+    __syncthreads();
+    for (unsigned r = 3; r < 3u + kMateLeftCap + 1u; ++r) {
+        for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+            const unsigned k = left[j];
+            if (k == 0xffffffffu) continue;
+            const typename M::Cand c = M::list(acc)[k];
+            atomicMax(&M::first(acc)[c.slot], mate_tag(prm.mate_round, r, c.local_idx));
+        }
+        __threadfence();
+        __syncthreads();
+        for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+            const unsigned k = left[j];
+            if (k == 0xffffffffu) continue;
+            const typename M::Cand c = M::list(acc)[k];
+            if (*(volatile unsigned long long*)&M::first(acc)[c.slot] != mate_tag(prm.mate_round, r, c.local_idx)) continue;
+            mate_apply<M>(acc, ref, c);
+            left[j] = 0xffffffffu;
+            atomicSub(&s_left, 1u);
+        }
+        __threadfence();
+        __syncthreads();
+        if (s_left == 0) break;
+        __syncthreads();
+    }
 }
 // rank samples in stream order and keep the first fragment_samples of the whole run   (RNASeQC.cpp:372, Expression.cpp:532)
 __global__ void __launch_bounds__(kScanThreads) sample_count_kernel(const unsigned char* __restrict__ flag, unsigned long long n, unsigned int* __restrict__ sums) {
@@ -914,50 +1013,6 @@ __global__ void sample_hist_kernel(const unsigned int* __restrict__ vals, unsign
         if (b >= hist_len) b = hist_len - 1;
         atomicAdd(&hist[b], 1ull);
     }
-}
-
-
-// ---- fragment GC content (--fasta) -----------------------------------------------------------------------------------------------
-// owner: the earliest candidate of a read name publishes (exon, PositionEnd)   (Expression.cpp:462-466)
-__global__ void gc_owner_kernel(const Accum acc, const Params prm) {
-    const unsigned int n = min(*acc.gc_cand_count, acc.gc_cand_capacity);
-    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const GcCandidate c = acc.gc_cand[k];
-    if (acc.gc_first[c.slot] == prm.record_base + c.local_idx)
-        acc.gc_payload[c.slot] = ((unsigned long long)c.exon_slot << 32) | (unsigned long long)(uint32_t)c.endpos;
-}
-// second: a later candidate on the same exon samples gc(getSeq(chr, stored end - Length(), PositionEnd()))   (:467-476)
-__global__ void gc_check_kernel(const Accum acc, const Params prm, const RefView ref) {
-    const unsigned int n = min(*acc.gc_cand_count, acc.gc_cand_capacity);
-    const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const GcCandidate c = acc.gc_cand[k];
-    if (acc.gc_first[c.slot] >= prm.record_base + c.local_idx) return;
-    const unsigned long long p = acc.gc_payload[c.slot];
-    if ((uint32_t)(p >> 32) != c.exon_slot) return;
-    const int stored_end = (int32_t)(uint32_t)p;
-    if (!c.cond_ok || c.endpos <= stored_end) return;                      // :471
-    // 0-based, end-exclusive window, clipped to the contig (Fasta.cpp:116-150, bioio.hpp:300-309)
-    const long long len = (long long)ref.length[c.contig];
-    const long long start = (long long)stored_end - c.l_qseq;
-    if (start < 0 || start >= len) return;
-    const long long stop = min((long long)c.endpos, len);
-    if (stop <= start) return;
-    const uint32_t* w = ref.bits + ref.word_off[c.contig];
-    int gcs = 0;
-    for (long long wi = start >> 5; wi <= (stop - 1) >> 5; ++wi) {
-        uint32_t m = __ldg(&w[wi]);
-        if (wi == (start >> 5)) m &= 0xffffffffu << (start & 31);
-        if (wi == ((stop - 1) >> 5) && (stop & 31)) m &= 0xffffffffu >> (32 - (int)(stop & 31));
-        gcs += __popc(m);
-    }
-    // gc() adds 1.0/size once per G/C base (Fasta.cpp:66-75): the same sequence of double additions
-    const double inv = 1.0 / (double)(stop - start);
-    double content = 0.0;
-    for (int t = 0; t < gcs; ++t) content += inv;
-    const unsigned bin = (unsigned)(content * 100.0);                      // RNASeQC.cpp:368
-    if (bin < 100u) atomicAdd(&acc.gc_hist[bin], 1ull);
 }
 
 
@@ -1132,9 +1187,9 @@ int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, i
 }
 
 
-int launch_pair_rehash(const Accum& old_acc, unsigned long long old_cap, unsigned long long* nk, unsigned long long* nf,
+int launch_pair_rehash(const unsigned long long* old_keys, const unsigned long long* old_payload, unsigned long long old_cap, unsigned long long* nk,
                        unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream) {
-    pair_rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_acc, old_cap, nk, nf, np, new_mask, error_flag);
+    pair_rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_keys, old_payload, old_cap, nk, np, new_mask, error_flag);
     return 1;
 }
 
@@ -1183,8 +1238,10 @@ size_t pair_scan_scratch_elems(size_t n_reads) { return (n_reads + kScanTile - 1
 int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsigned int* scratch, cudaStream_t stream) {
     if (!n_reads) return 0;
     const unsigned cgrid = (unsigned)((std::min<size_t>(n_reads, acc.cand_capacity) + 255) / 256);
-    pair_owner_kernel<<<cgrid, 256, 0, stream>>>(acc, prm);
-    pair_check_kernel<<<cgrid, 256, 0, stream>>>(acc, prm);
+    const RefView no_ref{};
+    mate_first_kernel<BedMap><<<cgrid, 256, 0, stream>>>(acc, prm, no_ref);
+    mate_second_kernel<BedMap><<<cgrid, 256, 0, stream>>>(acc, prm, no_ref);
+    mate_rest_kernel<BedMap><<<1, 1024, 0, stream>>>(acc, prm, no_ref);
     const unsigned long long tiles = (n_reads + kScanTile - 1) / kScanTile;
     unsigned int* sums = scratch;
     unsigned int* last = scratch + tiles + 1;
@@ -1193,7 +1250,7 @@ int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsi
     scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, tiles);
     sample_rank_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(acc.sample_flag, acc.sample_isize, n_reads, sums, acc, prm);
     sample_commit_kernel<<<1, 32, 0, stream>>>(sums, tiles, last, acc);
-    return 7;
+    return 8;
 }
 
 int launch_unpack_counts_of(const rsq_read_packed* packed, size_t n, unsigned int* tot, unsigned int* expl, cudaStream_t stream) {
@@ -1218,9 +1275,10 @@ int launch_expand_compact(const unsigned char* buf, const rsq_batch16& hdr, rsq_
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
     const unsigned cgrid = (unsigned)((std::min<size_t>(n_reads, acc.gc_cand_capacity) + 255) / 256);
-    gc_owner_kernel<<<cgrid, 256, 0, stream>>>(acc, prm);
-    gc_check_kernel<<<cgrid, 256, 0, stream>>>(acc, prm, ref);
-    return 2;
+    mate_first_kernel<GcMap><<<cgrid, 256, 0, stream>>>(acc, prm, ref);
+    mate_second_kernel<GcMap><<<cgrid, 256, 0, stream>>>(acc, prm, ref);
+    mate_rest_kernel<GcMap><<<1, 1024, 0, stream>>>(acc, prm, ref);
+    return 3;
 }
 
 int launch_sample_histogram(const unsigned int* vals, unsigned long long n, unsigned long long* hist, unsigned long long hist_len, cudaStream_t stream) {

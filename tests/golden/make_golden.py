@@ -7,6 +7,9 @@
 Cases
   synth_small : seeded synthetic annotation (90 genes / 3 contigs incl. a tiny chrM) + 30 k 150 bp PE records from
                 rnaseqc_b200.synth; reference run with --coverage --bed.
+  kat_odd     : the two shapes round 2 closed: exons that reach past their gene line (the gene leaves the reference's
+                sliding window early: coverage dropped, fragments counted anew) and three, four and five records under one read
+                name inside one BED interval / exon (the mate maps' erase-and-restart rule), --bed + --fasta.
   kat         : hand-written known-answer GTF + SAM, one read (pair) per quirk listed in SURVEY.md §8c; reference run
                 under several flag sets (default, --stranded rf/fr, -u, --exclude-chimeric, -t XS, --rpkm -s).
 """
@@ -39,6 +42,8 @@ KAT_LEGACY_FLAGSETS = {
 }
 SYNTH_FASTA_FLAGSETS = {"fasta": ["--fasta", "g.fa", "--coverage"], "fasta_rf_bed": ["--fasta", "g.fa", "--stranded", "rf", "--bed", "a.bed"],
                         "fasta_legacy": ["--fasta", "g.fa", "--legacy"]}
+KAT_ODD_FLAGSETS = {"odd": ["--coverage", "--coverage-mask", "0", "--gene-length", "50", "--bed", "a.bed", "--fasta", "g.fa"],
+                    "odd_few": ["--bed", "a.bed", "--fragment-samples", "7", "--stranded", "fr"]}
 SYNTH_FLAGSETS = {"coverage_bed": ["--coverage", "--bed", "a.bed"], "legacy": ["--legacy", "--coverage", "--bed", "a.bed"]}
 
 
@@ -319,6 +324,77 @@ def make_kat_legacy():
     os.remove(sam)
 
 
+def kat_odd_files():
+    import random
+    rng = random.Random(777)
+    A = 'gene_id "{g}"; transcript_id "{g}"; gene_type "protein_coding"; gene_name "{g}n"; transcript_type "protein_coding";'
+    L = []
+
+    def feat(kind, g, s, e, strand="+", eid=None, chrom="chr1"):
+        L.append(f"{chrom}\tx\t{kind}\t{s}\t{e}\t.\t{strand}\t.\t" + A.format(g=g) + (f' exon_id "{eid}";' if eid else ""))
+    # a gene line that ends before its second exon does
+    feat("gene", "G1", 1000, 2000); feat("exon", "G1", 1000, 1200, eid="G1_1"); feat("exon", "G1", 1800, 3000, eid="G1_2")
+    # a long gene that starts earlier keeps G2's line in the window until ITS end (prefix maximum of the list)
+    feat("gene", "GL", 5000, 9000, "-"); feat("exon", "GL", 5000, 5200, "-", eid="GL_1"); feat("exon", "GL", 8800, 9000, "-", eid="GL_2")
+    feat("gene", "G2", 5500, 6000); feat("exon", "G2", 5500, 5700, eid="G2_1"); feat("exon", "G2", 5900, 9500, eid="G2_2")
+    feat("gene", "G3", 20000, 24000); feat("exon", "G3", 20000, 24000, eid="G3_1")
+    feat("gene", "G4", 30000, 33000, "-"); feat("exon", "G4", 30000, 31500, "-", eid="G4_1"); feat("exon", "G4", 32000, 33000, "-", eid="G4_2")
+    feat("gene", "G5", 1000, 5000, chrom="chr2"); feat("exon", "G5", 1000, 5000, eid="G5_1", chrom="chr2")
+    H = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:chr1\tLN:100000", "@SQ\tSN:chr2\tLN:100000"]
+    R = []
+
+    def rd(name, pos, flag, cigar="100M", lq=100, pnext=0, tlen=0, chrom="chr1"):
+        R.append((chrom, pos, "\t".join([name, str(flag), chrom, str(pos), "255", cigar, "=", str(pnext), str(tlen), "A" * lq, "F" * lq, "NM:i:0"])))
+
+    def pair(name, p1, p2, chrom="chr1", f=(99, 147)):
+        rd(name, p1, f[0], pnext=p2, tlen=p2 + 100 - p1, chrom=chrom); rd(name, p2, f[1], pnext=p1, tlen=-(p2 + 100 - p1), chrom=chrom)
+    pair("p1", 1010, 1850)            # both mates while the gene line is in the window
+    pair("p2", 1900, 2500)            # the second mate finds the gene evicted: a second fragment, no coverage
+    pair("p3", 2100, 2600)            # both beyond
+    for k in range(30):
+        rd(f"q{k}", 2200 + 10 * k, 99 if k % 2 == 0 else 147, pnext=2200)
+    pair("r1", 5950, 6500); pair("r2", 8000, 9100); pair("r3", 9150, 9300)
+    # G3 / G4 / G5 are BED intervals too: names shared by three, four and five records
+    for i in range(60):
+        base = 20000 + 40 * i
+        n = rng.choice([2, 2, 3, 3, 4, 5])
+        for k in range(n):
+            fwd = k % 2 == 0 if rng.random() < 0.8 else rng.random() < 0.5
+            p = base + 110 * k + rng.choice([0, 0, 3])
+            rd(f"m{i}", p, 99 if fwd else 147, pnext=base if not fwd else p + 150, tlen=(300 if fwd else -300) + k)
+    for i in range(40):
+        base = 1000 + 60 * i
+        n = rng.choice([3, 4])
+        for k in range(n):
+            fwd = k % 2 == 0
+            rd(f"n{i}", base + 150 * k, 99 if fwd else 147, pnext=base, tlen=(250 if fwd else -250) - k, chrom="chr2")
+    order = {"chr1": 0, "chr2": 1}
+    R.sort(key=lambda x: (order[x[0]], x[1]))
+    bed = "chr1\t19999\t24000\nchr1\t29999\t31500\nchr2\t999\t5000\n"
+    seq = {c: "".join(rng.choice("ACGT") for _ in range(100000)) for c in ("chr1", "chr2")}
+    fa = "".join(f">{c}\n" + "\n".join(seq[c][i:i + 60] for i in range(0, 100000, 60)) + "\n" for c in ("chr1", "chr2"))
+    fai, off = "", 0
+    for c in ("chr1", "chr2"):
+        off += len(c) + 2
+        fai += f"{c}\t100000\t{off}\t60\t61\n"
+        off += 100000 + (100000 + 59) // 60
+    return "\n".join(L) + "\n", "\n".join(H + [x[2] for x in R]) + "\n", bed, fa, fai
+
+
+def make_kat_odd():
+    d = os.path.join(HERE, "kat_odd")
+    os.makedirs(d, exist_ok=True)
+    gtf, sam, bed, fa, fai = kat_odd_files()
+    for name, text in (("a.gtf", gtf), ("a.sam", sam), ("a.bed", bed), ("g.fa", fa), ("g.fa.fai", fai)):
+        open(os.path.join(d, name), "w").write(text)
+    for name, flags in KAT_ODD_FLAGSETS.items():
+        run_ref("a.gtf", "a.sam", os.path.join("expected", name), flags, d)
+    for f in ("a.sam", "g.fa"):
+        with open(os.path.join(d, f), "rb") as fi, gzip.open(os.path.join(d, f + ".gz"), "wb", compresslevel=9) as fo:
+            shutil.copyfileobj(fi, fo)
+        os.remove(os.path.join(d, f))
+
+
 def make_kat():
     d = os.path.join(HERE, "kat")
     os.makedirs(d, exist_ok=True)
@@ -339,4 +415,5 @@ if __name__ == "__main__":
     make_kat()
     make_kat_legacy()
     make_synth_fasta()
+    make_kat_odd()
     print("golden fixtures written under", HERE)

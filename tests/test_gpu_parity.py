@@ -10,7 +10,7 @@ import pytest
 from util import assert_results_equal, compare_outputs, run_cli, unpack_case
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_golden import KAT_FLAGSETS, KAT_LEGACY_FLAGSETS, SYNTH_FASTA_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
+from make_golden import KAT_FLAGSETS, KAT_LEGACY_FLAGSETS, KAT_ODD_FLAGSETS, SYNTH_FASTA_FLAGSETS, SYNTH_FLAGSETS  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -256,6 +256,25 @@ def test_cuda_legacy_rules_match_oracle(libs, legacy_case, name):
     assert got_bytes == want_bytes
     assert want.counter("Split Reads") > 10000 and want.gene_reads.sum() > 100000
     assert want.counter("Chimeric Fragments_auto") > 0
+
+
+@pytest.mark.parametrize("flagset", sorted(KAT_ODD_FLAGSETS))
+@pytest.mark.parametrize("batch", [None, "37"])
+def test_kat_odd_product_cli_matches_reference(libs, tmp_path, flagset, batch):
+    """The two shapes round 2 closed, on the device: a gene that has left the reference's window while one of its exons goes on
+    (coverage dropped, fragments counted in a second epoch), and three to five records under one read name in the mate maps
+    (stream-order automaton per name: rounds 1 and 2 in parallel, the rest replayed) — also with launches of 37 records, so that
+    the records of one name are spread over several launches."""
+    d = unpack_case("kat_odd", tmp_path)
+    out = os.path.join(d, "out_" + flagset)
+    flags = [os.path.join(d, f) if f in ("a.bed", "g.fa") else f for f in KAT_ODD_FLAGSETS[flagset]]
+    if batch:
+        flags += ["--batch-records", batch]
+    run_cli(libs["cli"], os.path.join(d, "a.gtf"), os.path.join(d, "a.sam"), out, *flags)
+    identical = set(compare_outputs(os.path.join(d, "expected", flagset), out))
+    assert {"a.sam.gene_reads.gct", "a.sam.gene_fragments.gct", "a.sam.fragmentSizes.txt"} <= identical, identical
+    if "--fasta" in flags:
+        assert "a.sam.gc_content.tsv" in identical
 
 
 @pytest.mark.parametrize("flagset", sorted(KAT_LEGACY_FLAGSETS))

@@ -2,8 +2,8 @@
 base, mates on other contigs, unmapped records with coordinates, contigs the GTF lacks) decoded by the host library and run
 through a backend, against the CPU oracle on the same records — which tests/test_sam_fuzz.py pins to the reference binary on
 these very inputs.  The CPU variant checks the harness with the oracle on both sides and the wire-format packer; the `-m gpu`
-variant is the CUDA path under the current and the --legacy rules.  (No --bed configuration here: these files give three and more
-records the same read name, which the device sampler's documented two-candidates-per-name rule does not cover)"""
+variant is the CUDA path under the current and the --legacy rules.  The pair cases below also give three and four records one read
+name: the mate maps replay every name's candidates in stream order (rsq_kernels.cu, mate_* kernels)."""
 import os
 import random
 
@@ -96,8 +96,8 @@ PAIR_CONFIGS = {
 
 
 def _check_pairs(libs, tmp_path, lib, seed, name):
-    """Odd PAIRS (tests/test_sam_fuzz.py::_pairs_sam, names unique per pair: the device sampler's documented two-candidates-per-name
-    rule) through the fragment-size and GC-content samplers."""
+    """Odd PAIRS (tests/test_sam_fuzz.py::_pairs_sam, incl. names shared by three and four records) through the fragment-size and
+    GC-content samplers."""
     api = libs["api"]
     kw = dict(PAIR_CONFIGS[name])
     legacy, fasta = kw.pop("legacy", False), kw.pop("fasta", False)
@@ -105,7 +105,7 @@ def _check_pairs(libs, tmp_path, lib, seed, name):
     d = str(tmp_path)
     gtf, sam, bed, fa = (os.path.join(d, n) for n in ("f.gtf", "f.sam", "f.bed", "f.fa"))
     rows = _gtf(gtf, rng)
-    _pairs_sam(sam, rng, rows, 1500, shared_names=False)
+    _pairs_sam(sam, rng, rows, 1500, shared_names=True)
     ex = sorted({(e[0], int(e[3]), int(e[4])) for e in (r.split("\t") for r in rows if "\texon\t" in r)})
     open(bed, "w").write("".join(f"{c}\t{s - 1}\t{e}\n" for c, s, e in ex))
     if fasta:
