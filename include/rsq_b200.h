@@ -377,7 +377,7 @@ typedef struct rsq_transcripts {
     uint32_t n_exon_refs;          /* exons over all listed genes, stitched (exonsForGene) order             */
     uint32_t coverage_mask;        /* COVERAGE_MASK, src/RNASeQC.cpp:91                                       */
     int32_t  bias_offset;          /* BIAS_OFFSET :94 (>= 0)                                                  */
-    int32_t  bias_window;          /* BIAS_WINDOW :95 (1..1024)                                               */
+    int32_t  bias_window;          /* BIAS_WINDOW :95 (1..8192)                                               */
     uint32_t bias_gene_length;     /* BIAS_LENGTH :96                                                         */
     uint32_t reserved;
     const uint64_t* gene_cov_off;  /* [n_genes] first base of the gene's stitched transcript in the coverage array */

@@ -84,6 +84,7 @@ struct Ctx {
     // bookkeeping
     unsigned long long records_submitted = 0;
     unsigned long long mate_launches = 0;     // launches with a mate map on: numbers the rounds of the mate-map stages
+    unsigned long long mate_known[2] = {0, 0}, mate_pending[2] = {0, 0};   // candidates read back / records launched since (BED, GC)
     unsigned long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;
     size_t timers_used = 0;
@@ -201,6 +202,8 @@ int zero_accumulators(Ctx* c) {
     }
     c->records_submitted = 0;
     c->mate_launches = 0;
+    c->mate_known[0] = c->mate_known[1] = c->mate_pending[0] = c->mate_pending[1] = 0;
+    if (a.mate_totals) CU_TRY(cudaMemsetAsync(a.mate_totals, 0, 16, c->stream));
     c->found_valid = false;
     c->frag_known = 0; c->frag_pending = 0;
     c->kernel_ms = 0.0;
@@ -267,13 +270,23 @@ int reserve_frag_capacity(Ctx* c, size_t* n) {
     return RSQ_OK;
 }
 
-// grows the mate map (BED mode) so that the records seen so far + n fit at load <= 3/4 even if every record
-// carried a distinct candidate name
-int ensure_pair_capacity(Ctx* c, size_t n) {
-    if (!(c->have_bed && c->cfg.fragment_samples)) return RSQ_OK;
-    const unsigned long long need = c->records_submitted + n;
-    if (need <= c->pair_cap / 4 * 3) return RSQ_OK;
-    const unsigned long long new_cap = next_pow2(need / 3 * 4 + 4);
+// The mate maps (BED fragment sizes, --fasta fragment GC) hold one entry per read name that ever was a candidate — a fraction of
+// the records.  They are sized by that, not by the records: a launch of n records may go while (candidates known + records
+// launched since the last look + n) stays below 3/4 of the capacity; beyond that the host synchronises, reads the exact number of
+// candidates so far (a device counter, an upper bound of the names), and grows the table only if even that leaves no room.
+int reserve_mate_capacity(Ctx* c, int which, size_t n) {
+    const bool on = which == 0 ? (c->have_bed && c->cfg.fragment_samples) : (c->have_ref && !c->cfg.legacy);
+    if (!on) return RSQ_OK;
+    unsigned long long& cap = which == 0 ? c->pair_cap : c->gc_cap;
+    unsigned long long& known = c->mate_known[which];
+    unsigned long long& pending = c->mate_pending[which];
+    if (known + pending + n <= cap / 4 * 3) { pending += n; return RSQ_OK; }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    unsigned long long exact = 0;
+    CU_TRY(cudaMemcpy(&exact, c->acc.mate_totals + which, 8, cudaMemcpyDeviceToHost));
+    known = exact; pending = n;
+    if (exact + n <= cap / 4 * 3) return RSQ_OK;
+    const unsigned long long new_cap = next_pow2((exact + n) / 3 * 4 + 4);
     unsigned long long *nk = nullptr, *nf = nullptr, *ns = nullptr, *np = nullptr;
     CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
     CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
@@ -283,17 +296,22 @@ int ensure_pair_capacity(Ctx* c, size_t n) {
     CU_TRY(cudaMemsetAsync(nf, 0, 8ull * new_cap, c->stream));
     CU_TRY(cudaMemsetAsync(ns, 0, 8ull * new_cap, c->stream));
     CU_TRY(cudaMemsetAsync(np, 0xff, 8ull * new_cap, c->stream));
-    c->launches += launch_pair_rehash(c->acc.pair_keys, c->acc.pair_payload, c->pair_cap, nk, np, new_cap - 1, c->acc.error_flag, c->stream);
+    Accum& a = c->acc;
+    unsigned long long*& keys = which == 0 ? a.pair_keys : a.gc_keys;
+    unsigned long long*& first = which == 0 ? a.pair_first : a.gc_first;
+    unsigned long long*& second = which == 0 ? a.pair_second : a.gc_second;
+    unsigned long long*& payload = which == 0 ? a.pair_payload : a.gc_payload;
+    c->launches += launch_pair_rehash(keys, payload, cap, nk, np, new_cap - 1, a.error_flag, c->stream);
     CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->acc.pair_keys); cudaFree(c->acc.pair_first); cudaFree(c->acc.pair_second); cudaFree(c->acc.pair_payload);
-    c->acc.pair_keys = nk; c->acc.pair_first = nf; c->acc.pair_second = ns; c->acc.pair_payload = np;
-    c->acc.pair_mask = new_cap - 1;
-    c->pair_cap = new_cap;
+    cudaFree(keys); cudaFree(first); cudaFree(second); cudaFree(payload);
+    keys = nk; first = nf; second = ns; payload = np;
+    (which == 0 ? a.pair_mask : a.gc_mask) = new_cap - 1;
+    cap = new_cap;
     return RSQ_OK;
 }
 
-// same for the GC-content mate map (--fasta) and its per-batch candidate list
-int ensure_gc_capacity(Ctx* c, size_t n) {
+// per-launch candidate list of the GC-content sampler
+int ensure_gc_buffers(Ctx* c, size_t n) {
     if (!c->have_ref || c->cfg.legacy) return RSQ_OK;
     const size_t need_cand = std::min(n, kSubBatch);
     if (need_cand > c->gc_cand_cap) {
@@ -303,31 +321,11 @@ int ensure_gc_capacity(Ctx* c, size_t n) {
         CU_TRY(cudaMalloc(&c->acc.gc_cand, sizeof(GcCandidate) * need_cand));
         c->acc.gc_cand_capacity = (unsigned int)need_cand;
     }
-    const unsigned long long need = c->records_submitted + n;
-    if (need <= c->gc_cap / 4 * 3) return RSQ_OK;
-    const unsigned long long new_cap = next_pow2(need / 3 * 4 + 4);
-    unsigned long long *nk = nullptr, *nf = nullptr, *ns = nullptr, *np = nullptr;
-    CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
-    CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
-    CU_TRY(cudaMalloc(&ns, 8ull * new_cap));
-    CU_TRY(cudaMalloc(&np, 8ull * new_cap));
-    CU_TRY(cudaMemsetAsync(nk, 0, 8ull * new_cap, c->stream));
-    CU_TRY(cudaMemsetAsync(nf, 0, 8ull * new_cap, c->stream));
-    CU_TRY(cudaMemsetAsync(ns, 0, 8ull * new_cap, c->stream));
-    CU_TRY(cudaMemsetAsync(np, 0xff, 8ull * new_cap, c->stream));
-    c->launches += launch_pair_rehash(c->acc.gc_keys, c->acc.gc_payload, c->gc_cap, nk, np, new_cap - 1, c->acc.error_flag, c->stream);
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->acc.gc_keys); cudaFree(c->acc.gc_first); cudaFree(c->acc.gc_second); cudaFree(c->acc.gc_payload);
-    c->acc.gc_keys = nk; c->acc.gc_first = nf; c->acc.gc_second = ns; c->acc.gc_payload = np;
-    c->acc.gc_mask = new_cap - 1;
-    c->gc_cap = new_cap;
     return RSQ_OK;
 }
 
 int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* d_blocks, size_t n_blocks) {
-    int rc = ensure_pair_capacity(c, n_reads);
-    if (rc != RSQ_OK) return rc;
-    rc = ensure_gc_capacity(c, n_reads);
+    int rc = ensure_gc_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
     rc = ensure_bed_buffers(c, n_reads);
     if (rc != RSQ_OK) return rc;
@@ -371,6 +369,7 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
         n = std::min(sub, n_reads - base);
         rc = reserve_frag_capacity(c, &n);      // may cut the launch down to the room left in the fragment-tracker set
         if (rc != RSQ_OK) return rc;
+        if ((rc = reserve_mate_capacity(c, 0, n)) != RSQ_OK || (rc = reserve_mate_capacity(c, 1, n)) != RSQ_OK) return rc;
         prm.record_base = c->records_submitted + base;
         if (prm.bed_enabled || prm.gc_enabled) {
             if (++c->mate_launches >= (1ull << 23)) { c->err = "too many launches for the mate-map round tags"; return RSQ_ERR_CAPACITY; }
@@ -445,7 +444,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     free_list(c->bed_allocs);
     free_list(c->ref_allocs);
     Accum& a = c->acc;
-    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_second, a.gc_payload, a.pair_second, a.mate_left, a.mate_left_count, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
+    void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_second, a.gc_payload, a.pair_second, a.mate_left, a.mate_left_count, a.mate_totals, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
                     a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_owned, c->d_found, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
@@ -610,13 +609,16 @@ int rsq_set_reference(rsq_ctx* ctx, const rsq_reference* r) {
     if ((rc = upload(c, c->ref_allocs, r->gc_bits, (size_t)r->word_off[r->n_contigs], &c->ref.bits))) return rc;
     c->d_ref_present = c->ref.present;
     Accum& acc = c->acc;
-    c->gc_cap = next_pow2((c->cfg.max_records ? c->cfg.max_records : (1ull << 24)) / 3 * 4 + 4);
+    c->gc_cap = next_pow2(std::min<unsigned long long>(c->cfg.max_records ? c->cfg.max_records : (1ull << 24), kSubBatch) / 3 * 4 + 4);   // grows with the candidates
     CU_TRY(cudaMalloc(&acc.gc_keys, 8ull * c->gc_cap));
     CU_TRY(cudaMalloc(&acc.gc_first, 8ull * c->gc_cap));
     CU_TRY(cudaMalloc(&acc.gc_second, 8ull * c->gc_cap));
     CU_TRY(cudaMalloc(&acc.gc_payload, 8ull * c->gc_cap));
     acc.gc_mask = c->gc_cap - 1;
-    if (!acc.mate_left) { CU_TRY(cudaMalloc(&acc.mate_left, 4ull * 2 * kMateLeftCap)); CU_TRY(cudaMalloc(&acc.mate_left_count, 8)); }
+    if (!acc.mate_left) {
+        CU_TRY(cudaMalloc(&acc.mate_left, 4ull * 2 * kMateLeftCap)); CU_TRY(cudaMalloc(&acc.mate_left_count, 8)); CU_TRY(cudaMalloc(&acc.mate_totals, 16));
+        CU_TRY(cudaMemsetAsync(acc.mate_totals, 0, 16, c->stream));
+    }
     CU_TRY(cudaMalloc(&acc.gc_cand_count, 4));
     CU_TRY(cudaMalloc(&acc.gc_hist, 8 * 100));
     CU_TRY(cudaMemsetAsync(acc.gc_keys, 0, 8ull * c->gc_cap, c->stream));
@@ -678,13 +680,16 @@ int rsq_set_bed(rsq_ctx* ctx, const rsq_bed* b) {
     c->have_bed = true;
     if (c->cfg.fragment_samples) {
         Accum& acc = c->acc;
-        c->pair_cap = next_pow2((c->cfg.max_records ? c->cfg.max_records : (1ull << 24)) / 3 * 4 + 4);
+        c->pair_cap = next_pow2(std::min<unsigned long long>(c->cfg.max_records ? c->cfg.max_records : (1ull << 24), kSubBatch) / 3 * 4 + 4);   // grows with the candidates
         CU_TRY(cudaMalloc(&acc.pair_keys, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_first, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_second, 8ull * c->pair_cap));
         CU_TRY(cudaMalloc(&acc.pair_payload, 8ull * c->pair_cap));
         acc.pair_mask = c->pair_cap - 1;
-        if (!acc.mate_left) { CU_TRY(cudaMalloc(&acc.mate_left, 4ull * 2 * kMateLeftCap)); CU_TRY(cudaMalloc(&acc.mate_left_count, 8)); }
+        if (!acc.mate_left) {
+        CU_TRY(cudaMalloc(&acc.mate_left, 4ull * 2 * kMateLeftCap)); CU_TRY(cudaMalloc(&acc.mate_left_count, 8)); CU_TRY(cudaMalloc(&acc.mate_totals, 16));
+        CU_TRY(cudaMemsetAsync(acc.mate_totals, 0, 16, c->stream));
+    }
         CU_TRY(cudaMalloc(&acc.cand_count, 4));
         CU_TRY(cudaMalloc(&acc.sample_vals, 4ull * c->cfg.fragment_samples));
         CU_TRY(cudaMalloc(&acc.sample_count, 8));
@@ -934,7 +939,7 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !q || !out || !c->have_ann || q->struct_size != sizeof(rsq_transcripts) || out->struct_size != sizeof(rsq_coverage_stats))
         return RSQ_ERR_INVALID;
-    if (q->bias_offset < 0 || q->bias_window < 1 || q->bias_window > 1024) { c->err = "bias offset/window out of range"; return RSQ_ERR_INVALID; }
+    if (q->bias_offset < 0 || q->bias_window < 1 || q->bias_window > 8192) { c->err = "bias offset/window out of range (offset >= 0, window 1..8192)"; return RSQ_ERR_INVALID; }
     CU_TRY(cudaSetDevice(c->cfg.device));
     CU_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaStream_t st = c->stream;

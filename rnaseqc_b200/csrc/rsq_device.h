@@ -142,6 +142,7 @@ struct Accum {
     unsigned long long  pair_mask;
     unsigned int*       mate_left;       // [2 * kMateLeftCap] candidate indices still to be replayed (BED half, GC half)
     unsigned int*       mate_left_count; // [2]
+    unsigned long long* mate_totals;     // [2] candidates since the last reset: what the host sizes the maps by
     PairCandidate*      cand;            // per-batch candidate list
     unsigned int*       cand_count;      // [1]
     unsigned int        cand_capacity;

@@ -915,6 +915,7 @@ __device__ __forceinline__ void mate_apply(const Accum& acc, const RefView& ref,
 template <class M>
 __global__ void mate_first_kernel(const Accum acc, const Params prm, const RefView ref) {
     const unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) atomicAdd(&acc.mate_totals[M::kWhich], (unsigned long long)M::count(acc));
     if (k >= M::count(acc)) return;
     const typename M::Cand c = M::list(acc)[k];
     if (M::first(acc)[c.slot] == mate_tag(prm.mate_round, 1u, c.local_idx)) mate_apply<M>(acc, ref, c);
