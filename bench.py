@@ -362,11 +362,18 @@ def run_ours(args):
     sampler.start()
     t_load = time.perf_counter()
     res = None
-    k = 0
-    while k < args.warmup or (time.perf_counter() - t_load < args.min_warmup_s and k < 1000):
+    for _ in range(args.warmup):
         res = step_resident()
-        k += 1
-    warm_done = k
+    # warm-up goes on until min_warmup_s have passed (nvidia-smi needs about a second of load before its first row).  Every step is
+    # a collective at N > 1, so the NUMBER of extra steps is fixed on rank 0 and broadcast: ranks that disagreed on it would wait
+    # for each other forever (that was the hang of the first 8-GPU run of round 2)
+    per_step = max((time.perf_counter() - t_load) / max(args.warmup, 1), 1e-4)
+    extra = [int(min(1000, max(0.0, args.min_warmup_s - (time.perf_counter() - t_load)) / per_step))]
+    if world > 1:
+        dist.broadcast_object_list(extra, src=0)
+    for _ in range(extra[0]):
+        res = step_resident()
+    warm_done = args.warmup + extra[0]
     algo_bytes = ctx.algorithmic_bytes()
     barrier()
     l0 = ctx.launch_count()
@@ -399,10 +406,22 @@ def run_ours(args):
     # ---------------- end to end from pinned host buffers ------------------------------------------------------------
     e2e = None
     e2e_rank = {}
-    if not args.no_e2e:
+    have_pinned = not args.no_e2e
+    if have_pinned:
         try:
             h_reads = torch.empty(rb.shape, dtype=rb.dtype, pin_memory=True)
             h_blocks = torch.empty(bb.shape, dtype=bb.dtype, pin_memory=True)
+        except (MemoryError, RuntimeError) as ex:   # pinned allocation can fail on a small host
+            log(f"[rank {rank}] no page-locked memory for the e2e leg: {ex!r}")
+            have_pinned = False
+        if world > 1:                               # every step is a collective: the ranks go through the e2e leg together or not at all
+            t = torch.tensor([1 if have_pinned else 0], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            have_pinned = bool(t.item())
+        if not have_pinned:
+            e2e = {"value": None, "unit": "reads/s", "error": "page-locked host buffers could not be allocated on every rank"}
+    if have_pinned:
+        try:
             h_reads.copy_(rb); h_blocks.copy_(bb)
             torch.cuda.synchronize()
             off = np.frombuffer(h_reads.numpy().reshape(-1).data, dtype=api.READ_DTYPE)
