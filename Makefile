@@ -15,7 +15,7 @@ HOST_SRCS := annotation.cpp alnreader.cpp cramreader.cpp bamparallel.cpp fasta.c
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
-oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so $(ODIR)/libhostlegacy.so
+oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so $(ODIR)/libhostlegacy.so $(ODIR)/libcudaemu.so
 ref:
 	$(MAKE) -f oracle/Makefile.ref
 
@@ -52,6 +52,12 @@ $(ODIR)/libhostlegacy.so: tests/hostcore/hostlegacy.cpp rnaseqc_b200/csrc/rsq_le
 $(ODIR)/libhostcore_sd.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h rnaseqc_b200/csrc/rsq_device.h include/rsq_b200.h
 	@mkdir -p $(ODIR)
 	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -DRSQ_STAGE_DESC -DRSQ_STAGE_N=64 -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
+
+# test infrastructure: the CUDA kernels that have no CPU twin, compiled for the host through tests/cudaemu/cuda_emu.h (one OS thread
+# per CUDA thread; barriers, warp shuffles and atomics emulated) — tests/test_cudaemu.py
+$(ODIR)/libcudaemu.so: tests/cudaemu/emu_kernels.cpp tests/cudaemu/emu_covstats.cpp tests/cudaemu/cuda_emu.h rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_covstats.cu rnaseqc_b200/csrc/rsq_device.h rnaseqc_b200/csrc/rsq_hot_core.cuh include/rsq_b200.h
+	@mkdir -p $(ODIR)
+	$(CXX) -std=c++17 -O1 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Wno-unused-value -Wno-attributes -Wno-unknown-pragmas -Iinclude -Irnaseqc_b200/csrc -Itests/cudaemu -I/usr/local/cuda/include -shared -o $@ tests/cudaemu/emu_kernels.cpp tests/cudaemu/emu_covstats.cpp -lpthread
 
 $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
 	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'

@@ -238,7 +238,7 @@ coverage_stats_kernel(const unsigned int* __restrict__ cov, uint32_t n_genes, co
                       int bias_window, uint32_t bias_gene_length, double* __restrict__ gene_mean, double* __restrict__ gene_std,
                       double* __restrict__ gene_cv, unsigned long long* __restrict__ five_end, unsigned long long* __restrict__ three_end,
                       double* __restrict__ exon_cv, const uint8_t* __restrict__ gene_owned, unsigned win_cap) {
-    extern __shared__ double s_dyn[];
+    RSQ_DYNAMIC_SMEM(double, s_dyn);
     __shared__ unsigned long long s_u64[kThreads / 32];
     constexpr unsigned kTeams = kThreads / kTeam;
     const uint32_t g = kTeam == 32 ? blockIdx.x * kTeams + (threadIdx.x >> 5) : blockIdx.x;
@@ -279,7 +279,7 @@ int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsig
                           const uint8_t* gene_owned, bool nan_prefill, cudaStream_t stream) {
     int n = 0;
     if (n_exons) {
-        if (nan_prefill) { fill_nan_kernel<<<(n_exons + 255) / 256, 256, 0, stream>>>(exon_cv, n_exons); ++n; }
+        if (nan_prefill) { RSQ_LAUNCH(fill_nan_kernel, (n_exons + 255) / 256, 256, 0, stream, exon_cv, n_exons); ++n; }
         else cudaMemsetAsync(exon_cv, 0, 8ull * n_exons, stream);       // partitions other than the first: zero bits
     }
     if (n_genes) {
@@ -287,13 +287,13 @@ int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsig
         while (p2 < (unsigned)bias_window) p2 <<= 1;
         // short transcripts: one warp each (four genes per CTA), windows of up to kWarpWindow values per warp
         const unsigned wcap = std::min<unsigned>(p2, kWarpWindow);
-        coverage_stats_kernel<32><<<(n_genes + 3) / 4, kThreads, 4 * 2 * wcap * sizeof(double), stream>>>(
+        RSQ_LAUNCH(coverage_stats_kernel<32>, (n_genes + 3) / 4, kThreads, 4 * 2 * wcap * sizeof(double), stream, 
             cov, n_genes, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length, gene_mean,
             gene_std, gene_cv, five_end, three_end, exon_cv, gene_owned, wcap);
         // the rest: one CTA each; windows of up to kMaxWindow values need more than the default 48 KB of shared memory
         const size_t big = 2 * (size_t)p2 * sizeof(double);
         if (big > 48 * 1024) cudaFuncSetAttribute(coverage_stats_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big);
-        coverage_stats_kernel<kThreads><<<n_genes, kThreads, big, stream>>>(
+        RSQ_LAUNCH(coverage_stats_kernel<kThreads>, n_genes, kThreads, big, stream, 
             cov, n_genes, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length, gene_mean,
             gene_std, gene_cv, five_end, three_end, exon_cv, gene_owned, p2);
         n += 2;

@@ -5,6 +5,16 @@
 
 #include "rsq_b200.h"
 
+// Kernel launches go through one macro so that the CPU test harness (tests/cudaemu: the kernels' own sources compiled for the host,
+// one OS thread per CUDA thread, barriers and warp shuffles emulated) can run what cannot be tested without a GPU otherwise.
+#if defined(RSQ_CUDA_EMU)
+#define RSQ_LAUNCH(kernel, grid, block, smem, stream, ...) ::cuda_emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define RSQ_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(::cuda_emu::dynamic_smem())
+#else
+#define RSQ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define RSQ_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 namespace rsqd {
 
 // Exon metadata packed for one 128-bit load.

@@ -74,6 +74,7 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
     return set_insert_seen(tab, cap, key, tab[set_home(key, cap)], err, err_bit);
 }
 
+#ifndef RSQ_CUDA_EMU   // the hot kernel: inline PTX (TMA, mbarrier, cp.async), match.any, redux — not for the CPU test harness (tests/cudaemu)
 // ---- per-warp staging of the interval starts into shared memory (TMA bulk copy) ----------------------------------------
 // A tile is 32 coordinate-sorted records, so their blocks fall into a short run of elementary intervals: the starts of the
 // kStageN intervals from the tile's lowest coordinate on are copied ONCE per tile into the warp's private slice of shared
@@ -618,6 +619,8 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     if (threadIdx.x == 0 && s_bytes) atomicAdd(acc.algo_bytes, s_bytes);
 }
 
+#endif  // RSQ_CUDA_EMU
+
 // ---- annotation preprocessing -----------------------------------------------------------------------------------------
 // running max of exon end inside each contig (one thread per contig: a few hundred thousand elements, once per run)
 __global__ void prefix_max_kernel(const int2* __restrict__ se, const uint32_t* __restrict__ off, uint32_t n_contigs, int32_t* __restrict__ pmax) {
@@ -1156,6 +1159,7 @@ __global__ void __launch_bounds__(256) expand_compact_kernel(const unsigned char
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------------------------------------------
+#ifndef RSQ_CUDA_EMU
 int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann, const BedView& bed,
                     const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
@@ -1177,20 +1181,22 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     }
     const size_t tiles = (n_reads + 31) / 32;
     const unsigned grid = (unsigned)std::min<size_t>((size_t)sms * per_sm[which], (tiles + 7) / 8);
-    kernels[which]<<<grid, kHotThreads, 0, stream>>>(reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
+    RSQ_LAUNCH(kernels[which], grid, kHotThreads, 0, stream, reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
     return 1;
 }
 
+#endif  // RSQ_CUDA_EMU
+
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream) {
     if (!n_contigs) return 0;
-    prefix_max_kernel<<<(n_contigs + 63) / 64, 64, 0, stream>>>(se, off, n_contigs, pmax);
+    RSQ_LAUNCH(prefix_max_kernel, (n_contigs + 63) / 64, 64, 0, stream, se, off, n_contigs, pmax);
     return 1;
 }
 
 
 int launch_pair_rehash(const unsigned long long* old_keys, const unsigned long long* old_payload, unsigned long long old_cap, unsigned long long* nk,
                        unsigned long long* np, unsigned long long new_mask, unsigned int* error_flag, cudaStream_t stream) {
-    pair_rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_keys, old_payload, old_cap, nk, np, new_mask, error_flag);
+    RSQ_LAUNCH(pair_rehash_kernel, (unsigned)((old_cap + 255) / 256), 256, 0, stream, old_keys, old_payload, old_cap, nk, np, new_mask, error_flag);
     return 1;
 }
 
@@ -1199,15 +1205,15 @@ size_t coverage_scan_scratch_elems(unsigned long long n) { return (size_t)((n + 
 int launch_coverage_scan(const unsigned int* diff, unsigned int* cov, unsigned long long n, unsigned int* block_sums, cudaStream_t stream) {
     if (!n) return 0;
     const unsigned long long tiles = (n + kScanTile - 1) / kScanTile;
-    tile_sum_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(diff, n, block_sums);
-    scan_sums_kernel<<<1, 1024, 0, stream>>>(block_sums, tiles);
-    tile_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(diff, cov, n, block_sums);
+    RSQ_LAUNCH(tile_sum_kernel, (unsigned)tiles, kScanThreads, 0, stream, diff, n, block_sums);
+    RSQ_LAUNCH(scan_sums_kernel, 1, 1024, 0, stream, block_sums, tiles);
+    RSQ_LAUNCH(tile_scan_kernel, (unsigned)tiles, kScanThreads, 0, stream, diff, cov, n, block_sums);
     return 3;
 }
 
 int launch_rehash(const unsigned long long* old_tab, unsigned long long old_cap, unsigned long long* new_tab, unsigned long long new_cap,
                   unsigned int* error_flag, cudaStream_t stream) {
-    rehash_kernel<<<(unsigned)((old_cap + 255) / 256), 256, 0, stream>>>(old_tab, old_cap, new_tab, new_cap, error_flag);
+    RSQ_LAUNCH(rehash_kernel, (unsigned)((old_cap + 255) / 256), 256, 0, stream, old_tab, old_cap, new_tab, new_cap, error_flag);
     return 1;
 }
 
@@ -1215,22 +1221,22 @@ size_t export_count_words(uint32_t n_genes, uint32_t n_exons, unsigned long long
     return (size_t)(RSQ_N_COUNTERS + 3ull * n_genes + 3ull * n_exons + 100ull + 1ull + (quota + 1ull) / 2ull);
 }
 int launch_pack_sample_counts(const Accum& acc, uint32_t rank, uint32_t world, unsigned long long* out, cudaStream_t stream) {
-    pack_sample_counts_kernel<<<(world + 63) / 64, 64, 0, stream>>>(acc, rank, world, out);
+    RSQ_LAUNCH(pack_sample_counts_kernel, (world + 63) / 64, 64, 0, stream, acc, rank, world, out);
     return 1;
 }
 int launch_pack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* found, uint32_t rank,
                        uint32_t world, unsigned long long* out, cudaStream_t stream) {
-    pack_counts_kernel<<<148 * 4, 256, 0, stream>>>(acc, n_genes, n_exons, quota, found, rank, world, out);
+    RSQ_LAUNCH(pack_counts_kernel, 148 * 4, 256, 0, stream, acc, n_genes, n_exons, quota, found, rank, world, out);
     return 1;
 }
 int launch_unpack_counts(const Accum& acc, uint32_t n_genes, uint32_t n_exons, unsigned long long quota, const unsigned long long* in, cudaStream_t stream) {
-    unpack_counts_kernel<<<148 * 4, 256, 0, stream>>>(acc, n_genes, n_exons, quota, in);
+    RSQ_LAUNCH(unpack_counts_kernel, 148 * 4, 256, 0, stream, acc, n_genes, n_exons, quota, in);
     return 1;
 }
 
 int launch_combine_exon(const Accum& acc, uint32_t n_exons, unsigned long long* whole_out, unsigned long long* frac_out, cudaStream_t stream) {
     if (!n_exons) return 0;
-    combine_exon_kernel<<<(n_exons + 255) / 256, 256, 0, stream>>>(acc, n_exons, whole_out, frac_out);
+    RSQ_LAUNCH(combine_exon_kernel, (n_exons + 255) / 256, 256, 0, stream, acc, n_exons, whole_out, frac_out);
     return 1;
 }
 
@@ -1240,51 +1246,51 @@ int launch_pair_stages(size_t n_reads, const Accum& acc, const Params& prm, unsi
     if (!n_reads) return 0;
     const unsigned cgrid = (unsigned)((std::min<size_t>(n_reads, acc.cand_capacity) + 255) / 256);
     const RefView no_ref{};
-    mate_first_kernel<BedMap><<<cgrid, 256, 0, stream>>>(acc, prm, no_ref);
-    mate_second_kernel<BedMap><<<cgrid, 256, 0, stream>>>(acc, prm, no_ref);
-    mate_rest_kernel<BedMap><<<1, 1024, 0, stream>>>(acc, prm, no_ref);
+    RSQ_LAUNCH(mate_first_kernel<BedMap>, cgrid, 256, 0, stream, acc, prm, no_ref);
+    RSQ_LAUNCH(mate_second_kernel<BedMap>, cgrid, 256, 0, stream, acc, prm, no_ref);
+    RSQ_LAUNCH(mate_rest_kernel<BedMap>, 1, 1024, 0, stream, acc, prm, no_ref);
     const unsigned long long tiles = (n_reads + kScanTile - 1) / kScanTile;
     unsigned int* sums = scratch;
     unsigned int* last = scratch + tiles + 1;
-    sample_count_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(acc.sample_flag, n_reads, sums);
-    save_last_kernel<<<1, 32, 0, stream>>>(sums, tiles, last);            // count of the last tile, before the scan overwrites it
-    scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, tiles);
-    sample_rank_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(acc.sample_flag, acc.sample_isize, n_reads, sums, acc, prm);
-    sample_commit_kernel<<<1, 32, 0, stream>>>(sums, tiles, last, acc);
+    RSQ_LAUNCH(sample_count_kernel, (unsigned)tiles, kScanThreads, 0, stream, acc.sample_flag, n_reads, sums);
+    RSQ_LAUNCH(save_last_kernel, 1, 32, 0, stream, sums, tiles, last);            // count of the last tile, before the scan overwrites it
+    RSQ_LAUNCH(scan_sums_kernel, 1, 1024, 0, stream, sums, tiles);
+    RSQ_LAUNCH(sample_rank_kernel, (unsigned)tiles, kScanThreads, 0, stream, acc.sample_flag, acc.sample_isize, n_reads, sums, acc, prm);
+    RSQ_LAUNCH(sample_commit_kernel, 1, 32, 0, stream, sums, tiles, last, acc);
     return 8;
 }
 
 int launch_unpack_counts_of(const rsq_read_packed* packed, size_t n, unsigned int* tot, unsigned int* expl, cudaStream_t stream) {
     if (!n) return 0;
-    unpack_counts_of_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(packed, n, tot, expl);
+    RSQ_LAUNCH(unpack_counts_of_kernel, (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream, packed, n, tot, expl);
     return 1;
 }
 int launch_unpack_records(const rsq_read_packed* packed, size_t n, const rsq_block* xblocks, size_t n_xblocks, const unsigned int* incl_tot,
                           const unsigned int* incl_expl, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream) {
     if (!n) return 0;
-    unpack_records_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(packed, n, xblocks, n_xblocks, incl_tot, incl_expl,
+    RSQ_LAUNCH(unpack_records_kernel, (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream, packed, n, xblocks, n_xblocks, incl_tot, incl_expl,
                                                                                                         reads, blocks, error_flag);
     return 1;
 }
 
 int launch_expand_compact(const unsigned char* buf, const rsq_batch16& hdr, rsq_read* reads, rsq_block* blocks, unsigned int* error_flag, cudaStream_t stream) {
     if (!hdr.n_tiles) return 0;
-    expand_compact_kernel<<<(hdr.n_tiles + 7) / 8, 256, 0, stream>>>(buf, hdr, reads, blocks, error_flag);
+    RSQ_LAUNCH(expand_compact_kernel, (hdr.n_tiles + 7) / 8, 256, 0, stream, buf, hdr, reads, blocks, error_flag);
     return 1;
 }
 
 int launch_gc_stages(size_t n_reads, const RefView& ref, const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
     const unsigned cgrid = (unsigned)((std::min<size_t>(n_reads, acc.gc_cand_capacity) + 255) / 256);
-    mate_first_kernel<GcMap><<<cgrid, 256, 0, stream>>>(acc, prm, ref);
-    mate_second_kernel<GcMap><<<cgrid, 256, 0, stream>>>(acc, prm, ref);
-    mate_rest_kernel<GcMap><<<1, 1024, 0, stream>>>(acc, prm, ref);
+    RSQ_LAUNCH(mate_first_kernel<GcMap>, cgrid, 256, 0, stream, acc, prm, ref);
+    RSQ_LAUNCH(mate_second_kernel<GcMap>, cgrid, 256, 0, stream, acc, prm, ref);
+    RSQ_LAUNCH(mate_rest_kernel<GcMap>, 1, 1024, 0, stream, acc, prm, ref);
     return 3;
 }
 
 int launch_sample_histogram(const unsigned int* vals, unsigned long long n, unsigned long long* hist, unsigned long long hist_len, cudaStream_t stream) {
     if (!n) return 0;
-    sample_hist_kernel<<<148, 256, 0, stream>>>(vals, n, hist, hist_len);
+    RSQ_LAUNCH(sample_hist_kernel, 148, 256, 0, stream, vals, n, hist, hist_len);
     return 1;
 }
 

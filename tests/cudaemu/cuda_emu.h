@@ -1,0 +1,207 @@
+// cuda_emu.h — TEST INFRASTRUCTURE: runs CUDA kernels on the CPU, one OS thread per CUDA thread of a block, blocks one after another.
+//
+// The kernels of rnaseqc_b200/csrc that have no CPU twin (the mate-map stages, the per-gene coverage statistics, the wire-format
+// expansion, the exchange packers, the scans) are compiled from their own sources with RSQ_CUDA_EMU defined and run through this
+// header, so that the CPU test suite exercises the very code the GPU runs — barriers, warp shuffles and atomics included:
+//   __syncthreads()            a barrier over the block's live threads (threads that returned have left it, as on the device)
+//   __shfl_*_sync, __ballot_sync, __syncwarp
+//                              exchange through a per-warp slot array between two warp barriers; every live lane of the warp
+//                              must take part (the kernels emulated here only use full masks on converged warps)
+//   atomicAdd / Max / Min / CAS / Or / Sub   real atomics (the threads of a block run concurrently)
+//   __shared__                 static storage (one block at a time), dynamic shared memory through RSQ_DYNAMIC_SMEM
+// Not emulated: inline PTX (TMA, mbarrier, cp.async), match.any / redux, occupancy queries — the hot kernel itself stays out (its
+// per-record logic has its own host emulation, tests/hostcore).
+#pragma once
+#include <cuda_runtime.h>      // vector types, cudaStream_t (host-side declarations only; nothing of the runtime is called)
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __shared__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __align__
+#define __global__
+#define __device__
+#define __host__
+#define __shared__ static
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+namespace cuda_emu {
+
+// a barrier whose party count can shrink (threads that return from the kernel leave it)
+class Barrier {
+public:
+    void reset(unsigned parties) { parties_ = parties; waiting_ = 0; generation_ = 0; }
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        const unsigned long gen = generation_;
+        if (++waiting_ >= parties_) { waiting_ = 0; ++generation_; cv_.notify_all(); return; }
+        cv_.wait(lk, [&] { return gen != generation_; });
+    }
+    void drop() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (parties_) --parties_;
+        if (parties_ && waiting_ >= parties_) { waiting_ = 0; ++generation_; cv_.notify_all(); }
+    }
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    unsigned parties_ = 0, waiting_ = 0;
+    unsigned long generation_ = 0;
+};
+
+struct Warp {
+    Barrier bar;
+    unsigned long long slot[32];
+    std::atomic<unsigned> live{0};      // mask of the lanes still running
+};
+
+struct Block {
+    Barrier bar;
+    std::vector<Warp> warps;
+    std::vector<unsigned char> dyn_smem;
+};
+
+struct Tls {
+    uint3 tid, bid;
+    dim3 bdim, gdim;
+    Block* block = nullptr;
+    Warp* warp = nullptr;
+    unsigned lane = 0;
+};
+inline Tls& tls() { static thread_local Tls t; return t; }
+inline void* dynamic_smem() { return tls().block->dyn_smem.data(); }
+
+inline unsigned to_dim(unsigned v) { return v; }
+inline unsigned to_dim(int v) { return (unsigned)v; }
+inline unsigned to_dim(unsigned long v) { return (unsigned)v; }
+inline unsigned to_dim(unsigned long long v) { return (unsigned)v; }
+inline unsigned to_dim(long v) { return (unsigned)v; }
+
+template <class G, class B>
+void launch(G grid, B block_threads, size_t smem, const std::function<void()>& body) {
+    const unsigned n_blocks = to_dim(grid), n_threads = to_dim(block_threads);
+    if (!n_blocks || !n_threads) return;
+    Block blk;
+    blk.warps = std::vector<Warp>((n_threads + 31) / 32);
+    blk.dyn_smem.assign(smem + 16, 0);
+    for (unsigned b = 0; b < n_blocks; ++b) {
+        blk.bar.reset(n_threads);
+        for (unsigned w = 0; w < blk.warps.size(); ++w) {
+            const unsigned lanes = std::min(32u, n_threads - 32 * w);
+            blk.warps[w].bar.reset(lanes);
+            blk.warps[w].live = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1u);
+        }
+        std::vector<std::thread> ts;
+        ts.reserve(n_threads);
+        for (unsigned t = 0; t < n_threads; ++t)
+            ts.emplace_back([&, t, b] {
+                Tls& T = tls();
+                T.tid = make_uint3(t, 0, 0); T.bid = make_uint3(b, 0, 0);
+                T.bdim = dim3(n_threads, 1, 1); T.gdim = dim3(n_blocks, 1, 1);
+                T.block = &blk; T.warp = &blk.warps[t / 32]; T.lane = t % 32;
+                body();
+                T.warp->live.fetch_and(~(1u << T.lane));
+                T.warp->bar.drop();
+                blk.bar.drop();
+            });
+        for (auto& th : ts) th.join();
+    }
+}
+
+}  // namespace cuda_emu
+
+#define threadIdx (::cuda_emu::tls().tid)
+#define blockIdx (::cuda_emu::tls().bid)
+#define blockDim (::cuda_emu::tls().bdim)
+#define gridDim (::cuda_emu::tls().gdim)
+
+// ---- synchronisation and warp collectives ---------------------------------------------------------------------------------------
+inline void __syncthreads() { ::cuda_emu::tls().block->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { ::cuda_emu::tls().warp->bar.arrive_and_wait(); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+namespace cuda_emu {
+template <class T> inline unsigned long long to_bits(T v) { unsigned long long b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
+// every live lane publishes `v`, then reads the slot of lane `src` (its own value when src is not a live lane)
+template <class T> inline T exchange(T v, int src) {
+    Tls& t = tls();
+    t.warp->slot[t.lane] = to_bits(v);
+    t.warp->bar.arrive_and_wait();
+    T r = v;
+    if (src >= 0 && src < 32 && (t.warp->live.load() >> src & 1u)) r = from_bits<T>(t.warp->slot[src]);
+    t.warp->bar.arrive_and_wait();
+    return r;
+}
+}  // namespace cuda_emu
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return ::cuda_emu::exchange(v, src & 31); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int d) { return ::cuda_emu::exchange(v, (int)(::cuda_emu::tls().lane ^ (unsigned)d)); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+    const int lane = (int)::cuda_emu::tls().lane;
+    return ::cuda_emu::exchange(v, lane - (int)d >= 0 ? lane - (int)d : lane);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    ::cuda_emu::Tls& t = ::cuda_emu::tls();
+    t.warp->slot[t.lane] = pred ? 1ull : 0ull;
+    t.warp->bar.arrive_and_wait();
+    unsigned m = 0;
+    const unsigned live = t.warp->live.load();
+    for (int l = 0; l < 32; ++l) if ((live >> l & 1u) && t.warp->slot[l]) m |= 1u << l;
+    t.warp->bar.arrive_and_wait();
+    return m;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+
+// ---- atomics ----------------------------------------------------------------------------------------------------------------------
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned int atomicSub(unsigned int* p, unsigned int v) { return __atomic_fetch_sub(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned int atomicOr(unsigned int* p, unsigned int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+    unsigned long long cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return cur;
+}
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+    unsigned long long cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (cur > v && !__atomic_compare_exchange_n(p, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return cur;
+}
+
+// ---- loads, bit tricks, maths ----------------------------------------------------------------------------------------------------
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+using std::isinf;
+using std::isnan;
+using std::sqrt;
+template <class T> inline T min(T a, T b) { return b < a ? b : a; }
+template <class T> inline T max(T a, T b) { return a < b ? b : a; }
+inline unsigned long long min(unsigned long long a, unsigned int b) { return a < b ? a : b; }
+inline unsigned int min(unsigned int a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
+
+// ---- the few runtime calls the launchers make ------------------------------------------------------------------------------------
+#define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
+#define cudaFuncSetAttribute(...) (cudaSuccess)
