@@ -15,7 +15,7 @@ HOST_SRCS := annotation.cpp alnreader.cpp cramreader.cpp bamparallel.cpp fasta.c
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc
-oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so $(ODIR)/libhostlegacy.so $(ODIR)/libcudaemu.so
+oracle: $(ODIR)/librsq_oracle.so $(ODIR)/rnaseqc_oracle $(ODIR)/libhostcore.so $(ODIR)/libhostcore_sd.so $(ODIR)/libhostlegacy.so $(ODIR)/librsq_emu.so $(ODIR)/rnaseqc_emu
 ref:
 	$(MAKE) -f oracle/Makefile.ref
 
@@ -53,11 +53,19 @@ $(ODIR)/libhostcore_sd.so: tests/hostcore/hostcore.cpp rnaseqc_b200/csrc/rsq_hot
 	@mkdir -p $(ODIR)
 	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -DRSQ_STAGE_DESC -DRSQ_STAGE_N=64 -Iinclude -Irnaseqc_b200/csrc -I/usr/local/cuda/include -x c++ -shared -o $@ $<
 
-# test infrastructure: the CUDA kernels that have no CPU twin, compiled for the host through tests/cudaemu/cuda_emu.h (one OS thread
-# per CUDA thread; barriers, warp shuffles and atomics emulated) — tests/test_cudaemu.py
-$(ODIR)/libcudaemu.so: tests/cudaemu/emu_kernels.cpp tests/cudaemu/emu_covstats.cpp tests/cudaemu/cuda_emu.h rnaseqc_b200/csrc/rsq_kernels.cu rnaseqc_b200/csrc/rsq_covstats.cu rnaseqc_b200/csrc/rsq_device.h rnaseqc_b200/csrc/rsq_hot_core.cuh include/rsq_b200.h
+# test infrastructure: the WHOLE CUDA library compiled for the host through tests/cudaemu/cuda_emu.h (kernel and C-ABI sources unchanged; one
+# OS thread per CUDA thread; barriers, warp collectives, atomics and the runtime calls emulated): librsq_emu.so implements include/rsq_b200.h
+# on the CPU, rnaseqc_emu is the product CLI over it — tests/test_cudaemu.py, and the -m gpu suite replayed with RSQ_EMULATE=1
+EMU_SRCS := tests/cudaemu/emu_kernels.cpp tests/cudaemu/emu_covstats.cpp tests/cudaemu/emu_capi.cpp
+EMU_DEPS := tests/cudaemu/cuda_emu.h $(CU_SRCS) rnaseqc_b200/csrc/rsq_device.h rnaseqc_b200/csrc/rsq_legacy.cuh rnaseqc_b200/csrc/rsq_hot_core.cuh rnaseqc_b200/csrc/rsq_eit.h include/rsq_b200.h
+EMU_FLAGS := -std=c++17 -O2 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Wno-unused-value -Wno-attributes -Wno-unknown-pragmas -Iinclude -Irnaseqc_b200/csrc -Itests/cudaemu -I/usr/local/cuda/include
+$(ODIR)/emu_%.o: tests/cudaemu/emu_%.cpp $(EMU_DEPS)
 	@mkdir -p $(ODIR)
-	$(CXX) -std=c++17 -O1 -fPIC -Wall -Wno-sign-compare -Wno-unused-function -Wno-unused-value -Wno-attributes -Wno-unknown-pragmas -Iinclude -Irnaseqc_b200/csrc -Itests/cudaemu -I/usr/local/cuda/include -shared -o $@ tests/cudaemu/emu_kernels.cpp tests/cudaemu/emu_covstats.cpp -lpthread
+	$(CXX) $(EMU_FLAGS) -c $< -o $@
+$(ODIR)/librsq_emu.so: $(ODIR)/emu_kernels.o $(ODIR)/emu_covstats.o $(ODIR)/emu_capi.o
+	$(CXX) -shared -o $@ $^ -lpthread -ldl
+$(ODIR)/rnaseqc_emu: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_emu.so
+	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_emu -lz -lpthread -Wl,-rpath,'$$ORIGIN'
 
 $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_oracle.so
 	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'

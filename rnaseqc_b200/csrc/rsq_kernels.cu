@@ -74,7 +74,6 @@ __device__ __forceinline__ bool set_insert(unsigned long long* __restrict__ tab,
     return set_insert_seen(tab, cap, key, tab[set_home(key, cap)], err, err_bit);
 }
 
-#ifndef RSQ_CUDA_EMU   // the hot kernel: inline PTX (TMA, mbarrier, cp.async), match.any, redux — not for the CPU test harness (tests/cudaemu)
 // ---- per-warp staging of the interval starts into shared memory (TMA bulk copy) ----------------------------------------
 // A tile is 32 coordinate-sorted records, so their blocks fall into a short run of elementary intervals: the starts of the
 // kStageN intervals from the tile's lowest coordinate on are copied ONCE per tile into the warp's private slice of shared
@@ -98,6 +97,7 @@ struct __align__(16) WarpStage {
     unsigned long long pad;
 };
 
+#if !defined(RSQ_CUDA_EMU)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t mbar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
@@ -118,6 +118,47 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
                      : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
     } while (!ok);
 }
+// the staged slice of one tile: issued by ONE lane, completion on the warp's mbarrier
+__device__ __forceinline__ void stage_issue(WarpStage* st, uint32_t mbar, const int32_t* starts, const uint2* descs) {
+#ifdef RSQ_STAGE_DESC
+    mbar_expect_tx(mbar, (uint32_t)(kStageN * 12));
+    tma_bulk_g2s(smem_u32(st->starts), starts, (uint32_t)(kStageN * 4), mbar);   // both arrays are padded
+    tma_bulk_g2s(smem_u32(st->descs), descs, (uint32_t)(kStageN * 8), mbar);
+#else
+    (void)descs;
+    mbar_expect_tx(mbar, (uint32_t)(kStageN * 4));
+    tma_bulk_g2s(smem_u32(st->starts), starts, (uint32_t)(kStageN * 4), mbar);   // the array is padded
+#endif
+}
+__device__ __forceinline__ void stage_wait(uint32_t mbar, uint32_t parity) { mbar_wait(mbar, parity); }
+// 8 bytes of global memory into shared memory without a register in between (LDGSTS); home_wait before they are read
+__device__ __forceinline__ void home_fetch(unsigned long long* dst_smem, const unsigned long long* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void home_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void home_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t peek_u32(const void* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+// CPU test harness (tests/cudaemu): the bulk copy is a memcpy by the issuing lane and its mbarrier a warp barrier; the asynchronous
+// 8-byte copy is a load; prefetches are nothing
+inline uint32_t smem_u32(const void*) { return 0u; }
+inline void mbar_init(uint32_t) {}
+inline void stage_issue(WarpStage* st, uint32_t, const int32_t* starts, const uint2* descs) {
+    memcpy(st->starts, starts, kStageN * 4);
+#ifdef RSQ_STAGE_DESC
+    memcpy(st->descs, descs, kStageN * 8);
+#else
+    (void)descs;
+#endif
+}
+inline void stage_wait(uint32_t, uint32_t) { __syncwarp(); }
+inline void home_fetch(unsigned long long* dst, const unsigned long long* src) { *dst = __atomic_load_n(src, __ATOMIC_SEQ_CST); }
+inline void home_commit() {}
+inline void home_wait() {}
+inline uint32_t peek_u32(const void* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline void prefetch_l2(const void*) {}
+#endif
 
 // Inserts the keys a warp parked one tile ago (their table lines were prefetched into L2 then) and counts the distinct
 // (read name, gene) pairs: geneFragmentCounts, src/Expression.cpp:383-387.  Coordinate-sorted input => the lanes mostly share
@@ -133,7 +174,7 @@ __device__ __forceinline__ int resolve_parked(Stage* st, const Accum& acc, unsig
 #ifdef RSQ_FRAG_PREFETCH_ONLY
     const bool fresh = key != 0ull && set_insert(acc.frag_set, acc.frag_cap, key, acc.error_flag, 1u);
 #else
-    asm volatile("cp.async.wait_group 0;" ::: "memory");               // the home slots fetched one tile ago have landed
+    home_wait();                                                        // the home slots fetched one tile ago have landed
     const bool fresh = key != 0ull && set_insert_seen(acc.frag_set, acc.frag_cap, key, st->fval[lane], acc.error_flag, 1u);
 #endif
 #endif
@@ -302,14 +343,11 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     next_boff = peek_boff;
     {
         const size_t t2 = (size_t)tile + 2u * (size_t)warps_total;
-        if (t2 * 32u + lane < n_reads)
-            asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(peek_boff) : "l"(reinterpret_cast<const char*>(reads + (t2 * 32u + lane)) + 40));
-        if (lane < 12u && t2 * 32u < n_reads)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(reads + t2 * 32u) + 128u * lane));
+        if (t2 * 32u + lane < n_reads) peek_boff = peek_u32(reinterpret_cast<const char*>(reads + (t2 * 32u + lane)) + 40);
+        if (lane < 12u && t2 * 32u < n_reads) prefetch_l2(reinterpret_cast<const char*>(reads + t2 * 32u) + 128u * lane);
     }
 #else
-    if (has_next)
-        asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(next_boff) : "l"(reinterpret_cast<const char*>(reads + ((size_t)RSQ_TILE_NEXT * 32u + lane)) + 40));
+    if (has_next) next_boff = peek_u32(reinterpret_cast<const char*>(reads + ((size_t)RSQ_TILE_NEXT * 32u + lane)) + 40);
 #endif
 #endif
 
@@ -336,16 +374,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
             to_end = w.hi == c_hi;
             w.on = true;
             __syncwarp();                                                // every lane is done with the previous tile's copy
-            if (lane == 0) {
-#ifdef RSQ_STAGE_DESC
-                mbar_expect_tx(mbar, (uint32_t)(kStageN * 12));
-                tma_bulk_g2s(smem_u32(st->starts), ann.ei_start + w.base, (uint32_t)(kStageN * 4), mbar);   // both arrays are padded
-                tma_bulk_g2s(smem_u32(st->descs), ann.ei_desc + w.base, (uint32_t)(kStageN * 8), mbar);
-#else
-                mbar_expect_tx(mbar, (uint32_t)(kStageN * 4));
-                tma_bulk_g2s(smem_u32(st->starts), ann.ei_start + w.base, (uint32_t)(kStageN * 4), mbar);   // the array is padded
-#endif
-            }
+            if (lane == 0) stage_issue(st, mbar, ann.ei_start + w.base, ann.ei_desc + w.base);
         }
     }
 #endif
@@ -368,7 +397,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     filter_cascade(prm, valid, f, mapq, aux, filter_mask, pos, mpos, endpos, nm_raw, nb, o);
 
     if (w.on) {                                                                        // the starts have landed in shared memory
-        mbar_wait(mbar, phase); phase ^= 1u;
+        stage_wait(mbar, phase); phase ^= 1u;
         w.lastv = to_end ? INT32_MAX : st->starts[w.hi - 1 - w.base];
     }
 
@@ -498,7 +527,7 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
     }
 
 #ifndef RSQ_AB_NO_PREFETCH
-    if (has_next) asm volatile("prefetch.global.L2 [%0];" ::"l"(blocks + next_boff));
+    if (has_next) prefetch_l2(blocks + next_boff);
 #endif
 
     // ---- warp-converged epilogue: aggregate before touching HBM -------------------------------------------------------
@@ -521,14 +550,13 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         st->fkey[lane] = o.frag_key; st->fgene[lane] = o.agg_gene; st->fpeers[lane] = peers;   // each lane reads back its own slot only
 #if defined(RSQ_AB_NO_FRAGSET)
 #elif defined(RSQ_FRAG_PREFETCH_ONLY)
-        if (o.frag_key) asm volatile("prefetch.global.L2 [%0];" ::"l"(acc.frag_set + set_home(o.frag_key, acc.frag_cap)));
+        if (o.frag_key) prefetch_l2(acc.frag_set + set_home(o.frag_key, acc.frag_cap));
 #else
         // asynchronous 8-byte copy of the key's home slot into the lane's parking place (LDGSTS): by the next tile the warp
         // knows without any further global access whether the key is already there (the upper mate of a pair), the slot is
         // free (one CAS on a line that is in L2 by then) or taken by another key (rare: probe on)
-        if (o.frag_key)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&st->fval[lane])), "l"(acc.frag_set + set_home(o.frag_key, acc.frag_cap)) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (o.frag_key) home_fetch(&st->fval[lane], acc.frag_set + set_home(o.frag_key, acc.frag_cap));
+        home_commit();
 #endif
     }
     // +1 counters: lane k of the warp OWNS counters k and k+32 in registers for the whole persistent loop.  The 64-bit mask of
@@ -618,8 +646,6 @@ hot_path_kernel(const rsq_read* __restrict__ reads, const rsq_block* __restrict_
         if (s_cnt[k]) atomicAdd(&acc.counters[k], s_cnt[k]);
     if (threadIdx.x == 0 && s_bytes) atomicAdd(acc.algo_bytes, s_bytes);
 }
-
-#endif  // RSQ_CUDA_EMU
 
 // ---- annotation preprocessing -----------------------------------------------------------------------------------------
 // running max of exon end inside each contig (one thread per contig: a few hundred thousand elements, once per run)
@@ -1159,7 +1185,6 @@ __global__ void __launch_bounds__(256) expand_compact_kernel(const unsigned char
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------------------------------------------
-#ifndef RSQ_CUDA_EMU
 int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_reads, size_t n_blocks, const AnnView& ann, const BedView& bed,
                     const Accum& acc, const Params& prm, cudaStream_t stream) {
     if (!n_reads) return 0;
@@ -1184,8 +1209,6 @@ int launch_hot_path(const rsq_read* reads, const rsq_block* blocks, size_t n_rea
     RSQ_LAUNCH(kernels[which], grid, kHotThreads, 0, stream, reads, blocks, (uint32_t)n_reads, (uint32_t)n_blocks, ann, bed, acc, prm);
     return 1;
 }
-
-#endif  // RSQ_CUDA_EMU
 
 int launch_prefix_max(const int2* se, const uint32_t* off, uint32_t n_contigs, int32_t* pmax, cudaStream_t stream) {
     if (!n_contigs) return 0;

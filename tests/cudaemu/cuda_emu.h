@@ -32,6 +32,7 @@
 #undef __forceinline__
 #undef __launch_bounds__
 #undef __align__
+#undef __noinline__
 #define __global__
 #define __device__
 #define __host__
@@ -39,6 +40,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
+#define __noinline__
 
 namespace cuda_emu {
 
@@ -131,41 +133,67 @@ void launch(G grid, B block_threads, size_t smem, const std::function<void()>& b
 #define gridDim (::cuda_emu::tls().gdim)
 
 // ---- synchronisation and warp collectives ---------------------------------------------------------------------------------------
+// A collective over a mask of ONE lane is local (the hot kernel's opportunistic aggregation asks __activemask() for the lanes that
+// happen to be converged: here that is always just the caller — any subset is a correct answer).  Every other mask must be the
+// warp's live lanes, all of which take part.
 inline void __syncthreads() { ::cuda_emu::tls().block->bar.arrive_and_wait(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { ::cuda_emu::tls().warp->bar.arrive_and_wait(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline unsigned __activemask() { return 1u << ::cuda_emu::tls().lane; }
 
 namespace cuda_emu {
 template <class T> inline unsigned long long to_bits(T v) { unsigned long long b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &v, sizeof(T)); return b; }
 template <class T> inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
-// every live lane publishes `v`, then reads the slot of lane `src` (its own value when src is not a live lane)
-template <class T> inline T exchange(T v, int src) {
+inline bool solo(unsigned mask) { return (mask & (mask - 1u)) == 0u; }
+// every live lane publishes `v`; f(slots, live mask) computes the caller's result between the two warp barriers
+template <class T, class F> inline auto collective(T v, F f) {
     Tls& t = tls();
     t.warp->slot[t.lane] = to_bits(v);
     t.warp->bar.arrive_and_wait();
-    T r = v;
-    if (src >= 0 && src < 32 && (t.warp->live.load() >> src & 1u)) r = from_bits<T>(t.warp->slot[src]);
+    auto r = f(t.warp->slot, t.warp->live.load(), t.lane);
     t.warp->bar.arrive_and_wait();
     return r;
 }
+template <class T> inline T exchange(T v, int src) {
+    return collective(v, [&](const unsigned long long* slot, unsigned live, unsigned) {
+        return (src >= 0 && src < 32 && (live >> src & 1u)) ? from_bits<T>(slot[src]) : v; });
+}
 }  // namespace cuda_emu
-template <class T> inline T __shfl_sync(unsigned, T v, int src) { return ::cuda_emu::exchange(v, src & 31); }
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src) { return ::cuda_emu::solo(mask) ? v : ::cuda_emu::exchange(v, src & 31); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int d) { return ::cuda_emu::exchange(v, (int)(::cuda_emu::tls().lane ^ (unsigned)d)); }
 template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned d) {
     const int lane = (int)::cuda_emu::tls().lane;
     return ::cuda_emu::exchange(v, lane - (int)d >= 0 ? lane - (int)d : lane);
 }
-inline unsigned __ballot_sync(unsigned, int pred) {
-    ::cuda_emu::Tls& t = ::cuda_emu::tls();
-    t.warp->slot[t.lane] = pred ? 1ull : 0ull;
-    t.warp->bar.arrive_and_wait();
-    unsigned m = 0;
-    const unsigned live = t.warp->live.load();
-    for (int l = 0; l < 32; ++l) if ((live >> l & 1u) && t.warp->slot[l]) m |= 1u << l;
-    t.warp->bar.arrive_and_wait();
-    return m;
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+    if (::cuda_emu::solo(mask)) return pred ? mask : 0u;
+    return ::cuda_emu::collective(pred ? 1ull : 0ull, [](const unsigned long long* slot, unsigned live, unsigned) {
+        unsigned m = 0;
+        for (int l = 0; l < 32; ++l) if ((live >> l & 1u) && slot[l]) m |= 1u << l;
+        return m; });
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    if (::cuda_emu::solo(mask)) return mask;
+    return ::cuda_emu::collective(v, [](const unsigned long long* slot, unsigned live, unsigned lane) {
+        unsigned m = 0;
+        for (int l = 0; l < 32; ++l) if ((live >> l & 1u) && slot[l] == slot[lane]) m |= 1u << l;
+        return m; });
+}
+namespace cuda_emu {
+template <class T, class Op> inline T reduce(unsigned mask, T v, Op op) {
+    if (solo(mask)) return v;
+    return collective(v, [&](const unsigned long long* slot, unsigned live, unsigned lane) {
+        T r = from_bits<T>(slot[lane]);
+        bool first = true;
+        for (int l = 0; l < 32; ++l) if (live >> l & 1u) { const T x = from_bits<T>(slot[l]); r = first ? x : op(r, x); first = false; }
+        return r; });
+}
+}  // namespace cuda_emu
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return ::cuda_emu::reduce(mask, v, [](unsigned a, unsigned b) { return a + b; }); }
+inline int __reduce_add_sync(unsigned mask, int v) { return ::cuda_emu::reduce(mask, v, [](int a, int b) { return (int)((unsigned)a + (unsigned)b); }); }
+inline int __reduce_min_sync(unsigned mask, int v) { return ::cuda_emu::reduce(mask, v, [](int a, int b) { return a < b ? a : b; }); }
+inline int __reduce_max_sync(unsigned mask, int v) { return ::cuda_emu::reduce(mask, v, [](int a, int b) { return a > b ? a : b; }); }
 
 // ---- atomics ----------------------------------------------------------------------------------------------------------------------
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -194,6 +222,9 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
 using std::isinf;
 using std::isnan;
 using std::sqrt;
@@ -202,6 +233,43 @@ template <class T> inline T max(T a, T b) { return a < b ? b : a; }
 inline unsigned long long min(unsigned long long a, unsigned int b) { return a < b ? a : b; }
 inline unsigned int min(unsigned int a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
 
-// ---- the few runtime calls the launchers make ------------------------------------------------------------------------------------
-#define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
-#define cudaFuncSetAttribute(...) (cudaSuccess)
+// ---- the CUDA runtime calls of the library, synchronous on host memory --------------------------------------------------------------
+namespace cuda_emu {
+template <class T> inline cudaError_t Malloc(T** p, size_t n) { *p = static_cast<T*>(malloc(n ? n : 1)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t Free(void* p) { free(p); return cudaSuccess; }
+inline cudaError_t Memset(void* p, int v, size_t n) { if (n) memset(p, v, n); return cudaSuccess; }
+inline cudaError_t Memcpy(void* d, const void* s, size_t n) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t Ok() { return cudaSuccess; }
+inline cudaError_t StreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t EventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t ElapsedTime(float* ms) { *ms = 0.001f; return cudaSuccess; }
+inline cudaError_t DeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t One(int* v) { *v = 1; return cudaSuccess; }
+inline cudaError_t Zero(int* v) { *v = 0; return cudaSuccess; }
+}  // namespace cuda_emu
+#define cudaMalloc(p, n) ::cuda_emu::Malloc((p), (n))
+#define cudaMallocHost(p, n) ::cuda_emu::Malloc((p), (n))
+#define cudaFree(p) ::cuda_emu::Free((void*)(p))
+#define cudaFreeHost(p) ::cuda_emu::Free((void*)(p))
+#define cudaMemsetAsync(p, v, n, s) ::cuda_emu::Memset((p), (v), (n))
+#define cudaMemcpyAsync(d, s, n, kind, st) ::cuda_emu::Memcpy((d), (s), (n))
+#define cudaMemcpy(d, s, n, kind) ::cuda_emu::Memcpy((d), (s), (n))
+#define cudaStreamSynchronize(s) ::cuda_emu::Ok()
+#define cudaDeviceSynchronize() ::cuda_emu::Ok()
+#define cudaSetDevice(d) ::cuda_emu::Ok()
+#define cudaGetLastError() ::cuda_emu::Ok()
+#define cudaGetDeviceCount(n) ::cuda_emu::DeviceCount(n)
+#define cudaGetDevice(d) ::cuda_emu::Zero(d)
+#define cudaDeviceGetAttribute(v, attr, dev) ::cuda_emu::One(v)
+#define cudaOccupancyMaxActiveBlocksPerMultiprocessor(v, k, t, s) ::cuda_emu::One(v)
+#define cudaStreamCreateWithFlags(s, f) ::cuda_emu::StreamCreate(s)
+#define cudaStreamDestroy(s) ::cuda_emu::Ok()
+#define cudaStreamWaitEvent(s, e, f) ::cuda_emu::Ok()
+#define cudaEventCreate(e) ::cuda_emu::EventCreate(e)
+#define cudaEventCreateWithFlags(e, f) ::cuda_emu::EventCreate(e)
+#define cudaEventDestroy(e) ::cuda_emu::Ok()
+#define cudaEventRecord(e, s) ::cuda_emu::Ok()
+#define cudaEventSynchronize(e) ::cuda_emu::Ok()
+#define cudaEventElapsedTime(ms, a, b) ::cuda_emu::ElapsedTime(ms)
+#define cudaFuncSetAttribute(...) ::cuda_emu::Ok()
+#define cudaGetErrorString(e) "emulated runtime"

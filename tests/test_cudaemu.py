@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU = os.path.join(ROOT, "oracle", "_build", "libcudaemu.so")
+EMU = os.path.join(ROOT, "oracle", "_build", "librsq_emu.so")
 
 
 @pytest.fixture(scope="module")
