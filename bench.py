@@ -312,7 +312,10 @@ def run_ours(args):
 
     pre = None
     if world > 1 and not args.no_preflight:
-        pre = preflight(be, ann, sa, local_rank, rank, world, with_bed=True)
+        # the pre-flight always runs with the --bed sampler on (the ordered first-N cut across the partitions is part of the exchange)
+        ann_pf = ann if args.bed else build_annotation(wl, tempfile.mkdtemp(prefix="rsq_pf_"), with_bed=True)[1]
+        pre = preflight(be, ann_pf, sa, local_rank, rank, world, with_bed=True)
+        del ann_pf
 
     # this rank's coordinate slice of the genome (cut where no gene lies): it draws its records there and owns those genes
     region, owned = None, None
