@@ -202,6 +202,16 @@ void rsqh_set_fasta(const char* path) { g_fasta = path ? path : ""; }
 const rsq_reference* rsqh_reference_view(void* h) { Handle* H = static_cast<Handle*>(h); return H->ref.open ? &H->ref_view : nullptr; }
 
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
+// hashes of the read names "<prefix><id>" for id = first .. first + n - 1 (tools/name_hash_collisions.py)
+void rsqh_hash_qname_series(const char* prefix, uint64_t first, size_t n, uint64_t* out) {
+    char buf[96];
+    const size_t lp = strnlen(prefix, 64);
+    memcpy(buf, prefix, lp);
+    for (size_t i = 0; i < n; ++i) {
+        const int l = snprintf(buf + lp, sizeof(buf) - lp, "%llu", (unsigned long long)(first + i));
+        out[i] = hash_qname(buf, lp + (size_t)l);
+    }
+}
 
 // Writes the reference's output files from finalised results.
 int rsqh_write_reports(void* hv, const rsq_results* res, const double* exon_seq_or_null, const rsq_coverage_stats* cs, const rsqh_run_options* o,
