@@ -299,7 +299,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        import datetime
+        # a rank that falls out of step with the others must end the run within minutes, not hold the box until the job's limit
+        dist.init_process_group("nccl", device_id=torch.device(device), timeout=datetime.timedelta(seconds=300))
     wl = WORKLOADS[args.workload]
     total_target = args.records or wl["records"]
     strong = args.scaling == "strong" and world > 1
