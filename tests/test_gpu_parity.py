@@ -413,7 +413,7 @@ def test_full_size_properties_200m_records(libs):
     """BASELINE.json configs[2] at full size (200 M synthetic records, GENCODE-scale annotation), where the oracle cannot follow:
     size-independent properties instead — batching invariance (one submit vs three uneven ones: every table and every base of
     the coverage identical), idempotence after reset, the conservation laws of the counters, exon sums vs gene counts, and a
-    300 k-record slice from the middle of the stream against the oracle."""
+    300 k-record slices from four places of the stream against the oracle."""
     import torch
     from rnaseqc_b200 import synth
     api = libs["api"]
@@ -467,15 +467,15 @@ def test_full_size_properties_200m_records(libs):
     assert int(whole.gene_reads.sum()) >= c("HQ Exonic Reads") > 100_000_000
     # every (read, gene) assignment spreads exactly 1 over the exons of the gene (each floor loses < 2^-64)
     assert abs(float(whole.exon_counts().sum()) - float(whole.gene_reads.sum())) < 1e-3
-    # a slice from the middle of the stream against the oracle
-    a0 = n // 3
-    pr = np.frombuffer(rb[a0:a0 + 300_000].cpu().numpy().reshape(-1).data, dtype=api.READ_DTYPE).copy()
-    b0, b1 = int(pr["block_off"][0]), int(pr["block_off"][-1]) + int(pr["n_blocks"][-1])
-    pr["block_off"] -= np.uint32(b0)
-    pb = np.frombuffer(bb[b0:b1].cpu().numpy().reshape(-1).data, dtype=api.BLOCK_DTYPE).copy()
-    want, _ = _run(api, libs["oracle"], ann, pr, pb, api.make_config(max_records=len(pr)))
-    got, _ = _run(api, libs["product"], ann, pr, pb, api.make_config(max_records=len(pr)))
-    assert_results_equal(got, want, "300 k-record slice vs oracle")
+    # slices from four places of the stream (its head, one and two thirds in, its tail) against the oracle
+    for a0 in (0, n // 3, 2 * (n // 3), n - 300_000):
+        pr = np.frombuffer(rb[a0:a0 + 300_000].cpu().numpy().reshape(-1).data, dtype=api.READ_DTYPE).copy()
+        b0, b1 = int(pr["block_off"][0]), int(pr["block_off"][-1]) + int(pr["n_blocks"][-1])
+        pr["block_off"] -= np.uint32(b0)
+        pb = np.frombuffer(bb[b0:b1].cpu().numpy().reshape(-1).data, dtype=api.BLOCK_DTYPE).copy()
+        want, _ = _run(api, libs["oracle"], ann, pr, pb, api.make_config(max_records=len(pr)))
+        got, _ = _run(api, libs["product"], ann, pr, pb, api.make_config(max_records=len(pr)))
+        assert_results_equal(got, want, f"300 k-record slice at record {a0} vs oracle")
 
 
 def test_product_cli_reads_cram_like_the_reference(libs, tmp_path):
