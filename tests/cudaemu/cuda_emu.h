@@ -94,10 +94,15 @@ inline unsigned to_dim(unsigned long v) { return (unsigned)v; }
 inline unsigned to_dim(unsigned long long v) { return (unsigned)v; }
 inline unsigned to_dim(long v) { return (unsigned)v; }
 
+inline std::mutex& kernel_mutex() { static std::mutex m; return m; }
+
 template <class G, class B>
 void launch(G grid, B block_threads, size_t smem, const std::function<void()>& body) {
     const unsigned n_blocks = to_dim(grid), n_threads = to_dim(block_threads);
     if (!n_blocks || !n_threads) return;
+    // one kernel at a time in the whole process: __shared__ variables are statics here, so launches from several host threads
+    // (one context per GPU in the multi-lane CLI) must not overlap
+    std::lock_guard<std::mutex> only(kernel_mutex());
     Block blk;
     blk.warps = std::vector<Warp>((n_threads + 31) / 32);
     blk.dyn_smem.assign(smem + 16, 0);
@@ -243,7 +248,7 @@ inline cudaError_t Ok() { return cudaSuccess; }
 inline cudaError_t StreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t EventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t ElapsedTime(float* ms) { *ms = 0.001f; return cudaSuccess; }
-inline cudaError_t DeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t DeviceCount(int* n) { *n = 64; return cudaSuccess; }
 inline cudaError_t One(int* v) { *v = 1; return cudaSuccess; }
 inline cudaError_t Zero(int* v) { *v = 0; return cudaSuccess; }
 }  // namespace cuda_emu

@@ -36,6 +36,20 @@ def test_multi_lane_cli_fasta_and_stranded(libs, tmp_path):
     _run_and_compare(libs["oracle_cli"], d, flags, ["--gpus", "3", "--records-per-gpu", "2500", "--batch-records", "700"], 9)
 
 
+def test_multi_lane_product_cli_in_emulation(libs, tmp_path, monkeypatch):
+    """the PRODUCT's side of a partitioned run — rsq_set_partition, the exchange packers with the kept samples at their global ranks,
+    the ownership-masked statistics kernel — under the same CLI, through the CPU emulation of the CUDA library (tests/cudaemu; its
+    exchange buffers are host memory, so they travel like the oracle's)"""
+    emu_cli = os.path.join(os.path.dirname(libs["oracle_cli"]), "rnaseqc_emu")
+    if not os.path.exists(emu_cli):
+        pytest.skip("rnaseqc_emu is not built")
+    monkeypatch.setenv("RSQ_HOST_EXCHANGE", "1")
+    d = unpack_case("kat_odd", tmp_path)
+    flags = ["--coverage", "--coverage-mask", "0", "--gene-length", "50", "--bed", os.path.join(d, "a.bed"), "--fragment-samples", "60"]
+    lanes = _run_and_compare(emu_cli, d, flags, ["--gpus", "2", "--records-per-gpu", "150", "--batch-records", "128"], 8)
+    assert sum(int(l.split()[2]) > 0 for l in lanes) >= 2, lanes
+
+
 def test_multi_lane_cli_refuses_unsorted_input(libs, tmp_path):
     d = unpack_case("synth_small", tmp_path)
     lines = open(os.path.join(d, "a.sam")).read().splitlines()
