@@ -46,7 +46,7 @@ def test_multi_lane_product_cli_in_emulation(libs, tmp_path, monkeypatch):
     monkeypatch.setenv("RSQ_HOST_EXCHANGE", "1")
     d = unpack_case("kat_odd", tmp_path)
     flags = ["--coverage", "--coverage-mask", "0", "--gene-length", "50", "--bed", os.path.join(d, "a.bed"), "--fragment-samples", "60"]
-    lanes = _run_and_compare(emu_cli, d, flags, ["--gpus", "2", "--records-per-gpu", "150", "--batch-records", "128"], 8)
+    lanes = _run_and_compare(emu_cli, d, flags, ["--gpus", "2", "--records-per-gpu", "150", "--batch-records", "64"], 8)
     assert sum(int(l.split()[2]) > 0 for l in lanes) >= 2, lanes
 
 
