@@ -47,7 +47,9 @@ def libs():
         "host": os.path.join(ROOT, need[1]),
         "cli": os.path.join(ROOT, "oracle/_build/rnaseqc_emu" if EMULATE else need[2]),
         "oracle": os.path.join(ROOT, need[3]),
-        "oracle_cli": os.path.join(ROOT, need[4]),
+        # RSQ_EMULATE_CLI=1: the CLI-level reference tests (goldens, live-reference fuzz) run the PRODUCT sources in emulation instead of
+        # the oracle harness: the strongest check of the device code that is possible without a device
+        "oracle_cli": os.path.join(ROOT, "oracle/_build/rnaseqc_emu" if os.environ.get("RSQ_EMULATE_CLI") == "1" else need[4]),
         "ref_cli": os.path.join(ROOT, "oracle/_ref/rnaseqc"),
         "api": api,
     }

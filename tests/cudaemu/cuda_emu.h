@@ -1,16 +1,21 @@
-// cuda_emu.h — TEST INFRASTRUCTURE: runs CUDA kernels on the CPU, one OS thread per CUDA thread of a block, blocks one after another.
+// cuda_emu.h — TEST INFRASTRUCTURE: runs CUDA kernels on the CPU, one OS thread per CUDA thread of a block, blocks one after another,
+// one kernel at a time.
 //
-// The kernels of rnaseqc_b200/csrc that have no CPU twin (the mate-map stages, the per-gene coverage statistics, the wire-format
-// expansion, the exchange packers, the scans) are compiled from their own sources with RSQ_CUDA_EMU defined and run through this
-// header, so that the CPU test suite exercises the very code the GPU runs — barriers, warp shuffles and atomics included:
+// rnaseqc_b200/csrc/rsq_kernels.cu, rsq_covstats.cu and rsq_capi.cu are compiled UNCHANGED with RSQ_CUDA_EMU defined (emu_*.cpp) into
+// oracle/_build/librsq_emu.so — the product's whole C-ABI on the CPU — so that the CPU test suite exercises the very code the GPU runs,
+// barriers, warp collectives and atomics included:
 //   __syncthreads()            a barrier over the block's live threads (threads that returned have left it, as on the device)
-//   __shfl_*_sync, __ballot_sync, __syncwarp
-//                              exchange through a per-warp slot array between two warp barriers; every live lane of the warp
-//                              must take part (the kernels emulated here only use full masks on converged warps)
+//   __shfl_*_sync, __ballot_sync, __any_sync, __match_any_sync, __reduce_*_sync, __syncwarp
+//                              exchange through a per-warp slot array between two warp barriers; every live lane of the warp takes part.
+//                              A collective over a ONE-lane mask is local, and __activemask() answers "just me": the hot kernel's
+//                              opportunistic aggregation (match.any over whatever lanes happen to be converged) accepts any subset
 //   atomicAdd / Max / Min / CAS / Or / Sub   real atomics (the threads of a block run concurrently)
-//   __shared__                 static storage (one block at a time), dynamic shared memory through RSQ_DYNAMIC_SMEM
-// Not emulated: inline PTX (TMA, mbarrier, cp.async), match.any / redux, occupancy queries — the hot kernel itself stays out (its
-// per-record logic has its own host emulation, tests/hostcore).
+//   __shared__                 static storage (one block, one kernel at a time), dynamic shared memory through RSQ_DYNAMIC_SMEM
+//   cudaMalloc, cudaMemcpyAsync, streams, events, ...   synchronous stand-ins on host memory ("device" pointers are host pointers)
+// The hot kernel's inline PTX (TMA bulk copy + mbarrier, cp.async, ld.global.nc, prefetch) sits behind six helpers in rsq_kernels.cu
+// that have an emulation body (memcpy by the issuing lane + warp barrier, plain loads, nothing).
+// What this cannot show: races between CTAs (blocks run one after another), anything that depends on the device's memory model
+// (everything here is sequentially consistent), performance.
 #pragma once
 #include <cuda_runtime.h>      // vector types, cudaStream_t (host-side declarations only; nothing of the runtime is called)
 
