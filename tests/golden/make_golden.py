@@ -71,6 +71,20 @@ def make_synth_small():
     os.remove(sam)
 
 
+def make_bam_small():
+    """A BAM of several ingest jobs (the multi-threaded reader cuts the decompressed stream into ~4 MB jobs, most of which start inside
+    a record): 60 k seeded records, --coverage --bed; the reference reads the same file."""
+    from rnaseqc_b200 import synth
+    d = os.path.join(HERE, "bam_small")
+    os.makedirs(d, exist_ok=True)
+    ann = synth.make_annotation(seed=61, n_genes=120, contig_names=["chr1", "chr2", "chrM"], contig_lens=[14_000_000, 9_000_000, 16569])
+    synth.write_gtf(ann, os.path.join(d, "a.gtf"))
+    synth.write_bed(ann, os.path.join(d, "a.bed"), min_len=400)
+    reads = synth.simulate_reads(ann, 60000, seed=62, dup_frac=0.0)
+    synth.write_bam(ann, reads, os.path.join(d, "a.bam"), level=9)
+    run_ref("a.gtf", "a.bam", os.path.join("expected", "coverage_bed"), ["--coverage", "--bed", "a.bed"], d)
+
+
 def make_synth_fasta():
     """--fasta: fragment GC-content sampler, exon GC column, gc_content.tsv (src/Expression.cpp:459-476, src/RNASeQC.cpp:632-674).
     The FASTA lists its contigs in another order than the GTF (that order seeds the chromosome ids, src/Fasta.cpp:91-93), lacks
@@ -416,4 +430,5 @@ if __name__ == "__main__":
     make_kat_legacy()
     make_synth_fasta()
     make_kat_odd()
+    make_bam_small()
     print("golden fixtures written under", HERE)

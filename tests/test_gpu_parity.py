@@ -478,6 +478,15 @@ def test_full_size_properties_200m_records(libs):
         assert_results_equal(got, want, f"300 k-record slice at record {a0} vs oracle")
 
 
+@pytest.mark.parametrize("mode", ["sequential", "threads", "threads_no_speculation", "threads_no_digest"])
+def test_product_cli_reads_a_multi_job_bam_like_the_reference(libs, tmp_path, mode, monkeypatch):
+    """BAM -> report files through the PRODUCT CLI (multi-threaded ingest with and without speculated framing / job digests, wire-format
+    packers, CUDA path) against the reference binary's outputs for the same BAM (tests/golden/bam_small: several ~4 MB ingest jobs)"""
+    from test_oracle_golden import run_bam_small
+    identical = run_bam_small(libs["cli"], tmp_path, mode, monkeypatch)
+    assert {"a.bam.gene_reads.gct", "a.bam.gene_fragments.gct", "a.bam.fragmentSizes.txt", "a.bam.exon_reads.gct"} <= identical, identical
+
+
 def test_product_cli_reads_cram_like_the_reference(libs, tmp_path):
     """CRAM input through the product CLI (host-side reader, tests/test_cram.py has its CPU twins) against the reference's outputs."""
     d = unpack_case("cram_small", tmp_path)
