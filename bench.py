@@ -395,6 +395,13 @@ def run_ours(args):
     ms_dev = ev0.elapsed_time(ev1)
     launches = ctx.launch_count() - l0
     ref_snap = snapshot(res, res.cov_stats)       # the pinned result buffers are reused by the next finalize
+    cs = res.cov_stats
+    n_cov_genes = len(cs["gene_mean"])
+    sanity = {"mapped_reads": res.counter("Mapped Reads"), "exonic_reads": res.counter("Exonic Reads"),
+              "gene_reads_sum": int(res.gene_reads.sum()), "device_ms_events": ms_dev / args.steps,
+              "genes_with_coverage_stats": int((cs["gene_mean"] > 0).sum()),
+              "fragment_samples_taken": int(res.fragment_samples_taken),
+              "genes_in_3prime_bias": int(((cs["five_end"] + cs["three_end"]) > 0).sum())}
     # the dominant kernel's own time (CUDA events recorded by the library around the hot-path launches of one step)
     ctx.reset(); ctx.submit_device(rb.data_ptr(), n_reads, bb.data_ptr(), n_blocks); ctx.sync()
     hot_ms = ctx.kernel_time_ms()
@@ -407,6 +414,38 @@ def run_ours(args):
         ms_step = float(t.item())
     total_records = n_reads if world == 1 else int(_allsum(n_reads, device))
     value = total_records / (ms_step * 1e-3)
+
+    # ---------------- BASELINE configs[3] beside the weak line: the workload's records SPLIT over the GPUs -------------------
+    # (the driver launches `bench.py --gpus N` without flags; `--scaling strong` makes this the headline instead)
+    strong_leg = None
+    if world > 1 and not strong and not args.no_strong_leg:
+        n_s = (total_target + world - 1) // world
+        rb2, bb2 = generate_on_device(sa, ann, n_s, device, region, rank, seed=SEED + 7)
+        n2, nb2 = rb2.shape[0], bb2.shape[0]
+
+        def step_strong():
+            ctx.reset()
+            ctx.submit_device(rb2.data_ptr(), n2, bb2.data_ptr(), nb2)
+            return finish()
+        for _ in range(3):
+            step_strong()
+        barrier()
+        t_s = time.perf_counter()
+        for _ in range(args.steps):
+            step_strong()
+        barrier()
+        dt_s = (time.perf_counter() - t_s) / args.steps
+        ctx.reset(); ctx.submit_device(rb2.data_ptr(), n2, bb2.data_ptr(), nb2); ctx.sync()
+        hot_s = ctx.kernel_time_ms()
+        finish()
+        t = torch.tensor([dt_s, hot_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_s = int(_allsum(n2, device))
+        strong_leg = {"scaling": "strong", "workload": "BASELINE configs[3]: the workload's records split over the GPUs by coordinate",
+                      "records_total": total_s, "records_per_gpu": int(n2), "steps": args.steps, "ms_per_step": float(t[0].item()) * 1e3,
+                      "value": total_s / float(t[0].item()), "unit": "reads/s", "slowest_hot_kernel_ms": float(t[1].item())}
+        del rb2, bb2
+        torch.cuda.empty_cache()
 
     # ---------------- end to end from pinned host buffers ------------------------------------------------------------
     e2e = None
@@ -504,7 +543,7 @@ def run_ours(args):
                 assert not bad, f"e2e ({fmt}) != resident in {bad}"
                 return dt, local
 
-            d2h = 8 * (api.RSQ_N_COUNTERS + 3 * ann.n_genes + 2 * ann.n_exons) + 8 * (5 * len(res.cov_stats["gene_mean"]) + ann.n_exons)
+            d2h = 8 * (api.RSQ_N_COUNTERS + 3 * ann.n_genes + 2 * ann.n_exons) + 8 * (5 * n_cov_genes + ann.n_exons)
             fmt = "compact" if compact else ("packed" if packed else "plain")
             wire = {"compact": lambda: int(sum(nb_ for _, nb_ in compact)),
                     "packed": lambda: int(32 * n_reads + 8 * sum(p[3] for p in packed)),
@@ -568,7 +607,6 @@ def run_ours(args):
         traffic, traffic_src = tj["dram_bytes_per_record"] * n_reads, tj["source"]
     achieved = algo_bytes / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
     if rank == 0:
-        cs = res.cov_stats
         out = {
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm_done, "ms_per_step": ms_step, "higher_is_better": True,
@@ -586,12 +624,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
                          "hot_kernel_ms_per_step": hot_ms, "kernel": "hot_path_kernel (rank 0; every rank's time is in per_rank)"},
-            "cpu_baseline": cpu_baseline, "e2e_cli": e2e_cli, "per_rank": per_rank, "preflight": pre,
-            "sanity": {"mapped_reads": res.counter("Mapped Reads"), "exonic_reads": res.counter("Exonic Reads"),
-                       "gene_reads_sum": int(res.gene_reads.sum()), "device_ms_events": ms_dev / args.steps,
-                       "genes_with_coverage_stats": int((cs["gene_mean"] > 0).sum()),
-                       "fragment_samples_taken": int(res.fragment_samples_taken),
-                       "genes_in_3prime_bias": int(((cs["five_end"] + cs["three_end"]) > 0).sum())},
+            "cpu_baseline": cpu_baseline, "e2e_cli": e2e_cli, "per_rank": per_rank, "preflight": pre, "strong_scaling": strong_leg,
+            "sanity": sanity,
         }
         emit(out)
     ctx.close()
@@ -739,6 +773,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preflight", action="store_true")
+    ap.add_argument("--no-strong-leg", action="store_true", help="N > 1, weak scaling: skip the extra configs[3] measurement")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's host cores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
