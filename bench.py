@@ -415,6 +415,26 @@ def run_ours(args):
     total_records = n_reads if world == 1 else int(_allsum(n_reads, device))
     value = total_records / (ms_step * 1e-3)
 
+    # ---------------- the same step over a region of >= --sustain-s seconds (the K steps above are 14 ms each) -----------------
+    sustained = None
+    if ms_step * args.steps < args.sustain_s * 1e3:
+        m_steps = int(min(5000, args.sustain_s * 1e3 / ms_step + 1))      # from the max-over-ranks time: the same count on every rank
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        t_s = time.perf_counter()
+        for _ in range(m_steps):
+            step_resident()
+        s1.record(stream)
+        barrier()
+        t_s = time.perf_counter() - t_s
+        ms_s = max(s0.elapsed_time(s1), t_s * 1e3) / m_steps
+        if world > 1:
+            t = torch.tensor([ms_s], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_s = float(t.item())
+        sustained = {"steps": m_steps, "seconds": ms_s * m_steps / 1e3, "ms_per_step": ms_s, "value": total_records / (ms_s * 1e-3), "unit": "reads/s"}
+
     # ---------------- BASELINE configs[3] beside the weak line: the workload's records SPLIT over the GPUs -------------------
     # (the driver launches `bench.py --gpus N` without flags; `--scaling strong` makes this the headline instead)
     strong_leg = None
@@ -625,7 +645,7 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": int(algo_bytes),
                          "hot_kernel_ms_per_step": hot_ms, "kernel": "hot_path_kernel (rank 0; every rank's time is in per_rank)"},
             "cpu_baseline": cpu_baseline, "e2e_cli": e2e_cli, "per_rank": per_rank, "preflight": pre, "strong_scaling": strong_leg,
-            "sanity": sanity,
+            "sanity": sanity, "sustained": sustained,
         }
         emit(out)
     ctx.close()
@@ -700,7 +720,16 @@ def run_reference(args):
         bed = os.path.join(tmpdir, "bench.bed")
         synth.write_bed(sa, bed, min_len=1000)
         flags += ["--bed", bed]
-    n_s = args.cpu_sample
+    # every step is one run of the reference binary: ~6 s of fixed cost (its GTF parse, the report files of 54 k genes) + the
+    # sample at ~0.3 M records/s.  The sample shrinks with the number of steps asked for, so that the whole arm stays within
+    # --ref-budget-s whatever --steps / --warmup the caller chose.
+    asked = (args.steps, args.warmup)
+    max_runs = max(2, int(args.ref_budget_s / 7.0))          # even the smallest sample costs ~7 s per run
+    if args.warmup + args.steps > max_runs:
+        args.warmup = min(args.warmup, 1)
+        args.steps = max(1, min(args.steps, max_runs - args.warmup))
+    runs = max(args.warmup + args.steps, 1)
+    n_s = int(min(args.cpu_sample, max(300_000, (args.ref_budget_s / runs - 6.0) * 0.3e6)))
     sr = synth.simulate_reads(sa, n_s, seed=SEED, device="cpu", dup_frac=0.0)   # no duplicates: keeps the 1e9-iteration
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "rnaseqc")                  # library-complexity scan (outside the path) out
     times = []
@@ -741,7 +770,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": wl["label"], "sample_records": sr.n, "gtf_parse_seconds_subtracted": t_gtf, "flags": flags[:1] + (["--bed"] if args.bed else []),
+           "config": {"workload": wl["label"], "sample_records": sr.n, "steps_asked": asked[0], "warmup_asked": asked[1], "wall_budget_seconds": args.ref_budget_s,
+                      "gtf_parse_seconds_subtracted": t_gtf, "flags": flags[:1] + (["--bed"] if args.bed else []),
                       "includes": "BGZF inflate + BAM record parse (about 10 % of the reference's time, SURVEY.md §6) — the GPU arm's e2e starts from decoded, packed records; bench.py's e2e_cli leg is the BAM-to-files comparison"},
            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -761,6 +791,10 @@ def main():
     ap.add_argument("--records", type=int, default=0, help="override the workload's record count (smoke runs)")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000,
                     help="records per step of `--impl reference` (the reference binary does ~0.2-0.4 M records/s: ~10 s)")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="`--impl reference`: wall-clock budget of all its runs together (sizes the sample)")
+    ap.add_argument("--sustain-s", type=float, default=2.0,
+                    help="when the K timed steps take less than this, a second region of as many steps as fill it is timed the same way (reported as `sustained`)")
+    ap.add_argument("--watchdog-s", type=float, default=720.0, help="dump all stacks and exit 1 when the run takes longer than this (0 = off)")
     ap.add_argument("--port-sample", type=int, default=30_000_000,
                     help="records of the cpu_baseline leg (the oracle port does ~3 M records/s on one core: ~10 s)")
     ap.add_argument("--e2e-chunk", type=int, default=8_000_000)
@@ -777,8 +811,11 @@ def main():
     ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's host cores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    if args.watchdog_s > 0:
+        # the library's own NCCL calls have no timeout: a rank that falls out of step would hold the box until the job's limit
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
     if args.impl == "reference":
-        args.steps = min(args.steps, 3) if args.steps == 150 else args.steps     # a step is ~10 s of one host core
         run_reference(args)
     else:
         run_ours(args)

@@ -187,21 +187,18 @@ int zero_accumulators(Ctx* c) {
     CU_TRY(cudaMemsetAsync(a.algo_bytes, 0, 8, c->stream));
     CU_TRY(cudaMemsetAsync(a.error_flag, 0, 4, c->stream));
     if (c->have_bed && c->cfg.fragment_samples) {
+        // keys and pending mates only: the round scratch (pair_first / pair_second) holds tags of earlier launches, and the launch
+        // number keeps growing across resets, so every later tag beats them (run_batch)
         CU_TRY(cudaMemsetAsync(a.pair_keys, 0, 8ull * c->pair_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(a.pair_first, 0, 8ull * c->pair_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(a.pair_second, 0, 8ull * c->pair_cap, c->stream));
         CU_TRY(cudaMemsetAsync(a.pair_payload, 0xff, 8ull * c->pair_cap, c->stream));      // kMateEmpty
         CU_TRY(cudaMemsetAsync(a.sample_count, 0, 8, c->stream));
     }
     if (c->have_ref) {
         CU_TRY(cudaMemsetAsync(a.gc_keys, 0, 8ull * c->gc_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(a.gc_first, 0, 8ull * c->gc_cap, c->stream));
-        CU_TRY(cudaMemsetAsync(a.gc_second, 0, 8ull * c->gc_cap, c->stream));
         CU_TRY(cudaMemsetAsync(a.gc_payload, 0xff, 8ull * c->gc_cap, c->stream));
         CU_TRY(cudaMemsetAsync(a.gc_hist, 0, 8 * 100, c->stream));
     }
     c->records_submitted = 0;
-    c->mate_launches = 0;
     c->mate_known[0] = c->mate_known[1] = c->mate_pending[0] = c->mate_pending[1] = 0;
     if (a.mate_totals) CU_TRY(cudaMemsetAsync(a.mate_totals, 0, 16, c->stream));
     c->found_valid = false;
@@ -285,8 +282,8 @@ int reserve_mate_capacity(Ctx* c, int which, size_t n) {
     unsigned long long exact = 0;
     CU_TRY(cudaMemcpy(&exact, c->acc.mate_totals + which, 8, cudaMemcpyDeviceToHost));
     known = exact; pending = n;
-    if (exact + n <= cap / 4 * 3) return RSQ_OK;
-    const unsigned long long new_cap = next_pow2((exact + n) / 3 * 4 + 4);
+    if (exact + 2 * n <= cap / 4 * 3) return RSQ_OK;                   // room for this launch and the next without another look
+    const unsigned long long new_cap = next_pow2((exact + 4 * n) / 3 * 4 + 4);   // ... and after a growth for four
     unsigned long long *nk = nullptr, *nf = nullptr, *ns = nullptr, *np = nullptr;
     CU_TRY(cudaMalloc(&nk, 8ull * new_cap));
     CU_TRY(cudaMalloc(&nf, 8ull * new_cap));
@@ -372,7 +369,12 @@ int run_batch(Ctx* c, const rsq_read* d_reads, size_t n_reads, const rsq_block* 
         if ((rc = reserve_mate_capacity(c, 0, n)) != RSQ_OK || (rc = reserve_mate_capacity(c, 1, n)) != RSQ_OK) return rc;
         prm.record_base = c->records_submitted + base;
         if (prm.bed_enabled || prm.gc_enabled) {
-            if (++c->mate_launches >= (1ull << 23)) { c->err = "too many launches for the mate-map round tags"; return RSQ_ERR_CAPACITY; }
+            if (++c->mate_launches >= (1ull << 23)) {   // the round tags have run out of launch numbers (they survive resets): start over
+                Accum& a = c->acc;
+                if (a.pair_first) { CU_TRY(cudaMemsetAsync(a.pair_first, 0, 8ull * c->pair_cap, c->stream)); CU_TRY(cudaMemsetAsync(a.pair_second, 0, 8ull * c->pair_cap, c->stream)); }
+                if (a.gc_first) { CU_TRY(cudaMemsetAsync(a.gc_first, 0, 8ull * c->gc_cap, c->stream)); CU_TRY(cudaMemsetAsync(a.gc_second, 0, 8ull * c->gc_cap, c->stream)); }
+                c->mate_launches = 1;
+            }
             prm.mate_round = c->mate_launches << 17;
             CU_TRY(cudaMemsetAsync(c->acc.mate_left_count, 0, 8, c->stream));
         }
