@@ -11,7 +11,7 @@ BINDIR   := rnaseqc_b200/bin
 OBJDIR   := build
 ODIR     := oracle/_build
 
-HOST_SRCS := annotation.cpp alnreader.cpp cramreader.cpp bamparallel.cpp fasta.cpp report.cpp pipeline.cpp
+HOST_SRCS := annotation.cpp alnreader.cpp cramreader.cpp bamparallel.cpp fastinflate.cpp fasta.cpp report.cpp pipeline.cpp
 HOST_OBJS := $(addprefix $(OBJDIR)/host/,$(HOST_SRCS:.cpp=.o))
 
 all: $(LIBDIR)/librsq_b200.so $(LIBDIR)/librsq_host.so $(BINDIR)/rnaseqc

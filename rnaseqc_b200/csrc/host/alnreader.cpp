@@ -1,5 +1,6 @@
 // alnreader.cpp — SAM text and BAM (BGZF) readers + record conversion (see alnreader.h).
 #include "alnreader.h"
+#include "fastinflate.h"
 
 #include <zlib.h>
 
@@ -198,6 +199,7 @@ private:
         out_.resize(isize);
         off_ = 0;
         if (isize == 0) return true;  // empty block (EOF marker): keep going
+        if (!std::getenv("RSQ_INGEST_ZLIB") && fast_inflate(in_.data(), cdata, out_.data(), isize)) return true;   // fastinflate.h; zlib decides the rest
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) throw HostError(-1, "zlib init failed");

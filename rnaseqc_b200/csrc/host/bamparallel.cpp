@@ -17,6 +17,7 @@
 //   consumer      : next_batch(): takes converted jobs in file order, runs Decoder::observe (readLength, contig-drop
 //                   state, unsorted warning: src/RNASeQC.cpp:275-278,346-356) and appends to the caller's batch
 #include "bamparallel.h"
+#include "fastinflate.h"
 
 #include <zlib.h>
 
@@ -77,6 +78,9 @@ struct ThreadInflater {
 
 void inflate_block(const uint8_t* src, size_t n, uint8_t* dst, size_t isize) {
     if (!isize) return;
+    // the whole-buffer decoder first (fastinflate.h); whatever it refuses goes to zlib, which inflates it or reports the error
+    static const bool use_fast = !std::getenv("RSQ_INGEST_ZLIB");
+    if (use_fast && fast_inflate(src, n, dst, isize)) return;
     thread_local ThreadInflater ti;
     if (!ti.ready) {
         memset(&ti.zs, 0, sizeof(ti.zs));
@@ -200,8 +204,8 @@ ParallelBamDecoder::~ParallelBamDecoder() {
     if (fp_) std::fclose(fp_);
     g_last_hits = n_chain_hits_; g_last_misses = n_chain_misses_; g_last_summarised = n_runs_summarised_;
     if (std::getenv("RSQ_INGEST_STATS"))
-        std::fprintf(stderr, "ingest busy seconds: reader %.3f, frame %.3f, inflate %.3f + convert %.3f over %d workers, consumer %.3f (+ %.3f waiting); jobs framed on the speculated chain %llu, by the sequential hop %llu; jobs observed through their digest %llu\n",
-                     t_reader_, t_frame_, t_inflate_, t_convert_, n_threads_, t_consumer_, t_consumer_wait_,
+        std::fprintf(stderr, "ingest busy seconds: reader %.3f, frame %.3f, inflate %.3f + convert on the speculated chain %.3f + convert after framing %.3f over %d workers, consumer %.3f (+ %.3f waiting); jobs framed on the speculated chain %llu, by the sequential hop %llu; jobs observed through their digest %llu\n",
+                     t_reader_, t_frame_, t_inflate_, t_speculate_, t_convert_, n_threads_, t_consumer_, t_consumer_wait_,
                      (unsigned long long)n_chain_hits_, (unsigned long long)n_chain_misses_, (unsigned long long)n_runs_summarised_);
 }
 
@@ -345,6 +349,7 @@ void ParallelBamDecoder::worker_loop() {
         lk.unlock();
         const auto t_stage = clk::now();
         bool framed_by_chain = false;
+        double dt_spec = 0.0;
         try {
             if (what == 3) {
                 if (todo->out.size() < kHeadroom + todo->data_len + 16) todo->out.resize(kHeadroom + todo->data_len + 16);
@@ -353,7 +358,7 @@ void ParallelBamDecoder::worker_loop() {
                     inflate_block(todo->comp.data() + todo->c_off[b], todo->c_len[b], todo->out.data() + o, todo->u_len[b]);
                     o += todo->u_len[b];
                 }
-                if (speculate_) speculate(*todo);
+                if (speculate_) { const auto t_spec = clk::now(); speculate(*todo); dt_spec = since(t_spec); }
             } else if (what == 1) {
                 // frame: [carry | data] must be contiguous; then hop over whole records
                 uint8_t* base = todo->out.data();
@@ -408,7 +413,8 @@ void ParallelBamDecoder::worker_loop() {
         }
         const double dt_stage = since(t_stage);
         lk.lock();
-        (what == 3 ? t_inflate_ : what == 1 ? t_frame_ : t_convert_) += dt_stage;
+        (what == 3 ? t_inflate_ : what == 1 ? t_frame_ : t_convert_) += dt_stage - dt_spec;
+        t_speculate_ += dt_spec;
         if (!todo->error.empty()) {
             // a failed job surfaces at the consumer when its turn comes; framing moves past it so earlier records still flow
             if (todo->id == next_frame_id_) ++next_frame_id_;

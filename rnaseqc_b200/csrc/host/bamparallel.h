@@ -72,7 +72,7 @@ private:
     bool speculate_ = true;            // RSQ_INGEST_NO_SPECULATION=1: the sequential hop for every job (A/B, tests)
     bool summarise_ = true;            // RSQ_INGEST_NO_SUMMARY=1: Decoder::observe per record on the consumer thread (A/B, tests)
     uint64_t n_chain_hits_ = 0, n_chain_misses_ = 0, n_runs_summarised_ = 0;
-    double t_reader_ = 0, t_frame_ = 0, t_inflate_ = 0, t_convert_ = 0, t_consumer_ = 0, t_consumer_wait_ = 0;
+    double t_reader_ = 0, t_frame_ = 0, t_inflate_ = 0, t_speculate_ = 0, t_convert_ = 0, t_consumer_ = 0, t_consumer_wait_ = 0;
 };
 
 }  // namespace rsqh

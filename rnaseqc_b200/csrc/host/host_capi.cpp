@@ -7,6 +7,7 @@
 
 #include "alnreader.h"
 #include "bamparallel.h"
+#include "fastinflate.h"
 #include "annotation.h"
 #include "fasta.h"
 #include "pipeline.h"
@@ -202,6 +203,8 @@ void rsqh_set_fasta(const char* path) { g_fasta = path ? path : ""; }
 const rsq_reference* rsqh_reference_view(void* h) { Handle* H = static_cast<Handle*>(h); return H->ref.open ? &H->ref_view : nullptr; }
 
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
+// the ingest workers' whole-buffer DEFLATE decoder (fastinflate.h): 1 = inflated exactly out_len bytes, 0 = refused (callers fall back to zlib)
+int rsqh_fast_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) { return rsqh::fast_inflate(in, in_len, out, out_len) ? 1 : 0; }
 // hashes of the read names "<prefix><id>" for id = first .. first + n - 1 (tools/name_hash_collisions.py)
 void rsqh_hash_qname_series(const char* prefix, uint64_t first, size_t n, uint64_t* out) {
     char buf[96];
