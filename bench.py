@@ -688,7 +688,7 @@ def run_cli_leg(sa, gtf, tmpdir, n_records, device):
                     pass
     out.update(seconds=best[0], records_per_s=sr.n / best[0], stages=stages,
                bam_loop_records_per_s=(sr.n / stages["bam_loop_s"]) if stages.get("bam_loop_s") else None,
-               ingest_stats=[l for l in best[2].splitlines() if l.startswith("[ingest]")][-12:])
+               ingest_stats=[l for l in best[2].splitlines() if l.startswith("ingest busy seconds")][-4:])
     return out
 
 

@@ -418,6 +418,11 @@ void Decoder::convert(const RawAln& a, std::vector<rsq_read>& reads, std::vector
 
 // Pure conversion of one raw BAM record (no RawAln intermediate): same field semantics as convert(RawAln).
 void Decoder::convert_bam_bytes(const uint8_t* b, size_t n, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid_out) const {
+    convert_bam_record(opt_, (int)tid_to_contig_.size(), b, n, r, blocks, tid_out);
+    bind_contig(r, tid_out);
+}
+
+void Decoder::convert_bam_record(const DecodeOptions& opt_, int n_refs, const uint8_t* b, size_t n, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid_out) {
     if (n < 32) throw HostError(-1, "truncated BAM record");
     auto i32 = [&](size_t o) { int32_t v; memcpy(&v, b + o, 4); return v; };
     auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, b + o, 2); return v; };
@@ -507,12 +512,10 @@ void Decoder::convert_bam_bytes(const uint8_t* b, size_t n, rsq_read& r, std::ve
         }
     }
     if (tid != mtid) r.aux |= RSQ_AUX_MATE_OTHER_CONTIG;
-    const int n_refs = (int)tid_to_contig_.size();
     const bool tid_ok = tid >= 0 && tid < n_refs;
     if (!tid_ok) r.aux |= RSQ_AUX_TID_OUT_OF_RANGE;
     if (tid > 127) r.aux |= RSQ_AUX_TID_GT_127;
-    const int chr = tid_ok ? tid_to_contig_[tid] : -1;
-    r.contig = (chr >= 0 && (size_t)chr < n_annotation_contigs_ && chr <= INT16_MAX) ? (int16_t)chr : (int16_t)-1;
+    r.contig = (int16_t)-1;                                                      // Decoder::bind_contig
 }
 
 }  // namespace rsqh

@@ -73,7 +73,7 @@ struct RunSummary {
     bool bad_tid = false;                // some record stops at the reference-id check (a message under -v)
     size_t n_reaching = 0;               // records that reach trimFeatures / dropFeatures
     bool single_chr = true, sorted = true;
-    int chr = -1;
+    int chr = -1;                        // as the BAM reference id (the workers digest jobs before the annotation's contig ids exist)
     int32_t first_pos = 0, last_pos = 0;
 };
 
@@ -88,10 +88,19 @@ public:
     //    r.block_off is relative to `blocks`; tid receives core.tid
     //  - observe: the order-dependent scalar state, must be called in file order
     void convert_bam_bytes(const uint8_t* rec, size_t len, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid) const;
+    //    ... and its two parts: everything that needs only the command line and the BAM header (the ingest starts converting while
+    //    the GTF is still being parsed: no Decoder exists yet), and the contig id of the annotation (bind_contig, by the consumer)
+    static void convert_bam_record(const DecodeOptions& opt, int n_refs, const uint8_t* rec, size_t len, rsq_read& r, std::vector<rsq_block>& blocks, int32_t& tid);
+    void bind_contig(rsq_read& r, int32_t tid) const {
+        const int chr = (tid >= 0 && tid < (int)tid_to_contig_.size()) ? tid_to_contig_[tid] : -1;
+        r.contig = (chr >= 0 && (size_t)chr < n_annotation_contigs_ && chr <= INT16_MAX) ? (int16_t)chr : (int16_t)-1;
+    }
     void observe(rsq_read& r, int32_t tid);
-    //  - summarise (pure) + observe_run: observe() for a whole run of records in O(1) when its digest allows (see below)
-    RunSummary summarise(const rsq_read* r, const int32_t* tids, size_t n) const;
+    //  - summarise (pure, static: command line + header only) + observe_run: observe() for a whole run of records in O(1) when its
+    //    digest allows (see below)
+    static RunSummary summarise(const DecodeOptions& opt, int n_refs, const rsq_read* r, const int32_t* tids, size_t n);
     bool observe_run(const RunSummary& s);
+    const DecodeOptions& options() const { return opt_; }
 
     bool saw_unsorted() const { return warned_unsorted_; }
     int read_length() const { return read_length_; }
@@ -106,7 +115,8 @@ public:
     int32_t trim_position() const { return last_metrics_chrom_ == current_chrom_ ? last_position_ : INT32_MIN; }
 
 private:
-    unsigned gates(const rsq_read& r, int32_t tid, bool tid_ok) const;
+    static unsigned gates(const DecodeOptions& opt_, const rsq_read& r, int32_t tid, bool tid_ok);
+    unsigned gates(const rsq_read& r, int32_t tid, bool tid_ok) const { return gates(opt_, r, tid, tid_ok); }
     DecodeOptions opt_;
     std::vector<int> tid_to_contig_;        // BAM tid -> ContigMap id (always valid: names are added)
     size_t n_annotation_contigs_;
@@ -123,7 +133,7 @@ private:
 // The gates of the loop in front of the order-dependent state, as a pure function of one record (same order as the loop; none of
 // them reads that state): bit 0 = the record gets to the read-length lines (:275-278), bit 1 = it reaches the metrics
 // (trimFeatures / dropFeatures, :346-356), bit 2 = it stopped at the reference-id check (:333-337).
-inline unsigned Decoder::gates(const rsq_read& r, int32_t tid, bool tid_ok) const {
+inline unsigned Decoder::gates(const DecodeOptions& opt_, const rsq_read& r, int32_t tid, bool tid_ok) {
     const bool has_ch = r.aux & RSQ_AUX_CHIMERIC_TAG;
     if ((r.flag & RSQ_F_SUPPLEMENTARY) && !(opt_.legacy || has_ch) && opt_.exclude_chimeric) return 0;   // :258-262
     if (r.flag & (RSQ_F_SECONDARY | RSQ_F_QCFAIL | RSQ_F_SUPPLEMENTARY)) return 0;               // :263
@@ -175,21 +185,20 @@ inline void Decoder::observe(rsq_read& r, int32_t tid) {
 }
 
 // Order-independent digest of a run of consecutive records (pure; the ingest workers compute it per job).
-inline RunSummary Decoder::summarise(const rsq_read* r, const int32_t* tids, size_t n) const {
+inline RunSummary Decoder::summarise(const DecodeOptions& opt, int n_refs, const rsq_read* r, const int32_t* tids, size_t n) {
     RunSummary s;
     s.n = n;
-    const int n_refs = (int)tid_to_contig_.size();
     for (size_t k = 0; k < n; ++k) {
         const int32_t tid = tids[k];
         const bool tid_ok = tid >= 0 && tid < n_refs;
-        const unsigned g = gates(r[k], tid, tid_ok);
+        const unsigned g = gates(opt, r[k], tid, tid_ok);
         if (g & 1) {
             if (!s.any_read_length_line) { s.any_read_length_line = true; s.l_qseq = r[k].l_qseq; }
             else if (r[k].l_qseq != s.l_qseq) s.l_qseq_uniform = false;
         }
         if (g & 4) s.bad_tid = true;
         if (g & 2) {
-            const int chr = tid_to_contig_[tid];
+            const int chr = tid;                 // two ids of one contig name (a header with a repeated @SQ) only make the digest unusable
             if (!s.n_reaching) { s.chr = chr; s.first_pos = r[k].pos; }
             else { if (chr != s.chr) s.single_chr = false; if (r[k].pos < s.last_pos) s.sorted = false; }
             s.last_pos = r[k].pos;
@@ -206,12 +215,13 @@ inline bool Decoder::observe_run(const RunSummary& s) {
     if (s.any_read_length_line && !(s.l_qseq_uniform && read_length_ != 0 && s.l_qseq == read_length_)) return false;
     if (s.bad_tid && opt_.verbosity) return false;
     if (s.n_reaching) {
-        if (!s.single_chr || (int64_t)s.chr != current_chrom_) return false;
-        if ((size_t)s.chr < dropped_.size() && dropped_[s.chr]) return false;
+        const int chr = tid_to_contig_[s.chr];                     // a record reaches the metrics only with a reference id in range
+        if (!s.single_chr || (int64_t)chr != current_chrom_) return false;
+        if ((size_t)chr < dropped_.size() && dropped_[chr]) return false;
         if (!warned_unsorted_ && !(s.sorted && last_position_ <= s.first_pos)) return false;
-        if ((size_t)s.chr >= dropped_.size()) dropped_.resize(s.chr + 1, 0);
+        if ((size_t)chr >= dropped_.size()) dropped_.resize(chr + 1, 0);
         last_position_ = s.last_pos;
-        last_metrics_chrom_ = s.chr;
+        last_metrics_chrom_ = chr;
     }
     alignment_count_ += s.n;
     return true;

@@ -14,8 +14,12 @@
 //                   CONVERT of the framed job: every whole BAM record -> rsq_read + rsq_block (Decoder::convert_bam_bytes, pure)
 //                   (the dependent hop through 4 MB another core had just written cost ~100 ns per record and capped ingest
 //                   at ~10 M records/s whatever the number of workers)
-//   consumer      : next_batch(): takes converted jobs in file order, runs Decoder::observe (readLength, contig-drop
-//                   state, unsorted warning: src/RNASeQC.cpp:275-278,346-356) and appends to the caller's batch
+//   consumer      : next_batch(): takes converted jobs in file order, binds the annotation's contig ids (Decoder::bind_contig),
+//                   runs Decoder::observe (readLength, contig-drop state, unsorted warning: src/RNASeQC.cpp:275-278,346-356)
+//                   and appends to the caller's batch
+// Nothing before the consumer needs the annotation: start() runs all of it while the GTF is parsed and the device comes up.
+// A job hands its 4 MB inflate buffer back as soon as its records are converted, so the jobs waiting for the consumer cost
+// about 1 MB each and the run-ahead can be deep (max_jobs_ahead_).
 #include "bamparallel.h"
 #include "fastinflate.h"
 
@@ -186,6 +190,9 @@ ParallelBamDecoder::ParallelBamDecoder(const std::string& path, int n_threads)
         std::fseek(fp_, 0, SEEK_SET);
     }
     max_jobs_in_flight_ = (size_t)n_threads_ * 3 + 4;
+    max_jobs_ahead_ = 1536;                                        // ~1.5 GB of converted records at most
+    if (const char* e = std::getenv("RSQ_INGEST_AHEAD_JOBS")) max_jobs_ahead_ = (size_t)std::max(1L, std::atol(e));
+    max_jobs_ahead_ = std::max(max_jobs_ahead_, max_jobs_in_flight_);
     speculate_ = !std::getenv("RSQ_INGEST_NO_SPECULATION");
     summarise_ = !std::getenv("RSQ_INGEST_NO_SUMMARY");
 }
@@ -200,7 +207,7 @@ ParallelBamDecoder::~ParallelBamDecoder() {
     cv_consumer_.notify_all();
     if (reader_.joinable()) reader_.join();
     for (auto& t : workers_) if (t.joinable()) t.join();
-    jobs_.clear();
+    jobs_.clear(); to_inflate_.clear(); to_convert_.clear();
     if (fp_) std::fclose(fp_);
     g_last_hits = n_chain_hits_; g_last_misses = n_chain_misses_; g_last_summarised = n_runs_summarised_;
     if (std::getenv("RSQ_INGEST_STATS"))
@@ -239,10 +246,12 @@ void ParallelBamDecoder::reader_loop() {
             job->data_len = total;
             t_reader_ += since(t_job);
             std::unique_lock<std::mutex> lk(mu_);
-            cv_reader_.wait(lk, [&] { return stop_ || jobs_.size() < max_jobs_in_flight_; });
+            cv_reader_.wait(lk, [&] { return stop_ || (n_unconverted_ < max_jobs_in_flight_ && jobs_.size() < max_jobs_ahead_); });
             if (stop_) return;
             job->id = next_job_id_++;
             jobs_.push_back(job);
+            to_inflate_.push_back(job);
+            ++n_unconverted_;
             lk.unlock();
             cv_work_.notify_one();
         }
@@ -281,7 +290,7 @@ void ParallelBamDecoder::speculate(Job& j) const {
             while ((v = plausible_record(base, p, end, n_ref)) == 1) {
                 uint32_t bs; memcpy(&bs, base + p, 4);
                 rsq_read r; int32_t tid;
-                dec_for_params_->convert_bam_bytes(base + p + 4, bs, r, j.rblocks, tid);
+                Decoder::convert_bam_record(conv_opt_, n_ref, base + p + 4, bs, r, j.rblocks, tid);
                 j.chain.push_back((uint32_t)p);
                 j.reads.push_back(r);
                 j.tids.push_back(tid);
@@ -290,7 +299,7 @@ void ParallelBamDecoder::speculate(Job& j) const {
         } catch (...) { v = 0; }
         if (v == 2) {
             j.chain_end = p; j.spec_ok = true;
-            if (summarise_) { j.summary = dec_for_params_->summarise(j.reads.data(), j.tids.data(), j.reads.size()); j.has_summary = true; }
+            if (summarise_) { j.summary = Decoder::summarise(conv_opt_, n_ref, j.reads.data(), j.tids.data(), j.reads.size()); j.has_summary = true; }
         }
         else { j.chain.clear(); j.reads.clear(); j.rblocks.clear(); j.tids.clear(); }
         return;                                  // one guess per job: a second would cost a second conversion
@@ -320,7 +329,7 @@ bool ParallelBamDecoder::frame_on_chain(Job& j, size_t begin, size_t end) {
     if (c) {
         memcpy(base + begin - c, carry_.data(), c);
         j.head_blocks.clear();
-        dec_for_params_->convert_bam_bytes(base + begin - c + 4, bs, j.head_read, j.head_blocks, j.head_tid);   // may throw: the job's error, as in CONVERT
+        Decoder::convert_bam_record(conv_opt_, (int)hdr_.ref_names.size(), base + begin - c + 4, bs, j.head_read, j.head_blocks, j.head_tid);   // may throw: the job's error, as in CONVERT
         j.head_read.block_off = 0;
         j.has_head = true;
     }
@@ -336,11 +345,17 @@ void ParallelBamDecoder::worker_loop() {
         auto& q = jobs_;
         std::shared_ptr<Job> todo;
         int what = 0;   // 1 frame, 2 convert, 3 inflate
-        // 1. framing is sequential: only the job whose id is next_frame_id_, and only one framer at a time (carry_ is its state)
-        for (auto& j : q)
-            if (j->id == next_frame_id_ && j->state == ST_INFLATED) { todo = j; what = 1; j->state = ST_FRAMING; break; }
-        if (!todo) for (auto& j : q) if (j->state == ST_FRAMED) { todo = j; what = 2; j->state = ST_CONVERTING; break; }
-        if (!todo) for (auto& j : q) if (j->state == ST_READ) { todo = j; what = 3; j->state = ST_INFLATING; break; }
+        // 1. framing is sequential: only the job whose id is next_frame_id_, and only one framer at a time (carry_ is its state);
+        //    ids are consecutive in jobs_, so that job sits at a known place
+        if (!q.empty() && next_frame_id_ >= q.front()->id && next_frame_id_ - q.front()->id < q.size()) {
+            auto& j = q[(size_t)(next_frame_id_ - q.front()->id)];
+            if (j->state == ST_INFLATED) { todo = j; what = 1; j->state = ST_FRAMING; }
+        }
+        if (!todo && !to_convert_.empty()) { todo = to_convert_.front(); to_convert_.pop_front(); what = 2; todo->state = ST_CONVERTING; }
+        if (!todo && !to_inflate_.empty()) {
+            todo = to_inflate_.front(); to_inflate_.pop_front(); what = 3; todo->state = ST_INFLATING;
+            if (todo->out.capacity() == 0 && !out_pool_.empty()) { todo->out = std::move(out_pool_.back()); out_pool_.pop_back(); }
+        }
         if (!todo) {
             if (reader_done_ && q.empty()) return;
             cv_work_.wait(lk);
@@ -399,12 +414,12 @@ void ParallelBamDecoder::worker_loop() {
                 while (p < todo->rec_end) {
                     uint32_t bs; memcpy(&bs, base + p, 4);
                     rsq_read r; int32_t tid;
-                    dec_for_params_->convert_bam_bytes(base + p + 4, bs, r, todo->rblocks, tid);
+                    Decoder::convert_bam_record(conv_opt_, (int)hdr_.ref_names.size(), base + p + 4, bs, r, todo->rblocks, tid);
                     todo->reads.push_back(r);
                     todo->tids.push_back(tid);
                     p += 4 + (size_t)bs;
                 }
-                if (summarise_) { todo->summary = dec_for_params_->summarise(todo->reads.data(), todo->tids.data(), todo->reads.size()); todo->has_summary = true; }
+                if (summarise_) { todo->summary = Decoder::summarise(conv_opt_, (int)hdr_.ref_names.size(), todo->reads.data(), todo->tids.data(), todo->reads.size()); todo->has_summary = true; }
             }
         } catch (HostError& e) {
             todo->error = e.what(); todo->error_code = e.exit_code ? e.exit_code : -1;
@@ -419,30 +434,38 @@ void ParallelBamDecoder::worker_loop() {
             // a failed job surfaces at the consumer when its turn comes; framing moves past it so earlier records still flow
             if (todo->id == next_frame_id_) ++next_frame_id_;
             todo->state = ST_CONVERTED;
-            cv_consumer_.notify_all();
         } else if (what == 3) todo->state = ST_INFLATED;
         else if (what == 1) {
             ++next_frame_id_;
-            if (framed_by_chain) { todo->state = ST_CONVERTED; ++n_chain_hits_; cv_consumer_.notify_all(); }
-            else { todo->state = ST_FRAMED; ++n_chain_misses_; }
+            if (framed_by_chain) { todo->state = ST_CONVERTED; ++n_chain_hits_; }
+            else { todo->state = ST_FRAMED; ++n_chain_misses_; to_convert_.push_back(todo); }
         }
-        else { todo->state = ST_CONVERTED; cv_consumer_.notify_all(); }
+        else todo->state = ST_CONVERTED;
+        if (todo->state == ST_CONVERTED) {
+            // the records are out of the inflated bytes: the 4 MB buffer goes to the next job, and the reader may read on
+            if (todo->out.capacity()) { out_pool_.push_back(std::move(todo->out)); todo->out = std::vector<uint8_t>(); }
+            todo->big = std::vector<uint8_t>(); todo->use_big = false;
+            --n_unconverted_;
+            cv_consumer_.notify_all();
+            cv_reader_.notify_one();
+        }
         cv_work_.notify_all();
     }
+}
+
+void ParallelBamDecoder::start(const DecodeOptions& opt) {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (started_) return;
+    started_ = true;
+    conv_opt_ = opt;
+    reader_ = std::thread(&ParallelBamDecoder::reader_loop, this);
+    for (int t = 0; t < n_threads_; ++t) workers_.emplace_back(&ParallelBamDecoder::worker_loop, this);
 }
 
 bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks) {
     reads.clear();
     blocks.clear();
-    {
-        std::unique_lock<std::mutex> lk(mu_);
-        if (!params_set_) {
-            dec_for_params_ = &dec;
-            params_set_ = true;
-            reader_ = std::thread(&ParallelBamDecoder::reader_loop, this);
-            for (int t = 0; t < n_threads_; ++t) workers_.emplace_back(&ParallelBamDecoder::worker_loop, this);
-        }
-    }
+    start(dec.options());
     while (reads.size() < max_records) {
         std::shared_ptr<Job> job = cur_;
         if (!job) {
@@ -464,6 +487,7 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
                 rsq_read r = job->head_read;
                 r.block_off = (uint32_t)blocks.size();
                 blocks.insert(blocks.end(), job->head_blocks.begin(), job->head_blocks.end());
+                dec.bind_contig(r, job->head_tid);
                 reads.push_back(r);
                 dec.observe(reads.back(), job->head_tid);
                 job->has_head = false;
@@ -486,10 +510,11 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
             // a whole job whose digest shows that no record moves the order-dependent state (but for the last position): O(1)
             if (job->has_summary && cur_read_ == 0 && n == job->reads.size() && dec.observe_run(job->summary)) {
                 ++n_runs_summarised_;
-                for (size_t k = 0; k < n; ++k) out[k].block_off += delta;
+                for (size_t k = 0; k < n; ++k) { out[k].block_off += delta; dec.bind_contig(out[k], tids[k]); }
             } else {
                 for (size_t k = 0; k < n; ++k) {
                     out[k].block_off += delta;
+                    dec.bind_contig(out[k], tids[k]);
                     dec.observe(out[k], tids[k]);
                 }
             }

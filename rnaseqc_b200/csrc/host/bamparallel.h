@@ -26,6 +26,11 @@ public:
     ParallelBamDecoder(const std::string& path, int n_threads);
     ~ParallelBamDecoder();
     const AlnHeader& header() const { return hdr_; }
+    // Starts the reader and the workers NOW: inflate, framing and conversion need only the command line's decode options and the
+    // BAM header, so the CLI calls this before it parses the GTF and brings the device up — by the time the first batch is asked
+    // for, up to `ahead` jobs (~1 MB of converted records each) are waiting.  next_batch() starts them itself otherwise.  The
+    // Decoder handed to next_batch() must have been built with the same options.
+    void start(const DecodeOptions& opt);
     // Appends up to max_records converted records (with their blocks) to the cleared vectors, in file order, running
     // dec.observe() on each.  Returns false once the stream is exhausted and nothing was appended.
     bool next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
@@ -53,16 +58,20 @@ private:
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_work_, cv_consumer_, cv_reader_;
-    std::deque<std::shared_ptr<Job>> jobs_;        // in file order; front = oldest not yet consumed
+    std::deque<std::shared_ptr<Job>> jobs_;        // in file order (ids are consecutive); front = oldest not yet consumed
+    std::deque<std::shared_ptr<Job>> to_inflate_, to_convert_;   // work lists of the stages that any worker may take, oldest first
     std::vector<std::shared_ptr<Job>> pool_;       // consumed jobs whose buffers are reused
+    std::vector<std::vector<uint8_t>> out_pool_;   // 4 MB inflate buffers: a job gives its buffer back once its records are converted
+    size_t n_unconverted_ = 0;                     // jobs that still hold an inflate buffer (or are about to take one)
     uint64_t next_job_id_ = 0;
     uint64_t next_frame_id_ = 0;       // framing is sequential: the next job id to frame
     std::vector<uint8_t> carry_;       // partial record at the end of the last framed job
     bool reader_done_ = false, stop_ = false;
-    size_t max_jobs_in_flight_;
-    // conversion parameters (copied from the Decoder at the first next_batch)
-    bool params_set_ = false;
-    const Decoder* dec_for_params_ = nullptr;
+    size_t max_jobs_in_flight_;        // ... of those: bounds the inflate buffers
+    size_t max_jobs_ahead_;            // ... of all jobs not yet consumed: bounds the converted records waiting for the consumer
+    // conversion parameters: the command line's decode options (start) and the header's number of references
+    bool started_ = false;
+    DecodeOptions conv_opt_;
     // consumer cursor
     std::shared_ptr<Job> cur_;
     size_t cur_read_ = 0;

@@ -15,5 +15,6 @@ int main(int argc, char** argv) {
                      rsq_host_free, rsq_set_partition, rsq_export_sample_counts, rsq_export_counts, rsq_import_counts, rsq_comm_unique_id,
                      rsq_comm_init, rsq_exchange};
     if (opt.verbosity) std::cout << "hot-path backend: " << be.backend() << std::endl;
+    opt.exit_after_reports = true;
     return rsqh::run_sample(be, opt);
 }

@@ -295,6 +295,23 @@ int run_sample(const Backend& be, CliOptions& opt) {
                 return be.create(&cfg, &L.ctx);
             });
         }
+        // So does the BAM ingest: inflating, framing and converting records needs the command line and the BAM header only
+        // (bamparallel.h: start), so the worker threads run ahead while this thread parses the GTF, builds the index and uploads
+        // it.  A file that cannot be opened or is no BAM is reported where the reference opens it (after the GTF, the BED and the
+        // output directory), not here.
+        std::unique_ptr<ParallelBamDecoder> pbam;
+        std::exception_ptr early_bam_error;
+        if (opt.decode_threads > 0 && !getenv("RSQ_INGEST_LATE_START")) {
+            unsigned char m[2] = {0, 0};
+            size_t got = 0;
+            if (FILE* fp = std::fopen(opt.bam.c_str(), "rb")) { got = std::fread(m, 1, 2, fp); std::fclose(fp); }
+            if (got == 2 && m[0] == 0x1f && m[1] == 0x8b) {
+                try {
+                    pbam.reset(new ParallelBamDecoder(opt.bam, opt.decode_threads));
+                    pbam->start(opt.decode);
+                } catch (...) { early_bam_error = std::current_exception(); pbam.reset(); }
+            }
+        }
         Annotation A;
         ReferenceModel ref;
         if (!opt.fasta.empty()) {                                                  // src/RNASeQC.cpp:117-122: before the GTF
@@ -324,8 +341,8 @@ int run_sample(const Backend& be, CliOptions& opt) {
 
         // BAM goes through the multi-threaded ingest (bamparallel.cpp); SAM text through the sequential reader
         std::unique_ptr<AlnReader> reader;
-        std::unique_ptr<ParallelBamDecoder> pbam;
-        {
+        if (early_bam_error) std::rethrow_exception(early_bam_error);              // ... with the precedence it always had
+        if (!pbam) {
             FILE* fp = std::fopen(opt.bam.c_str(), "rb");
             if (!fp) throw HostError(10, "Unable to open BAM file: " + opt.bam);
             unsigned char m[2] = {0, 0};
@@ -641,6 +658,12 @@ int run_sample(const Backend& be, CliOptions& opt) {
         auto t_rep = clk::now();
         write_reports(A, R, opt.run, st, ref.open ? &ref : nullptr);
         if (opt.verbosity) std::cout << "Report files: " << std::chrono::duration<double>(clk::now() - t_rep).count() << " seconds" << std::endl;
+        if (opt.exit_after_reports && !getenv("RSQ_FULL_TEARDOWN")) {
+            for (Staged& st : staged) if (st.how.valid()) st.how.wait();
+            if (getenv("RSQ_INGEST_STATS")) pbam.reset();          // its stage times are printed when it goes
+            std::cout.flush(); std::cerr.flush(); std::fflush(nullptr);
+            std::_Exit(0);
+        }
     } catch (HostError& e) {
         std::cerr << e.what() << std::endl;
         exit_code = e.exit_code;

@@ -56,6 +56,8 @@ struct CliOptions {
     size_t records_per_gpu = 0;       // --records-per-gpu: records a GPU takes before the stream moves on to the next (0 = by file size)
     int decode_threads = -1;          // -1: hardware threads (<= 32); 0: sequential reader
     int verbosity = 0;
+    bool exit_after_reports = false;  // the CLI binary: once the report files are closed the process ends without tearing down page-locked
+                                      // buffers, device tables and ingest threads one by one (the OS does that in one sweep)
 };
 
 // Fills `opt` from argv with the reference's flag set (src/RNASeQC.cpp:39-65).  Returns an exit code < 0 to

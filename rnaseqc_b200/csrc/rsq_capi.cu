@@ -6,6 +6,7 @@
 #include <nccl.h>      // types and enums only: the library is bound at run time (dlopen), never linked
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -475,6 +476,15 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     if (c->cfg.legacy && (!a->gline_off || !a->exon_order || (a->n_gene_lines && (!a->gline_start || !a->gline_end || !a->gline_gene || !a->gline_flags || !a->gline_order)))) {
         c->err = "legacy mode needs the gene-line arrays of rsq_annotation"; return RSQ_ERR_INVALID;
     }
+    // RSQ_SETUP_STATS=1: where the time of this call goes (host-side index build against device allocation and upload)
+    const bool setup_stats = getenv("RSQ_SETUP_STATS") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!setup_stats) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "rsq_set_annotation: %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_mark).count());
+        t_mark = now;
+    };
     // repack host-side into the device layout: (start,end) pairs and 16-byte metadata
     std::vector<int2> se((size_t)a->n_exons + 4, make_int2(INT32_MAX, INT32_MAX));   // padded for the rounded-up bulk copies
     std::vector<ExonMeta> meta((size_t)a->n_exons + 4);
@@ -518,6 +528,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         v.gline_pmax = gpmax;
         CU_TRY(cudaStreamSynchronize(c->stream));   // gse / ggf are locals
     }
+    lap("exon tables");
     // deepest stack of overlapping exons: bounds the fragment-set inserts of one record
     {
         unsigned long long depth = 1;
@@ -530,10 +541,12 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         }
         c->exon_depth = depth;
     }
+    lap("exon depth");
     // elementary-interval index (rsq_eit.h): what the hot path searches instead of the exon list
     if (!c->cfg.legacy) {
         EiIndex X;
         const std::string why = build_ei_index(a, X);
+        lap("elementary-interval index");
         if (!why.empty()) { c->err = "annotation cannot be indexed: " + why; return RSQ_ERR_INVALID; }
         static_assert(sizeof(EiDesc) == sizeof(uint2), "descriptor is read as one 64-bit word");
         if ((rc = upload(c, c->ann_allocs, X.ei_off.data(), X.ei_off.size(), &v.ei_off))) return rc;
@@ -550,6 +563,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         v.recip64 = nullptr;
         v.ei_off = nullptr; v.ei_start = nullptr; v.ei_desc = nullptr; v.cover = nullptr; v.eib_off = nullptr; v.eib = nullptr;
     }
+    lap("index upload + reciprocals");
 #ifndef RSQ_NO_CASCADE_LUT
     {   // the filter cascade as a pure function of 17 bits of a record: tabulated once per context
         std::vector<unsigned long long> lut(kCascadeEntries);
@@ -558,6 +572,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
         CU_TRY(cudaStreamSynchronize(c->stream));   // lut is a local
     }
 #endif
+    lap("cascade table");
     // accumulators
     Accum& acc = c->acc;
     CU_TRY(cudaMalloc(&acc.counters, 8 * RSQ_N_COUNTERS));
@@ -592,6 +607,7 @@ int rsq_set_annotation(rsq_ctx* ctx, const rsq_annotation* a) {
     rc = zero_accumulators(c);
     if (rc != RSQ_OK) return rc;
     CU_TRY(cudaStreamSynchronize(c->stream));   // host staging vectors go out of scope
+    lap("accumulators (alloc + zero)");
     return RSQ_OK;
 }
 
