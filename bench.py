@@ -403,7 +403,9 @@ def run_ours(args):
               "fragment_samples_taken": int(res.fragment_samples_taken),
               "genes_in_3prime_bias": int(((cs["five_end"] + cs["three_end"]) > 0).sum())}
     # the dominant kernel's own time (CUDA events recorded by the library around the hot-path launches of one step)
-    ctx.reset(); ctx.submit_device(rb.data_ptr(), n_reads, bb.data_ptr(), n_blocks); ctx.sync()
+    ctx.reset()
+    torch.cuda.synchronize()      # the kernel ALONE: also the side stream, where the other fragment-tracker table is being zeroed
+    ctx.submit_device(rb.data_ptr(), n_reads, bb.data_ptr(), n_blocks); ctx.sync()
     hot_ms = ctx.kernel_time_ms()
     finish()
     ms_step_local = max(ms_dev, t_wall * 1e3) / args.steps
@@ -455,7 +457,9 @@ def run_ours(args):
             step_strong()
         barrier()
         dt_s = (time.perf_counter() - t_s) / args.steps
-        ctx.reset(); ctx.submit_device(rb2.data_ptr(), n2, bb2.data_ptr(), nb2); ctx.sync()
+        ctx.reset()
+        torch.cuda.synchronize()
+        ctx.submit_device(rb2.data_ptr(), n2, bb2.data_ptr(), nb2); ctx.sync()
         hot_s = ctx.kernel_time_ms()
         finish()
         t = torch.tensor([dt_s, hot_s], device=device, dtype=torch.float64)
@@ -635,7 +639,7 @@ def run_ours(args):
                        "records_total": int(total_records), "records_per_gpu": n_reads, "blocks_per_gpu": n_blocks, "genes": ann.n_genes, "exons": ann.n_exons,
                        "exon_bases": ann.cov_len, "bed_fragment_sizes": bool(args.bed),
                        "partitioning": ("coordinate ranges cut at gene-free positions; " + ("the workload's records split over the GPUs (BASELINE configs[3])" if strong else "every GPU draws the workload's record count from its own range")) if world > 1 else "none",
-                       "step": "reset + hot-path kernel" + (" + rsq_exchange (NCCL inside the library: count vectors, ordered first-N fragment-size cut)" if world > 1 else "") +
+                       "step": "reset (the fragment-tracker table of the next pass is zeroed on a side stream during this one) + hot-path kernel" + (" + rsq_exchange (NCCL inside the library: count vectors, ordered first-N fragment-size cut)" if world > 1 else "") +
                                " + coverage integration + per-gene coverage/bias statistics kernel" + (" of the rank's own genes + NCCL gather" if world > 1 else "") + " + count/statistics read-back",
                        "l2_policy": f"inputs ({(48 * n_reads + 8 * n_blocks) / 1e9:.1f} GB per GPU) larger than the 126 MB L2",
                        "timed_seconds": ms_step * args.steps / 1e3,

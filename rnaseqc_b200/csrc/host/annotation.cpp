@@ -2,7 +2,9 @@
 #include "annotation.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -125,6 +127,15 @@ uint32_t Annotation::gene_universe(const std::string& id) {
 }
 
 void load_gtf(const std::string& path, Annotation& A, bool legacy) {
+    // RSQ_SETUP_STATS=1: where the time of the start-up goes (like rsq_set_annotation in the library)
+    const bool setup_stats = getenv("RSQ_SETUP_STATS") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!setup_stats) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "load_gtf: %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_mark).count());
+        t_mark = now;
+    };
     // the whole file in memory, lines and fields as views into it (the loop below runs ~0.5 M times for a GENCODE-scale GTF)
     std::string text;
     {
@@ -145,6 +156,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
         }
     }
 
+    lap("file read");
     // State of the single re-used Feature object (src/RNASeQC.cpp:109): these three survive from line to line
     // because operator>> only assigns them when the attribute exists (src/GTF.cpp:81,89,90,95,110).
     std::string cur_feature_id, cur_gene_id, cur_transcript_type;
@@ -257,6 +269,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
         }
     }
 
+    lap("line loop");
     if (A.gene_list.empty() || A.exon_ids.empty()) {
         std::cerr << "There were either no genes or no exons in the GTF" << std::endl;
         std::cerr << A.gene_list.size() << " genes parsed" << std::endl;
@@ -279,6 +292,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
         if (it != ids.end() && it->second.named) A.exon_desc[e] = it->second.name;
     }
 
+    lap("names");
     // Per contig, list.sort(compIntervalStart) — a stable sort by start over genes and exons interleaved
     // (src/RNASeQC.cpp:150-152).  Genes and exons are separated here; relative order inside each kind is
     // what the stable sort would give, which is all that exonsForGene and the eviction order depend on.
@@ -368,7 +382,9 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
     A.f_exon_off[nc] = (uint32_t)A.f_exon_start.size();
     A.f_seg_off[nc] = (uint32_t)A.f_seg_start.size();
     A.f_gline_off[nc] = (uint32_t)A.f_gline_start.size();
+    lap("sort + flatten");
     A.build_transcripts();
+    lap("transcripts");
 }
 
 void Annotation::pad_contigs(size_t n_contigs) {

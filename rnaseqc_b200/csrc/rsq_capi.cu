@@ -48,6 +48,13 @@ struct Ctx {
     unsigned int* d_scan = nullptr;           // scan scratch
     size_t scan_elems = 0;
     unsigned long long frag_cap = 0, pair_cap = 0;
+    // contexts that are reset and run again (one sample after another): a second fragment-tracker table is zeroed on a side stream
+    // while the hot kernel fills the first one, and rsq_reset swaps the two — the 3.2 GB memset (200 M records) leaves the step
+    unsigned long long* frag_spare = nullptr;
+    unsigned long long frag_spare_cap = 0;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_spare_clean = nullptr, ev_reset_mark = nullptr;
+    unsigned resets = 0;
     unsigned long long frag_known = 0, frag_pending = 0;   // entries read back from the device / upper bound of those in flight
     unsigned long long exon_depth = 1;                     // deepest stack of overlapping exons (inserts per record <= this)
     unsigned long long* d_export = nullptr;
@@ -174,7 +181,43 @@ void free_list(std::vector<void*>& v) {
     v.clear();
 }
 
-int zero_accumulators(Ctx* c) {
+// The fragment-tracker table of the next run.  First run of a context (and one-shot users, the CLI): zeroed in line.  From the second
+// rsq_reset on, a spare table of the same size exists: it was zeroed on the side stream while the previous run's kernels filled the
+// other one, so the reset only swaps the two and sends the used one to the side stream — after everything queued on the compute
+// stream so far (the kernels that wrote it), and the compute stream waits for the clean one before it goes on.
+int fresh_frag_table(Ctx* c, bool from_reset) {
+    Accum& a = c->acc;
+    const size_t bytes = 8ull * c->frag_cap;
+    if (from_reset && c->frag_spare && c->frag_spare_cap == c->frag_cap) {
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_spare_clean, 0));
+        std::swap(a.frag_set, c->frag_spare);
+    } else {
+        if (c->frag_spare) {                                           // the table has grown since: the spare no longer fits
+            CU_TRY(cudaStreamSynchronize(c->aux_stream));
+            cudaFree(c->frag_spare);
+            c->frag_spare = nullptr; c->frag_spare_cap = 0;
+        }
+        CU_TRY(cudaMemsetAsync(a.frag_set, 0, bytes, c->stream));
+        if (from_reset && ++c->resets >= 2 && !getenv("RSQ_NO_SPARE_TABLE")) {
+            if (!c->aux_stream) {
+                CU_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+                CU_TRY(cudaEventCreateWithFlags(&c->ev_spare_clean, cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&c->ev_reset_mark, cudaEventDisableTiming));
+            }
+            if (cudaMalloc(&c->frag_spare, bytes) == cudaSuccess) c->frag_spare_cap = c->frag_cap;
+            else { c->frag_spare = nullptr; cudaGetLastError(); }      // no room for a second table: resets keep zeroing in line
+        }
+    }
+    if (c->frag_spare) {
+        CU_TRY(cudaEventRecord(c->ev_reset_mark, c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_reset_mark, 0));
+        CU_TRY(cudaMemsetAsync(c->frag_spare, 0, bytes, c->aux_stream));
+        CU_TRY(cudaEventRecord(c->ev_spare_clean, c->aux_stream));
+    }
+    return RSQ_OK;
+}
+
+int zero_accumulators(Ctx* c, bool from_reset = false) {
     Accum& a = c->acc;
     CU_TRY(cudaMemsetAsync(a.counters, 0, 8 * RSQ_N_COUNTERS, c->stream));
     CU_TRY(cudaMemsetAsync(a.gene_reads, 0, 8ull * c->n_genes, c->stream));
@@ -184,7 +227,7 @@ int zero_accumulators(Ctx* c) {
     CU_TRY(cudaMemsetAsync(a.exon_fhi, 0, 8ull * c->n_exons, c->stream));
     CU_TRY(cudaMemsetAsync(a.exon_flo, 0, 8ull * c->n_exons, c->stream));
     CU_TRY(cudaMemsetAsync(a.cov_diff, 0, 4ull * (c->cov_len + 1), c->stream));
-    CU_TRY(cudaMemsetAsync(a.frag_set, 0, 8ull * c->frag_cap, c->stream));
+    { const int rc = fresh_frag_table(c, from_reset); if (rc != RSQ_OK) return rc; }
     CU_TRY(cudaMemsetAsync(a.algo_bytes, 0, 8, c->stream));
     CU_TRY(cudaMemsetAsync(a.error_flag, 0, 4, c->stream));
     if (c->have_bed && c->cfg.fragment_samples) {
@@ -455,6 +498,8 @@ void rsq_destroy(rsq_ctx* ctx) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& t : c->timers) { cudaEventDestroy(t.first); cudaEventDestroy(t.second); }
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(c->ev_copied[k]); cudaEventDestroy(c->ev_done[k]); }
+    if (c->frag_spare) cudaFree(c->frag_spare);
+    if (c->aux_stream) { cudaEventDestroy(c->ev_spare_clean); cudaEventDestroy(c->ev_reset_mark); cudaStreamDestroy(c->aux_stream); }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -891,7 +936,7 @@ int rsq_reset(rsq_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !c->have_ann) return RSQ_ERR_INVALID;
     CU_TRY(cudaSetDevice(c->cfg.device));
-    return zero_accumulators(c);
+    return zero_accumulators(c, true);
 }
 
 int rsq_finalize(rsq_ctx* ctx, rsq_results* out) {

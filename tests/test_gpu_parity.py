@@ -118,6 +118,19 @@ def test_empty_and_tiny_batches(libs, synth_case):
     ctx.reset()
     ctx.submit(reads[:33].copy(), blocks)
     assert_results_equal(ctx.finalize(), want, "after reset")
+    # a context that is reset again and again swaps between two fragment-tracker tables, the idle one zeroed on a side stream
+    # (rsq_capi.cu: fresh_frag_table): every run must start from an empty set, with and without a finalize in between
+    want_1000, _ = _run(api, libs["oracle"], ann, reads[:1000], blocks, api.make_config())
+    for rep in range(6):
+        ctx.reset()
+        if rep % 2:
+            ctx.submit(reads[:1000].copy(), blocks)
+            assert_results_equal(ctx.finalize(), want_1000, f"reset {rep}: 1000 reads")
+        else:
+            ctx.submit(reads[:500].copy(), blocks)       # left without a finalize: the next reset follows queued kernels
+            ctx.reset()
+            ctx.submit(reads[:33].copy(), blocks)
+            assert_results_equal(ctx.finalize(), want, f"reset {rep}: 33 reads")
 
 
 @pytest.mark.parametrize("flagset", sorted(KAT_FLAGSETS))
