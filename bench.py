@@ -671,7 +671,7 @@ def run_cli_leg(sa, gtf, tmpdir, n_records, device):
     synth.write_bam(sa, sr, bam, level=1)
     t_write = time.perf_counter() - t
     out = {"records": int(sr.n), "bam_bytes": os.path.getsize(bam), "bam_write_seconds": t_write, "host_cores": os.cpu_count(), "flags": "--coverage"}
-    env = dict(os.environ, RSQ_INGEST_STATS="1")
+    env = dict(os.environ, RSQ_INGEST_STATS="1", RSQ_SETUP_STATS="1")      # stage times of the ingest and of the start-up on stderr
     best = None
     for rep in range(2):
         t = time.perf_counter()
@@ -692,7 +692,7 @@ def run_cli_leg(sa, gtf, tmpdir, n_records, device):
                     pass
     out.update(seconds=best[0], records_per_s=sr.n / best[0], stages=stages,
                bam_loop_records_per_s=(sr.n / stages["bam_loop_s"]) if stages.get("bam_loop_s") else None,
-               ingest_stats=[l for l in best[2].splitlines() if l.startswith("ingest busy seconds")][-4:])
+               ingest_stats=[l for l in best[2].splitlines() if l.startswith(("ingest busy seconds", "load_gtf:", "rsq_set_annotation:"))][-16:])
     return out
 
 

@@ -8,7 +8,8 @@ namespace rsqh {
 namespace {
 
 // ---- decode-table entries ------------------------------------------------------------------------------------------------------
-//   bits  0..7   code length in bits (sub-table entries: the WHOLE code, root bits included)
+//   bits  0..7   bits to consume: code length (sub-table entries: the WHOLE code, root bits included) + extra bits — one shift
+//                takes both off the bit buffer, the extra bits are read from a copy (off the critical path)
 //   bits  8..11  number of extra bits (lengths, distances) / index bits of the sub-table (pointers)
 //   bits 12..15  kind flags
 //   bits 16..31  literal byte / base length / base distance / offset of the sub-table
@@ -24,7 +25,7 @@ const uint8_t kPreOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 1
 
 enum Kind { kPrecode, kLitLen, kDist };
 
-inline uint32_t symbol_entry(Kind kind, int sym) {
+inline uint32_t make_symbol_entry(Kind kind, int sym) {
     if (kind == kPrecode) return (uint32_t)sym << 16;
     if (kind == kLitLen) {
         if (sym < 256) return ((uint32_t)sym << 16) | kLit;
@@ -36,12 +37,26 @@ inline uint32_t symbol_entry(Kind kind, int sym) {
     return kBad;
 }
 
-inline uint32_t reverse_bits(uint32_t code, int len) {
-    code = ((code & 0x5555u) << 1) | ((code >> 1) & 0x5555u);
-    code = ((code & 0x3333u) << 2) | ((code >> 2) & 0x3333u);
-    code = ((code & 0x0f0fu) << 4) | ((code >> 4) & 0x0f0fu);
-    code = ((code & 0x00ffu) << 8) | ((code >> 8) & 0x00ffu);
-    return code >> (16 - len);
+// entry templates per alphabet and the byte-reversal table, built once
+struct Constants {
+    uint32_t entry[3][288];
+    uint8_t rev8[256];
+    Constants() {
+        for (int k = 0; k < 3; ++k)
+            for (int s = 0; s < 288; ++s) entry[k][s] = make_symbol_entry((Kind)k, s);
+        for (int v = 0; v < 256; ++v) {
+            int r = 0;
+            for (int b = 0; b < 8; ++b) r |= ((v >> b) & 1) << (7 - b);
+            rev8[v] = (uint8_t)r;
+        }
+    }
+};
+const Constants kConst;
+
+inline uint32_t symbol_entry(Kind kind, int sym) { return kConst.entry[kind][sym]; }
+
+inline uint32_t reverse_bits(uint32_t code, int len) {                 // len <= 15
+    return (((uint32_t)kConst.rev8[code & 0xffu] << 8) | kConst.rev8[code >> 8]) >> (16 - len);
 }
 
 // Canonical Huffman code of `n` symbols -> a root table of 2^root entries indexed by the next stream bits (LSB first) and, for
@@ -63,7 +78,8 @@ bool build_table(const uint8_t* lens, int n, Kind kind, int root, uint32_t* tabl
         if (used != 1 || count[1] != 1) return false;
         int sym = 0;
         while (lens[sym] != 1) ++sym;
-        for (int i = 0; i < n_root; i += 2) { table[i] = symbol_entry(kind, sym) | 1u; table[i + 1] = kBad | 1u; }
+        const uint32_t t = symbol_entry(kind, sym);
+        for (int i = 0; i < n_root; i += 2) { table[i] = t | (1u + ((t >> 8) & 15u)); table[i + 1] = kBad | 1u; }
         return true;
     }
     uint32_t next[16];
@@ -83,7 +99,7 @@ bool build_table(const uint8_t* lens, int n, Kind kind, int root, uint32_t* tabl
         const uint32_t rev = reverse_bits(next[l]++, l);
         rev_of[s] = rev;
         if (l <= root) {
-            const uint32_t e = symbol_entry(kind, s) | (uint32_t)l;
+            const uint32_t t = symbol_entry(kind, s), e = t | ((uint32_t)l + ((t >> 8) & 15u));
             for (int i = (int)rev; i < n_root; i += 1 << l) table[i] = e;
         } else {
             uint8_t& m = longest[rev & (uint32_t)(n_root - 1)];
@@ -106,7 +122,7 @@ bool build_table(const uint8_t* lens, int n, Kind kind, int root, uint32_t* tabl
         const uint32_t rev = rev_of[s], ptr = table[rev & (uint32_t)(n_root - 1)];
         const int size = 1 << ((ptr >> 8) & 15);
         uint32_t* sub = table + (ptr >> 16);
-        const uint32_t e = symbol_entry(kind, s) | (uint32_t)l;
+        const uint32_t t = symbol_entry(kind, s), e = t | ((uint32_t)l + ((t >> 8) & 15u));
         for (int i = (int)(rev >> root); i < size; i += 1 << (l - root)) sub[i] = e;
     }
     return true;
@@ -178,16 +194,16 @@ bool huffman_block(Bits& b, const uint32_t* lt, const uint32_t* dt, uint8_t* con
                 break;
             }
             // a match: length code (<= 15 + 5 bits) and distance code (<= 15 + 13 bits) fit the 56 bits of one refill
-            RSQ_DROP((int)(e & 0xffu));
-            const int lx = (int)((e >> 8) & 15u);
-            const uint32_t length = (e >> 16) + ((uint32_t)buf & ((1u << lx) - 1u));
-            RSQ_DROP(lx);
+            const uint64_t at_len = buf;
+            RSQ_DROP((int)(e & 0xffu));                                   // code + extra bits in one shift
             const uint32_t d = lookup(dt, kDistRoot, buf);
+            const int lx = (int)((e >> 8) & 15u);
+            const uint32_t length = (e >> 16) + ((uint32_t)(at_len >> ((e & 0xffu) - lx)) & ((1u << lx) - 1u));
             if (__builtin_expect(d & kBad, 0)) { ok = false; break; }
+            const uint64_t at_dist = buf;
             RSQ_DROP((int)(d & 0xffu));
             const int dx = (int)((d >> 8) & 15u);
-            const uint32_t dist = (d >> 16) + ((uint32_t)buf & ((1u << dx) - 1u));
-            RSQ_DROP(dx);
+            const uint32_t dist = (d >> 16) + ((uint32_t)(at_dist >> ((d & 0xffu) - dx)) & ((1u << dx) - 1u));
             if (__builtin_expect((size_t)dist > (size_t)(out - out_begin), 0)) { ok = false; break; }
             const uint8_t* src = out - dist;
             uint8_t* dst = out;
@@ -216,24 +232,24 @@ bool huffman_block(Bits& b, const uint32_t* lt, const uint32_t* dt, uint8_t* con
     for (;;) {
         b.refill();
         const uint32_t e = lookup(lt, kLitRoot, b.buf);
-        const int len = (int)(e & 0xffu);
+        const int len = (int)(e & 0xffu);                              // code and extra bits together
         if ((e & kBad) || b.cnt < len) return false;
-        b.drop(len);
         if (e & kLit) {
             if (out == out_end) return false;
+            b.drop(len);
             *out++ = (uint8_t)(e >> 16);
             continue;
         }
-        if (e & kEob) { out_io = out; return true; }
-        uint32_t x;
-        if (!b.take((int)((e >> 8) & 15u), x)) return false;
-        const uint32_t length = (e >> 16) + x;
+        if (e & kEob) { b.drop(len); out_io = out; return true; }
+        const int lx = (int)((e >> 8) & 15u);
+        const uint32_t length = (e >> 16) + ((uint32_t)(b.buf >> (len - lx)) & ((1u << lx) - 1u));
+        b.drop(len);
         const uint32_t d = lookup(dt, kDistRoot, b.buf);
         const int dl = (int)(d & 0xffu);
         if ((d & kBad) || b.cnt < dl) return false;
+        const int dx = (int)((d >> 8) & 15u);
+        const uint32_t dist = (d >> 16) + ((uint32_t)(b.buf >> (dl - dx)) & ((1u << dx) - 1u));
         b.drop(dl);
-        if (!b.take((int)((d >> 8) & 15u), x)) return false;
-        const uint32_t dist = (d >> 16) + x;
         if ((size_t)dist > (size_t)(out - out_begin) || (size_t)length > (size_t)(out_end - out)) return false;
         const uint8_t* src = out - dist;
         for (uint32_t k = 0; k < length; ++k) out[k] = src[k];
