@@ -71,7 +71,11 @@ $(ODIR)/rnaseqc_oracle: $(HOST_OBJS) $(OBJDIR)/host/cli_main.o $(ODIR)/librsq_or
 	$(CXX) -o $@ $(HOST_OBJS) $(OBJDIR)/host/cli_main.o -L$(ODIR) -lrsq_oracle -lz -lpthread -Wl,-rpath,'$$ORIGIN'
 
 # host-side measurement tool: BAM ingest records/s by thread count (RSQ_INGEST_STATS=1 prints the busy time of every stage)
-tools: $(OBJDIR)/decode_bench
+tools: $(OBJDIR)/decode_bench $(OBJDIR)/inflate_bench
+# zlib against the ingest's own DEFLATE decoder on the BGZF blocks of a BAM, one thread
+$(OBJDIR)/inflate_bench: tools/inflate_bench.cpp rnaseqc_b200/csrc/host/fastinflate.cpp rnaseqc_b200/csrc/host/fastinflate.h
+	@mkdir -p $(OBJDIR)
+	$(CXX) -std=c++17 -O2 -Irnaseqc_b200/csrc/host -o $@ tools/inflate_bench.cpp rnaseqc_b200/csrc/host/fastinflate.cpp -lz
 $(OBJDIR)/decode_bench: tools/decode_bench.cpp $(HOST_OBJS)
 	$(CXX) $(CXXFLAGS) -o $@ tools/decode_bench.cpp $(filter-out $(OBJDIR)/host/report.o $(OBJDIR)/host/pipeline.o,$(HOST_OBJS)) -lz -lpthread
 

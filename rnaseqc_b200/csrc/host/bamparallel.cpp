@@ -19,7 +19,7 @@
 //                   and appends to the caller's batch
 // Nothing before the consumer needs the annotation: start() runs all of it while the GTF is parsed and the device comes up.
 // A job hands its 4 MB inflate buffer back as soon as its records are converted, so the jobs waiting for the consumer cost
-// about 1 MB each and the run-ahead can be deep (max_jobs_ahead_).
+// about 1 MB each and the run-ahead can be deep (max_jobs_ahead_: 3072 jobs, ~45 M records of 150 bp reads).
 #include "bamparallel.h"
 #include "fastinflate.h"
 
@@ -190,7 +190,7 @@ ParallelBamDecoder::ParallelBamDecoder(const std::string& path, int n_threads)
         std::fseek(fp_, 0, SEEK_SET);
     }
     max_jobs_in_flight_ = (size_t)n_threads_ * 3 + 4;
-    max_jobs_ahead_ = 1536;                                        // ~1.5 GB of converted records at most
+    max_jobs_ahead_ = 3072;                                        // ~3 GB of converted records at most
     if (const char* e = std::getenv("RSQ_INGEST_AHEAD_JOBS")) max_jobs_ahead_ = (size_t)std::max(1L, std::atol(e));
     max_jobs_ahead_ = std::max(max_jobs_ahead_, max_jobs_in_flight_);
     speculate_ = !std::getenv("RSQ_INGEST_NO_SPECULATION");

@@ -28,7 +28,7 @@ public:
     const AlnHeader& header() const { return hdr_; }
     // Starts the reader and the workers NOW: inflate, framing and conversion need only the command line's decode options and the
     // BAM header, so the CLI calls this before it parses the GTF and brings the device up — by the time the first batch is asked
-    // for, up to `ahead` jobs (~1 MB of converted records each) are waiting.  next_batch() starts them itself otherwise.  The
+    // for, up to max_jobs_ahead_ jobs (~1 MB of converted records each; RSQ_INGEST_AHEAD_JOBS) are waiting.  next_batch() starts them itself otherwise.  The
     // Decoder handed to next_batch() must have been built with the same options.
     void start(const DecodeOptions& opt);
     // Appends up to max_records converted records (with their blocks) to the cleared vectors, in file order, running
