@@ -7,6 +7,7 @@
 #include "report.h"
 
 #include <algorithm>
+#include <chrono>
 #include <charconv>
 #include <climits>
 #include <cmath>
@@ -61,7 +62,14 @@ Stats get_statistics(std::vector<double>& data) {
     return Stats{avg, median, sd, med_dev};
 }
 
+// `stream << v` with the stream's defaults is printf's %g (precision 6); std::to_chars(general, 6) prints the same digits without
+// the stream machinery (the report writer formats about a million numbers); non-finite values keep the stream's spelling
 std::string fmt_default(double v) {
+    if (std::isfinite(v)) {
+        char num[64];
+        const auto r = std::to_chars(num, num + sizeof num, v, std::chars_format::general, 6);
+        return std::string(num, r.ptr);
+    }
     std::ostringstream s;
     s << v;
     return s.str();
@@ -219,6 +227,14 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         throw HostError(8, std::string("Filesystem error:  ") + e.what());
     }
     const std::string base = opt.output_dir + "/" + opt.sample_name;
+    const bool setup_stats = getenv("RSQ_SETUP_STATS") != nullptr;          // stage times of the report writer on stderr
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!setup_stats) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "write_reports: %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_mark).count());
+        t_mark = now;
+    };
     uint64_t C[RSQ_N_COUNTERS];
     for (int i = 0; i < RSQ_N_COUNTERS; ++i) C[i] = R.counters[i];
     // counter.increment("Total Alignments", alignmentCount): the int parameter truncates (src/RNASeQC.cpp:397,
@@ -255,14 +271,17 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
     // ---- coverage statistics (the reference computes them as genes leave the window) -------------------------
     CoverageSummary cov;
     compute_coverage_summary(A, R, opt, st, cov);
+    lap("coverage summary");
     {
         std::ofstream w(opt.write_coverage ? base + ".coverage.tsv" : std::string("/dev/null"));
         if (!w.is_open() && opt.write_coverage) throw HostError(-1, "Unable to open BaseCoverage output file");
         w << "gene_id\tcoverage_mean\tcoverage_std\tcoverage_CV" << '\n';     // src/Metrics.h:113
         for (const std::string& r : cov.rows) w << r << '\n';
     }
+    lap("coverage.tsv");
     const unsigned min_reads = library_complexity((double)C[RSQ_C_DUPLICATE_PAIRS], (double)C[RSQ_C_UNIQUE_FRAGMENTS],
                                                   opt.exact_complexity_scan);
+    lap("library complexity");
     // ---- gene tables (src/RNASeQC.cpp:419-475) -----------------------------------------------------------------
     unsigned genes_detected = 0;
     unsigned bias_genes = 0;
@@ -284,14 +303,23 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         const double scale_rpkm = (double)C[RSQ_C_EXONIC_READS] / 1000000.0;
         double scale_tpm = 0.0;
         std::vector<double> tpms(A.gene_list.size(), 0.0);
+        // rows are formatted into buffers (std::to_chars prints what `<<` and `<< std::fixed <<` print, without the stream machinery)
+        std::string b_reads, b_frag, b_rpkm;
+        b_reads.reserve(A.gene_list.size() * 48); b_frag.reserve(A.gene_list.size() * 48); b_rpkm.reserve(A.gene_list.size() * 56);
+        char num[400];
+        auto put_long = [&](std::string& b, long v) { const auto r = std::to_chars(num, num + sizeof num, v); b.append(num, r.ptr); };
+        auto put_fixed = [&](std::string& b, double v) {
+            if (std::isfinite(v)) { const auto r = std::to_chars(num, num + sizeof num, v, std::chars_format::fixed, 6); b.append(num, r.ptr); }
+            else { std::ostringstream o; o << std::fixed << v; b += o.str(); }
+        };
         for (size_t i = 0; i < A.gene_list.size(); ++i) {
             const uint32_t g = A.gene_list[i];
             const double count = (double)R.gene_reads[g];
-            gene_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_reads[g] << '\n';
-            fragment_report << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << (long)R.gene_fragments[g] << '\n';
+            b_reads += A.gene_ids[g]; b_reads += '\t'; b_reads += A.gene_desc[g]; b_reads += '\t'; put_long(b_reads, (long)R.gene_reads[g]); b_reads += '\n';
+            b_frag += A.gene_ids[g]; b_frag += '\t'; b_frag += A.gene_desc[g]; b_frag += '\t'; put_long(b_frag, (long)R.gene_fragments[g]); b_frag += '\n';
             if (opt.use_rpkm) {
                 double rpkm = (1000.0 * count / scale_rpkm) / (double)A.gene_coding_len[g];
-                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << rpkm << '\n';
+                b_rpkm += A.gene_ids[g]; b_rpkm += '\t'; b_rpkm += A.gene_desc[g]; b_rpkm += '\t'; put_fixed(b_rpkm, rpkm); b_rpkm += '\n';
             } else {
                 double tpm = (1000.0 * count) / (double)A.gene_coding_len[g];
                 tpms[i] = tpm;
@@ -306,10 +334,14 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             scale_tpm /= 1000000.0;
             for (size_t i = 0; i < A.gene_list.size(); ++i) {
                 const uint32_t g = A.gene_list[i];
-                gene_rpkm << A.gene_ids[g] << "\t" << A.gene_desc[g] << "\t" << tpms[i] / scale_tpm << '\n';
+                b_rpkm += A.gene_ids[g]; b_rpkm += '\t'; b_rpkm += A.gene_desc[g]; b_rpkm += '\t'; put_fixed(b_rpkm, tpms[i] / scale_tpm); b_rpkm += '\n';
             }
         }
+        gene_report.write(b_reads.data(), (std::streamsize)b_reads.size());
+        fragment_report.write(b_frag.data(), (std::streamsize)b_frag.size());
+        gene_rpkm.write(b_rpkm.data(), (std::streamsize)b_rpkm.size());
     }
+    lap("gene tables");
     // ---- 3'/5' ratio statistics (src/RNASeQC.cpp:478-508) ------------------------------------------------------
     double ratio_avg = 0.0, ratio_mad = 0.0, ratio_median = 0.0, ratio_std = 0.0, ratio75 = 0.0, ratio25 = 0.0;
     if (ratios.size() > 1) {
@@ -425,6 +457,7 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
             output << "Fragment Length MAD_Std\t" << fragment_mad << '\n';
         }
     }
+    lap("metrics rows, fragment sizes");
     // ---- coverage medians and exon_cv.tsv (src/RNASeQC.cpp:609-659) --------------------------------------------
     {
         std::vector<double> means = cov.gene_means, stds = cov.gene_stds, cvs;
@@ -438,31 +471,43 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         output << "Median of Transcript Coverage Std\t" << median_quirk(n_transcripts, [&](unsigned long i) { return stds[i]; }) << '\n';
         output << "Median of Transcript Coverage CV\t" << (n_cvs ? median_quirk(n_cvs, [&](unsigned long i) { return cvs[i]; }) : 0.0) << '\n';
         const bool fasta = ref && ref->open;
+        // exonCoverage is a std::map keyed by exon id: rows in key order, later entries of one id overwrite earlier ones — here a
+        // stable sort of pointers into the id table and the last entry of every run of equal ids
+        std::vector<const std::pair<std::string, double>*> by_id;
+        by_id.reserve(cov.exon_cvs.size());
+        for (auto& kv : cov.exon_cvs) by_id.push_back(&kv);
+        std::stable_sort(by_id.begin(), by_id.end(), [](const std::pair<std::string, double>* a, const std::pair<std::string, double>* b) { return a->first < b->first; });
         std::map<std::string, uint32_t> slot_of;
         if (fasta) for (size_t e = 0; e < A.exon_ids.size(); ++e) slot_of[A.exon_ids[e]] = (uint32_t)e;
-        std::map<std::string, double> exon_cov;  // exonCoverage: later entries overwrite
-        for (auto& kv : cov.exon_cvs) exon_cov[kv.first] = kv.second;
         std::ofstream cv_report(base + ".exon_cv.tsv");
         cv_report << "Exon ID\tExon CV";
         if (fasta) cv_report << "\tGC Content";
         cv_report << '\n';
         std::vector<double> total_exon_cv;
-        for (auto& kv : exon_cov) {
-            cv_report << kv.first << "\t" << kv.second;
+        total_exon_cv.reserve(by_id.size());
+        std::string buf;
+        buf.reserve(1 << 20);
+        for (size_t k = 0; k < by_id.size(); ++k) {
+            if (k + 1 < by_id.size() && by_id[k + 1]->first == by_id[k]->first) continue;      // overwritten by a later entry
+            const std::pair<std::string, double>& kv = *by_id[k];
+            buf += kv.first; buf += '\t'; buf += fmt_default(kv.second);
             if (fasta) {
                 // gc(getSeq(chromosome, start, start + length)) with the 1-based GTF start used as a 0-based offset (src/Metrics.cpp:299-302)
                 const uint32_t s = slot_of[kv.first];
                 const double g = ref->present.size() > A.exon_contig[s] && ref->present[A.exon_contig[s]]
                                      ? ref->gc_content(A.exon_contig[s], A.exon_start[s], A.exon_start[s] + A.exon_len[s]) : -1.0;
-                cv_report << "\t" << g;
+                buf += '\t'; buf += fmt_default(g);
             }
-            cv_report << '\n';
+            buf += '\n';
+            if (buf.size() > (1 << 20) - 4096) { cv_report.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
             total_exon_cv.push_back(kv.second);
         }
+        cv_report.write(buf.data(), (std::streamsize)buf.size());
         Stats cs = get_statistics(total_exon_cv);
         output << "Median Exon CV\t" << cs.med << '\n';
         output << "Exon CV MAD\t" << cs.mad << '\n';
     }
+    lap("exon_cv.tsv");
     if (ref && ref->open) {                                                          // src/RNASeQC.cpp:660-674
         std::ofstream gc_report(base + ".gc_content.tsv");
         gc_report << "Content Bin\tCount" << '\n';
@@ -493,6 +538,8 @@ void write_reports(const Annotation& A, const HostResults& R, const RunOptions& 
         output << "Fragment GC Content Kurtosis\t" << s_kurt << '\n';
     }
     output.close();
+    if (exon_table.valid()) exon_table.wait();
+    lap("rest + exon_reads.gct (thread)");
 }
 
 }  // namespace rsqh
