@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "alnreader.h"
@@ -34,6 +35,9 @@ int main(int argc, char** argv) {
         Decoder dec(pb.header(), contigs, contigs.names.size(), opt);
         std::vector<rsq_read> R; std::vector<rsq_block> B;
         R.resize(1u << 20); B.resize(3u << 20); R.clear(); B.clear();     // like the CLI's batch buffers after their first batch: mapped
+        // RSQ_BENCH_PREDECODE=<seconds>: start the workers first and let them run ahead for that long (as the CLI does while it parses
+        // the GTF and brings the device up): the loop below then measures the consumer alone
+        if (const char* e = std::getenv("RSQ_BENCH_PREDECODE")) { pb.start(opt); std::this_thread::sleep_for(std::chrono::milliseconds((long)(std::atof(e) * 1000))); }
         auto t0 = clk::now();
         size_t n = 0;
         std::vector<rsq_read_packed> P(1u << 20);
