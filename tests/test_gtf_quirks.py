@@ -177,3 +177,39 @@ def test_bed_files_match_the_reference(libs, tmp_path, name):
     if pr.returncode == 0:
         identical = set(compare_outputs(os.path.join(d, "ref"), os.path.join(d, "ours")))
         assert {"q.sam.gene_reads.gct", "q.sam.fragmentSizes.txt"} <= identical, identical
+
+
+def test_alignment_file_errors_keep_their_place_behind_the_annotation(libs, tmp_path):
+    """The CLI starts the BAM ingest before it parses the GTF (csrc/host/pipeline.cpp); what goes wrong with the alignment file is still
+    reported where the reference opens it — after the GTF and the BED (src/RNASeQC.cpp:105-219) — with the reference's exit codes."""
+    import gzip
+    import shutil
+    from rnaseqc_b200 import synth
+    d = str(tmp_path)
+    gtf = os.path.join(d, "a.gtf")
+    with open(gtf, "w") as f:
+        f.write("\n".join(BASE) + "\n")
+    bad_gtf = os.path.join(d, "bad.gtf")
+    with open(bad_gtf, "w") as f:
+        f.write("\n".join(BASE + [BASE[0]]) + "\n")                      # gene id twice: exit 11
+    sa = synth.make_annotation(seed=5, n_genes=20, contig_names=["chr1"], contig_lens=[1_000_000])
+    good = os.path.join(d, "good.bam")
+    synth.write_bam(sa, synth.simulate_reads(sa, 500, seed=6), good, level=1)
+    not_bam = os.path.join(d, "text.bam")                                 # gzip magic, no BAM inside
+    with gzip.open(not_bam, "wb") as f:
+        f.write(b"hello, this is not a BAM file\n" * 100)
+    truncated = os.path.join(d, "cut.bam")
+    shutil.copy(good, truncated)
+    with open(truncated, "r+b") as f:
+        f.truncate(os.path.getsize(good) // 2)
+    missing = os.path.join(d, "nothing_here.bam")
+    for k, (g, b) in enumerate([(gtf, good), (gtf, missing), (bad_gtf, missing), (bad_gtf, not_bam), (gtf, not_bam), (bad_gtf, good), (gtf, truncated)]):
+        pr = run_cli(REF, g, b, os.path.join(d, f"ref{k}"), check=False)
+        for threads in ("0", "3"):
+            po = run_cli(libs["oracle_cli"], g, b, os.path.join(d, f"ours{k}_{threads}"), "--decode-threads", threads, check=False)
+            if os.path.basename(b) in ("text.bam", "cut.bam") and os.path.basename(g) == "a.gtf":
+                assert (pr.returncode != 0) == (po.returncode != 0), (g, b, threads, pr.returncode, po.returncode)   # htslib words its own failures
+            else:
+                assert pr.returncode == po.returncode, (g, b, threads, pr.returncode, po.returncode, pr.stderr[-300:], po.stderr[-300:])
+        if pr.returncode == 0:
+            compare_outputs(os.path.join(d, f"ref{k}"), os.path.join(d, f"ours{k}_3"))
