@@ -292,7 +292,18 @@ int run_sample(const Backend& be, CliOptions& opt) {
             L.creating = std::async(std::launch::async, [&be, &opt, &L] {
                 rsq_config cfg = opt.cfg;
                 cfg.device = L.device;
-                return be.create(&cfg, &L.ctx);
+                const int rc = be.create(&cfg, &L.ctx);
+                if (rc == RSQ_OK) {
+                    // the lane's page-locked staging buffers, sized for a full batch of two-block records: page-locking ~80 MB takes
+                    // tens of milliseconds each, which the main thread used to spend inside its first three batches
+                    const size_t n = opt.batch_records;
+                    const size_t est = std::max(rsq_compact_bound(n, 2 * n), 48 * n + 16 * n + 16);
+                    for (int s = 0; s < Lane::kSlots; ++s) {
+                        L.pinned[s] = be.host_alloc(est);
+                        L.cap[s] = L.pinned[s] ? est : 0;             // no room now: acquire() asks again, and reports it
+                    }
+                }
+                return rc;
             });
         }
         // So does the BAM ingest: inflating, framing and converting records needs the command line and the BAM header only
