@@ -170,10 +170,11 @@ int parse_cli(int argc, char** argv, CliOptions& opt) {
         std::cerr << "At most 8 --tag filters are supported" << std::endl;
         return 6;
     }
-    // what rsq_coverage_statistics accepts: refused here, before hours of alignments are processed (the reference takes any
-    // --window-size; with a negative --offset its window loops run over an unsigned wrap-around and it ends in a range_error)
-    if (opt.run.bias_window < 1 || opt.run.bias_window > 8192 || opt.run.bias_offset < 0) {
-        std::cerr << "Argument validation error: --window-size must be between 1 and 8192 and --offset must not be negative in this build" << std::endl;
+    // what rsq_coverage_statistics accepts: refused here, before hours of alignments are processed (with --window-size 0 the
+    // reference dies of an empty median as soon as a gene gets that far; with a negative --offset its window loops run over an
+    // unsigned wrap-around, read past the end of the coverage vector and end the same way)
+    if (opt.run.bias_window < 1 || opt.run.bias_offset < 0) {
+        std::cerr << "Argument validation error: --window-size must be at least 1 and --offset must not be negative in this build" << std::endl;
         return 6;
     }
     opt.cfg.n_filter_tags = (uint32_t)opt.decode.filter_tags.size();

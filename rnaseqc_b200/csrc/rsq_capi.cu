@@ -67,6 +67,8 @@ struct Ctx {
     unsigned long long* cs_off = nullptr; uint32_t *cs_eoff = nullptr, *cs_len = nullptr, *cs_slot = nullptr; uint8_t* cs_strand = nullptr;
     double* cs_out = nullptr; unsigned long long* cs_ends = nullptr;   // one allocation: mean | std | cv | exon_cv | five | three
     uint8_t* cs_owned = nullptr;
+    double* cs_big = nullptr;                 // window scratch of the wide-window statistics kernel
+    size_t cs_big_elems = 0;
     size_t cs_cap_genes = 0, cs_cap_refs = 0;
     size_t export_words = 0;
     unsigned long long* d_hist = nullptr;
@@ -492,7 +494,7 @@ void rsq_destroy(rsq_ctx* ctx) {
     Accum& a = c->acc;
     void* ptrs[] = {a.gc_keys, a.gc_first, a.gc_second, a.gc_payload, a.pair_second, a.mate_left, a.mate_left_count, a.mate_totals, a.gc_cand, a.gc_cand_count, a.gc_hist, a.counters, a.gene_reads, a.gene_unique, a.gene_fragments, a.exon_whole, a.exon_fhi, a.exon_flo, c->d_exon_out, a.cov_diff, a.frag_set,
                     a.algo_bytes, a.error_flag, a.pair_keys, a.pair_first, a.pair_payload, a.cand, a.cand_count, a.sample_flag,
-                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_owned, c->d_found, c->d_hist, c->d_pair_scratch,
+                    a.sample_isize, a.sample_vals, a.sample_count, c->d_cov, c->d_scan, c->d_export, c->cs_off, c->cs_eoff, c->cs_len, c->cs_slot, c->cs_strand, c->cs_out, c->cs_owned, c->cs_big, c->d_found, c->d_hist, c->d_pair_scratch,
                     c->d_reads[0], c->d_reads[1], c->d_blocks[0], c->d_blocks[1], c->d_packed[0], c->d_packed[1], c->d_xblocks[0], c->d_xblocks[1],
                     c->d_up_tot, c->d_up_expl, c->d_up_scan, c->d_compact[0], c->d_compact[1]};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -1002,7 +1004,7 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c || !q || !out || !c->have_ann || q->struct_size != sizeof(rsq_transcripts) || out->struct_size != sizeof(rsq_coverage_stats))
         return RSQ_ERR_INVALID;
-    if (q->bias_offset < 0 || q->bias_window < 1 || q->bias_window > 8192) { c->err = "bias offset/window out of range (offset >= 0, window 1..8192)"; return RSQ_ERR_INVALID; }
+    if (q->bias_offset < 0 || q->bias_window < 1) { c->err = "bias offset/window out of range (offset >= 0, window >= 1)"; return RSQ_ERR_INVALID; }
     CU_TRY(cudaSetDevice(c->cfg.device));
     CU_TRY(cudaStreamSynchronize(c->copy_stream));
     cudaStream_t st = c->stream;
@@ -1037,9 +1039,28 @@ int rsq_coverage_statistics(rsq_ctx* ctx, const rsq_transcripts* q, rsq_coverage
         c->launches += launch_coverage_scan(c->acc.cov_diff, c->d_cov, c->cov_len + 1, c->d_scan, st);
     else
         CU_TRY(cudaMemsetAsync(c->d_cov, 0, 4ull * (c->cov_len + 1), st));
+    unsigned big_ctas = 0, big_cap = 0;
+    if (coverage_stats_needs_scratch(q->bias_window) && ng) {          // windows beyond shared memory: scratch in global memory
+        unsigned long long longest = 0;
+        for (size_t g = 0; g < ng; ++g) {
+            unsigned long long T = 0;
+            for (uint32_t e = q->gene_exon_off[g]; e < q->gene_exon_off[g + 1]; ++e) T += q->exon_len[e];
+            longest = std::max(longest, T);
+        }
+        big_cap = big_window_cap(q->bias_window, longest);
+        big_ctas = (unsigned)std::min<size_t>(ng, 296);
+        const size_t need = (size_t)big_ctas * 2 * big_cap;
+        if (need > c->cs_big_elems) {
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(c->cs_big);
+            c->cs_big = nullptr; c->cs_big_elems = 0;
+            CU_TRY(cudaMalloc(&c->cs_big, 8 * need));
+            c->cs_big_elems = need;
+        }
+    }
     c->launches += launch_coverage_stats(c->d_cov, (uint32_t)ng, d_off, d_eoff, d_strand, d_len, d_slot, q->coverage_mask, q->bias_offset,
                                          q->bias_window, q->bias_gene_length, d_mean, d_std, d_cv, d_ends, d_ends + c->cs_cap_genes,
-                                         d_ecv, (uint32_t)ne, d_owned, !d_owned || c->part_rank == 0, st);
+                                         d_ecv, (uint32_t)ne, d_owned, !d_owned || c->part_rank == 0, c->cs_big, big_ctas, big_cap, st);
     if (d_owned && c->comm) {   // owner-gather as a bitwise sum: every value has exactly one non-zero contributor
         if (ng < c->cs_cap_genes) {            // the unused tails of the five per-gene arrays travel too: keep them defined
             for (int k = 0; k < 3; ++k) CU_TRY(cudaMemsetAsync(d_out + k * c->cs_cap_genes + ng, 0, 8 * (c->cs_cap_genes - ng), st));

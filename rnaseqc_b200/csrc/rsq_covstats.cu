@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "rsq_device.h"
 
@@ -21,7 +22,7 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kMaxWindow = 8192;          // bias windows are sorted in shared memory: 2 x 8 bytes x the next power of two
+constexpr int kMaxWindow = 8192;          // bias windows up to this are sorted in shared memory (2 x 8 bytes x the next power of two), wider ones in global scratch
 constexpr int kWarpWindow = 128;          // ... the warp-per-gene kernel keeps its windows below this
 constexpr unsigned long long kWarpGeneMax = 6144;   // stitched transcripts up to this length go one warp each (no block barriers)
 
@@ -228,7 +229,40 @@ __device__ void gene_statistics(const unsigned int* __restrict__ cov, uint32_t g
     }
 }
 
-// which == 0: one warp per gene, the genes with short transcripts and bias windows up to kWarpWindow; which == 1: one CTA per
+// One gene line by one team (a warp or a CTA): whose gene is it, is it owned, then the statistics.  `s_win`: two windows of win_cap
+// doubles for this team.  kBig: bias windows beyond what shared memory holds — every gene goes to a CTA whose windows live in global
+// memory (coverage_stats_big_kernel).
+template <int kTeam, bool kBig>
+__device__ __forceinline__ void gene_entry(uint32_t g, const unsigned int* __restrict__ cov, const unsigned long long* __restrict__ gene_cov_off,
+                                           const uint32_t* __restrict__ gene_exon_off, const uint8_t* __restrict__ gene_strand,
+                                           const uint32_t* __restrict__ exon_len, const uint32_t* __restrict__ exon_slot, uint32_t mask, int bias_offset,
+                                           int bias_window, uint32_t bias_gene_length, double* __restrict__ gene_mean, double* __restrict__ gene_std,
+                                           double* __restrict__ gene_cv, unsigned long long* __restrict__ five_end, unsigned long long* __restrict__ three_end,
+                                           double* __restrict__ exon_cv, const uint8_t* __restrict__ gene_owned, unsigned long long* s_u64, double* s_win, unsigned win_cap) {
+    const unsigned tid = Team<kTeam>::tid();
+    const uint32_t e0 = gene_exon_off[g], e1 = gene_exon_off[g + 1];
+    unsigned long long T = 0;
+    for (uint32_t e = e0; e < e1; ++e) T += exon_len[e];
+    if (!kBig) {
+        const bool warp_sized = T <= kWarpGeneMax && bias_window <= kWarpWindow;
+        if (warp_sized != (kTeam == 32)) return;                   // the other kernel's gene (uniform over the team)
+    }
+    if (gene_owned && !gene_owned[g]) {
+        // another partition owns this gene's reads (rsq_transcripts.gene_owned): all-zero bits, so that the u64 sum over the
+        // partitions is the owner's value
+        for (uint32_t e = e0 + tid; e < e1; e += kTeam) exon_cv[exon_slot[e]] = 0.0;
+        if (tid == 0) { gene_mean[g] = 0.0; gene_std[g] = 0.0; gene_cv[g] = 0.0; five_end[g] = 0ull; three_end[g] = 0ull; }
+        return;
+    }
+    if (gene_owned) {   // the slots this gene does not write below must read "no entry" (NaN) whatever the prefill of this partition was
+        for (uint32_t e = e0 + tid; e < e1; e += kTeam) exon_cv[exon_slot[e]] = CUDART_NAN;
+        Team<kTeam>::sync();
+    }
+    gene_statistics<kTeam>(cov, g, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length,
+                           gene_mean, gene_std, gene_cv, five_end, three_end, exon_cv, T, s_u64, s_win, win_cap);
+}
+
+// kTeam == 32: one warp per gene, the genes with short transcripts and bias windows up to kWarpWindow; kTeam == kThreads: one CTA per
 // gene, the rest.  Both kernels run over all genes and skip the ones that are the other's.
 template <int kTeam>
 __global__ void __launch_bounds__(kThreads)
@@ -243,26 +277,28 @@ coverage_stats_kernel(const unsigned int* __restrict__ cov, uint32_t n_genes, co
     constexpr unsigned kTeams = kThreads / kTeam;
     const uint32_t g = kTeam == 32 ? blockIdx.x * kTeams + (threadIdx.x >> 5) : blockIdx.x;
     if (g >= n_genes) return;
-    const unsigned tid = Team<kTeam>::tid();
-    const uint32_t e0 = gene_exon_off[g], e1 = gene_exon_off[g + 1];
-    unsigned long long T = 0;
-    for (uint32_t e = e0; e < e1; ++e) T += exon_len[e];
-    const bool warp_sized = T <= kWarpGeneMax && bias_window <= kWarpWindow;
-    if (warp_sized != (kTeam == 32)) return;                       // the other kernel's gene (uniform over the team)
-    if (gene_owned && !gene_owned[g]) {
-        // another partition owns this gene's reads (rsq_transcripts.gene_owned): all-zero bits, so that the u64 sum over the
-        // partitions is the owner's value
-        for (uint32_t e = e0 + tid; e < e1; e += kTeam) exon_cv[exon_slot[e]] = 0.0;
-        if (tid == 0) { gene_mean[g] = 0.0; gene_std[g] = 0.0; gene_cv[g] = 0.0; five_end[g] = 0ull; three_end[g] = 0ull; }
-        return;
-    }
-    if (gene_owned) {   // the slots this gene does not write below must read "no entry" (NaN) whatever the prefill of this partition was
-        for (uint32_t e = e0 + tid; e < e1; e += kTeam) exon_cv[exon_slot[e]] = CUDART_NAN;
-        Team<kTeam>::sync();
-    }
     double* s_win = s_dyn + (kTeam == 32 ? (threadIdx.x >> 5) * 2u * win_cap : 0u);
-    gene_statistics<kTeam>(cov, g, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length,
-                           gene_mean, gene_std, gene_cv, five_end, three_end, exon_cv, T, s_u64, s_win, win_cap);
+    gene_entry<kTeam, false>(g, cov, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length,
+                             gene_mean, gene_std, gene_cv, five_end, three_end, exon_cv, gene_owned, s_u64, s_win, win_cap);
+}
+
+// Bias windows above kMaxWindow (the reference accepts any --window-size): a fixed number of CTAs walk over all genes, each with
+// its two windows in a slice of a global scratch buffer (2 x win_cap doubles per CTA; win_cap = the next power of two of the
+// smaller of the window and the longest transcript, rsqd::big_window_cap).  Rare by construction: no attempt at speed.
+__global__ void __launch_bounds__(kThreads)
+coverage_stats_big_kernel(const unsigned int* __restrict__ cov, uint32_t n_genes, const unsigned long long* __restrict__ gene_cov_off,
+                          const uint32_t* __restrict__ gene_exon_off, const uint8_t* __restrict__ gene_strand,
+                          const uint32_t* __restrict__ exon_len, const uint32_t* __restrict__ exon_slot, uint32_t mask, int bias_offset,
+                          int bias_window, uint32_t bias_gene_length, double* __restrict__ gene_mean, double* __restrict__ gene_std,
+                          double* __restrict__ gene_cv, unsigned long long* __restrict__ five_end, unsigned long long* __restrict__ three_end,
+                          double* __restrict__ exon_cv, const uint8_t* __restrict__ gene_owned, double* __restrict__ scratch, unsigned win_cap) {
+    __shared__ unsigned long long s_u64[kThreads / 32];
+    double* s_win = scratch + (size_t)blockIdx.x * 2u * win_cap;
+    for (uint32_t g = blockIdx.x; g < n_genes; g += gridDim.x) {
+        gene_entry<kThreads, true>(g, cov, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length,
+                                   gene_mean, gene_std, gene_cv, five_end, three_end, exon_cv, gene_owned, s_u64, s_win, win_cap);
+        __syncthreads();                                               // the windows and s_u64 are the next gene's
+    }
 }
 
 __global__ void fill_nan_kernel(double* p, uint32_t n) {
@@ -272,15 +308,31 @@ __global__ void fill_nan_kernel(double* p, uint32_t n) {
 
 }  // namespace
 
+// RSQ_COVSTATS_SMEM_WINDOW (tests): a lower limit sends ordinary windows through the global-scratch kernel
+static int smem_window_limit() {
+    const char* e = getenv("RSQ_COVSTATS_SMEM_WINDOW");
+    const int v = e ? atoi(e) : kMaxWindow;
+    return v < 1 || v > kMaxWindow ? kMaxWindow : v;
+}
+bool coverage_stats_needs_scratch(int bias_window) { return bias_window > smem_window_limit(); }
+
 int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsigned long long* gene_cov_off, const uint32_t* gene_exon_off,
                           const uint8_t* gene_strand, const uint32_t* exon_len, const uint32_t* exon_slot, uint32_t mask, int bias_offset,
                           int bias_window, uint32_t bias_gene_length, double* gene_mean, double* gene_std, double* gene_cv,
                           unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons,
-                          const uint8_t* gene_owned, bool nan_prefill, cudaStream_t stream) {
+                          const uint8_t* gene_owned, bool nan_prefill, double* big_scratch, unsigned big_ctas, unsigned big_win_cap,
+                          cudaStream_t stream) {
     int n = 0;
     if (n_exons) {
         if (nan_prefill) { RSQ_LAUNCH(fill_nan_kernel, (n_exons + 255) / 256, 256, 0, stream, exon_cv, n_exons); ++n; }
         else cudaMemsetAsync(exon_cv, 0, 8ull * n_exons, stream);       // partitions other than the first: zero bits
+    }
+    if (n_genes && coverage_stats_needs_scratch(bias_window)) {
+        // windows that do not fit shared memory: global scratch, big_ctas CTAs over all genes (the caller sized both)
+        RSQ_LAUNCH(coverage_stats_big_kernel, big_ctas, kThreads, 0, stream,
+            cov, n_genes, gene_cov_off, gene_exon_off, gene_strand, exon_len, exon_slot, mask, bias_offset, bias_window, bias_gene_length, gene_mean,
+            gene_std, gene_cv, five_end, three_end, exon_cv, gene_owned, big_scratch, big_win_cap);
+        return n + 1;
     }
     if (n_genes) {
         unsigned p2 = 1;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "rsq_b200.h"
 
 // Kernel launches go through one macro so that the CPU test harness (tests/cudaemu: the kernels' own sources compiled for the host,
@@ -223,6 +225,15 @@ int launch_coverage_stats(const unsigned int* cov, uint32_t n_genes, const unsig
                           const uint8_t* gene_strand, const uint32_t* exon_len, const uint32_t* exon_slot, uint32_t mask, int bias_offset,
                           int bias_window, uint32_t bias_gene_length, double* gene_mean, double* gene_std, double* gene_cv,
                           unsigned long long* five_end, unsigned long long* three_end, double* exon_cv, uint32_t n_exons,
-                          const uint8_t* gene_owned, bool nan_prefill, cudaStream_t stream);
+                          const uint8_t* gene_owned, bool nan_prefill, double* big_scratch, unsigned big_ctas, unsigned big_win_cap,
+                          cudaStream_t stream);
+// bias windows too wide for shared memory: the caller provides big_ctas x 2 x big_win_cap doubles of scratch, big_win_cap = big_window_cap(...)
+bool coverage_stats_needs_scratch(int bias_window);
+inline unsigned big_window_cap(int bias_window, unsigned long long longest_transcript) {
+    unsigned long long need = std::min<unsigned long long>((unsigned long long)std::max(bias_window, 1), std::max<unsigned long long>(longest_transcript, 1ull));
+    unsigned p2 = 1;
+    while (p2 < need) p2 <<= 1;
+    return p2;
+}
 
 }  // namespace rsqd

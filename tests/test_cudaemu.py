@@ -70,16 +70,30 @@ def _close(got, want):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(mask=100, bias_window=40, bias_gene_length=120), dict(mask=0, bias_offset=20),
-                                dict(bias_window=300, mask=200), dict(bias_window=129, bias_gene_length=50, mask=0)])
+                                dict(bias_window=300, mask=200), dict(bias_window=129, bias_gene_length=50, mask=0),
+                                dict(bias_window=9000, bias_gene_length=150, mask=0), dict(bias_window=8193, bias_offset=7, bias_gene_length=100)])
 def test_coverage_statistics_kernels_match_oracle(emu, cov_case, kw):
     """windows up to 128 take the warp-per-gene kernel for short transcripts and the CTA kernel for long ones; wider windows send
-    every gene through the CTA kernel with its dynamic shared memory"""
+    every gene through the CTA kernel with its dynamic shared memory, windows above 8192 through the kernel with global scratch"""
     api, ann, ctx, cov = cov_case
     want = ctx.coverage_statistics(ann, **kw)
     got = _emu_stats(emu, api, ann, cov, ann.n_exons, **kw)
     _close(got, want)
-    assert (want["five_end"] > 0).sum() > 3, "bias path not exercised"
+    if kw.get("bias_window", 100) <= 8192:            # (no transcript of this fixture is as long as the two widest windows)
+        assert (want["five_end"] > 0).sum() > 3, "bias path not exercised"
     assert (want["gene_mean"] > 0).sum() > 15
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(bias_window=300, mask=200), dict(mask=0, bias_offset=20, bias_window=129)])
+def test_wide_window_kernel_sorts_in_global_scratch(emu, cov_case, kw, monkeypatch):
+    """--window-size above 8192 (the reference takes any): a few CTAs walk over all genes with their two windows in global memory.
+    The limit is lowered for the test, so that this fixture's transcripts fill and sort such windows."""
+    api, ann, ctx, cov = cov_case
+    want = ctx.coverage_statistics(ann, **kw)
+    monkeypatch.setenv("RSQ_COVSTATS_SMEM_WINDOW", "64")
+    got = _emu_stats(emu, api, ann, cov, ann.n_exons, **kw)
+    _close(got, want)
+    assert (want["five_end"] > 0).sum() > 3, "bias path not exercised"
 
 
 def test_coverage_statistics_ownership_masks_sum_to_the_whole(emu, cov_case):
