@@ -23,6 +23,9 @@
 #include "bamparallel.h"
 #include "fastinflate.h"
 
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -339,6 +342,9 @@ bool ParallelBamDecoder::frame_on_chain(Job& j, size_t begin, size_t end) {
 }
 
 void ParallelBamDecoder::worker_loop() {
+    // The workers fill every core; the thread that matters for the wall clock is the caller's (GTF parse, then the consumer and the
+    // submits).  A few nice levels keep it on a core when there are as many workers as cores (Linux: per-thread priority by tid).
+    if (!std::getenv("RSQ_INGEST_NO_NICE")) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 5);
     std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
         if (stop_) return;
