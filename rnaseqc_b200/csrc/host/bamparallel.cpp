@@ -127,6 +127,7 @@ int plausible_record(const uint8_t* base, size_t p, size_t end, int32_t n_ref) {
 struct ParallelBamDecoder::Job {
     uint64_t id = 0;
     std::vector<uint8_t> comp;
+    size_t comp_bytes = 0;             // comp.size() before the buffer went back to the pool (file-position estimates)
     std::vector<uint32_t> c_off, c_len, u_len;
     std::vector<uint8_t> out;          // [kHeadroom | inflated bytes]
     size_t data_len = 0;
@@ -231,8 +232,13 @@ void ParallelBamDecoder::reader_loop() {
             {   // recycle a consumed job: its buffers are already mapped (fresh 4 MB vectors cost a page fault per page)
                 std::lock_guard<std::mutex> lk(mu_);
                 if (!pool_.empty()) { job = pool_.back(); pool_.pop_back(); }
+                if (job && job->comp.capacity() == 0 && !comp_pool_.empty()) { job->comp = std::move(comp_pool_.back()); comp_pool_.pop_back(); }
             }
-            if (!job) job = std::make_shared<Job>();
+            if (!job) {
+                job = std::make_shared<Job>();
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!comp_pool_.empty()) { job->comp = std::move(comp_pool_.back()); comp_pool_.pop_back(); }
+            }
             job->comp.clear(); job->c_off.clear(); job->c_len.clear(); job->u_len.clear();
             job->reads.clear(); job->rblocks.clear(); job->tids.clear(); job->big.clear();
             job->use_big = false; job->error.clear(); job->error_code = 0; job->state = ST_READ;
@@ -451,6 +457,10 @@ void ParallelBamDecoder::worker_loop() {
             // the records are out of the inflated bytes: the 4 MB buffer goes to the next job, and the reader may read on
             if (todo->out.capacity()) { out_pool_.push_back(std::move(todo->out)); todo->out = std::vector<uint8_t>(); }
             todo->big = std::vector<uint8_t>(); todo->use_big = false;
+            // ... and neither the compressed bytes nor the chain are looked at again: a waiting job keeps its records only
+            todo->comp_bytes = todo->comp.size();
+            if (todo->comp.capacity()) { comp_pool_.push_back(std::move(todo->comp)); todo->comp = std::vector<uint8_t>(); }
+            todo->chain = std::vector<uint32_t>();
             --n_unconverted_;
             cv_consumer_.notify_all();
             cv_reader_.notify_one();
@@ -528,7 +538,7 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
         t_consumer_ += since(t_copy);
         cur_read_ += n;
         if (cur_read_ >= job->reads.size()) {
-            compressed_consumed_ += cur_->comp.size();
+            compressed_consumed_ += cur_->comp_bytes;
             { std::lock_guard<std::mutex> lk(mu_); pool_.push_back(cur_); }
             cur_.reset(); cur_read_ = 0;
         }

@@ -62,6 +62,7 @@ private:
     std::deque<std::shared_ptr<Job>> to_inflate_, to_convert_;   // work lists of the stages that any worker may take, oldest first
     std::vector<std::shared_ptr<Job>> pool_;       // consumed jobs whose buffers are reused
     std::vector<std::vector<uint8_t>> out_pool_;   // 4 MB inflate buffers: a job gives its buffer back once its records are converted
+    std::vector<std::vector<uint8_t>> comp_pool_;  // ... and the buffer of its compressed bytes
     size_t n_unconverted_ = 0;                     // jobs that still hold an inflate buffer (or are about to take one)
     uint64_t next_job_id_ = 0;
     uint64_t next_frame_id_ = 0;       // framing is sequential: the next job id to frame
