@@ -178,6 +178,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
         return memo_gene;
     };
 
+    std::string memo_chr; uint32_t memo_contig = 0; bool memo_chr_ok = false;
     Attrs at;
     size_t lp = 0;
     while (lp < text.size()) {
@@ -189,7 +190,12 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
         size_t cur = 0;
         Span f_chr, f_track, f_type, f_start, f_end, f_score, f_strand, f_frame;
         if (!split_tab(line, cur, f_chr)) throw HostError(11, "Failed to parse the GTF: Unable to parse chromosome. Invalid GTF line: " + line.str());
-        uint32_t contig = A.contigs.get(f_chr.str());
+        if (!(memo_chr_ok && f_chr.n == memo_chr.size() && !memcmp(f_chr.p, memo_chr.data(), f_chr.n))) {   // neighbouring lines share the contig
+            memo_chr.assign(f_chr.p, f_chr.n);
+            memo_contig = A.contigs.get(memo_chr);
+            memo_chr_ok = true;
+        }
+        const uint32_t contig = memo_contig;
         if (!split_tab(line, cur, f_track)) throw HostError(11, "Failed to parse the GTF: Unable to parse track. Invalid GTF line: " + line.str());
         if (!split_tab(line, cur, f_type)) throw HostError(11, "Failed to parse the GTF: Unable to parse feature type. Invalid GTF line: " + line.str());
         enum { T_GENE, T_TRANSCRIPT, T_EXON, T_OTHER } type =
