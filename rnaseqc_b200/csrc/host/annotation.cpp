@@ -165,6 +165,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
     struct IdInfo { std::string name; bool named = false, exon_seen = false; };
     std::unordered_map<std::string, IdInfo> ids;
     ids.reserve(text.size() / 200 + 16);
+    std::vector<const IdInfo*> exon_info;                             // per exon slot: its entry (looked up again for the names below otherwise)
     std::unordered_set<std::string> seen_gene_ids;
     std::map<std::string, unsigned> unnamed_exon_counter;            // exon_names (src/GTF.cpp:27)
     std::vector<GeneFeature> kept_genes;
@@ -244,6 +245,7 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
             if (info->exon_seen)
                 throw HostError(11, "Failed to parse the GTF: Detected non-unique Exon ID: " + cur_feature_id);
             info->exon_seen = true;
+            exon_info.push_back(info);                                                 // elements of an unordered_map stay where they are
             exon_slot = (uint32_t)A.exon_ids.size();
             A.exon_ids.push_back(cur_feature_id);
             A.exon_len.push_back(1 + (end - start));
@@ -293,10 +295,8 @@ void load_gtf(const std::string& path, Annotation& A, bool legacy) {
             if (A.gene_desc[g] == glob) A.gene_flags[g] |= RSQ_GENE_GLOBIN;
     }
     A.exon_desc.assign(A.exon_ids.size(), std::string());
-    for (size_t e = 0; e < A.exon_ids.size(); ++e) {
-        auto it = ids.find(A.exon_ids[e]);
-        if (it != ids.end() && it->second.named) A.exon_desc[e] = it->second.name;
-    }
+    for (size_t e = 0; e < A.exon_ids.size(); ++e)
+        if (exon_info[e]->named) A.exon_desc[e] = exon_info[e]->name;
 
     lap("names");
     // Per contig, list.sort(compIntervalStart) — a stable sort by start over genes and exons interleaved
