@@ -493,17 +493,35 @@ static inline size_t rsq_compact_bound(size_t n_reads, size_t n_blocks) {
     return 256 + 24 * n_tiles + 16 * n_reads + 16 * 65536 + 4 * n_blocks + 48 * max_exc + 8 * n_blocks + 7 * 16;
 }
 
-/* Packs one rsq_submit batch (block_off relative to `blocks`) into a compact batch at `out` (capacity `cap` bytes, 16-byte
- * aligned; rsq_compact_bound says how much is enough).  `scratch` must hold 131072 uint32_t (the dictionary's hash table).
+/* A batch handed over in pieces: the ingest workers convert ~4 MB jobs of the BAM stream on their own, and copying their records
+ * into one array was the serial ceiling of the whole ingest — rsq_pack_compact_segments reads them where they lie.  Each piece has
+ * its own block array (block_off relative to it).  `tids` non-NULL: the records' contig field is not final yet and is taken from
+ * contig_of_tid[tids[i]] (-1 outside [0, n_tids)) — the annotation's contig ids did not exist when the workers converted them. */
+typedef struct rsq_segment {
+    const rsq_read* reads;
+    const int32_t* tids;
+    size_t n_reads;
+    const rsq_block* blocks;
+    size_t n_blocks;
+} rsq_segment;
+
+/* Packs one batch (the concatenation of the segments) into a compact batch at `out` (capacity `cap` bytes, 16-byte aligned;
+ * rsq_compact_bound over the totals says how much is enough).  `scratch` must hold 131072 uint32_t (the dictionary's hash table).
  * Returns RSQ_OK and the bytes written, or RSQ_ERR_INVALID when the batch does not suit the format (too many exceptions, too
- * many blocks for 32-bit offsets, capacity): the caller then uses rsq_submit_packed / rsq_submit. */
-static inline int rsq_pack_compact(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks, void* out, size_t cap,
-                                   uint32_t* scratch, size_t* bytes_out) {
-    const size_t n_tiles = (n_reads + 31) / 32, max_exc = n_reads / 8 + 32;
+ * many blocks for 32-bit offsets, capacity): the caller then uses rsq_submit_packed / rsq_submit.  The bytes do not depend on
+ * how the batch is cut into segments. */
+static inline int rsq_pack_compact_segments(const rsq_segment* segs, size_t n_segs, const int16_t* contig_of_tid, size_t n_tids, void* out,
+                                            size_t cap, uint32_t* scratch, size_t* bytes_out) {
+    size_t n_reads = 0, n_blocks = 0, s_at = 0, k_at = 0;
+    size_t n_tiles, max_exc;
     unsigned char* base = (unsigned char*)out;
     rsq_batch16* H = (rsq_batch16*)out;
     size_t off = 0, t, i, b, n_combos = 0, n_xb = 0, n_exc = 0, n_eb = 0, out_blocks = 0;
     rsq_tile16* tiles; rsq_read16* R; rsq_combo16* D; uint32_t* XB; rsq_read* E; rsq_block* EB;
+    rsq_read tile_reads[32];                 /* the tile's records, gathered from the segments (contig bound) */
+    const rsq_block* tile_blocks[32];        /* ... and where each one's blocks start */
+    for (i = 0; i < n_segs; ++i) { n_reads += segs[i].n_reads; n_blocks += segs[i].n_blocks; }
+    n_tiles = (n_reads + 31) / 32; max_exc = n_reads / 8 + 32;
     if (n_reads >= 0xffffffffu || n_blocks >= 0xffffffffu || cap < rsq_compact_bound(n_reads, n_blocks) || ((size_t)out & 15u)) return RSQ_ERR_INVALID;
 #define RSQ_P16_ALIGN(x) (((x) + 15u) & ~(size_t)15u)
     off = RSQ_P16_ALIGN(sizeof(rsq_batch16));
@@ -519,17 +537,28 @@ static inline int rsq_pack_compact(const rsq_read* reads, size_t n_reads, const 
         const size_t lo = 32 * t, hi = lo + 32 < n_reads ? lo + 32 : n_reads;
         rsq_tile16* T = &tiles[t];
         int32_t bp = 0x7fffffff;
-        const int16_t contig = reads[lo].contig;
-        for (i = lo; i < hi; ++i) if (reads[i].contig == contig && reads[i].pos < bp) bp = reads[i].pos;
+        int16_t contig;
+        for (i = lo; i < hi; ++i) {          /* gather */
+            const rsq_segment* S;
+            rsq_read* q = &tile_reads[i - lo];
+            while (k_at == segs[s_at].n_reads) { ++s_at; k_at = 0; }
+            S = &segs[s_at];
+            *q = S->reads[k_at];
+            if (S->tids) { const int32_t tid = S->tids[k_at]; q->contig = (tid >= 0 && (size_t)tid < n_tids) ? contig_of_tid[tid] : (int16_t)-1; }
+            if ((size_t)q->block_off + q->n_blocks > S->n_blocks) return RSQ_ERR_INVALID;
+            tile_blocks[i - lo] = S->blocks + q->block_off;
+            ++k_at;
+        }
+        contig = tile_reads[0].contig;
+        for (i = lo; i < hi; ++i) if (tile_reads[i - lo].contig == contig && tile_reads[i - lo].pos < bp) bp = tile_reads[i - lo].pos;
         T->base_pos = bp; T->block_base = (uint32_t)n_xb; T->out_block_base = (uint32_t)out_blocks; T->exc_base = (uint32_t)n_exc;
         T->contig = contig; T->reserved = 0; T->reserved2 = 0;
         for (i = lo; i < hi; ++i) {
-            const rsq_read* r = &reads[i];
-            const rsq_block* rb = blocks + r->block_off;
+            const rsq_read* r = &tile_reads[i - lo];
+            const rsq_block* rb = tile_blocks[i - lo];
             rsq_read16* p = &R[i];
             int ok, implicit = 0;
             const long long dpos = (long long)r->pos - bp, dm = (long long)r->mpos - r->pos;
-            if ((size_t)r->block_off + r->n_blocks > n_blocks) return RSQ_ERR_INVALID;
             ok = r->contig == contig && dpos >= 0 && dpos <= 65535 && dm >= -32768 && dm <= 32767 && r->isize >= -32768 && r->isize <= 32767 &&
                  r->l_qseq >= 0 && r->l_qseq <= 65535 && r->nm >= 0 && r->nm <= 65535 && r->n_blocks <= 255 && !(r->aux & RSQ_AUX_IMPLICIT_BLOCK);
             if (ok) {
@@ -590,5 +619,13 @@ static inline int rsq_pack_compact(const rsq_read* reads, size_t n_reads, const 
     H->total_bytes = off;
     *bytes_out = off;
     return RSQ_OK;
+}
+
+/* The same for a batch that lies in one piece (block_off relative to `blocks`). */
+static inline int rsq_pack_compact(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks, void* out, size_t cap,
+                                   uint32_t* scratch, size_t* bytes_out) {
+    rsq_segment one;
+    one.reads = reads; one.tids = NULL; one.n_reads = n_reads; one.blocks = blocks; one.n_blocks = n_blocks;
+    return rsq_pack_compact_segments(&one, 1, NULL, 0, out, cap, scratch, bytes_out);
 }
 #endif /* RSQ_B200_H */

@@ -101,6 +101,12 @@ public:
     static RunSummary summarise(const DecodeOptions& opt, int n_refs, const rsq_read* r, const int32_t* tids, size_t n);
     bool observe_run(const RunSummary& s);
     const DecodeOptions& options() const { return opt_; }
+    // bind_contig as a table over the BAM reference ids (for rsq_pack_compact_segments, which binds while it packs)
+    std::vector<int16_t> contig_of_tid() const {
+        std::vector<int16_t> t(tid_to_contig_.size());
+        for (size_t k = 0; k < t.size(); ++k) { rsq_read r{}; bind_contig(r, (int32_t)k); t[k] = r.contig; }
+        return t;
+    }
 
     bool saw_unsorted() const { return warned_unsorted_; }
     int read_length() const { return read_length_; }

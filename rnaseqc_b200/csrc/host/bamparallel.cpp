@@ -546,4 +546,100 @@ bool ParallelBamDecoder::next_batch(Decoder& dec, size_t max_records, std::vecto
     return !reads.empty();
 }
 
+// next_batch without the copy (bamparallel.h).  Same order of Decoder calls as next_batch: the stream state cannot tell the two apart.
+bool ParallelBamDecoder::next_batch_segments(Decoder& dec, size_t max_records, Segments& out) {
+    out.segs.clear(); out.jobs.clear(); out.loose_reads.clear(); out.loose_blocks.clear(); out.loose.clear();
+    out.n_reads = 0; out.n_blocks = 0;
+    start(dec.options());
+    auto loose_piece = [&]() -> Segments::Loose& {          // the copied piece at the end of the batch so far (a new one if a job piece is last)
+        if (out.loose.empty() || out.loose.back().seg + 1 != out.segs.size()) {
+            out.loose.push_back(Segments::Loose{out.segs.size(), out.loose_reads.size(), 0, out.loose_blocks.size(), 0});
+            out.segs.push_back(rsq_segment{nullptr, nullptr, 0, nullptr, 0});
+        }
+        return out.loose.back();
+    };
+    while (out.n_reads < max_records) {
+        std::shared_ptr<Job> job = cur_;
+        if (!job) {
+            std::unique_lock<std::mutex> lk(mu_);
+            auto& q = jobs_;
+            const auto t_wait = clk::now();
+            cv_consumer_.wait(lk, [&] { return stop_ || (!q.empty() && q.front()->state == ST_CONVERTED) || (reader_done_ && q.empty()); });
+            t_consumer_wait_ += since(t_wait);
+            if (stop_ || q.empty()) break;
+            job = q.front();
+            q.pop_front();
+            lk.unlock();
+            cv_reader_.notify_one();
+            cv_work_.notify_all();
+            if (!job->error.empty()) throw HostError(job->error_code, job->error);
+            cur_ = job;
+            cur_read_ = job->first_read;
+            if (job->has_head) {                 // the record that straddles the previous job's end comes first
+                Segments::Loose& L = loose_piece();
+                rsq_read r = job->head_read;
+                r.block_off = (uint32_t)(out.loose_blocks.size() - L.block0);
+                out.loose_blocks.insert(out.loose_blocks.end(), job->head_blocks.begin(), job->head_blocks.end());
+                dec.bind_contig(r, job->head_tid);
+                out.loose_reads.push_back(r);
+                dec.observe(out.loose_reads.back(), job->head_tid);
+                L.n += 1; L.nb += job->head_blocks.size();
+                out.n_reads += 1; out.n_blocks += job->head_blocks.size();
+                job->has_head = false;
+                if (out.n_reads >= max_records) continue;
+            }
+        }
+        const size_t n = std::min(job->reads.size() - cur_read_, max_records - out.n_reads);
+        const auto t_copy = clk::now();
+        bool by_reference = false;
+        if (n) {
+            const rsq_read* first = job->reads.data() + cur_read_;
+            const uint32_t b_lo = first->block_off;
+            const uint32_t b_hi = first[n - 1].block_off + first[n - 1].n_blocks;
+            if (job->has_summary && cur_read_ == 0 && n == job->reads.size() && dec.observe_run(job->summary)) {
+                ++n_runs_summarised_;
+                out.segs.push_back(rsq_segment{first, job->tids.data(), n, job->rblocks.data(), job->rblocks.size()});
+                out.jobs.push_back(job);
+                by_reference = true;
+            } else {
+                Segments::Loose& L = loose_piece();
+                const size_t at = out.loose_reads.size();
+                const uint32_t delta = (uint32_t)(out.loose_blocks.size() - L.block0) - b_lo;
+                out.loose_reads.insert(out.loose_reads.end(), first, first + n);
+                out.loose_blocks.insert(out.loose_blocks.end(), job->rblocks.data() + b_lo, job->rblocks.data() + b_hi);
+                const int32_t* tids = job->tids.data() + cur_read_;
+                rsq_read* o = out.loose_reads.data() + at;
+                for (size_t k = 0; k < n; ++k) {
+                    o[k].block_off += delta;
+                    dec.bind_contig(o[k], tids[k]);
+                    dec.observe(o[k], tids[k]);
+                }
+                L.n += n; L.nb += b_hi - b_lo;
+            }
+            out.n_reads += n; out.n_blocks += b_hi - b_lo;
+        }
+        t_consumer_ += since(t_copy);
+        cur_read_ += n;
+        if (cur_read_ >= job->reads.size()) {
+            compressed_consumed_ += cur_->comp_bytes;
+            if (!by_reference) { std::lock_guard<std::mutex> lk(mu_); pool_.push_back(cur_); }   // a referenced job goes back in recycle()
+            cur_.reset(); cur_read_ = 0;
+        }
+    }
+    for (const Segments::Loose& L : out.loose) {          // the copied pieces have stopped moving
+        rsq_segment& S = out.segs[L.seg];
+        S.reads = out.loose_reads.data() + L.read0; S.tids = nullptr; S.n_reads = L.n;
+        S.blocks = out.loose_blocks.data() + L.block0; S.n_blocks = L.nb;
+    }
+    return out.n_reads != 0;
+}
+
+void ParallelBamDecoder::recycle(Segments& s) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& j : s.jobs) pool_.push_back(std::move(j));
+    }
+    s.jobs.clear(); s.segs.clear();
+}
+
 }  // namespace rsqh

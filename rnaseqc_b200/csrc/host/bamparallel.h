@@ -17,10 +17,12 @@
 #include <vector>
 
 #include "alnreader.h"
+#include "rsq_b200.h"
 
 namespace rsqh {
 
 class ParallelBamDecoder {
+    struct Job;                        // one ~4 MB piece of the decompressed stream (bamparallel.cpp)
 public:
     // n_threads worker threads (>= 1) besides one file-reader thread; throws HostError(10) if the file cannot be opened
     ParallelBamDecoder(const std::string& path, int n_threads);
@@ -34,6 +36,21 @@ public:
     // Appends up to max_records converted records (with their blocks) to the cleared vectors, in file order, running
     // dec.observe() on each.  Returns false once the stream is exhausted and nothing was appended.
     bool next_batch(Decoder& dec, size_t max_records, std::vector<rsq_read>& reads, std::vector<rsq_block>& blocks);
+    // The same stream as a list of pieces that stay where the workers wrote them (rsq_segment, include/rsq_b200.h): a job that goes
+    // through its digest costs the caller's thread O(1) — no copy; records that need Decoder::observe one by one (first job, contig
+    // changes, jobs cut by a batch boundary, the records that straddle two jobs) are copied, bound and observed into the batch's own
+    // small arrays.  The jobs stay alive until recycle(); the contig ids of job pieces are bound by the packer (tids).
+    struct Segments {
+        std::vector<rsq_segment> segs;
+        size_t n_reads = 0, n_blocks = 0;
+        std::vector<std::shared_ptr<Job>> jobs;
+        std::vector<rsq_read> loose_reads;            // the copied pieces, in stream order
+        std::vector<rsq_block> loose_blocks;
+        struct Loose { size_t seg, read0, n, block0, nb; };
+        std::vector<Loose> loose;
+    };
+    bool next_batch_segments(Decoder& dec, size_t max_records, Segments& out);
+    void recycle(Segments& s);
     // compressed bytes of the jobs handed out so far / size of the file: lets a caller extrapolate the record count
     uint64_t compressed_consumed() const { return compressed_consumed_; }
     uint64_t file_bytes() const { return file_bytes_; }
@@ -43,7 +60,6 @@ public:
     static unsigned long long last_runs_summarised();          // jobs whose records went through Decoder::observe_run
 
 private:
-    struct Job;                        // one ~4 MB piece of the decompressed stream (bamparallel.cpp)
     void reader_loop();
     void worker_loop();
     void speculate(Job& j) const;                              // inflate stage: guessed record chain, converted

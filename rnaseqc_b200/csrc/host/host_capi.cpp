@@ -202,6 +202,37 @@ void rsqh_set_legacy(int on) { g_legacy = on != 0; }
 void rsqh_set_fasta(const char* path) { g_fasta = path ? path : ""; }
 const rsq_reference* rsqh_reference_view(void* h) { Handle* H = static_cast<Handle*>(h); return H->ref.open ? &H->ref_view : nullptr; }
 
+// Test hook for rsq_pack_compact_segments: the batch cut at the given record indices into pieces with their own (rebased) block arrays;
+// with `use_tids` the pieces carry the contig as a reference id (identity table) and a scrambled contig field, as the ingest workers' do.
+int rsqh_pack_compact_split(const rsq_read* reads, size_t n_reads, const rsq_block* blocks, size_t n_blocks, const size_t* cuts, size_t n_cuts,
+                            int use_tids, void* out, size_t cap, size_t* bytes_out) {
+    std::vector<std::vector<rsq_read>> pr;
+    std::vector<std::vector<rsq_block>> pb;
+    std::vector<std::vector<int32_t>> pt;
+    std::vector<rsq_segment> segs;
+    int16_t max_contig = 0;
+    for (size_t i = 0; i < n_reads; ++i) max_contig = std::max(max_contig, reads[i].contig);
+    std::vector<int16_t> table((size_t)max_contig + 1);
+    for (size_t k = 0; k < table.size(); ++k) table[k] = (int16_t)k;
+    size_t lo = 0;
+    for (size_t c = 0; c <= n_cuts; ++c) {
+        const size_t hi = c < n_cuts ? cuts[c] : n_reads;
+        if (hi < lo || hi > n_reads) return RSQ_ERR_INVALID;
+        pr.emplace_back(reads + lo, reads + hi); pb.emplace_back(); pt.emplace_back();
+        for (rsq_read& r : pr.back()) {
+            if ((size_t)r.block_off + r.n_blocks > n_blocks) return RSQ_ERR_INVALID;
+            const uint32_t at = (uint32_t)pb.back().size();
+            pb.back().insert(pb.back().end(), blocks + r.block_off, blocks + r.block_off + r.n_blocks);
+            r.block_off = at;
+            if (use_tids) { pt.back().push_back(r.contig); r.contig = (int16_t)0x5a5a; }      // -1 stays -1: out of the table's range
+        }
+        lo = hi;
+    }
+    for (size_t k = 0; k < pr.size(); ++k)
+        segs.push_back(rsq_segment{pr[k].data(), use_tids ? pt[k].data() : nullptr, pr[k].size(), pb[k].data(), pb[k].size()});
+    std::vector<uint32_t> scratch(131072);
+    return rsq_pack_compact_segments(segs.data(), segs.size(), table.data(), table.size(), out, cap, scratch.data(), bytes_out);
+}
 uint64_t rsqh_hash_qname(const char* s, size_t n) { return hash_qname(s, n); }
 // the ingest workers' whole-buffer DEFLATE decoder (fastinflate.h): 1 = inflated exactly out_len bytes, 0 = refused (callers fall back to zlib)
 int rsqh_fast_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) { return rsqh::fast_inflate(in, in_len, out, out_len) ? 1 : 0; }

@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <filesystem>
 #include <future>
 #include <iostream>
@@ -522,6 +523,102 @@ int run_sample(const Backend& be, CliOptions& opt) {
         };
         int cur = 0;
         bool more = true;
+        // One GPU, BAM input, 16-byte wire format: the batches are not copied together at all.  The decoder hands every batch over
+        // as a list of pieces that stay in the ingest workers' buffers (bamparallel.h: next_batch_segments) and the packers read
+        // them there, binding the contig ids on the way — this thread only walks over job digests, and up to three packers (one
+        // per page-locked slot) work at a time.  A batch that does not suit the format is copied together by its packer and goes
+        // down the usual chain of formats.
+        const bool by_segments = pbam && n_lanes == 1 && opt.packed_submit && opt.compact_submit && be.submit_compact && !getenv("RSQ_INGEST_COPY_BATCHES");
+        if (by_segments) {
+            struct Piece {
+                std::shared_ptr<ParallelBamDecoder::Segments> segs;
+                Staged st;
+            };
+            std::deque<Piece> queue;                       // staged batches, oldest first
+            size_t by_format[3] = {0, 0, 0};
+            const std::vector<int16_t> contig_of_tid = decoder.contig_of_tid();
+            Lane& L = lanes[0];
+            auto submit_front = [&]() {
+                const int how = queue.front().st.how.get();          // the packer writes into this element: wait before it moves
+                Piece pc = std::move(queue.front());
+                queue.pop_front();
+                pbam->recycle(*pc.segs);
+                unsigned char* buf = (unsigned char*)L.pinned[pc.st.slot];
+                int r2;
+                if (how == 2) { r2 = be.submit_compact(L.ctx, buf, pc.st.compact_bytes); L.wire_bytes += pc.st.compact_bytes; }
+                else if (how == 1) { r2 = be.submit_packed(L.ctx, (const rsq_read_packed*)buf, pc.st.n_reads, (const rsq_block*)(buf + pc.st.blocks_off), pc.st.n_packed_blocks); L.wire_bytes += 32 * pc.st.n_reads + 8 * pc.st.n_packed_blocks; }
+                else { r2 = be.submit(L.ctx, (const rsq_read*)buf, pc.st.n_reads, (const rsq_block*)(buf + pc.st.blocks_off), pc.st.n_blocks); L.wire_bytes += 48 * pc.st.n_reads + 8 * pc.st.n_blocks; }
+                L.in_flight[pc.st.slot] = true;
+                L.records += pc.st.n_reads; ++L.batches;
+                ++by_format[how];
+                if (r2 != RSQ_OK) throw HostError(-1, std::string("rsq_submit failed: ") + be.last_error(L.ctx));
+            };
+            try {
+                while (more) {
+                    auto segs = std::make_shared<ParallelBamDecoder::Segments>();
+                    if (!pbam->next_batch_segments(decoder, opt.batch_records, *segs)) break;
+                    more = segs->n_reads == opt.batch_records;
+                    while (queue.size() >= (size_t)Lane::kSlots) submit_front();     // its slot comes free
+                    const size_t n = segs->n_reads, nb = segs->n_blocks;
+                    const size_t blocks_off = (48 * n + 15) & ~(size_t)15;
+                    const size_t need = std::max(rsq_compact_bound(n, nb), blocks_off + 8 * std::max<size_t>(nb, 1));
+                    queue.emplace_back();
+                    Piece& pc = queue.back();
+                    pc.segs = segs;
+                    pc.st.lane = 0; pc.st.slot = L.acquire(need); pc.st.n_reads = n; pc.st.n_blocks = nb; pc.st.blocks_off = blocks_off;
+                    unsigned char* dst = (unsigned char*)L.pinned[pc.st.slot];
+                    const size_t cap = L.cap[pc.st.slot];
+                    const ParallelBamDecoder::Segments* sg = segs.get();
+                    const int16_t* c_of_t = contig_of_tid.data();
+                    const size_t n_tids = contig_of_tid.size();
+                    const bool try_packed = opt.packed_submit && be.submit_packed;
+                    size_t* compact_bytes = &pc.st.compact_bytes;      // (deque: elements stay where they are when others come and go)
+                    size_t* n_packed = &pc.st.n_packed_blocks;
+                    pc.st.how = std::async(std::launch::async, [=]() -> int {
+                        std::vector<uint32_t> scratch(131072);
+                        if (rsq_pack_compact_segments(sg->segs.data(), sg->segs.size(), c_of_t, n_tids, dst, cap, scratch.data(), compact_bytes) == RSQ_OK) return 2;
+                        // not this batch: copy it together (contig ids bound) and try the other formats
+                        std::vector<rsq_read> flat;
+                        std::vector<rsq_block> fblocks;
+                        flat.reserve(n); fblocks.reserve(nb);
+                        for (const rsq_segment& S : sg->segs) {
+                            // the blocks a piece's records point at (a piece of a job: all of the job's)
+                            const size_t base = fblocks.size();
+                            fblocks.insert(fblocks.end(), S.blocks, S.blocks + S.n_blocks);
+                            for (size_t k = 0; k < S.n_reads; ++k) {
+                                rsq_read r = S.reads[k];
+                                if (S.tids) { const int32_t tid = S.tids[k]; r.contig = (tid >= 0 && (size_t)tid < n_tids) ? c_of_t[tid] : (int16_t)-1; }
+                                r.block_off += (uint32_t)base;
+                                flat.push_back(r);
+                            }
+                        }
+                        if (try_packed && blocks_off + 8 * fblocks.size() <= cap &&
+                            rsq_pack_records(flat.data(), n, fblocks.data(), fblocks.size(), (rsq_read_packed*)dst, (rsq_block*)(dst + blocks_off), n_packed) == RSQ_OK) return 1;
+                        // plain records: the blocks in record order (what the batch's block count was sized for)
+                        rsq_read* out = (rsq_read*)dst;
+                        rsq_block* ob = (rsq_block*)(dst + blocks_off);
+                        size_t w = 0;
+                        for (size_t i = 0; i < n; ++i) {
+                            out[i] = flat[i];
+                            out[i].block_off = (uint32_t)w;
+                            for (unsigned b = 0; b < flat[i].n_blocks; ++b) ob[w++] = fblocks[flat[i].block_off + b];
+                        }
+                        return 0;
+                    });
+                    if (opt.verbosity > 1)
+                        std::cout << "Time elapsed: " << std::chrono::duration<double>(clk::now() - t1).count()
+                                  << "; Alignments processed: " << decoder.alignment_count() << std::endl;
+                }
+                while (!queue.empty()) submit_front();
+                if (opt.verbosity)
+                    std::cout << "Batches read in place from the ingest workers' buffers: " << by_format[2] << " in the 16-byte wire format, "
+                              << by_format[1] << " in the 32-byte one, " << by_format[0] << " as plain records" << std::endl;
+            } catch (...) {
+                for (Piece& pc : queue) if (pc.st.how.valid()) pc.st.how.wait();   // the packers still read the jobs and write the slots
+                throw;
+            }
+            more = false;
+        }
         try {
         while (more) {
             std::vector<rsq_read>& reads = reads_buf[cur];

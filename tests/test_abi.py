@@ -203,3 +203,43 @@ def test_pinned_result_buffers_match_plain_ones(libs, tmp_path):
     assert again.gene_reads.ctypes.data == pinned.gene_reads.ctypes.data      # the same page-locked memory
     assert plain.gene_reads.sum() > 0
     ctx.close()
+
+
+def test_segmented_packer_writes_the_same_bytes_however_the_batch_is_cut(libs):
+    """rsq_pack_compact_segments (include/rsq_b200.h): the ingest hands a batch over as pieces lying in its workers' buffers, each
+    with its own block array and the contig still a BAM reference id; the compact batch must not depend on the cuts (rsq_pack_compact
+    is the one-piece case), including empty pieces, pieces of one record, cuts inside a 32-record tile and records that travel as
+    exceptions."""
+    import ctypes as C
+    import numpy as np
+    from rnaseqc_b200 import synth
+    api = libs["api"]
+    H = api.host_lib()
+    H.rsqh_pack_compact_split.restype = C.c_int
+    H.rsqh_pack_compact_split.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    sa = synth.make_annotation(seed=31, n_genes=120, contig_names=["chr1", "chr2"], contig_lens=[2_000_000, 1_000_000])
+    sr = synth.simulate_reads(sa, 40000, seed=32)
+    rb, bb = synth.pack(sr, [0, 1])
+    reads, blocks = synth.to_numpy(rb, bb)
+    reads = reads.copy()
+    rng = np.random.default_rng(9)
+    odd = rng.choice(len(reads), 300, replace=False)              # records the 16-byte slot cannot express: exceptions
+    reads["isize"][odd[:100]] = 70000
+    reads["mpos"][odd[100:200]] = reads["pos"][odd[100:200]] + 50000
+    reads["contig"][odd[200:]] = -1
+    want = api.pack_compact(reads, blocks)
+    assert want is not None
+    cap = api.compact_bound(len(reads), len(blocks))
+    for trial in range(12):
+        k = int(rng.integers(0, 40))
+        cuts = np.sort(rng.integers(0, len(reads) + 1, k)).astype(np.uint64)
+        if trial == 0:
+            cuts = np.array([0, 0, 1, 2, 31, 32, 33, 33, len(reads), len(reads)], np.uint64)
+        raw = np.zeros(cap + 16, np.uint8)
+        a = (-raw.ctypes.data) % 16
+        out = raw[a:a + cap]
+        w = C.c_size_t(0)
+        rc = H.rsqh_pack_compact_split(reads.ctypes.data, len(reads), blocks.ctypes.data, len(blocks), cuts.ctypes.data, len(cuts), trial % 2,
+                                       out.ctypes.data, cap, C.byref(w))
+        assert rc == 0, (trial, rc)
+        assert w.value == want.nbytes and np.array_equal(out[:w.value], want), trial
