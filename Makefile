@@ -79,6 +79,14 @@ $(OBJDIR)/inflate_bench: tools/inflate_bench.cpp rnaseqc_b200/csrc/host/fastinfl
 $(OBJDIR)/decode_bench: tools/decode_bench.cpp $(HOST_OBJS)
 	$(CXX) $(CXXFLAGS) -o $@ tools/decode_bench.cpp $(filter-out $(OBJDIR)/host/report.o $(OBJDIR)/host/pipeline.o,$(HOST_OBJS)) -lz -lpthread
 
+# the host side (CLI over the CPU oracle backend) under AddressSanitizer + UBSan: build/rnaseqc_asan — run it over BAMs by hand or put it
+# in the place of oracle/_build/rnaseqc_oracle in tools/ingest_mutation_fuzz.py (ASAN_OPTIONS=detect_leaks=0:exitcode=99 RSQ_FULL_TEARDOWN=1)
+asan:
+	@mkdir -p $(OBJDIR)/asan
+	for f in $(HOST_SRCS:.cpp=) cli_main; do $(CXX) -std=c++17 -O1 -g -fsanitize=address,undefined -fno-omit-frame-pointer -Wno-sign-compare -Iinclude -Irnaseqc_b200/csrc/host -c rnaseqc_b200/csrc/host/$$f.cpp -o $(OBJDIR)/asan/$$f.o || exit 1; done
+	$(CXX) -std=c++17 -O1 -g -fsanitize=address,undefined -Wno-sign-compare -Iinclude -c oracle/rsq_oracle.cpp -o $(OBJDIR)/asan/oracle.o
+	$(CXX) -fsanitize=address,undefined -o $(OBJDIR)/rnaseqc_asan $(OBJDIR)/asan/*.o -lz -lpthread
+
 clean:
 	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) $(ODIR)
-.PHONY: all oracle ref tools clean
+.PHONY: all oracle ref tools asan clean
